@@ -1,0 +1,121 @@
+/* nova_b200 -- C ABI of the B200-native Nova prover hot path.
+ *
+ * This is the drop-in boundary: the entry points a `provider/b200.rs` module in
+ * nova-snark would bind through a `nova-b200-sys` crate, exactly as `provider/blitzar.rs:7-40`
+ * binds the blitzar library today.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions (mirroring the reference's call sites):
+ *   - field element  = 32 B = 4 x u64 little-endian limbs, Montgomery form, R = 2^256
+ *                      (halo2curves 0.9.0 in-memory layout; blitzar.rs:10-16 precedent)
+ *   - affine point   = {x, y} 64 B; identity = all-zero coordinates
+ *   - group result   = Jacobian {x, y, z} 96 B (x_aff = x/z^2, y_aff = y/z^3); identity has z = 0
+ *   - inputs are borrowed and never mutated; outputs are caller-owned; the library keeps no
+ *     host pointer after return (src/provider/traits.rs:77-117 take slices, return by value)
+ *   - every function returns 0 on success, a B200_E_* code otherwise; it never throws and never
+ *     calls back.  b200_last_error() gives a thread-local message.  The reference's MSM/commit
+ *     are infallible (`assert!` on length mismatch, msm.rs:226, pedersen.rs:264): the Rust shim
+ *     panics on non-zero for those and maps to NovaError::GpuError (errors.rs:84-86) for the
+ *     Result-returning sites (r1cs/mod.rs:411-413).
+ *   - all entry points are thread-safe and re-entrant: the reference calls commits concurrently
+ *     from rayon workers (r1cs/mod.rs:509-512, ppsnark.rs:1155-1158, hyperkzg.rs:1062-1065).
+ *   - `*_dev` variants take DEVICE pointers (on the key's device) and a cudaStream_t passed as
+ *     void* (NULL = the library's stream); they are asynchronous and are what a device-resident
+ *     pipeline (fused Z1+Z2 -> SpMV -> T -> MSM(T)) chains together.
+ *   - THERE IS NO CPU FALLBACK: if no CUDA device is usable every call returns B200_E_CUDA.
+ */
+#ifndef NOVA_B200_H
+#define NOVA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* field ids (moduli: bn256_grumpkin.rs:39-40,84-85; pasta.rs:37-38,45-46) */
+enum { B200_FIELD_BN254_FR = 0, B200_FIELD_BN254_FQ = 1, B200_FIELD_PALLAS_FP = 2, B200_FIELD_PALLAS_FQ = 3 };
+/* curve ids: (base field, scalar field) = G1:(FQ,FR) Grumpkin:(FR,FQ) Pallas:(FP,FQ) Vesta:(FQ,FP) */
+enum { B200_CURVE_BN254_G1 = 0, B200_CURVE_GRUMPKIN = 1, B200_CURVE_PALLAS = 2, B200_CURVE_VESTA = 3 };
+
+enum {
+  B200_OK = 0,
+  B200_E_ARG = 1,      /* bad argument (null pointer, unknown id, length mismatch: msm.rs:226) */
+  B200_E_CUDA = 2,     /* CUDA runtime failure or no device (maps to NovaError::GpuError) */
+  B200_E_HANDLE = 3,   /* unknown / released handle */
+  B200_E_NOMEM = 4,    /* device memory exhausted */
+  B200_E_RANGE = 5     /* slice outside the registered key (pedersen.rs:264 assert) */
+};
+
+/* ---- library / device ------------------------------------------------------------------ */
+int b200_init(int device);                 /* idempotent; selects the device for this process */
+int b200_device_count(int* count);
+const char* b200_last_error(void);         /* thread-local */
+const char* b200_version(void);
+
+/* pinned host buffers + raw device buffers, so a host language can stage witnesses for DMA and
+ * keep folded vectors (W, E, T) resident between calls */
+int b200_host_alloc(size_t bytes, void** ptr);
+int b200_host_free(void* ptr);
+int b200_dev_alloc(size_t bytes, void** dptr);
+int b200_dev_free(void* dptr);
+int b200_memcpy_h2d(void* dptr, const void* hptr, size_t bytes);
+int b200_memcpy_d2h(void* hptr, const void* dptr, size_t bytes);
+int b200_sync(void);
+
+/* ---- commitment keys -------------------------------------------------------------------
+ * Replaces holding `CommitmentKey{ck: Vec<Affine>, h}` (pedersen.rs:32-38, hyperkzg.rs:76-84) on
+ * the host only: the bases are uploaded ONCE, expanded into the 2^(c*t)*P window tables, and stay
+ * resident.  window_bits = 0 picks c from n.  Keys are immutable after registration. */
+int b200_ck_register(int curve_id, const void* bases_affine_mont, size_t n, int window_bits,
+                     uint64_t* ck_handle);
+int b200_ck_release(uint64_t ck_handle);
+int b200_ck_len(uint64_t ck_handle, size_t* n, int* window_bits, int* num_tables);
+
+/* ---- MSM  (DlogGroupExt, src/provider/traits.rs:77-117; msm.rs:225) ---------------------- */
+/* out = sum_i scalars[i] * ck[base_offset + i],  i < n.   n == 0 -> identity (msm.rs:228-230).
+ * Replaces DlogGroupExt::vartime_multiscalar_mul(scalars, &ck.ck[..n]) (pedersen.rs:263-270,
+ * hyperkzg.rs:584-591). */
+int b200_msm(uint64_t ck_handle, size_t base_offset, const void* scalars_mont, size_t n,
+             void* out_jacobian_mont);
+int b200_msm_dev(uint64_t ck_handle, size_t base_offset, const void* d_scalars_mont, size_t n,
+                 void* d_out_jacobian_mont, void* stream);
+/* k MSMs over prefixes of the same key: vector j uses ck[..lens[j]] (traits.rs:82-90,
+ * blitzar.rs:23-40, hyperkzg.rs:594-612 batch_commit).  out = k x 96 B. */
+int b200_msm_batch(uint64_t ck_handle, const void* const* scalars_mont, const size_t* lens,
+                   size_t k, void* out_jacobian_mont);
+/* integer scalars (msm.rs:469-503 msm_small / msm_small_with_max_num_bits): elem_bytes in
+ * {1,2,4,8} little-endian unsigned; max_bits = 0 computes it from the data (msm.rs:473). */
+int b200_msm_small(uint64_t ck_handle, size_t base_offset, const void* scalars_uint,
+                   int elem_bytes, size_t n, int max_bits, void* out_jacobian_mont);
+/* sum of ck[idx[j]] (msm.rs:689-708 batch_add; pedersen.rs commit_sparse_binary) */
+int b200_msm_indices(uint64_t ck_handle, const uint64_t* idx, size_t m, void* out_jacobian_mont);
+/* one-shot MSM over bases that are not a registered key (pedersen.rs:418-420,492,505) */
+int b200_msm_adhoc(int curve_id, const void* bases_affine_mont, const void* scalars_mont, size_t n,
+                   void* out_jacobian_mont);
+
+/* ---- R1CS witness field arithmetic (host-pointer forms) ---------------------------------- */
+/* t[i] = az[i]*bz[i] - u*cz[i] - e1[i] (- e2[i] if e2 != NULL)   (r1cs/mod.rs:614-620,650-657) */
+int b200_cross_term(int field_id, const void* az, const void* bz, const void* cz, const void* e1,
+                    const void* e2_or_null, const void* u, size_t n, void* t);
+/* out[i] = a[i] + r*b[i]   (RelaxedR1CSWitness::fold, r1cs/mod.rs:1044-1073) */
+int b200_axpy(int field_id, const void* a, const void* b, const void* r, size_t n, void* out);
+/* out[i] = a[i] + b[i]     (Z = Z1 + Z2, r1cs/mod.rs:589-609) */
+int b200_vec_add(int field_id, const void* a, const void* b, size_t n, void* out);
+/* z[i] += r*(z[i + n/2] - z[i]) for i < n/2; caller truncates to n/2
+ * (MultilinearPolynomial::bind_poly_var_top, spartan/polys/multilinear.rs:65-84) */
+int b200_bind_top(int field_id, void* z_inout, size_t n, const void* r);
+
+/* device-pointer forms of the same (asynchronous on `stream`) */
+int b200_cross_term_dev(int field_id, const void* az, const void* bz, const void* cz,
+                        const void* e1, const void* e2_or_null, const void* u, size_t n, void* t,
+                        void* stream);
+int b200_axpy_dev(int field_id, const void* a, const void* b, const void* r, size_t n, void* out,
+                  void* stream);
+int b200_vec_add_dev(int field_id, const void* a, const void* b, size_t n, void* out, void* stream);
+int b200_bind_top_dev(int field_id, void* z_inout, size_t n, const void* r, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOVA_B200_H */

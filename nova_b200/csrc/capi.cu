@@ -1,0 +1,682 @@
+// C ABI of nova_b200 (include/nova_b200.h): handles, workspaces, streams, error reporting.
+// Template-free: all kernels are reached through the per-field launcher tables (ops.cuh).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/nova_b200.h"
+#include "msm_kernels.cuh"
+#include "ops.cuh"
+
+using namespace nova;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(e_ == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA,         \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct curve_info {
+  int base_fid, scalar_fid;
+};
+const curve_info CURVES[4] = {
+    {B200_FIELD_BN254_FQ, B200_FIELD_BN254_FR},   // BN254 G1   (bn256_grumpkin.rs:35-41)
+    {B200_FIELD_BN254_FR, B200_FIELD_BN254_FQ},   // Grumpkin   (bn256_grumpkin.rs:80-86)
+    {B200_FIELD_PALLAS_FP, B200_FIELD_PALLAS_FQ}, // Pallas     (pasta.rs:33-39)
+    {B200_FIELD_PALLAS_FQ, B200_FIELD_PALLAS_FP}, // Vesta      (pasta.rs:41-47)
+};
+const int FIELD_BITS[4] = {254, 254, 255, 255};
+
+struct device_state {
+  std::mutex mu;
+  bool ready = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+} g_dev;
+
+int ensure_init() {
+  std::lock_guard<std::mutex> lk(g_dev.mu);
+  if (g_dev.ready) {
+    CU(cudaSetDevice(g_dev.device));
+    return B200_OK;
+  }
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0)
+    return fail(B200_E_CUDA, "no usable CUDA device (%s); nova_b200 has no CPU fallback",
+                e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+  CU(cudaSetDevice(g_dev.device));
+  CU(cudaStreamCreateWithFlags(&g_dev.stream, cudaStreamNonBlocking));
+  g_dev.ready = true;
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// commitment-key context
+// ---------------------------------------------------------------------------------------------
+struct workspace {
+  size_t cap_n = 0;  // scalars the buffers are sized for
+  void* scalars = nullptr;
+  int32_t* digits = nullptr;
+  uint32_t *counts = nullptr, *start = nullptr, *cursor = nullptr, *blocksums = nullptr;
+  uint64_t* entries = nullptr;
+  void *buckets = nullptr, *parts = nullptr, *rparts = nullptr, *sumscratch = nullptr;
+  uint32_t* pkeys = nullptr;
+  uint32_t* heavy = nullptr;
+  uint32_t heavy_cap = 0;
+  void* d_out = nullptr;   // result slots (device)
+  void* h_out = nullptr;   // pinned mirror
+  size_t out_slots = 0;
+  uint32_t* idx32 = nullptr;
+  size_t idx_cap = 0;
+  void release() {
+    void* ptrs[] = {scalars, digits, counts, start, cursor, blocksums, entries, buckets,
+                    parts, rparts, sumscratch, pkeys, heavy, d_out, idx32};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    if (h_out) cudaFreeHost(h_out);
+    *this = workspace();
+  }
+};
+
+struct ck_ctx {
+  std::mutex mu;
+  int curve = 0;
+  size_t n = 0;
+  int c = 0, W = 0, F = 0, G = 0;
+  uint32_t B = 0;
+  int m = 4;
+  void* tables = nullptr;  // [F][n] affine
+  workspace ws;
+  ~ck_ctx() {
+    if (tables) cudaFree(tables);
+    ws.release();
+  }
+};
+
+std::mutex g_handles_mu;
+std::map<uint64_t, std::shared_ptr<ck_ctx>> g_handles;
+uint64_t g_next_handle = 1;
+
+std::shared_ptr<ck_ctx> get_ck(uint64_t h) {
+  std::lock_guard<std::mutex> lk(g_handles_mu);
+  auto it = g_handles.find(h);
+  return it == g_handles.end() ? nullptr : it->second;
+}
+
+constexpr size_t XYZZ_BYTES = 128;
+constexpr int SUM_THREADS = 148 * 128;
+constexpr int L_MIN = 32;
+// accumulate threads are sized to ~3 full waves of 148 SMs x 16 warps x 32 lanes
+constexpr size_t ACC_THREADS = (size_t)148 * 16 * 32 * 3;
+constexpr uint32_t HEAVY_PARTS = 96;  // buckets spanning more segments than this get a block
+
+int segment_len(size_t entries) {
+  size_t L = (entries + ACC_THREADS - 1) / ACC_THREADS;
+  return (int)(L < L_MIN ? L_MIN : L);
+}
+
+int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
+  workspace& w = ck.ws;
+  if (out_slots > w.out_slots) {
+    if (w.d_out) cudaFree(w.d_out);
+    if (w.h_out) cudaFreeHost(w.h_out);
+    w.d_out = w.h_out = nullptr;
+    CU(cudaMalloc(&w.d_out, out_slots * 96));
+    CU(cudaMallocHost(&w.h_out, out_slots * 96));
+    w.out_slots = out_slots;
+  }
+  if (n <= w.cap_n) return B200_OK;
+  // grow: release the size-dependent buffers and reallocate
+  void** szbufs[] = {&w.scalars, (void**)&w.digits, (void**)&w.entries, &w.parts, (void**)&w.pkeys,
+                     (void**)&w.heavy};
+  for (void** p : szbufs)
+    if (*p) {
+      cudaFree(*p);
+      *p = nullptr;
+    }
+  size_t K = (size_t)ck.G * ck.B;
+  size_t entries = n * (size_t)ck.W;
+  size_t nseg = (entries + L_MIN - 1) / L_MIN;  // upper bound over every L this key will use
+  w.heavy_cap = (uint32_t)(entries / ((size_t)HEAVY_PARTS * L_MIN) + 2);
+  CU(cudaMalloc((void**)&w.heavy, ((size_t)w.heavy_cap + 1) * 4));
+  CU(cudaMalloc(&w.scalars, n * 32));
+  CU(cudaMalloc((void**)&w.digits, entries * sizeof(int32_t)));
+  CU(cudaMalloc((void**)&w.entries, entries * sizeof(uint64_t)));
+  CU(cudaMalloc(&w.parts, 2 * nseg * XYZZ_BYTES));
+  CU(cudaMalloc((void**)&w.pkeys, 2 * nseg * sizeof(uint32_t)));
+  if (!w.counts) {
+    CU(cudaMalloc((void**)&w.counts, K * 4));
+    CU(cudaMalloc((void**)&w.start, (K + 1) * 4));
+    CU(cudaMalloc((void**)&w.cursor, K * 4));
+    CU(cudaMalloc((void**)&w.blocksums, 4096 * 4));
+    CU(cudaMalloc(&w.buckets, K * XYZZ_BYTES));
+    CU(cudaMalloc(&w.rparts, ((size_t)ck.G * (ck.B / ck.m)) * XYZZ_BYTES));
+    CU(cudaMalloc(&w.sumscratch, (size_t)SUM_THREADS * XYZZ_BYTES));
+  }
+  w.cap_n = n;
+  return B200_OK;
+}
+
+msm_plan make_plan(ck_ctx& ck, size_t base_offset, size_t n) {
+  msm_plan p;
+  p.n = n;
+  p.n_ck = ck.n;
+  p.base_offset = base_offset;
+  p.c = ck.c;
+  p.W = ck.W;
+  p.G = ck.G;
+  p.B = ck.B;
+  p.L = segment_len(n * (size_t)ck.W);
+  p.m = ck.m;
+  p.heavy = ck.ws.heavy;
+  p.heavy_min = HEAVY_PARTS * (uint32_t)p.L;
+  p.heavy_cap = ck.ws.heavy_cap;
+  p.digits = ck.ws.digits;
+  p.counts = ck.ws.counts;
+  p.start = ck.ws.start;
+  p.cursor = ck.ws.cursor;
+  p.entries = ck.ws.entries;
+  p.buckets = ck.ws.buckets;
+  p.parts = ck.ws.parts;
+  p.pkeys = ck.ws.pkeys;
+  p.rparts = ck.ws.rparts;
+  p.blocksums = ck.ws.blocksums;
+  return p;
+}
+
+// enqueue one full-width MSM on `s`; scalars and out are device pointers
+int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
+                cudaStream_t s, int small_elem_bytes = 0) {
+  if (n == 0) {  // identity (msm.rs:228-230): z = 0
+    CU(cudaMemsetAsync(d_out, 0, 96, s));
+    return B200_OK;
+  }
+  const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
+  const field_ops* bops = ops_for_field(CURVES[ck.curve].base_fid);
+  msm_plan p = make_plan(ck, base_offset, n);
+  size_t K = (size_t)ck.G * ck.B;
+  CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
+  CU(cudaMemsetAsync(p.heavy, 0, 4, s));
+  if (small_elem_bytes)
+    msm_digits_small(s, d_scalars, small_elem_bytes, p);
+  else
+    sops->digits(s, d_scalars, p);
+  msm_scan(s, p);
+  msm_scatter(s, p);
+  bops->accumulate(s, ck.tables, p);
+  bops->reduce(s, p, d_out);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+int choose_window(size_t n) {
+  int lg = 0;
+  while (((size_t)1 << lg) < n) lg++;
+  int c = lg;
+  if (c < 8) c = 8;
+  if (c > 16) c = 16;
+  return c;
+}
+
+int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n, int window_bits,
+                 bool expand, std::shared_ptr<ck_ctx>& out) {
+  if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
+  if (bases == nullptr || n == 0) return fail(B200_E_ARG, "empty commitment key");
+  if (window_bits != 0 && (window_bits < 2 || window_bits > 24))
+    return fail(B200_E_ARG, "window_bits %d out of range [2,24]", window_bits);
+  auto ck = std::make_shared<ck_ctx>();
+  ck->curve = curve_id;
+  ck->n = n;
+  ck->c = window_bits ? window_bits : choose_window(n);
+  int bits = FIELD_BITS[CURVES[curve_id].scalar_fid];
+  ck->W = (bits + ck->c - 1) / ck->c;
+  ck->F = expand ? ck->W : 1;
+  ck->G = expand ? 1 : ck->W;
+  ck->B = 1u << (ck->c - 1);
+  ck->m = ck->B >= 4 ? 4 : 1;
+  if ((size_t)ck->F * n >= ((size_t)1 << 31))
+    return fail(B200_E_RANGE, "key too large for 31-bit table indices (%zu x %d)", n, ck->F);
+  CU(cudaMalloc(&ck->tables, (size_t)ck->F * n * 64));
+  CU(cudaMemcpyAsync(ck->tables, bases, n * 64,
+                     bases_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                     g_dev.stream));
+  if (ck->F > 1) {
+    const field_ops* bops = ops_for_field(CURVES[curve_id].base_fid);
+    bops->expand_key(g_dev.stream, ck->tables, n, ck->F, ck->c * ck->G);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(g_dev.stream));
+  out = ck;
+  return B200_OK;
+}
+
+template <class Fn>
+int with_field(int field_id, Fn fn) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  const field_ops* ops = ops_for_field(field_id);
+  if (!ops) return fail(B200_E_ARG, "unknown field id %d", field_id);
+  return fn(ops);
+}
+
+// host-pointer wrapper for the streaming field kernels: stage through device scratch
+struct dev_buf {
+  void* p = nullptr;
+  ~dev_buf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    CU(cudaMalloc(&p, bytes ? bytes : 1));
+    return B200_OK;
+  }
+};
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* b200_last_error(void) { return g_err; }
+const char* b200_version(void) { return "nova_b200 0.1 (sm_100a)"; }
+
+int b200_init(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_dev.mu);
+    if (!g_dev.ready) g_dev.device = device;
+  }
+  return ensure_init();
+}
+
+int b200_device_count(int* count) {
+  if (!count) return fail(B200_E_ARG, "null count");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(B200_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  return B200_OK;
+}
+
+int b200_host_alloc(size_t bytes, void** ptr) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaMallocHost(ptr, bytes ? bytes : 1));
+  return B200_OK;
+}
+int b200_host_free(void* ptr) {
+  CU(cudaFreeHost(ptr));
+  return B200_OK;
+}
+int b200_dev_alloc(size_t bytes, void** dptr) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaMalloc(dptr, bytes ? bytes : 1));
+  return B200_OK;
+}
+int b200_dev_free(void* dptr) {
+  CU(cudaFree(dptr));
+  return B200_OK;
+}
+int b200_memcpy_h2d(void* dptr, const void* hptr, size_t bytes) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, g_dev.stream));
+  CU(cudaStreamSynchronize(g_dev.stream));
+  return B200_OK;
+}
+int b200_memcpy_d2h(void* hptr, const void* dptr, size_t bytes) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, g_dev.stream));
+  CU(cudaStreamSynchronize(g_dev.stream));
+  return B200_OK;
+}
+int b200_sync(void) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());
+  return B200_OK;
+}
+
+// ---- keys -------------------------------------------------------------------------------------
+int b200_ck_register(int curve_id, const void* bases, size_t n, int window_bits, uint64_t* handle) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!handle) return fail(B200_E_ARG, "null handle pointer");
+  std::shared_ptr<ck_ctx> ck;
+  rc = register_key(curve_id, bases, false, n, window_bits, true, ck);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_handles_mu);
+  *handle = g_next_handle++;
+  g_handles[*handle] = ck;
+  return B200_OK;
+}
+
+int b200_ck_release(uint64_t handle) {
+  std::shared_ptr<ck_ctx> ck;
+  {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    auto it = g_handles.find(handle);
+    if (it == g_handles.end()) return fail(B200_E_HANDLE, "unknown key handle %llu",
+                                           (unsigned long long)handle);
+    ck = it->second;
+    g_handles.erase(it);
+  }
+  std::lock_guard<std::mutex> lk(ck->mu);  // wait for in-flight calls
+  cudaSetDevice(g_dev.device);
+  return B200_OK;
+}
+
+int b200_ck_len(uint64_t handle, size_t* n, int* window_bits, int* num_tables) {
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (n) *n = ck->n;
+  if (window_bits) *window_bits = ck->c;
+  if (num_tables) *num_tables = ck->F;
+  return B200_OK;
+}
+
+// ---- MSM --------------------------------------------------------------------------------------
+static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t n, void* out) {
+  std::lock_guard<std::mutex> lk(ck.mu);
+  int rc = ensure_workspace(ck, n ? n : 1, 1);
+  if (rc) return rc;
+  cudaStream_t s = g_dev.stream;
+  if (n) CU(cudaMemcpyAsync(ck.ws.scalars, scalars, n * 32, cudaMemcpyHostToDevice, s));
+  rc = enqueue_msm(ck, base_offset, ck.ws.scalars, n, ck.ws.d_out, s);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ck.ws.h_out, ck.ws.d_out, 96, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  memcpy(out, ck.ws.h_out, 96);
+  return B200_OK;
+}
+
+int b200_msm(uint64_t handle, size_t base_offset, const void* scalars, size_t n, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (!out || (n && !scalars)) return fail(B200_E_ARG, "null pointer");
+  if (base_offset + n > ck->n)
+    return fail(B200_E_RANGE, "msm slice [%zu, %zu) exceeds key length %zu", base_offset,
+                base_offset + n, ck->n);
+  return msm_host(*ck, base_offset, scalars, n, out);
+}
+
+int b200_msm_dev(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
+                 void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (!d_out || (n && !d_scalars)) return fail(B200_E_ARG, "null pointer");
+  if (base_offset + n > ck->n)
+    return fail(B200_E_RANGE, "msm slice [%zu, %zu) exceeds key length %zu", base_offset,
+                base_offset + n, ck->n);
+  std::lock_guard<std::mutex> lk(ck->mu);
+  rc = ensure_workspace(*ck, n ? n : 1, 1);
+  if (rc) return rc;
+  return enqueue_msm(*ck, base_offset, d_scalars, n, d_out,
+                     stream ? (cudaStream_t)stream : g_dev.stream);
+}
+
+int b200_msm_batch(uint64_t handle, const void* const* scalars, const size_t* lens, size_t k,
+                   void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (k == 0) return B200_OK;
+  if (!scalars || !lens || !out) return fail(B200_E_ARG, "null pointer");
+  size_t nmax = 1;
+  for (size_t j = 0; j < k; j++) {
+    if (lens[j] > ck->n)
+      return fail(B200_E_RANGE, "batch vector %zu has %zu scalars, key has %zu", j, lens[j], ck->n);
+    if (lens[j] && !scalars[j]) return fail(B200_E_ARG, "null scalar vector %zu", j);
+    if (lens[j] > nmax) nmax = lens[j];
+  }
+  std::lock_guard<std::mutex> lk(ck->mu);
+  rc = ensure_workspace(*ck, nmax, k);
+  if (rc) return rc;
+  cudaStream_t s = g_dev.stream;
+  for (size_t j = 0; j < k; j++) {
+    if (lens[j])
+      CU(cudaMemcpyAsync(ck->ws.scalars, scalars[j], lens[j] * 32, cudaMemcpyHostToDevice, s));
+    rc = enqueue_msm(*ck, 0, ck->ws.scalars, lens[j], (char*)ck->ws.d_out + 96 * j, s);
+    if (rc) return rc;
+  }
+  CU(cudaMemcpyAsync(ck->ws.h_out, ck->ws.d_out, 96 * k, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  memcpy(out, ck->ws.h_out, 96 * k);
+  return B200_OK;
+}
+
+int b200_msm_small(uint64_t handle, size_t base_offset, const void* scalars, int elem_bytes, size_t n,
+                   int max_bits, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (!out || (n && !scalars)) return fail(B200_E_ARG, "null pointer");
+  if (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8)
+    return fail(B200_E_ARG, "elem_bytes must be 1, 2, 4 or 8 (got %d)", elem_bytes);
+  if (max_bits < 0 || max_bits > 64) return fail(B200_E_ARG, "max_bits %d out of range", max_bits);
+  if (base_offset + n > ck->n)
+    return fail(B200_E_RANGE, "msm slice [%zu, %zu) exceeds key length %zu", base_offset,
+                base_offset + n, ck->n);
+  // max_bits only selects the algorithm in the reference (msm.rs:487-502); the digit stream
+  // below skips zero windows, so every width takes the same path here.
+  std::lock_guard<std::mutex> lk(ck->mu);
+  rc = ensure_workspace(*ck, n ? n : 1, 1);
+  if (rc) return rc;
+  cudaStream_t s = g_dev.stream;
+  if (n) CU(cudaMemcpyAsync(ck->ws.scalars, scalars, n * elem_bytes, cudaMemcpyHostToDevice, s));
+  rc = enqueue_msm(*ck, base_offset, ck->ws.scalars, n, ck->ws.d_out, s, elem_bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ck->ws.h_out, ck->ws.d_out, 96, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  memcpy(out, ck->ws.h_out, 96);
+  return B200_OK;
+}
+
+int b200_msm_indices(uint64_t handle, const uint64_t* idx, size_t m, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (!out || (m && !idx)) return fail(B200_E_ARG, "null pointer");
+  std::vector<uint32_t> idx32(m);
+  for (size_t j = 0; j < m; j++) {
+    if (idx[j] >= ck->n) return fail(B200_E_RANGE, "index %llu outside key of %zu",
+                                     (unsigned long long)idx[j], ck->n);
+    idx32[j] = (uint32_t)idx[j];
+  }
+  std::lock_guard<std::mutex> lk(ck->mu);
+  rc = ensure_workspace(*ck, 1, 1);
+  if (rc) return rc;
+  workspace& w = ck->ws;
+  if (m > w.idx_cap) {
+    if (w.idx32) cudaFree(w.idx32);
+    w.idx32 = nullptr;
+    CU(cudaMalloc((void**)&w.idx32, m * 4));
+    w.idx_cap = m;
+  }
+  cudaStream_t s = g_dev.stream;
+  if (m) CU(cudaMemcpyAsync(w.idx32, idx32.data(), m * 4, cudaMemcpyHostToDevice, s));
+  const field_ops* bops = ops_for_field(CURVES[ck->curve].base_fid);
+  bops->sum_points(s, ck->tables, w.idx32, m, w.sumscratch, w.d_out);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(w.h_out, w.d_out, 96, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  memcpy(out, w.h_out, 96);
+  return B200_OK;
+}
+
+int b200_msm_adhoc(int curve_id, const void* bases, const void* scalars, size_t n, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!out) return fail(B200_E_ARG, "null out");
+  if (n == 0) {
+    memset(out, 0, 96);
+    return B200_OK;
+  }
+  if (!bases || !scalars) return fail(B200_E_ARG, "null pointer");
+  std::shared_ptr<ck_ctx> ck;
+  rc = register_key(curve_id, bases, false, n, 0, /*expand=*/false, ck);
+  if (rc) return rc;
+  return msm_host(*ck, 0, scalars, n, out);
+}
+
+// ---- field vectors ------------------------------------------------------------------------------
+int b200_cross_term_dev(int fid, const void* az, const void* bz, const void* cz, const void* e1,
+                        const void* e2, const void* u, size_t n, void* t, void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (n == 0) return (int)B200_OK;
+    if (!az || !bz || !cz || !e1 || !u || !t) return fail(B200_E_ARG, "null pointer");
+    ops->cross_term(stream ? (cudaStream_t)stream : g_dev.stream, az, bz, cz, e1, e2, u, n, t);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
+int b200_axpy_dev(int fid, const void* a, const void* b, const void* r, size_t n, void* out,
+                  void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (n == 0) return (int)B200_OK;
+    if (!a || !b || !r || !out) return fail(B200_E_ARG, "null pointer");
+    ops->axpy(stream ? (cudaStream_t)stream : g_dev.stream, a, b, r, n, out);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
+int b200_vec_add_dev(int fid, const void* a, const void* b, size_t n, void* out, void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (n == 0) return (int)B200_OK;
+    if (!a || !b || !out) return fail(B200_E_ARG, "null pointer");
+    ops->vec_add(stream ? (cudaStream_t)stream : g_dev.stream, a, b, n, out);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
+int b200_bind_top_dev(int fid, void* z, size_t n, const void* r, void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (n < 2) return (int)B200_OK;
+    if (n & 1) return fail(B200_E_ARG, "bind_top needs an even length, got %zu", n);
+    if (!z || !r) return fail(B200_E_ARG, "null pointer");
+    ops->bind_top(stream ? (cudaStream_t)stream : g_dev.stream, z, n, r);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
+
+// host-pointer forms: upload, run, download
+int b200_cross_term(int fid, const void* az, const void* bz, const void* cz, const void* e1,
+                    const void* e2, const void* u, size_t n, void* t) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) return B200_OK;
+  if (!az || !bz || !cz || !e1 || !u || !t) return fail(B200_E_ARG, "null pointer");
+  dev_buf buf;
+  size_t vec = n * 32;
+  int nvec = e2 ? 6 : 5;
+  rc = buf.alloc(vec * nvec + 32);
+  if (rc) return rc;
+  char* d = (char*)buf.p;
+  cudaStream_t s = g_dev.stream;
+  const void* src[5] = {az, bz, cz, e1, e2};
+  for (int k = 0; k < (e2 ? 5 : 4); k++)
+    CU(cudaMemcpyAsync(d + vec * k, src[k], vec, cudaMemcpyHostToDevice, s));
+  char* du = d + vec * nvec;
+  CU(cudaMemcpyAsync(du, u, 32, cudaMemcpyHostToDevice, s));
+  char* dt = d + vec * (nvec - 1);
+  rc = b200_cross_term_dev(fid, d, d + vec, d + 2 * vec, d + 3 * vec, e2 ? d + 4 * vec : nullptr, du,
+                           n, dt, s);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(t, dt, vec, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+int b200_axpy(int fid, const void* a, const void* b, const void* r, size_t n, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) return B200_OK;
+  if (!a || !b || !r || !out) return fail(B200_E_ARG, "null pointer");
+  dev_buf buf;
+  size_t vec = n * 32;
+  rc = buf.alloc(vec * 3 + 32);
+  if (rc) return rc;
+  char* d = (char*)buf.p;
+  cudaStream_t s = g_dev.stream;
+  CU(cudaMemcpyAsync(d, a, vec, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + vec, b, vec, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + 3 * vec, r, 32, cudaMemcpyHostToDevice, s));
+  rc = b200_axpy_dev(fid, d, d + vec, d + 3 * vec, n, d + 2 * vec, s);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, d + 2 * vec, vec, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+int b200_vec_add(int fid, const void* a, const void* b, size_t n, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n == 0) return B200_OK;
+  if (!a || !b || !out) return fail(B200_E_ARG, "null pointer");
+  dev_buf buf;
+  size_t vec = n * 32;
+  rc = buf.alloc(vec * 3);
+  if (rc) return rc;
+  char* d = (char*)buf.p;
+  cudaStream_t s = g_dev.stream;
+  CU(cudaMemcpyAsync(d, a, vec, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + vec, b, vec, cudaMemcpyHostToDevice, s));
+  rc = b200_vec_add_dev(fid, d, d + vec, n, d + 2 * vec, s);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, d + 2 * vec, vec, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+int b200_bind_top(int fid, void* z, size_t n, const void* r) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n < 2) return B200_OK;
+  if (n & 1) return fail(B200_E_ARG, "bind_top needs an even length, got %zu", n);
+  if (!z || !r) return fail(B200_E_ARG, "null pointer");
+  dev_buf buf;
+  size_t vec = n * 32;
+  rc = buf.alloc(vec + 32);
+  if (rc) return rc;
+  char* d = (char*)buf.p;
+  cudaStream_t s = g_dev.stream;
+  CU(cudaMemcpyAsync(d, z, vec, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + vec, r, 32, cudaMemcpyHostToDevice, s));
+  rc = b200_bind_top_dev(fid, d, n, d + vec, s);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(z, d, vec / 2, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+}  // extern "C"

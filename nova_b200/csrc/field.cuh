@@ -1,0 +1,366 @@
+// 256-bit Montgomery prime-field arithmetic for sm_100a (K1 of SURVEY.md §2).
+//
+// Replaces, on the device, what the reference gets from the third-party crate
+// halo2curves 0.9.0 (bn256::{Fr,Fq}, pasta::{Fp,Fq}; re-exported at
+// src/provider/bn256_grumpkin.rs:26-33 and src/provider/pasta.rs:24-31).
+// In-memory layout at the boundary is halo2curves': 4 x u64 little-endian limbs in
+// Montgomery form, R = 2^256  ==  8 x u32 little-endian limbs here.
+//
+// Design: 8 x 32-bit limbs per element, one element per thread, everything in registers.
+// The multiplier is a CIOS Montgomery product whose partial products are split over two
+// accumulators by the parity of their limb position, so that every (lo,hi) pair of one
+// 32x32 product lands in adjacent limbs of ONE carry chain -- ptxas turns each
+// mad.lo.cc/madc.hi.cc pair into a single IMAD.WIDE.U32(.X).  Each chain is one asm
+// statement (the carry flag never crosses a statement boundary).  Every chain has a
+// bit-exact host emulation so the algorithm is unit-tested on CPU (tests/test_host_field.py).
+#pragma once
+#include <cstdint>
+#include "field_constants.cuh"
+
+#if defined(__CUDACC__)
+#define NOVA_HD __host__ __device__ __forceinline__
+#define NOVA_D __device__ __forceinline__
+#else
+#define NOVA_HD inline
+#define NOVA_D inline
+#endif
+
+namespace nova {
+
+struct alignas(16) fe_t {
+  uint32_t l[8];
+};
+
+// ---------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------
+
+// X[OFF .. OFF+7] += (x0,x1,x2,x3) * y  with product k occupying limbs (OFF+2k, OFF+2k+1);
+// X[OFF+8] += carry-out.  If CIN, the chain starts with carry-in = carry32(ca + cb).
+template <int OFF, bool CIN, int N>
+NOVA_HD void chain_mad(uint32_t (&X)[N], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3,
+                       uint32_t y, uint32_t ca = 0, uint32_t cb = 0) {
+  static_assert(OFF + 8 < N, "accumulator too short");
+#ifdef __CUDA_ARCH__
+  if constexpr (CIN) {
+    asm("{\n\t"
+        ".reg .u32 t;\n\t"
+        "add.cc.u32 t, %14, %15;\n\t"
+        "madc.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;\n\t"
+        "}"
+        : "+r"(X[OFF + 0]), "+r"(X[OFF + 1]), "+r"(X[OFF + 2]), "+r"(X[OFF + 3]),
+          "+r"(X[OFF + 4]), "+r"(X[OFF + 5]), "+r"(X[OFF + 6]), "+r"(X[OFF + 7]),
+          "+r"(X[OFF + 8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y), "r"(ca), "r"(cb));
+  } else {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(X[OFF + 0]), "+r"(X[OFF + 1]), "+r"(X[OFF + 2]), "+r"(X[OFF + 3]),
+          "+r"(X[OFF + 4]), "+r"(X[OFF + 5]), "+r"(X[OFF + 6]), "+r"(X[OFF + 7]),
+          "+r"(X[OFF + 8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+  }
+#else
+  uint64_t cf = CIN ? (((uint64_t)ca + cb) >> 32) : 0;
+  const uint32_t xs[4] = {x0, x1, x2, x3};
+  for (int k = 0; k < 4; k++) {
+    uint64_t prod = (uint64_t)xs[k] * y;
+    uint64_t t = (uint64_t)X[OFF + 2 * k] + (uint32_t)prod + cf;
+    X[OFF + 2 * k] = (uint32_t)t;
+    cf = t >> 32;
+    t = (uint64_t)X[OFF + 2 * k + 1] + (prod >> 32) + cf;
+    X[OFF + 2 * k + 1] = (uint32_t)t;
+    cf = t >> 32;
+  }
+  X[OFF + 8] += (uint32_t)cf;
+#endif
+}
+
+// r = a + b (8 limbs) ; returns nothing, carry-out impossible for p < 2^255 operands < p
+NOVA_HD void add8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t t = (uint64_t)a[i] + b[i] + c;
+    r[i] = (uint32_t)t;
+    c = t >> 32;
+  }
+#endif
+}
+
+// r = a + b + carry32(ca + cb)
+NOVA_HD void add8_cin(uint32_t (&r)[8], const uint32_t* a, const uint32_t* b, uint32_t ca,
+                      uint32_t cb) {
+#ifdef __CUDA_ARCH__
+  asm("{\n\t"
+      ".reg .u32 t;\n\t"
+      "add.cc.u32 t, %24, %25;\n\t"
+      "addc.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      "}"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]),
+        "r"(ca), "r"(cb));
+#else
+  uint64_t c = ((uint64_t)ca + cb) >> 32;
+  for (int i = 0; i < 8; i++) {
+    uint64_t t = (uint64_t)a[i] + b[i] + c;
+    r[i] = (uint32_t)t;
+    c = t >> 32;
+  }
+#endif
+}
+
+// r = a - b (8 limbs); returns 0xffffffff if the subtraction borrowed, else 0
+NOVA_HD uint32_t sub8(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  uint32_t borrow;
+#ifdef __CUDA_ARCH__
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t t = (uint64_t)a[i] - b[i] - c;
+    r[i] = (uint32_t)t;
+    c = (t >> 32) & 1;
+  }
+  borrow = c ? 0xffffffffu : 0u;
+#endif
+  return borrow;
+}
+
+template <class F>
+NOVA_HD void load_p(uint32_t (&p)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) p[i] = F::p(i);
+}
+
+// ---------------------------------------------------------------------------------------
+// field operations (all inputs and outputs fully reduced, in [0, p))
+// ---------------------------------------------------------------------------------------
+
+template <class F>
+NOVA_HD fe_t fe_zero() {
+  fe_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = 0;
+  return r;
+}
+
+template <class F>
+NOVA_HD fe_t fe_one() {  // Montgomery form of 1
+  fe_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = F::r(i);
+  return r;
+}
+
+NOVA_HD bool fe_is_zero(const fe_t& a) {
+  return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0;
+}
+
+NOVA_HD bool fe_eq(const fe_t& a, const fe_t& b) {
+  return ((a.l[0] ^ b.l[0]) | (a.l[1] ^ b.l[1]) | (a.l[2] ^ b.l[2]) | (a.l[3] ^ b.l[3]) |
+          (a.l[4] ^ b.l[4]) | (a.l[5] ^ b.l[5]) | (a.l[6] ^ b.l[6]) | (a.l[7] ^ b.l[7])) == 0;
+}
+
+// conditional subtract of p: r in [0, 2p) -> [0, p)
+template <class F>
+NOVA_HD void fe_reduce_once(uint32_t (&r)[8]) {
+  uint32_t p[8], t[8];
+  load_p<F>(p);
+  uint32_t borrow = sub8(t, r, p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+template <class F>
+NOVA_HD fe_t fe_add(const fe_t& a, const fe_t& b) {
+  fe_t r;
+  add8(r.l, a.l, b.l);  // < 2p < 2^256
+  fe_reduce_once<F>(r.l);
+  return r;
+}
+
+template <class F>
+NOVA_HD fe_t fe_sub(const fe_t& a, const fe_t& b) {
+  fe_t r;
+  uint32_t p[8], t[8];
+  load_p<F>(p);
+  uint32_t borrow = sub8(r.l, a.l, b.l);
+  add8(t, r.l, p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = borrow ? t[i] : r.l[i];
+  return r;
+}
+
+template <class F>
+NOVA_HD fe_t fe_neg(const fe_t& a) {
+  fe_t z = fe_zero<F>();
+  return fe_is_zero(a) ? z : fe_sub<F>(z, a);
+}
+
+template <class F>
+NOVA_HD fe_t fe_dbl(const fe_t& a) {
+  return fe_add<F>(a, a);
+}
+
+template <class F, int I>
+NOVA_HD void mont_round(uint32_t (&E)[17], uint32_t (&O)[17], const fe_t& a, uint32_t bi) {
+  // Round I adds a*b[I] and m*p at absolute limb position I.  The accumulator whose
+  // (lo,hi) pairs start at position I is E for even I, O for odd I.
+  if constexpr ((I & 1) == 0) {
+    if constexpr (I == 0)
+      chain_mad<I, false>(E, a.l[0], a.l[2], a.l[4], a.l[6], bi);
+    else  // carry-in retires position I-1: carry32(E[I-1] + O[I-1])
+      chain_mad<I, true>(E, a.l[0], a.l[2], a.l[4], a.l[6], bi, E[I - 1], O[I - 1]);
+    chain_mad<I + 1, false>(O, a.l[1], a.l[3], a.l[5], a.l[7], bi);
+    uint32_t m = (E[I] + O[I]) * F::INV;
+    chain_mad<I, false>(E, F::p(0), F::p(2), F::p(4), F::p(6), m);
+    chain_mad<I + 1, false>(O, F::p(1), F::p(3), F::p(5), F::p(7), m);
+  } else {
+    chain_mad<I, true>(O, a.l[0], a.l[2], a.l[4], a.l[6], bi, E[I - 1], O[I - 1]);
+    chain_mad<I + 1, false>(E, a.l[1], a.l[3], a.l[5], a.l[7], bi);
+    uint32_t m = (E[I] + O[I]) * F::INV;
+    chain_mad<I, false>(O, F::p(0), F::p(2), F::p(4), F::p(6), m);
+    chain_mad<I + 1, false>(E, F::p(1), F::p(3), F::p(5), F::p(7), m);
+  }
+}
+
+// r = a * b * R^-1 mod p
+template <class F>
+NOVA_HD fe_t fe_mul(const fe_t& a, const fe_t& b) {
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) E[i] = O[i] = 0;
+  mont_round<F, 0>(E, O, a, b.l[0]);
+  mont_round<F, 1>(E, O, a, b.l[1]);
+  mont_round<F, 2>(E, O, a, b.l[2]);
+  mont_round<F, 3>(E, O, a, b.l[3]);
+  mont_round<F, 4>(E, O, a, b.l[4]);
+  mont_round<F, 5>(E, O, a, b.l[5]);
+  mont_round<F, 6>(E, O, a, b.l[6]);
+  mont_round<F, 7>(E, O, a, b.l[7]);
+  fe_t r;
+  add8_cin(r.l, &E[8], &O[8], E[7], O[7]);  // < 2p
+  fe_reduce_once<F>(r.l);
+  return r;
+}
+
+template <class F>
+NOVA_HD fe_t fe_sqr(const fe_t& a) {
+  return fe_mul<F>(a, a);
+}
+
+// Montgomery <-> canonical
+template <class F>
+NOVA_HD fe_t fe_from_mont(const fe_t& a) {
+  fe_t one;
+#pragma unroll
+  for (int i = 0; i < 8; i++) one.l[i] = (i == 0);
+  return fe_mul<F>(a, one);
+}
+
+template <class F>
+NOVA_HD fe_t fe_to_mont(const fe_t& a) {
+  fe_t r2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r2.l[i] = F::r2(i);
+  return fe_mul<F>(a, r2);
+}
+
+// a^(p-2) by square-and-multiply (only used O(1) times per call, never in hot loops)
+template <class F>
+NOVA_HD fe_t fe_inv(const fe_t& a) {
+  uint32_t e[8];
+  uint32_t bw = 2;  // e = p - 2 with borrow propagation (Pasta moduli have low limb 1)
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t pi = F::p(i);
+    e[i] = pi - bw;
+    bw = (pi < bw) ? 1u : 0u;
+  }
+  fe_t acc = fe_one<F>();
+  for (int i = 255; i >= 0; i--) {
+    acc = fe_sqr<F>(acc);
+    if ((e[i >> 5] >> (i & 31)) & 1) acc = fe_mul<F>(acc, a);
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// global-memory access: 2 x 128-bit per element
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+NOVA_D fe_t fe_load(const void* base, size_t idx) {
+  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * idx;
+  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+  fe_t r;
+  r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+  r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
+// same, but through the normal (coherent) path -- for buffers written earlier in the same kernel
+NOVA_D fe_t fe_load_rw(const void* base, size_t idx) {
+  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * idx;
+  uint4 lo = p[0], hi = p[1];
+  fe_t r;
+  r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+  r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+  return r;
+}
+NOVA_D void fe_store(void* base, size_t idx, const fe_t& a) {
+  uint4* p = reinterpret_cast<uint4*>(base) + 2 * idx;
+  p[0] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
+  p[1] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
+}
+#endif
+
+}  // namespace nova

@@ -1,0 +1,341 @@
+// Pippenger bucket MSM for sm_100a (K2/K3 of SURVEY.md §2).
+//
+// Replaces  src/provider/msm.rs:225-419 `msm` (+ the third-party
+// halo2curves::msm::msm_best it delegates to at msm.rs:399-411,493-501) behind
+// DlogGroupExt::vartime_multiscalar_mul (src/provider/traits.rs:77-117).
+//
+// Because a commitment key is fixed for the life of PublicParams (src/nova/mod.rs:55-58), the
+// key is registered once and expanded into F tables  T_t[i] = 2^(c*G*t) * P_i  (affine).  A
+// scalar's signed c-bit digit for window w = t*G + g then selects table t and bucket group g,
+// so   sum_i s_i P_i = sum_g 2^(c g) * sum_b b * Bucket[g][b].   With F = W (full expansion)
+// there is ONE bucket group and no serial doubling tail.
+//
+// Pipeline (all on one stream, no host sync):
+//   k_digits      scalar (Montgomery) -> canonical -> sign-fold (s > p/2 => p-s, flip) ->
+//                 signed c-bit digits; histogram of bucket keys            [msm.rs:247-252 idea]
+//   scan          exclusive prefix sum of the histogram
+//   k_scatter     counting-sort scatter of (key, sign, table index) entries
+//   k_accumulate  one thread per L consecutive sorted entries: XYZZ mixed adds
+//                 (msm.rs:126-165); interior runs go straight to their bucket, the first/last
+//                 run of a segment to a boundary-partial list
+//   k_fixup       joins boundary partials of the same bucket (msm.rs:91-123 full add)
+//   k_reduce1/2   sum_b b*Bucket[b] by chunked running sums (msm.rs:555-560 is the serial form),
+//                 group Horner, XYZZ -> Jacobian
+#pragma once
+#include <cuda_runtime.h>
+#include "curve.cuh"
+
+namespace nova {
+
+constexpr uint32_t KEY_INVALID = 0xffffffffu;
+
+struct msm_plan {
+  // problem
+  size_t n;            // scalars in this call
+  size_t n_ck;         // points per table in the registered key
+  size_t base_offset;  // first key point used
+  int c;               // window bits
+  int W;               // number of windows = F*G
+  int G;               // bucket groups
+  uint32_t B;          // buckets per group = 2^(c-1)
+  int L;               // entries per accumulate segment
+  int m;               // buckets per reduce chunk
+  // workspace (device)
+  int32_t* digits;     // [W][n]
+  uint32_t* counts;    // [K]     K = G*B
+  uint32_t* start;     // [K+1]
+  uint32_t* cursor;    // [K]
+  uint64_t* entries;   // [n*W]
+  void* buckets;       // [K] xyzz
+  void* parts;         // [2*nseg_max] xyzz
+  uint32_t* pkeys;     // [2*nseg_max]
+  void* rparts;        // [G*T] xyzz, T = B/m
+  uint32_t* blocksums; // scan scratch
+  uint32_t* heavy;     // [0] = count, [1..] = keys whose bucket spans > heavy_min entries
+  uint32_t heavy_min;  // entries; such buckets are joined by k_fixup_heavy (one block each)
+  uint32_t heavy_cap;  // capacity of the heavy list
+};
+
+// ------------------------------------------------------------------------------------------
+// digits + histogram   (templated on the SCALAR field)
+// ------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(256) k_digits(const void* __restrict__ scalars, size_t n, int c,
+                                                int W, int G, uint32_t B,
+                                                int32_t* __restrict__ digits,
+                                                uint32_t* __restrict__ counts) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_t s = fe_from_mont<S>(fe_load(scalars, i));
+  // sign fold: use p - s when that is the smaller integer (msm.rs:1-8 "signed scalar
+  // decomposition"); small negative witness values then cost one bucket add, not W.
+  uint32_t p[8], t[8];
+  load_p<S>(p);
+  bool neg = false;
+  if (!fe_is_zero(s)) {
+    sub8(t, p, s.l);  // p - s, never borrows
+    // compare t < s  <=> p - s < s
+    uint32_t d[8];
+    uint32_t lt = sub8(d, t, s.l);
+    if (lt) {
+      neg = true;
+#pragma unroll
+      for (int k = 0; k < 8; k++) s.l[k] = t[k];
+    }
+  }
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (1u << c) - 1;
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    int bit = w * c;
+    int limb = bit >> 5, sh = bit & 31;
+    uint32_t v = 0;
+    if (limb < 8) {
+      uint64_t two = s.l[limb];
+      if (limb + 1 < 8) two |= (uint64_t)s.l[limb + 1] << 32;
+      v = (uint32_t)(two >> sh) & mask;
+    }
+    v += carry;
+    int32_t dgt;
+    if (v > half) {  // digits in [-(half-1), half]
+      dgt = (int32_t)v - (int32_t)(1u << c);
+      carry = 1;
+    } else {
+      dgt = (int32_t)v;
+      carry = 0;
+    }
+    if (neg) dgt = -dgt;
+    digits[(size_t)w * n + i] = dgt;
+    if (dgt != 0) {
+      uint32_t mag = dgt < 0 ? (uint32_t)(-dgt) : (uint32_t)dgt;
+      uint32_t key = (uint32_t)(w % G) * B + (mag - 1);
+      atomicAdd(&counts[key], 1u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket accumulation   (templated on the BASE field)
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const uint64_t* __restrict__ entries,
+                                                    const uint32_t* __restrict__ start, uint32_t K,
+                                                    const void* __restrict__ tables, int L,
+                                                    void* __restrict__ buckets,
+                                                    void* __restrict__ parts,
+                                                    uint32_t* __restrict__ pkeys) {
+  const uint32_t M = start[K];
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t seg_start = t * (size_t)L;
+  if (seg_start >= M) return;
+  size_t seg_end = seg_start + L < M ? seg_start + L : M;
+
+  xyzz_t acc = xyzz_identity<F>();
+  uint64_t ent = entries[seg_start];
+  uint32_t cur_key = (uint32_t)(ent >> 32);
+  bool first = true;
+  affine_t pt = affine_load(tables, (uint32_t)ent & 0x7fffffffu);
+  for (size_t e = seg_start; e < seg_end; e++) {
+    uint32_t key = (uint32_t)(ent >> 32);
+    bool sign = (ent >> 31) & 1;
+    affine_t cur = pt;
+    // prefetch the next entry's point while this one is being added
+    if (e + 1 < seg_end) {
+      ent = entries[e + 1];
+      pt = affine_load(tables, (uint32_t)ent & 0x7fffffffu);
+    }
+    if (key != cur_key) {
+      if (first) {
+        xyzz_store(parts, 2 * t, acc);
+        pkeys[2 * t] = cur_key;
+        first = false;
+      } else {
+        xyzz_store(buckets, cur_key, acc);
+      }
+      acc = xyzz_identity<F>();
+      cur_key = key;
+    }
+    if (!affine_is_identity(cur)) {  // identity bases are skipped (msm.rs:247)
+      if (sign) cur.y = fe_neg<F>(cur.y);
+      xyzz_madd<F>(acc, cur.x, cur.y);
+    }
+  }
+  if (first) {
+    xyzz_store(parts, 2 * t, acc);
+    pkeys[2 * t] = cur_key;
+    pkeys[2 * t + 1] = KEY_INVALID;
+  } else {
+    xyzz_store(parts, 2 * t + 1, acc);
+    pkeys[2 * t + 1] = cur_key;
+  }
+}
+
+// one thread per boundary partial; the head of each same-key run sums the run
+template <class F>
+__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ start, uint32_t K,
+                                               int L, uint32_t heavy_min,
+                                               const void* __restrict__ parts,
+                                               const uint32_t* __restrict__ pkeys,
+                                               void* __restrict__ buckets) {
+  const uint32_t M = start[K];
+  const size_t nseg = ((size_t)M + L - 1) / L;
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * nseg) return;
+  uint32_t key = pkeys[j];
+  if (key == KEY_INVALID) return;
+  if (start[key + 1] - start[key] > heavy_min) return;  // joined by k_fixup_heavy
+  if (j > 0) {
+    uint32_t pk = pkeys[j - 1];
+    if (pk == KEY_INVALID && j > 1) pk = pkeys[j - 2];
+    if (pk == key) return;  // not a run head
+  }
+  xyzz_t acc = xyzz_load(parts, j);
+  for (size_t k = j + 1; k < 2 * nseg; k++) {
+    uint32_t kk = pkeys[k];
+    if (kk == KEY_INVALID) continue;
+    if (kk != key) break;
+    xyzz_t o = xyzz_load(parts, k);
+    xyzz_add<F>(acc, o);
+  }
+  xyzz_store(buckets, key, acc);
+}
+
+// Heavy buckets (skewed scalars: 0/1 witnesses, repeated values) would serialise the run-head
+// loop above, so each gets a whole block: the threads stride over the bucket's partial slots,
+// then tree-sum through shared memory.
+template <class F>
+__global__ void __launch_bounds__(256) k_fixup_heavy(const uint32_t* __restrict__ start, int L,
+                                                     const uint32_t* __restrict__ heavy,
+                                                     const void* __restrict__ parts,
+                                                     const uint32_t* __restrict__ pkeys,
+                                                     void* __restrict__ buckets) {
+  __shared__ xyzz_t sm[256];
+  const uint32_t nheavy = heavy[0];
+  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    uint32_t key = heavy[1 + h];
+    size_t s0 = 2 * ((size_t)start[key] / L);
+    size_t s1 = 2 * (((size_t)start[key + 1] - 1) / L) + 1;
+    xyzz_t acc = xyzz_identity<F>();
+    for (size_t k = s0 + threadIdx.x; k <= s1; k += blockDim.x) {
+      if (pkeys[k] == key) {
+        xyzz_t o = xyzz_load(parts, k);
+        xyzz_add<F>(acc, o);
+      }
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        xyzz_t a = sm[threadIdx.x];
+        xyzz_add<F>(a, sm[threadIdx.x + s]);
+        sm[threadIdx.x] = a;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) xyzz_store(buckets, key, sm[0]);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket reduction
+// ------------------------------------------------------------------------------------------
+// thread (g, k): chunk of m buckets [k*m, (k+1)*m) of group g ->
+//   rparts[g*T + k] = sum_{b in chunk} (b+1) * Bucket[g][b]
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce1(const uint32_t* __restrict__ start, uint32_t B,
+                                                 int G, int m, const void* __restrict__ buckets,
+                                                 void* __restrict__ rparts) {
+  uint32_t T = B / m;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= T * (uint32_t)G) return;
+  uint32_t g = tid / T, k = tid % T;
+  uint32_t lo = k * m;
+  xyzz_t run = xyzz_identity<F>(), tot = xyzz_identity<F>();
+  for (int b = m - 1; b >= 0; b--) {
+    uint32_t key = g * B + lo + b;
+    if (start[key + 1] > start[key]) {
+      xyzz_t bk = xyzz_load(buckets, key);
+      xyzz_add<F>(run, bk);
+    }
+    xyzz_add<F>(tot, run);
+  }
+  if (lo != 0) {
+    xyzz_t sc = xyzz_mul_small<F>(run, lo);
+    xyzz_add<F>(tot, sc);
+  }
+  xyzz_store(rparts, tid, tot);
+}
+
+// single block: per group tree-sum of T partials, Horner over groups (c doublings each),
+// plus an optional extra XYZZ addend, then Jacobian out (3 x fe_t).
+template <class F>
+__global__ void __launch_bounds__(256) k_reduce2(const void* __restrict__ rparts, uint32_t T, int G,
+                                                 int c, void* __restrict__ out_jac) {
+  __shared__ xyzz_t sm[256];
+  xyzz_t total = xyzz_identity<F>();
+  for (int g = G - 1; g >= 0; g--) {
+    xyzz_t acc = xyzz_identity<F>();
+    for (uint32_t k = threadIdx.x; k < T; k += blockDim.x) {
+      xyzz_t o = xyzz_load(rparts, (size_t)g * T + k);
+      xyzz_add<F>(acc, o);
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        xyzz_t a = sm[threadIdx.x];
+        xyzz_add<F>(a, sm[threadIdx.x + s]);
+        sm[threadIdx.x] = a;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (g != G - 1)
+        for (int d = 0; d < c; d++) xyzz_dbl<F>(total);
+      xyzz_add<F>(total, sm[0]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    fe_t X, Y, Z;
+    xyzz_to_jacobian<F>(total, X, Y, Z);
+    fe_store(out_jac, 0, X);
+    fe_store(out_jac, 1, Y);
+    fe_store(out_jac, 2, Z);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// key expansion:  tables[t][i] = 2^(shift*t) * bases[i]  (affine; identity stays (0,0))
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_expand_key(void* __restrict__ tables, size_t n_ck,
+                                                    int ntables, int shift) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ck) return;
+  affine_t p;
+  p.x = fe_load_rw(tables, 2 * i);
+  p.y = fe_load_rw(tables, 2 * i + 1);
+  if (affine_is_identity(p)) {
+    for (int t = 1; t < ntables; t++) {
+      fe_store(tables, 2 * ((size_t)t * n_ck + i), p.x);
+      fe_store(tables, 2 * ((size_t)t * n_ck + i) + 1, p.y);
+    }
+    return;
+  }
+  for (int t = 1; t < ntables; t++) {
+    xyzz_t q = xyzz_identity<F>();
+    xyzz_madd<F>(q, p.x, p.y);
+    for (int d = 0; d < shift; d++) xyzz_dbl<F>(q);
+    // affine: x = X/ZZ, y = Y/ZZZ;  1/ZZ = ZZ^2 * (1/ZZZ)^2 because ZZ^3 = ZZZ^2
+    fe_t iz3 = fe_inv<F>(q.zzz);
+    fe_t iz2 = fe_mul<F>(fe_sqr<F>(q.zz), fe_sqr<F>(iz3));
+    p.x = fe_mul<F>(q.x, iz2);
+    p.y = fe_mul<F>(q.y, iz3);
+    fe_store(tables, 2 * ((size_t)t * n_ck + i), p.x);
+    fe_store(tables, 2 * ((size_t)t * n_ck + i) + 1, p.y);
+  }
+}
+
+}  // namespace nova

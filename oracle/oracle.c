@@ -1,0 +1,802 @@
+/* CPU oracle for the Nova prover hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  nova_b200/ never links or calls it; the product path fails loudly when
+ * the CUDA library is missing.
+ *
+ * What it restates (plain C, unsigned __int128 Montgomery arithmetic, pthreads):
+ *   - prime fields of halo2curves 0.9.0 (Cargo.toml:38; NOT vendored in /root/reference):
+ *     4 x u64 little-endian limbs, Montgomery R = 2^256, moduli from
+ *     src/provider/bn256_grumpkin.rs:39-40,84-85 and src/provider/pasta.rs:37-38,45-46
+ *   - XYZZ bucket arithmetic                         src/provider/msm.rs:38-183
+ *   - msm() classification + 11-group dispatch       src/provider/msm.rs:225-419
+ *   - msm_simple / accumulate_bases                  src/provider/msm.rs:422-454
+ *   - msm_small_with_max_num_bits, msm_binary, msm_10, msm_small_rest, compute_ln
+ *                                                    src/provider/msm.rs:469-686
+ *   - batch_add                                      src/provider/msm.rs:689-708
+ *   - halo2curves::msm::msm_best (called at msm.rs:411,500; source absent): restated from its
+ *     published algorithm -- windowed Pippenger over canonical scalar bytes with signed (Booth)
+ *     digits, window from ln(n), per-thread slices reduced at the end.
+ *   - R1CS field arithmetic: cross-term, folds, bind  src/r1cs/mod.rs:614-620,650-657,1044-1073;
+ *                                                    src/spartan/polys/multilinear.rs:65-84
+ *
+ * Parity status: field encodings PINNED by the keccak transcript golden vectors
+ * (src/provider/keccak.rs:241-258) through oracle/pyref.py, against which this file is checked
+ * element-by-element (tests/test_oracle_golden.py).  MSM outputs: the reference holds no literal
+ * commitment bytes; they are pinned semantically (every algorithm here == naive
+ * sum == Python big-int group law) exactly as the reference's own tests do (msm.rs:722-821,
+ * curve_property_tests.rs:172-218).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "field_constants.h"
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[4]; } fe;
+typedef struct { fe x, y; } aff;            /* identity: x = y = 0 */
+typedef struct { fe x, y, zz, zzz; } xyzz;  /* identity: zz = 0 (msm.rs:53-62) */
+
+/* ------------------------------------------------------------------ field ---------------- */
+static inline int fe_is_zero(const fe* a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static inline int fe_eq(const fe* a, const fe* b) {
+  return ((a->l[0] ^ b->l[0]) | (a->l[1] ^ b->l[1]) | (a->l[2] ^ b->l[2]) | (a->l[3] ^ b->l[3])) == 0;
+}
+static inline int geq(const uint64_t* a, const uint64_t* b) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] > b[i]) return 1;
+    if (a[i] < b[i]) return 0;
+  }
+  return 1;
+}
+static inline uint64_t sub4(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  u128 br = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a[i] - b[i] - br;
+    r[i] = (uint64_t)t;
+    br = (t >> 64) & 1;
+  }
+  return (uint64_t)br;
+}
+static inline uint64_t add4(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a[i] + b[i] + c;
+    r[i] = (uint64_t)t;
+    c = t >> 64;
+  }
+  return (uint64_t)c;
+}
+static inline void fe_add(const orc_field_t* F, fe* r, const fe* a, const fe* b) {
+  uint64_t t[4];
+  add4(t, a->l, b->l); /* p < 2^255: no carry out */
+  if (geq(t, F->p)) sub4(r->l, t, F->p); else memcpy(r->l, t, 32);
+}
+static inline void fe_sub(const orc_field_t* F, fe* r, const fe* a, const fe* b) {
+  uint64_t t[4];
+  if (sub4(t, a->l, b->l)) add4(r->l, t, F->p); else memcpy(r->l, t, 32);
+}
+static inline void fe_neg(const orc_field_t* F, fe* r, const fe* a) {
+  if (fe_is_zero(a)) { memset(r, 0, 32); return; }
+  sub4(r->l, F->p, a->l);
+}
+static inline void fe_dbl(const orc_field_t* F, fe* r, const fe* a) { fe_add(F, r, a, a); }
+/* CIOS Montgomery product */
+static inline void fe_mul(const orc_field_t* F, fe* r, const fe* a, const fe* b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      u128 s = (u128)a->l[j] * b->l[i] + t[j] + c;
+      t[j] = (uint64_t)s;
+      c = s >> 64;
+    }
+    u128 s = (u128)t[4] + c;
+    t[4] = (uint64_t)s;
+    t[5] = (uint64_t)(s >> 64);
+    uint64_t m = t[0] * F->inv;
+    c = ((u128)m * F->p[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) {
+      u128 s2 = (u128)m * F->p[j] + t[j] + c;
+      t[j - 1] = (uint64_t)s2;
+      c = s2 >> 64;
+    }
+    s = (u128)t[4] + c;
+    t[3] = (uint64_t)s;
+    t[4] = t[5] + (uint64_t)(s >> 64);
+  }
+  if (t[4] || geq(t, F->p)) sub4(r->l, t, F->p); else memcpy(r->l, t, 32);
+}
+static inline void fe_sqr(const orc_field_t* F, fe* r, const fe* a) { fe_mul(F, r, a, a); }
+static void fe_one(const orc_field_t* F, fe* r) { memcpy(r->l, F->r, 32); }
+static void fe_from_mont(const orc_field_t* F, fe* r, const fe* a) {
+  fe one = {{1, 0, 0, 0}};
+  fe_mul(F, r, a, &one);
+}
+static void fe_to_mont(const orc_field_t* F, fe* r, const fe* a) {
+  fe r2;
+  memcpy(r2.l, F->r2, 32);
+  fe_mul(F, r, a, &r2);
+}
+static void fe_inv(const orc_field_t* F, fe* r, const fe* a) { /* a^(p-2); inv(0) = 0 */
+  uint64_t e[4], two[4] = {2, 0, 0, 0};
+  sub4(e, F->p, two);
+  fe acc;
+  fe_one(F, &acc);
+  for (int i = 255; i >= 0; i--) {
+    fe_sqr(F, &acc, &acc);
+    if ((e[i >> 6] >> (i & 63)) & 1) fe_mul(F, &acc, &acc, a);
+  }
+  *r = acc;
+}
+static void fe_from_u64(const orc_field_t* F, fe* r, uint64_t v) {
+  fe t = {{v, 0, 0, 0}};
+  fe_to_mont(F, r, &t);
+}
+
+/* ------------------------------------------------------------------ XYZZ (msm.rs:38-183) -- */
+static void xyzz_zero(const orc_field_t* F, xyzz* b) { /* msm.rs:53-60 */
+  fe_one(F, &b->x);
+  fe_one(F, &b->y);
+  memset(&b->zz, 0, 32);
+  memset(&b->zzz, 0, 32);
+}
+static int xyzz_is_zero(const xyzz* b) { return fe_is_zero(&b->zz); }
+static int aff_is_identity(const aff* p) { return fe_is_zero(&p->x) && fe_is_zero(&p->y); }
+
+static void xyzz_double(const orc_field_t* F, xyzz* s) { /* msm.rs:65-88 */
+  if (xyzz_is_zero(s)) return;
+  fe u, v, w, S, xsq, m, t, x3, y3;
+  fe_dbl(F, &u, &s->y);
+  fe_sqr(F, &v, &u);
+  fe_mul(F, &w, &u, &v);
+  fe_mul(F, &S, &s->x, &v);
+  fe_sqr(F, &xsq, &s->x);
+  fe_dbl(F, &m, &xsq);
+  fe_add(F, &m, &m, &xsq);
+  fe_sqr(F, &x3, &m);
+  fe_dbl(F, &t, &S);
+  fe_sub(F, &x3, &x3, &t);
+  fe_sub(F, &t, &S, &x3);
+  fe_mul(F, &y3, &m, &t);
+  fe_mul(F, &t, &w, &s->y);
+  fe_sub(F, &y3, &y3, &t);
+  s->x = x3;
+  s->y = y3;
+  fe_mul(F, &s->zz, &s->zz, &v);
+  fe_mul(F, &s->zzz, &s->zzz, &w);
+}
+static void xyzz_add(const orc_field_t* F, xyzz* s, const xyzz* o) { /* msm.rs:91-123 */
+  if (xyzz_is_zero(o)) return;
+  if (xyzz_is_zero(s)) { *s = *o; return; }
+  fe u1, u2, s1, s2;
+  fe_mul(F, &u1, &s->x, &o->zz);
+  fe_mul(F, &u2, &o->x, &s->zz);
+  fe_mul(F, &s1, &s->y, &o->zzz);
+  fe_mul(F, &s2, &o->y, &s->zzz);
+  if (fe_eq(&u1, &u2)) {
+    if (fe_eq(&s1, &s2)) xyzz_double(F, s); else xyzz_zero(F, s);
+    return;
+  }
+  fe p, r, pp, ppp, q, t, x3, y3;
+  fe_sub(F, &p, &u2, &u1);
+  fe_sub(F, &r, &s2, &s1);
+  fe_sqr(F, &pp, &p);
+  fe_mul(F, &ppp, &p, &pp);
+  fe_mul(F, &q, &u1, &pp);
+  fe_sqr(F, &x3, &r);
+  fe_sub(F, &x3, &x3, &ppp);
+  fe_dbl(F, &t, &q);
+  fe_sub(F, &x3, &x3, &t);
+  fe_sub(F, &t, &q, &x3);
+  fe_mul(F, &y3, &r, &t);
+  fe_mul(F, &t, &s1, &ppp);
+  fe_sub(F, &y3, &y3, &t);
+  s->x = x3;
+  s->y = y3;
+  fe_mul(F, &s->zz, &s->zz, &o->zz);
+  fe_mul(F, &s->zz, &s->zz, &pp);
+  fe_mul(F, &s->zzz, &s->zzz, &o->zzz);
+  fe_mul(F, &s->zzz, &s->zzz, &ppp);
+}
+static void xyzz_add_affine(const orc_field_t* F, xyzz* b, const aff* p) { /* msm.rs:126-165 */
+  if (aff_is_identity(p)) return;
+  if (xyzz_is_zero(b)) {
+    b->x = p->x;
+    b->y = p->y;
+    fe_one(F, &b->zz);
+    fe_one(F, &b->zzz);
+    return;
+  }
+  fe u2, s2;
+  fe_mul(F, &u2, &p->x, &b->zz);
+  fe_mul(F, &s2, &p->y, &b->zzz);
+  if (fe_eq(&b->x, &u2)) {
+    if (fe_eq(&b->y, &s2)) xyzz_double(F, b); else xyzz_zero(F, b);
+    return;
+  }
+  fe pv, r, pp, ppp, q, t, x3, y3;
+  fe_sub(F, &pv, &u2, &b->x);
+  fe_sub(F, &r, &s2, &b->y);
+  fe_sqr(F, &pp, &pv);
+  fe_mul(F, &ppp, &pv, &pp);
+  fe_mul(F, &q, &b->x, &pp);
+  fe_sqr(F, &x3, &r);
+  fe_sub(F, &x3, &x3, &ppp);
+  fe_dbl(F, &t, &q);
+  fe_sub(F, &x3, &x3, &t);
+  fe_sub(F, &t, &q, &x3);
+  fe_mul(F, &y3, &r, &t);
+  fe_mul(F, &t, &b->y, &ppp);
+  fe_sub(F, &y3, &y3, &t);
+  b->x = x3;
+  b->y = y3;
+  fe_mul(F, &b->zz, &b->zz, &pp);
+  fe_mul(F, &b->zzz, &b->zzz, &ppp);
+}
+static void xyzz_neg(const orc_field_t* F, xyzz* b) { fe_neg(F, &b->y, &b->y); }
+/* msm.rs:172-183 bucket_to_curve: affine via two inversions; identity -> (0,0) */
+static void xyzz_to_affine(const orc_field_t* F, aff* out, const xyzz* b) {
+  if (xyzz_is_zero(b)) { memset(out, 0, sizeof(aff)); return; }
+  fe zi, zzi;
+  fe_inv(F, &zi, &b->zz);
+  fe_inv(F, &zzi, &b->zzz);
+  fe_mul(F, &out->x, &b->x, &zi);
+  fe_mul(F, &out->y, &b->y, &zzi);
+}
+static void aff_neg(const orc_field_t* F, aff* r, const aff* p) {
+  r->x = p->x;
+  fe_neg(F, &r->y, &p->y);
+}
+
+/* ------------------------------------------------------------------ curves ---------------- */
+typedef struct { const orc_field_t* base; const orc_field_t* scalar; } curve_t;
+static int get_curve(int id, curve_t* c) {
+  static const int base_of[4] = {1, 0, 2, 3}, scalar_of[4] = {0, 1, 3, 2};
+  if (id < 0 || id > 3) return 1;
+  c->base = &ORC_FIELDS[base_of[id]];
+  c->scalar = &ORC_FIELDS[scalar_of[id]];
+  return 0;
+}
+
+/* scalar helpers (msm.rs:191-211): operate on canonical little-endian limbs */
+static uint32_t num_bits4(const uint64_t* c) {
+  for (int i = 3; i >= 0; i--)
+    if (c[i]) return (uint32_t)(i * 64 + 64 - __builtin_clzll(c[i]));
+  return 0;
+}
+
+/* [k]P by double-and-add over canonical bits: the definition (msm.rs:422-429 `base * coeff`) */
+static void scalar_mul(const orc_field_t* F, xyzz* out, const aff* p, const uint64_t* k) {
+  xyzz acc;
+  xyzz_zero(F, &acc);
+  int nb = (int)num_bits4(k);
+  for (int i = nb - 1; i >= 0; i--) {
+    xyzz_double(F, &acc);
+    if ((k[i >> 6] >> (i & 63)) & 1) xyzz_add_affine(F, &acc, p);
+  }
+  *out = acc;
+}
+
+/* ------------------------------------------------------------------ threading ------------- */
+typedef void (*chunk_fn)(void* ctx, size_t lo, size_t hi, int tid);
+typedef struct { chunk_fn fn; void* ctx; size_t lo, hi; int tid; } job_t;
+static void* job_main(void* a) {
+  job_t* j = (job_t*)a;
+  j->fn(j->ctx, j->lo, j->hi, j->tid);
+  return NULL;
+}
+/* split [0,n) into nthreads contiguous chunks (rayon par_chunks shape, msm.rs:564-575) */
+static void par_chunks(size_t n, int nthreads, chunk_fn fn, void* ctx) {
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n) nthreads = n ? (int)n : 1;
+  if (nthreads == 1) { fn(ctx, 0, n, 0); return; }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  job_t* jobs = (job_t*)malloc(sizeof(job_t) * nthreads);
+  size_t chunk = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    size_t lo = (size_t)t * chunk, hi = lo + chunk;
+    if (lo > n) lo = n;
+    if (hi > n) hi = n;
+    jobs[t] = (job_t){fn, ctx, lo, hi, t};
+    pthread_create(&th[t], NULL, job_main, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+}
+
+/* ------------------------------------------------------------------ MSM pieces ------------ */
+typedef struct {
+  const orc_field_t* F;
+  const aff* bases;
+  const uint64_t* u64s;   /* integer scalars, or NULL */
+  const size_t* idx;      /* gather indices, or NULL */
+  int max_bits;
+  xyzz* partial;          /* one per thread */
+} small_ctx;
+
+/* msm.rs:432-454 accumulate_bases / msm.rs:505-530 msm_binary / msm.rs:689-708 batch_add */
+static void binary_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  small_ctx* c = (small_ctx*)vctx;
+  xyzz acc;
+  xyzz_zero(c->F, &acc);
+  for (size_t i = lo; i < hi; i++) {
+    if (c->u64s && c->u64s[i] == 0) continue;
+    xyzz_add_affine(c->F, &acc, &c->bases[c->idx ? c->idx[i] : i]);
+  }
+  c->partial[tid] = acc;
+}
+/* msm.rs:533-575 msm_10: one window, 2^bits buckets, suffix running sum */
+static void msm10_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  small_ctx* c = (small_ctx*)vctx;
+  size_t nb = (size_t)1 << c->max_bits;
+  xyzz* buckets = (xyzz*)malloc(sizeof(xyzz) * nb);
+  for (size_t b = 0; b < nb; b++) xyzz_zero(c->F, &buckets[b]);
+  for (size_t i = lo; i < hi; i++) {
+    uint64_t s = c->u64s[i];
+    if (s == 0) continue;
+    xyzz_add_affine(c->F, &buckets[s], &c->bases[i]);
+  }
+  xyzz result, running;
+  xyzz_zero(c->F, &result);
+  xyzz_zero(c->F, &running);
+  for (size_t b = nb - 1; b >= 1; b--) {
+    xyzz_add(c->F, &running, &buckets[b]);
+    xyzz_add(c->F, &result, &running);
+  }
+  free(buckets);
+  c->partial[tid] = result;
+}
+static size_t compute_ln(size_t a) { /* msm.rs:679-686 */
+  if (a == 0) return 0;
+  size_t lg = 63 - (size_t)__builtin_clzll((unsigned long long)a);
+  return lg * 69 / 100;
+}
+/* msm.rs:577-677 msm_small_rest (serial body) */
+static void small_rest_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  small_ctx* cx = (small_ctx*)vctx;
+  const orc_field_t* F = cx->F;
+  size_t len = hi - lo;
+  size_t c = len < 32 ? 3 : compute_ln(len) + 2;
+  if (cx->max_bits == 32 || cx->max_bits == 64) c = 8;
+  size_t nwin = ((size_t)cx->max_bits + c - 1) / c;
+  size_t nb = ((size_t)1 << c) - 1;
+  xyzz* buckets = (xyzz*)malloc(sizeof(xyzz) * nb);
+  xyzz* wsum = (xyzz*)malloc(sizeof(xyzz) * (nwin ? nwin : 1));
+  for (size_t w = 0; w < nwin; w++) {
+    size_t w_start = w * c;
+    xyzz res, running;
+    xyzz_zero(F, &res);
+    for (size_t b = 0; b < nb; b++) xyzz_zero(F, &buckets[b]);
+    for (size_t i = lo; i < hi; i++) {
+      uint64_t s = cx->u64s[i];
+      if (s == 0) continue;
+      if (s == 1) {
+        if (w_start == 0) xyzz_add_affine(F, &res, &cx->bases[i]); /* msm.rs:613-617 */
+      } else {
+        s >>= w_start;
+        s &= ((uint64_t)1 << c) - 1;
+        if (s != 0) xyzz_add_affine(F, &buckets[s - 1], &cx->bases[i]);
+      }
+    }
+    xyzz_zero(F, &running);
+    for (size_t b = nb; b-- > 0;) {
+      xyzz_add(F, &running, &buckets[b]);
+      xyzz_add(F, &res, &running);
+    }
+    wsum[w] = res;
+  }
+  /* msm.rs:647-661: lowest + fold(high -> low, c doublings each) */
+  xyzz total;
+  xyzz_zero(F, &total);
+  for (size_t w = nwin; w-- > 1;) {
+    xyzz_add(F, &total, &wsum[w]);
+    for (size_t d = 0; d < c; d++) xyzz_double(F, &total);
+  }
+  if (nwin) xyzz_add(F, &total, &wsum[0]);
+  free(buckets);
+  free(wsum);
+  cx->partial[tid] = total;
+}
+
+/* ---- halo2curves::msm::msm_best stand-in: full-width signed-digit Pippenger -------------- */
+typedef struct {
+  const orc_field_t* F;
+  const aff* bases;
+  const uint64_t* canon; /* n x 4 canonical limbs */
+  int c, nwin;
+  xyzz* partial;
+} best_ctx;
+static inline uint32_t get_window(const uint64_t* k, int bit, int c) {
+  int limb = bit >> 6, sh = bit & 63;
+  if (limb >= 4) return 0;
+  u128 two = k[limb];
+  if (limb + 1 < 4) two |= (u128)k[limb + 1] << 64;
+  return (uint32_t)((two >> sh) & (((u128)1 << c) - 1));
+}
+static void best_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  best_ctx* cx = (best_ctx*)vctx;
+  const orc_field_t* F = cx->F;
+  int c = cx->c;
+  size_t nb = (size_t)1 << (c - 1);
+  xyzz* buckets = (xyzz*)malloc(sizeof(xyzz) * nb);
+  uint8_t* carries = (uint8_t*)calloc(hi - lo ? hi - lo : 1, 1);
+  xyzz total;
+  xyzz_zero(F, &total);
+  xyzz* wsum = (xyzz*)malloc(sizeof(xyzz) * cx->nwin);
+  for (int w = 0; w < cx->nwin; w++) {
+    for (size_t b = 0; b < nb; b++) xyzz_zero(F, &buckets[b]);
+    for (size_t i = lo; i < hi; i++) {
+      uint32_t v = get_window(&cx->canon[4 * i], w * c, c) + carries[i - lo];
+      if (v > nb) { /* signed digit v - 2^c, carry to the next window */
+        uint32_t mag = ((uint32_t)1 << c) - v;
+        carries[i - lo] = 1;
+        if (mag) {
+          aff np;
+          aff_neg(F, &np, &cx->bases[i]);
+          xyzz_add_affine(F, &buckets[mag - 1], &np);
+        }
+      } else {
+        carries[i - lo] = 0;
+        if (v) xyzz_add_affine(F, &buckets[v - 1], &cx->bases[i]);
+      }
+    }
+    xyzz res, running;
+    xyzz_zero(F, &res);
+    xyzz_zero(F, &running);
+    for (size_t b = nb; b-- > 0;) {
+      xyzz_add(F, &running, &buckets[b]);
+      xyzz_add(F, &res, &running);
+    }
+    wsum[w] = res;
+  }
+  for (int w = cx->nwin - 1; w >= 0; w--) {
+    for (int d = 0; d < c; d++) xyzz_double(F, &total);
+    xyzz_add(F, &total, &wsum[w]);
+  }
+  free(buckets);
+  free(carries);
+  free(wsum);
+  cx->partial[tid] = total;
+}
+static void msm_best_canon(const curve_t* cv, const uint64_t* canon, const aff* bases, size_t n,
+                           int nthreads, xyzz* out) {
+  const orc_field_t* F = cv->base;
+  xyzz_zero(F, out);
+  if (n == 0) return;
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n) nthreads = (int)n;
+  size_t per = (n + nthreads - 1) / nthreads;
+  int c = per < 32 ? 3 : (int)compute_ln(per) + 2; /* ln(n)+2, the usual Pippenger window */
+  if (c > 16) c = 16;
+  best_ctx cx = {F, bases, canon, c, (cv->scalar->bits + 1 + c - 1) / c, NULL};
+  cx.partial = (xyzz*)malloc(sizeof(xyzz) * nthreads);
+  for (int t = 0; t < nthreads; t++) xyzz_zero(F, &cx.partial[t]);
+  par_chunks(n, nthreads, best_chunk, &cx);
+  for (int t = 0; t < nthreads; t++) xyzz_add(F, out, &cx.partial[t]);
+  free(cx.partial);
+}
+
+/* msm.rs:478-503 msm_small_with_max_num_bits on u64 scalars */
+static void msm_small_u64(const curve_t* cv, const uint64_t* s, const aff* bases, size_t n,
+                          int max_bits, int nthreads, xyzz* out) {
+  const orc_field_t* F = cv->base;
+  xyzz_zero(F, out);
+  if (n == 0 || max_bits == 0) return; /* msm.rs:487 */
+  if (max_bits > 32) {                 /* msm.rs:491-501: convert to field, msm_best */
+    uint64_t* canon = (uint64_t*)calloc(n * 4, 8);
+    for (size_t i = 0; i < n; i++) canon[4 * i] = s[i];
+    msm_best_canon(cv, canon, bases, n, nthreads, out);
+    free(canon);
+    return;
+  }
+  /* msm.rs:505-530 / 564-575 / 664-676: "if len > num_threads: chunks of len/num_threads" */
+  int nt = nthreads < 1 ? 1 : nthreads;
+  if (n <= (size_t)nt) nt = 1;
+  small_ctx cx = {F, bases, s, NULL, max_bits, NULL};
+  cx.partial = (xyzz*)malloc(sizeof(xyzz) * (nt + 1));
+  for (int t = 0; t <= nt; t++) xyzz_zero(F, &cx.partial[t]);
+  chunk_fn fn = max_bits == 1 ? binary_chunk : (max_bits <= 10 ? msm10_chunk : small_rest_chunk);
+  par_chunks(n, nt, fn, &cx);
+  for (int t = 0; t < nt; t++) xyzz_add(F, out, &cx.partial[t]);
+  free(cx.partial);
+}
+
+/* ------------------------------------------------------------------ exported API ---------- */
+#define EXPORT __attribute__((visibility("default")))
+
+EXPORT int orc_fe_op(int fid, int op, const void* a, const void* b, void* out, size_t n) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe *A = (const fe*)a, *B = (const fe*)b;
+  fe* R = (fe*)out;
+  for (size_t i = 0; i < n; i++) {
+    switch (op) {
+      case 0: fe_add(F, &R[i], &A[i], &B[i]); break;
+      case 1: fe_sub(F, &R[i], &A[i], &B[i]); break;
+      case 2: fe_mul(F, &R[i], &A[i], &B[i]); break;
+      case 3: fe_inv(F, &R[i], &A[i]); break;
+      case 4: fe_to_mont(F, &R[i], &A[i]); break;
+      case 5: fe_from_mont(F, &R[i], &A[i]); break;
+      case 6: fe_neg(F, &R[i], &A[i]); break;
+      default: return 1;
+    }
+  }
+  return 0;
+}
+
+/* Jacobian {x,y,z} (96 B, Montgomery) -> affine {x,y} (64 B), identity -> zeros.  Host-side
+ * normalisation helper for tests (group(p)/affine(), traits.rs:285-294). */
+EXPORT int orc_jacobian_to_affine(int curve, const void* jac, size_t n, void* out) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  const orc_field_t* F = cv.base;
+  const fe* J = (const fe*)jac;
+  aff* O = (aff*)out;
+  for (size_t i = 0; i < n; i++) {
+    const fe *X = &J[3 * i], *Y = &J[3 * i + 1], *Z = &J[3 * i + 2];
+    if (fe_is_zero(Z)) { memset(&O[i], 0, sizeof(aff)); continue; }
+    fe zi, zi2, zi3;
+    fe_inv(F, &zi, Z);
+    fe_sqr(F, &zi2, &zi);
+    fe_mul(F, &zi3, &zi2, &zi);
+    fe_mul(F, &O[i].x, X, &zi2);
+    fe_mul(F, &O[i].y, Y, &zi3);
+  }
+  return 0;
+}
+
+/* is (x,y) on y^2 = x^3 + b ?  b given as a Montgomery field element */
+EXPORT int orc_on_curve(int curve, const void* pt, const void* b_mont) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return -1;
+  const orc_field_t* F = cv.base;
+  const aff* p = (const aff*)pt;
+  if (aff_is_identity(p)) return 1;
+  fe l, r;
+  fe_sqr(F, &l, &p->y);
+  fe_sqr(F, &r, &p->x);
+  fe_mul(F, &r, &r, &p->x);
+  fe_add(F, &r, &r, (const fe*)b_mont);
+  return fe_eq(&l, &r);
+}
+
+/* naive definition: sum_i [s_i] P_i  (msm.rs:422-429) */
+typedef struct { const curve_t* cv; const fe* scalars; const aff* bases; xyzz* partial; } naive_ctx;
+static void naive_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  naive_ctx* c = (naive_ctx*)vctx;
+  xyzz acc, t;
+  xyzz_zero(c->cv->base, &acc);
+  for (size_t i = lo; i < hi; i++) {
+    fe k;
+    fe_from_mont(c->cv->scalar, &k, &c->scalars[i]);
+    scalar_mul(c->cv->base, &t, &c->bases[i], k.l);
+    xyzz_add(c->cv->base, &acc, &t);
+  }
+  c->partial[tid] = acc;
+}
+EXPORT int orc_msm_naive(int curve, const void* scalars, const void* bases, size_t n, int nthreads,
+                         void* out_affine) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  if (nthreads < 1) nthreads = 1;
+  naive_ctx cx = {&cv, (const fe*)scalars, (const aff*)bases, NULL};
+  cx.partial = (xyzz*)malloc(sizeof(xyzz) * nthreads);
+  for (int t = 0; t < nthreads; t++) xyzz_zero(cv.base, &cx.partial[t]);
+  par_chunks(n, nthreads, naive_chunk, &cx);
+  xyzz tot;
+  xyzz_zero(cv.base, &tot);
+  for (int t = 0; t < nthreads; t++) xyzz_add(cv.base, &tot, &cx.partial[t]);
+  free(cx.partial);
+  xyzz_to_affine(cv.base, (aff*)out_affine, &tot);
+  return 0;
+}
+
+/* the msm_best stand-in on Montgomery scalars */
+EXPORT int orc_msm_best(int curve, const void* scalars, const void* bases, size_t n, int nthreads,
+                        void* out_affine) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  uint64_t* canon = (uint64_t*)malloc((n ? n : 1) * 32);
+  for (size_t i = 0; i < n; i++) {
+    fe k;
+    fe_from_mont(cv.scalar, &k, &((const fe*)scalars)[i]);
+    memcpy(&canon[4 * i], k.l, 32);
+  }
+  xyzz tot;
+  msm_best_canon(&cv, canon, (const aff*)bases, n, nthreads, &tot);
+  free(canon);
+  xyzz_to_affine(cv.base, (aff*)out_affine, &tot);
+  return 0;
+}
+
+EXPORT int orc_msm_small(int curve, const uint64_t* scalars, const void* bases, size_t n,
+                         int max_bits, int nthreads, void* out_affine) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  if (max_bits < 0) { /* msm.rs:469-476 msm_small: bits of the maximum */
+    uint64_t mx = 0;
+    for (size_t i = 0; i < n; i++)
+      if (scalars[i] > mx) mx = scalars[i];
+    max_bits = mx ? 64 - __builtin_clzll(mx) : 0;
+  }
+  xyzz tot;
+  msm_small_u64(&cv, scalars, (const aff*)bases, n, max_bits, nthreads, &tot);
+  xyzz_to_affine(cv.base, (aff*)out_affine, &tot);
+  return 0;
+}
+
+EXPORT int orc_batch_add(int curve, const void* bases, const uint64_t* idx, size_t m, int nthreads,
+                         void* out_affine) { /* msm.rs:689-708 */
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  if (nthreads < 1) nthreads = 1;
+  size_t* ix = (size_t*)malloc((m ? m : 1) * sizeof(size_t));
+  for (size_t i = 0; i < m; i++) ix[i] = (size_t)idx[i];
+  small_ctx cx = {cv.base, (const aff*)bases, NULL, ix, 1, NULL};
+  cx.partial = (xyzz*)malloc(sizeof(xyzz) * nthreads);
+  for (int t = 0; t < nthreads; t++) xyzz_zero(cv.base, &cx.partial[t]);
+  par_chunks(m, nthreads, binary_chunk, &cx);
+  xyzz tot;
+  xyzz_zero(cv.base, &tot);
+  for (int t = 0; t < nthreads; t++) xyzz_add(cv.base, &tot, &cx.partial[t]);
+  free(cx.partial);
+  free(ix);
+  xyzz_to_affine(cv.base, (aff*)out_affine, &tot);
+  return 0;
+}
+
+/* msm.rs:225-419: the full dispatcher */
+typedef struct { uint64_t key; } cls_t;
+static int cls_cmp(const void* a, const void* b) {
+  uint8_t ga = (uint8_t)(((const cls_t*)a)->key >> 60), gb = (uint8_t)(((const cls_t*)b)->key >> 60);
+  return (int)ga - (int)gb;
+}
+EXPORT int orc_msm(int curve, const void* scalars_v, const void* bases_v, size_t n, int nthreads,
+                   void* out_affine) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  const orc_field_t *F = cv.base, *S = cv.scalar;
+  const fe* scalars = (const fe*)scalars_v;
+  const aff* bases = (const aff*)bases_v;
+  xyzz total;
+  xyzz_zero(F, &total);
+  if (n == 0) { memset(out_affine, 0, 64); return 0; }          /* msm.rs:228-230 */
+  if (n <= 16) return orc_msm_naive(curve, scalars_v, bases_v, n, 1, out_affine); /* :233 */
+  /* Phase 1: classify (msm.rs:243-279) */
+  cls_t* cls = (cls_t*)malloc(sizeof(cls_t) * n);
+  uint64_t* canon = (uint64_t*)malloc(n * 32);   /* canonical s        */
+  uint64_t* ncanon = (uint64_t*)malloc(n * 32);  /* canonical of (-s)  */
+  size_t m = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (fe_is_zero(&scalars[i]) || aff_is_identity(&bases[i])) continue; /* :247 */
+    fe s, ns, t;
+    fe_from_mont(S, &s, &scalars[i]);
+    fe_neg(S, &t, &scalars[i]);
+    fe_from_mont(S, &ns, &t);
+    memcpy(&canon[4 * i], s.l, 32);
+    memcpy(&ncanon[4 * i], ns.l, 32);
+    uint32_t bs = num_bits4(s.l), bn = num_bits4(ns.l);
+    uint8_t g = bs <= 1 ? 0 : bn <= 1 ? 1 : bs <= 8 ? 2 : bn <= 8 ? 3 : bs <= 16 ? 4 : bn <= 16 ? 5
+                : bs <= 32 ? 6 : bn <= 32 ? 7 : bs <= 64 ? 8 : bn <= 64 ? 9 : 10;
+    cls[m++].key = ((uint64_t)i & 0x0FFFFFFFFFFFFFFFull) | ((uint64_t)g << 60);
+  }
+  if (m == 0) { free(cls); free(canon); free(ncanon); memset(out_affine, 0, 64); return 0; }
+  /* Phase 2: sort by group, boundaries (msm.rs:287-301) */
+  qsort(cls, m, sizeof(cls_t), cls_cmp);
+  size_t bnd[12];
+  {
+    size_t pos = 0;
+    for (int g = 0; g < 11; g++) {
+      bnd[g] = pos;
+      while (pos < m && (uint8_t)(cls[pos].key >> 60) <= g) pos++;
+    }
+    bnd[11] = m;
+  }
+  /* Phase 3 (msm.rs:343-416) */
+  aff* gb = (aff*)malloc(sizeof(aff) * m);
+  uint64_t* gs = (uint64_t*)malloc(sizeof(uint64_t) * m);
+  xyzz part;
+  for (int g = 0; g < 10; g++) {
+    size_t lo = bnd[g], hi = bnd[g + 1];
+    if (lo >= hi) continue;
+    int negate = g & 1;
+    for (size_t k = lo; k < hi; k++) {
+      size_t idx = (size_t)(cls[k].key & 0x0FFFFFFFFFFFFFFFull);
+      gb[k - lo] = bases[idx];
+      gs[k - lo] = negate ? ncanon[4 * idx] : canon[4 * idx]; /* repr_low_u64, msm.rs:202-211 */
+    }
+    if (g < 2) { /* unit groups: accumulate_bases (msm.rs:346-356) */
+      small_ctx cx = {F, gb, NULL, NULL, 1, NULL};
+      int nt = nthreads < 1 ? 1 : nthreads;
+      cx.partial = (xyzz*)malloc(sizeof(xyzz) * nt);
+      for (int t = 0; t < nt; t++) xyzz_zero(F, &cx.partial[t]);
+      par_chunks(hi - lo, nt, binary_chunk, &cx);
+      xyzz_zero(F, &part);
+      for (int t = 0; t < nt; t++) xyzz_add(F, &part, &cx.partial[t]);
+      free(cx.partial);
+    } else {
+      static const int widths[5] = {0, 8, 16, 32, 64};
+      msm_small_u64(&cv, gs, gb, hi - lo, widths[g / 2], nthreads, &part); /* :362-396 */
+    }
+    if (negate) xyzz_neg(F, &part); /* pos - neg */
+    xyzz_add(F, &total, &part);
+  }
+  if (bnd[10] < bnd[11]) { /* large group -> msm_best (msm.rs:399-411) */
+    size_t lo = bnd[10], hi = bnd[11];
+    uint64_t* lc = (uint64_t*)malloc((hi - lo) * 32);
+    for (size_t k = lo; k < hi; k++) {
+      size_t idx = (size_t)(cls[k].key & 0x0FFFFFFFFFFFFFFFull);
+      gb[k - lo] = bases[idx];
+      memcpy(&lc[4 * (k - lo)], &canon[4 * idx], 32);
+    }
+    msm_best_canon(&cv, lc, gb, hi - lo, nthreads, &part);
+    xyzz_add(F, &total, &part);
+    free(lc);
+  }
+  free(cls); free(canon); free(ncanon); free(gb); free(gs);
+  xyzz_to_affine(F, (aff*)out_affine, &total);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ R1CS field vectors ---- */
+/* T = AZ o BZ - u*CZ - E1 (- E2)   r1cs/mod.rs:614-620, 650-657 */
+EXPORT int orc_cross_term(int fid, const void* az, const void* bz, const void* cz, const void* e1,
+                          const void* e2, const void* u, size_t n, void* t) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe *A = az, *B = bz, *C = cz, *E1 = e1, *E2 = e2, *U = u;
+  fe* T = (fe*)t;
+  for (size_t i = 0; i < n; i++) {
+    fe ab, uc, r;
+    fe_mul(F, &ab, &A[i], &B[i]);
+    fe_mul(F, &uc, U, &C[i]);
+    fe_sub(F, &r, &ab, &uc);
+    fe_sub(F, &r, &r, &E1[i]);
+    if (E2) fe_sub(F, &r, &r, &E2[i]);
+    T[i] = r;
+  }
+  return 0;
+}
+/* out = a + r*b   r1cs/mod.rs:1058-1069 (W fold, E fold) */
+EXPORT int orc_axpy(int fid, const void* a, const void* b, const void* r, size_t n, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe *A = a, *B = b, *Rr = r;
+  fe* O = (fe*)out;
+  for (size_t i = 0; i < n; i++) {
+    fe t;
+    fe_mul(F, &t, Rr, &B[i]);
+    fe_add(F, &O[i], &A[i], &t);
+  }
+  return 0;
+}
+EXPORT int orc_vec_add(int fid, const void* a, const void* b, size_t n, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  for (size_t i = 0; i < n; i++) fe_add(F, &((fe*)out)[i], &((const fe*)a)[i], &((const fe*)b)[i]);
+  return 0;
+}
+/* multilinear.rs:65-84 bind_poly_var_top: in place on the low half */
+EXPORT int orc_bind_top(int fid, void* z, size_t n, const void* r) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  fe* Z = (fe*)z;
+  size_t h = n / 2;
+  for (size_t i = 0; i < h; i++) {
+    fe d, t;
+    fe_sub(F, &d, &Z[i + h], &Z[i]);
+    fe_mul(F, &t, (const fe*)r, &d);
+    fe_add(F, &Z[i], &Z[i], &t);
+  }
+  return 0;
+}
+
+EXPORT int orc_field_from_u64(int fid, const uint64_t* v, size_t n, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  for (size_t i = 0; i < n; i++) fe_from_u64(&ORC_FIELDS[fid], &((fe*)out)[i], v[i]);
+  return 0;
+}

@@ -1,0 +1,364 @@
+"""Python big-integer oracle for the Nova prover hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this
+module; the product path (nova_b200/) never does.
+
+Everything here is a first-principles restatement (no halo2curves available: the crate
+`halo2curves = "0.9.0"`, Cargo.toml:38, is not vendored in /root/reference) of:
+
+  * the four prime fields named at  src/provider/bn256_grumpkin.rs:39-40,84-85 and
+    src/provider/pasta.rs:37-38,45-46  (moduli as hex literals there);
+  * `from_uniform` = 64-byte little-endian integer mod p  (src/provider/traits.rs:315-319,
+    pinned by src/provider/curve_property_tests.rs:40-72);
+  * `to_repr` / `to_bytes` = 32-byte little-endian canonical (src/provider/traits.rs:323-327);
+  * the short-Weierstrass a=0 group law for BN254 G1, Grumpkin, Pallas, Vesta;
+  * the Keccak256 Fiat-Shamir transcript (src/provider/keccak.rs:60-160), used ONLY to pin the
+    field code against the golden vectors at src/provider/keccak.rs:241-258.
+
+Parity status: PINNED for field encodings (keccak golden vectors, tests/test_oracle_golden.py),
+pinned structurally (MSM == naive sum, src/provider/msm.rs:722-821) for group results; the
+reference holds no literal commitment bytes.
+"""
+from __future__ import annotations
+
+# ----------------------------------------------------------------------------------------
+# Fields
+# ----------------------------------------------------------------------------------------
+BN254_FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+BN254_FQ = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+PALLAS_FP = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
+PALLAS_FQ = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
+
+# field ids used across the C ABI (include/nova_b200.h)
+FIELD_BN254_FR, FIELD_BN254_FQ, FIELD_PALLAS_FP, FIELD_PALLAS_FQ = 0, 1, 2, 3
+FIELD_MODULUS = {
+    FIELD_BN254_FR: BN254_FR,
+    FIELD_BN254_FQ: BN254_FQ,
+    FIELD_PALLAS_FP: PALLAS_FP,
+    FIELD_PALLAS_FQ: PALLAS_FQ,
+}
+FIELD_NAME = {0: "bn254_fr", 1: "bn254_fq", 2: "pallas_fp", 3: "pallas_fq"}
+
+R_BITS = 256
+R = 1 << R_BITS
+
+
+def from_uniform(p: int, b: bytes) -> int:
+    """src/provider/traits.rs:315-319 -> halo2curves `from_uniform_bytes`: LE integer mod p."""
+    assert len(b) == 64
+    return int.from_bytes(b, "little") % p
+
+
+def to_repr(x: int) -> bytes:
+    """32-byte little-endian canonical encoding (src/provider/traits.rs:323-327)."""
+    return int(x).to_bytes(32, "little")
+
+
+def to_mont(p: int, x: int) -> int:
+    return (x << R_BITS) % p
+
+
+def from_mont(p: int, x: int) -> int:
+    return (x * pow(R, -1, p)) % p
+
+
+def mont_bytes(p: int, x: int) -> bytes:
+    """In-memory layout of a halo2curves field element: 4 x u64 LE limbs, Montgomery R=2^256."""
+    return to_mont(p, x % p).to_bytes(32, "little")
+
+
+def from_mont_bytes(p: int, b: bytes) -> int:
+    return from_mont(p, int.from_bytes(b, "little"))
+
+
+# ----------------------------------------------------------------------------------------
+# Curves (all y^2 = x^3 + b, a = 0)
+# ----------------------------------------------------------------------------------------
+CURVE_BN254_G1, CURVE_GRUMPKIN, CURVE_PALLAS, CURVE_VESTA = 0, 1, 2, 3
+
+
+def _sqrt(p: int, a: int) -> int:
+    """Tonelli-Shanks."""
+    a %= p
+    if a == 0:
+        return 0
+    assert pow(a, (p - 1) // 2, p) == 1, "not a square"
+    if p % 4 == 3:
+        return pow(a, (p + 1) // 4, p)
+    q, s = p - 1, 0
+    while q % 2 == 0:
+        q //= 2
+        s += 1
+    z = 2
+    while pow(z, (p - 1) // 2, p) != p - 1:
+        z += 1
+    m, c, t, r = s, pow(z, q, p), pow(a, q, p), pow(a, (q + 1) // 2, p)
+    while t != 1:
+        i, t2 = 0, t
+        while t2 != 1:
+            t2 = t2 * t2 % p
+            i += 1
+        b = pow(c, 1 << (m - i - 1), p)
+        m, c, t, r = i, b * b % p, t * b * b % p, r * b % p
+    return r
+
+
+class Curve:
+    def __init__(self, cid, name, base_field, scalar_field, b, gen):
+        self.id = cid
+        self.name = name
+        self.base_field = base_field      # field id of coordinates
+        self.scalar_field = scalar_field  # field id of scalars
+        self.p = FIELD_MODULUS[base_field]
+        self.q = FIELD_MODULUS[scalar_field]
+        self.b = b % self.p
+        self.gen = gen
+        assert self.on_curve(gen)
+
+    def on_curve(self, P):
+        if P is None:
+            return True
+        x, y = P
+        return (y * y - x * x * x - self.b) % self.p == 0
+
+    # affine group law; None is the identity
+    def neg(self, P):
+        return None if P is None else (P[0], (-P[1]) % self.p)
+
+    def add(self, P, Q):
+        p = self.p
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        x1, y1 = P
+        x2, y2 = Q
+        if x1 == x2:
+            if (y1 + y2) % p == 0:
+                return None
+            lam = 3 * x1 * x1 * pow(2 * y1, -1, p) % p
+        else:
+            lam = (y2 - y1) * pow(x2 - x1, -1, p) % p
+        x3 = (lam * lam - x1 - x2) % p
+        return (x3, (lam * (x1 - x3) - y1) % p)
+
+    def mul(self, k, P):
+        k %= self.q
+        acc = None
+        add = P
+        while k:
+            if k & 1:
+                acc = self.add(acc, add)
+            add = self.add(add, add)
+            k >>= 1
+        return acc
+
+    def msm_naive(self, scalars, bases):
+        """Sum_i s_i * P_i  (src/provider/msm.rs:422-429 `msm_simple`, the definition)."""
+        acc = None
+        for s, P in zip(scalars, bases):
+            acc = self.add(acc, self.mul(s, P))
+        return acc
+
+    # --- fast Jacobian arithmetic for building large deterministic base sets --------------
+    def bases_arith(self, n, k0=0x5EED):
+        """P_i = [k0]G + i*G for i in 0..n (same construction as
+        src/provider/curve_property_tests.rs:186-194), batch-normalised."""
+        p = self.p
+        P0 = self.mul(k0, self.gen)
+        G = self.gen
+        # incremental affine adds with batched inversion in blocks
+        out = []
+        cur = P0
+        # simple: Jacobian accumulate then batch normalise
+        jac = []
+        X, Y, Z = cur[0], cur[1], 1
+        gx, gy = G
+        for _ in range(n):
+            jac.append((X, Y, Z))
+            # mixed add (X,Y,Z) + (gx,gy)
+            Z2 = Z * Z % p
+            U2 = gx * Z2 % p
+            S2 = gy * Z2 * Z % p
+            H = (U2 - X) % p
+            Rr = (S2 - Y) % p
+            if H == 0:
+                # doubling / inverse: fall back to affine
+                aff = self.add(self._jac_to_aff((X, Y, Z)), G)
+                X, Y, Z = (aff[0], aff[1], 1) if aff else (1, 1, 0)
+                continue
+            H2 = H * H % p
+            H3 = H2 * H % p
+            X3 = (Rr * Rr - H3 - 2 * X * H2) % p
+            Y3 = (Rr * (X * H2 - X3) - Y * H3) % p
+            Z3 = Z * H % p
+            X, Y, Z = X3, Y3, Z3
+        # batch inversion of Z's
+        zs = [j[2] for j in jac]
+        pref = [1] * (n + 1)
+        for i, z in enumerate(zs):
+            pref[i + 1] = pref[i] * z % p
+        inv = pow(pref[n], -1, p)
+        for i in range(n - 1, -1, -1):
+            zi = inv * pref[i] % p
+            inv = inv * zs[i] % p
+            zi2 = zi * zi % p
+            out.append((jac[i][0] * zi2 % p, jac[i][1] * zi2 * zi % p))
+        out.reverse()
+        return out
+
+    def _jac_to_aff(self, J):
+        X, Y, Z = J
+        if Z % self.p == 0:
+            return None
+        zi = pow(Z, -1, self.p)
+        return (X * zi * zi % self.p, Y * zi * zi * zi % self.p)
+
+    # --- boundary encodings ---------------------------------------------------------------
+    def affine_bytes(self, P) -> bytes:
+        """halo2curves affine {x,y} 64 B, Montgomery limbs; identity = zero coordinates."""
+        if P is None:
+            return bytes(64)
+        return mont_bytes(self.p, P[0]) + mont_bytes(self.p, P[1])
+
+    def affine_from_bytes(self, b: bytes):
+        x = from_mont_bytes(self.p, b[:32])
+        y = from_mont_bytes(self.p, b[32:64])
+        if x == 0 and y == 0:
+            return None
+        return (x, y)
+
+    def jacobian_from_bytes(self, b: bytes):
+        """{x,y,z} 96 B Jacobian Montgomery -> affine tuple / None."""
+        X = from_mont_bytes(self.p, b[:32])
+        Y = from_mont_bytes(self.p, b[32:64])
+        Z = from_mont_bytes(self.p, b[64:96])
+        return self._jac_to_aff((X, Y, Z))
+
+
+def _grumpkin_gen():
+    # y^2 = x^3 - 17 over BN254 Fr, generator x = 1 (halo2curves grumpkin); the root whose
+    # low hex digits are ...d823f272c (SURVEY.md §8 "field/curve facts").
+    y = _sqrt(BN254_FR, 1 - 17)
+    if (y & 0xFFF) != 0x72C:
+        y = BN254_FR - y
+    assert (y & 0xFFFFFFFFF) == 0xD823F272C
+    return (1, y)
+
+
+CURVES = {
+    CURVE_BN254_G1: Curve(CURVE_BN254_G1, "bn254_g1", FIELD_BN254_FQ, FIELD_BN254_FR, 3, (1, 2)),
+    CURVE_GRUMPKIN: Curve(CURVE_GRUMPKIN, "grumpkin", FIELD_BN254_FR, FIELD_BN254_FQ, -17, _grumpkin_gen()),
+    CURVE_PALLAS: Curve(CURVE_PALLAS, "pallas", FIELD_PALLAS_FP, FIELD_PALLAS_FQ, 5, (PALLAS_FP - 1, 2)),
+    CURVE_VESTA: Curve(CURVE_VESTA, "vesta", FIELD_PALLAS_FQ, FIELD_PALLAS_FP, 5, (PALLAS_FQ - 1, 2)),
+}
+
+# ----------------------------------------------------------------------------------------
+# Keccak-256 (original Keccak padding 0x01, not SHA3's 0x06) + Nova transcript
+# ----------------------------------------------------------------------------------------
+_RC = [
+    0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000,
+    0x000000000000808B, 0x0000000080000001, 0x8000000080008081, 0x8000000000008009,
+    0x000000000000008A, 0x0000000000000088, 0x0000000080008009, 0x000000008000000A,
+    0x000000008000808B, 0x800000000000008B, 0x8000000000008089, 0x8000000000008003,
+    0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+    0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008,
+]
+_ROT = [
+    [0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14],
+]
+_M64 = (1 << 64) - 1
+
+
+def _rol(x, n):
+    n %= 64
+    return ((x << n) | (x >> (64 - n))) & _M64 if n else x
+
+
+def _keccak_f(A):
+    for rc in _RC:
+        C = [A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4] for x in range(5)]
+        D = [C[(x - 1) % 5] ^ _rol(C[(x + 1) % 5], 1) for x in range(5)]
+        A = [[A[x][y] ^ D[x] for y in range(5)] for x in range(5)]
+        B = [[0] * 5 for _ in range(5)]
+        for x in range(5):
+            for y in range(5):
+                B[y][(2 * x + 3 * y) % 5] = _rol(A[x][y], _ROT[x][y])
+        A = [[B[x][y] ^ ((~B[(x + 1) % 5][y]) & B[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+        A[0][0] ^= rc
+    return A
+
+
+def keccak256(data: bytes) -> bytes:
+    rate = 136
+    msg = bytearray(data)
+    msg.append(0x01)
+    while len(msg) % rate:
+        msg.append(0)
+    msg[-1] |= 0x80
+    A = [[0] * 5 for _ in range(5)]
+    for off in range(0, len(msg), rate):
+        blk = msg[off:off + rate]
+        for i in range(rate // 8):
+            x, y = i % 5, i // 5
+            A[x][y] ^= int.from_bytes(blk[8 * i:8 * i + 8], "little")
+        A = _keccak_f(A)
+    out = b""
+    for i in range(4):
+        x, y = i % 5, i // 5
+        out += A[x][y].to_bytes(8, "little")
+    return out
+
+
+class Keccak256Transcript:
+    """Non-EVM variant of src/provider/keccak.rs:98-160."""
+
+    def __init__(self, p: int, label: bytes):
+        self.p = p
+        self.round = 0
+        self.buf = b""
+        self.state = self._updated_state(b"", b"NoTR" + label)
+
+    @staticmethod
+    def _updated_state(buf: bytes, inp: bytes) -> bytes:
+        # keccak.rs:66-95: H(buf || inp || 0) || H(buf || inp || 1)
+        return keccak256(buf + inp + b"\x00") + keccak256(buf + inp + b"\x01")
+
+    def absorb_bytes(self, label: bytes, repr_: bytes):
+        self.buf += label + repr_
+
+    def absorb_scalar(self, label: bytes, x: int):
+        self.absorb_bytes(label, to_repr(x % self.p))
+
+    def squeeze(self, label: bytes) -> int:
+        inp = b"NoDS" + self.round.to_bytes(8, "little") + self.state + label
+        out = self._updated_state(self.buf, inp)
+        self.round += 1
+        self.state = out
+        self.buf = b""
+        return from_uniform(self.p, out)
+
+
+# ----------------------------------------------------------------------------------------
+# Deterministic PRNG shared by every harness (SplitMix64) -- OUR generator, not halo2curves'
+# ----------------------------------------------------------------------------------------
+class SplitMix64:
+    def __init__(self, seed: int):
+        self.s = seed & _M64
+
+    def next(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _M64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+        return z ^ (z >> 31)
+
+    def bytes(self, n: int) -> bytes:
+        out = b""
+        while len(out) < n:
+            out += self.next().to_bytes(8, "little")
+        return out[:n]
+
+    def field(self, p: int) -> int:
+        """uniform via the from_uniform rule (64 bytes reduced mod p)."""
+        return from_uniform(p, self.bytes(64))

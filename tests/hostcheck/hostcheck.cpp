@@ -1,0 +1,69 @@
+// Host-side build of the device field/curve templates (the non-__CUDA_ARCH__ branches of
+// nova_b200/csrc/field.cuh emulate every PTX carry chain bit-exactly).  Test-only: lets the
+// CPU test-suite validate the Montgomery/XYZZ algorithm structure without a GPU.
+#include <cstring>
+#include "../../nova_b200/csrc/curve.cuh"
+using namespace nova;
+
+template <class F>
+static void fe_op(int op, const fe_t& a, const fe_t& b, fe_t& r) {
+  switch (op) {
+    case 0: r = fe_add<F>(a, b); break;
+    case 1: r = fe_sub<F>(a, b); break;
+    case 2: r = fe_mul<F>(a, b); break;
+    case 3: r = fe_inv<F>(a); break;
+    case 4: r = fe_to_mont<F>(a); break;
+    case 5: r = fe_from_mont<F>(a); break;
+    case 6: r = fe_neg<F>(a); break;
+  }
+}
+
+// sum of n affine points via madd (mode 0), or via pairwise xyzz_add of singletons (mode 1),
+// or [k]P via xyzz_mul_small of point 0 with k = n (mode 2) -> Jacobian 96 B
+template <class F>
+static void pt_sum(int mode, const affine_t* pts, size_t n, fe_t* out) {
+  xyzz_t acc = xyzz_identity<F>();
+  if (mode == 0) {
+    for (size_t i = 0; i < n; i++)
+      if (!affine_is_identity(pts[i])) xyzz_madd<F>(acc, pts[i].x, pts[i].y);
+  } else if (mode == 1) {
+    for (size_t i = 0; i < n; i++) {
+      xyzz_t q = xyzz_identity<F>();
+      if (!affine_is_identity(pts[i])) xyzz_madd<F>(q, pts[i].x, pts[i].y);
+      xyzz_add<F>(acc, q);
+    }
+  } else {
+    xyzz_t q = xyzz_identity<F>();
+    if (!affine_is_identity(pts[0])) xyzz_madd<F>(q, pts[0].x, pts[0].y);
+    acc = xyzz_mul_small<F>(q, (uint32_t)n);
+  }
+  xyzz_to_jacobian<F>(acc, out[0], out[1], out[2]);
+}
+
+extern "C" {
+int hc_fe_op(int fid, int op, const void* a, const void* b, void* out, size_t n) {
+  const fe_t* A = (const fe_t*)a;
+  const fe_t* B = (const fe_t*)b;
+  fe_t* R = (fe_t*)out;
+  for (size_t i = 0; i < n; i++) {
+    switch (fid) {
+      case 0: fe_op<BN254_FR>(op, A[i], B[i], R[i]); break;
+      case 1: fe_op<BN254_FQ>(op, A[i], B[i], R[i]); break;
+      case 2: fe_op<PALLAS_FP>(op, A[i], B[i], R[i]); break;
+      case 3: fe_op<PALLAS_FQ>(op, A[i], B[i], R[i]); break;
+      default: return 1;
+    }
+  }
+  return 0;
+}
+int hc_pt_sum(int fid, int mode, const void* pts, size_t n, void* out) {
+  switch (fid) {
+    case 0: pt_sum<BN254_FR>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 1: pt_sum<BN254_FQ>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 2: pt_sum<PALLAS_FP>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 3: pt_sum<PALLAS_FQ>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    default: return 1;
+  }
+  return 0;
+}
+}
