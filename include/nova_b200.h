@@ -66,9 +66,10 @@ int b200_sync(void);
 /* ---- commitment keys -------------------------------------------------------------------
  * Replaces holding `CommitmentKey{ck: Vec<Affine>, h}` (pedersen.rs:32-38, hyperkzg.rs:76-84) on
  * the host only: the bases are uploaded ONCE, expanded into the 2^(c*t)*P window tables, and stay
- * resident.  window_bits = 0 picks c from n.  Keys are immutable after registration. */
-int b200_ck_register(int curve_id, const void* bases_affine_mont, size_t n, int window_bits,
-                     uint64_t* ck_handle);
+ * resident.  `h` is the blinding generator (CommitmentKey.h); NULL if the caller never blinds.
+ * window_bits = 0 picks c from n.  Keys are immutable after registration. */
+int b200_ck_register(int curve_id, const void* bases_affine_mont, size_t n,
+                     const void* h_affine_mont_or_null, int window_bits, uint64_t* ck_handle);
 int b200_ck_release(uint64_t ck_handle);
 int b200_ck_len(uint64_t ck_handle, size_t* n, int* window_bits, int* num_tables);
 
@@ -80,6 +81,11 @@ int b200_msm(uint64_t ck_handle, size_t base_offset, const void* scalars_mont, s
              void* out_jacobian_mont);
 int b200_msm_dev(uint64_t ck_handle, size_t base_offset, const void* d_scalars_mont, size_t n,
                  void* d_out_jacobian_mont, void* stream);
+/* CommitmentEngineTrait::commit(ck, v, r) = MSM(v, ck[..n]) + r*h in ONE pass
+ * (pedersen.rs:263-270, hyperkzg.rs:584-591).  r_or_null == NULL means r = 0 (benches/commit.rs:30).
+ * Needs a key registered with h unless r is NULL. */
+int b200_commit(uint64_t ck_handle, const void* scalars_mont, size_t n, const void* r_mont_or_null,
+                void* out_jacobian_mont);
 /* k MSMs over prefixes of the same key: vector j uses ck[..lens[j]] (traits.rs:82-90,
  * blitzar.rs:23-40, hyperkzg.rs:594-612 batch_commit).  out = k x 96 B. */
 int b200_msm_batch(uint64_t ck_handle, const void* const* scalars_mont, const size_t* lens,

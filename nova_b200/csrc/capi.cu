@@ -102,7 +102,9 @@ struct workspace {
 struct ck_ctx {
   std::mutex mu;
   int curve = 0;
-  size_t n = 0;
+  size_t n = 0;       // usable bases
+  size_t stride = 0;  // points per table = n (+1 when the blinding generator h is present)
+  bool has_h = false;
   int c = 0, W = 0, F = 0, G = 0;
   uint32_t B = 0;
   int m = 4;
@@ -147,7 +149,9 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
     w.out_slots = out_slots;
   }
   if (n <= w.cap_n) return B200_OK;
-  // grow: release the size-dependent buffers and reallocate
+  // grow: release the size-dependent buffers and reallocate (after draining any asynchronous
+  // *_dev work that may still be using them)
+  CU(cudaDeviceSynchronize());
   void** szbufs[] = {&w.scalars, (void**)&w.digits, (void**)&w.entries, &w.parts, (void**)&w.pkeys,
                      (void**)&w.heavy};
   for (void** p : szbufs)
@@ -181,8 +185,10 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
 msm_plan make_plan(ck_ctx& ck, size_t base_offset, size_t n) {
   msm_plan p;
   p.n = n;
-  p.n_ck = ck.n;
+  p.n_ck = ck.stride;
   p.base_offset = base_offset;
+  p.blind_i = SIZE_MAX;
+  p.h_index = ck.n;
   p.c = ck.c;
   p.W = ck.W;
   p.G = ck.G;
@@ -207,7 +213,8 @@ msm_plan make_plan(ck_ctx& ck, size_t base_offset, size_t n) {
 
 // enqueue one full-width MSM on `s`; scalars and out are device pointers
 int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
-                cudaStream_t s, int small_elem_bytes = 0) {
+                cudaStream_t s, int small_elem_bytes = 0, bool blinded = false) {
+  // blinded: d_scalars holds n-1 vector entries followed by r, whose base is h
   if (n == 0) {  // identity (msm.rs:228-230): z = 0
     CU(cudaMemsetAsync(d_out, 0, 96, s));
     return B200_OK;
@@ -215,6 +222,7 @@ int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n,
   const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
   const field_ops* bops = ops_for_field(CURVES[ck.curve].base_fid);
   msm_plan p = make_plan(ck, base_offset, n);
+  if (blinded) p.blind_i = n - 1;
   size_t K = (size_t)ck.G * ck.B;
   CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
   CU(cudaMemsetAsync(p.heavy, 0, 4, s));
@@ -239,8 +247,8 @@ int choose_window(size_t n) {
   return c;
 }
 
-int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n, int window_bits,
-                 bool expand, std::shared_ptr<ck_ctx>& out) {
+int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n, const void* h,
+                 int window_bits, bool expand, std::shared_ptr<ck_ctx>& out) {
   if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
   if (bases == nullptr || n == 0) return fail(B200_E_ARG, "empty commitment key");
   if (window_bits != 0 && (window_bits < 2 || window_bits > 24))
@@ -248,6 +256,8 @@ int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n
   auto ck = std::make_shared<ck_ctx>();
   ck->curve = curve_id;
   ck->n = n;
+  ck->has_h = h != nullptr;
+  ck->stride = n + (h ? 1 : 0);
   ck->c = window_bits ? window_bits : choose_window(n);
   int bits = FIELD_BITS[CURVES[curve_id].scalar_fid];
   ck->W = (bits + ck->c - 1) / ck->c;
@@ -255,15 +265,17 @@ int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n
   ck->G = expand ? 1 : ck->W;
   ck->B = 1u << (ck->c - 1);
   ck->m = ck->B >= 4 ? 4 : 1;
-  if ((size_t)ck->F * n >= ((size_t)1 << 31))
+  if ((size_t)ck->F * ck->stride >= ((size_t)1 << 31))
     return fail(B200_E_RANGE, "key too large for 31-bit table indices (%zu x %d)", n, ck->F);
-  CU(cudaMalloc(&ck->tables, (size_t)ck->F * n * 64));
+  CU(cudaMalloc(&ck->tables, (size_t)ck->F * ck->stride * 64));
   CU(cudaMemcpyAsync(ck->tables, bases, n * 64,
                      bases_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                      g_dev.stream));
+  if (h)
+    CU(cudaMemcpyAsync((char*)ck->tables + n * 64, h, 64, cudaMemcpyHostToDevice, g_dev.stream));
   if (ck->F > 1) {
     const field_ops* bops = ops_for_field(CURVES[curve_id].base_fid);
-    bops->expand_key(g_dev.stream, ck->tables, n, ck->F, ck->c * ck->G);
+    bops->expand_key(g_dev.stream, ck->tables, ck->stride, ck->F, ck->c * ck->G);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(g_dev.stream));
@@ -360,12 +372,13 @@ int b200_sync(void) {
 }
 
 // ---- keys -------------------------------------------------------------------------------------
-int b200_ck_register(int curve_id, const void* bases, size_t n, int window_bits, uint64_t* handle) {
+int b200_ck_register(int curve_id, const void* bases, size_t n, const void* h, int window_bits,
+                     uint64_t* handle) {
   int rc = ensure_init();
   if (rc) return rc;
   if (!handle) return fail(B200_E_ARG, "null handle pointer");
   std::shared_ptr<ck_ctx> ck;
-  rc = register_key(curve_id, bases, false, n, window_bits, true, ck);
+  rc = register_key(curve_id, bases, false, n, h, window_bits, true, ck);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_handles_mu);
   *handle = g_next_handle++;
@@ -398,13 +411,17 @@ int b200_ck_len(uint64_t handle, size_t* n, int* window_bits, int* num_tables) {
 }
 
 // ---- MSM --------------------------------------------------------------------------------------
-static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t n, void* out) {
+static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t n, void* out,
+                    const void* blind = nullptr) {
   std::lock_guard<std::mutex> lk(ck.mu);
-  int rc = ensure_workspace(ck, n ? n : 1, 1);
+  int rc = ensure_workspace(ck, n + 1, 1);
   if (rc) return rc;
   cudaStream_t s = g_dev.stream;
   if (n) CU(cudaMemcpyAsync(ck.ws.scalars, scalars, n * 32, cudaMemcpyHostToDevice, s));
-  rc = enqueue_msm(ck, base_offset, ck.ws.scalars, n, ck.ws.d_out, s);
+  if (blind)
+    CU(cudaMemcpyAsync((char*)ck.ws.scalars + n * 32, blind, 32, cudaMemcpyHostToDevice, s));
+  rc = enqueue_msm(ck, base_offset, ck.ws.scalars, n + (blind ? 1 : 0), ck.ws.d_out, s, 0,
+                   blind != nullptr);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ck.ws.h_out, ck.ws.d_out, 96, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -422,6 +439,18 @@ int b200_msm(uint64_t handle, size_t base_offset, const void* scalars, size_t n,
     return fail(B200_E_RANGE, "msm slice [%zu, %zu) exceeds key length %zu", base_offset,
                 base_offset + n, ck->n);
   return msm_host(*ck, base_offset, scalars, n, out);
+}
+
+int b200_commit(uint64_t handle, const void* scalars, size_t n, const void* r, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (!out || (n && !scalars)) return fail(B200_E_ARG, "null pointer");
+  if (n > ck->n)  // pedersen.rs:264 assert!(ck.ck.len() >= v.len())
+    return fail(B200_E_RANGE, "commit of %zu scalars exceeds key length %zu", n, ck->n);
+  if (r && !ck->has_h) return fail(B200_E_ARG, "key was registered without a blinding generator");
+  return msm_host(*ck, 0, scalars, n, out, r);
 }
 
 int b200_msm_dev(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
@@ -543,7 +572,7 @@ int b200_msm_adhoc(int curve_id, const void* bases, const void* scalars, size_t 
   }
   if (!bases || !scalars) return fail(B200_E_ARG, "null pointer");
   std::shared_ptr<ck_ctx> ck;
-  rc = register_key(curve_id, bases, false, n, 0, /*expand=*/false, ck);
+  rc = register_key(curve_id, bases, false, n, nullptr, 0, /*expand=*/false, ck);
   if (rc) return rc;
   return msm_host(*ck, 0, scalars, n, out);
 }

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256) k_digits_small(const void* __restrict__ s
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ digits, size_t n,
                                                  int W, int G, uint32_t B, size_t n_ck,
-                                                 size_t base_offset, uint32_t* __restrict__ cursor,
+                                                 size_t base_offset, size_t blind_i, size_t h_index,
+                                                 uint32_t* __restrict__ cursor,
                                                  uint64_t* __restrict__ entries) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int w = blockIdx.y;
@@ -161,7 +162,9 @@ __global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ dig
   uint32_t sign = dgt < 0 ? 1u : 0u;
   uint32_t mag = sign ? (uint32_t)(-dgt) : (uint32_t)dgt;
   uint32_t key = (uint32_t)(w % G) * B + (mag - 1);
-  uint32_t idx = (uint32_t)((size_t)(w / G) * n_ck + base_offset + i);
+  // the blinding scalar r rides along as one more (scalar, base) pair whose base is h
+  size_t bi = (i == blind_i) ? h_index : base_offset + i;
+  uint32_t idx = (uint32_t)((size_t)(w / G) * n_ck + bi);
   uint32_t pos = atomicAdd(&cursor[key], 1u);
   entries[pos] = ((uint64_t)key << 32) | ((uint64_t)sign << 31) | idx;
 }
@@ -183,7 +186,8 @@ void msm_digits_small(cudaStream_t s, const void* scalars, int elem_bytes, const
 
 void msm_scatter(cudaStream_t s, const msm_plan& p) {
   dim3 grid((unsigned)((p.n + 255) / 256), (unsigned)p.W);
-  k_scatter<<<grid, 256, 0, s>>>(p.digits, p.n, p.W, p.G, p.B, p.n_ck, p.base_offset, p.cursor,
+  k_scatter<<<grid, 256, 0, s>>>(p.digits, p.n, p.W, p.G, p.B, p.n_ck, p.base_offset, p.blind_i,
+                                 p.h_index, p.cursor,
                                  p.entries);
 }
 

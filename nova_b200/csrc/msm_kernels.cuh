@@ -34,6 +34,8 @@ struct msm_plan {
   size_t n;            // scalars in this call
   size_t n_ck;         // points per table in the registered key
   size_t base_offset;  // first key point used
+  size_t blind_i;      // scalar index whose base is the blinding generator h (SIZE_MAX: none)
+  size_t h_index;      // position of h inside each table
   int c;               // window bits
   int W;               // number of windows = F*G
   int G;               // bucket groups

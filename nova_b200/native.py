@@ -1,0 +1,81 @@
+"""ctypes loader for libnova_b200.so.  Fails loudly -- there is no fallback path."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_size_t, c_int, c_void_p, c_u64 = ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"nova_b200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libnova_b200.so")
+
+
+# every symbol include/nova_b200.h declares: name -> argtypes (all return int unless noted)
+_P = c_void_p
+SIGNATURES = {
+    "b200_init": [c_int],
+    "b200_device_count": [ctypes.POINTER(c_int)],
+    "b200_host_alloc": [c_size_t, ctypes.POINTER(_P)],
+    "b200_host_free": [_P],
+    "b200_dev_alloc": [c_size_t, ctypes.POINTER(_P)],
+    "b200_dev_free": [_P],
+    "b200_memcpy_h2d": [_P, _P, c_size_t],
+    "b200_memcpy_d2h": [_P, _P, c_size_t],
+    "b200_sync": [],
+    "b200_ck_register": [c_int, _P, c_size_t, _P, c_int, ctypes.POINTER(c_u64)],
+    "b200_ck_release": [c_u64],
+    "b200_ck_len": [c_u64, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
+    "b200_msm": [c_u64, c_size_t, _P, c_size_t, _P],
+    "b200_msm_dev": [c_u64, c_size_t, _P, c_size_t, _P, _P],
+    "b200_commit": [c_u64, _P, c_size_t, _P, _P],
+    "b200_msm_batch": [c_u64, ctypes.POINTER(_P), ctypes.POINTER(c_size_t), c_size_t, _P],
+    "b200_msm_small": [c_u64, c_size_t, _P, c_int, c_size_t, c_int, _P],
+    "b200_msm_indices": [c_u64, ctypes.POINTER(c_u64), c_size_t, _P],
+    "b200_msm_adhoc": [c_int, _P, _P, c_size_t, _P],
+    "b200_cross_term": [c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P],
+    "b200_axpy": [c_int, _P, _P, _P, c_size_t, _P],
+    "b200_vec_add": [c_int, _P, _P, c_size_t, _P],
+    "b200_bind_top": [c_int, _P, c_size_t, _P],
+    "b200_cross_term_dev": [c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P],
+    "b200_axpy_dev": [c_int, _P, _P, _P, c_size_t, _P, _P],
+    "b200_vec_add_dev": [c_int, _P, _P, c_size_t, _P, _P],
+    "b200_bind_top_dev": [c_int, _P, c_size_t, _P, _P],
+}
+STRING_FUNCS = ["b200_last_error", "b200_version"]
+
+
+def lib():
+    """Load the C-ABI library (does not touch the GPU)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C nova_b200/csrc`.  nova_b200 has no CPU fallback."
+            )
+        L = ctypes.CDLL(path)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        for name in STRING_FUNCS:
+            getattr(L, name).restype = ctypes.c_char_p
+            getattr(L, name).argtypes = []
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B200Error(rc, lib().b200_last_error().decode())

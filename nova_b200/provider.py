@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference's provider surface for the hot path.
+
+Names follow the reference so the parity tests read like its own tests:
+
+  DlogGroup.vartime_multiscalar_mul / batch_vartime_multiscalar_mul /
+  vartime_multiscalar_mul_small(_with_max_num_bits)        src/provider/traits.rs:77-117
+  CommitmentEngine.commit / batch_commit / commit_small / commit_sparse_binary
+                                                           src/provider/pedersen.rs:263-427,
+                                                           src/provider/hyperkzg.rs:584-783
+  cross_term (commit_T's T), fold_witness                   src/r1cs/mod.rs:578-664, 1044-1107
+  bind_poly_var_top                                         src/spartan/polys/multilinear.rs:65-84
+
+Vectors cross this layer as raw bytes in the FFI layout (32 B Montgomery field elements,
+64 B affine points); group results come back as affine (x, y) integer tuples or None for the
+identity -- the single Jacobian->affine normalisation per result is done here with Python
+integers (it is O(1) per call, the reference does it in `affine()`, traits.rs:285-289).
+Length mismatches raise AssertionError like the reference's `assert_eq!` (msm.rs:226).
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+
+from . import fields
+from .native import c_size_t, c_u64, check, lib
+
+
+class Curve(enum.IntEnum):
+    BN254_G1 = 0
+    GRUMPKIN = 1
+    PALLAS = 2
+    VESTA = 3
+
+    @property
+    def base_field(self) -> int:
+        return (fields.BN254_FQ, fields.BN254_FR, fields.PALLAS_FP, fields.PALLAS_FQ)[int(self)]
+
+    @property
+    def scalar_field(self) -> int:
+        return (fields.BN254_FR, fields.BN254_FQ, fields.PALLAS_FQ, fields.PALLAS_FP)[int(self)]
+
+
+def _cbuf(b):
+    if b is None:
+        return None
+    return (ctypes.c_char * len(b)).from_buffer_copy(b) if len(b) else (ctypes.c_char * 1)()
+
+
+def _jac_to_affine(curve: Curve, jac: bytes):
+    fid = curve.base_field
+    p = fields.MODULUS[fid]
+    x, y, z = (fields.from_mont_bytes(fid, jac[i:i + 32]) for i in (0, 32, 64))
+    if z == 0:
+        return None
+    zi = pow(z, -1, p)
+    return (x * zi * zi % p, y * zi * zi * zi % p)
+
+
+class CommitmentKey:
+    """Device-resident `CommitmentKey{ck, h}` (pedersen.rs:32-38 / hyperkzg.rs:76-84)."""
+
+    def __init__(self, curve: Curve, bases: bytes, h: bytes | None = None, window_bits: int = 0):
+        assert len(bases) % 64 == 0 and len(bases) > 0
+        self.curve = Curve(curve)
+        self.n = len(bases) // 64
+        handle = c_u64(0)
+        check(lib().b200_ck_register(int(curve), _cbuf(bases), self.n, _cbuf(h) if h else None,
+                                     window_bits, ctypes.byref(handle)))
+        self.handle = handle.value
+        self.has_h = h is not None
+
+    def __len__(self):
+        return self.n
+
+    def release(self):
+        if self.handle:
+            check(lib().b200_ck_release(self.handle))
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class DlogGroup:
+    """`DlogGroupExt` for one curve (src/provider/traits.rs:77-117)."""
+
+    def __init__(self, curve: Curve):
+        self.curve = Curve(curve)
+
+    def vartime_multiscalar_mul(self, scalars: bytes, bases) -> tuple | None:
+        """msm(scalars, bases) (msm.rs:225).  `bases` is a CommitmentKey (uses ck[..n]) or raw
+        affine bytes (one-shot key, pedersen.rs:418-420)."""
+        n = len(scalars) // 32
+        out = ctypes.create_string_buffer(96)
+        if isinstance(bases, CommitmentKey):
+            assert n <= len(bases), "scalars and bases length mismatch"
+            check(lib().b200_msm(bases.handle, 0, _cbuf(scalars), n, out))
+        else:
+            assert len(bases) == 64 * n, "scalars and bases length mismatch"  # msm.rs:226
+            check(lib().b200_msm_adhoc(int(self.curve), _cbuf(bases), _cbuf(scalars), n, out))
+        return _jac_to_affine(self.curve, out.raw)
+
+    def batch_vartime_multiscalar_mul(self, scalars: list, ck: CommitmentKey) -> list:
+        """traits.rs:82-90: vector k uses bases[..len(scalars[k])]."""
+        k = len(scalars)
+        bufs = [_cbuf(s) for s in scalars]
+        ptrs = (ctypes.c_void_p * max(k, 1))(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+        lens = (c_size_t * max(k, 1))(*[len(s) // 32 for s in scalars])
+        out = ctypes.create_string_buffer(96 * max(k, 1))
+        check(lib().b200_msm_batch(ck.handle, ptrs, lens, k, out))
+        return [_jac_to_affine(self.curve, out.raw[96 * j:96 * j + 96]) for j in range(k)]
+
+    def vartime_multiscalar_mul_small(self, scalars, ck: CommitmentKey, elem_bytes: int = 8,
+                                      max_num_bits: int = 0):
+        """msm_small / msm_small_with_max_num_bits (msm.rs:469-503) on integer scalars."""
+        n = len(scalars)
+        assert n <= len(ck)
+        raw = b"".join(int(s).to_bytes(elem_bytes, "little") for s in scalars)
+        out = ctypes.create_string_buffer(96)
+        check(lib().b200_msm_small(ck.handle, 0, _cbuf(raw), elem_bytes, n, max_num_bits, out))
+        return _jac_to_affine(self.curve, out.raw)
+
+    def batch_add(self, ck: CommitmentKey, one_indices) -> tuple | None:
+        """msm.rs:689-708."""
+        m = len(one_indices)
+        idx = (c_u64 * max(m, 1))(*one_indices)
+        out = ctypes.create_string_buffer(96)
+        check(lib().b200_msm_indices(ck.handle, idx, m, out))
+        return _jac_to_affine(self.curve, out.raw)
+
+
+class CommitmentEngine:
+    """`CommitmentEngineTrait` for Pedersen / HyperKZG commitments (same MSM + r*h shape:
+    pedersen.rs:263-270, hyperkzg.rs:584-591)."""
+
+    def __init__(self, curve: Curve):
+        self.curve = Curve(curve)
+        self.group = DlogGroup(curve)
+
+    def commit(self, ck: CommitmentKey, v: bytes, r: bytes | None = None):
+        n = len(v) // 32
+        assert len(ck) >= n  # pedersen.rs:264
+        out = ctypes.create_string_buffer(96)
+        check(lib().b200_commit(ck.handle, _cbuf(v), n, _cbuf(r) if r else None, out))
+        return _jac_to_affine(self.curve, out.raw)
+
+    def batch_commit(self, ck: CommitmentKey, vs: list):
+        """traits/commitment.rs:94-104 default / hyperkzg.rs:594-612 with r = 0."""
+        return self.group.batch_vartime_multiscalar_mul(vs, ck)
+
+    def commit_small(self, ck: CommitmentKey, v, elem_bytes: int = 8):
+        return self.group.vartime_multiscalar_mul_small(v, ck, elem_bytes)
+
+    def commit_sparse_binary(self, ck: CommitmentKey, non_zero_indices):
+        return self.group.batch_add(ck, non_zero_indices)
+
+
+# ---- R1CS witness field arithmetic ------------------------------------------------------------
+def cross_term(fid: int, az: bytes, bz: bytes, cz: bytes, e1: bytes, u: bytes,
+               e2: bytes | None = None) -> bytes:
+    """T of commit_T / commit_T_relaxed (r1cs/mod.rs:614-620, 650-657)."""
+    n = len(az) // 32
+    assert len(bz) == len(az) == len(cz) == len(e1) and (e2 is None or len(e2) == len(az))
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    check(lib().b200_cross_term(fid, _cbuf(az), _cbuf(bz), _cbuf(cz), _cbuf(e1),
+                                _cbuf(e2) if e2 is not None else None, _cbuf(u), n, out))
+    return out.raw[:32 * n]
+
+
+def fold_witness(fid: int, a: bytes, b: bytes, r: bytes) -> bytes:
+    """a + r*b  (RelaxedR1CSWitness::fold, r1cs/mod.rs:1058-1069)."""
+    n = len(a) // 32
+    if len(a) != len(b):
+        raise ValueError("InvalidWitnessLength")  # r1cs/mod.rs:1054-1056
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    check(lib().b200_axpy(fid, _cbuf(a), _cbuf(b), _cbuf(r), n, out))
+    return out.raw[:32 * n]
+
+
+def vec_add(fid: int, a: bytes, b: bytes) -> bytes:
+    n = len(a) // 32
+    assert len(a) == len(b)
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    check(lib().b200_vec_add(fid, _cbuf(a), _cbuf(b), n, out))
+    return out.raw[:32 * n]
+
+
+def bind_poly_var_top(fid: int, z: bytes, r: bytes) -> bytes:
+    """multilinear.rs:65-84: returns the bound polynomial of half the length."""
+    n = len(z) // 32
+    buf = _cbuf(z)
+    check(lib().b200_bind_top(fid, buf, n, _cbuf(r)))
+    return bytes(buf[:32 * (n // 2)])

@@ -124,3 +124,38 @@ def field_from_u64(fid, vals) -> bytes:
     out = ctypes.create_string_buffer(32 * n)
     assert lib().orc_field_from_u64(fid, arr, ctypes.c_size_t(n), out) == 0
     return out.raw
+
+
+# ---- synthetic inputs (shared by tests and bench; SplitMix64 streams match pyref) -------------
+K0_DEFAULT = 0x5EED
+
+
+def gen_scalars(fid: int, seed: int, n: int) -> bytes:
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    assert lib().orc_gen_scalars(fid, ctypes.c_uint64(seed), ctypes.c_size_t(n), out) == 0
+    return out.raw[: 32 * n]
+
+
+def _limbs(k: int):
+    return (ctypes.c_uint64 * 4)(*[(k >> (64 * i)) & ((1 << 64) - 1) for i in range(4)])
+
+
+def gen_bases(curve: int, n: int, k0: int = K0_DEFAULT) -> bytes:
+    from . import pyref
+    c = pyref.CURVES[curve]
+    out = ctypes.create_string_buffer(max(64 * n, 1))
+    assert lib().orc_gen_bases(curve, _buf(c.affine_bytes(c.gen)), _limbs(k0), ctypes.c_size_t(n), out) == 0
+    return out.raw[: 64 * n]
+
+
+def dot_index(fid: int, scalars: bytes, k0: int = K0_DEFAULT) -> int:
+    n = len(scalars) // 32
+    out = ctypes.create_string_buffer(32)
+    assert lib().orc_dot_index(fid, _buf(scalars), ctypes.c_size_t(n), _limbs(k0), out) == 0
+    return int.from_bytes(out.raw, "little")
+
+
+def scalar_mul(curve: int, pt: bytes, k: int) -> bytes:
+    out = ctypes.create_string_buffer(64)
+    assert lib().orc_scalar_mul(curve, _buf(pt), _limbs(k), out) == 0
+    return out.raw

@@ -800,3 +800,104 @@ EXPORT int orc_field_from_u64(int fid, const uint64_t* v, size_t n, void* out) {
   for (size_t i = 0; i < n; i++) fe_from_u64(&ORC_FIELDS[fid], &((fe*)out)[i], v[i]);
   return 0;
 }
+
+/* ------------------------------------------------------------------ synthetic inputs ------ */
+/* SplitMix64 -- OUR generator (identical to oracle/pyref.py SplitMix64), not halo2curves' */
+static inline uint64_t splitmix(uint64_t* s) {
+  *s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = *s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+/* n uniform field elements by the from_uniform rule (64 LE bytes mod p, traits.rs:315-319),
+ * Montgomery form out.  Element i consumes PRNG words 8i..8i+7, so the stream matches
+ * pyref.SplitMix64(seed).field(p) called n times. */
+EXPORT int orc_gen_scalars(int fid, uint64_t seed, size_t n, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  fe r2, r3;
+  memcpy(r2.l, F->r2, 32);
+  fe_mul(F, &r3, &r2, &r2);
+  uint64_t s = seed;
+  for (size_t i = 0; i < n; i++) {
+    fe lo, hi, a, b;
+    for (int k = 0; k < 4; k++) lo.l[k] = splitmix(&s);
+    for (int k = 0; k < 4; k++) hi.l[k] = splitmix(&s);
+    fe_mul(F, &a, &lo, &r2); /* lo * R */
+    fe_mul(F, &b, &hi, &r3); /* hi * 2^256 * R */
+    fe_add(F, &((fe*)out)[i], &a, &b);
+  }
+  return 0;
+}
+/* bases P_i = [k0]G + i*G, i < n, batch-normalised affine (the construction of
+ * curve_property_tests.rs:186-194).  gen = affine generator (Montgomery), k0 canonical limbs. */
+EXPORT int orc_gen_bases(int curve, const void* gen, const uint64_t* k0, size_t n, void* out) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  const orc_field_t* F = cv.base;
+  const aff* G = (const aff*)gen;
+  aff* O = (aff*)out;
+  xyzz acc;
+  scalar_mul(F, &acc, G, k0);
+  const size_t BLK = 4096;
+  xyzz* blk = (xyzz*)malloc(sizeof(xyzz) * BLK);
+  fe* pref = (fe*)malloc(sizeof(fe) * (BLK + 1));
+  for (size_t base = 0; base < n; base += BLK) {
+    size_t m = n - base < BLK ? n - base : BLK;
+    for (size_t j = 0; j < m; j++) {
+      blk[j] = acc;
+      xyzz_add_affine(F, &acc, G);
+    }
+    /* batch-invert zzz (identity entries, zzz = 0, are skipped) */
+    fe_one(F, &pref[0]);
+    for (size_t j = 0; j < m; j++) {
+      if (xyzz_is_zero(&blk[j])) pref[j + 1] = pref[j];
+      else fe_mul(F, &pref[j + 1], &pref[j], &blk[j].zzz);
+    }
+    fe inv;
+    fe_inv(F, &inv, &pref[m]);
+    for (size_t j = m; j-- > 0;) {
+      if (xyzz_is_zero(&blk[j])) { memset(&O[base + j], 0, sizeof(aff)); continue; }
+      fe zi3, zi2, t;
+      fe_mul(F, &zi3, &inv, &pref[j]);        /* 1/zzz_j */
+      fe_mul(F, &inv, &inv, &blk[j].zzz);
+      fe_sqr(F, &t, &blk[j].zz);
+      fe_sqr(F, &zi2, &zi3);
+      fe_mul(F, &zi2, &zi2, &t);              /* 1/zz = zz^2 / zzz^2 */
+      fe_mul(F, &O[base + j].x, &blk[j].x, &zi2);
+      fe_mul(F, &O[base + j].y, &blk[j].y, &zi3);
+    }
+  }
+  free(blk);
+  free(pref);
+  return 0;
+}
+/* sum_i s_i * (k0 + i) mod q, canonical limbs out: the scalar that multiplies G in
+ * MSM(s, gen_bases(k0)) -- a size-independent closed form for full-size checks */
+EXPORT int orc_dot_index(int fid, const void* scalars, size_t n, const uint64_t* k0, void* out_canon) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  fe acc, k, one, t;
+  memset(&acc, 0, 32);
+  fe kc;
+  memcpy(kc.l, k0, 32);
+  fe_to_mont(F, &k, &kc);
+  fe_one(F, &one);
+  for (size_t i = 0; i < n; i++) {
+    fe_mul(F, &t, &((const fe*)scalars)[i], &k);
+    fe_add(F, &acc, &acc, &t);
+    fe_add(F, &k, &k, &one);
+  }
+  fe_from_mont(F, (fe*)out_canon, &acc);
+  return 0;
+}
+/* [k]P for one point, canonical k -> affine */
+EXPORT int orc_scalar_mul(int curve, const void* pt, const uint64_t* k, void* out_affine) {
+  curve_t cv;
+  if (get_curve(curve, &cv)) return 1;
+  xyzz r;
+  scalar_mul(cv.base, &r, (const aff*)pt, k);
+  xyzz_to_affine(cv.base, (aff*)out_affine, &r);
+  return 0;
+}

@@ -1,0 +1,82 @@
+"""The device field/curve templates (nova_b200/csrc/field.cuh, curve.cuh) compiled for the HOST,
+where every PTX carry chain is replaced by its bit-exact emulation: validates the Montgomery
+even/odd-accumulator algorithm and the XYZZ formulas without a GPU."""
+import ctypes
+import itertools
+import os
+import subprocess
+
+import pytest
+
+from oracle.pyref import CURVES, FIELD_MODULUS, SplitMix64, from_mont, mont_bytes, to_repr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hc():
+    src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+    so = os.path.join(HERE, "hostcheck", "libhostcheck.so")
+    hdrs = [os.path.join(HERE, "..", "nova_b200", "csrc", f) for f in ("field.cuh", "curve.cuh", "field_constants.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+    return ctypes.CDLL(so)
+
+
+def _buf(b):
+    return ctypes.create_string_buffer(b, len(b))
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_field_ops(hc, fid):
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(fid + 1)
+    edge = [0, 1, 2, p - 1, p - 2, (1 << 256) % p, (p - (1 << 256) % p) % p, (1 << 255) % p, (1 << 128) - 1, 1 << 64]
+    pairs = list(itertools.product(edge, edge)) + [(rng.field(p), rng.field(p)) for _ in range(3000)]
+    A = b"".join(mont_bytes(p, a) for a, _ in pairs)
+    B = b"".join(mont_bytes(p, b) for _, b in pairs)
+    n = len(pairs)
+    for op, fn in [(0, lambda a, b: (a + b) % p), (1, lambda a, b: (a - b) % p), (2, lambda a, b: a * b % p),
+                   (6, lambda a, b: (-a) % p)]:
+        out = ctypes.create_string_buffer(32 * n)
+        assert hc.hc_fe_op(fid, op, _buf(A), _buf(B), out, ctypes.c_size_t(n)) == 0
+        for i, (a, b) in enumerate(pairs):
+            got = int.from_bytes(out.raw[32 * i:32 * i + 32], "little")
+            assert got < p
+            assert from_mont(p, got) == fn(a, b), (op, a, b)
+    m = 100  # inversion is slow on host; fewer cases
+    out = ctypes.create_string_buffer(32 * m)
+    hc.hc_fe_op(fid, 3, _buf(A[:32 * m]), _buf(A[:32 * m]), out, ctypes.c_size_t(m))
+    for i, (a, _) in enumerate(pairs[:m]):
+        assert from_mont(p, int.from_bytes(out.raw[32 * i:32 * i + 32], "little")) == (pow(a, -1, p) if a else 0)
+    raw = b"".join(to_repr(a) for a, _ in pairs)
+    out = ctypes.create_string_buffer(32 * n)
+    hc.hc_fe_op(fid, 4, _buf(raw), _buf(raw), out, ctypes.c_size_t(n))
+    assert out.raw == A
+    out2 = ctypes.create_string_buffer(32 * n)
+    hc.hc_fe_op(fid, 5, _buf(A), _buf(A), out2, ctypes.c_size_t(n))
+    assert out2.raw == raw
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_xyzz_formulas(hc, cid):
+    """madd / add / dbl incl. the exceptional cases of msm.rs:92-113,130-155."""
+    c = CURVES[cid]
+    pts = c.bases_arith(20)
+    seq = [pts[3], pts[3], None, pts[5], c.neg(pts[5]), pts[7], pts[7], pts[7], pts[1], None] + pts
+    exp = None
+    for P in seq:
+        exp = c.add(exp, P)
+    data = b"".join(c.affine_bytes(P) for P in seq)
+    for mode in (0, 1):
+        out = ctypes.create_string_buffer(96)
+        hc.hc_pt_sum(c.base_field, mode, _buf(data), ctypes.c_size_t(len(seq)), out)
+        assert c.jacobian_from_bytes(out.raw) == exp
+    d2 = c.affine_bytes(pts[2]) + c.affine_bytes(c.neg(pts[2]))
+    out = ctypes.create_string_buffer(96)
+    hc.hc_pt_sum(c.base_field, 0, _buf(d2), ctypes.c_size_t(2), out)
+    assert c.jacobian_from_bytes(out.raw) is None
+    for k in (1, 2, 3, 77, 65535, 1000003):
+        out = ctypes.create_string_buffer(96)
+        hc.hc_pt_sum(c.base_field, 2, _buf(c.affine_bytes(pts[4])), ctypes.c_size_t(k), out)
+        assert c.jacobian_from_bytes(out.raw) == c.mul(k, pts[4])
