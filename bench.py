@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: BN254 G1 commitment MSM (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (oracle)
+
+A "step" is ONE multi-scalar multiplication of 2^LOG2N uniformly random BN254 scalars against a
+resident commitment key (CE::commit with r = 0, benches/commit.rs:30,112-125).
+  value   device-resident throughput: scalars already in HBM, K calls of b200_msm_dev timed with
+          CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  e2e     the same metric through the host-pointer C ABI (b200_commit for N=1): scalars start in
+          PINNED HOST memory, the H2D copy and the D2H read of the 96-byte result are inside the
+          timed region (wall clock around K blocking calls).
+  N > 1   the (scalar, base) pairs are sharded by index range across ranks; every rank reduces its
+          slice to one point, the partials are all-gathered over NCCL (96 B per rank) and summed on
+          every rank.  Total work is fixed => "scaling": "strong".
+Inputs are synthetic: key bases[i] = (k0+i)*G built on the device, scalars from numpy's seeded
+PRNG (32 random bytes masked below the modulus = a uniform Montgomery residue).
+The GPU arm never touches oracle/; the cpu_baseline leg and --impl reference do (as the timed
+CPU implementation, which is what they are for).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CURVE = 0  # BN254 G1
+SCALAR_FIELD = 0  # BN254 Fr
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+K0 = 0x5EED
+METRIC = "MSM throughput (2^20 BN254 scalar*G1/s)"
+UNIT = "pairs/s"
+ALG_BYTES_PER_PAIR = 96  # 32 B scalar + 64 B affine base, each read once
+
+
+def synth_scalars(n, seed):
+    """n x 32 B little-endian values uniform in [0, 2^253): every 32-byte string below the
+    modulus is the Montgomery representation of exactly one field element, so this is a
+    (near-)uniform scalar vector without any field arithmetic on the host."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * 2 + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)  # < 2^253 < r
+    return a
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import nova_b200 as nb
+    from nova_b200.native import check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    L = lib()
+    check(L.b200_init(local_rank))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_total = 1 << args.log2n
+    assert n_total % world == 0
+    n = n_total // world  # this rank's index range [rank*n, (rank+1)*n)
+    ck = nb.CommitmentKey.setup_synthetic(nb.Curve(CURVE), n, k0=K0 + rank * n, window_bits=args.window_bits)
+    sc_np = synth_scalars(n_total, seed=2)[rank * n:(rank + 1) * n]
+
+    stream = torch.cuda.Stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    d_sc = torch.from_numpy(sc_np.view("uint8").reshape(-1)).cuda()
+    d_part = torch.zeros(96, dtype=torch.uint8, device="cuda")
+    d_all = torch.zeros(96 * world, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        check(L.b200_msm_dev(ck.handle, 0, d_sc.data_ptr(), n, d_part.data_ptr(), sp))
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_part)
+            check(L.b200_jacobian_sum_dev(CURVE, d_all.data_ptr(), world, d_out.data_ptr(), sp))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value") --------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        check(L.b200_profile_enable(1))
+        check(L.b200_profile_reset())
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    stage_ms = (ctypes.c_double * 5)()
+    msms, launches = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    check(L.b200_profile_read(stage_ms, 5, ctypes.byref(msms), ctypes.byref(launches)))
+    check(L.b200_profile_enable(0))
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---------------- end to end through the host-pointer C ABI ("e2e") -------------------------
+    h_ptr = ctypes.c_void_p()
+    check(L.b200_host_alloc(n * 32, ctypes.byref(h_ptr)))
+    ctypes.memmove(h_ptr, sc_np.ctypes.data, n * 32)
+    out_host = ctypes.create_string_buffer(96)
+    h_pinned_t = None
+    if world > 1:
+        h_pinned_t = torch.empty(96, dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        if world == 1:
+            check(L.b200_commit(ck.handle, h_ptr, n, None, out_host))  # H2D + MSM + D2H, blocking
+        else:
+            with torch.cuda.stream(stream):
+                check(L.b200_memcpy_h2d(d_sc.data_ptr(), h_ptr, n * 32))
+                step_device()
+                h_pinned_t.copy_(d_out, non_blocking=True)
+                stream.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(t.item()) / args.steps
+    check(L.b200_host_free(h_ptr))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (k_accumulate) ----------------------------
+    peak, peak_src = measured_peak_hbm()
+    acc_ms = stage_ms[2] / max(1, msms.value)  # average launch duration over the timed region
+    alg_bytes = ALG_BYTES_PER_PAIR * n
+    achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
+    stage_names = ["digits", "sort", "accumulate", "fixup", "reduce"]
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "accumulate_traffic_bytes.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get(f"log2n_{args.log2n}_gpus_{world}")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "k_accumulate<BN254_FQ>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,
+        "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(acc_ms, 4),
+        "note": "MSM is INT32-multiply bound, not HBM bound (DESIGN.md §Roofline); the HBM fraction is "
+                "reported because north_star asks for it",
+        "stage_ms_per_msm": {k: round(stage_ms[i] / max(1, msms.value), 4) for i, k in enumerate(stage_names)},
+    }
+
+    # ---------------- CPU baseline beside it (N = 1 only) ---------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_run(args.log2n, steps=1, warmup=0, sc_np=sc_np)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit prime-field / curve integers)",
+        "data": "synthetic",
+        "config": {"workload": f"BN254 G1 Pippenger MSM, 2^{args.log2n} uniform scalars, resident key "
+                               f"(BASELINE.json configs[1])",
+                   "log2n": args.log2n, "pairs_per_step": n_total, "sharding": f"index-range x{world}",
+                   "l2": "working set (window tables 64*16*n B + sort buffers) >> 126 MB L2; no flush needed"},
+        "clocks": clocks,
+        "e2e": {"value": n_total / (e2e_ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_per_step,
+                "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
+                "api": "b200_commit (host pointers, pinned)" if world == 1 else
+                       "b200_memcpy_h2d + b200_msm_dev + NCCL all_gather + b200_jacobian_sum_dev + D2H"},
+        "gpu_launches": int(launches.value),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_run(log2n, steps, warmup, sc_np=None):
+    """Time the CPU restatement of the reference's msm() (oracle/oracle.c, msm.rs:225-419 with the
+    msm_best stand-in) with all host cores on the bench workload (or a bounded sample of it)."""
+    from oracle import coracle as co
+    cores = os.cpu_count() or 1
+    n_full = 1 << log2n
+    if sc_np is None:
+        sc_np = synth_scalars(n_full, seed=2)
+    # bound the sample to a few seconds of work per step: probe at 2^16
+    probe = 1 << min(16, log2n)
+    bases_probe = co.gen_bases(CURVE, probe, K0)
+    sc_probe = sc_np[:probe].tobytes()
+    t0 = time.perf_counter()
+    co.msm(CURVE, sc_probe, bases_probe, cores)
+    t_probe = time.perf_counter() - t0
+    est_full = t_probe * (n_full / probe)
+    budget_s = 20.0
+    n = n_full
+    while n > probe and est_full * (n / n_full) * (steps + warmup) > budget_s:
+        n //= 2
+    bases = co.gen_bases(CURVE, n, K0)
+    sc = sc_np[:n].tobytes()
+    for _ in range(warmup):
+        co.msm(CURVE, sc, bases, cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        co.msm(CURVE, sc, bases, cores)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first 2^{n.bit_length() - 1} of the 2^{log2n} pairs, {steps} run(s), {dt * 1e3:.1f} ms each",
+            "note": "C restatement of msm.rs (signed split + bit-width partition; halo2curves msm_best "
+                    "restated as signed-digit Pippenger), pthreads, no hand-written asm"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_run(args.log2n, steps=args.steps, warmup=min(args.warmup, 1))
+    n_sample = cb["sample"]
+    out = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64 limbs (256-bit prime-field / curve integers)",
+        "data": "synthetic",
+        "config": {"workload": f"BN254 G1 Pippenger MSM, 2^{args.log2n} uniform scalars, resident key "
+                               f"(BASELINE.json configs[1])", "log2n": args.log2n, "sample": n_sample},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=20)
+    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

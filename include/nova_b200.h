@@ -63,6 +63,13 @@ int b200_memcpy_h2d(void* dptr, const void* hptr, size_t bytes);
 int b200_memcpy_d2h(void* hptr, const void* dptr, size_t bytes);
 int b200_sync(void);
 
+/* per-stage device timing of the MSM pipeline (CUDA events on the launching stream) and a count
+ * of the kernels this library launched; used by bench.py for the roofline line.  Stages:
+ * 0 digits, 1 sort (scan + scatter), 2 bucket accumulate, 3 boundary fix-up, 4 bucket reduce. */
+int b200_profile_enable(int on);
+int b200_profile_reset(void);
+int b200_profile_read(double* stage_ms, int nstages, uint64_t* msms, uint64_t* launches);
+
 /* ---- commitment keys -------------------------------------------------------------------
  * Replaces holding `CommitmentKey{ck: Vec<Affine>, h}` (pedersen.rs:32-38, hyperkzg.rs:76-84) on
  * the host only: the bases are uploaded ONCE, expanded into the 2^(c*t)*P window tables, and stay
@@ -70,6 +77,11 @@ int b200_sync(void);
  * window_bits = 0 picks c from n.  Keys are immutable after registration. */
 int b200_ck_register(int curve_id, const void* bases_affine_mont, size_t n,
                      const void* h_affine_mont_or_null, int window_bits, uint64_t* ck_handle);
+/* test/bench key: bases[i] = (k0 + i) * G generated on the device (the analogue of the
+ * reference's test-only setups, hyperkzg.rs:357-376 / curve_property_tests.rs:186-194);
+ * with_h != 0 appends h = (k0 + n) * G as the blinding generator. */
+int b200_ck_setup_synthetic(int curve_id, const void* generator_affine_mont, uint64_t k0, size_t n,
+                            int with_h, int window_bits, uint64_t* ck_handle);
 int b200_ck_release(uint64_t ck_handle);
 int b200_ck_len(uint64_t ck_handle, size_t* n, int* window_bits, int* num_tables);
 
@@ -99,6 +111,11 @@ int b200_msm_indices(uint64_t ck_handle, const uint64_t* idx, size_t m, void* ou
 /* one-shot MSM over bases that are not a registered key (pedersen.rs:418-420,492,505) */
 int b200_msm_adhoc(int curve_id, const void* bases_affine_mont, const void* scalars_mont, size_t n,
                    void* out_jacobian_mont);
+
+/* out = sum of k Jacobian points (device pointers): the local combine after the all-gather of
+ * per-GPU partial MSMs (NCCL has no group-law reduction operator) */
+int b200_jacobian_sum_dev(int curve_id, const void* d_points_jacobian, size_t k,
+                          void* d_out_jacobian, void* stream);
 
 /* ---- R1CS witness field arithmetic (host-pointer forms) ---------------------------------- */
 /* t[i] = az[i]*bz[i] - u*cz[i] - e1[i] (- e2[i] if e2 != NULL)   (r1cs/mod.rs:614-620,650-657) */

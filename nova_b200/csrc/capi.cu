@@ -116,6 +116,37 @@ struct ck_ctx {
   }
 };
 
+// ---- optional per-stage device timing + launch accounting (for bench.py's roofline) ---------
+enum { ST_DIGITS = 0, ST_SORT, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_COUNT };
+const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 2};
+struct profile_state {
+  std::mutex mu;
+  bool enabled = false;
+  cudaEvent_t ev[ST_COUNT + 1] = {};
+  bool have_events = false;
+  bool pending = false;        // events of the last MSM not folded in yet
+  double ms[ST_COUNT] = {};    // accumulated
+  uint64_t msms = 0;
+  uint64_t launches = 0;       // kernels launched by this library (always counted)
+} g_prof;
+
+void prof_fold_locked() {  // caller holds g_prof.mu
+  if (!g_prof.pending) return;
+  if (cudaEventSynchronize(g_prof.ev[ST_COUNT]) == cudaSuccess) {
+    for (int i = 0; i < ST_COUNT; i++) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]) == cudaSuccess) g_prof.ms[i] += t;
+    }
+    g_prof.msms++;
+  }
+  g_prof.pending = false;
+}
+
+void count_launch(int k) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.launches += k;
+}
+
 std::mutex g_handles_mu;
 std::map<uint64_t, std::shared_ptr<ck_ctx>> g_handles;
 uint64_t g_next_handle = 1;
@@ -226,14 +257,35 @@ int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n,
   size_t K = (size_t)ck.G * ck.B;
   CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
   CU(cudaMemsetAsync(p.heavy, 0, 4, s));
+  std::lock_guard<std::mutex> plk(g_prof.mu);
+  const bool prof = g_prof.enabled;
+  if (prof) {
+    prof_fold_locked();
+    if (!g_prof.have_events) {
+      for (auto& e : g_prof.ev) CU(cudaEventCreate(&e));
+      g_prof.have_events = true;
+    }
+  }
+#define STAGE_MARK(i) \
+  if (prof) CU(cudaEventRecord(g_prof.ev[i], s))
+  STAGE_MARK(ST_DIGITS);
   if (small_elem_bytes)
     msm_digits_small(s, d_scalars, small_elem_bytes, p);
   else
     sops->digits(s, d_scalars, p);
+  STAGE_MARK(ST_SORT);
   msm_scan(s, p);
   msm_scatter(s, p);
+  STAGE_MARK(ST_ACCUMULATE);
   bops->accumulate(s, ck.tables, p);
+  STAGE_MARK(ST_FIXUP);
+  bops->fixup(s, p);
+  STAGE_MARK(ST_REDUCE);
   bops->reduce(s, p, d_out);
+  STAGE_MARK(ST_COUNT);
+#undef STAGE_MARK
+  if (prof) g_prof.pending = true;
+  for (int i = 0; i < ST_COUNT; i++) g_prof.launches += STAGE_KERNELS[i];
   CU(cudaGetLastError());
   return B200_OK;
 }
@@ -371,6 +423,45 @@ int b200_sync(void) {
   return B200_OK;
 }
 
+// ---- profiling / accounting --------------------------------------------------------------------
+int b200_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.enabled = on != 0;
+  return B200_OK;
+}
+int b200_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  prof_fold_locked();
+  for (double& m : g_prof.ms) m = 0;
+  g_prof.msms = 0;
+  g_prof.launches = 0;
+  return B200_OK;
+}
+int b200_profile_read(double* stage_ms, int nstages, uint64_t* msms, uint64_t* launches) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  prof_fold_locked();
+  for (int i = 0; i < nstages && i < ST_COUNT; i++)
+    if (stage_ms) stage_ms[i] = g_prof.ms[i];
+  if (msms) *msms = g_prof.msms;
+  if (launches) *launches = g_prof.launches;
+  return B200_OK;
+}
+
+int b200_jacobian_sum_dev(int curve_id, const void* d_points, size_t k, void* d_out, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
+  if (!d_out || (k && !d_points)) return fail(B200_E_ARG, "null pointer");
+  const field_ops* bops = ops_for_field(CURVES[curve_id].base_fid);
+  bops->jacobian_sum(stream ? (cudaStream_t)stream : g_dev.stream, d_points, (int)k, d_out);
+  {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.launches += 1;
+  }
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
 // ---- keys -------------------------------------------------------------------------------------
 int b200_ck_register(int curve_id, const void* bases, size_t n, const void* h, int window_bits,
                      uint64_t* handle) {
@@ -379,6 +470,33 @@ int b200_ck_register(int curve_id, const void* bases, size_t n, const void* h, i
   if (!handle) return fail(B200_E_ARG, "null handle pointer");
   std::shared_ptr<ck_ctx> ck;
   rc = register_key(curve_id, bases, false, n, h, window_bits, true, ck);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_handles_mu);
+  *handle = g_next_handle++;
+  g_handles[*handle] = ck;
+  return B200_OK;
+}
+
+int b200_ck_setup_synthetic(int curve_id, const void* gen_affine, uint64_t k0, size_t n, int with_h,
+                            int window_bits, uint64_t* handle) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
+  if (!gen_affine || !handle || n == 0) return fail(B200_E_ARG, "bad argument");
+  size_t total = n + (with_h ? 1 : 0);
+  dev_buf bases, gen;
+  if ((rc = bases.alloc(total * 64))) return rc;
+  if ((rc = gen.alloc(64))) return rc;
+  CU(cudaMemcpyAsync(gen.p, gen_affine, 64, cudaMemcpyHostToDevice, g_dev.stream));
+  const field_ops* bops = ops_for_field(CURVES[curve_id].base_fid);
+  bops->index_bases(g_dev.stream, bases.p, total, gen.p, k0);
+  CU(cudaGetLastError());
+  std::vector<char> h(64);
+  if (with_h)
+    CU(cudaMemcpyAsync(h.data(), (char*)bases.p + n * 64, 64, cudaMemcpyDeviceToHost, g_dev.stream));
+  CU(cudaStreamSynchronize(g_dev.stream));
+  std::shared_ptr<ck_ctx> ck;
+  rc = register_key(curve_id, bases.p, true, n, with_h ? h.data() : nullptr, window_bits, true, ck);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_handles_mu);
   *handle = g_next_handle++;
@@ -555,6 +673,7 @@ int b200_msm_indices(uint64_t handle, const uint64_t* idx, size_t m, void* out) 
   if (m) CU(cudaMemcpyAsync(w.idx32, idx32.data(), m * 4, cudaMemcpyHostToDevice, s));
   const field_ops* bops = ops_for_field(CURVES[ck->curve].base_fid);
   bops->sum_points(s, ck->tables, w.idx32, m, w.sumscratch, w.d_out);
+  count_launch(2);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(w.h_out, w.d_out, 96, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -584,6 +703,7 @@ int b200_cross_term_dev(int fid, const void* az, const void* bz, const void* cz,
     if (n == 0) return (int)B200_OK;
     if (!az || !bz || !cz || !e1 || !u || !t) return fail(B200_E_ARG, "null pointer");
     ops->cross_term(stream ? (cudaStream_t)stream : g_dev.stream, az, bz, cz, e1, e2, u, n, t);
+    count_launch(1);
     CU(cudaGetLastError());
     return (int)B200_OK;
   });
@@ -594,6 +714,7 @@ int b200_axpy_dev(int fid, const void* a, const void* b, const void* r, size_t n
     if (n == 0) return (int)B200_OK;
     if (!a || !b || !r || !out) return fail(B200_E_ARG, "null pointer");
     ops->axpy(stream ? (cudaStream_t)stream : g_dev.stream, a, b, r, n, out);
+    count_launch(1);
     CU(cudaGetLastError());
     return (int)B200_OK;
   });
@@ -603,6 +724,7 @@ int b200_vec_add_dev(int fid, const void* a, const void* b, size_t n, void* out,
     if (n == 0) return (int)B200_OK;
     if (!a || !b || !out) return fail(B200_E_ARG, "null pointer");
     ops->vec_add(stream ? (cudaStream_t)stream : g_dev.stream, a, b, n, out);
+    count_launch(1);
     CU(cudaGetLastError());
     return (int)B200_OK;
   });
@@ -613,6 +735,7 @@ int b200_bind_top_dev(int fid, void* z, size_t n, const void* r, void* stream) {
     if (n & 1) return fail(B200_E_ARG, "bind_top needs an even length, got %zu", n);
     if (!z || !r) return fail(B200_E_ARG, "null pointer");
     ops->bind_top(stream ? (cudaStream_t)stream : g_dev.stream, z, n, r);
+    count_launch(1);
     CU(cudaGetLastError());
     return (int)B200_OK;
   });

@@ -172,34 +172,31 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint64_t* __restrict__
   }
 }
 
-// one thread per boundary partial; the head of each same-key run sums the run
+// One thread per bucket key: joins the boundary partials of that bucket.  The bucket's entries
+// span segments t0..t1, so its partials can only sit in slots 2*t0 .. 2*t1+1.  A bucket whose
+// entries are interior to one segment finds no matching slot (it was stored directly by
+// k_accumulate); buckets above heavy_min are left to k_fixup_heavy.
 template <class F>
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ start, uint32_t K,
                                                int L, uint32_t heavy_min,
                                                const void* __restrict__ parts,
                                                const uint32_t* __restrict__ pkeys,
                                                void* __restrict__ buckets) {
-  const uint32_t M = start[K];
-  const size_t nseg = ((size_t)M + L - 1) / L;
-  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * nseg) return;
-  uint32_t key = pkeys[j];
-  if (key == KEY_INVALID) return;
-  if (start[key + 1] - start[key] > heavy_min) return;  // joined by k_fixup_heavy
-  if (j > 0) {
-    uint32_t pk = pkeys[j - 1];
-    if (pk == KEY_INVALID && j > 1) pk = pkeys[j - 2];
-    if (pk == key) return;  // not a run head
+  uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+  if (key >= K) return;
+  uint32_t s0 = start[key], s1 = start[key + 1];
+  if (s1 == s0 || s1 - s0 > heavy_min) return;
+  size_t j0 = 2 * ((size_t)s0 / L), j1 = 2 * (((size_t)s1 - 1) / L) + 1;
+  xyzz_t acc = xyzz_identity<F>();
+  bool found = false;
+  for (size_t j = j0; j <= j1; j++) {
+    if (pkeys[j] == key) {
+      xyzz_t o = xyzz_load(parts, j);
+      xyzz_add<F>(acc, o);
+      found = true;
+    }
   }
-  xyzz_t acc = xyzz_load(parts, j);
-  for (size_t k = j + 1; k < 2 * nseg; k++) {
-    uint32_t kk = pkeys[k];
-    if (kk == KEY_INVALID) continue;
-    if (kk != key) break;
-    xyzz_t o = xyzz_load(parts, k);
-    xyzz_add<F>(acc, o);
-  }
-  xyzz_store(buckets, key, acc);
+  if (found) xyzz_store(buckets, key, acc);
 }
 
 // Heavy buckets (skewed scalars: 0/1 witnesses, repeated values) would serialise the run-head
@@ -306,6 +303,56 @@ __global__ void __launch_bounds__(256) k_reduce2(const void* __restrict__ rparts
     fe_store(out_jac, 1, Y);
     fe_store(out_jac, 2, Z);
   }
+}
+
+// sum of k Jacobian points (the per-GPU partial MSMs after the all-gather);
+// k is tiny (= number of GPUs), one thread.
+template <class F>
+__global__ void k_jacobian_sum(const void* __restrict__ pts, int k, void* __restrict__ out_jac) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  xyzz_t acc = xyzz_identity<F>();
+  for (int i = 0; i < k; i++) {
+    fe_t X = fe_load(pts, 3 * (size_t)i), Y = fe_load(pts, 3 * (size_t)i + 1),
+         Z = fe_load(pts, 3 * (size_t)i + 2);
+    if (fe_is_zero(Z)) continue;
+    xyzz_t p;  // Jacobian (X,Y,Z) == XYZZ (X, Y, Z^2, Z^3)
+    p.x = X;
+    p.y = Y;
+    p.zz = fe_sqr<F>(Z);
+    p.zzz = fe_mul<F>(p.zz, Z);
+    xyzz_add<F>(acc, p);
+  }
+  fe_t X, Y, Z;
+  xyzz_to_jacobian<F>(acc, X, Y, Z);
+  fe_store(out_jac, 0, X);
+  fe_store(out_jac, 1, Y);
+  fe_store(out_jac, 2, Z);
+}
+
+// Synthetic key for tests/benches: bases[i] = (k0 + i) * G, affine.  Plays the role of the
+// reference's test-only key generators (hyperkzg.rs:357-376 `setup_from_rng`, the
+// "P0 + i*G" bases of curve_property_tests.rs:186-194); real keys come from the host.
+template <class F>
+__global__ void __launch_bounds__(128) k_index_bases(void* __restrict__ bases, size_t n,
+                                                     const void* __restrict__ gen, uint64_t k0) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_t gx = fe_load(gen, 0), gy = fe_load(gen, 1);
+  uint64_t k = k0 + i;
+  xyzz_t acc = xyzz_identity<F>();
+  for (int b = 63; b >= 0; b--) {
+    xyzz_dbl<F>(acc);
+    if ((k >> b) & 1) xyzz_madd<F>(acc, gx, gy);
+  }
+  fe_t x = fe_zero<F>(), y = fe_zero<F>();
+  if (!xyzz_is_identity(acc)) {
+    fe_t iz3 = fe_inv<F>(acc.zzz);
+    fe_t iz2 = fe_mul<F>(fe_sqr<F>(acc.zz), fe_sqr<F>(iz3));
+    x = fe_mul<F>(acc.x, iz2);
+    y = fe_mul<F>(acc.y, iz3);
+  }
+  fe_store(bases, 2 * i, x);
+  fe_store(bases, 2 * i + 1, y);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -20,10 +20,13 @@ struct field_ops {
   // base-field side
   void (*expand_key)(cudaStream_t, void* tables, size_t n_ck, int ntables, int shift);
   void (*accumulate)(cudaStream_t, const void* tables, const msm_plan&);
+  void (*fixup)(cudaStream_t, const msm_plan&);
   void (*reduce)(cudaStream_t, const msm_plan&, void* out_jac);
   // small helpers on points (base field)
   void (*sum_points)(cudaStream_t, const void* tables, const uint32_t* idx_or_null, size_t n,
                      void* scratch_xyzz, void* out_jac);
+  void (*jacobian_sum)(cudaStream_t, const void* pts, int k, void* out_jac);
+  void (*index_bases)(cudaStream_t, void* bases, size_t n, const void* gen_affine, uint64_t k0);
   // --- field-vector kernels (K4..K8) --------------------------------------------------------
   void (*cross_term)(cudaStream_t, const void* az, const void* bz, const void* cz, const void* e1,
                      const void* e2_or_null, const void* u, size_t n, void* t);

@@ -51,9 +51,18 @@ struct ops_impl {
     int grid = (int)((nseg + block - 1) / block);
     k_accumulate<F><<<grid, block, 0, s>>>(p.entries, p.start, K, tables, p.L, p.buckets, p.parts,
                                            p.pkeys);
-    int grid2 = (int)((2 * nseg + block - 1) / block);
-    k_fixup<F><<<grid2, block, 0, s>>>(p.start, K, p.L, p.heavy_min, p.parts, p.pkeys, p.buckets);
+  }
+  static void fixup(cudaStream_t s, const msm_plan& p) {
+    uint32_t K = (uint32_t)p.G * p.B;
+    k_fixup<F><<<(K + 127) / 128, 128, 0, s>>>(p.start, K, p.L, p.heavy_min, p.parts, p.pkeys,
+                                               p.buckets);
     k_fixup_heavy<F><<<148, 256, 0, s>>>(p.start, p.L, p.heavy, p.parts, p.pkeys, p.buckets);
+  }
+  static void index_bases(cudaStream_t s, void* bases, size_t n, const void* gen, uint64_t k0) {
+    k_index_bases<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(bases, n, gen, k0);
+  }
+  static void jacobian_sum(cudaStream_t s, const void* pts, int k, void* out_jac) {
+    k_jacobian_sum<F><<<1, 32, 0, s>>>(pts, k, out_jac);
   }
   static void reduce(cudaStream_t s, const msm_plan& p, void* out_jac) {
     uint32_t T = p.B / p.m;
@@ -84,8 +93,8 @@ struct ops_impl {
     k_bind_top<F><<<stream_grid(n / 2, 256), 256, 0, s>>>(z, n / 2, r);
   }
   static constexpr field_ops table() {
-    return field_ops{F::ID,      digits,  expand_key, accumulate, reduce, sum_points,
-                     cross_term, axpy,    vec_add,    bind_top};
+    return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
+                     sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top};
   }
 };
 

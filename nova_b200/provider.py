@@ -40,6 +40,15 @@ class Curve(enum.IntEnum):
         return (fields.BN254_FR, fields.BN254_FQ, fields.PALLAS_FQ, fields.PALLAS_FP)[int(self)]
 
 
+# curve generators (halo2curves): G1 (1,2); Grumpkin (1, sqrt(-16)); Pallas/Vesta (-1, 2)
+GENERATORS = {
+    0: (1, 2),
+    1: (1, 0x0000000000000002CF135E7506A45D632D270D45F1181294833FC48D823F272C),
+    2: (fields.MODULUS[fields.PALLAS_FP] - 1, 2),
+    3: (fields.MODULUS[fields.PALLAS_FQ] - 1, 2),
+}
+
+
 def _cbuf(b):
     if b is None:
         return None
@@ -68,6 +77,23 @@ class CommitmentKey:
                                      window_bits, ctypes.byref(handle)))
         self.handle = handle.value
         self.has_h = h is not None
+
+    @classmethod
+    def setup_synthetic(cls, curve: "Curve", n: int, k0: int = 0x5EED, with_h: bool = False,
+                        window_bits: int = 0) -> "CommitmentKey":
+        """Test/bench key bases[i] = (k0+i)*G built on the device (cf. hyperkzg.rs:357-376)."""
+        self = cls.__new__(cls)
+        self.curve = Curve(curve)
+        self.n = n
+        self.has_h = with_h
+        gen = GENERATORS[int(curve)]
+        fid = self.curve.base_field
+        g = fields.to_mont_bytes(fid, gen[0]) + fields.to_mont_bytes(fid, gen[1])
+        handle = c_u64(0)
+        check(lib().b200_ck_setup_synthetic(int(curve), _cbuf(g), k0, n, int(with_h), window_bits,
+                                            ctypes.byref(handle)))
+        self.handle = handle.value
+        return self
 
     def __len__(self):
         return self.n

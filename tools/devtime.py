@@ -18,8 +18,9 @@ from oracle.pyref import CURVES
 
 def time_msm(ck, d_scalars, n, d_out, iters=5):
     L = lib()
-    s = torch.cuda.current_stream()
+    s = torch.cuda.Stream()  # a real (non-NULL) stream: NULL would select the library's own
     sp = ctypes.c_void_p(s.cuda_stream)
+    torch.cuda.synchronize()
     for _ in range(2):
         check(L.b200_msm_dev(ck.handle, 0, d_scalars.data_ptr(), n, d_out.data_ptr(), sp))
     torch.cuda.synchronize()
