@@ -129,11 +129,12 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from nova_b200.sharding import shard_range
     n_total = 1 << args.log2n
-    assert n_total % world == 0
-    n = n_total // world  # this rank's index range [rank*n, (rank+1)*n)
-    ck = nb.CommitmentKey.setup_synthetic(nb.Curve(CURVE), n, k0=K0 + rank * n, window_bits=args.window_bits)
-    sc_np = synth_scalars(n_total, seed=2)[rank * n:(rank + 1) * n]
+    lo, hi = shard_range(n_total, rank, world)  # this rank's index range of (scalar, base) pairs
+    n = hi - lo
+    ck = nb.CommitmentKey.setup_synthetic(nb.Curve(CURVE), n, k0=K0 + lo, window_bits=args.window_bits)
+    sc_np = synth_scalars(n_total, seed=2)[lo:hi]
 
     stream = torch.cuda.Stream()
     sp = ctypes.c_void_p(stream.cuda_stream)

@@ -1,0 +1,75 @@
+// Instruction-throughput probe for the big-integer inner loops (developer tool, not product).
+// Measures ops/clk/SM for: IMAD.WIDE.U32 chains, IMAD (lo), IADD3, 64-bit integer add, DFMA.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench tools/microbench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int ITER = 4096;
+constexpr int ILP = 8;
+
+template <int OP>
+__global__ void probe(uint64_t* out, uint32_t a0, uint32_t b0, double d0) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t acc[ILP];
+  uint32_t lo[ILP], x = a0 + tid, y = b0 | 1;
+  double fd[ILP], da = d0 + tid * 1e-9, db = 1.0000001;
+  for (int k = 0; k < ILP; k++) { acc[k] = tid + k; lo[k] = tid * 7 + k; fd[k] = d0 + k; }
+  for (int i = 0; i < ITER; i++) {
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+      if (OP == 0) {  // IMAD.WIDE.U32: 32x32 + 64
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
+      } else if (OP == 1) {  // IMAD lo
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(x), "r"(y));
+      } else if (OP == 2) {  // IADD3
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(lo[k]) : "r"(x));
+      } else if (OP == 3) {  // 64-bit add
+        asm volatile("add.u64 %0, %0, %1;" : "+l"(acc[k]) : "l"((uint64_t)x << 20 | y));
+      } else if (OP == 4) {  // DFMA
+        asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(fd[k]) : "d"(da), "d"(db));
+      } else if (OP == 5) {  // mad.hi
+        asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(x), "r"(y));
+      } else if (OP == 6) {  // carry chain pair (the field.cuh pattern)
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                     : "+r"(lo[k]), "+r"(lo[(k + 1) % ILP]) : "r"(x), "r"(y));
+      }
+    }
+  }
+  uint64_t s = 0;
+  for (int k = 0; k < ILP; k++) s += acc[k] + lo[k] + (uint64_t)fd[k];
+  out[tid] = s;
+}
+
+template <int OP>
+void run(const char* name, int ops_per_iter) {
+  int dev; cudaGetDevice(&dev);
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
+  int blocks = p.multiProcessorCount * 4, threads = 256;
+  uint64_t* out; cudaMalloc(&out, (size_t)blocks * threads * 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  probe<OP><<<blocks, threads>>>(out, 3, 5, 1.5);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  probe<OP><<<blocks, threads>>>(out, 3, 5, 1.5);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double ops = (double)blocks * threads * ITER * ILP * ops_per_iter;
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
+  double per_clk_sm = ops / (ms * 1e-3) / (clk * 1e3) / p.multiProcessorCount;
+  printf("%-28s %8.3f ms  %8.2f Gop/s  %6.1f lane-ops/clk/SM (at %d MHz nominal)\n", name, ms,
+         ops / ms / 1e6, per_clk_sm, clk / 1000);
+  cudaFree(out);
+}
+
+int main() {
+  run<0>("mad.wide.u32 (IMAD.WIDE)", 1);
+  run<1>("mad.lo.u32 (IMAD)", 1);
+  run<5>("mad.hi.u32", 1);
+  run<6>("mad.lo.cc+madc.hi pair", 1);
+  run<2>("add.u32 (IADD3)", 1);
+  run<3>("add.u64", 1);
+  run<4>("fma.rz.f64 (DFMA)", 1);
+  return 0;
+}
