@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../nova_b200/csrc/field.cuh"
 
 constexpr int ITER = 4096;
 constexpr int ILP = 8;
@@ -41,6 +42,77 @@ __global__ void probe(uint64_t* out, uint32_t a0, uint32_t b0, double d0) {
   out[tid] = s;
 }
 
+// the real thing: dependent fe_mul chains, NCH independent chains per thread
+template <int NCH>
+__global__ void __launch_bounds__(128) probe_femul(nova::fe_t* out, int iters) {
+  using namespace nova;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  fe_t x[NCH], y;
+  for (int k = 0; k < NCH; k++)
+    for (int i = 0; i < 8; i++) x[k].l[i] = tid * 31 + i + k;
+  for (int i = 0; i < 8; i++) y.l[i] = tid + 77 * i;
+  x[0].l[7] &= 0x0fffffff; y.l[7] &= 0x0fffffff;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < NCH; k++) x[k] = fe_mul<BN254_FQ>(x[k], y);
+  }
+  fe_t s = x[0];
+  for (int k = 1; k < NCH; k++) s = fe_add<BN254_FQ>(s, x[k]);
+  out[tid] = s;
+}
+// chain_mad block exactly as in field.cuh (4 wide products + carry-out), independent accumulators
+__global__ void probe_chain(uint32_t* out, uint32_t a0, uint32_t b0) {
+  using namespace nova;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t X[4][9];
+  for (int k = 0; k < 4; k++) for (int i = 0; i < 9; i++) X[k][i] = tid + i + k;
+  uint32_t x = a0 + tid, y = b0 | 1;
+  for (int i = 0; i < ITER / 4; i++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) chain_mad<0, false>(X[k], x, x + 1, x + 2, x + 3, y);
+  }
+  uint32_t s = 0;
+  for (int k = 0; k < 4; k++) for (int i = 0; i < 9; i++) s += X[k][i];
+  out[tid] = s;
+}
+
+template <int NCH>
+void run_femul(int blocks_per_sm) {
+  int dev; cudaGetDevice(&dev);
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
+  int blocks = p.multiProcessorCount * blocks_per_sm, threads = 128, iters = 512;
+  nova::fe_t* out; cudaMalloc(&out, (size_t)blocks * threads * 32);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  probe_femul<NCH><<<blocks, threads>>>(out, iters);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  probe_femul<NCH><<<blocks, threads>>>(out, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double muls = (double)blocks * threads * iters * NCH;
+  printf("fe_mul chains=%d warps/SM=%2d  %8.3f ms  %7.2f G mul/s  (%.0f wide-mults/clk/SM of 64)\n", NCH,
+         blocks_per_sm * 4, ms, muls / ms / 1e6, muls * 136 / (ms * 1e-3) / 1.965e9 / p.multiProcessorCount);
+  cudaFree(out);
+}
+
+void run_chain() {
+  int dev; cudaGetDevice(&dev);
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
+  int blocks = p.multiProcessorCount * 4, threads = 256;
+  uint32_t* out; cudaMalloc(&out, (size_t)blocks * threads * 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  probe_chain<<<blocks, threads>>>(out, 3, 5);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  probe_chain<<<blocks, threads>>>(out, 3, 5);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double prods = (double)blocks * threads * (ITER / 4) * 4 * 4;
+  printf("chain_mad block (4 wide products + carry)   %8.3f ms  %6.1f wide-products/clk/SM\n", ms,
+         prods / (ms * 1e-3) / 1.965e9 / p.multiProcessorCount);
+  cudaFree(out);
+}
+
 template <int OP>
 void run(const char* name, int ops_per_iter) {
   int dev; cudaGetDevice(&dev);
@@ -71,5 +143,9 @@ int main() {
   run<2>("add.u32 (IADD3)", 1);
   run<3>("add.u64", 1);
   run<4>("fma.rz.f64 (DFMA)", 1);
+  run_chain();
+  run_femul<1>(2); run_femul<1>(4); run_femul<1>(8);
+  run_femul<2>(2); run_femul<2>(4);
+  run_femul<4>(2);
   return 0;
 }
