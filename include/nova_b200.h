@@ -44,7 +44,8 @@ enum {
   B200_E_CUDA = 2,     /* CUDA runtime failure or no device (maps to NovaError::GpuError) */
   B200_E_HANDLE = 3,   /* unknown / released handle */
   B200_E_NOMEM = 4,    /* device memory exhausted */
-  B200_E_RANGE = 5     /* slice outside the registered key (pedersen.rs:264 assert) */
+  B200_E_RANGE = 5,    /* slice outside the registered key (pedersen.rs:264 assert) */
+  B200_E_ZERO = 6      /* batch_invert met a zero (NovaError::InternalError, spartan/mod.rs:98-100) */
 };
 
 /* ---- library / device ------------------------------------------------------------------ */
@@ -137,6 +138,67 @@ int b200_axpy_dev(int field_id, const void* a, const void* b, const void* r, siz
                   void* stream);
 int b200_vec_add_dev(int field_id, const void* a, const void* b, size_t n, void* out, void* stream);
 int b200_bind_top_dev(int field_id, void* z_inout, size_t n, const void* r, void* stream);
+
+/* ---- sum-check rounds (spartan/sumcheck.rs) ------------------------------------------------
+ * One call computes the O(N) sums of one round; the host keeps the O(1) algebra (claim
+ * derivation with its inversion, sumcheck.rs:680-747), UniPoly and the transcript.
+ * `len` = current polynomial length (even); lo = P[i], hi = P[i + len/2].  Forms:
+ *   0 quad_prod  (sum A_lo B_lo, sum dA dB)                          sumcheck.rs:165-186
+ *   1 linear     (sum A_lo-B_lo, sum A(-1)-B(-1))                    sumcheck.rs:352-377
+ *   2 quadratic  (sum A_lo B_lo, sum A(-1)B(-1))                     sumcheck.rs:379-405
+ *   3 cubic      (sum ABC_lo, sum dA dB dC, sum A(-1)B(-1)C(-1))     sumcheck.rs:407-443
+ *   4 eq_cubic3  (t0, tinf) of eq*(A*B - C)                          sumcheck.rs:900-966
+ *   5 eq_cubic2  (t0, tinf) of eq*(A*B - 1)                          sumcheck.rs:972-1033
+ *   6 eq_quad1   t0 of eq*A                                          sumcheck.rs:1039-1080
+ *   7,8,9        t(-1) fall-backs of 4,5,6 (tau = 0)                 sumcheck.rs:1082-1213
+ *   10 dot_eq    sum Z[i] * eq[i]  (len = number of terms)
+ * eq factor of index id: eq_left[id >> shift] * eq_right[id & (2^shift - 1)], or eq_right[id] when
+ * eq_left is NULL (sumcheck.rs:1233-1251).  out receives 2, 2, 2, 3, 2, 2, 1, 1, 1, 1, 1 elements. */
+int b200_sc_eval(int field_id, int form, const void* A, const void* B, const void* C, size_t len,
+                 const void* eq_left, size_t eq_left_len, const void* eq_right, size_t eq_right_len,
+                 int shift, void* out);
+int b200_sc_eval_dev(int field_id, int form, const void* A, const void* B, const void* C, size_t len,
+                     const void* eq_left, const void* eq_right, int shift, void* out, void* stream);
+/* EqPolynomial::evals_from_points (spartan/polys/eq.rs:54-73): out has 2^ell entries */
+int b200_eq_table(int field_id, const void* r, int ell, void* out);
+int b200_eq_table_dev(int field_id, const void* r, int ell, void* out, void* stream);
+/* MultilinearPolynomial::evaluate_with (spartan/polys/multilinear.rs:98-127): out = Z(r) */
+int b200_mle_eval(int field_id, const void* Z, int ell, const void* r, void* out);
+int b200_mle_eval_dev(int field_id, const void* Z, int ell, const void* r, void* out, void* stream);
+/* batch_invert (spartan/mod.rs:54-145); B200_E_ZERO if an element is zero */
+int b200_batch_invert(int field_id, const void* in, size_t n, void* out);
+int b200_batch_invert_dev(int field_id, const void* in, size_t n, void* out, int* d_zero_flag,
+                          void* stream);
+/* out[i] = sum_k coeffs[k]*polys[k][i], polys zero-extended to n, k <= 32
+ * (PolyEvalWitness::batch, spartan/mod.rs:232-277; kzg_compute_batch_polynomial hyperkzg.rs:1028-1040) */
+int b200_rlc(int field_id, const void* const* polys, const size_t* lens, size_t k, const void* coeffs,
+             size_t n, void* out);
+int b200_rlc_dev(int field_id, const void* const* d_polys, const size_t* lens, size_t k,
+                 const void* d_coeffs, size_t n, void* d_out, void* stream);
+
+/* ---- HyperKZG prover pieces (provider/hyperkzg.rs:926-1116) -------------------------------- */
+/* out[j] = x*(p[2j+1] - p[2j]) + p[2j], j < n/2   (hyperkzg.rs:1085-1095) */
+int b200_kzg_fold(int field_id, const void* p, size_t n, const void* x, void* out);
+int b200_kzg_fold_dev(int field_id, const void* p, size_t n, const void* x, void* out, void* stream);
+/* evals[q] = f(us[q]), q < nu <= 8 (Horner, hyperkzg.rs:1011-1019) */
+int b200_poly_eval(int field_id, const void* f, size_t n, const void* us, size_t nu, void* evals);
+int b200_poly_eval_dev(int field_id, const void* f, size_t n, const void* us, size_t nu, void* evals,
+                       void* stream);
+/* h = f / (X - u): n-1 coefficients, h[i-1] = f[i] + u*h[i] (hyperkzg.rs:961-999) */
+int b200_poly_div(int field_id, const void* f, size_t n, const void* u, void* out);
+int b200_poly_div_dev(int field_id, const void* f, size_t n, const void* u, void* out, void* stream);
+
+/* ---- sparse matrices (r1cs/sparse.rs:19-319) ------------------------------------------------
+ * CSR as in SparseMatrix{data, indices, indptr, cols} (sparse.rs:235-247); registration uploads
+ * the matrix once and classifies its coefficients (+-1, small +-2..7, general: sparse.rs:40-105). */
+int b200_spmv_register(int field_id, const void* data_mont, const uint64_t* indices,
+                       const uint64_t* indptr, size_t rows, size_t cols, uint64_t* m_handle);
+int b200_spmv_release(uint64_t m_handle);
+int b200_spmv_dev(uint64_t m_handle, const void* d_z1, const void* d_z2_or_null, void* d_out1,
+                  void* d_out2_or_null, void* stream);
+/* R1CSShape::multiply_vec / multiply_vec_pair (r1cs/mod.rs:407-471): k matrices, one or two z */
+int b200_spmv_multi(const uint64_t* m_handles, size_t k, const void* z1, const void* z2_or_null,
+                    size_t z_len, void* const* out1, void* const* out2_or_null);
 
 #ifdef __cplusplus
 }

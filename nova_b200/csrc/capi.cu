@@ -13,6 +13,7 @@
 #include "../../include/nova_b200.h"
 #include "msm_kernels.cuh"
 #include "ops.cuh"
+#include "poly_kernels.cuh"
 
 using namespace nova;
 
@@ -832,3 +833,5 @@ int b200_bind_top(int fid, void* z, size_t n, const void* r) {
 }
 
 }  // extern "C"
+
+#include "capi_poly.inc"

@@ -33,7 +33,30 @@ struct field_ops {
   void (*axpy)(cudaStream_t, const void* a, const void* b, const void* r, size_t n, void* out);
   void (*vec_add)(cudaStream_t, const void* a, const void* b, size_t n, void* out);
   void (*bind_top)(cudaStream_t, void* z, size_t n, const void* r);
+  // --- sum-check / MLE / HyperKZG / SpMV (poly_kernels.cuh) ----------------------------------
+  // form: sc_form_id; writes sc_form_nout(form) elements to out; scratch >= SC_MAX_BLOCKS*3*32 B
+  void (*sc_reduce)(cudaStream_t, int form, const void* A, const void* B, const void* C, size_t count,
+                    size_t half, const void* eq_left, const void* eq_right, int shift, void* scratch,
+                    void* out);
+  void (*eq_small)(cudaStream_t, const void* r, int ell, void* out);
+  void (*eq_outer)(cudaStream_t, const void* left, const void* right, int right_bits, size_t n,
+                   void* out);
+  void (*batch_invert)(cudaStream_t, const void* in, size_t n, void* out, int* zero_flag);
+  void (*rlc)(cudaStream_t, const void* const* polys, const size_t* lens, int k, const void* coeffs,
+              size_t n, void* out);
+  void (*kzg_fold)(cudaStream_t, const void* p, const void* x, size_t half, void* out);
+  // chunk values + suffix carries + evaluations for nu points; vals/suffix hold nu*T elements
+  void (*poly_scan)(cudaStream_t, const void* b, size_t n, const void* us, int nu, void* vals,
+                    void* suffix, void* evals);
+  void (*poly_div_apply)(cudaStream_t, const void* b, size_t n, const void* u, const void* suffix,
+                         void* out);
+  void (*spmv_classify)(cudaStream_t, const void* vals, size_t nnz, int8_t* codes);
+  void (*spmv)(cudaStream_t, const uint32_t* indptr, const uint32_t* cols, const int8_t* codes,
+               const void* vals, size_t rows, const void* z1, const void* z2_or_null, void* o1,
+               void* o2_or_null);
 };
+constexpr int SC_MAX_BLOCKS = 148 * 4;
+constexpr int POLY_CHUNK_HOST = 64;  // must equal POLY_CHUNK in poly_kernels.cuh
 
 extern const field_ops OPS_BN254_FR, OPS_BN254_FQ, OPS_PALLAS_FP, OPS_PALLAS_FQ;
 

@@ -3,6 +3,7 @@
 #include "ops.cuh"
 #include "msm_kernels.cuh"
 #include "field_kernels.cuh"
+#include "poly_kernels.cuh"
 
 namespace nova {
 
@@ -92,9 +93,98 @@ struct ops_impl {
   static void bind_top(cudaStream_t s, void* z, size_t n, const void* r) {
     k_bind_top<F><<<stream_grid(n / 2, 256), 256, 0, s>>>(z, n / 2, r);
   }
+  template <int FORM>
+  static void sc_launch(cudaStream_t s, const void* A, const void* B, const void* C, size_t count,
+                        size_t half, const void* eq_left, const void* eq_right, int shift,
+                        void* scratch, void* out) {
+    constexpr int NOUT = sc_form_nout(FORM);
+    sc_form<F, FORM> f;
+    f.A = A;
+    f.B = B;
+    f.C = C;
+    f.h = half;
+    f.eq.left = eq_left;
+    f.eq.right = eq_right;
+    f.eq.shift = shift;
+    f.eq.mask = ((size_t)1 << shift) - 1;
+    size_t need = (count + 255) / 256;
+    int grid = (int)(need < (size_t)SC_MAX_BLOCKS ? (need ? need : 1) : SC_MAX_BLOCKS);
+    k_form_reduce<F, NOUT, sc_form<F, FORM>><<<grid, 256, 0, s>>>(f, count, scratch);
+    k_form_final<F, NOUT><<<1, 256, 0, s>>>(scratch, grid, out);
+  }
+  static void sc_reduce(cudaStream_t s, int form, const void* A, const void* B, const void* C,
+                        size_t count, size_t half, const void* eq_left, const void* eq_right,
+                        int shift, void* scratch, void* out) {
+#define SC_CASE(X) \
+  case X: sc_launch<X>(s, A, B, C, count, half, eq_left, eq_right, shift, scratch, out); break
+    switch (form) {
+      SC_CASE(SC_QUAD_PROD);
+      SC_CASE(SC_LINEAR);
+      SC_CASE(SC_QUADRATIC);
+      SC_CASE(SC_CUBIC);
+      SC_CASE(SC_EQ_CUBIC3);
+      SC_CASE(SC_EQ_CUBIC2);
+      SC_CASE(SC_EQ_QUAD1);
+      SC_CASE(SC_EQ_CUBIC3_M1);
+      SC_CASE(SC_EQ_CUBIC2_M1);
+      SC_CASE(SC_EQ_QUAD1_M1);
+      SC_CASE(SC_DOT_EQ);
+      default: break;
+    }
+#undef SC_CASE
+  }
+  static void eq_small(cudaStream_t s, const void* r, int ell, void* out) {
+    size_t n = (size_t)1 << ell;
+    k_eq_small<F><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, ell, out);
+  }
+  static void eq_outer(cudaStream_t s, const void* left, const void* right, int right_bits, size_t n,
+                       void* out) {
+    k_eq_outer<F><<<stream_grid(n, 256), 256, 0, s>>>(left, right, right_bits, n, out);
+  }
+  static void batch_invert(cudaStream_t s, const void* in, size_t n, void* out, int* zero_flag) {
+    size_t threads = (n + BINV_CHUNK - 1) / BINV_CHUNK;
+    k_batch_invert<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(in, n, out, zero_flag);
+  }
+  static void rlc(cudaStream_t s, const void* const* polys, const size_t* lens, int k,
+                  const void* coeffs, size_t n, void* out) {
+    rlc_args a;
+    a.k = k;
+    for (int i = 0; i < k; i++) {
+      a.p[i] = polys[i];
+      a.len[i] = lens[i];
+    }
+    k_rlc<F><<<stream_grid(n, 256), 256, 0, s>>>(a, coeffs, n, out);
+  }
+  static void kzg_fold(cudaStream_t s, const void* p, const void* x, size_t half, void* out) {
+    k_kzg_fold<F><<<stream_grid(half, 256), 256, 0, s>>>(p, x, half, out);
+  }
+  static void poly_scan(cudaStream_t s, const void* b, size_t n, const void* us, int nu, void* vals,
+                        void* suffix, void* evals) {
+    static_assert(POLY_CHUNK == POLY_CHUNK_HOST, "chunk constants out of sync");
+    size_t T = (n + POLY_CHUNK - 1) / POLY_CHUNK;
+    k_poly_chunk_vals<F><<<(unsigned)((T + 127) / 128), 128, 0, s>>>(b, n, us, nu, vals);
+    k_poly_suffix<F><<<nu, 512, 0, s>>>(vals, T, us, suffix, evals);
+  }
+  static void poly_div_apply(cudaStream_t s, const void* b, size_t n, const void* u,
+                             const void* suffix, void* out) {
+    size_t T = (n + POLY_CHUNK - 1) / POLY_CHUNK;
+    k_poly_div_apply<F><<<(unsigned)((T + 127) / 128), 128, 0, s>>>(b, n, u, suffix, out);
+  }
+  static void spmv_classify(cudaStream_t s, const void* vals, size_t nnz, int8_t* codes) {
+    k_spmv_classify<F><<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(vals, nnz, codes);
+  }
+  static void spmv(cudaStream_t s, const uint32_t* indptr, const uint32_t* cols, const int8_t* codes,
+                   const void* vals, size_t rows, const void* z1, const void* z2, void* o1, void* o2) {
+    if (z2)
+      k_spmv<F, 2><<<stream_grid(rows, 256), 256, 0, s>>>(indptr, cols, codes, vals, rows, z1, z2, o1, o2);
+    else
+      k_spmv<F, 1><<<stream_grid(rows, 256), 256, 0, s>>>(indptr, cols, codes, vals, rows, z1, z1, o1, o1);
+  }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
-                     sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top};
+                     sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top,
+                     sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_scan,
+                     poly_div_apply, spmv_classify, spmv};
   }
 };
 

@@ -1,0 +1,457 @@
+// Sum-check, multilinear-extension, HyperKZG and sparse-matrix kernels (K5-K8 of SURVEY.md §2).
+// All are HBM-bound streaming passes over 32-byte field elements; reductions produce 1-3 field
+// elements through a two-stage (per-block partial, single-block final) tree.
+//
+// Reference functions restated here (the host keeps the O(1) algebra, transcript and control):
+//   compute_eval_points_{quad_prod,linear,quadratic,cubic}   src/spartan/sumcheck.rs:165-186,352-443
+//   EqSumCheckInstance::evaluation_points_* (t(0), t(inf), t(-1) sums)
+//                                                            src/spartan/sumcheck.rs:900-1213
+//   EqPolynomial::evals_from_points                          src/spartan/polys/eq.rs:54-73
+//   MultilinearPolynomial::evaluate_with                     src/spartan/polys/multilinear.rs:98-127
+//   batch_invert                                             src/spartan/mod.rs:54-145
+//   PolyEvalWitness::batch (RLC of polynomials)              src/spartan/mod.rs:232-277
+//   HyperKZG fold / Horner evaluation / divide by (X-u)      src/provider/hyperkzg.rs:1083-1095,
+//                                                            1011-1019, 961-999
+//   PrecomputedSparseMatrix::multiply_vec(_pair)             src/r1cs/sparse.rs:136-230
+#pragma once
+#include <cuda_runtime.h>
+#include "field.cuh"
+
+namespace nova {
+
+// ------------------------------------------------------------------------------------------
+// reduction framework
+// ------------------------------------------------------------------------------------------
+NOVA_D fe_t fe_shfl_down(const fe_t& a, int delta) {
+  fe_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, a.l[i], delta);
+  return r;
+}
+
+// block-wide sum of NOUT accumulators; result valid in thread 0
+template <class F, int NOUT>
+NOVA_D void block_sum(fe_t (&acc)[NOUT], fe_t* sm /* [8][NOUT] */) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc[k] = fe_add<F>(acc[k], fe_shfl_down(acc[k], d));
+    if (lane == 0) sm[wid * NOUT + k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+      fe_t s = sm[k];
+      for (int w = 1; w < nw; w++) s = fe_add<F>(s, sm[w * NOUT + k]);
+      acc[k] = s;
+    }
+  }
+}
+
+template <class F, int NOUT, class Form>
+__global__ void __launch_bounds__(256) k_form_reduce(Form form, size_t count, void* partials) {
+  __shared__ fe_t sm[8 * NOUT];
+  fe_t acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) acc[k] = fe_zero<F>();
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < count;
+       id += (size_t)gridDim.x * blockDim.x)
+    form(id, acc);
+  block_sum<F, NOUT>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) fe_store(partials, (size_t)blockIdx.x * NOUT + k, acc[k]);
+}
+
+template <class F, int NOUT>
+__global__ void __launch_bounds__(256) k_form_final(const void* partials, int nblocks, void* out) {
+  __shared__ fe_t sm[8 * NOUT];
+  fe_t acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) acc[k] = fe_zero<F>();
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) acc[k] = fe_add<F>(acc[k], fe_load_rw(partials, (size_t)b * NOUT + k));
+  block_sum<F, NOUT>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) fe_store(out, k, acc[k]);
+}
+
+// ------------------------------------------------------------------------------------------
+// sum-check round forms.  `h` = half length; lo = P[id], hi = P[id + h].
+// eq factor: f = eq_left[id >> shift] * eq_right[id & mask]  (first half of the rounds), or
+//            f = eq_right[id] when eq_left == nullptr          (sumcheck.rs:1233-1251)
+// ------------------------------------------------------------------------------------------
+struct eq_factor {
+  const void* left;
+  const void* right;
+  int shift;
+  size_t mask;
+  template <class F>
+  NOVA_D fe_t get(size_t id) const {
+    if (left == nullptr) return fe_load(right, id);
+    return fe_mul<F>(fe_load(left, id >> shift), fe_load(right, id & mask));
+  }
+};
+
+enum sc_form_id {
+  SC_QUAD_PROD = 0,   // (sum A_lo B_lo, sum dA dB)                         sumcheck.rs:165-186
+  SC_LINEAR = 1,      // (sum A_lo-B_lo, sum A(-1)-B(-1))                   sumcheck.rs:352-377
+  SC_QUADRATIC = 2,   // (sum A_lo B_lo, sum A(-1) B(-1))                   sumcheck.rs:379-405
+  SC_CUBIC = 3,       // (sum ABC lo, sum dA dB dC, sum A(-1)B(-1)C(-1))    sumcheck.rs:407-443
+  SC_EQ_CUBIC3 = 4,   // t0 = sum f (A_lo B_lo - C_lo), tinf = sum f dA dB  sumcheck.rs:900-966
+  SC_EQ_CUBIC2 = 5,   // t0 = sum f (A_lo B_lo - 1),    tinf = sum f dA dB  sumcheck.rs:972-1033
+  SC_EQ_QUAD1 = 6,    // t0 = sum f A_lo                                    sumcheck.rs:1039-1080
+  SC_EQ_CUBIC3_M1 = 7,  // t(-1) = sum f (A(-1)B(-1) - C(-1))   fallback     sumcheck.rs:1082-1130
+  SC_EQ_CUBIC2_M1 = 8,  // t(-1) = sum f (A(-1)B(-1) - 1)       fallback     sumcheck.rs:1132-1178
+  SC_EQ_QUAD1_M1 = 9,   // t(-1) = sum f A(-1)                  fallback     sumcheck.rs:1180-1213
+  SC_DOT_EQ = 10,     // sum f Z[id]  (MLE evaluation, multilinear.rs:98-127; h unused)
+};
+
+template <class F, int FORM>
+struct sc_form {
+  const void *A, *B, *C;
+  size_t h;
+  eq_factor eq;
+  template <int N>
+  NOVA_D void operator()(size_t id, fe_t (&acc)[N]) const {
+    if constexpr (FORM == SC_DOT_EQ) {
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), eq.get<F>(id)));
+    } else if constexpr (FORM == SC_QUAD_PROD) {
+      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(al, bl));
+      acc[1] = fe_add<F>(acc[1], fe_mul<F>(fe_sub<F>(ah, al), fe_sub<F>(bh, bl)));
+    } else if constexpr (FORM == SC_LINEAR) {
+      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      acc[0] = fe_add<F>(acc[0], fe_sub<F>(al, bl));
+      fe_t am = fe_sub<F>(fe_dbl<F>(al), ah), bm = fe_sub<F>(fe_dbl<F>(bl), bh);
+      acc[1] = fe_add<F>(acc[1], fe_sub<F>(am, bm));
+    } else if constexpr (FORM == SC_QUADRATIC) {
+      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(al, bl));
+      fe_t am = fe_sub<F>(fe_dbl<F>(al), ah), bm = fe_sub<F>(fe_dbl<F>(bl), bh);
+      acc[1] = fe_add<F>(acc[1], fe_mul<F>(am, bm));
+    } else if constexpr (FORM == SC_CUBIC) {
+      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t cl = fe_load(C, id), ch = fe_load(C, id + h);
+      fe_t da = fe_sub<F>(ah, al), db = fe_sub<F>(bh, bl), dc = fe_sub<F>(ch, cl);
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_mul<F>(al, bl), cl));
+      acc[1] = fe_add<F>(acc[1], fe_mul<F>(fe_mul<F>(da, db), dc));
+      acc[2] = fe_add<F>(acc[2], fe_mul<F>(fe_mul<F>(fe_sub<F>(al, da), fe_sub<F>(bl, db)),
+                                           fe_sub<F>(cl, dc)));
+    } else if constexpr (FORM == SC_EQ_CUBIC3 || FORM == SC_EQ_CUBIC2) {
+      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t e0 = fe_mul<F>(al, bl);
+      if constexpr (FORM == SC_EQ_CUBIC3)
+        e0 = fe_sub<F>(e0, fe_load(C, id));
+      else
+        e0 = fe_sub<F>(e0, fe_one<F>());
+      fe_t q = fe_mul<F>(fe_sub<F>(ah, al), fe_sub<F>(bh, bl));
+      fe_t f = eq.get<F>(id);
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(e0, f));
+      acc[1] = fe_add<F>(acc[1], fe_mul<F>(q, f));
+    } else if constexpr (FORM == SC_EQ_QUAD1) {
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), eq.get<F>(id)));
+    } else if constexpr (FORM == SC_EQ_CUBIC3_M1 || FORM == SC_EQ_CUBIC2_M1) {
+      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t am = fe_sub<F>(fe_dbl<F>(al), ah), bm = fe_sub<F>(fe_dbl<F>(bl), bh);
+      fe_t e = fe_mul<F>(am, bm);
+      if constexpr (FORM == SC_EQ_CUBIC3_M1) {
+        fe_t cl = fe_load(C, id), ch = fe_load(C, id + h);
+        e = fe_sub<F>(e, fe_sub<F>(fe_dbl<F>(cl), ch));
+      } else {
+        e = fe_sub<F>(e, fe_one<F>());
+      }
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(e, eq.get<F>(id)));
+    } else if constexpr (FORM == SC_EQ_QUAD1_M1) {
+      fe_t al = fe_load(A, id), ah = fe_load(A, id + h);
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_sub<F>(fe_dbl<F>(al), ah), eq.get<F>(id)));
+    }
+  }
+};
+
+constexpr int sc_form_nout(int form) {
+  return form == SC_CUBIC ? 3
+         : (form == SC_EQ_QUAD1 || form == SC_DOT_EQ || form >= SC_EQ_CUBIC3_M1) ? 1
+                                                                                : 2;
+}
+
+// ------------------------------------------------------------------------------------------
+// eq tables (eq.rs:54-73): index bit (ell-1-k) <-> r[k]; built as an outer product of two
+// sqrt-sized tables, each entry of which is a direct product over its bits.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) k_eq_small(const void* __restrict__ r, int ell,
+                                                  void* __restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ((size_t)1 << ell)) return;
+  fe_t acc = fe_one<F>();
+  const fe_t one = fe_one<F>();
+  for (int k = 0; k < ell; k++) {
+    fe_t rk = fe_load(r, k);
+    bool bit = (idx >> (ell - 1 - k)) & 1;
+    acc = fe_mul<F>(acc, bit ? rk : fe_sub<F>(one, rk));
+  }
+  fe_store(out, idx, acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_eq_outer(const void* __restrict__ left,
+                                                  const void* __restrict__ right, int right_bits,
+                                                  size_t n, void* __restrict__ out) {
+  size_t mask = ((size_t)1 << right_bits) - 1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    fe_store(out, i, fe_mul<F>(fe_load(left, i >> right_bits), fe_load(right, i & mask)));
+}
+
+// ------------------------------------------------------------------------------------------
+// batch inversion (spartan/mod.rs:54-145).  Each thread runs Montgomery's trick over a chunk;
+// zero inputs are reported through *zero_flag (the reference returns Err(InternalError)).
+// ------------------------------------------------------------------------------------------
+constexpr int BINV_CHUNK = 32;
+template <class F>
+__global__ void __launch_bounds__(128) k_batch_invert(const void* __restrict__ in, size_t n,
+                                                      void* __restrict__ out,
+                                                      int* __restrict__ zero_flag) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * BINV_CHUNK;
+  if (lo >= n) return;
+  size_t hi = lo + BINV_CHUNK < n ? lo + BINV_CHUNK : n;
+  // pass 1: out[i] = product of in[lo..i)
+  fe_t acc = fe_one<F>();
+  for (size_t i = lo; i < hi; i++) {
+    fe_store(out, i, acc);
+    acc = fe_mul<F>(acc, fe_load(in, i));
+  }
+  if (fe_is_zero(acc)) {
+    atomicExch(zero_flag, 1);
+    return;
+  }
+  acc = fe_inv<F>(acc);
+  for (size_t i = hi; i-- > lo;) {
+    fe_t v = fe_load(in, i);
+    fe_t pre = fe_load_rw(out, i);
+    fe_store(out, i, fe_mul<F>(acc, pre));
+    acc = fe_mul<F>(acc, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// random linear combination  out[i] = sum_k coeff[k] * P_k[i]  with P_k zero-extended to n
+// (PolyEvalWitness::batch / batch_diff_size, spartan/mod.rs:232-277; hyperkzg.rs:1028-1040)
+// ------------------------------------------------------------------------------------------
+constexpr int RLC_MAX = 32;
+struct rlc_args {
+  const void* p[RLC_MAX];
+  size_t len[RLC_MAX];
+  int k;
+};
+template <class F>
+__global__ void __launch_bounds__(256) k_rlc(rlc_args a, const void* __restrict__ coeffs, size_t n,
+                                             void* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fe_t acc = fe_zero<F>();
+    for (int k = 0; k < a.k; k++)
+      if (i < a.len[k]) acc = fe_add<F>(acc, fe_mul<F>(fe_load(coeffs, k), fe_load(a.p[k], i)));
+    fe_store(out, i, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// HyperKZG pieces
+// ------------------------------------------------------------------------------------------
+// fold: out[j] = x*(P[2j+1] - P[2j]) + P[2j]                      hyperkzg.rs:1085-1095
+template <class F>
+__global__ void __launch_bounds__(256) k_kzg_fold(const void* __restrict__ p,
+                                                  const void* __restrict__ x_ptr, size_t half,
+                                                  void* __restrict__ out) {
+  const fe_t x = fe_load(x_ptr, 0);
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < half;
+       j += (size_t)gridDim.x * blockDim.x) {
+    fe_t a = fe_load(p, 2 * j), b = fe_load(p, 2 * j + 1);
+    fe_store(out, j, fe_add<F>(fe_mul<F>(x, fe_sub<F>(b, a)), a));
+  }
+}
+
+template <class F>
+NOVA_D fe_t fe_pow_u64(fe_t base, uint64_t e) {
+  fe_t acc = fe_one<F>();
+  while (e) {
+    if (e & 1) acc = fe_mul<F>(acc, base);
+    base = fe_sqr<F>(base);
+    e >>= 1;
+  }
+  return acc;
+}
+
+constexpr int POLY_CHUNK = 64;
+// chunk values V_c = sum_{k<len_c} B[c*m + k] u^k  for each of the NU points (Horner per chunk)
+template <class F>
+__global__ void __launch_bounds__(128) k_poly_chunk_vals(const void* __restrict__ b, size_t n,
+                                                         const void* __restrict__ us, int nu,
+                                                         void* __restrict__ vals /* [nu][T] */) {
+  size_t T = (n + POLY_CHUNK - 1) / POLY_CHUNK;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  size_t lo = t * POLY_CHUNK, hi = lo + POLY_CHUNK < n ? lo + POLY_CHUNK : n;
+  for (int q = 0; q < nu; q++) {
+    fe_t u = fe_load(us, q);
+    fe_t acc = fe_zero<F>();
+    for (size_t i = hi; i-- > lo;) acc = fe_add<F>(fe_mul<F>(acc, u), fe_load(b, i));
+    fe_store(vals, (size_t)q * T + t, acc);
+  }
+}
+
+// single block per point: suffix recurrence over chunk values
+//   H_c = V_{c+1} + y * H_{c+1},  H_{T-1} = 0,  y = u^m      (carry into chunk c from above)
+// and the polynomial value  P(u) = V_0 + y * H_0.  Affine maps x -> a*x + b are composed with a
+// block-wide scan.  suffix[q][c] = H_c, evals[q] = P(u_q).
+template <class F>
+__global__ void __launch_bounds__(512) k_poly_suffix(const void* __restrict__ vals, size_t T,
+                                                      const void* __restrict__ us,
+                                                      void* __restrict__ suffix,
+                                                      void* __restrict__ evals) {
+  __shared__ fe_t sa[512], sb[512];
+  const int q = blockIdx.x;
+  const fe_t y = fe_pow_u64<F>(fe_load(us, q), POLY_CHUNK);
+  const int nt = blockDim.x, tid = threadIdx.x;
+  // thread tid owns chunk indices [clo, chi) ; processed from high to low
+  size_t per = (T + nt - 1) / nt;
+  size_t clo = (size_t)tid * per, chi = clo + per < T ? clo + per : T;
+  if (clo > T) clo = T;
+  // map for the thread's range: H_{clo-1}... we define g(x) = value entering below the range
+  // given x = H_{chi-1} (carry entering the top chunk of the range).  For c from chi-1 down to clo:
+  //   carry_below = V_c + y * carry_in
+  fe_t a = fe_one<F>(), b = fe_zero<F>();  // identity map
+  for (size_t c = chi; c-- > clo;) {
+    // new = V_c + y * (a*x + b) = (y a) x + (y b + V_c)
+    a = fe_mul<F>(y, a);
+    b = fe_add<F>(fe_mul<F>(y, b), fe_load(vals, (size_t)q * T + c));
+  }
+  sa[tid] = a;
+  sb[tid] = b;
+  __syncthreads();
+  // inclusive scan from high tid to low tid: total_t = map_t o total_{t+1}
+  for (int d = 1; d < nt; d <<= 1) {
+    fe_t oa, ob;
+    bool have = tid + d < nt;
+    if (have) {
+      oa = sa[tid + d];
+      ob = sb[tid + d];
+    }
+    __syncthreads();
+    if (have) {
+      // combined(x) = mine(other(x)) = a*(oa x + ob) + b
+      fe_t na = fe_mul<F>(sa[tid], oa);
+      fe_t nb = fe_add<F>(fe_mul<F>(sa[tid], ob), sb[tid]);
+      sa[tid] = na;
+      sb[tid] = nb;
+    }
+    __syncthreads();
+  }
+  // carry entering the top of my range = total_{tid+1}(0) = sb[tid+1]
+  fe_t carry = (tid + 1 < nt) ? sb[tid + 1] : fe_zero<F>();
+  if (tid == 0) fe_store(evals, q, sb[0]);  // total_0(0) = P(u)
+  for (size_t c = chi; c-- > clo;) {
+    fe_store(suffix, (size_t)q * T + c, carry);
+    carry = fe_add<F>(fe_load(vals, (size_t)q * T + c), fe_mul<F>(y, carry));
+  }
+}
+
+// quotient by (X - u): h[k-1] = B[k] + u*h[k], h[n-1] := 0  (hyperkzg.rs:961-999); chunk c starts
+// from the carry H_c computed above.  out has n-1 coefficients.
+template <class F>
+__global__ void __launch_bounds__(128) k_poly_div_apply(const void* __restrict__ b, size_t n,
+                                                        const void* __restrict__ u_ptr,
+                                                        const void* __restrict__ suffix,
+                                                        void* __restrict__ out) {
+  size_t T = (n + POLY_CHUNK - 1) / POLY_CHUNK;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const fe_t u = fe_load(u_ptr, 0);
+  size_t lo = t * POLY_CHUNK, hi = lo + POLY_CHUNK < n ? lo + POLY_CHUNK : n;
+  fe_t carry = fe_load(suffix, t);  // = h[hi-1]
+  for (size_t k = hi; k-- > lo;) {
+    // carry == h[k];  h[k-1] = B[k] + u*h[k]
+    if (k < n - 1) fe_store(out, k, carry);
+    carry = fe_add<F>(fe_load(b, k), fe_mul<F>(u, carry));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// sparse matrix (CSR) x dense vector, coefficient classes of sparse.rs:19-133
+//   code  1 / -1      : add / subtract
+//   code  +-2..+-7     : doubling/add chains (small_mul, sparse.rs:110-133)
+//   code  0            : general coefficient, full field multiplication with vals[e]
+// One thread per row (R1CS rows carry a handful of entries); z stays L2-resident.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) k_spmv_classify(const void* __restrict__ vals, size_t nnz,
+                                                       int8_t* __restrict__ codes) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  fe_t v = fe_load(vals, e);
+  fe_t k = fe_one<F>();
+  const fe_t one = k;
+  int8_t code = 0;
+  for (int c = 1; c <= 7; c++) {
+    if (fe_eq(v, k)) code = (int8_t)c;
+    if (fe_eq(v, fe_neg<F>(k))) code = (int8_t)(-c);
+    k = fe_add<F>(k, one);
+  }
+  codes[e] = code;
+}
+
+template <class F>
+NOVA_D fe_t small_mul(int c, const fe_t& x) {  // sparse.rs:110-133
+  int a = c < 0 ? -c : c;
+  fe_t d = fe_dbl<F>(x), r;
+  switch (a) {
+    case 1: r = x; break;
+    case 2: r = d; break;
+    case 3: r = fe_add<F>(d, x); break;
+    case 4: r = fe_dbl<F>(d); break;
+    case 5: r = fe_add<F>(fe_dbl<F>(d), x); break;
+    case 6: r = fe_add<F>(fe_dbl<F>(d), d); break;
+    default: r = fe_add<F>(fe_add<F>(fe_dbl<F>(d), d), x); break;
+  }
+  return c < 0 ? fe_neg<F>(r) : r;
+}
+
+template <class F, int NV>
+__global__ void __launch_bounds__(256) k_spmv(const uint32_t* __restrict__ indptr,
+                                              const uint32_t* __restrict__ cols,
+                                              const int8_t* __restrict__ codes,
+                                              const void* __restrict__ vals, size_t rows,
+                                              const void* __restrict__ z1,
+                                              const void* __restrict__ z2, void* __restrict__ o1,
+                                              void* __restrict__ o2) {
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (size_t)gridDim.x * blockDim.x) {
+    fe_t s1 = fe_zero<F>(), s2 = fe_zero<F>();
+    for (uint32_t e = indptr[r]; e < indptr[r + 1]; e++) {
+      uint32_t col = cols[e];
+      int c = codes[e];
+      fe_t x1 = fe_load(z1, col), x2;
+      if (NV == 2) x2 = fe_load(z2, col);
+      if (c == 0) {
+        fe_t v = fe_load(vals, e);
+        s1 = fe_add<F>(s1, fe_mul<F>(v, x1));
+        if (NV == 2) s2 = fe_add<F>(s2, fe_mul<F>(v, x2));
+      } else {
+        s1 = fe_add<F>(s1, small_mul<F>(c, x1));
+        if (NV == 2) s2 = fe_add<F>(s2, small_mul<F>(c, x2));
+      }
+    }
+    fe_store(o1, r, s1);
+    if (NV == 2) fe_store(o2, r, s2);
+  }
+}
+
+}  // namespace nova

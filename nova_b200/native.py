@@ -55,6 +55,28 @@ SIGNATURES = {
     "b200_axpy_dev": [c_int, _P, _P, _P, c_size_t, _P, _P],
     "b200_vec_add_dev": [c_int, _P, _P, c_size_t, _P, _P],
     "b200_bind_top_dev": [c_int, _P, c_size_t, _P, _P],
+    "b200_sc_eval": [c_int, c_int, _P, _P, _P, c_size_t, _P, c_size_t, _P, c_size_t, c_int, _P],
+    "b200_sc_eval_dev": [c_int, c_int, _P, _P, _P, c_size_t, _P, _P, c_int, _P, _P],
+    "b200_eq_table": [c_int, _P, c_int, _P],
+    "b200_eq_table_dev": [c_int, _P, c_int, _P, _P],
+    "b200_mle_eval": [c_int, _P, c_int, _P, _P],
+    "b200_mle_eval_dev": [c_int, _P, c_int, _P, _P, _P],
+    "b200_batch_invert": [c_int, _P, c_size_t, _P],
+    "b200_batch_invert_dev": [c_int, _P, c_size_t, _P, _P, _P],
+    "b200_rlc": [c_int, ctypes.POINTER(_P), ctypes.POINTER(c_size_t), c_size_t, _P, c_size_t, _P],
+    "b200_rlc_dev": [c_int, ctypes.POINTER(_P), ctypes.POINTER(c_size_t), c_size_t, _P, c_size_t, _P, _P],
+    "b200_kzg_fold": [c_int, _P, c_size_t, _P, _P],
+    "b200_kzg_fold_dev": [c_int, _P, c_size_t, _P, _P, _P],
+    "b200_poly_eval": [c_int, _P, c_size_t, _P, c_size_t, _P],
+    "b200_poly_eval_dev": [c_int, _P, c_size_t, _P, c_size_t, _P, _P],
+    "b200_poly_div": [c_int, _P, c_size_t, _P, _P],
+    "b200_poly_div_dev": [c_int, _P, c_size_t, _P, _P, _P],
+    "b200_spmv_register": [c_int, _P, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), c_size_t, c_size_t,
+                           ctypes.POINTER(c_u64)],
+    "b200_spmv_release": [c_u64],
+    "b200_spmv_dev": [c_u64, _P, _P, _P, _P, _P],
+    "b200_spmv_multi": [ctypes.POINTER(c_u64), c_size_t, _P, _P, c_size_t, ctypes.POINTER(_P),
+                        ctypes.POINTER(_P)],
 }
 STRING_FUNCS = ["b200_last_error", "b200_version"]
 

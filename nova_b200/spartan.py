@@ -1,0 +1,369 @@
+"""Host-side mirror of the R1CS / Spartan / HyperKZG prover pieces on the hot path.
+
+Same names and argument meaning as the reference:
+
+  SparseMatrix, R1CSShape.multiply_vec / multiply_vec_pair     src/r1cs/sparse.rs, src/r1cs/mod.rs:407-471
+  EqPolynomial.evals_from_points                               src/spartan/polys/eq.rs:54-73
+  MultilinearPolynomial.evaluate_with / bind_poly_var_top      src/spartan/polys/multilinear.rs:65-127
+  batch_invert                                                 src/spartan/mod.rs:54-145
+  UniPoly                                                      src/spartan/polys/univariate.rs:89-205
+  EqSumCheckInstance, SumcheckProof.prove_quad_prod /
+  prove_cubic_with_three_inputs                                src/spartan/sumcheck.rs:199-242, 446-507, 593-1251
+  hyperkzg_prove_core (fold, batch commit, 3-point evals, batch polynomial, quotients)
+                                                               src/provider/hyperkzg.rs:926-1116
+
+The O(N) work runs on the device through the C ABI; this layer keeps exactly what the Rust host
+would keep: O(1) field algebra per round (Python integers), the transcript interface and control
+flow.  Polynomials stay RESIDENT on the device across sum-check rounds (`DeviceVec`).
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import fields
+from .native import B200Error, c_size_t, c_u64, check, lib
+from .provider import CommitmentKey, DlogGroup, _cbuf
+
+(SC_QUAD_PROD, SC_LINEAR, SC_QUADRATIC, SC_CUBIC, SC_EQ_CUBIC3, SC_EQ_CUBIC2, SC_EQ_QUAD1, SC_EQ_CUBIC3_M1,
+ SC_EQ_CUBIC2_M1, SC_EQ_QUAD1_M1, SC_DOT_EQ) = range(11)
+SC_NOUT = {0: 2, 1: 2, 2: 2, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1, 9: 1, 10: 1}
+
+
+class DeviceVec:
+    """A vector of field elements resident in HBM (b200_dev_alloc)."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = nbytes
+        p = ctypes.c_void_p()
+        check(lib().b200_dev_alloc(max(nbytes, 1), ctypes.byref(p)))
+        self.ptr = p
+
+    @classmethod
+    def from_bytes(cls, b: bytes) -> "DeviceVec":
+        v = cls(len(b))
+        if b:
+            check(lib().b200_memcpy_h2d(v.ptr, _cbuf(b), len(b)))
+        return v
+
+    def to_bytes(self, nbytes: int | None = None) -> bytes:
+        n = self.nbytes if nbytes is None else nbytes
+        out = ctypes.create_string_buffer(max(n, 1))
+        if n:
+            check(lib().b200_memcpy_d2h(out, self.ptr, n))
+        return out.raw[:n]
+
+    def free(self):
+        if self.ptr:
+            lib().b200_dev_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# sparse matrices / R1CS shape
+# ---------------------------------------------------------------------------------------------
+class SparseMatrix:
+    """CSR `SparseMatrix{data, indices, indptr, cols}` (sparse.rs:235-247), device resident."""
+
+    def __init__(self, fid: int, data: bytes, indices, indptr, cols: int):
+        self.fid, self.rows, self.cols = fid, len(indptr) - 1, cols
+        ia = (c_u64 * max(len(indices), 1))(*indices)
+        ip = (c_u64 * len(indptr))(*indptr)
+        h = c_u64(0)
+        check(lib().b200_spmv_register(fid, _cbuf(data), ia, ip, self.rows, cols, ctypes.byref(h)))
+        self.handle = h.value
+
+    def multiply_vec(self, z: bytes) -> bytes:
+        return R1CSShape._multi([self], z, None)[0][0]
+
+    def release(self):
+        if self.handle:
+            lib().b200_spmv_release(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class R1CSShape:
+    def __init__(self, A: SparseMatrix, B: SparseMatrix, C: SparseMatrix):
+        self.A, self.B, self.C = A, B, C
+
+    @staticmethod
+    def _multi(mats, z1: bytes, z2: bytes | None):
+        k = len(mats)
+        zlen = len(z1) // 32
+        hs = (c_u64 * k)(*[m.handle for m in mats])
+        o1 = [ctypes.create_string_buffer(max(32 * m.rows, 1)) for m in mats]
+        o2 = [ctypes.create_string_buffer(max(32 * m.rows, 1)) for m in mats] if z2 is not None else None
+        p1 = (ctypes.c_void_p * k)(*[ctypes.cast(b, ctypes.c_void_p) for b in o1])
+        p2 = (ctypes.c_void_p * k)(*[ctypes.cast(b, ctypes.c_void_p) for b in o2]) if o2 else None
+        rc = lib().b200_spmv_multi(hs, k, _cbuf(z1), _cbuf(z2) if z2 is not None else None, zlen, p1, p2)
+        if rc == 1 and b"InvalidWitnessLength" in lib().b200_last_error():
+            raise ValueError("InvalidWitnessLength")  # r1cs/mod.rs:411-413
+        check(rc)
+        r1 = [b.raw[:32 * m.rows] for b, m in zip(o1, mats)]
+        r2 = [b.raw[:32 * m.rows] for b, m in zip(o2, mats)] if o2 else None
+        return r1, r2
+
+    def multiply_vec(self, z: bytes):
+        """(Az, Bz, Cz) — r1cs/mod.rs:407-431."""
+        r, _ = self._multi([self.A, self.B, self.C], z, None)
+        return tuple(r)
+
+    def multiply_vec_pair(self, z1: bytes, z2: bytes):
+        """((Az1,Bz1,Cz1),(Az2,Bz2,Cz2)) — r1cs/mod.rs:435-471."""
+        r1, r2 = self._multi([self.A, self.B, self.C], z1, z2)
+        return tuple(r1), tuple(r2)
+
+
+# ---------------------------------------------------------------------------------------------
+# polynomials
+# ---------------------------------------------------------------------------------------------
+def eq_evals_from_points(fid: int, r: bytes) -> bytes:
+    ell = len(r) // 32
+    out = ctypes.create_string_buffer(32 << ell)
+    check(lib().b200_eq_table(fid, _cbuf(r), ell, out))
+    return out.raw
+
+
+def evaluate_with(fid: int, Z: bytes, r: bytes) -> bytes:
+    ell = len(r) // 32
+    assert len(Z) == 32 << ell  # multilinear.rs:90
+    out = ctypes.create_string_buffer(32)
+    check(lib().b200_mle_eval(fid, _cbuf(Z), ell, _cbuf(r), out))
+    return out.raw
+
+
+def batch_invert(fid: int, v: bytes) -> bytes:
+    """Raises ValueError("InternalError") on a zero element (spartan/mod.rs:98-100)."""
+    n = len(v) // 32
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    rc = lib().b200_batch_invert(fid, _cbuf(v), n, out)
+    if rc == 6:
+        raise ValueError("InternalError")
+    check(rc)
+    return out.raw[:32 * n]
+
+
+def rlc(fid: int, polys: list, coeffs: bytes, n: int) -> bytes:
+    k = len(polys)
+    bufs = [_cbuf(p) for p in polys]
+    ptrs = (ctypes.c_void_p * max(k, 1))(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+    lens = (c_size_t * max(k, 1))(*[len(p) // 32 for p in polys])
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    check(lib().b200_rlc(fid, ptrs, lens, k, _cbuf(coeffs), n, out))
+    return out.raw[:32 * n]
+
+
+def kzg_fold(fid: int, p: bytes, x: bytes) -> bytes:
+    n = len(p) // 32
+    out = ctypes.create_string_buffer(max(16 * n, 1))
+    check(lib().b200_kzg_fold(fid, _cbuf(p), n, _cbuf(x), out))
+    return out.raw[:16 * n]
+
+
+def poly_eval(fid: int, f: bytes, us: bytes) -> bytes:
+    n, nu = len(f) // 32, len(us) // 32
+    out = ctypes.create_string_buffer(32 * nu)
+    check(lib().b200_poly_eval(fid, _cbuf(f), n, _cbuf(us), nu, out))
+    return out.raw
+
+
+def poly_div(fid: int, f: bytes, u: bytes) -> bytes:
+    n = len(f) // 32
+    assert n > 0  # hyperkzg.rs:966
+    out = ctypes.create_string_buffer(max(32 * (n - 1), 1))
+    check(lib().b200_poly_div(fid, _cbuf(f), n, _cbuf(u), out))
+    return out.raw[:32 * (n - 1)]
+
+
+# ---------------------------------------------------------------------------------------------
+# sum-check (host keeps O(1) algebra on Python integers; device does the sums and binds)
+# ---------------------------------------------------------------------------------------------
+class UniPoly:
+    """polys/univariate.rs:89-154; transcript bytes :177-190 (non-evm)."""
+
+    def __init__(self, p, coeffs):
+        self.p, self.coeffs = p, [c % p for c in coeffs]
+
+    @classmethod
+    def from_evals_deg2(cls, p, ev):
+        c, abc, a = ev
+        return cls(p, [c, abc - a - c, a])
+
+    @classmethod
+    def from_evals_deg3(cls, p, ev):
+        d, abcd, a, m1 = ev
+        b = ((abcd + m1) * pow(2, -1, p) - d) % p
+        return cls(p, [d, abcd - a - d - b, b, a])
+
+    def evaluate(self, r):
+        acc, pw = self.coeffs[0], r
+        for c in self.coeffs[1:]:
+            acc = (acc + pw * c) % self.p
+            pw = pw * r % self.p
+        return acc
+
+    def compress(self):
+        return [self.coeffs[0]] + self.coeffs[2:]
+
+    def to_transcript_bytes(self):
+        return b"".join(int(c).to_bytes(32, "little") for c in self.compress())
+
+
+def _sc_eval_dev(fid, form, A, B, C, length, eq_left, eq_right, shift) -> list:
+    out = DeviceVec(96)
+    check(lib().b200_sc_eval_dev(fid, form, A.ptr, B.ptr if B else None, C.ptr if C else None, length,
+                                 eq_left.ptr if eq_left else None, eq_right.ptr if eq_right else None,
+                                 shift, out.ptr, None))
+    raw = out.to_bytes(32 * SC_NOUT[form])
+    return fields.unpack(fid, raw)
+
+
+def _bind_dev(fid, Z: DeviceVec, length: int, r_int: int):
+    rdev = DeviceVec.from_bytes(fields.to_mont_bytes(fid, r_int))
+    check(lib().b200_bind_top_dev(fid, Z.ptr, length, rdev.ptr, None))
+    check(lib().b200_sync())
+
+
+class EqSumCheckInstance:
+    """sumcheck.rs:593-1251.  The sqrt-sized eq tables are built on the host exactly as in `new`
+    (:606-664) and uploaded once; per-round sums run on the device."""
+
+    def __init__(self, fid: int, taus: list):
+        p = fields.MODULUS[fid]
+        self.fid, self.p = fid, p
+        l = len(taus)
+        self.init_num_vars, self.first_half = l, l // 2
+        self.second_half = l - self.first_half
+        self.round, self.taus, self.eval_eq_left = 1, list(taus), 1
+
+        def compute(ts):
+            res = [[1]]
+            for t in ts:
+                prev = res[-1]
+                hi = [v * t % p for v in prev]
+                res.append([(a - b) % p for a, b in zip(prev, hi)] + hi)
+            return res
+
+        left = list(reversed(taus[1:self.first_half])) if self.first_half >= 1 else []
+        right = list(reversed(taus[self.first_half:]))
+        self._left = [DeviceVec.from_bytes(fields.pack(fid, t)) for t in compute(left)]
+        self._right = [DeviceVec.from_bytes(fields.pack(fid, t)) for t in compute(right)]
+        self.eq_tau_0_a_inf = [((1 - t) % p, (2 * t - 1) % p, (2 - 3 * t) % p) for t in taus]
+
+    def _tables(self):
+        if self.round < self.first_half:  # poly_eqs_first_half, sumcheck.rs:1233-1246
+            return self._left[self.first_half - self.round], self._right[self.second_half], self.second_half
+        return None, self._right[self.init_num_vars - self.round], 0  # :1248-1251
+
+    def _derive(self, t0, tinf, claim, deg2: bool):
+        p, q = self.p, self.eval_eq_left
+        e0, slope, em1 = self.eq_tau_0_a_inf[self.round - 1]
+        l1p = (e0 + slope) * q % p
+        if l1p == 0:
+            return None  # tau = 0: caller computes the third sum (sumcheck.rs:696-698)
+        s0 = e0 * q * t0 % p
+        t1 = (claim - s0) * pow(l1p, -1, p) % p
+        if deg2:
+            return s0, slope * q * tinf % p, em1 * q * ((2 * tinf + 2 * t0 - t1) % p) % p
+        return s0, 0, em1 * q * ((2 * t0 - t1) % p) % p
+
+    def evaluation_points_cubic_with_three_inputs(self, A, B, C, length, claim):
+        L, R, sh = self._tables()
+        t0, tinf = _sc_eval_dev(self.fid, SC_EQ_CUBIC3, A, B, C, length, L, R, sh)
+        d = self._derive(t0, tinf, claim, True)
+        if d is not None:
+            return d
+        (tm1,) = _sc_eval_dev(self.fid, SC_EQ_CUBIC3_M1, A, B, C, length, L, R, sh)
+        e0, slope, em1 = self.eq_tau_0_a_inf[self.round - 1]
+        q, p = self.eval_eq_left, self.p
+        return e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p
+
+    def bound(self, r):
+        tau = self.taus[self.round - 1]
+        self.eval_eq_left = self.eval_eq_left * (1 - tau - r + 2 * r * tau) % self.p
+        self.round += 1
+
+
+class SumcheckProof:
+    @staticmethod
+    def prove_quad_prod(fid, claim, num_rounds, poly_A: bytes, poly_B: bytes, transcript):
+        """sumcheck.rs:199-242 -> (compressed polys, challenges r, [A(r), B(r)])."""
+        p = fields.MODULUS[fid]
+        A, B = DeviceVec.from_bytes(poly_A), DeviceVec.from_bytes(poly_B)
+        length = len(poly_A) // 32
+        rs, polys = [], []
+        for _ in range(num_rounds):
+            e0, bc = _sc_eval_dev(fid, SC_QUAD_PROD, A, B, None, length, None, None, 0)
+            poly = UniPoly.from_evals_deg2(p, [e0, (claim - e0) % p, bc])
+            transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+            r = transcript.squeeze(b"c")
+            rs.append(r)
+            polys.append(poly.compress())
+            claim = poly.evaluate(r)
+            _bind_dev(fid, A, length, r)
+            _bind_dev(fid, B, length, r)
+            length //= 2
+        return polys, rs, fields.unpack(fid, A.to_bytes(32)) + fields.unpack(fid, B.to_bytes(32))
+
+    @staticmethod
+    def prove_cubic_with_three_inputs(fid, claim, taus, poly_A: bytes, poly_B: bytes, poly_C: bytes,
+                                      transcript):
+        """sumcheck.rs:446-507."""
+        p = fields.MODULUS[fid]
+        A, B, C = (DeviceVec.from_bytes(x) for x in (poly_A, poly_B, poly_C))
+        length = len(poly_A) // 32
+        eq = EqSumCheckInstance(fid, taus)
+        rs, polys = [], []
+        for _ in range(len(taus)):
+            e0, lead, em1 = eq.evaluation_points_cubic_with_three_inputs(A, B, C, length, claim)
+            poly = UniPoly.from_evals_deg3(p, [e0, (claim - e0) % p, lead, em1])
+            transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+            r = transcript.squeeze(b"c")
+            rs.append(r)
+            polys.append(poly.compress())
+            claim = poly.evaluate(r)
+            for Z in (A, B, C):
+                _bind_dev(fid, Z, length, r)
+            eq.bound(r)
+            length //= 2
+        finals = [fields.unpack(fid, Z.to_bytes(32))[0] for Z in (A, B, C)]
+        return polys, rs, finals
+
+
+# ---------------------------------------------------------------------------------------------
+# HyperKZG prover core (hyperkzg.rs:1076-1116 with the transcript challenges r, q given)
+# ---------------------------------------------------------------------------------------------
+def hyperkzg_prove_core(curve, ck: CommitmentKey, hat_P: bytes, x: list, r: int, q: int):
+    """Returns (com[ell-1], v[ell][3], w[3]) for challenges r (evaluation points r, -r, r^2) and q
+    (batching).  `x` is the evaluation point as integers."""
+    group = DlogGroup(curve)
+    fid = group.curve.scalar_field
+    p = fields.MODULUS[fid]
+    ell = len(x)
+    n = len(hat_P) // 32
+    assert n == 1 << ell  # hyperkzg.rs:1078
+    polys = [hat_P]
+    for i in range(ell - 1):  # Phase 1: fold (hyperkzg.rs:1083-1095)
+        polys.append(kzg_fold(fid, polys[i], fields.to_mont_bytes(fid, x[ell - i - 1])))
+    com = group.batch_vartime_multiscalar_mul(polys[1:], ck)  # :1099-1100
+    u = [r % p, (-r) % p, r * r % p]  # :1105-1106
+    us = fields.pack(fid, u)
+    v = [fields.unpack(fid, poly_eval(fid, f, us)) for f in polys]  # :1048-1056
+    qp = [pow(q, k, p) for k in range(len(polys))]  # batch_challenge_powers
+    Bpoly = rlc(fid, polys, fields.pack(fid, qp), n)  # :1028-1040
+    w = []
+    for ut in u:  # :1062-1065: w_t = commit(B / (X - u_t))
+        h = poly_div(fid, Bpoly, fields.to_mont_bytes(fid, ut))
+        w.append(group.vartime_multiscalar_mul(h, ck))
+    return com, v, w

@@ -159,3 +159,79 @@ def scalar_mul(curve: int, pt: bytes, k: int) -> bytes:
     out = ctypes.create_string_buffer(64)
     assert lib().orc_scalar_mul(curve, _buf(pt), _limbs(k), out) == 0
     return out.raw
+
+
+# ---- sum-check / MLE / HyperKZG / SpMV -----------------------------------------------------------
+SC_NOUT = {0: 2, 1: 2, 2: 2, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1, 9: 1, 10: 1}
+
+
+def sc_eval(fid, form, A, B=None, C=None, eq_left=None, eq_right=None, shift=0) -> bytes:
+    n = len(A) // 32
+    out = ctypes.create_string_buffer(96)
+    rc = lib().orc_sc_eval(fid, form, _buf(A), _buf(B) if B else None, _buf(C) if C else None,
+                           ctypes.c_size_t(n), _buf(eq_left) if eq_left else None,
+                           _buf(eq_right) if eq_right else None, shift, out)
+    assert rc == 0
+    return out.raw[: 32 * SC_NOUT[form]]
+
+
+def eq_table(fid, r: bytes) -> bytes:
+    ell = len(r) // 32
+    out = ctypes.create_string_buffer(32 << ell)
+    assert lib().orc_eq_table(fid, _buf(r), ell, out) == 0
+    return out.raw
+
+
+def mle_eval(fid, Z: bytes, r: bytes) -> bytes:
+    ell = len(r) // 32
+    assert len(Z) == 32 << ell
+    out = ctypes.create_string_buffer(32)
+    assert lib().orc_mle_eval(fid, _buf(Z), ell, _buf(r), out) == 0
+    return out.raw
+
+
+def batch_invert(fid, v: bytes):
+    n = len(v) // 32
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    rc = lib().orc_batch_invert(fid, _buf(v), ctypes.c_size_t(n), out)
+    return None if rc == 2 else out.raw[: 32 * n]
+
+
+def rlc(fid, polys, coeffs: bytes, n: int) -> bytes:
+    k = len(polys)
+    bufs = [_buf(p) for p in polys]
+    ptrs = (ctypes.c_void_p * max(k, 1))(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+    lens = (ctypes.c_size_t * max(k, 1))(*[len(p) // 32 for p in polys])
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    assert lib().orc_rlc(fid, ptrs, lens, ctypes.c_size_t(k), _buf(coeffs), ctypes.c_size_t(n), out) == 0
+    return out.raw[: 32 * n]
+
+
+def kzg_fold(fid, p: bytes, x: bytes) -> bytes:
+    n = len(p) // 32
+    out = ctypes.create_string_buffer(max(16 * n, 1))
+    assert lib().orc_kzg_fold(fid, _buf(p), ctypes.c_size_t(n), _buf(x), out) == 0
+    return out.raw[: 16 * n]
+
+
+def poly_eval(fid, f: bytes, us: bytes) -> bytes:
+    n, nu = len(f) // 32, len(us) // 32
+    out = ctypes.create_string_buffer(32 * nu)
+    assert lib().orc_poly_eval(fid, _buf(f), ctypes.c_size_t(n), _buf(us), ctypes.c_size_t(nu), out) == 0
+    return out.raw
+
+
+def poly_div(fid, f: bytes, u: bytes) -> bytes:
+    n = len(f) // 32
+    out = ctypes.create_string_buffer(max(32 * (n - 1), 1))
+    assert lib().orc_poly_div(fid, _buf(f), ctypes.c_size_t(n), _buf(u), out) == 0
+    return out.raw[: 32 * (n - 1)]
+
+
+def spmv(fid, data: bytes, indices, indptr, z: bytes) -> bytes:
+    rows = len(indptr) - 1
+    ia = (ctypes.c_uint64 * max(len(indices), 1))(*indices)
+    ip = (ctypes.c_uint64 * len(indptr))(*indptr)
+    out = ctypes.create_string_buffer(max(32 * rows, 1))
+    assert lib().orc_spmv(fid, _buf(data), ia, ip, ctypes.c_size_t(rows), _buf(z), out) == 0
+    return out.raw[: 32 * rows]

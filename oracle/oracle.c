@@ -901,3 +901,256 @@ EXPORT int orc_scalar_mul(int curve, const void* pt, const uint64_t* k, void* ou
   xyzz_to_affine(cv.base, (aff*)out_affine, &r);
   return 0;
 }
+
+/* ------------------------------------------------------------------ sum-check / MLE -------- */
+/* eq factor of index id (sumcheck.rs:1233-1251): left[id >> shift] * right[id & mask], or right[id] */
+static void eq_factor(const orc_field_t* F, fe* f, const fe* left, const fe* right, int shift, size_t id) {
+  if (!left) { *f = right[id]; return; }
+  fe_mul(F, f, &left[id >> shift], &right[id & (((size_t)1 << shift) - 1)]);
+}
+/* forms 0..10 of include/nova_b200.h b200_sc_eval; restates sumcheck.rs:165-186, 352-443,
+ * 900-1213 (the O(N) sums only; claim derivation lives in oracle/pyref.py) */
+EXPORT int orc_sc_eval(int fid, int form, const void* a, const void* b, const void* c, size_t len,
+                       const void* eql, const void* eqr, int shift, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe *A = a, *B = b, *C = c, *L = eql, *R = eqr;
+  fe acc[3], one;
+  memset(acc, 0, sizeof(acc));
+  fe_one(F, &one);
+  size_t h = len / 2;
+  size_t count = form == 10 ? len : h;
+  for (size_t i = 0; i < count; i++) {
+    fe t, u, v, f, da, db, dc, am, bm, cm;
+    switch (form) {
+      case 0: /* quad_prod */
+        fe_mul(F, &t, &A[i], &B[i]); fe_add(F, &acc[0], &acc[0], &t);
+        fe_sub(F, &da, &A[h + i], &A[i]); fe_sub(F, &db, &B[h + i], &B[i]);
+        fe_mul(F, &t, &da, &db); fe_add(F, &acc[1], &acc[1], &t);
+        break;
+      case 1: /* linear */
+        fe_sub(F, &t, &A[i], &B[i]); fe_add(F, &acc[0], &acc[0], &t);
+        fe_add(F, &am, &A[i], &A[i]); fe_sub(F, &am, &am, &A[h + i]);
+        fe_add(F, &bm, &B[i], &B[i]); fe_sub(F, &bm, &bm, &B[h + i]);
+        fe_sub(F, &t, &am, &bm); fe_add(F, &acc[1], &acc[1], &t);
+        break;
+      case 2: /* quadratic */
+        fe_mul(F, &t, &A[i], &B[i]); fe_add(F, &acc[0], &acc[0], &t);
+        fe_add(F, &am, &A[i], &A[i]); fe_sub(F, &am, &am, &A[h + i]);
+        fe_add(F, &bm, &B[i], &B[i]); fe_sub(F, &bm, &bm, &B[h + i]);
+        fe_mul(F, &t, &am, &bm); fe_add(F, &acc[1], &acc[1], &t);
+        break;
+      case 3: /* cubic */
+        fe_mul(F, &t, &A[i], &B[i]); fe_mul(F, &t, &t, &C[i]); fe_add(F, &acc[0], &acc[0], &t);
+        fe_sub(F, &da, &A[h + i], &A[i]); fe_sub(F, &db, &B[h + i], &B[i]); fe_sub(F, &dc, &C[h + i], &C[i]);
+        fe_mul(F, &t, &da, &db); fe_mul(F, &t, &t, &dc); fe_add(F, &acc[1], &acc[1], &t);
+        fe_sub(F, &am, &A[i], &da); fe_sub(F, &bm, &B[i], &db); fe_sub(F, &cm, &C[i], &dc);
+        fe_mul(F, &t, &am, &bm); fe_mul(F, &t, &t, &cm); fe_add(F, &acc[2], &acc[2], &t);
+        break;
+      case 4: case 5: /* eq * (A*B - C) / eq * (A*B - 1): t(0), t(inf) */
+        fe_mul(F, &t, &A[i], &B[i]);
+        if (form == 4) fe_sub(F, &t, &t, &C[i]); else fe_sub(F, &t, &t, &one);
+        fe_sub(F, &da, &A[h + i], &A[i]); fe_sub(F, &db, &B[h + i], &B[i]);
+        fe_mul(F, &u, &da, &db);
+        eq_factor(F, &f, L, R, shift, i);
+        fe_mul(F, &t, &t, &f); fe_add(F, &acc[0], &acc[0], &t);
+        fe_mul(F, &u, &u, &f); fe_add(F, &acc[1], &acc[1], &u);
+        break;
+      case 6: /* eq * A: t(0) */
+        eq_factor(F, &f, L, R, shift, i);
+        fe_mul(F, &t, &A[i], &f); fe_add(F, &acc[0], &acc[0], &t);
+        break;
+      case 7: case 8: /* t(-1) fall-backs */
+        fe_add(F, &am, &A[i], &A[i]); fe_sub(F, &am, &am, &A[h + i]);
+        fe_add(F, &bm, &B[i], &B[i]); fe_sub(F, &bm, &bm, &B[h + i]);
+        fe_mul(F, &t, &am, &bm);
+        if (form == 7) { fe_add(F, &cm, &C[i], &C[i]); fe_sub(F, &cm, &cm, &C[h + i]); fe_sub(F, &t, &t, &cm); }
+        else fe_sub(F, &t, &t, &one);
+        eq_factor(F, &f, L, R, shift, i);
+        fe_mul(F, &t, &t, &f); fe_add(F, &acc[0], &acc[0], &t);
+        break;
+      case 9:
+        fe_add(F, &am, &A[i], &A[i]); fe_sub(F, &am, &am, &A[h + i]);
+        eq_factor(F, &f, L, R, shift, i);
+        fe_mul(F, &t, &am, &f); fe_add(F, &acc[0], &acc[0], &t);
+        break;
+      case 10: /* dot with the eq factor */
+        eq_factor(F, &f, L, R, shift, i);
+        fe_mul(F, &t, &A[i], &f); fe_add(F, &acc[0], &acc[0], &t);
+        break;
+      default: return 1;
+    }
+    (void)v;
+  }
+  int nout = form == 3 ? 3 : (form == 6 || form >= 7) ? 1 : 2;
+  memcpy(out, acc, 32 * nout);
+  return 0;
+}
+/* eq.rs:54-73 evals_from_points, the doubling algorithm verbatim */
+EXPORT int orc_eq_table(int fid, const void* r, int ell, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  fe* ev = (fe*)out;
+  size_t n = (size_t)1 << ell, size = 1;
+  memset(ev, 0, n * 32);
+  fe_one(F, &ev[0]);
+  for (int k = ell - 1; k >= 0; k--) {
+    const fe* rk = &((const fe*)r)[k];
+    for (size_t i = 0; i < size; i++) {
+      fe_mul(F, &ev[size + i], &ev[i], rk);
+      fe_sub(F, &ev[i], &ev[i], &ev[size + i]);
+    }
+    size *= 2;
+  }
+  return 0;
+}
+/* multilinear.rs:98-127 evaluate_with: two sqrt-sized tables, row dots, then the column dot */
+EXPORT int orc_mle_eval(int fid, const void* z, int ell, const void* r, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  int s_right = ell / 2, s_left = ell - s_right;
+  size_t nl = (size_t)1 << s_left, nr = (size_t)1 << s_right;
+  fe* el = (fe*)malloc(nl * 32);
+  fe* er = (fe*)malloc(nr * 32);
+  orc_eq_table(fid, r, s_left, el);
+  orc_eq_table(fid, (const fe*)r + s_left, s_right, er);
+  fe acc, t;
+  memset(&acc, 0, 32);
+  const fe* Z = (const fe*)z;
+  for (size_t i = 0; i < nl; i++) {
+    fe row;
+    memset(&row, 0, 32);
+    for (size_t j = 0; j < nr; j++) {
+      fe_mul(F, &t, &Z[i * nr + j], &er[j]);
+      fe_add(F, &row, &row, &t);
+    }
+    fe_mul(F, &t, &el[i], &row);
+    fe_add(F, &acc, &acc, &t);
+  }
+  free(el);
+  free(er);
+  memcpy(out, &acc, 32);
+  return 0;
+}
+/* spartan/mod.rs:119-145 batch_invert_serial; returns 2 when the product is zero (Err) */
+EXPORT int orc_batch_invert(int fid, const void* in, size_t n, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe* V = (const fe*)in;
+  fe* O = (fe*)out;
+  fe* prod = (fe*)malloc((n ? n : 1) * 32);
+  fe acc;
+  fe_one(F, &acc);
+  for (size_t i = 0; i < n; i++) { prod[i] = acc; fe_mul(F, &acc, &acc, &V[i]); }
+  if (fe_is_zero(&acc)) { free(prod); return 2; }
+  fe_inv(F, &acc, &acc);
+  for (size_t i = n; i-- > 0;) {
+    fe tmp;
+    fe_mul(F, &tmp, &acc, &V[i]);
+    fe_mul(F, &O[i], &prod[i], &acc);
+    acc = tmp;
+  }
+  free(prod);
+  return 0;
+}
+/* spartan/mod.rs:232-277 / hyperkzg.rs:1028-1040: out = sum_k coeff_k * P_k (zero-extended) */
+EXPORT int orc_rlc(int fid, const void* const* polys, const size_t* lens, size_t k, const void* coeffs,
+                   size_t n, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  fe* O = (fe*)out;
+  memset(O, 0, n * 32);
+  for (size_t j = 0; j < k; j++)
+    for (size_t i = 0; i < lens[j]; i++) {
+      fe t;
+      fe_mul(F, &t, &((const fe*)coeffs)[j], &((const fe*)polys[j])[i]);
+      fe_add(F, &O[i], &O[i], &t);
+    }
+  return 0;
+}
+/* hyperkzg.rs:1085-1095 */
+EXPORT int orc_kzg_fold(int fid, const void* p, size_t n, const void* x, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe* P = (const fe*)p;
+  for (size_t j = 0; j < n / 2; j++) {
+    fe d, t;
+    fe_sub(F, &d, &P[2 * j + 1], &P[2 * j]);
+    fe_mul(F, &t, (const fe*)x, &d);
+    fe_add(F, &((fe*)out)[j], &t, &P[2 * j]);
+  }
+  return 0;
+}
+/* hyperkzg.rs:1011-1019 Horner */
+EXPORT int orc_poly_eval(int fid, const void* f, size_t n, const void* us, size_t nu, void* evals) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  for (size_t q = 0; q < nu; q++) {
+    fe acc;
+    memset(&acc, 0, 32);
+    for (size_t i = n; i-- > 0;) {
+      fe_mul(F, &acc, &acc, &((const fe*)us)[q]);
+      fe_add(F, &acc, &acc, &((const fe*)f)[i]);
+    }
+    ((fe*)evals)[q] = acc;
+  }
+  return 0;
+}
+/* hyperkzg.rs:950-960 (the serial definition): h[n-2] = f[n-1]; h[i-1] = f[i] + u*h[i] */
+EXPORT int orc_poly_div(int fid, const void* f, size_t n, const void* u, void* out) {
+  if (fid < 0 || fid > 3 || n == 0) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe* Fc = (const fe*)f;
+  fe* H = (fe*)out;
+  if (n == 1) return 0;
+  H[n - 2] = Fc[n - 1];
+  for (size_t i = n - 2; i >= 1; i--) {
+    fe t;
+    fe_mul(F, &t, (const fe*)u, &H[i]);
+    fe_add(F, &H[i - 1], &Fc[i], &t);
+  }
+  return 0;
+}
+/* r1cs/sparse.rs:19-230: classification into +1 / -1 / small +-2..7 / general and the row loop */
+EXPORT int orc_spmv(int fid, const void* data, const uint64_t* indices, const uint64_t* indptr,
+                    size_t rows, const void* z, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  const fe* D = (const fe*)data;
+  const fe* Z = (const fe*)z;
+  fe small[8], nsmall[8];
+  for (uint64_t k = 1; k <= 7; k++) { fe_from_u64(F, &small[k], k); fe_neg(F, &nsmall[k], &small[k]); }
+  for (size_t r = 0; r < rows; r++) {
+    fe sum;
+    memset(&sum, 0, 32);
+    for (uint64_t e = indptr[r]; e < indptr[r + 1]; e++) {
+      const fe* x = &Z[indices[e]];
+      int code = 0;
+      for (int k = 1; k <= 7; k++) {
+        if (fe_eq(&D[e], &small[k])) code = k;
+        if (fe_eq(&D[e], &nsmall[k])) code = -k;
+      }
+      fe t;
+      if (code == 0) {
+        fe_mul(F, &t, &D[e], x);                 /* sparse.rs:155-158 general */
+      } else {                                   /* sparse.rs:110-133 small_mul (1 = plain add) */
+        int a = code < 0 ? -code : code;
+        fe d;
+        fe_dbl(F, &d, x);
+        switch (a) {
+          case 1: t = *x; break;
+          case 2: t = d; break;
+          case 3: fe_add(F, &t, &d, x); break;
+          case 4: fe_dbl(F, &t, &d); break;
+          case 5: fe_dbl(F, &t, &d); fe_add(F, &t, &t, x); break;
+          case 6: fe_dbl(F, &t, &d); fe_add(F, &t, &t, &d); break;
+          default: fe_dbl(F, &t, &d); fe_add(F, &t, &t, &d); fe_add(F, &t, &t, x); break;
+        }
+        if (code < 0) fe_neg(F, &t, &t);
+      }
+      fe_add(F, &sum, &sum, &t);
+    }
+    ((fe*)out)[r] = sum;
+  }
+  return 0;
+}

@@ -362,3 +362,197 @@ class SplitMix64:
     def field(self, p: int) -> int:
         """uniform via the from_uniform rule (64 bytes reduced mod p)."""
         return from_uniform(p, self.bytes(64))
+
+
+# ----------------------------------------------------------------------------------------
+# Sum-check restatement on Python integers (src/spartan/sumcheck.rs, polys/*.rs).  Canonical
+# integers mod p throughout; slow, for sizes up to ~2^12.
+# ----------------------------------------------------------------------------------------
+def eq_evals(p: int, r):
+    """EqPolynomial::evals_from_points (polys/eq.rs:54-73)."""
+    ev = [0] * (1 << len(r))
+    ev[0] = 1
+    size = 1
+    for rk in reversed(r):
+        for i in range(size):
+            ev[size + i] = ev[i] * rk % p
+            ev[i] = (ev[i] - ev[size + i]) % p
+        size *= 2
+    return ev
+
+
+def mle_evaluate(p: int, Z, r):
+    """MultilinearPolynomial::evaluate (polys/multilinear.rs:89-127) = <Z, eq(r)>."""
+    e = eq_evals(p, r)
+    return sum(z * w for z, w in zip(Z, e)) % p
+
+
+def bind_top(p: int, Z, r):
+    """bind_poly_var_top (polys/multilinear.rs:65-84)."""
+    h = len(Z) // 2
+    return [(Z[i] + r * (Z[i + h] - Z[i])) % p for i in range(h)]
+
+
+class UniPoly:
+    """polys/univariate.rs:89-154, 177-205."""
+
+    def __init__(self, p, coeffs):
+        self.p, self.coeffs = p, [c % p for c in coeffs]
+
+    @classmethod
+    def from_evals_deg2(cls, p, ev):
+        c, abc, a = ev[0], ev[1], ev[2]
+        return cls(p, [c, abc - a - c, a])
+
+    @classmethod
+    def from_evals_deg3(cls, p, ev):
+        d, abcd, a = ev[0], ev[1], ev[2]
+        b = ((abcd + ev[3]) * pow(2, -1, p) - d) % p
+        c = (abcd - a - d - b) % p
+        return cls(p, [d, c, b, a])
+
+    def evaluate(self, r):
+        return sum(c * pow(r, i, self.p) for i, c in enumerate(self.coeffs)) % self.p
+
+    def compressed(self):
+        return [self.coeffs[0]] + self.coeffs[2:]
+
+    def to_transcript_bytes(self):
+        return b"".join(to_repr(c) for c in self.compressed())
+
+
+class EqSumCheckInstance:
+    """spartan/sumcheck.rs:593-1251 (Gruen split-eq + BDDT claim-derived points)."""
+
+    def __init__(self, p, taus):
+        self.p = p
+        l = len(taus)
+        self.init_num_vars = l
+        self.first_half = l // 2
+        self.second_half = l - self.first_half
+        self.round = 1
+        self.taus = list(taus)
+        self.eval_eq_left = 1
+
+        def compute(ts):  # sumcheck.rs:614-634
+            res = [[1]]
+            for t in ts:
+                prev = res[-1]
+                hi = [v * t % p for v in prev]
+                lo = [(a - b) % p for a, b in zip(prev, hi)]
+                res.append(lo + hi)
+            return res
+
+        left = list(reversed(taus[1:self.first_half])) if self.first_half >= 1 else []
+        right = list(reversed(taus[self.first_half:]))
+        self.poly_eq_left = compute(left)
+        self.poly_eq_right = compute(right)
+        self.eq_tau_0_a_inf = [((1 - t) % p, (2 * t - 1) % p, (2 - 3 * t) % p) for t in taus]
+
+    # -- which tables a round uses (sumcheck.rs:1233-1251) --
+    def tables(self):
+        if self.round < self.first_half:
+            return (self.poly_eq_left[self.first_half - self.round], self.poly_eq_right[self.second_half],
+                    self.second_half)
+        return (None, self.poly_eq_right[self.init_num_vars - self.round], 0)
+
+    def factor(self, idx):
+        L, R, sh = self.tables()
+        if L is None:
+            return R[idx]
+        return L[idx >> sh] * R[idx & ((1 << sh) - 1)] % self.p
+
+    def derive_deg2(self, t0, tinf, claim):  # sumcheck.rs:680-715
+        p = self.p
+        e0, slope, em1 = self.eq_tau_0_a_inf[self.round - 1]
+        l1p = (e0 + slope) * self.eval_eq_left % p
+        if l1p == 0:
+            return None
+        s0 = e0 * self.eval_eq_left * t0 % p
+        t1 = (claim - s0) * pow(l1p, -1, p) % p
+        s_lead = slope * self.eval_eq_left * tinf % p
+        tm1 = (2 * tinf + 2 * t0 - t1) % p
+        return s0, s_lead, em1 * self.eval_eq_left * tm1 % p
+
+    def derive_deg1(self, t0, claim):  # sumcheck.rs:717-747
+        p = self.p
+        e0, slope, em1 = self.eq_tau_0_a_inf[self.round - 1]
+        l1p = (e0 + slope) * self.eval_eq_left % p
+        if l1p == 0:
+            return None
+        s0 = e0 * self.eval_eq_left * t0 % p
+        t1 = (claim - s0) * pow(l1p, -1, p) % p
+        tm1 = (2 * t0 - t1) % p
+        return s0, 0, em1 * self.eval_eq_left * tm1 % p
+
+    def evaluation_points_cubic_with_three_inputs(self, A, B, C, claim):  # sumcheck.rs:900-966
+        p = self.p
+        h = len(A) // 2
+        t0 = tinf = 0
+        for i in range(h):
+            f = self.factor(i)
+            t0 += (A[i] * B[i] - C[i]) * f
+            tinf += (A[h + i] - A[i]) * (B[h + i] - B[i]) * f
+        t0 %= p
+        tinf %= p
+        d = self.derive_deg2(t0, tinf, claim)
+        if d is not None:
+            return d
+        e0, slope, em1 = self.eq_tau_0_a_inf[self.round - 1]  # fallback sumcheck.rs:1082-1130
+        tm1 = sum(((2 * A[i] - A[h + i]) * (2 * B[i] - B[h + i]) - (2 * C[i] - C[h + i])) * self.factor(i)
+                  for i in range(h)) % p
+        q = self.eval_eq_left
+        return e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p
+
+    def evaluation_points_quadratic_with_one_input(self, A, claim):  # sumcheck.rs:1039-1080
+        p = self.p
+        h = len(A) // 2
+        t0 = sum(A[i] * self.factor(i) for i in range(h)) % p
+        d = self.derive_deg1(t0, claim)
+        if d is not None:
+            return d
+        e0, slope, em1 = self.eq_tau_0_a_inf[self.round - 1]
+        tm1 = sum((2 * A[i] - A[h + i]) * self.factor(i) for i in range(h)) % p
+        q = self.eval_eq_left
+        return e0 * q * t0 % p, 0, em1 * q * tm1 % p
+
+    def bound(self, r):  # sumcheck.rs:1226-1231
+        tau = self.taus[self.round - 1]
+        self.eval_eq_left = self.eval_eq_left * (1 - tau - r + 2 * r * tau) % self.p
+        self.round += 1
+
+
+def prove_quad_prod(p, claim, num_rounds, A, B, transcript):
+    """SumcheckProof::prove_quad_prod (sumcheck.rs:199-242).  Returns (compressed polys, r, finals)."""
+    A, B = list(A), list(B)
+    rs, polys = [], []
+    for _ in range(num_rounds):
+        h = len(A) // 2
+        e0 = sum(A[i] * B[i] for i in range(h)) % p
+        bc = sum((A[h + i] - A[i]) * (B[h + i] - B[i]) for i in range(h)) % p
+        poly = UniPoly.from_evals_deg2(p, [e0, (claim - e0) % p, bc])
+        transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+        r = transcript.squeeze(b"c")
+        rs.append(r)
+        polys.append(poly.compressed())
+        claim = poly.evaluate(r)
+        A, B = bind_top(p, A, r), bind_top(p, B, r)
+    return polys, rs, [A[0], B[0]]
+
+
+def prove_cubic_with_three_inputs(p, claim, taus, A, B, C, transcript):
+    """SumcheckProof::prove_cubic_with_three_inputs (sumcheck.rs:446-507)."""
+    A, B, C = list(A), list(B), list(C)
+    rs, polys = [], []
+    eq = EqSumCheckInstance(p, taus)
+    for _ in range(len(taus)):
+        e0, lead, em1 = eq.evaluation_points_cubic_with_three_inputs(A, B, C, claim)
+        poly = UniPoly.from_evals_deg3(p, [e0, (claim - e0) % p, lead, em1])
+        transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+        r = transcript.squeeze(b"c")
+        rs.append(r)
+        polys.append(poly.compressed())
+        claim = poly.evaluate(r)
+        A, B, C = bind_top(p, A, r), bind_top(p, B, r), bind_top(p, C, r)
+        eq.bound(r)
+    return polys, rs, [A[0], B[0], C[0]]

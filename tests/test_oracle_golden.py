@@ -168,3 +168,42 @@ def test_field_vector_kats():
     ax = co.axpy(fid, pk[0], pk[1], mont_bytes(p, u))
     for i in range(n):
         assert from_mont_bytes(p, ax[32 * i:32 * i + 32]) == (v[0][i] + u * v[1][i]) % p
+
+
+def test_sumcheck_kats_and_c_vs_python():
+    """Reference KATs through the C oracle (eq.rs:88-104, multilinear.rs:257-281,327-347,
+    sparse.rs:452-465, hyperkzg.rs:1265-1327) and the C sum-check forms against the Python
+    EqSumCheckInstance restatement."""
+    from oracle import pyref
+    fid = 0
+    p = FIELD_MODULUS[fid]
+    ints = lambda b: [from_mont_bytes(p, b[i:i + 32]) for i in range(0, len(b), 32)]
+    assert ints(co.eq_table(fid, co.field_from_u64(fid, [1, 0, 1]))) == [0, 0, 0, 0, 0, 1, 0, 0]
+    assert ints(co.mle_eval(fid, co.field_from_u64(fid, [0, 0, 0, 1, 0, 1, 0, 2]), co.field_from_u64(fid, [1, 1, 1]))) == [2]
+    assert ints(co.mle_eval(fid, co.field_from_u64(fid, [8, 8, 8, 8]), co.field_from_u64(fid, [3, 4]))) == [8]
+    assert ints(co.mle_eval(fid, co.field_from_u64(fid, [1, 2, 1, 4]), co.field_from_u64(fid, [4, 3]))) == [28]
+    out = co.spmv(fid, co.field_from_u64(fid, [2, 7, 3, 4]), [1, 2, 2, 0], [0, 2, 3, 4], co.field_from_u64(fid, [1, 2, 3]))
+    assert ints(out) == [25, 9, 4]
+    rng = SplitMix64(12)
+    l = 6
+    n = 1 << l
+    A, B, C = ([rng.field(p) for _ in range(n)] for _ in range(3))
+    taus = [rng.field(p) for _ in range(l)]
+    pk = lambda xs: b"".join(mont_bytes(p, x) for x in xs)
+    # eq table (C, doubling) == python; MLE evaluate
+    assert ints(co.eq_table(fid, pk(taus))) == pyref.eq_evals(p, taus)
+    assert ints(co.mle_eval(fid, pk(A), pk(taus))) == [pyref.mle_evaluate(p, A, taus)]
+    # t(0), t(inf) of round 1 and a later round of the eq-instance, via the C form 4 with the tables
+    # the Python instance selects
+    eq = pyref.EqSumCheckInstance(p, taus)
+    for _ in range(l):
+        L, R, sh = eq.tables()
+        h = len(A) // 2
+        t0 = sum((A[i] * B[i] - C[i]) * eq.factor(i) for i in range(h)) % p
+        tinf = sum((A[h + i] - A[i]) * (B[h + i] - B[i]) * eq.factor(i) for i in range(h)) % p
+        got = co.sc_eval(fid, 4, pk(A), pk(B), pk(C), pk(L) if L else None, pk(R), sh)
+        assert ints(got) == [t0, tinf]
+        r = rng.field(p)
+        assert ints(co.bind_top(fid, pk(A), mont_bytes(p, r))) == pyref.bind_top(p, A, r)
+        A, B, C = pyref.bind_top(p, A, r), pyref.bind_top(p, B, r), pyref.bind_top(p, C, r)
+        eq.bound(r)
