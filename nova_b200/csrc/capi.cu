@@ -158,7 +158,7 @@ std::shared_ptr<ck_ctx> get_ck(uint64_t h) {
   return it == g_handles.end() ? nullptr : it->second;
 }
 
-constexpr size_t XYZZ_BYTES = 128;
+constexpr size_t XYZZ_BYTES = 144;  // 36 words (pa29); pa32 uses the first 128
 constexpr int SUM_THREADS = 148 * 128;
 constexpr int L_MIN = 32;
 // accumulate threads are sized to ~3 full waves of 148 SMs x 16 warps x 32 lanes
@@ -326,7 +326,7 @@ int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n
                      g_dev.stream));
   if (h)
     CU(cudaMemcpyAsync((char*)ck->tables + n * 64, h, 64, cudaMemcpyHostToDevice, g_dev.stream));
-  if (ck->F > 1) {
+  {  // converts table 0 to the kernels' table format and builds tables 1..F-1
     const field_ops* bops = ops_for_field(CURVES[curve_id].base_fid);
     bops->expand_key(g_dev.stream, ck->tables, ck->stride, ck->F, ck->c * ck->G);
     CU(cudaGetLastError());

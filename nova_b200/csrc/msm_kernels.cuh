@@ -23,7 +23,7 @@
 //                 group Horner, XYZZ -> Jacobian
 #pragma once
 #include <cuda_runtime.h>
-#include "curve.cuh"
+#include "curve29.cuh"
 
 namespace nova {
 
@@ -126,48 +126,49 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint64_t* __restrict__
                                                     void* __restrict__ buckets,
                                                     void* __restrict__ parts,
                                                     uint32_t* __restrict__ pkeys) {
+  using PA = msm_arith<F>;
   const uint32_t M = start[K];
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t seg_start = t * (size_t)L;
   if (seg_start >= M) return;
   size_t seg_end = seg_start + L < M ? seg_start + L : M;
 
-  xyzz_t acc = xyzz_identity<F>();
+  typename PA::pt acc = PA::identity();
   uint64_t ent = entries[seg_start];
   uint32_t cur_key = (uint32_t)(ent >> 32);
   bool first = true;
-  affine_t pt = affine_load(tables, (uint32_t)ent & 0x7fffffffu);
+  typename PA::aff pt = PA::load_table(tables, (uint32_t)ent & 0x7fffffffu);
   for (size_t e = seg_start; e < seg_end; e++) {
     uint32_t key = (uint32_t)(ent >> 32);
     bool sign = (ent >> 31) & 1;
-    affine_t cur = pt;
+    typename PA::aff cur = pt;
     // prefetch the next entry's point while this one is being added
     if (e + 1 < seg_end) {
       ent = entries[e + 1];
-      pt = affine_load(tables, (uint32_t)ent & 0x7fffffffu);
+      pt = PA::load_table(tables, (uint32_t)ent & 0x7fffffffu);
     }
     if (key != cur_key) {
       if (first) {
-        xyzz_store(parts, 2 * t, acc);
+        PA::store(parts, 2 * t, acc);
         pkeys[2 * t] = cur_key;
         first = false;
       } else {
-        xyzz_store(buckets, cur_key, acc);
+        PA::store(buckets, cur_key, acc);
       }
-      acc = xyzz_identity<F>();
+      acc = PA::identity();
       cur_key = key;
     }
-    if (!affine_is_identity(cur)) {  // identity bases are skipped (msm.rs:247)
-      if (sign) cur.y = fe_neg<F>(cur.y);
-      xyzz_madd<F>(acc, cur.x, cur.y);
+    if (!PA::aff_is_identity(cur)) {  // identity bases are skipped (msm.rs:247)
+      if (sign) PA::neg_aff(cur);
+      PA::madd(acc, cur);
     }
   }
   if (first) {
-    xyzz_store(parts, 2 * t, acc);
+    PA::store(parts, 2 * t, acc);
     pkeys[2 * t] = cur_key;
     pkeys[2 * t + 1] = KEY_INVALID;
   } else {
-    xyzz_store(parts, 2 * t + 1, acc);
+    PA::store(parts, 2 * t + 1, acc);
     pkeys[2 * t + 1] = cur_key;
   }
 }
@@ -182,21 +183,22 @@ __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ star
                                                const void* __restrict__ parts,
                                                const uint32_t* __restrict__ pkeys,
                                                void* __restrict__ buckets) {
+  using PA = msm_arith<F>;
   uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
   if (key >= K) return;
   uint32_t s0 = start[key], s1 = start[key + 1];
   if (s1 == s0 || s1 - s0 > heavy_min) return;
   size_t j0 = 2 * ((size_t)s0 / L), j1 = 2 * (((size_t)s1 - 1) / L) + 1;
-  xyzz_t acc = xyzz_identity<F>();
+  typename PA::pt acc = PA::identity();
   bool found = false;
   for (size_t j = j0; j <= j1; j++) {
     if (pkeys[j] == key) {
-      xyzz_t o = xyzz_load(parts, j);
-      xyzz_add<F>(acc, o);
+      typename PA::pt o = PA::load(parts, j);
+      PA::add(acc, o);
       found = true;
     }
   }
-  if (found) xyzz_store(buckets, key, acc);
+  if (found) PA::store(buckets, key, acc);
 }
 
 // Heavy buckets (skewed scalars: 0/1 witnesses, repeated values) would serialise the run-head
@@ -208,30 +210,31 @@ __global__ void __launch_bounds__(256) k_fixup_heavy(const uint32_t* __restrict_
                                                      const void* __restrict__ parts,
                                                      const uint32_t* __restrict__ pkeys,
                                                      void* __restrict__ buckets) {
-  __shared__ xyzz_t sm[256];
+  using PA = msm_arith<F>;
+  __shared__ typename msm_arith<F>::pt sm[256];
   const uint32_t nheavy = heavy[0];
   for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
     uint32_t key = heavy[1 + h];
     size_t s0 = 2 * ((size_t)start[key] / L);
     size_t s1 = 2 * (((size_t)start[key + 1] - 1) / L) + 1;
-    xyzz_t acc = xyzz_identity<F>();
+    typename PA::pt acc = PA::identity();
     for (size_t k = s0 + threadIdx.x; k <= s1; k += blockDim.x) {
       if (pkeys[k] == key) {
-        xyzz_t o = xyzz_load(parts, k);
-        xyzz_add<F>(acc, o);
+        typename PA::pt o = PA::load(parts, k);
+        PA::add(acc, o);
       }
     }
     sm[threadIdx.x] = acc;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
       if ((int)threadIdx.x < s) {
-        xyzz_t a = sm[threadIdx.x];
-        xyzz_add<F>(a, sm[threadIdx.x + s]);
+        typename PA::pt a = sm[threadIdx.x];
+        PA::add(a, sm[threadIdx.x + s]);
         sm[threadIdx.x] = a;
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) xyzz_store(buckets, key, sm[0]);
+    if (threadIdx.x == 0) PA::store(buckets, key, sm[0]);
     __syncthreads();
   }
 }
@@ -245,25 +248,26 @@ template <class F>
 __global__ void __launch_bounds__(128) k_reduce1(const uint32_t* __restrict__ start, uint32_t B,
                                                  int G, int m, const void* __restrict__ buckets,
                                                  void* __restrict__ rparts) {
+  using PA = msm_arith<F>;
   uint32_t T = B / m;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= T * (uint32_t)G) return;
   uint32_t g = tid / T, k = tid % T;
   uint32_t lo = k * m;
-  xyzz_t run = xyzz_identity<F>(), tot = xyzz_identity<F>();
+  typename PA::pt run = PA::identity(), tot = PA::identity();
   for (int b = m - 1; b >= 0; b--) {
     uint32_t key = g * B + lo + b;
     if (start[key + 1] > start[key]) {
-      xyzz_t bk = xyzz_load(buckets, key);
-      xyzz_add<F>(run, bk);
+      typename PA::pt bk = PA::load(buckets, key);
+      PA::add(run, bk);
     }
-    xyzz_add<F>(tot, run);
+    PA::add(tot, run);
   }
   if (lo != 0) {
-    xyzz_t sc = xyzz_mul_small<F>(run, lo);
-    xyzz_add<F>(tot, sc);
+    typename PA::pt sc = PA::mul_small(run, lo);
+    PA::add(tot, sc);
   }
-  xyzz_store(rparts, tid, tot);
+  PA::store(rparts, tid, tot);
 }
 
 // single block: per group tree-sum of T partials, Horner over groups (c doublings each),
@@ -271,34 +275,35 @@ __global__ void __launch_bounds__(128) k_reduce1(const uint32_t* __restrict__ st
 template <class F>
 __global__ void __launch_bounds__(256) k_reduce2(const void* __restrict__ rparts, uint32_t T, int G,
                                                  int c, void* __restrict__ out_jac) {
-  __shared__ xyzz_t sm[256];
-  xyzz_t total = xyzz_identity<F>();
+  using PA = msm_arith<F>;
+  __shared__ typename msm_arith<F>::pt sm[256];
+  typename PA::pt total = PA::identity();
   for (int g = G - 1; g >= 0; g--) {
-    xyzz_t acc = xyzz_identity<F>();
+    typename PA::pt acc = PA::identity();
     for (uint32_t k = threadIdx.x; k < T; k += blockDim.x) {
-      xyzz_t o = xyzz_load(rparts, (size_t)g * T + k);
-      xyzz_add<F>(acc, o);
+      typename PA::pt o = PA::load(rparts, (size_t)g * T + k);
+      PA::add(acc, o);
     }
     sm[threadIdx.x] = acc;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
       if ((int)threadIdx.x < s) {
-        xyzz_t a = sm[threadIdx.x];
-        xyzz_add<F>(a, sm[threadIdx.x + s]);
+        typename PA::pt a = sm[threadIdx.x];
+        PA::add(a, sm[threadIdx.x + s]);
         sm[threadIdx.x] = a;
       }
       __syncthreads();
     }
     if (threadIdx.x == 0) {
       if (g != G - 1)
-        for (int d = 0; d < c; d++) xyzz_dbl<F>(total);
-      xyzz_add<F>(total, sm[0]);
+        for (int d = 0; d < c; d++) PA::dbl(total);
+      PA::add(total, sm[0]);
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     fe_t X, Y, Z;
-    xyzz_to_jacobian<F>(total, X, Y, Z);
+    PA::to_jacobian_std(total, X, Y, Z);
     fe_store(out_jac, 0, X);
     fe_store(out_jac, 1, Y);
     fe_store(out_jac, 2, Z);
@@ -309,21 +314,17 @@ __global__ void __launch_bounds__(256) k_reduce2(const void* __restrict__ rparts
 // k is tiny (= number of GPUs), one thread.
 template <class F>
 __global__ void k_jacobian_sum(const void* __restrict__ pts, int k, void* __restrict__ out_jac) {
+  using PA = msm_arith<F>;
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  xyzz_t acc = xyzz_identity<F>();
+  typename PA::pt acc = PA::identity();
   for (int i = 0; i < k; i++) {
     fe_t X = fe_load(pts, 3 * (size_t)i), Y = fe_load(pts, 3 * (size_t)i + 1),
          Z = fe_load(pts, 3 * (size_t)i + 2);
-    if (fe_is_zero(Z)) continue;
-    xyzz_t p;  // Jacobian (X,Y,Z) == XYZZ (X, Y, Z^2, Z^3)
-    p.x = X;
-    p.y = Y;
-    p.zz = fe_sqr<F>(Z);
-    p.zzz = fe_mul<F>(p.zz, Z);
-    xyzz_add<F>(acc, p);
+    typename PA::pt p = PA::from_jacobian_std(X, Y, Z);  // Jacobian (X,Y,Z) == XYZZ (X, Y, Z^2, Z^3)
+    PA::add(acc, p);
   }
   fe_t X, Y, Z;
-  xyzz_to_jacobian<F>(acc, X, Y, Z);
+  PA::to_jacobian_std(acc, X, Y, Z);
   fe_store(out_jac, 0, X);
   fe_store(out_jac, 1, Y);
   fe_store(out_jac, 2, Z);
@@ -358,32 +359,27 @@ __global__ void __launch_bounds__(128) k_index_bases(void* __restrict__ bases, s
 // ------------------------------------------------------------------------------------------
 // key expansion:  tables[t][i] = 2^(shift*t) * bases[i]  (affine; identity stays (0,0))
 // ------------------------------------------------------------------------------------------
+// In: table 0 holds the host's bases in the BOUNDARY format.  Out: every table in the arithmetic
+// policy's own table format (table 0 is converted in place).
 template <class F>
 __global__ void __launch_bounds__(128) k_expand_key(void* __restrict__ tables, size_t n_ck,
                                                     int ntables, int shift) {
+  using PA = msm_arith<F>;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ck) return;
-  affine_t p;
-  p.x = fe_load_rw(tables, 2 * i);
-  p.y = fe_load_rw(tables, 2 * i + 1);
-  if (affine_is_identity(p)) {
-    for (int t = 1; t < ntables; t++) {
-      fe_store(tables, 2 * ((size_t)t * n_ck + i), p.x);
-      fe_store(tables, 2 * ((size_t)t * n_ck + i) + 1, p.y);
-    }
+  fe_t bx = fe_load_rw(tables, 2 * i), by = fe_load_rw(tables, 2 * i + 1);
+  if (fe_is_zero(bx) && fe_is_zero(by)) {  // identity base: stays (0,0) in every table
+    for (int t = 1; t < ntables; t++) PA::store_table_identity(tables, (size_t)t * n_ck + i);
     return;
   }
+  typename PA::aff p = PA::from_std_affine(bx, by);
+  PA::store_table(tables, i, p);
   for (int t = 1; t < ntables; t++) {
-    xyzz_t q = xyzz_identity<F>();
-    xyzz_madd<F>(q, p.x, p.y);
-    for (int d = 0; d < shift; d++) xyzz_dbl<F>(q);
-    // affine: x = X/ZZ, y = Y/ZZZ;  1/ZZ = ZZ^2 * (1/ZZZ)^2 because ZZ^3 = ZZZ^2
-    fe_t iz3 = fe_inv<F>(q.zzz);
-    fe_t iz2 = fe_mul<F>(fe_sqr<F>(q.zz), fe_sqr<F>(iz3));
-    p.x = fe_mul<F>(q.x, iz2);
-    p.y = fe_mul<F>(q.y, iz3);
-    fe_store(tables, 2 * ((size_t)t * n_ck + i), p.x);
-    fe_store(tables, 2 * ((size_t)t * n_ck + i) + 1, p.y);
+    typename PA::pt q = PA::identity();
+    PA::madd(q, p);
+    for (int d = 0; d < shift; d++) PA::dbl(q);
+    p = PA::to_affine(q);
+    PA::store_table(tables, (size_t)t * n_ck + i, p);
   }
 }
 

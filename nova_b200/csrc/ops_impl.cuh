@@ -24,12 +24,13 @@ __global__ void __launch_bounds__(128) k_sum_points1(const void* __restrict__ ta
                                                      void* __restrict__ partial) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t nthreads = (size_t)gridDim.x * blockDim.x;
-  xyzz_t acc = xyzz_identity<F>();
+  using PA = msm_arith<F>;
+  typename PA::pt acc = PA::identity();
   for (size_t i = tid; i < n; i += nthreads) {
-    affine_t p = affine_load(tables, idx ? idx[i] : i);
-    if (!affine_is_identity(p)) xyzz_madd<F>(acc, p.x, p.y);
+    typename PA::aff p = PA::load_table(tables, idx ? idx[i] : i);
+    if (!PA::aff_is_identity(p)) PA::madd(acc, p);
   }
-  xyzz_store(partial, tid, acc);
+  PA::store(partial, tid, acc);
 }
 
 template <class F>

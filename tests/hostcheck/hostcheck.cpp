@@ -67,3 +67,99 @@ int hc_pt_sum(int fid, int mode, const void* pts, size_t n, void* out) {
   return 0;
 }
 }
+
+// ---- 9 x 29-bit carry-free backend (field29.cuh / curve29.cuh), same sources as the device ----
+#include "../../nova_b200/csrc/curve29.cuh"
+
+template <class F>
+static void fe29_op(int op, const fe_t& a, const fe_t& b, fe_t& r) {
+  fe29_t x = f29_from_std<F>(a), y = f29_from_std<F>(b), z;
+  switch (op) {
+    case 0: z = f29_add(x, y); f29_carry(z); break;
+    case 1: z = f29_sub<F, 2>(x, y); break;
+    case 2: z = f29_mul<F>(x, y); break;
+    case 3: z = pa29<F>::inv(x); break;
+    case 6: z = f29_neg<F, 2>(x); break;
+    case 7: z = f29_sqr<F>(x); break;
+    case 8: {  // lazy chain: ((x + y) * (x - y + 4p)) with un-normalised sum, then squared
+      fe29_t s = f29_add(x, y), d = f29_sub<F, 4>(x, y);
+      z = f29_sqr<F>(f29_mul<F>(s, d));
+      break;
+    }
+    case 9: {  // zero test: returns 1 iff x == y mod p
+      fe29_t d = f29_sub<F, 8>(x, y);
+      r = fe_zero<F>();
+      r.l[0] = f29_is_zero_modp<F>(d) ? 1 : 0;
+      return;
+    }
+    default: z = x;
+  }
+  r = f29_to_std<F>(z);
+}
+
+template <class F>
+static void pt29_sum(int mode, const affine_t* pts, size_t n, fe_t* out) {
+  using PA = pa29<F>;
+  typename PA::pt acc = PA::identity();
+  auto conv = [](const affine_t& a) { return PA::from_std_affine(a.x, a.y); };
+  if (mode == 0) {
+    for (size_t i = 0; i < n; i++)
+      if (!affine_is_identity(pts[i])) PA::madd(acc, conv(pts[i]));
+  } else if (mode == 1) {
+    for (size_t i = 0; i < n; i++) {
+      typename PA::pt q = PA::identity();
+      if (!affine_is_identity(pts[i])) PA::madd(q, conv(pts[i]));
+      PA::add(acc, q);
+    }
+  } else if (mode == 2) {
+    typename PA::pt q = PA::identity();
+    if (!affine_is_identity(pts[0])) PA::madd(q, conv(pts[0]));
+    acc = PA::mul_small(q, (uint32_t)n);
+  } else if (mode == 3) {  // through the table format and negation, then to_affine -> store/load raw
+    for (size_t i = 0; i < n; i++) {
+      if (affine_is_identity(pts[i])) continue;
+      typename PA::aff a = conv(pts[i]);
+      fe_t rx = f29_store_raw<F>(a.x), ry = f29_store_raw<F>(a.y);
+      typename PA::aff b;
+      b.x = f29_load_raw(rx);
+      b.y = f29_load_raw(ry);
+      if (i & 1) { PA::neg_aff(b); PA::neg_aff(b); }  // double negation (y -> 2p - y twice)
+      PA::madd(acc, b);
+    }
+    if (!PA::is_identity(acc)) {
+      typename PA::aff t = PA::to_affine(acc);
+      typename PA::pt q = PA::identity();
+      PA::madd(q, t);
+      acc = q;
+    }
+  }
+  PA::to_jacobian_std(acc, out[0], out[1], out[2]);
+}
+
+extern "C" {
+int hc_fe29_op(int fid, int op, const void* a, const void* b, void* out, size_t n) {
+  const fe_t* A = (const fe_t*)a;
+  const fe_t* B = (const fe_t*)b;
+  fe_t* R = (fe_t*)out;
+  for (size_t i = 0; i < n; i++) {
+    switch (fid) {
+      case 0: fe29_op<BN254_FR>(op, A[i], B[i], R[i]); break;
+      case 1: fe29_op<BN254_FQ>(op, A[i], B[i], R[i]); break;
+      case 2: fe29_op<PALLAS_FP>(op, A[i], B[i], R[i]); break;
+      case 3: fe29_op<PALLAS_FQ>(op, A[i], B[i], R[i]); break;
+      default: return 1;
+    }
+  }
+  return 0;
+}
+int hc_pt29_sum(int fid, int mode, const void* pts, size_t n, void* out) {
+  switch (fid) {
+    case 0: pt29_sum<BN254_FR>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 1: pt29_sum<BN254_FQ>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 2: pt29_sum<PALLAS_FP>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 3: pt29_sum<PALLAS_FQ>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    default: return 1;
+  }
+  return 0;
+}
+}
