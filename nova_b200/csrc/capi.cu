@@ -119,7 +119,7 @@ struct ck_ctx {
 
 // ---- optional per-stage device timing + launch accounting (for bench.py's roofline) ---------
 enum { ST_DIGITS = 0, ST_SORT, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_COUNT };
-const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 2};
+const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 3};
 struct profile_state {
   std::mutex mu;
   bool enabled = false;
@@ -207,7 +207,9 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
     CU(cudaMalloc((void**)&w.cursor, K * 4));
     CU(cudaMalloc((void**)&w.blocksums, 4096 * 4));
     CU(cudaMalloc(&w.buckets, K * XYZZ_BYTES));
-    CU(cudaMalloc(&w.rparts, ((size_t)ck.G * (ck.B / ck.m)) * XYZZ_BYTES));
+    // chunk partials of the running-sum reduce, or [G][NR+NC] row/column sums + [G][2] of the
+    // two-level reduce (NR + NC <= 2 * sqrt(2B) + 1 <= B / m + 514)
+    CU(cudaMalloc(&w.rparts, ((size_t)ck.G * (ck.B / ck.m + 516)) * XYZZ_BYTES));
     CU(cudaMalloc(&w.sumscratch, (size_t)SUM_THREADS * XYZZ_BYTES));
   }
   w.cap_n = n;

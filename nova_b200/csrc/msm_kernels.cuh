@@ -310,6 +310,111 @@ __global__ void __launch_bounds__(256) k_reduce2(const void* __restrict__ rparts
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Two-level bucket reduction (used when the bucket index splits into <= 8 + 8 bits).
+// With b = NC*u + v:   sum_b (b+1) B_b = NC * sum_u u R_u + sum_v (v+1) C_v,
+//   R_u = sum_v B[u][v] (row sums),  C_v = sum_u B[u][v] (column sums).
+// A weighted sum  sum_j j S_j  equals  sum_{j>=1} T_j  with suffix sums T_j = sum_{k>=j} S_k, so it
+// needs only a log-depth suffix scan and a tree sum -- no scalar multiplications, no serial
+// running sum.  Critical path: ~9 point additions (k_red_rowcol) + ~17 + log2(NC) doublings
+// (k_red_scan) + 2 (k_red_combine), against ~70 for the chunked running-sum kernels above.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_red_rowcol(const uint32_t* __restrict__ start, uint32_t B,
+                                                    uint32_t NR, uint32_t NC,
+                                                    const void* __restrict__ buckets,
+                                                    void* __restrict__ rc /* [G][NR+NC] */) {
+  using PA = msm_arith<F>;
+  __shared__ typename PA::pt sm[128];
+  const uint32_t g = blockIdx.y, j = blockIdx.x;  // j < NR: row j ; else column j - NR
+  const bool is_row = j < NR;
+  const uint32_t len = is_row ? NC : NR;
+  typename PA::pt acc = PA::identity();
+  for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) {
+    uint32_t b = is_row ? j * NC + k : k * NC + (j - NR);
+    uint32_t key = g * B + b;
+    if (b < B && start[key + 1] > start[key]) {
+      typename PA::pt o = PA::load(buckets, key);
+      PA::add(acc, o);
+    }
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      typename PA::pt a = sm[threadIdx.x];
+      PA::add(a, sm[threadIdx.x + s]);
+      sm[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) PA::store(rc, (size_t)g * (NR + NC) + j, sm[0]);
+}
+
+// block (g, which): which = 0 -> X = NC * sum_u u R_u ; which = 1 -> Y = sum_v (v+1) C_v
+template <class F>
+__global__ void __launch_bounds__(256) k_red_scan(const void* __restrict__ rc, uint32_t NR, uint32_t NC,
+                                                  int log_nc, void* __restrict__ xy /* [G][2] */) {
+  using PA = msm_arith<F>;
+  __shared__ typename PA::pt sm[256];
+  const uint32_t g = blockIdx.x, which = blockIdx.y;
+  const uint32_t n = which == 0 ? NR : NC;
+  const uint32_t base = g * (NR + NC) + (which == 0 ? 0 : NR);
+  const int tid = threadIdx.x;
+  typename PA::pt mine = PA::identity();
+  if ((uint32_t)tid < n) mine = PA::load(rc, base + tid);
+  sm[tid] = mine;
+  __syncthreads();
+  // inclusive suffix scan: T_tid = sum_{k >= tid} S_k
+  for (int d = 1; d < (int)n; d <<= 1) {
+    typename PA::pt o = PA::identity();
+    bool have = (uint32_t)(tid + d) < n;
+    if (have) o = sm[tid + d];
+    __syncthreads();
+    if (have) {
+      PA::add(mine, o);
+      sm[tid] = mine;
+    }
+    __syncthreads();
+  }
+  // rows: sum_{j>=1} T_j (weight u);  columns: sum_{j>=0} T_j (weight v+1)
+  if ((uint32_t)tid >= n || (which == 0 && tid == 0)) sm[tid] = PA::identity();
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+      typename PA::pt a = sm[tid];
+      PA::add(a, sm[tid + s]);
+      sm[tid] = a;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    typename PA::pt r = sm[0];
+    if (which == 0)
+      for (int d = 0; d < log_nc; d++) PA::dbl(r);  // * NC
+    PA::store(xy, (size_t)g * 2 + which, r);
+  }
+}
+
+template <class F>
+__global__ void k_red_combine(const void* __restrict__ xy, int G, int c, void* __restrict__ out_jac) {
+  using PA = msm_arith<F>;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typename PA::pt total = PA::identity();
+  for (int g = G - 1; g >= 0; g--) {
+    if (g != G - 1)
+      for (int d = 0; d < c; d++) PA::dbl(total);
+    typename PA::pt x = PA::load(xy, (size_t)g * 2), y = PA::load(xy, (size_t)g * 2 + 1);
+    PA::add(total, x);
+    PA::add(total, y);
+  }
+  fe_t X, Y, Z;
+  PA::to_jacobian_std(total, X, Y, Z);
+  fe_store(out_jac, 0, X);
+  fe_store(out_jac, 1, Y);
+  fe_store(out_jac, 2, Z);
+}
+
 // sum of k Jacobian points (the per-GPU partial MSMs after the all-gather);
 // k is tiny (= number of GPUs), one thread.
 template <class F>

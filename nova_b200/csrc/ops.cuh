@@ -45,11 +45,11 @@ struct field_ops {
   void (*rlc)(cudaStream_t, const void* const* polys, const size_t* lens, int k, const void* coeffs,
               size_t n, void* out);
   void (*kzg_fold)(cudaStream_t, const void* p, const void* x, size_t half, void* out);
-  // chunk values + suffix carries + evaluations for nu points; vals/suffix hold nu*T elements
-  void (*poly_scan)(cudaStream_t, const void* b, size_t n, const void* us, int nu, void* vals,
-                    void* suffix, void* evals);
-  void (*poly_div_apply)(cudaStream_t, const void* b, size_t n, const void* u, const void* suffix,
-                         void* out);
+  // evals[q] = f(us[q]), q < nu <= 3, coalesced strided Horner; scratch >= SC_MAX_BLOCKS*3*32 B
+  void (*poly_eval)(cudaStream_t, const void* f, size_t n, const void* us, int nu, void* scratch,
+                    void* evals);
+  // quotient f / (X - u) (n-1 coefficients); scratch >= poly_div_scratch_elems(n) * 32 B
+  void (*poly_div)(cudaStream_t, const void* f, size_t n, const void* u, void* scratch, void* out);
   void (*spmv_classify)(cudaStream_t, const void* vals, size_t nnz, int8_t* codes);
   void (*spmv)(cudaStream_t, const uint32_t* indptr, const uint32_t* cols, const int8_t* codes,
                const void* vals, size_t rows, const void* z1, const void* z2_or_null, void* o1,
@@ -57,6 +57,10 @@ struct field_ops {
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
 constexpr int POLY_CHUNK_HOST = 64;  // must equal POLY_CHUNK in poly_kernels.cuh
+inline size_t poly_div_scratch_elems(size_t n) {
+  size_t t1 = (n + POLY_CHUNK_HOST - 1) / POLY_CHUNK_HOST, t2 = (t1 + POLY_CHUNK_HOST - 1) / POLY_CHUNK_HOST;
+  return 2 * t1 + 2 * t2 + 8;
+}
 
 extern const field_ops OPS_BN254_FR, OPS_BN254_FQ, OPS_PALLAS_FP, OPS_PALLAS_FQ;
 

@@ -67,6 +67,18 @@ struct ops_impl {
     k_jacobian_sum<F><<<1, 32, 0, s>>>(pts, k, out_jac);
   }
   static void reduce(cudaStream_t s, const msm_plan& p, void* out_jac) {
+    int bits = p.c - 1;  // bucket index bits
+    if (bits >= 2 && bits <= 16) {  // two-level row/column reduction
+      int log_nc = bits / 2, log_nr = bits - log_nc;
+      uint32_t NR = 1u << log_nr, NC = 1u << log_nc;
+      dim3 g1(NR + NC, (unsigned)p.G);
+      k_red_rowcol<F><<<g1, 128, 0, s>>>(p.start, p.B, NR, NC, p.buckets, p.rparts);
+      void* xy = (char*)p.rparts + (size_t)p.G * (NR + NC) * 144;
+      dim3 g2((unsigned)p.G, 2);
+      k_red_scan<F><<<g2, 256, 0, s>>>(p.rparts, NR, NC, log_nc, xy);
+      k_red_combine<F><<<1, 32, 0, s>>>(xy, p.G, p.c, out_jac);
+      return;
+    }
     uint32_t T = p.B / p.m;
     int block = 128;
     int grid = (int)(((size_t)T * p.G + block - 1) / block);
@@ -159,17 +171,44 @@ struct ops_impl {
   static void kzg_fold(cudaStream_t s, const void* p, const void* x, size_t half, void* out) {
     k_kzg_fold<F><<<stream_grid(half, 256), 256, 0, s>>>(p, x, half, out);
   }
-  static void poly_scan(cudaStream_t s, const void* b, size_t n, const void* us, int nu, void* vals,
-                        void* suffix, void* evals) {
-    static_assert(POLY_CHUNK == POLY_CHUNK_HOST, "chunk constants out of sync");
-    size_t T = (n + POLY_CHUNK - 1) / POLY_CHUNK;
-    k_poly_chunk_vals<F><<<(unsigned)((T + 127) / 128), 128, 0, s>>>(b, n, us, nu, vals);
-    k_poly_suffix<F><<<nu, 512, 0, s>>>(vals, T, us, suffix, evals);
+  template <int NU>
+  static void poly_eval_n(cudaStream_t s, const void* f, size_t n, const void* us, void* scratch,
+                          void* evals) {
+    size_t need = (n + 255) / 256;
+    int grid = (int)(need < (size_t)SC_MAX_BLOCKS ? (need ? need : 1) : SC_MAX_BLOCKS);
+    k_poly_eval_strided<F, NU><<<grid, 256, 0, s>>>(f, n, us, scratch);
+    k_form_final<F, NU><<<1, 256, 0, s>>>(scratch, grid, evals);
   }
-  static void poly_div_apply(cudaStream_t s, const void* b, size_t n, const void* u,
-                             const void* suffix, void* out) {
-    size_t T = (n + POLY_CHUNK - 1) / POLY_CHUNK;
-    k_poly_div_apply<F><<<(unsigned)((T + 127) / 128), 128, 0, s>>>(b, n, u, suffix, out);
+  static void poly_eval(cudaStream_t s, const void* f, size_t n, const void* us, int nu, void* scratch,
+                        void* evals) {
+    if (nu == 1) poly_eval_n<1>(s, f, n, us, scratch, evals);
+    else if (nu == 2) poly_eval_n<2>(s, f, n, us, scratch, evals);
+    else poly_eval_n<3>(s, f, n, us, scratch, evals);
+  }
+  // h = f / (X - u).  Level 1: chunk values V1 (Horner per 64 coefficients).  If there are few
+  // chunks a single block scans them; otherwise the same two kernels run one level up (V1 as a
+  // polynomial in y = u^64) so the single-block scan only ever sees <= ~n/4096 values.
+  static void poly_div(cudaStream_t s, const void* f, size_t n, const void* u, void* scratch, void* out) {
+    static_assert(POLY_CHUNK == POLY_CHUNK_HOST, "chunk constants out of sync");
+    size_t T1 = (n + POLY_CHUNK - 1) / POLY_CHUNK, T2 = (T1 + POLY_CHUNK - 1) / POLY_CHUNK;
+    char* base = (char*)scratch;
+    void* v1 = base;
+    void* s1 = base + T1 * 32;
+    void* v2 = base + 2 * T1 * 32;
+    void* s2 = base + (2 * T1 + T2) * 32;
+    void* y = base + (2 * T1 + 2 * T2) * 32;
+    void* ev = base + (2 * T1 + 2 * T2 + 1) * 32;
+    unsigned g1 = (unsigned)((T1 + 127) / 128), g2 = (unsigned)((T2 + 127) / 128);
+    k_poly_chunk_vals<F><<<g1, 128, 0, s>>>(f, n, u, 1, v1);
+    if (T1 <= 8192) {
+      k_poly_suffix<F><<<1, 512, 0, s>>>(v1, T1, u, s1, ev);
+    } else {
+      k_fe_pow<F><<<1, 32, 0, s>>>(u, POLY_CHUNK, y);
+      k_poly_chunk_vals<F><<<g2, 128, 0, s>>>(v1, T1, y, 1, v2);
+      k_poly_suffix<F><<<1, 512, 0, s>>>(v2, T2, y, s2, ev);
+      k_poly_div_apply<F><<<g2, 128, 0, s>>>(v1, T1, y, s2, T1, s1);  // carries into level-1 chunks
+    }
+    k_poly_div_apply<F><<<g1, 128, 0, s>>>(f, n, u, s1, n - 1, out);
   }
   static void spmv_classify(cudaStream_t s, const void* vals, size_t nnz, int8_t* codes) {
     k_spmv_classify<F><<<(unsigned)((nnz + 255) / 256), 256, 0, s>>>(vals, nnz, codes);
@@ -184,8 +223,7 @@ struct ops_impl {
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top,
-                     sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_scan,
-                     poly_div_apply, spmv_classify, spmv};
+                     sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv};
   }
 };
 

@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(256) k_kzg_fold(const void* __restrict__ p,
   }
 }
 
+
 template <class F>
 NOVA_D fe_t fe_pow_u64(fe_t base, uint64_t e) {
   fe_t acc = fe_one<F>();
@@ -288,6 +289,41 @@ NOVA_D fe_t fe_pow_u64(fe_t base, uint64_t e) {
     e >>= 1;
   }
   return acc;
+}
+
+// Horner evaluation at NU points with COALESCED loads: thread t owns coefficients t, t+T, t+2T, ...
+// and evaluates  A_t(y) = sum_k f[t + kT] y^k  with y = u^T by Horner (high k first); then
+//   f(u) = sum_t u^t A_t(u^T).   (hyperkzg.rs:1011-1019 computes the same value serially.)
+// Every coefficient is loaded once for all NU points; partials[blockIdx][q] feed k_form_final.
+template <class F, int NU>
+__global__ void __launch_bounds__(256) k_poly_eval_strided(const void* __restrict__ f, size_t n,
+                                                           const void* __restrict__ us,
+                                                           void* __restrict__ partials) {
+  __shared__ fe_t sm[8 * NU];
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fe_t acc[NU], y[NU], ut[NU];
+#pragma unroll
+  for (int q = 0; q < NU; q++) {
+    fe_t u = fe_load(us, q);
+    y[q] = fe_pow_u64<F>(u, T);
+    ut[q] = fe_pow_u64<F>(u, t);
+    acc[q] = fe_zero<F>();
+  }
+  if (t < n) {
+    size_t kmax = (n - 1 - t) / T;  // largest k with t + kT < n
+    for (size_t k = kmax + 1; k-- > 0;) {
+      fe_t c = fe_load(f, t + k * T);
+#pragma unroll
+      for (int q = 0; q < NU; q++) acc[q] = fe_add<F>(fe_mul<F>(acc[q], y[q]), c);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NU; q++) acc[q] = fe_mul<F>(acc[q], ut[q]);
+  block_sum<F, NU>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int q = 0; q < NU; q++) fe_store(partials, (size_t)blockIdx.x * NU + q, acc[q]);
 }
 
 constexpr int POLY_CHUNK = 64;
@@ -364,13 +400,20 @@ __global__ void __launch_bounds__(512) k_poly_suffix(const void* __restrict__ va
   }
 }
 
+// y = u^e (single element), for the second scan level
+template <class F>
+__global__ void k_fe_pow(const void* __restrict__ u, uint64_t e, void* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) fe_store(out, 0, fe_pow_u64<F>(fe_load(u, 0), e));
+}
+
 // quotient by (X - u): h[k-1] = B[k] + u*h[k], h[n-1] := 0  (hyperkzg.rs:961-999); chunk c starts
-// from the carry H_c computed above.  out has n-1 coefficients.
+// from the carry H_c computed above.  out[k] = h[k] for k < out_len (n-1 for the quotient; n when the
+// same recurrence is reused one level up to spread carries over the level-1 chunks).
 template <class F>
 __global__ void __launch_bounds__(128) k_poly_div_apply(const void* __restrict__ b, size_t n,
                                                         const void* __restrict__ u_ptr,
                                                         const void* __restrict__ suffix,
-                                                        void* __restrict__ out) {
+                                                        size_t out_len, void* __restrict__ out) {
   size_t T = (n + POLY_CHUNK - 1) / POLY_CHUNK;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -379,7 +422,7 @@ __global__ void __launch_bounds__(128) k_poly_div_apply(const void* __restrict__
   fe_t carry = fe_load(suffix, t);  // = h[hi-1]
   for (size_t k = hi; k-- > lo;) {
     // carry == h[k];  h[k-1] = B[k] + u*h[k]
-    if (k < n - 1) fe_store(out, k, carry);
+    if (k < out_len) fe_store(out, k, carry);
     carry = fe_add<F>(fe_load(b, k), fe_mul<F>(u, carry));
   }
 }

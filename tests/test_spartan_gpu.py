@@ -193,7 +193,7 @@ def test_rlc_diff_sizes(sp, oracle):
 
 
 # ---------------------------------------------------------------- HyperKZG pieces --------------
-@pytest.mark.parametrize("n", [2, 64, 65, 128, 4097, 1 << 16])
+@pytest.mark.parametrize("n", [2, 3, 64, 65, 128, 4097, 1 << 16, (1 << 20) + 3])
 def test_poly_eval_div_fold(sp, oracle, n):
     fid = 0
     f = oracle.gen_scalars(fid, n, n)
