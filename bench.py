@@ -246,7 +246,7 @@ def run_b200(args):
     # ---------------- CPU baseline beside it (N = 1 only) ---------------------------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_reference_run(args.log2n, steps=1, warmup=0, sc_np=sc_np)
+        cpu_baseline = cpu_reference_run(args.log2n, steps=2, warmup=1, sc_np=sc_np)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -302,14 +302,15 @@ def cpu_reference_run(log2n, steps, warmup, sc_np=None):
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first 2^{n.bit_length() - 1} of the 2^{log2n} pairs, {steps} run(s), {dt * 1e3:.1f} ms each",
             "note": "C restatement of msm.rs (signed split + bit-width partition; halo2curves msm_best "
-                    "restated as signed-digit Pippenger), pthreads, no hand-written asm"}
+                    "restated as signed-digit Pippenger, c = ln(n)+2, (window x slice) jobs over all "
+                    "cores), pthreads, __int128 Montgomery (~21 ns/mul on a 2.1 GHz Xeon), no hand asm"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference_run(args.log2n, steps=args.steps, warmup=min(args.warmup, 1))
+    cb = cpu_reference_run(args.log2n, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
     n_sample = cb["sample"]
     out = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,

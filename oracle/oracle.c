@@ -31,6 +31,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <time.h>
+static double now_s(void){struct timespec t;clock_gettime(CLOCK_MONOTONIC,&t);return t.tv_sec+t.tv_nsec*1e-9;}
 
 #include "field_constants.h"
 
@@ -308,6 +311,34 @@ static void par_chunks(size_t n, int nthreads, chunk_fn fn, void* ctx) {
   free(jobs);
 }
 
+/* dynamic variant: threads pull single job indices from a shared counter (rayon-style work
+ * stealing is approximated by this; jobs are coarse so contention is nil) */
+typedef struct { chunk_fn fn; void* ctx; size_t njobs; size_t* next; int tid; } djob_t;
+static void* djob_main(void* a) {
+  djob_t* j = (djob_t*)a;
+  for (;;) {
+    size_t k = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+    if (k >= j->njobs) break;
+    j->fn(j->ctx, k, k + 1, j->tid);
+  }
+  return NULL;
+}
+static void par_jobs(size_t njobs, int nthreads, chunk_fn fn, void* ctx) {
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > njobs) nthreads = njobs ? (int)njobs : 1;
+  size_t next = 0;
+  if (nthreads == 1) { fn(ctx, 0, njobs, 0); return; }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  djob_t* jobs = (djob_t*)malloc(sizeof(djob_t) * nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (djob_t){fn, ctx, njobs, &next, t};
+    pthread_create(&th[t], NULL, djob_main, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+}
+
 /* ------------------------------------------------------------------ MSM pieces ------------ */
 typedef struct {
   const orc_field_t* F;
@@ -462,22 +493,88 @@ static void best_chunk(void* vctx, size_t lo, size_t hi, int tid) {
   free(wsum);
   cx->partial[tid] = total;
 }
+/* halo2curves::msm::msm_best stand-in, parallel shape: one global window size c = ln(n) + 2 (the
+ * published Pippenger choice), signed digits precomputed per scalar, and the work split into
+ * (window, point-slice) jobs so that all host threads stay busy for any n -- this mirrors how
+ * msm_best parallelises (over windows, then within a window), and is what the CPU baseline times. */
+typedef struct {
+  const orc_field_t* F;
+  const aff* bases;
+  const int32_t* digits; /* [n][nwin] */
+  size_t n;
+  int c, nwin, nslices;
+  xyzz* job_out; /* [nwin][nslices] */
+} best2_ctx;
+static void best2_job(void* vctx, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  best2_ctx* cx = (best2_ctx*)vctx;
+  const orc_field_t* F = cx->F;
+  size_t nb = (size_t)1 << (cx->c - 1);
+  xyzz* buckets = (xyzz*)malloc(sizeof(xyzz) * nb);
+  for (size_t job = lo; job < hi; job++) {
+    int w = (int)(job / cx->nslices), sl = (int)(job % cx->nslices);
+    size_t per = (cx->n + cx->nslices - 1) / cx->nslices;
+    size_t plo = (size_t)sl * per, phi = plo + per < cx->n ? plo + per : cx->n;
+    for (size_t b = 0; b < nb; b++) xyzz_zero(F, &buckets[b]);
+    for (size_t i = plo; i < phi; i++) {
+      int32_t d = cx->digits[i * cx->nwin + w];
+      if (d > 0) xyzz_add_affine(F, &buckets[d - 1], &cx->bases[i]);
+      else if (d < 0) {
+        aff np;
+        aff_neg(F, &np, &cx->bases[i]);
+        xyzz_add_affine(F, &buckets[-d - 1], &np);
+      }
+    }
+    xyzz res, running;
+    xyzz_zero(F, &res);
+    xyzz_zero(F, &running);
+    for (size_t b = nb; b-- > 0;) {
+      xyzz_add(F, &running, &buckets[b]);
+      xyzz_add(F, &res, &running);
+    }
+    cx->job_out[job] = res;
+  }
+  free(buckets);
+}
+typedef struct { const uint64_t* canon; int32_t* digits; int c, nwin; } dig_ctx;
+static void digits_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  dig_ctx* cx = (dig_ctx*)vctx;
+  uint32_t half = (uint32_t)1 << (cx->c - 1);
+  for (size_t i = lo; i < hi; i++) {
+    uint32_t carry = 0;
+    for (int w = 0; w < cx->nwin; w++) {
+      uint32_t v = get_window(&cx->canon[4 * i], w * cx->c, cx->c) + carry;
+      if (v > half) { cx->digits[i * cx->nwin + w] = (int32_t)v - (int32_t)((uint32_t)1 << cx->c); carry = 1; }
+      else { cx->digits[i * cx->nwin + w] = (int32_t)v; carry = 0; }
+    }
+  }
+}
 static void msm_best_canon(const curve_t* cv, const uint64_t* canon, const aff* bases, size_t n,
                            int nthreads, xyzz* out) {
   const orc_field_t* F = cv->base;
   xyzz_zero(F, out);
   if (n == 0) return;
   if (nthreads < 1) nthreads = 1;
-  if ((size_t)nthreads > n) nthreads = (int)n;
-  size_t per = (n + nthreads - 1) / nthreads;
-  int c = per < 32 ? 3 : (int)compute_ln(per) + 2; /* ln(n)+2, the usual Pippenger window */
+  int c = n < 32 ? 3 : (int)compute_ln(n) + 2;
   if (c > 16) c = 16;
-  best_ctx cx = {F, bases, canon, c, (cv->scalar->bits + 1 + c - 1) / c, NULL};
-  cx.partial = (xyzz*)malloc(sizeof(xyzz) * nthreads);
-  for (int t = 0; t < nthreads; t++) xyzz_zero(F, &cx.partial[t]);
-  par_chunks(n, nthreads, best_chunk, &cx);
-  for (int t = 0; t < nthreads; t++) xyzz_add(F, out, &cx.partial[t]);
-  free(cx.partial);
+  int nwin = (cv->scalar->bits + 1 + c - 1) / c;
+  int nslices = (2 * nthreads + nwin - 1) / nwin; /* ~2 jobs per thread, pulled dynamically */
+  if ((size_t)nslices > n) nslices = (int)n;
+  if (nslices < 1) nslices = 1;
+  int32_t* digits = (int32_t*)malloc(sizeof(int32_t) * n * nwin);
+  dig_ctx dc = {canon, digits, c, nwin};
+  par_chunks(n, nthreads, digits_chunk, &dc);
+  best2_ctx cx = {F, bases, digits, n, c, nwin, nslices, NULL};
+  size_t njobs = (size_t)nwin * nslices;
+  cx.job_out = (xyzz*)malloc(sizeof(xyzz) * njobs);
+  par_jobs(njobs, nthreads, best2_job, &cx);
+  for (int w = nwin - 1; w >= 0; w--) {
+    for (int d = 0; d < c; d++) xyzz_double(F, out);
+    for (int sl = 0; sl < nslices; sl++) xyzz_add(F, out, &cx.job_out[(size_t)w * nslices + sl]);
+  }
+  free(cx.job_out);
+  free(digits);
 }
 
 /* msm.rs:478-503 msm_small_with_max_num_bits on u64 scalars */
@@ -649,12 +746,41 @@ EXPORT int orc_batch_add(int curve, const void* bases, const uint64_t* idx, size
   return 0;
 }
 
-/* msm.rs:225-419: the full dispatcher */
 typedef struct { uint64_t key; } cls_t;
-static int cls_cmp(const void* a, const void* b) {
-  uint8_t ga = (uint8_t)(((const cls_t*)a)->key >> 60), gb = (uint8_t)(((const cls_t*)b)->key >> 60);
-  return (int)ga - (int)gb;
+typedef struct { const cls_t* cls; const aff* bases; const uint64_t* canon; aff* gb; uint64_t* lc; } gather_ctx;
+static void gather_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  gather_ctx* g = (gather_ctx*)vctx;
+  for (size_t k = lo; k < hi; k++) {
+    size_t idx = (size_t)(g->cls[k].key & 0x0FFFFFFFFFFFFFFFull);
+    g->gb[k] = g->bases[idx];
+    memcpy(&g->lc[4 * k], &g->canon[4 * idx], 32);
+  }
 }
+typedef struct {
+  const orc_field_t* S;
+  const fe* scalars;
+  const aff* bases;
+  uint64_t *canon, *ncanon;
+  uint8_t* grp;
+} classify_ctx;
+static void classify_chunk(void* vctx, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  classify_ctx* c = (classify_ctx*)vctx;
+  for (size_t i = lo; i < hi; i++) {
+    if (fe_is_zero(&c->scalars[i]) || aff_is_identity(&c->bases[i])) { c->grp[i] = 0xff; continue; } /* :247 */
+    fe s, ns, t;
+    fe_from_mont(c->S, &s, &c->scalars[i]);
+    fe_neg(c->S, &t, &c->scalars[i]);
+    fe_from_mont(c->S, &ns, &t);
+    memcpy(&c->canon[4 * i], s.l, 32);
+    memcpy(&c->ncanon[4 * i], ns.l, 32);
+    uint32_t bs = num_bits4(s.l), bn = num_bits4(ns.l);
+    c->grp[i] = bs <= 1 ? 0 : bn <= 1 ? 1 : bs <= 8 ? 2 : bn <= 8 ? 3 : bs <= 16 ? 4 : bn <= 16 ? 5
+                : bs <= 32 ? 6 : bn <= 32 ? 7 : bs <= 64 ? 8 : bn <= 64 ? 9 : 10;
+  }
+}
+/* msm.rs:225-419: the full dispatcher */
 EXPORT int orc_msm(int curve, const void* scalars_v, const void* bases_v, size_t n, int nthreads,
                    void* out_affine) {
   curve_t cv;
@@ -666,36 +792,34 @@ EXPORT int orc_msm(int curve, const void* scalars_v, const void* bases_v, size_t
   xyzz_zero(F, &total);
   if (n == 0) { memset(out_affine, 0, 64); return 0; }          /* msm.rs:228-230 */
   if (n <= 16) return orc_msm_naive(curve, scalars_v, bases_v, n, 1, out_affine); /* :233 */
-  /* Phase 1: classify (msm.rs:243-279) */
+  double T0 = now_s();
+  /* Phase 1: classify in parallel (msm.rs:243-279 par_iter().filter_map) */
   cls_t* cls = (cls_t*)malloc(sizeof(cls_t) * n);
   uint64_t* canon = (uint64_t*)malloc(n * 32);   /* canonical s        */
   uint64_t* ncanon = (uint64_t*)malloc(n * 32);  /* canonical of (-s)  */
+  uint8_t* grp = (uint8_t*)malloc(n);
+  classify_ctx cc = {S, scalars, bases, canon, ncanon, grp};
+  par_chunks(n, nthreads, classify_chunk, &cc);
   size_t m = 0;
-  for (size_t i = 0; i < n; i++) {
-    if (fe_is_zero(&scalars[i]) || aff_is_identity(&bases[i])) continue; /* :247 */
-    fe s, ns, t;
-    fe_from_mont(S, &s, &scalars[i]);
-    fe_neg(S, &t, &scalars[i]);
-    fe_from_mont(S, &ns, &t);
-    memcpy(&canon[4 * i], s.l, 32);
-    memcpy(&ncanon[4 * i], ns.l, 32);
-    uint32_t bs = num_bits4(s.l), bn = num_bits4(ns.l);
-    uint8_t g = bs <= 1 ? 0 : bn <= 1 ? 1 : bs <= 8 ? 2 : bn <= 8 ? 3 : bs <= 16 ? 4 : bn <= 16 ? 5
-                : bs <= 32 ? 6 : bn <= 32 ? 7 : bs <= 64 ? 8 : bn <= 64 ? 9 : 10;
-    cls[m++].key = ((uint64_t)i & 0x0FFFFFFFFFFFFFFFull) | ((uint64_t)g << 60);
-  }
+  for (size_t i = 0; i < n; i++)
+    if (grp[i] != 0xff) cls[m++].key = ((uint64_t)i & 0x0FFFFFFFFFFFFFFFull) | ((uint64_t)grp[i] << 60);
+  free(grp);
   if (m == 0) { free(cls); free(canon); free(ncanon); memset(out_affine, 0, 64); return 0; }
   /* Phase 2: sort by group, boundaries (msm.rs:287-301) */
-  qsort(cls, m, sizeof(cls_t), cls_cmp);
+  double T1 = now_s();
   size_t bnd[12];
-  {
-    size_t pos = 0;
-    for (int g = 0; g < 11; g++) {
-      bnd[g] = pos;
-      while (pos < m && (uint8_t)(cls[pos].key >> 60) <= g) pos++;
-    }
-    bnd[11] = m;
+  { /* 11 groups: a counting sort does what par_sort_unstable_by_key + partition_point do */
+    size_t cnt[12];
+    memset(cnt, 0, sizeof(cnt));
+    for (size_t k = 0; k < m; k++) cnt[(cls[k].key >> 60) + 1]++;
+    for (int g = 0; g < 11; g++) cnt[g + 1] += cnt[g];
+    memcpy(bnd, cnt, sizeof(bnd));
+    cls_t* sorted = (cls_t*)malloc(sizeof(cls_t) * m);
+    for (size_t k = 0; k < m; k++) sorted[cnt[cls[k].key >> 60]++] = cls[k];
+    free(cls);
+    cls = sorted;
   }
+  double T2 = now_s();
   /* Phase 3 (msm.rs:343-416) */
   aff* gb = (aff*)malloc(sizeof(aff) * m);
   uint64_t* gs = (uint64_t*)malloc(sizeof(uint64_t) * m);
@@ -728,11 +852,10 @@ EXPORT int orc_msm(int curve, const void* scalars_v, const void* bases_v, size_t
   if (bnd[10] < bnd[11]) { /* large group -> msm_best (msm.rs:399-411) */
     size_t lo = bnd[10], hi = bnd[11];
     uint64_t* lc = (uint64_t*)malloc((hi - lo) * 32);
-    for (size_t k = lo; k < hi; k++) {
-      size_t idx = (size_t)(cls[k].key & 0x0FFFFFFFFFFFFFFFull);
-      gb[k - lo] = bases[idx];
-      memcpy(&lc[4 * (k - lo)], &canon[4 * idx], 32);
-    }
+    gather_ctx gc = {cls + lo, bases, canon, gb, lc};
+    par_chunks(hi - lo, nthreads, gather_chunk, &gc); /* msm.rs:403-410 unzip, in parallel */
+    double T3 = now_s();
+    if (getenv("ORC_DEBUG")) fprintf(stderr, "classify %.3f sort %.3f gather %.3f\n", T1 - T0, T2 - T1, T3 - T2);
     msm_best_canon(&cv, lc, gb, hi - lo, nthreads, &part);
     xyzz_add(F, &total, &part);
     free(lc);
