@@ -248,6 +248,18 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_run(args.log2n, steps=2, warmup=1, sc_np=sc_np)
 
+    # ---------------- secondary metric of BASELINE.json: prove_step (kernel-sequence replay) -----
+    prove_step = None
+    if world == 1 and not args.no_prove_step:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import prove_step_replay as psr
+        ck.release()
+        del d_sc
+        torch.cuda.empty_cache()
+        prove_step = psr.gpu_replay(steps=5, warmup=2)
+        if not args.no_cpu_baseline:
+            prove_step["cpu_baseline"] = psr.cpu_replay(steps=1)
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -265,6 +277,7 @@ def run_b200(args):
         "gpu_launches": int(launches.value),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "prove_step_replay": prove_step,
     }
     print(json.dumps(out))
     if world > 1:
@@ -334,6 +347,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prove-step", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

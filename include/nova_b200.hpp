@@ -1,0 +1,196 @@
+// nova_b200.hpp -- C++ host-side mirror of the reference's provider surface for the hot path,
+// layered on the C ABI (include/nova_b200.h).  The reference is Rust; no Rust toolchain exists in
+// this image, so this header is the compiled-language host layer: same names, argument meaning
+// and error behaviour as the traits it stands under, so that the Rust shim of INTEGRATION.md is a
+// transliteration of it.
+//
+//   nova::b200::DlogGroup<Curve>::vartime_multiscalar_mul / batch_...   provider/traits.rs:77-117
+//   nova::b200::CommitmentEngine<Curve>::commit / batch_commit          pedersen.rs:263-270,
+//                                                                       hyperkzg.rs:584-612
+//   nova::b200::R1CSShape::multiply_vec / multiply_vec_pair / cross_term r1cs/mod.rs:407-471,578-664
+//   nova::b200::fold_witness, bind_poly_var_top                         r1cs/mod.rs:1044-1107,
+//                                                                       polys/multilinear.rs:65-84
+//   nova::b200::sumcheck_eval                                           spartan/sumcheck.rs (round sums)
+//
+// Conventions: `Scalar` / `Affine` / `Point` are the FFI layouts (32 / 64 / 96 bytes).  Infallible
+// trait functions (MSM, commit) throw std::logic_error on length mismatch (the reference
+// `assert!`s, msm.rs:226) and std::runtime_error("GpuError: ...") on device failure
+// (NovaError::GpuError, errors.rs:84-86).  All calls are thread-safe (rayon workers call commits
+// concurrently in the reference: r1cs/mod.rs:509-512).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "nova_b200.h"
+
+namespace nova {
+namespace b200 {
+
+struct Scalar { std::array<uint64_t, 4> limbs; };           // Montgomery, R = 2^256
+struct Affine { Scalar x, y; };                             // identity: all zero
+struct Point { Scalar x, y, z; bool is_identity() const {   // Jacobian; identity: z = 0
+  return (z.limbs[0] | z.limbs[1] | z.limbs[2] | z.limbs[3]) == 0; } };
+static_assert(sizeof(Scalar) == 32 && sizeof(Affine) == 64 && sizeof(Point) == 96, "FFI layout");
+
+struct BN254 { static constexpr int curve = B200_CURVE_BN254_G1, scalar_field = B200_FIELD_BN254_FR; };
+struct Grumpkin { static constexpr int curve = B200_CURVE_GRUMPKIN, scalar_field = B200_FIELD_BN254_FQ; };
+struct Pallas { static constexpr int curve = B200_CURVE_PALLAS, scalar_field = B200_FIELD_PALLAS_FQ; };
+struct Vesta { static constexpr int curve = B200_CURVE_VESTA, scalar_field = B200_FIELD_PALLAS_FP; };
+
+inline void check(int rc, const char* what) {
+  if (rc == B200_OK) return;
+  std::string msg = std::string(what) + ": " + b200_last_error();
+  if (rc == B200_E_ARG || rc == B200_E_RANGE) throw std::logic_error(msg);
+  throw std::runtime_error("GpuError: " + msg);
+}
+
+// CommitmentKey{ck, h} resident on the device (pedersen.rs:32-38, hyperkzg.rs:76-84)
+template <class C>
+class CommitmentKey {
+ public:
+  CommitmentKey(const std::vector<Affine>& ck, const Affine* h = nullptr, int window_bits = 0) : n_(ck.size()) {
+    check(b200_ck_register(C::curve, ck.data(), ck.size(), h, window_bits, &handle_), "b200_ck_register");
+  }
+  CommitmentKey(const CommitmentKey&) = delete;
+  CommitmentKey& operator=(const CommitmentKey&) = delete;
+  ~CommitmentKey() { if (handle_) b200_ck_release(handle_); }
+  size_t len() const { return n_; }
+  uint64_t handle() const { return handle_; }
+ private:
+  uint64_t handle_ = 0;
+  size_t n_;
+};
+
+template <class C>
+struct DlogGroup {
+  // msm(scalars, &ck[..scalars.len()])  (provider/traits.rs:79, msm.rs:225)
+  static Point vartime_multiscalar_mul(const std::vector<Scalar>& scalars, const CommitmentKey<C>& ck) {
+    if (scalars.size() > ck.len()) throw std::logic_error("scalars and bases length mismatch");
+    Point out{};
+    check(b200_msm(ck.handle(), 0, scalars.data(), scalars.size(), &out), "b200_msm");
+    return out;
+  }
+  // one-shot bases (pedersen.rs:418-420)
+  static Point vartime_multiscalar_mul(const std::vector<Scalar>& scalars, const std::vector<Affine>& bases) {
+    if (scalars.size() != bases.size()) throw std::logic_error("scalars and bases length mismatch");
+    Point out{};
+    check(b200_msm_adhoc(C::curve, bases.data(), scalars.data(), scalars.size(), &out), "b200_msm_adhoc");
+    return out;
+  }
+  // traits.rs:82-90
+  static std::vector<Point> batch_vartime_multiscalar_mul(const std::vector<std::vector<Scalar>>& scalars,
+                                                          const CommitmentKey<C>& ck) {
+    std::vector<const void*> ptrs(scalars.size());
+    std::vector<size_t> lens(scalars.size());
+    for (size_t j = 0; j < scalars.size(); j++) { ptrs[j] = scalars[j].data(); lens[j] = scalars[j].size(); }
+    std::vector<Point> out(scalars.size());
+    check(b200_msm_batch(ck.handle(), ptrs.data(), lens.data(), scalars.size(), out.data()), "b200_msm_batch");
+    return out;
+  }
+  template <class T>  // msm_small (msm.rs:469-503)
+  static Point vartime_multiscalar_mul_small(const std::vector<T>& scalars, const CommitmentKey<C>& ck,
+                                             int max_num_bits = 0) {
+    static_assert(sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8, "integer scalars");
+    if (scalars.size() > ck.len()) throw std::logic_error("scalars and bases length mismatch");
+    Point out{};
+    check(b200_msm_small(ck.handle(), 0, scalars.data(), (int)sizeof(T), scalars.size(), max_num_bits, &out),
+          "b200_msm_small");
+    return out;
+  }
+  static Point batch_add(const CommitmentKey<C>& ck, const std::vector<uint64_t>& one_indices) {  // msm.rs:689
+    Point out{};
+    check(b200_msm_indices(ck.handle(), one_indices.data(), one_indices.size(), &out), "b200_msm_indices");
+    return out;
+  }
+};
+
+template <class C>
+struct CommitmentEngine {
+  // commit(ck, v, r) = MSM(v, ck[..len]) + h*r   (pedersen.rs:263-270)
+  static Point commit(const CommitmentKey<C>& ck, const std::vector<Scalar>& v, const Scalar* r = nullptr) {
+    if (ck.len() < v.size()) throw std::logic_error("commitment key too short");  // pedersen.rs:264
+    Point out{};
+    check(b200_commit(ck.handle(), v.data(), v.size(), r, &out), "b200_commit");
+    return out;
+  }
+  static std::vector<Point> batch_commit(const CommitmentKey<C>& ck, const std::vector<std::vector<Scalar>>& vs) {
+    return DlogGroup<C>::batch_vartime_multiscalar_mul(vs, ck);
+  }
+};
+
+// CSR matrix + R1CS shape (r1cs/sparse.rs:235-247, r1cs/mod.rs:407-471)
+class SparseMatrix {
+ public:
+  SparseMatrix(int field, const std::vector<Scalar>& data, const std::vector<uint64_t>& indices,
+               const std::vector<uint64_t>& indptr, size_t cols)
+      : rows_(indptr.size() - 1), cols_(cols) {
+    check(b200_spmv_register(field, data.data(), indices.data(), indptr.data(), rows_, cols, &handle_),
+          "b200_spmv_register");
+  }
+  SparseMatrix(const SparseMatrix&) = delete;
+  ~SparseMatrix() { if (handle_) b200_spmv_release(handle_); }
+  uint64_t handle() const { return handle_; }
+  size_t rows() const { return rows_; }
+  size_t cols() const { return cols_; }
+ private:
+  uint64_t handle_ = 0;
+  size_t rows_, cols_;
+};
+
+struct R1CSShape {
+  const SparseMatrix &A, &B, &C;
+  int field;
+  // (Az, Bz, Cz); throws std::invalid_argument("InvalidWitnessLength") like r1cs/mod.rs:411-413
+  std::array<std::vector<Scalar>, 3> multiply_vec(const std::vector<Scalar>& z) const {
+    if (z.size() != A.cols()) throw std::invalid_argument("InvalidWitnessLength");
+    std::array<std::vector<Scalar>, 3> out{std::vector<Scalar>(A.rows()), std::vector<Scalar>(B.rows()),
+                                           std::vector<Scalar>(C.rows())};
+    uint64_t hs[3] = {A.handle(), B.handle(), C.handle()};
+    void* o[3] = {out[0].data(), out[1].data(), out[2].data()};
+    check(b200_spmv_multi(hs, 3, z.data(), nullptr, z.size(), o, nullptr), "b200_spmv_multi");
+    return out;
+  }
+  // T = AZ o BZ - u*CZ - E1 (- E2)   (commit_T / commit_T_relaxed, r1cs/mod.rs:614-620, 650-657)
+  std::vector<Scalar> cross_term(const std::vector<Scalar>& az, const std::vector<Scalar>& bz,
+                                 const std::vector<Scalar>& cz, const std::vector<Scalar>& e1, const Scalar& u,
+                                 const std::vector<Scalar>* e2 = nullptr) const {
+    std::vector<Scalar> t(az.size());
+    check(b200_cross_term(field, az.data(), bz.data(), cz.data(), e1.data(), e2 ? e2->data() : nullptr, &u,
+                          az.size(), t.data()), "b200_cross_term");
+    return t;
+  }
+};
+
+// W1 + r*W2 (RelaxedR1CSWitness::fold, r1cs/mod.rs:1058-1069)
+inline std::vector<Scalar> fold_witness(int field, const std::vector<Scalar>& a, const std::vector<Scalar>& b,
+                                        const Scalar& r) {
+  if (a.size() != b.size()) throw std::invalid_argument("InvalidWitnessLength");  // r1cs/mod.rs:1054
+  std::vector<Scalar> out(a.size());
+  check(b200_axpy(field, a.data(), b.data(), &r, a.size(), out.data()), "b200_axpy");
+  return out;
+}
+// MultilinearPolynomial::bind_poly_var_top (polys/multilinear.rs:65-84): in place, truncates
+inline void bind_poly_var_top(int field, std::vector<Scalar>& Z, const Scalar& r) {
+  check(b200_bind_top(field, Z.data(), Z.size(), &r), "b200_bind_top");
+  Z.resize(Z.size() / 2);
+}
+// one round's O(N) sums (see include/nova_b200.h for the form table); returns 1-3 field elements
+inline std::vector<Scalar> sumcheck_eval(int field, int form, const std::vector<Scalar>& A,
+                                         const std::vector<Scalar>* B, const std::vector<Scalar>* C,
+                                         const std::vector<Scalar>* eq_left, const std::vector<Scalar>* eq_right,
+                                         int shift) {
+  Scalar out[3];
+  check(b200_sc_eval(field, form, A.data(), B ? B->data() : nullptr, C ? C->data() : nullptr, A.size(),
+                     eq_left ? eq_left->data() : nullptr, eq_left ? eq_left->size() : 0,
+                     eq_right ? eq_right->data() : nullptr, eq_right ? eq_right->size() : 0, shift, out),
+        "b200_sc_eval");
+  int n = form == 3 ? 3 : (form == 6 || form >= 7) ? 1 : 2;
+  return std::vector<Scalar>(out, out + n);
+}
+
+}  // namespace b200
+}  // namespace nova

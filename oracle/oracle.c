@@ -1277,3 +1277,36 @@ EXPORT int orc_spmv(int fid, const void* data, const uint64_t* indices, const ui
   }
   return 0;
 }
+
+/* ---- threaded forms of the R1CS field kernels for the CPU baseline: the reference runs these
+ * under rayon (sparse.rs:203-212 into_par_iter over rows; r1cs/mod.rs:614-620 par_iter) ---------- */
+typedef struct { int fid; const void* data; const uint64_t* indices; const uint64_t* indptr; const void* z; void* out; } spmv_par_ctx;
+static void spmv_par_chunk(void* v, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  spmv_par_ctx* c = (spmv_par_ctx*)v;
+  /* rows [lo,hi): reuse the serial row loop on a shifted view */
+  orc_spmv(c->fid, c->data, c->indices, c->indptr + lo, hi - lo, c->z, (fe*)c->out + lo);
+}
+EXPORT int orc_spmv_par(int fid, const void* data, const uint64_t* indices, const uint64_t* indptr,
+                        size_t rows, const void* z, void* out, int nthreads) {
+  spmv_par_ctx c = {fid, data, indices, indptr, z, out};
+  par_chunks(rows, nthreads, spmv_par_chunk, &c);
+  return 0;
+}
+typedef struct { int fid, op; const void *a, *b, *c, *e1, *e2, *u; void* out; } vec_par_ctx;
+static void vec_par_chunk(void* v, size_t lo, size_t hi, int tid) {
+  (void)tid;
+  vec_par_ctx* c = (vec_par_ctx*)v;
+  size_t n = hi - lo;
+#define OFF(p) ((p) ? (const void*)((const fe*)(p) + lo) : NULL)
+  if (c->op == 0) orc_cross_term(c->fid, OFF(c->a), OFF(c->b), OFF(c->c), OFF(c->e1), OFF(c->e2), c->u, n, (fe*)c->out + lo);
+  else if (c->op == 1) orc_axpy(c->fid, OFF(c->a), OFF(c->b), c->u, n, (fe*)c->out + lo);
+  else orc_vec_add(c->fid, OFF(c->a), OFF(c->b), n, (fe*)c->out + lo);
+#undef OFF
+}
+EXPORT int orc_vec_par(int fid, int op, const void* a, const void* b, const void* c, const void* e1,
+                       const void* e2, const void* u, size_t n, void* out, int nthreads) {
+  vec_par_ctx x = {fid, op, a, b, c, e1, e2, u, out};
+  par_chunks(n, nthreads, vec_par_chunk, &x);
+  return 0;
+}
