@@ -196,6 +196,13 @@ int b200_spmv_register(int field_id, const void* data_mont, const uint64_t* indi
 int b200_spmv_release(uint64_t m_handle);
 int b200_spmv_dev(uint64_t m_handle, const void* d_z1, const void* d_z2_or_null, void* d_out1,
                   void* d_out2_or_null, void* stream);
+/* out[col] = sum over entries (row, col, val) of rx[row]*val, for col < out_len (zero beyond the
+ * matrix' columns): compute_eval_table_sparse (spartan/mod.rs:497-534), one matrix per call */
+int b200_spmv_t(uint64_t m_handle, const void* rx, size_t out_len, void* out);
+int b200_spmv_t_dev(uint64_t m_handle, const void* d_rx, size_t out_len, void* d_out, void* stream);
+/* out[i] = table[idx[i]]: the L_row / L_col oracles of ppsnark (spartan/ppsnark.rs:236-250) */
+int b200_gather(const void* table, size_t table_len, const uint64_t* idx, size_t n, void* out);
+int b200_gather_dev(const void* d_table, const uint32_t* d_idx, size_t n, void* d_out, void* stream);
 /* R1CSShape::multiply_vec / multiply_vec_pair (r1cs/mod.rs:407-471): k matrices, one or two z */
 int b200_spmv_multi(const uint64_t* m_handles, size_t k, const void* z1, const void* z2_or_null,
                     size_t z_len, void* const* out1, void* const* out2_or_null);

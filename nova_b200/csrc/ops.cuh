@@ -54,6 +54,9 @@ struct field_ops {
   void (*spmv)(cudaStream_t, const uint32_t* indptr, const uint32_t* cols, const int8_t* codes,
                const void* vals, size_t rows, const void* z1, const void* z2_or_null, void* o1,
                void* o2_or_null);
+  void (*spmv_t)(cudaStream_t, const uint32_t* tptr, const uint32_t* trow, const uint32_t* tperm,
+                 const int8_t* codes, const void* vals, size_t cols, size_t out_len, const void* rx,
+                 void* out);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
 constexpr int POLY_CHUNK_HOST = 64;  // must equal POLY_CHUNK in poly_kernels.cuh

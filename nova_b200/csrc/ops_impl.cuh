@@ -220,10 +220,15 @@ struct ops_impl {
     else
       k_spmv<F, 1><<<stream_grid(rows, 256), 256, 0, s>>>(indptr, cols, codes, vals, rows, z1, z1, o1, o1);
   }
+  static void spmv_t(cudaStream_t s, const uint32_t* tptr, const uint32_t* trow, const uint32_t* tperm,
+                     const int8_t* codes, const void* vals, size_t cols, size_t out_len, const void* rx,
+                     void* out) {
+    k_spmv_t<F><<<stream_grid(out_len, 256), 256, 0, s>>>(tptr, trow, tperm, codes, vals, cols, out_len, rx, out);
+  }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top,
-                     sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv};
+                     sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t};
   }
 };
 

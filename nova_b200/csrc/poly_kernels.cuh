@@ -497,4 +497,38 @@ __global__ void __launch_bounds__(256) k_spmv(const uint32_t* __restrict__ indpt
   }
 }
 
+// transposed product  out[col] = sum_{(row,col,val) in M} rx[row] * val   (compute_eval_table_sparse,
+// spartan/mod.rs:497-534: serial scatter in the reference; here one thread per COLUMN over the CSC
+// view built at registration, so no atomics on 256-bit values are needed)
+template <class F>
+__global__ void __launch_bounds__(256) k_spmv_t(const uint32_t* __restrict__ tptr,
+                                                const uint32_t* __restrict__ trow,
+                                                const uint32_t* __restrict__ tperm,
+                                                const int8_t* __restrict__ codes,
+                                                const void* __restrict__ vals, size_t cols, size_t out_len,
+                                                const void* __restrict__ rx, void* __restrict__ out) {
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < out_len;
+       c += (size_t)gridDim.x * blockDim.x) {
+    fe_t s = fe_zero<F>();
+    if (c < cols) {
+      for (uint32_t e = tptr[c]; e < tptr[c + 1]; e++) {
+        uint32_t src = tperm[e];
+        fe_t x = fe_load(rx, trow[e]);
+        int code = codes[src];
+        s = fe_add<F>(s, code == 0 ? fe_mul<F>(fe_load(vals, src), x) : small_mul<F>(code, x));
+      }
+    }
+    fe_store(out, c, s);
+  }
+}
+
+// out[i] = table[idx[i]]  (L_row / L_col of ppsnark.rs:236-250)
+static __global__ void __launch_bounds__(256) k_gather32(const void* __restrict__ table,
+                                                  const uint32_t* __restrict__ idx, size_t n,
+                                                  void* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    fe_store(out, i, fe_load(table, idx[i]));
+}
+
 }  // namespace nova

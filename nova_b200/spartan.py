@@ -81,6 +81,13 @@ class SparseMatrix:
     def multiply_vec(self, z: bytes) -> bytes:
         return R1CSShape._multi([self], z, None)[0][0]
 
+    def multiply_transpose(self, rx: bytes, out_len: int) -> bytes:
+        """M^T rx padded to out_len: one matrix of compute_eval_table_sparse (spartan/mod.rs:497-534)."""
+        assert len(rx) == 32 * self.rows  # spartan/mod.rs:501
+        out = ctypes.create_string_buffer(max(32 * out_len, 1))
+        check(lib().b200_spmv_t(self.handle, _cbuf(rx), out_len, out))
+        return out.raw[:32 * out_len]
+
     def release(self):
         if self.handle:
             lib().b200_spmv_release(self.handle)
@@ -141,6 +148,15 @@ def evaluate_with(fid: int, Z: bytes, r: bytes) -> bytes:
     out = ctypes.create_string_buffer(32)
     check(lib().b200_mle_eval(fid, _cbuf(Z), ell, _cbuf(r), out))
     return out.raw
+
+
+def gather(table: bytes, indices) -> bytes:
+    """out[i] = table[indices[i]] (L_row / L_col, spartan/ppsnark.rs:236-250)."""
+    n = len(indices)
+    idx = (c_u64 * max(n, 1))(*indices)
+    out = ctypes.create_string_buffer(max(32 * n, 1))
+    check(lib().b200_gather(_cbuf(table), len(table) // 32, idx, n, out))
+    return out.raw[:32 * n]
 
 
 def batch_invert(fid: int, v: bytes) -> bytes:

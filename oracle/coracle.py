@@ -235,3 +235,12 @@ def spmv(fid, data: bytes, indices, indptr, z: bytes) -> bytes:
     out = ctypes.create_string_buffer(max(32 * rows, 1))
     assert lib().orc_spmv(fid, _buf(data), ia, ip, ctypes.c_size_t(rows), _buf(z), out) == 0
     return out.raw[: 32 * rows]
+
+
+def spmv_t(fid, data: bytes, indices, indptr, rx: bytes, out_len: int) -> bytes:
+    rows = len(indptr) - 1
+    ia = (ctypes.c_uint64 * max(len(indices), 1))(*indices)
+    ip = (ctypes.c_uint64 * len(indptr))(*indptr)
+    out = ctypes.create_string_buffer(max(32 * out_len, 1))
+    assert lib().orc_spmv_t(fid, _buf(data), ia, ip, ctypes.c_size_t(rows), _buf(rx), ctypes.c_size_t(out_len), out) == 0
+    return out.raw[: 32 * out_len]

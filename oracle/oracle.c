@@ -504,13 +504,13 @@ typedef struct {
   size_t n;
   int c, nwin, nslices;
   xyzz* job_out; /* [nwin][nslices] */
+  xyzz* scratch; /* [nthreads][2^(c-1)] per-thread bucket arrays (allocated once) */
 } best2_ctx;
 static void best2_job(void* vctx, size_t lo, size_t hi, int tid) {
-  (void)tid;
   best2_ctx* cx = (best2_ctx*)vctx;
   const orc_field_t* F = cx->F;
   size_t nb = (size_t)1 << (cx->c - 1);
-  xyzz* buckets = (xyzz*)malloc(sizeof(xyzz) * nb);
+  xyzz* buckets = cx->scratch + (size_t)tid * nb;
   for (size_t job = lo; job < hi; job++) {
     int w = (int)(job / cx->nslices), sl = (int)(job % cx->nslices);
     size_t per = (cx->n + cx->nslices - 1) / cx->nslices;
@@ -534,7 +534,6 @@ static void best2_job(void* vctx, size_t lo, size_t hi, int tid) {
     }
     cx->job_out[job] = res;
   }
-  free(buckets);
 }
 typedef struct { const uint64_t* canon; int32_t* digits; int c, nwin; } dig_ctx;
 static void digits_chunk(void* vctx, size_t lo, size_t hi, int tid) {
@@ -562,17 +561,26 @@ static void msm_best_canon(const curve_t* cv, const uint64_t* canon, const aff* 
   int nslices = (2 * nthreads + nwin - 1) / nwin; /* ~2 jobs per thread, pulled dynamically */
   if ((size_t)nslices > n) nslices = (int)n;
   if (nslices < 1) nslices = 1;
+  double td = now_s();
   int32_t* digits = (int32_t*)malloc(sizeof(int32_t) * n * nwin);
   dig_ctx dc = {canon, digits, c, nwin};
   par_chunks(n, nthreads, digits_chunk, &dc);
-  best2_ctx cx = {F, bases, digits, n, c, nwin, nslices, NULL};
+  if (getenv("ORC_DEBUG")) fprintf(stderr, "msm_best: digits %.3f s\n", now_s() - td);
+  double t0 = now_s();
+  best2_ctx cx = {F, bases, digits, n, c, nwin, nslices, NULL, NULL};
   size_t njobs = (size_t)nwin * nslices;
   cx.job_out = (xyzz*)malloc(sizeof(xyzz) * njobs);
+  cx.scratch = (xyzz*)malloc(sizeof(xyzz) * ((size_t)1 << (c - 1)) * nthreads);
   par_jobs(njobs, nthreads, best2_job, &cx);
+  double t1 = now_s();
   for (int w = nwin - 1; w >= 0; w--) {
     for (int d = 0; d < c; d++) xyzz_double(F, out);
     for (int sl = 0; sl < nslices; sl++) xyzz_add(F, out, &cx.job_out[(size_t)w * nslices + sl]);
   }
+  if (getenv("ORC_DEBUG"))
+    fprintf(stderr, "msm_best: c=%d nwin=%d nslices=%d threads=%d  jobs %.3f s  combine %.3f s\n", c, nwin,
+            nslices, nthreads, t1 - t0, now_s() - t1);
+  free(cx.scratch);
   free(cx.job_out);
   free(digits);
 }
@@ -1308,5 +1316,21 @@ EXPORT int orc_vec_par(int fid, int op, const void* a, const void* b, const void
                        const void* e2, const void* u, size_t n, void* out, int nthreads) {
   vec_par_ctx x = {fid, op, a, b, c, e1, e2, u, out};
   par_chunks(n, nthreads, vec_par_chunk, &x);
+  return 0;
+}
+
+/* spartan/mod.rs:497-534 compute_eval_table_sparse, one matrix: M_evals[col] += rx[row] * val */
+EXPORT int orc_spmv_t(int fid, const void* data, const uint64_t* indices, const uint64_t* indptr,
+                      size_t rows, const void* rx, size_t out_len, void* out) {
+  if (fid < 0 || fid > 3) return 1;
+  const orc_field_t* F = &ORC_FIELDS[fid];
+  fe* O = (fe*)out;
+  memset(O, 0, out_len * 32);
+  for (size_t r = 0; r < rows; r++)
+    for (uint64_t e = indptr[r]; e < indptr[r + 1]; e++) {
+      fe t;
+      fe_mul(F, &t, &((const fe*)rx)[r], &((const fe*)data)[e]);
+      fe_add(F, &O[indices[e]], &O[indices[e]], &t);
+    }
   return 0;
 }

@@ -184,3 +184,20 @@ def test_errors(b200, oracle):
     ck.release()
     with pytest.raises(nova_b200.B200Error):
         b200.DlogGroup(0).vartime_multiscalar_mul(bytes(32), ck)
+
+
+def test_config1_pedersen_commit_pallas_2p16(b200, oracle):
+    """BASELINE.json configs[0]: Pedersen commit of 2^16 random Pallas scalars, bit-exact against the
+    CPU restatement (commit = MSM(v, ck) + r*h, pedersen.rs:263-270; bench shape benches/commit.rs)."""
+    cid, c = 2, CURVES[2]
+    n = 1 << 16
+    ck, bases = make_key(b200, oracle, cid, n, h=True)
+    v = oracle.gen_scalars(c.scalar_field, 1, n)
+    r = oracle.gen_scalars(c.scalar_field, 7, 1)
+    ce = b200.CommitmentEngine(cid)
+    assert ce.commit(ck, v, r) == aff(c, oracle.msm(cid, v + r, bases))
+    assert ce.commit(ck, v, None) == aff(c, oracle.msm(cid, v, bases[:64 * n]))
+    # commit is additively homomorphic: commit(v1) + commit(v2) == commit(v1 + v2)
+    v2 = oracle.gen_scalars(c.scalar_field, 2, n)
+    s = oracle.vec_add(c.scalar_field, v, v2)
+    assert c.add(ce.commit(ck, v, None), ce.commit(ck, v2, None)) == ce.commit(ck, s, None)

@@ -58,6 +58,25 @@ def test_spmv_random(sp, oracle, fid, rows, cols):
     assert m.multiply_vec(z) == oracle.spmv(fid, d, indices, indptr, z)
 
 
+def test_eval_table_sparse_and_gather(sp, oracle):
+    """compute_eval_table_sparse (spartan/mod.rs:497-534) as a transposed product, and the
+    L_row / L_col gathers of ppsnark.rs:236-250."""
+    fid = 0
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(77)
+    rows, cols = 4000, 3000
+    data, idx, ptr = _random_csr(rng, p, rows, cols, 5)
+    d = pack(p, data)
+    m = sp.SparseMatrix(fid, d, idx, ptr, cols)
+    rx = oracle.gen_scalars(fid, 3, rows)
+    for out_len in (cols, 2 * cols, 4096):
+        assert m.multiply_transpose(rx, out_len) == oracle.spmv_t(fid, d, idx, ptr, rx, out_len)
+    table = oracle.gen_scalars(fid, 4, 1 << 12)
+    ix = [rng.next() % (1 << 12) for _ in range(5000)]
+    got = sp.gather(table, ix)
+    assert got == b"".join(table[32 * i:32 * i + 32] for i in ix)
+
+
 def test_r1cs_multiply_vec_and_pair(sp, oracle):
     """multiply_vec_pair == 2 x multiply_vec (r1cs/mod.rs:1500-1526) and the tiny cubic R1CS
     x^3 + x + 5 = y (r1cs/mod.rs:1349-1413): rows satisfied <=> Az o Bz == Cz."""
