@@ -284,11 +284,23 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def effective_cores():
+    """Host threads actually available: min(visible CPUs, cgroup v2 CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_run(log2n, steps, warmup, sc_np=None):
     """Time the CPU restatement of the reference's msm() (oracle/oracle.c, msm.rs:225-419 with the
     msm_best stand-in) with all host cores on the bench workload (or a bounded sample of it)."""
     from oracle import coracle as co
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     n_full = 1 << log2n
     if sc_np is None:
         sc_np = synth_scalars(n_full, seed=2)

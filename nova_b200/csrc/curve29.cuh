@@ -240,6 +240,17 @@ struct pa29 {
     }
     return p;
   }
+  static NOVA_D pt shfl_down(const pt& p, int d, int width) {
+    pt r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      r.x.l[i] = __shfl_down_sync(0xffffffffu, p.x.l[i], d, width);
+      r.y.l[i] = __shfl_down_sync(0xffffffffu, p.y.l[i], d, width);
+      r.zz.l[i] = __shfl_down_sync(0xffffffffu, p.zz.l[i], d, width);
+      r.zzz.l[i] = __shfl_down_sync(0xffffffffu, p.zzz.l[i], d, width);
+    }
+    return r;
+  }
   static NOVA_D void store(void* base, size_t idx, const pt& p) {
     uint32_t w[36];
 #pragma unroll
@@ -306,6 +317,17 @@ struct pa32 {
   static NOVA_D void store_table_identity(void* tables, size_t idx) {
     fe_store(tables, 2 * idx, fe_zero<F>());
     fe_store(tables, 2 * idx + 1, fe_zero<F>());
+  }
+  static NOVA_D pt shfl_down(const pt& p, int d, int width) {
+    pt r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      r.x.l[i] = __shfl_down_sync(0xffffffffu, p.x.l[i], d, width);
+      r.y.l[i] = __shfl_down_sync(0xffffffffu, p.y.l[i], d, width);
+      r.zz.l[i] = __shfl_down_sync(0xffffffffu, p.zz.l[i], d, width);
+      r.zzz.l[i] = __shfl_down_sync(0xffffffffu, p.zzz.l[i], d, width);
+    }
+    return r;
   }
   static NOVA_D pt load(const void* base, size_t idx) { return xyzz_load(base, idx); }
   static NOVA_D void store(void* base, size_t idx, const pt& p) { xyzz_store(base, idx, p); }

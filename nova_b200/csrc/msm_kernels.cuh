@@ -173,32 +173,50 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint64_t* __restrict__
   }
 }
 
-// One thread per bucket key: joins the boundary partials of that bucket.  The bucket's entries
-// span segments t0..t1, so its partials can only sit in slots 2*t0 .. 2*t1+1.  A bucket whose
-// entries are interior to one segment finds no matching slot (it was stored directly by
-// k_accumulate); buckets above heavy_min are left to k_fixup_heavy.
+// G threads per bucket key (G a power of two <= 32, chosen by the host from the expected number of
+// partials per bucket): join the boundary partials of that bucket.  The bucket's entries span
+// segments t0..t1, so its partials can only sit in slots 2*t0 .. 2*t1+1; the G lanes stride over
+// that range and combine with a shuffle tree.  A bucket whose entries are interior to one segment
+// finds no matching slot (it was stored directly by k_accumulate); buckets above heavy_min are
+// left to k_fixup_heavy.
 template <class F>
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ start, uint32_t K,
-                                               int L, uint32_t heavy_min,
+                                               int L, uint32_t heavy_min, int G,
                                                const void* __restrict__ parts,
                                                const uint32_t* __restrict__ pkeys,
                                                void* __restrict__ buckets) {
   using PA = msm_arith<F>;
-  uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
-  if (key >= K) return;
-  uint32_t s0 = start[key], s1 = start[key + 1];
-  if (s1 == s0 || s1 - s0 > heavy_min) return;
-  size_t j0 = 2 * ((size_t)s0 / L), j1 = 2 * (((size_t)s1 - 1) / L) + 1;
+  uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t key = gtid / G, sub = gtid % G;
+  bool live = key < K;
+  uint32_t s0 = 0, s1 = 0;
+  if (live) {
+    s0 = start[key];
+    s1 = start[key + 1];
+    live = s1 != s0 && s1 - s0 <= heavy_min;
+  }
   typename PA::pt acc = PA::identity();
   bool found = false;
-  for (size_t j = j0; j <= j1; j++) {
-    if (pkeys[j] == key) {
-      typename PA::pt o = PA::load(parts, j);
+  if (live) {
+    size_t j0 = 2 * ((size_t)s0 / L), j1 = 2 * (((size_t)s1 - 1) / L) + 1;
+    for (size_t j = j0 + sub; j <= j1; j += G) {
+      if (pkeys[j] == key) {
+        typename PA::pt o = PA::load(parts, j);
+        PA::add(acc, o);
+        found = true;
+      }
+    }
+  }
+  // all 32 lanes take part in the shuffles (groups are aligned sub-warps)
+  for (int d = G / 2; d > 0; d >>= 1) {
+    typename PA::pt o = PA::shfl_down(acc, d, G);
+    bool of = __shfl_down_sync(0xffffffffu, (int)found, d, G) != 0;
+    if (sub + d < (uint32_t)G && of) {
       PA::add(acc, o);
       found = true;
     }
   }
-  if (found) PA::store(buckets, key, acc);
+  if (live && sub == 0 && found) PA::store(buckets, key, acc);
 }
 
 // Heavy buckets (skewed scalars: 0/1 witnesses, repeated values) would serialise the run-head

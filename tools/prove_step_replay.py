@@ -152,6 +152,12 @@ def gpu_replay(steps=5, warmup=2):
 def cpu_replay(steps=1):
     from oracle import coracle as co
     cores = os.cpu_count() or 1
+    try:  # honour a cgroup CPU quota (the GPU boxes expose 128 CPUs with a 16-CPU quota)
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            cores = max(1, min(cores, int(int(quota) / int(period))))
+    except Exception:
+        pass
     L = co.lib()
     sides = make_sides()
     prep = []
