@@ -56,11 +56,13 @@ struct ops_impl {
   }
   static void fixup(cudaStream_t s, const msm_plan& p) {
     uint32_t K = (uint32_t)p.G * p.B;
-    // expected partials per bucket = (entries / K) / L + 1; about 4 per lane, at most a warp per key
+    // expected partials per bucket = (entries / K) / L + 1; about 8 per lane (a lone thread up to 16),
+    // at most a warp per key
     size_t entries = p.n * (size_t)p.W;
     size_t ppk = entries / ((size_t)K * p.L) + 1;
     int G = 1;
-    while (G < 32 && (size_t)G * 4 < ppk) G <<= 1;
+    while (G < 32 && (size_t)G * 8 < ppk) G <<= 1;
+    if (ppk <= 16) G = 1;
     size_t threads = (size_t)K * G;
     k_fixup<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(p.start, K, p.L, p.heavy_min, G, p.parts,
                                                                  p.pkeys, p.buckets);
