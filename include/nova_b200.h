@@ -159,6 +159,14 @@ int b200_sc_eval(int field_id, int form, const void* A, const void* B, const voi
                  int shift, void* out);
 int b200_sc_eval_dev(int field_id, int form, const void* A, const void* B, const void* C, size_t len,
                      const void* eq_left, const void* eq_right, int shift, void* out, void* stream);
+/* Multi-GPU form: the polynomials are sharded CYCLICALLY over id_mul ranks (rank
+ * id_add holds global entries id_add, id_add + id_mul, ...).  (i, i + len/2) pairs stay
+ * co-resident, so bind_top needs no exchange; the local index j weighs with the eq factor of the
+ * global index j*id_mul + id_add.  Each rank gets partial sums; the host all-gathers 2-3 field
+ * elements per round and adds them. */
+int b200_sc_eval_sharded_dev(int field_id, int form, const void* A, const void* B, const void* C,
+                             size_t local_len, const void* eq_left, const void* eq_right, int shift,
+                             size_t id_mul, size_t id_add, void* out, void* stream);
 /* EqPolynomial::evals_from_points (spartan/polys/eq.rs:54-73): out has 2^ell entries */
 int b200_eq_table(int field_id, const void* r, int ell, void* out);
 int b200_eq_table_dev(int field_id, const void* r, int ell, void* out, void* stream);

@@ -36,8 +36,8 @@ struct field_ops {
   // --- sum-check / MLE / HyperKZG / SpMV (poly_kernels.cuh) ----------------------------------
   // form: sc_form_id; writes sc_form_nout(form) elements to out; scratch >= SC_MAX_BLOCKS*3*32 B
   void (*sc_reduce)(cudaStream_t, int form, const void* A, const void* B, const void* C, size_t count,
-                    size_t half, const void* eq_left, const void* eq_right, int shift, void* scratch,
-                    void* out);
+                    size_t half, const void* eq_left, const void* eq_right, int shift, size_t id_mul,
+                    size_t id_add, void* scratch, void* out);
   void (*eq_small)(cudaStream_t, const void* r, int ell, void* out);
   void (*eq_outer)(cudaStream_t, const void* left, const void* right, int right_bits, size_t n,
                    void* out);

@@ -117,7 +117,7 @@ struct ops_impl {
   template <int FORM>
   static void sc_launch(cudaStream_t s, const void* A, const void* B, const void* C, size_t count,
                         size_t half, const void* eq_left, const void* eq_right, int shift,
-                        void* scratch, void* out) {
+                        size_t id_mul, size_t id_add, void* scratch, void* out) {
     constexpr int NOUT = sc_form_nout(FORM);
     sc_form<F, FORM> f;
     f.A = A;
@@ -128,6 +128,8 @@ struct ops_impl {
     f.eq.right = eq_right;
     f.eq.shift = shift;
     f.eq.mask = ((size_t)1 << shift) - 1;
+    f.eq.id_mul = id_mul;
+    f.eq.id_add = id_add;
     size_t need = (count + 255) / 256;
     int grid = (int)(need < (size_t)SC_MAX_BLOCKS ? (need ? need : 1) : SC_MAX_BLOCKS);
     k_form_reduce<F, NOUT, sc_form<F, FORM>><<<grid, 256, 0, s>>>(f, count, scratch);
@@ -135,9 +137,9 @@ struct ops_impl {
   }
   static void sc_reduce(cudaStream_t s, int form, const void* A, const void* B, const void* C,
                         size_t count, size_t half, const void* eq_left, const void* eq_right,
-                        int shift, void* scratch, void* out) {
+                        int shift, size_t id_mul, size_t id_add, void* scratch, void* out) {
 #define SC_CASE(X) \
-  case X: sc_launch<X>(s, A, B, C, count, half, eq_left, eq_right, shift, scratch, out); break
+  case X: sc_launch<X>(s, A, B, C, count, half, eq_left, eq_right, shift, id_mul, id_add, scratch, out); break
     switch (form) {
       SC_CASE(SC_QUAD_PROD);
       SC_CASE(SC_LINEAR);

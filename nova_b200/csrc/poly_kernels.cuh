@@ -86,13 +86,19 @@ __global__ void __launch_bounds__(256) k_form_final(const void* partials, int nb
 // eq factor: f = eq_left[id >> shift] * eq_right[id & mask]  (first half of the rounds), or
 //            f = eq_right[id] when eq_left == nullptr          (sumcheck.rs:1233-1251)
 // ------------------------------------------------------------------------------------------
+// When a polynomial is sharded cyclically over `id_mul` ranks (rank r holds entries r, r+N, ...)
+// the local index j stands for the global index j*id_mul + id_add; binding the top variable then
+// needs no data movement (pairs (i, i+h) are co-resident) and only the eq weight must use the
+// global index.  Unsharded calls pass id_mul = 1, id_add = 0.
 struct eq_factor {
   const void* left;
   const void* right;
   int shift;
   size_t mask;
+  size_t id_mul, id_add;
   template <class F>
-  NOVA_D fe_t get(size_t id) const {
+  NOVA_D fe_t get(size_t local_id) const {
+    size_t id = local_id * id_mul + id_add;
     if (left == nullptr) return fe_load(right, id);
     return fe_mul<F>(fe_load(left, id >> shift), fe_load(right, id & mask));
   }

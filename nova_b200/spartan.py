@@ -383,3 +383,40 @@ def hyperkzg_prove_core(curve, ck: CommitmentKey, hat_P: bytes, x: list, r: int,
         h = poly_div(fid, Bpoly, fields.to_mont_bytes(fid, ut))
         w.append(group.vartime_multiscalar_mul(h, ck))
     return com, v, w
+
+
+class DeviceSumcheckEngine:
+    """Local engine of `sharding.sharded_prove_cubic_with_three_inputs` on one GPU: tables resident
+    in HBM, sums through b200_sc_eval_sharded_dev, binds through b200_bind_top_dev."""
+
+    def __init__(self, fid: int):
+        self.fid = fid
+        self.p = fields.MODULUS[fid]
+
+    def upload(self, b: bytes) -> DeviceVec:
+        return DeviceVec.from_bytes(b)
+
+    def download(self, h: DeviceVec, n_elems: int) -> bytes:
+        return h.to_bytes(32 * n_elems)
+
+    def download_canonical(self, h: DeviceVec) -> bytes:
+        return fields.from_mont_bytes(self.fid, h.to_bytes(32)).to_bytes(32, "little")
+
+    def eq_tables(self, taus):
+        inst = EqSumCheckInstance(self.fid, taus)
+
+        class _T:
+            def tables(_, rnd):
+                inst.round = rnd
+                return inst._tables()
+        return _T()
+
+    def sc_eval(self, form, A, B, C, local_len, left, right, shift, id_mul, id_add):
+        out = DeviceVec(96)
+        check(lib().b200_sc_eval_sharded_dev(self.fid, form, A.ptr, B.ptr, C.ptr, local_len,
+                                             left.ptr if left else None, right.ptr, shift, id_mul, id_add,
+                                             out.ptr, None))
+        return fields.unpack(self.fid, out.to_bytes(32 * SC_NOUT[form]))
+
+    def bind(self, h, local_len, r):
+        _bind_dev(self.fid, h, local_len, r)

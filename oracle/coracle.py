@@ -165,12 +165,13 @@ def scalar_mul(curve: int, pt: bytes, k: int) -> bytes:
 SC_NOUT = {0: 2, 1: 2, 2: 2, 3: 3, 4: 2, 5: 2, 6: 1, 7: 1, 8: 1, 9: 1, 10: 1}
 
 
-def sc_eval(fid, form, A, B=None, C=None, eq_left=None, eq_right=None, shift=0) -> bytes:
+def sc_eval(fid, form, A, B=None, C=None, eq_left=None, eq_right=None, shift=0, id_mul=1, id_add=0) -> bytes:
     n = len(A) // 32
     out = ctypes.create_string_buffer(96)
-    rc = lib().orc_sc_eval(fid, form, _buf(A), _buf(B) if B else None, _buf(C) if C else None,
-                           ctypes.c_size_t(n), _buf(eq_left) if eq_left else None,
-                           _buf(eq_right) if eq_right else None, shift, out)
+    rc = lib().orc_sc_eval_sharded(fid, form, _buf(A), _buf(B) if B else None, _buf(C) if C else None,
+                                   ctypes.c_size_t(n), _buf(eq_left) if eq_left else None,
+                                   _buf(eq_right) if eq_right else None, shift, ctypes.c_size_t(id_mul),
+                                   ctypes.c_size_t(id_add), out)
     assert rc == 0
     return out.raw[: 32 * SC_NOUT[form]]
 

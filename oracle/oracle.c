@@ -1035,7 +1035,9 @@ EXPORT int orc_scalar_mul(int curve, const void* pt, const uint64_t* k, void* ou
 
 /* ------------------------------------------------------------------ sum-check / MLE -------- */
 /* eq factor of index id (sumcheck.rs:1233-1251): left[id >> shift] * right[id & mask], or right[id] */
+static size_t g_id_mul = 1, g_id_add = 0; /* cyclic sharding of the index (single-threaded use) */
 static void eq_factor(const orc_field_t* F, fe* f, const fe* left, const fe* right, int shift, size_t id) {
+  id = id * g_id_mul + g_id_add;
   if (!left) { *f = right[id]; return; }
   fe_mul(F, f, &left[id >> shift], &right[id & (((size_t)1 << shift) - 1)]);
 }
@@ -1333,4 +1335,16 @@ EXPORT int orc_spmv_t(int fid, const void* data, const uint64_t* indices, const 
       fe_add(F, &O[indices[e]], &O[indices[e]], &t);
     }
   return 0;
+}
+
+/* sharded form: local index j stands for global index j*id_mul + id_add in the eq weight */
+EXPORT int orc_sc_eval_sharded(int fid, int form, const void* a, const void* b, const void* c, size_t len,
+                               const void* eql, const void* eqr, int shift, size_t id_mul, size_t id_add,
+                               void* out) {
+  g_id_mul = id_mul;
+  g_id_add = id_add;
+  int rc = orc_sc_eval(fid, form, a, b, c, len, eql, eqr, shift, out);
+  g_id_mul = 1;
+  g_id_add = 0;
+  return rc;
 }

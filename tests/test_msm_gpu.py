@@ -201,3 +201,21 @@ def test_config1_pedersen_commit_pallas_2p16(b200, oracle):
     v2 = oracle.gen_scalars(c.scalar_field, 2, n)
     s = oracle.vec_add(c.scalar_field, v, v2)
     assert c.add(ce.commit(ck, v, None), ce.commit(ck, v2, None)) == ce.commit(ck, s, None)
+
+
+def test_config4_size_2p22_closed_form(b200, oracle):
+    """BASELINE.json configs[3] size (2^22 BN254 scalars): device-built key bases[i] = (k0+i)G, so the
+    commitment must equal [sum_i s_i (k0+i)] G; plus prefix consistency commit(v[:n/2]) + commit of the
+    zero-padded upper half == commit(v)."""
+    cid, c = 0, CURVES[0]
+    n = 1 << 22
+    ck = b200.CommitmentKey.setup_synthetic(b200.Curve(cid), n, k0=oracle.K0_DEFAULT)
+    sc = oracle.gen_scalars(c.scalar_field, 22, n)
+    g = b200.DlogGroup(cid)
+    got = g.vartime_multiscalar_mul(sc, ck)
+    k = oracle.dot_index(c.scalar_field, sc)
+    assert got == aff(c, oracle.scalar_mul(cid, c.affine_bytes(c.gen), k))
+    half = n // 2
+    lo = g.vartime_multiscalar_mul(sc[:32 * half], ck)
+    hi = g.vartime_multiscalar_mul(bytes(32 * half) + sc[32 * half:], ck)
+    assert c.add(lo, hi) == got
