@@ -119,7 +119,7 @@ struct ck_ctx {
 
 // ---- optional per-stage device timing + launch accounting (for bench.py's roofline) ---------
 enum { ST_DIGITS = 0, ST_SORT, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_COUNT };
-const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 3};
+const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 2};
 struct profile_state {
   std::mutex mu;
   bool enabled = false;

@@ -329,31 +329,40 @@ __global__ void __launch_bounds__(256) k_reduce2(const void* __restrict__ rparts
 }
 
 // ------------------------------------------------------------------------------------------
-// Two-level bucket reduction (used when the bucket index splits into <= 8 + 8 bits).
-// With b = NC*u + v:   sum_b (b+1) B_b = NC * sum_u u R_u + sum_v (v+1) C_v,
-//   R_u = sum_v B[u][v] (row sums),  C_v = sum_u B[u][v] (column sums).
-// A weighted sum  sum_j j S_j  equals  sum_{j>=1} T_j  with suffix sums T_j = sum_{k>=j} S_k, so it
-// needs only a log-depth suffix scan and a tree sum -- no scalar multiplications, no serial
-// running sum.  Critical path: ~9 point additions (k_red_rowcol) + ~17 + log2(NC) doublings
-// (k_red_scan) + 2 (k_red_combine), against ~70 for the chunked running-sum kernels above.
+// Radix-16 digit-sum bucket reduction.  Write the bucket index b in base 16, b = sum_d 16^d v_d:
+//     sum_b (b+1) B_b  =  S_all  +  sum_d 16^d  sum_{v=1}^{15} v * S_d[v],
+//     S_d[v] = sum of the buckets whose digit d equals v,   S_all = sum_b B_b = sum_v S_d[v].
+// k_red_digits computes the (at most 6 x 16) digit sums with plain tree sums spread over the whole
+// GPU (every bucket is read once per digit position); k_red_final turns each 16-entry array into
+// its weighted sum with a shuffle suffix-scan (sum_v v S_v = sum_{j>=1} sum_{v>=j} S_v), scales by
+// 16^d with 4d doublings in parallel across digit positions, and adds up.  No scalar
+// multiplications, no long serial running sums: ~25 dependent point operations in total, each
+// executed with at most a few warps per SM (a lone warp needs ~4 us per point addition because one
+// field product occupies the integer-multiply pipe for ~550 cycles).
 // ------------------------------------------------------------------------------------------
+constexpr int RED_NSPLIT = 4;
 template <class F>
-__global__ void __launch_bounds__(128) k_red_rowcol(const uint32_t* __restrict__ start, uint32_t B,
-                                                    uint32_t NR, uint32_t NC,
-                                                    const void* __restrict__ buckets,
-                                                    void* __restrict__ rc /* [G][NR+NC] */) {
+__global__ void __launch_bounds__(128) k_red_digits(const uint32_t* __restrict__ start, uint32_t B,
+                                                    int bits, const void* __restrict__ buckets,
+                                                    void* __restrict__ parts /* [G][nd][16][NSPLIT] */) {
   using PA = msm_arith<F>;
   __shared__ typename PA::pt sm[128];
-  const uint32_t g = blockIdx.y, j = blockIdx.x;  // j < NR: row j ; else column j - NR
-  const bool is_row = j < NR;
-  const uint32_t len = is_row ? NC : NR;
+  const int nd = (bits + 3) / 4;
+  const int x = blockIdx.x, d = blockIdx.y / 16, v = blockIdx.y % 16, g = blockIdx.z;
+  const int width = bits - 4 * d < 4 ? bits - 4 * d : 4;
   typename PA::pt acc = PA::identity();
-  for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) {
-    uint32_t b = is_row ? j * NC + k : k * NC + (j - NR);
-    uint32_t key = g * B + b;
-    if (b < B && start[key + 1] > start[key]) {
-      typename PA::pt o = PA::load(buckets, key);
-      PA::add(acc, o);
+  if (v < (1 << width)) {
+    const uint32_t count = B >> width;  // buckets whose digit d equals v
+    const uint32_t per = (count + RED_NSPLIT - 1) / RED_NSPLIT;
+    const uint32_t lo = x * per, hi = lo + per < count ? lo + per : count;
+    const uint32_t lowmask = (1u << (4 * d)) - 1;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      uint32_t b = ((i >> (4 * d)) << (4 * d + width)) | ((uint32_t)v << (4 * d)) | (i & lowmask);
+      uint32_t key = g * B + b;
+      if (start[key + 1] > start[key]) {
+        typename PA::pt o = PA::load(buckets, key);
+        PA::add(acc, o);
+      }
     }
   }
   sm[threadIdx.x] = acc;
@@ -366,71 +375,57 @@ __global__ void __launch_bounds__(128) k_red_rowcol(const uint32_t* __restrict__
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) PA::store(rc, (size_t)g * (NR + NC) + j, sm[0]);
+  if (threadIdx.x == 0) PA::store(parts, (((size_t)g * nd + d) * 16 + v) * RED_NSPLIT + x, sm[0]);
 }
 
-// block (g, which): which = 0 -> X = NC * sum_u u R_u ; which = 1 -> Y = sum_v (v+1) C_v
+// one block, 32 threads per digit position (16 active lanes each)
 template <class F>
-__global__ void __launch_bounds__(256) k_red_scan(const void* __restrict__ rc, uint32_t NR, uint32_t NC,
-                                                  int log_nc, void* __restrict__ xy /* [G][2] */) {
+__global__ void __launch_bounds__(256) k_red_final(const void* __restrict__ parts, int G, int bits, int c,
+                                                   void* __restrict__ out_jac) {
   using PA = msm_arith<F>;
-  __shared__ typename PA::pt sm[256];
-  const uint32_t g = blockIdx.x, which = blockIdx.y;
-  const uint32_t n = which == 0 ? NR : NC;
-  const uint32_t base = g * (NR + NC) + (which == 0 ? 0 : NR);
-  const int tid = threadIdx.x;
-  typename PA::pt mine = PA::identity();
-  if ((uint32_t)tid < n) mine = PA::load(rc, base + tid);
-  sm[tid] = mine;
-  __syncthreads();
-  // inclusive suffix scan: T_tid = sum_{k >= tid} S_k
-  for (int d = 1; d < (int)n; d <<= 1) {
-    typename PA::pt o = PA::identity();
-    bool have = (uint32_t)(tid + d) < n;
-    if (have) o = sm[tid + d];
-    __syncthreads();
-    if (have) {
-      PA::add(mine, o);
-      sm[tid] = mine;
-    }
-    __syncthreads();
-  }
-  // rows: sum_{j>=1} T_j (weight u);  columns: sum_{j>=0} T_j (weight v+1)
-  if ((uint32_t)tid >= n || (which == 0 && tid == 0)) sm[tid] = PA::identity();
-  __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (tid < s) {
-      typename PA::pt a = sm[tid];
-      PA::add(a, sm[tid + s]);
-      sm[tid] = a;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    typename PA::pt r = sm[0];
-    if (which == 0)
-      for (int d = 0; d < log_nc; d++) PA::dbl(r);  // * NC
-    PA::store(xy, (size_t)g * 2 + which, r);
-  }
-}
-
-template <class F>
-__global__ void k_red_combine(const void* __restrict__ xy, int G, int c, void* __restrict__ out_jac) {
-  using PA = msm_arith<F>;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ typename PA::pt sm[8];
+  const int nd = (bits + 3) / 4;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typename PA::pt total = PA::identity();
   for (int g = G - 1; g >= 0; g--) {
-    if (g != G - 1)
-      for (int d = 0; d < c; d++) PA::dbl(total);
-    typename PA::pt x = PA::load(xy, (size_t)g * 2), y = PA::load(xy, (size_t)g * 2 + 1);
-    PA::add(total, x);
-    PA::add(total, y);
+    typename PA::pt S = PA::identity();
+    if (w < nd && lane < 16)
+      for (int x = 0; x < RED_NSPLIT; x++) {
+        typename PA::pt o = PA::load(parts, (((size_t)g * nd + w) * 16 + lane) * RED_NSPLIT + x);
+        PA::add(S, o);
+      }
+    // suffix scan over the 16 digit values: T_v = sum_{k >= v} S_k
+    for (int d = 1; d < 16; d <<= 1) {
+      typename PA::pt o = PA::shfl_down(S, d, 16);
+      if (lane < 16 && lane + d < 16) PA::add(S, o);
+    }
+    // weighted sum  sum_{v>=1} T_v  (lane 0 keeps T_0 = S_all aside)
+    typename PA::pt T0 = S;
+    typename PA::pt X = (lane >= 1 && lane < 16) ? S : PA::identity();
+    for (int d = 8; d > 0; d >>= 1) {
+      typename PA::pt o = PA::shfl_down(X, d, 16);
+      if (lane < 16 && lane + d < 16) PA::add(X, o);
+    }
+    if (lane == 0 && w < nd) {
+      for (int k = 0; k < 4 * w; k++) PA::dbl(X);  // * 16^w
+      if (w == 0) PA::add(X, T0);                   // + S_all
+      sm[w] = X;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (g != G - 1)
+        for (int k = 0; k < c; k++) PA::dbl(total);
+      for (int k = 0; k < nd; k++) PA::add(total, sm[k]);
+    }
+    __syncthreads();
   }
-  fe_t X, Y, Z;
-  PA::to_jacobian_std(total, X, Y, Z);
-  fe_store(out_jac, 0, X);
-  fe_store(out_jac, 1, Y);
-  fe_store(out_jac, 2, Z);
+  if (threadIdx.x == 0) {
+    fe_t X, Y, Z;
+    PA::to_jacobian_std(total, X, Y, Z);
+    fe_store(out_jac, 0, X);
+    fe_store(out_jac, 1, Y);
+    fe_store(out_jac, 2, Z);
+  }
 }
 
 // sum of k Jacobian points (the per-GPU partial MSMs after the all-gather);

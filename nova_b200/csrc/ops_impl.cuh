@@ -76,15 +76,11 @@ struct ops_impl {
   }
   static void reduce(cudaStream_t s, const msm_plan& p, void* out_jac) {
     int bits = p.c - 1;  // bucket index bits
-    if (bits >= 2 && bits <= 16) {  // two-level row/column reduction
-      int log_nc = bits / 2, log_nr = bits - log_nc;
-      uint32_t NR = 1u << log_nr, NC = 1u << log_nc;
-      dim3 g1(NR + NC, (unsigned)p.G);
-      k_red_rowcol<F><<<g1, 128, 0, s>>>(p.start, p.B, NR, NC, p.buckets, p.rparts);
-      void* xy = (char*)p.rparts + (size_t)p.G * (NR + NC) * 144;
-      dim3 g2((unsigned)p.G, 2);
-      k_red_scan<F><<<g2, 256, 0, s>>>(p.rparts, NR, NC, log_nc, xy);
-      k_red_combine<F><<<1, 32, 0, s>>>(xy, p.G, p.c, out_jac);
+    if (bits >= 1 && bits <= 24) {  // radix-16 digit sums (msm_kernels.cuh)
+      int nd = (bits + 3) / 4;
+      dim3 g1(RED_NSPLIT, (unsigned)(nd * 16), (unsigned)p.G);
+      k_red_digits<F><<<g1, 128, 0, s>>>(p.start, p.B, bits, p.buckets, p.rparts);
+      k_red_final<F><<<1, 256, 0, s>>>(p.rparts, p.G, bits, p.c, out_jac);
       return;
     }
     uint32_t T = p.B / p.m;
