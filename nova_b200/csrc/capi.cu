@@ -209,7 +209,7 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
     CU(cudaMalloc(&w.buckets, K * XYZZ_BYTES));
     // chunk partials of the running-sum reduce, or [G][NR+NC] row/column sums + [G][2] of the
     // two-level reduce (NR + NC <= 2 * sqrt(2B) + 1 <= B / m + 514)
-    CU(cudaMalloc(&w.rparts, ((size_t)ck.G * (ck.B / ck.m + 516)) * XYZZ_BYTES));
+    CU(cudaMalloc(&w.rparts, ((size_t)ck.G * (ck.B / ck.m + 1600)) * XYZZ_BYTES));
     CU(cudaMalloc(&w.sumscratch, (size_t)SUM_THREADS * XYZZ_BYTES));
   }
   w.cap_n = n;

@@ -24,6 +24,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "curve29.cuh"
+#include "coop.cuh"
 
 namespace nova {
 
@@ -427,6 +428,164 @@ __global__ void __launch_bounds__(256) k_red_final(const void* __restrict__ part
     fe_store(out_jac, 2, Z);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Quad-cooperative versions of the latency-bound tail (coop.cuh): four lanes share every point
+// operation.  Used with the default 8x32-bit arithmetic (pa32); same mathematics as k_fixup /
+// k_red_digits / k_red_final above.
+// ------------------------------------------------------------------------------------------
+#if !defined(NOVA_MSM_ARITH29)
+NOVA_D xyzz_t xyzz_load_q(const void* base, size_t idx) { return xyzz_load(base, idx); }
+
+// one quad per bucket key: serial cooperative adds over the key's boundary partials
+template <class F>
+__global__ void __launch_bounds__(128) k_fixup_q(const uint32_t* __restrict__ start, uint32_t K, int L,
+                                                 uint32_t heavy_min, const void* __restrict__ parts,
+                                                 const uint32_t* __restrict__ pkeys,
+                                                 void* __restrict__ buckets) {
+  quad_comm_dev cm;
+  uint32_t key = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  bool live = key < K;
+  uint32_t s0 = 0, s1 = 0;
+  if (live) {
+    s0 = start[key];
+    s1 = start[key + 1];
+    live = s1 != s0 && s1 - s0 <= heavy_min;
+  }
+  // all lanes of the warp stay in the loop structure; quads whose key is dead add nothing
+  size_t j0 = live ? 2 * ((size_t)s0 / L) : 1, j1 = live ? 2 * (((size_t)s1 - 1) / L) + 1 : 0;
+  xyzz_t acc = xyzz_identity<F>();
+  bool found = false;
+  for (size_t j = j0; j <= j1; j++) {
+    if (pkeys[j] == key) {  // uniform within the quad
+      xyzz_t o = xyzz_load(parts, j);
+      coop_add<F>(acc, o, cm);
+      found = true;
+    }
+  }
+  if (live && found && cm.lane() == 0) xyzz_store(buckets, key, acc);
+}
+
+constexpr int REDQ_NSPLIT = 8;
+// block = 64 quads; block (x, d*16+v, g) sums its slice of the buckets whose digit d equals v
+template <class F>
+__global__ void __launch_bounds__(256) k_red_digits_q(const uint32_t* __restrict__ start, uint32_t B,
+                                                      int bits, const void* __restrict__ buckets,
+                                                      void* __restrict__ parts /* [G][nd][16][NSPLIT] */) {
+  __shared__ xyzz_t sm[64];
+  quad_comm_dev cm;
+  const int nd = (bits + 3) / 4;
+  const int x = blockIdx.x, d = blockIdx.y / 16, v = blockIdx.y % 16, g = blockIdx.z;
+  const int width = bits - 4 * d < 4 ? bits - 4 * d : 4;
+  const int quad = threadIdx.x >> 2;
+  xyzz_t acc = xyzz_identity<F>();
+  if (v < (1 << width)) {
+    const uint32_t count = B >> width;
+    const uint32_t per = (count + REDQ_NSPLIT - 1) / REDQ_NSPLIT;
+    const uint32_t lo = x * per, hi = lo + per < count ? lo + per : count;
+    const uint32_t lowmask = (1u << (4 * d)) - 1;
+    for (uint32_t i = lo + quad; i < hi; i += 64) {
+      uint32_t b = ((i >> (4 * d)) << (4 * d + width)) | ((uint32_t)v << (4 * d)) | (i & lowmask);
+      uint32_t key = g * B + b;
+      if (start[key + 1] > start[key]) {  // uniform within the quad
+        xyzz_t o = xyzz_load(buckets, key);
+        coop_add<F>(acc, o, cm);
+      }
+    }
+  }
+  if (cm.lane() == 0) sm[quad] = acc;
+  __syncthreads();
+  for (int s = 32; s > 0; s >>= 1) {
+    if (quad < s) {
+      xyzz_t o = sm[quad + s];
+      coop_add<F>(acc, o, cm);
+    }
+    __syncthreads();
+    if (quad < s && cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) xyzz_store(parts, (((size_t)g * nd + d) * 16 + v) * REDQ_NSPLIT + x, acc);
+}
+
+// one block of 512 threads = 128 quads: quad (d, v, k), k < 2, for d < nd <= 4 (bits <= 16)
+template <class F>
+__global__ void __launch_bounds__(512) k_red_final_q(const void* __restrict__ parts, int G, int bits, int c,
+                                                      void* __restrict__ out_jac) {
+  __shared__ xyzz_t sm[128];
+  quad_comm_dev cm;
+  const int nd = (bits + 3) / 4;  // <= 4
+  const int quad = threadIdx.x >> 2;
+  const int d = quad >> 5, v = (quad >> 1) & 15, k = quad & 1;  // 2 quads share one (d, v)
+  xyzz_t total = xyzz_identity<F>();
+  for (int g = G - 1; g >= 0; g--) {
+    // 1. S_d[v] = sum of the 8 split partials: 4 serial per quad + 1 tree level
+    xyzz_t acc = xyzz_identity<F>();
+    if (d < nd)
+      for (int x = k; x < REDQ_NSPLIT; x += 2) {
+        xyzz_t o = xyzz_load(parts, (((size_t)g * nd + d) * 16 + v) * REDQ_NSPLIT + x);
+        coop_add<F>(acc, o, cm);
+      }
+    if (cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+    if (k == 0) {
+      xyzz_t o = sm[quad + 1];
+      coop_add<F>(acc, o, cm);
+    }
+    __syncthreads();
+    // quads with k == 0 now hold S_d[v]; their smem slot is sm[(d*16 + v)*2]
+    if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+    // 2. suffix scan over v: T_v = sum_{j>=v} S_j
+    for (int dd = 1; dd < 16; dd <<= 1) {
+      bool have = k == 0 && v + dd < 16;
+      xyzz_t o = xyzz_identity<F>();
+      if (have) o = sm[quad + 2 * dd];
+      __syncthreads();
+      if (have) coop_add<F>(acc, o, cm);
+      if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+      __syncthreads();
+    }
+    // 3. W_d = sum_{v>=1} T_v (tree over v), S_all = T_0 of digit 0
+    xyzz_t t0 = acc;  // T_v of this quad
+    if (k == 0 && v == 0) acc = xyzz_identity<F>();
+    if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+    for (int s = 8; s > 0; s >>= 1) {
+      bool have = k == 0 && v < s;
+      xyzz_t o = xyzz_identity<F>();
+      if (have) o = sm[quad + 2 * s];
+      __syncthreads();
+      if (have) coop_add<F>(acc, o, cm);
+      if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+      __syncthreads();
+    }
+    // 4. quad (d, 0, 0): W_d * 16^d ; digit 0 also adds S_all
+    if (k == 0 && v == 0 && d < nd) {
+      for (int i = 0; i < 4 * d; i++) coop_dbl<F>(acc, cm);
+      if (d == 0) coop_add<F>(acc, t0, cm);
+      if (cm.lane() == 0) sm[quad] = acc;
+    }
+    __syncthreads();
+    // 5. quad 0 combines the digits and the groups
+    if (quad == 0) {
+      if (g != G - 1)
+        for (int i = 0; i < c; i++) coop_dbl<F>(total, cm);
+      for (int dd = 0; dd < nd; dd++) {
+        xyzz_t o = sm[dd * 32];  // quad index of (dd, 0, 0)
+        coop_add<F>(total, o, cm);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    fe_t X, Y, Z;
+    xyzz_to_jacobian<F>(total, X, Y, Z);
+    fe_store(out_jac, 0, X);
+    fe_store(out_jac, 1, Y);
+    fe_store(out_jac, 2, Z);
+  }
+}
+#endif  // !NOVA_MSM_ARITH29
 
 // sum of k Jacobian points (the per-GPU partial MSMs after the all-gather);
 // k is tiny (= number of GPUs), one thread.

@@ -64,8 +64,15 @@ struct ops_impl {
     while (G < 32 && (size_t)G * 8 < ppk) G <<= 1;
     if (ppk <= 16) G = 1;
     size_t threads = (size_t)K * G;
-    k_fixup<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(p.start, K, p.L, p.heavy_min, G, p.parts,
-                                                                 p.pkeys, p.buckets);
+#if !defined(NOVA_MSM_ARITH29)
+    if (G == 1) {  // few partials per bucket: one quad per key, cooperative adds
+      threads = (size_t)K * 4;
+      k_fixup_q<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(p.start, K, p.L, p.heavy_min, p.parts,
+                                                                     p.pkeys, p.buckets);
+    } else
+#endif
+      k_fixup<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(p.start, K, p.L, p.heavy_min, G, p.parts,
+                                                                   p.pkeys, p.buckets);
     k_fixup_heavy<F><<<148, 256, 0, s>>>(p.start, p.L, p.heavy, p.parts, p.pkeys, p.buckets);
   }
   static void index_bases(cudaStream_t s, void* bases, size_t n, const void* gen, uint64_t k0) {
@@ -76,6 +83,15 @@ struct ops_impl {
   }
   static void reduce(cudaStream_t s, const msm_plan& p, void* out_jac) {
     int bits = p.c - 1;  // bucket index bits
+#if !defined(NOVA_MSM_ARITH29)
+    if (bits >= 1 && bits <= 16) {  // radix-16 digit sums, quad-cooperative point operations
+      int nd = (bits + 3) / 4;
+      dim3 g1(REDQ_NSPLIT, (unsigned)(nd * 16), (unsigned)p.G);
+      k_red_digits_q<F><<<g1, 256, 0, s>>>(p.start, p.B, bits, p.buckets, p.rparts);
+      k_red_final_q<F><<<1, 512, 0, s>>>(p.rparts, p.G, bits, p.c, out_jac);
+      return;
+    }
+#endif
     if (bits >= 1 && bits <= 24) {  // radix-16 digit sums (msm_kernels.cuh)
       int nd = (bits + 3) / 4;
       dim3 g1(RED_NSPLIT, (unsigned)(nd * 16), (unsigned)p.G);

@@ -163,3 +163,74 @@ int hc_pt29_sum(int fid, int mode, const void* pts, size_t n, void* out) {
   return 0;
 }
 }
+
+// ---- quad-cooperative XYZZ ops (coop.cuh): 4 std::threads per quad, barrier-based exchange ----
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include "../../nova_b200/csrc/coop.cuh"
+
+namespace {
+struct host_barrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int count = 0, gen = 0;
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    int g = gen;
+    if (++count == 4) { count = 0; gen++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+};
+struct quad_shared { fe_t slot[4]; host_barrier bar; };
+struct quad_comm_host {
+  quad_shared* sh;
+  int q;
+  int lane() const { return q; }
+  fe_t get(const fe_t& v, int src) const {
+    sh->slot[q] = v;
+    sh->bar.wait();
+    fe_t r = sh->slot[src];
+    sh->bar.wait();
+    return r;
+  }
+};
+}  // namespace
+
+// mode 0: sum of points with coop_add (pairs, incl. P+P and P-P); mode 1: [2^k]P with coop_dbl
+template <class F>
+static void coop_run(int mode, const affine_t* pts, size_t n, fe_t* out) {
+  quad_shared sh;
+  xyzz_t results[4];
+  std::thread th[4];
+  for (int q = 0; q < 4; q++)
+    th[q] = std::thread([&, q] {
+      quad_comm_host cm{&sh, q};
+      xyzz_t acc = xyzz_identity<F>();
+      if (mode == 0) {
+        for (size_t i = 0; i < n; i++) {
+          xyzz_t p = xyzz_identity<F>();
+          if (!affine_is_identity(pts[i])) xyzz_madd<F>(p, pts[i].x, pts[i].y);
+          coop_add<F>(acc, p, cm);
+        }
+      } else {
+        xyzz_madd<F>(acc, pts[0].x, pts[0].y);
+        for (size_t i = 0; i < n; i++) coop_dbl<F>(acc, cm);
+      }
+      results[q] = acc;
+    });
+  for (auto& t : th) t.join();
+  for (int q = 1; q < 4; q++)  // all lanes must agree bit for bit
+    if (memcmp(&results[q], &results[0], sizeof(xyzz_t)) != 0) { memset(out, 0xff, 96); return; }
+  xyzz_to_jacobian<F>(results[0], out[0], out[1], out[2]);
+}
+extern "C" int hc_coop(int fid, int mode, const void* pts, size_t n, void* out) {
+  switch (fid) {
+    case 0: coop_run<BN254_FR>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 1: coop_run<BN254_FQ>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 2: coop_run<PALLAS_FP>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    case 3: coop_run<PALLAS_FQ>(mode, (const affine_t*)pts, n, (fe_t*)out); break;
+    default: return 1;
+  }
+  return 0;
+}

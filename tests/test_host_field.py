@@ -17,9 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def hc():
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
     so = os.path.join(HERE, "hostcheck", "libhostcheck.so")
-    hdrs = [os.path.join(HERE, "..", "nova_b200", "csrc", f) for f in ("field.cuh", "curve.cuh", "field_constants.cuh")]
+    hdrs = [os.path.join(HERE, "..", "nova_b200", "csrc", f) for f in ("field.cuh", "curve.cuh", "field_constants.cuh", "field29.cuh", "curve29.cuh", "coop.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
     return ctypes.CDLL(so)
 
 
@@ -80,3 +80,23 @@ def test_xyzz_formulas(hc, cid):
         out = ctypes.create_string_buffer(96)
         hc.hc_pt_sum(c.base_field, 2, _buf(c.affine_bytes(pts[4])), ctypes.c_size_t(k), out)
         assert c.jacobian_from_bytes(out.raw) == c.mul(k, pts[4])
+
+
+@pytest.mark.parametrize("cid", [0, 2])
+def test_quad_cooperative_ops(hc, cid):
+    """coop.cuh: four lanes (here four std::threads with a barrier-based exchange) share one XYZZ
+    addition / doubling and must all end with the same, correct point."""
+    c = CURVES[cid]
+    pts = c.bases_arith(12)
+    seq = [pts[3], pts[3], None, pts[5], c.neg(pts[5]), pts[7], pts[7], pts[7], pts[1], None] + pts
+    exp = None
+    for P in seq:
+        exp = c.add(exp, P)
+    data = b"".join(c.affine_bytes(P) for P in seq)
+    out = ctypes.create_string_buffer(96)
+    hc.hc_coop(c.base_field, 0, _buf(data), ctypes.c_size_t(len(seq)), out)
+    assert c.jacobian_from_bytes(out.raw) == exp
+    for k in (1, 5, 17):
+        out = ctypes.create_string_buffer(96)
+        hc.hc_coop(c.base_field, 1, _buf(c.affine_bytes(pts[4])), ctypes.c_size_t(k), out)
+        assert c.jacobian_from_bytes(out.raw) == c.mul(1 << k, pts[4])
