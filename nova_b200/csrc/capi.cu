@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -166,7 +167,13 @@ constexpr size_t ACC_THREADS = (size_t)148 * 16 * 32 * 3;
 constexpr uint32_t HEAVY_PARTS = 96;  // buckets spanning more segments than this get a block
 
 int segment_len(size_t entries) {
-  size_t L = (entries + ACC_THREADS - 1) / ACC_THREADS;
+  // tuning hook: NOVA_B200_ACC_WAVES overrides the number of full-GPU waves of accumulate threads
+  static const size_t threads = [] {
+    const char* e = getenv("NOVA_B200_ACC_WAVES");
+    double w = e ? atof(e) : 0.0;
+    return w > 0.0 ? (size_t)(148.0 * 16 * 32 * w) : ACC_THREADS;
+  }();
+  size_t L = (entries + threads - 1) / threads;
   return (int)(L < L_MIN ? L_MIN : L);
 }
 
@@ -299,6 +306,9 @@ int choose_window(size_t n) {
   int c = lg;
   if (c < 8) c = 8;
   if (c > 16) c = 16;
+  // large keys: 13 windows of 20 bits instead of 16 of 16 (-19 % bucket additions); the 2^19-bucket
+  // reduction costs ~1 ms, so this only pays from 2^22 points (measured: profiles/r01i_sizes.md)
+  if (lg >= 22) c = 20;
   return c;
 }
 

@@ -85,7 +85,7 @@ def test_msm_identity_bases_and_duplicates(b200, oracle):
     assert b200.DlogGroup(cid).vartime_multiscalar_mul(sc[:32 * 32], ck0) is None
 
 
-@pytest.mark.parametrize("window_bits", [4, 8, 11, 13, 16])
+@pytest.mark.parametrize("window_bits", [2, 4, 8, 11, 13, 16, 17, 20])
 def test_msm_window_sizes(b200, oracle, window_bits):
     cid, c = 0, CURVES[0]
     n = 3000
