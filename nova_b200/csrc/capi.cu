@@ -120,7 +120,7 @@ struct ck_ctx {
 
 // ---- optional per-stage device timing + launch accounting (for bench.py's roofline) ---------
 enum { ST_DIGITS = 0, ST_SORT, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_COUNT };
-const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 2};
+const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 3};
 struct profile_state {
   std::mutex mu;
   bool enabled = false;
@@ -216,7 +216,7 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
     CU(cudaMalloc(&w.buckets, K * XYZZ_BYTES));
     // chunk partials of the running-sum reduce, or [G][NR+NC] row/column sums + [G][2] of the
     // two-level reduce (NR + NC <= 2 * sqrt(2B) + 1 <= B / m + 514)
-    CU(cudaMalloc(&w.rparts, ((size_t)ck.G * (ck.B / ck.m + 1600)) * XYZZ_BYTES));
+    CU(cudaMalloc(&w.rparts, ((size_t)ck.G * (ck.B / ck.m + 4096)) * XYZZ_BYTES));
     CU(cudaMalloc(&w.sumscratch, (size_t)SUM_THREADS * XYZZ_BYTES));
   }
   w.cap_n = n;
@@ -309,6 +309,7 @@ int choose_window(size_t n) {
   // large keys: 13 windows of 20 bits instead of 16 of 16 (-19 % bucket additions); the 2^19-bucket
   // reduction costs ~1 ms, so this only pays from 2^22 points (measured: profiles/r01i_sizes.md)
   if (lg >= 22) c = 20;
+  else if (lg >= 19) c = 17;  // 15 windows; the 65536-bucket reduction still fits the fast tail
   return c;
 }
 

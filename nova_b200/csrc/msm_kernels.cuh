@@ -466,22 +466,23 @@ __global__ void __launch_bounds__(128) k_fixup_q(const uint32_t* __restrict__ st
   if (live && found && cm.lane() == 0) xyzz_store(buckets, key, acc);
 }
 
-constexpr int REDQ_NSPLIT = 8;
-// block = 64 quads; block (x, d*16+v, g) sums its slice of the buckets whose digit d equals v
+// Stage 1: block (x, d*16+v, g), 64 quads, sums its slice of the buckets whose digit d equals v.
+// nsplit = gridDim.x is chosen by the host so that a quad adds ~4 buckets before the tree.
 template <class F>
 __global__ void __launch_bounds__(256) k_red_digits_q(const uint32_t* __restrict__ start, uint32_t B,
                                                       int bits, const void* __restrict__ buckets,
-                                                      void* __restrict__ parts /* [G][nd][16][NSPLIT] */) {
+                                                      void* __restrict__ parts /* [G][nd][16][nsplit] */) {
   __shared__ xyzz_t sm[64];
   quad_comm_dev cm;
   const int nd = (bits + 3) / 4;
+  const int nsplit = gridDim.x;
   const int x = blockIdx.x, d = blockIdx.y / 16, v = blockIdx.y % 16, g = blockIdx.z;
   const int width = bits - 4 * d < 4 ? bits - 4 * d : 4;
   const int quad = threadIdx.x >> 2;
   xyzz_t acc = xyzz_identity<F>();
   if (v < (1 << width)) {
     const uint32_t count = B >> width;
-    const uint32_t per = (count + REDQ_NSPLIT - 1) / REDQ_NSPLIT;
+    const uint32_t per = (count + nsplit - 1) / nsplit;
     const uint32_t lo = x * per, hi = lo + per < count ? lo + per : count;
     const uint32_t lowmask = (1u << (4 * d)) - 1;
     for (uint32_t i = lo + quad; i < hi; i += 64) {
@@ -504,74 +505,88 @@ __global__ void __launch_bounds__(256) k_red_digits_q(const uint32_t* __restrict
     if (quad < s && cm.lane() == 0) sm[quad] = acc;
     __syncthreads();
   }
-  if (threadIdx.x == 0) xyzz_store(parts, (((size_t)g * nd + d) * 16 + v) * REDQ_NSPLIT + x, acc);
+  if (threadIdx.x == 0) xyzz_store(parts, (((size_t)g * nd + d) * 16 + v) * nsplit + x, acc);
 }
 
-// one block of 512 threads = 128 quads: quad (d, v, k), k < 2, for d < nd <= 4 (bits <= 16)
+// Stage 2: block (d*16+v, g) tree-sums the nsplit partials of one digit value -> merged[g][d][v]
 template <class F>
-__global__ void __launch_bounds__(512) k_red_final_q(const void* __restrict__ parts, int G, int bits, int c,
-                                                      void* __restrict__ out_jac) {
-  __shared__ xyzz_t sm[128];
+__global__ void __launch_bounds__(256) k_red_merge_q(const void* __restrict__ parts, int nd, int nsplit,
+                                                     void* __restrict__ merged) {
+  __shared__ xyzz_t sm[64];
   quad_comm_dev cm;
-  const int nd = (bits + 3) / 4;  // <= 4
+  const int dv = blockIdx.x, g = blockIdx.y;
   const int quad = threadIdx.x >> 2;
-  const int d = quad >> 5, v = (quad >> 1) & 15, k = quad & 1;  // 2 quads share one (d, v)
-  xyzz_t total = xyzz_identity<F>();
-  for (int g = G - 1; g >= 0; g--) {
-    // 1. S_d[v] = sum of the 8 split partials: 4 serial per quad + 1 tree level
-    xyzz_t acc = xyzz_identity<F>();
-    if (d < nd)
-      for (int x = k; x < REDQ_NSPLIT; x += 2) {
-        xyzz_t o = xyzz_load(parts, (((size_t)g * nd + d) * 16 + v) * REDQ_NSPLIT + x);
-        coop_add<F>(acc, o, cm);
-      }
-    if (cm.lane() == 0) sm[quad] = acc;
-    __syncthreads();
-    if (k == 0) {
-      xyzz_t o = sm[quad + 1];
+  const size_t base = ((size_t)g * nd * 16 + dv) * nsplit;
+  xyzz_t acc = xyzz_identity<F>();
+  for (int x = quad; x < nsplit; x += 64) {
+    xyzz_t o = xyzz_load(parts, base + x);
+    coop_add<F>(acc, o, cm);
+  }
+  if (cm.lane() == 0) sm[quad] = acc;
+  __syncthreads();
+  for (int s = 32; s > 0; s >>= 1) {
+    if (quad < s && s < nsplit) {  // uniform per block level: skip levels beyond the partial count
+      xyzz_t o = sm[quad + s];
       coop_add<F>(acc, o, cm);
     }
     __syncthreads();
-    // quads with k == 0 now hold S_d[v]; their smem slot is sm[(d*16 + v)*2]
-    if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+    if (quad < s && cm.lane() == 0) sm[quad] = acc;
     __syncthreads();
-    // 2. suffix scan over v: T_v = sum_{j>=v} S_j
+  }
+  if (threadIdx.x == 0) xyzz_store(merged, (size_t)g * nd * 16 + dv, acc);
+}
+
+// Stage 3: one block, one quad per (d, v), d < nd <= 6: weighted sums, 16^d scaling, combine
+template <class F>
+__global__ void __launch_bounds__(384) k_red_final_q(const void* __restrict__ merged, int G, int bits, int c,
+                                                     void* __restrict__ out_jac) {
+  __shared__ xyzz_t sm[96];
+  quad_comm_dev cm;
+  const int nd = (bits + 3) / 4;  // <= 6
+  const int quad = threadIdx.x >> 2;
+  const int d = quad >> 4, v = quad & 15;
+  xyzz_t total = xyzz_identity<F>();
+  for (int g = G - 1; g >= 0; g--) {
+    xyzz_t acc = xyzz_identity<F>();
+    if (d < nd) acc = xyzz_load(merged, ((size_t)g * nd + d) * 16 + v);  // S_d[v]
+    if (cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+    // suffix scan over v: T_v = sum_{j>=v} S_j
     for (int dd = 1; dd < 16; dd <<= 1) {
-      bool have = k == 0 && v + dd < 16;
+      bool have = v + dd < 16;
       xyzz_t o = xyzz_identity<F>();
-      if (have) o = sm[quad + 2 * dd];
+      if (have) o = sm[quad + dd];
       __syncthreads();
       if (have) coop_add<F>(acc, o, cm);
-      if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+      if (cm.lane() == 0) sm[quad] = acc;
       __syncthreads();
     }
-    // 3. W_d = sum_{v>=1} T_v (tree over v), S_all = T_0 of digit 0
-    xyzz_t t0 = acc;  // T_v of this quad
-    if (k == 0 && v == 0) acc = xyzz_identity<F>();
-    if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+    // W_d = sum_{v>=1} T_v (tree over v); S_all = T_0 of digit 0
+    xyzz_t t0 = acc;
+    if (v == 0) acc = xyzz_identity<F>();
+    if (cm.lane() == 0) sm[quad] = acc;
     __syncthreads();
     for (int s = 8; s > 0; s >>= 1) {
-      bool have = k == 0 && v < s;
+      bool have = v < s;
       xyzz_t o = xyzz_identity<F>();
-      if (have) o = sm[quad + 2 * s];
+      if (have) o = sm[quad + s];
       __syncthreads();
       if (have) coop_add<F>(acc, o, cm);
-      if (k == 0 && cm.lane() == 0) sm[quad] = acc;
+      if (cm.lane() == 0) sm[quad] = acc;
       __syncthreads();
     }
-    // 4. quad (d, 0, 0): W_d * 16^d ; digit 0 also adds S_all
-    if (k == 0 && v == 0 && d < nd) {
+    // quad (d, 0): W_d * 16^d ; digit 0 also adds S_all
+    if (v == 0 && d < nd) {
       for (int i = 0; i < 4 * d; i++) coop_dbl<F>(acc, cm);
       if (d == 0) coop_add<F>(acc, t0, cm);
       if (cm.lane() == 0) sm[quad] = acc;
     }
     __syncthreads();
-    // 5. quad 0 combines the digits and the groups
-    if (quad == 0) {
+    if (quad == 0) {  // combine the digits and (for un-expanded keys) the window groups
       if (g != G - 1)
         for (int i = 0; i < c; i++) coop_dbl<F>(total, cm);
       for (int dd = 0; dd < nd; dd++) {
-        xyzz_t o = sm[dd * 32];  // quad index of (dd, 0, 0)
+        xyzz_t o = sm[dd * 16];
         coop_add<F>(total, o, cm);
       }
     }

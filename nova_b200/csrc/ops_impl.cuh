@@ -84,11 +84,18 @@ struct ops_impl {
   static void reduce(cudaStream_t s, const msm_plan& p, void* out_jac) {
     int bits = p.c - 1;  // bucket index bits
 #if !defined(NOVA_MSM_ARITH29)
-    if (bits >= 1 && bits <= 16) {  // radix-16 digit sums, quad-cooperative point operations
+    if (bits >= 1 && bits <= 24) {  // radix-16 digit sums, quad-cooperative point operations
       int nd = (bits + 3) / 4;
-      dim3 g1(REDQ_NSPLIT, (unsigned)(nd * 16), (unsigned)p.G);
+      uint32_t count = p.B >> (bits < 4 ? bits : 4);  // buckets per digit value (full-width digits)
+      int nsplit = (int)((count + 255) / 256);          // ~4 buckets per quad, then a 6-level tree
+      if (nsplit < 1) nsplit = 1;
+      if (nsplit > 4096) nsplit = 4096;
+      char* merged = (char*)p.rparts + (size_t)p.G * nd * 16 * nsplit * 128;
+      dim3 g1((unsigned)nsplit, (unsigned)(nd * 16), (unsigned)p.G);
       k_red_digits_q<F><<<g1, 256, 0, s>>>(p.start, p.B, bits, p.buckets, p.rparts);
-      k_red_final_q<F><<<1, 512, 0, s>>>(p.rparts, p.G, bits, p.c, out_jac);
+      dim3 g2((unsigned)(nd * 16), (unsigned)p.G);
+      k_red_merge_q<F><<<g2, 256, 0, s>>>(p.rparts, nd, nsplit, merged);
+      k_red_final_q<F><<<1, 384, 0, s>>>(merged, p.G, bits, p.c, out_jac);
       return;
     }
 #endif
