@@ -305,13 +305,81 @@ class EqSumCheckInstance:
         q, p = self.eval_eq_left, self.p
         return e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p
 
+    def evaluation_points_quadratic_with_one_input(self, A, length, claim):
+        """sumcheck.rs:1039-1080 (+ fall-back :1180-1213)."""
+        L, R, sh = self._tables()
+        (t0,) = _sc_eval_dev(self.fid, SC_EQ_QUAD1, A, None, None, length, L, R, sh)
+        d = self._derive(t0, 0, claim, False)
+        if d is not None:
+            return d
+        (tm1,) = _sc_eval_dev(self.fid, SC_EQ_QUAD1_M1, A, None, None, length, L, R, sh)
+        e0, _, em1 = self.eq_tau_0_a_inf[self.round - 1]
+        q, p = self.eval_eq_left, self.p
+        return e0 * q * t0 % p, 0, em1 * q * tm1 % p
+
     def bound(self, r):
         tau = self.taus[self.round - 1]
         self.eval_eq_left = self.eval_eq_left * (1 - tau - r + 2 * r * tau) % self.p
         self.round += 1
 
 
+def update_claim(p, claim, evals, r):
+    """SumcheckProof::update_claim (sumcheck.rs:68-75)."""
+    e0, c3, em1 = evals
+    e1 = (claim - e0) % p
+    half = pow(2, -1, p)
+    a1 = ((e1 - em1) * half - c3) % p
+    a2 = ((e1 + em1) * half - e0) % p
+    return (e0 + r * (a1 + r * (a2 + r * c3))) % p
+
+
 class SumcheckProof:
+    @staticmethod
+    def prove_batch_eval(fid, claims, num_rounds, polys: list, eq_points: list, coeffs, transcript):
+        """sumcheck.rs:251-351: batched evaluation claims of different sizes; polynomials resident on
+        the device, one `eq_quad1` reduction per active instance per round."""
+        p = fields.MODULUS[fid]
+        k = len(claims)
+        assert len(num_rounds) == k and len(polys) == k and len(eq_points) == k and len(coeffs) == k
+        for i in range(k):
+            assert len(polys[i]) == 32 << num_rounds[i], f"poly size mismatch at index {i}"
+            assert len(eq_points[i]) == num_rounds[i], f"eq_point length mismatch at index {i}"
+        nmax = max(num_rounds)
+        dev = [DeviceVec.from_bytes(P) for P in polys]
+        lens = [1 << nr for nr in num_rounds]
+        eqs = [EqSumCheckInstance(fid, pts) for pts in eq_points]
+        running = list(claims)
+        e = sum(claims[i] * pow(2, nmax - num_rounds[i], p) * coeffs[i] for i in range(k)) % p
+        rs, out = [], []
+        for cur in range(nmax):
+            rem = nmax - cur
+            evals = []
+            for i in range(k):
+                if rem <= num_rounds[i]:
+                    e0, _, em1 = eqs[i].evaluation_points_quadratic_with_one_input(dev[i], lens[i], running[i])
+                    evals.append((e0, 0, em1))
+                else:
+                    sc = pow(2, rem - num_rounds[i] - 1, p) * claims[i] % p
+                    evals.append((sc, 0, sc))
+            c0 = sum(evals[i][0] * coeffs[i] for i in range(k)) % p
+            cm1 = sum(evals[i][2] * coeffs[i] for i in range(k)) % p
+            c1 = (e - c0) % p
+            quad = (c1 + cm1 - 2 * c0) * pow(2, -1, p) % p
+            poly = UniPoly.from_evals_deg2(p, [c0, c1, quad])
+            transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+            r = transcript.squeeze(b"c")
+            rs.append(r)
+            for i in range(k):
+                if rem <= num_rounds[i]:
+                    running[i] = update_claim(p, running[i], evals[i], r)
+                    _bind_dev(fid, dev[i], lens[i], r)
+                    lens[i] //= 2
+                    eqs[i].bound(r)
+            e = poly.evaluate(r)
+            out.append(poly.compress())
+        finals = [fields.unpack(fid, d.to_bytes(32))[0] for d in dev]
+        return out, rs, finals
+
     @staticmethod
     def prove_quad_prod(fid, claim, num_rounds, poly_A: bytes, poly_B: bytes, transcript):
         """sumcheck.rs:199-242 -> (compressed polys, challenges r, [A(r), B(r)])."""

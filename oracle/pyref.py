@@ -556,3 +556,51 @@ def prove_cubic_with_three_inputs(p, claim, taus, A, B, C, transcript):
         A, B, C = bind_top(p, A, r), bind_top(p, B, r), bind_top(p, C, r)
         eq.bound(r)
     return polys, rs, [A[0], B[0], C[0]]
+
+
+def update_claim(p, claim, evals, r):
+    """SumcheckProof::update_claim (sumcheck.rs:68-75)."""
+    e0, c3, em1 = evals
+    e1 = (claim - e0) % p
+    half = pow(2, -1, p)
+    a1 = ((e1 - em1) * half - c3) % p
+    a2 = ((e1 + em1) * half - e0) % p
+    return (e0 + r * (a1 + r * (a2 + r * c3))) % p
+
+
+def prove_batch_eval(p, claims, num_rounds, polys, eq_points, coeffs, transcript):
+    """SumcheckProof::prove_batch_eval (sumcheck.rs:251-351): instances of different sizes,
+    e_i = sum_x P_i(x) eq(x_i, x), combined with `coeffs`."""
+    k = len(claims)
+    polys = [list(P) for P in polys]
+    nmax = max(num_rounds)
+    eqs = [EqSumCheckInstance(p, pts) for pts in eq_points]
+    running = list(claims)
+    e = sum(claims[i] * pow(2, nmax - num_rounds[i], p) * coeffs[i] for i in range(k)) % p
+    rs, out = [], []
+    for cur in range(nmax):
+        rem = nmax - cur
+        evals = []
+        for i in range(k):
+            if rem <= num_rounds[i]:
+                e0, _, em1 = eqs[i].evaluation_points_quadratic_with_one_input(polys[i], running[i])
+                evals.append((e0, 0, em1))
+            else:
+                sc = pow(2, rem - num_rounds[i] - 1, p) * claims[i] % p
+                evals.append((sc, 0, sc))
+        c0 = sum(evals[i][0] * coeffs[i] for i in range(k)) % p
+        cm1 = sum(evals[i][2] * coeffs[i] for i in range(k)) % p
+        c1 = (e - c0) % p
+        quad = (c1 + cm1 - 2 * c0) * pow(2, -1, p) % p
+        poly = UniPoly.from_evals_deg2(p, [c0, c1, quad])
+        transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+        r = transcript.squeeze(b"c")
+        rs.append(r)
+        for i in range(k):
+            if rem <= num_rounds[i]:
+                running[i] = update_claim(p, running[i], evals[i], r)
+                polys[i] = bind_top(p, polys[i], r)
+                eqs[i].bound(r)
+        e = poly.evaluate(r)
+        out.append(poly.compressed())
+    return out, rs, [P[0] for P in polys]

@@ -190,6 +190,26 @@ def test_sumcheck_provers_match_reference_restatement(sp, oracle, fid):
         assert got == exp
 
 
+def test_prove_batch_eval_matches_restatement(sp, oracle):
+    """SumcheckProof::prove_batch_eval (sumcheck.rs:251-351): instances of different sizes (the
+    smaller ones start late with replicated constants), eq instance of the one-input form incl. the
+    tau = 0 fall-back; prover messages equal the big-integer restatement."""
+    from oracle.pyref import prove_batch_eval
+    fid = 0
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(99)
+    num_rounds = [9, 6, 9, 1]
+    polys = [[rng.field(p) for _ in range(1 << nr)] for nr in num_rounds]
+    eq_points = [[rng.field(p) for _ in range(nr)] for nr in num_rounds]
+    eq_points[1][2] = 0  # tau = 0 in the middle of the smaller instance
+    claims = [rng.field(p) for _ in num_rounds]
+    coeffs = [rng.field(p) for _ in num_rounds]
+    exp = prove_batch_eval(p, claims, num_rounds, polys, eq_points, coeffs, Keccak256Transcript(p, b"be"))
+    got = sp.SumcheckProof.prove_batch_eval(fid, claims, num_rounds, [pack(p, P) for P in polys], eq_points, coeffs,
+                                            Keccak256Transcript(p, b"be"))
+    assert got == exp
+
+
 # ---------------------------------------------------------------- batch invert / rlc ----------
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 4096, (1 << 15) + 5])
 def test_batch_invert(sp, oracle, n):
