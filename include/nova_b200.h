@@ -99,6 +99,8 @@ int b200_msm_dev(uint64_t ck_handle, size_t base_offset, const void* d_scalars_m
  * Needs a key registered with h unless r is NULL. */
 int b200_commit(uint64_t ck_handle, const void* scalars_mont, size_t n, const void* r_mont_or_null,
                 void* out_jacobian_mont);
+int b200_commit_dev(uint64_t ck_handle, const void* d_scalars_mont, size_t n,
+                    const void* d_blind_mont_or_null, void* d_out_jacobian_mont, void* stream);
 /* k MSMs over prefixes of the same key: vector j uses ck[..lens[j]] (traits.rs:82-90,
  * blitzar.rs:23-40, hyperkzg.rs:594-612 batch_commit).  out = k x 96 B. */
 int b200_msm_batch(uint64_t ck_handle, const void* const* scalars_mont, const size_t* lens,
@@ -152,8 +154,9 @@ int b200_bind_top_dev(int field_id, void* z_inout, size_t n, const void* r, void
  *   6 eq_quad1   t0 of eq*A                                          sumcheck.rs:1039-1080
  *   7,8,9        t(-1) fall-backs of 4,5,6 (tau = 0)                 sumcheck.rs:1082-1213
  *   10 dot_eq    sum Z[i] * eq[i]  (len = number of terms)
+ *   11 dot       sum A[i] * B[i]   (inner_product, provider/ipa_pc.rs:102-108)
  * eq factor of index id: eq_left[id >> shift] * eq_right[id & (2^shift - 1)], or eq_right[id] when
- * eq_left is NULL (sumcheck.rs:1233-1251).  out receives 2, 2, 2, 3, 2, 2, 1, 1, 1, 1, 1 elements. */
+ * eq_left is NULL (sumcheck.rs:1233-1251).  out receives 2, 2, 2, 3, 2, 2, 1, 1, 1, 1, 1, 1 elements. */
 int b200_sc_eval(int field_id, int form, const void* A, const void* B, const void* C, size_t len,
                  const void* eq_left, size_t eq_left_len, const void* eq_right, size_t eq_right_len,
                  int shift, void* out);
@@ -195,6 +198,23 @@ int b200_poly_eval_dev(int field_id, const void* f, size_t n, const void* us, si
 /* h = f / (X - u): n-1 coefficients, h[i-1] = f[i] + u*h[i] (hyperkzg.rs:961-999) */
 int b200_poly_div(int field_id, const void* f, size_t n, const void* u, void* out);
 int b200_poly_div_dev(int field_id, const void* f, size_t n, const void* u, void* out, void* stream);
+
+/* ---- inner-product argument (provider/ipa_pc.rs:174-285), "next" row (f)1 of SURVEY.md §8 ------
+ * The reference folds the commitment key every round (ck.fold, pedersen.rs:484-497: n/2 two-point
+ * MSMs) and commits over the folded key.  Equivalent and GPU-friendlier: keep the ORIGINAL key
+ * (registered once, window tables) and put the fold weights into the scalars:
+ *     L_k = MSM(key, sL) + (c_L r0) * ck_c,   sL[j] = [j & nk/2] a[j mod nk/2] w[j]
+ *     R_k = MSM(key, sR) + (c_R r0) * ck_c,   sR[j] = [!(j & nk/2)] a[(j mod nk/2) + nk/2] w[j]
+ * with w the running product of r / r^-1 per original index.  Group elements are canonical, so
+ * L_vec, R_vec and a_hat are bit-identical to the reference's. */
+/* out[i] = v[i]*x_lo + v[i + n/2]*x_hi, i < n/2  (a and b folds, ipa_pc.rs:244-254) */
+int b200_fold_halves_dev(int field_id, const void* v, size_t n, const void* x_lo, const void* x_hi,
+                         void* out, void* stream);
+int b200_ipa_scalars_dev(int field_id, const void* a, const void* w, size_t n, size_t nk, void* sL,
+                         void* sR, void* stream);
+/* nk == 0: w := 1 ; else w[j] *= (j & nk/2) ? r : r_inv */
+int b200_ipa_weights_dev(int field_id, void* w, size_t n, size_t nk, const void* r, const void* r_inv,
+                         void* stream);
 
 /* ---- sparse matrices (r1cs/sparse.rs:19-319) ------------------------------------------------
  * CSR as in SparseMatrix{data, indices, indptr, cols} (sparse.rs:235-247); registration uploads

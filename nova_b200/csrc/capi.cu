@@ -602,6 +602,27 @@ int b200_msm_dev(uint64_t handle, size_t base_offset, const void* d_scalars, siz
                      stream ? (cudaStream_t)stream : g_dev.stream);
 }
 
+int b200_commit_dev(uint64_t handle, const void* d_scalars, size_t n, const void* d_blind_or_null,
+                    void* d_out, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (!d_out || (n && !d_scalars)) return fail(B200_E_ARG, "null pointer");
+  if (n > ck->n) return fail(B200_E_RANGE, "commit of %zu scalars exceeds key length %zu", n, ck->n);
+  if (d_blind_or_null && !ck->has_h)
+    return fail(B200_E_ARG, "key was registered without a blinding generator");
+  std::lock_guard<std::mutex> lk(ck->mu);
+  rc = ensure_workspace(*ck, n + 1, 1);
+  if (rc) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : g_dev.stream;
+  if (!d_blind_or_null) return enqueue_msm(*ck, 0, d_scalars, n, d_out, s);
+  // the blinding scalar must follow the vector in one buffer: stage both in the workspace
+  if (n) CU(cudaMemcpyAsync(ck->ws.scalars, d_scalars, n * 32, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync((char*)ck->ws.scalars + n * 32, d_blind_or_null, 32, cudaMemcpyDeviceToDevice, s));
+  return enqueue_msm(*ck, 0, ck->ws.scalars, n + 1, d_out, s, 0, true);
+}
+
 int b200_msm_batch(uint64_t handle, const void* const* scalars, const size_t* lens, size_t k,
                    void* out) {
   int rc = ensure_init();

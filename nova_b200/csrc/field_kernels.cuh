@@ -65,4 +65,52 @@ __global__ void __launch_bounds__(256) k_bind_top(void* z, size_t half,
   }
 }
 
+// ---- inner-product argument helpers (provider/ipa_pc.rs:174-285, restated without key folding) --
+// out[i] = v[i]*x_lo + v[i+half]*x_hi   (a' = a_L r + r^-1 a_R ; b' = b_L r^-1 + r b_R, ipa_pc.rs:244-254)
+template <class F>
+__global__ void __launch_bounds__(256) k_fold_halves(const void* __restrict__ v, size_t half,
+                                                     const void* __restrict__ x_lo,
+                                                     const void* __restrict__ x_hi, void* __restrict__ out) {
+  const fe_t xl = fe_load(x_lo, 0), xh = fe_load(x_hi, 0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half;
+       i += (size_t)gridDim.x * blockDim.x)
+    fe_store(out, i, fe_add<F>(fe_mul<F>(fe_load_rw(v, i), xl), fe_mul<F>(fe_load_rw(v, i + half), xh)));
+}
+// The folded key of round k is G^(k)_i = sum_m w[i + m nk] G_{i + m nk} over the ORIGINAL key, so
+//   L = <a_L, ck_R^(k)> = MSM(original key, sL),  sL[j] = [j & nk/2] a[j mod nk/2] w[j]
+//   R = <a_R, ck_L^(k)> = MSM(original key, sR),  sR[j] = [!(j & nk/2)] a[(j mod nk/2) + nk/2] w[j]
+// and the key itself is never folded (pedersen.rs:484-497 `fold` is what this replaces).
+template <class F>
+__global__ void __launch_bounds__(256) k_ipa_scalars(const void* __restrict__ a, const void* __restrict__ w,
+                                                     size_t n, size_t nk, void* __restrict__ sL,
+                                                     void* __restrict__ sR) {
+  const size_t half = nk / 2;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (size_t)gridDim.x * blockDim.x) {
+    size_t i = j & (half - 1);
+    bool hi = (j & half) != 0;
+    fe_t wj = fe_load_rw(w, j);
+    fe_t prod = fe_mul<F>(fe_load_rw(a, hi ? i : i + half), wj);
+    fe_store(sL, j, hi ? prod : fe_zero<F>());
+    fe_store(sR, j, hi ? fe_zero<F>() : prod);
+  }
+}
+// w[j] *= (j & nk/2) ? r : r^-1   (ck.fold(&r_inverse, &r): first half r^-1, second half r)
+template <class F>
+__global__ void __launch_bounds__(256) k_ipa_weights(void* __restrict__ w, size_t n, size_t nk,
+                                                     const void* __restrict__ r,
+                                                     const void* __restrict__ r_inv) {
+  const size_t half = nk / 2;
+  const fe_t rr = fe_load(r, 0), ri = fe_load(r_inv, 0);
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (size_t)gridDim.x * blockDim.x)
+    fe_store(w, j, fe_mul<F>(fe_load_rw(w, j), (j & half) ? rr : ri));
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_fill_one(void* __restrict__ w, size_t n) {
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (size_t)gridDim.x * blockDim.x)
+    fe_store(w, j, fe_one<F>());
+}
+
 }  // namespace nova

@@ -33,6 +33,10 @@ struct field_ops {
   void (*axpy)(cudaStream_t, const void* a, const void* b, const void* r, size_t n, void* out);
   void (*vec_add)(cudaStream_t, const void* a, const void* b, size_t n, void* out);
   void (*bind_top)(cudaStream_t, void* z, size_t n, const void* r);
+  void (*fold_halves)(cudaStream_t, const void* v, size_t half, const void* x_lo, const void* x_hi, void* out);
+  void (*ipa_scalars)(cudaStream_t, const void* a, const void* w, size_t n, size_t nk, void* sL, void* sR);
+  void (*ipa_weights)(cudaStream_t, void* w, size_t n, size_t nk, const void* r, const void* r_inv);
+  void (*fill_one)(cudaStream_t, void* w, size_t n);
   // --- sum-check / MLE / HyperKZG / SpMV (poly_kernels.cuh) ----------------------------------
   // form: sc_form_id; writes sc_form_nout(form) elements to out; scratch >= SC_MAX_BLOCKS*3*32 B
   void (*sc_reduce)(cudaStream_t, int form, const void* A, const void* B, const void* C, size_t count,

@@ -133,6 +133,20 @@ struct ops_impl {
   static void bind_top(cudaStream_t s, void* z, size_t n, const void* r) {
     k_bind_top<F><<<stream_grid(n / 2, 256), 256, 0, s>>>(z, n / 2, r);
   }
+  static void fold_halves(cudaStream_t s, const void* v, size_t half, const void* x_lo, const void* x_hi,
+                          void* out) {
+    k_fold_halves<F><<<stream_grid(half, 256), 256, 0, s>>>(v, half, x_lo, x_hi, out);
+  }
+  static void ipa_scalars(cudaStream_t s, const void* a, const void* w, size_t n, size_t nk, void* sL,
+                          void* sR) {
+    k_ipa_scalars<F><<<stream_grid(n, 256), 256, 0, s>>>(a, w, n, nk, sL, sR);
+  }
+  static void ipa_weights(cudaStream_t s, void* w, size_t n, size_t nk, const void* r, const void* r_inv) {
+    k_ipa_weights<F><<<stream_grid(n, 256), 256, 0, s>>>(w, n, nk, r, r_inv);
+  }
+  static void fill_one(cudaStream_t s, void* w, size_t n) {
+    k_fill_one<F><<<stream_grid(n, 256), 256, 0, s>>>(w, n);
+  }
   template <int FORM>
   static void sc_launch(cudaStream_t s, const void* A, const void* B, const void* C, size_t count,
                         size_t half, const void* eq_left, const void* eq_right, int shift,
@@ -171,6 +185,7 @@ struct ops_impl {
       SC_CASE(SC_EQ_CUBIC2_M1);
       SC_CASE(SC_EQ_QUAD1_M1);
       SC_CASE(SC_DOT_EQ);
+      SC_CASE(SC_DOT);
       default: break;
     }
 #undef SC_CASE
@@ -257,6 +272,7 @@ struct ops_impl {
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top,
+                     fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t};
   }
 };

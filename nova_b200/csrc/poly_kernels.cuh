@@ -116,6 +116,7 @@ enum sc_form_id {
   SC_EQ_CUBIC2_M1 = 8,  // t(-1) = sum f (A(-1)B(-1) - 1)       fallback     sumcheck.rs:1132-1178
   SC_EQ_QUAD1_M1 = 9,   // t(-1) = sum f A(-1)                  fallback     sumcheck.rs:1180-1213
   SC_DOT_EQ = 10,     // sum f Z[id]  (MLE evaluation, multilinear.rs:98-127; h unused)
+  SC_DOT = 11,        // sum A[id] B[id]  (inner_product, provider/ipa_pc.rs:102-108)
 };
 
 template <class F, int FORM>
@@ -125,7 +126,9 @@ struct sc_form {
   eq_factor eq;
   template <int N>
   NOVA_D void operator()(size_t id, fe_t (&acc)[N]) const {
-    if constexpr (FORM == SC_DOT_EQ) {
+    if constexpr (FORM == SC_DOT) {
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), fe_load(B, id)));
+    } else if constexpr (FORM == SC_DOT_EQ) {
       acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), eq.get<F>(id)));
     } else if constexpr (FORM == SC_QUAD_PROD) {
       fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
@@ -182,7 +185,7 @@ struct sc_form {
 
 constexpr int sc_form_nout(int form) {
   return form == SC_CUBIC ? 3
-         : (form == SC_EQ_QUAD1 || form == SC_DOT_EQ || form >= SC_EQ_CUBIC3_M1) ? 1
+         : (form == SC_EQ_QUAD1 || form == SC_DOT_EQ || form == SC_DOT || form >= SC_EQ_CUBIC3_M1) ? 1
                                                                                 : 2;
 }
 

@@ -604,3 +604,44 @@ def prove_batch_eval(p, claims, num_rounds, polys, eq_points, coeffs, transcript
         e = poly.evaluate(r)
         out.append(poly.compressed())
     return out, rs, [P[0] for P in polys]
+
+
+# ----------------------------------------------------------------------------------------
+# Inner-product argument, literal restatement of provider/ipa_pc.rs:174-285 (key folded each round)
+# ----------------------------------------------------------------------------------------
+def commitment_transcript_bytes(P) -> bytes:
+    """pedersen.rs:107-117: x || y || is_infinity (coordinates are (0, 0, 1) for the identity)."""
+    if P is None:
+        return to_repr(0) + to_repr(0) + b"\x01"
+    return to_repr(P[0]) + to_repr(P[1]) + b"\x00"
+
+
+def ipa_prove(curve: "Curve", ck, ck_c, comm_a, b_vec, c_claim, a_vec, transcript):
+    """InnerProductArgument::prove.  ck: list of affine points (len >= n), ck_c: one affine point,
+    U = (comm_a, b_vec, c).  Returns (L_vec, R_vec, a_hat)."""
+    q = curve.q
+    n = len(b_vec)
+    assert len(a_vec) == n
+    transcript.absorb_bytes(b"NoDS", b"IPA")  # dom_sep(protocol_name) (keccak.rs:162-167)
+    ck = list(ck[:n])  # split_at(U.b_vec.len())
+    transcript.absorb_bytes(b"U", commitment_transcript_bytes(comm_a) + to_repr(c_claim % q))  # :131-140
+    r0 = transcript.squeeze(b"r")
+    ck_c_s = curve.mul(r0, ck_c)  # ck_c.scale(&r)
+    a, b = [x % q for x in a_vec], [x % q for x in b_vec]
+    L_vec, R_vec = [], []
+    while len(a) > 1:
+        h = len(a) // 2
+        c_L = sum(x * y for x, y in zip(a[:h], b[h:])) % q
+        c_R = sum(x * y for x, y in zip(a[h:], b[:h])) % q
+        L = curve.msm_naive(a[:h] + [c_L], ck[h:] + [ck_c_s])  # commit(ck_R.combine(ck_c), a_L || c_L, 0)
+        R = curve.msm_naive(a[h:] + [c_R], ck[:h] + [ck_c_s])
+        transcript.absorb_bytes(b"L", commitment_transcript_bytes(L))
+        transcript.absorb_bytes(b"R", commitment_transcript_bytes(R))
+        r = transcript.squeeze(b"r")
+        ri = pow(r, -1, q)
+        a = [(a[i] * r + ri * a[i + h]) % q for i in range(h)]
+        b = [(b[i] * ri + r * b[i + h]) % q for i in range(h)]
+        ck = [curve.add(curve.mul(ri, ck[i]), curve.mul(r, ck[i + h])) for i in range(h)]  # ck.fold(r_inv, r)
+        L_vec.append(L)
+        R_vec.append(R)
+    return L_vec, R_vec, a[0]
