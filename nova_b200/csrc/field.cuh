@@ -274,9 +274,9 @@ NOVA_HD void mont_round(uint32_t (&E)[17], uint32_t (&O)[17], const fe_t& a, uin
   }
 }
 
-// r = a * b * R^-1 mod p
+// r = a * b * R^-1 mod p   (carry-chain form; fe_mul below selects the form the build uses)
 template <class F>
-NOVA_HD fe_t fe_mul(const fe_t& a, const fe_t& b) {
+NOVA_HD fe_t fe_mul_chain(const fe_t& a, const fe_t& b) {
   uint32_t E[17], O[17];
 #pragma unroll
   for (int i = 0; i < 17; i++) E[i] = O[i] = 0;
@@ -292,6 +292,110 @@ NOVA_HD fe_t fe_mul(const fe_t& a, const fe_t& b) {
   add8_cin(r.l, &E[8], &O[8], E[7], O[7]);  // < 2p
   fe_reduce_once<F>(r.l);
   return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Carry-save variant.  On B200 the carry-IN form IMAD.WIDE.U32.X issues at half the rate of
+// the plain IMAD.WIDE.U32 (profiles/r01b_microbench.md), and 103 of the 128 wide products of
+// fe_mul above sit inside carry chains.  Here every wide product is its own two-instruction
+// chain (carry-out only) and the carry-out is counted into a small per-position counter K[]
+// by an addc on the ALU pipe; counters are folded in when their position retires.
+// Same even/odd accumulators, same result (bit-exact with fe_mul; tests/test_host_field.py).
+// ---------------------------------------------------------------------------------------
+NOVA_HD void mad_cs(uint32_t& lo, uint32_t& hi, uint32_t& k, uint32_t x, uint32_t y) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(lo), "+r"(hi), "+r"(k)
+      : "r"(x), "r"(y));
+#else
+  uint64_t acc = ((uint64_t)hi << 32) | lo;
+  uint64_t prod = (uint64_t)x * y;
+  uint64_t s = acc + prod;
+  k += s < prod ? 1u : 0u;
+  lo = (uint32_t)s;
+  hi = (uint32_t)(s >> 32);
+#endif
+}
+
+// k_next += carry32(e + o) + kz   (kz in {0,1})
+NOVA_HD void retire_cs(uint32_t& k_next, uint32_t e, uint32_t o, uint32_t kz) {
+#ifdef __CUDA_ARCH__
+  uint32_t t;
+  asm("add.cc.u32 %1, %2, %3;\n\t"
+      "addc.u32 %0, %0, %4;"
+      : "+r"(k_next), "=r"(t)
+      : "r"(e), "r"(o), "r"(kz));
+#else
+  k_next += (uint32_t)(((uint64_t)e + o) >> 32) + kz;
+#endif
+}
+
+template <class F, int I>
+NOVA_HD void mont_round_cs(uint32_t (&E)[16], uint32_t (&O)[16], uint32_t (&K)[17], const fe_t& a,
+                           uint32_t bi) {
+  // A: the accumulator whose (lo,hi) pairs start at position I; B: the one starting at I+1
+  uint32_t(&A)[16] = (I & 1) ? O : E;
+  uint32_t(&B)[16] = (I & 1) ? E : O;
+  mad_cs(A[I + 0], A[I + 1], K[I + 2], a.l[0], bi);
+  mad_cs(B[I + 1], B[I + 2], K[I + 3], a.l[1], bi);
+  mad_cs(A[I + 2], A[I + 3], K[I + 4], a.l[2], bi);
+  mad_cs(B[I + 3], B[I + 4], K[I + 5], a.l[3], bi);
+  mad_cs(A[I + 4], A[I + 5], K[I + 6], a.l[4], bi);
+  mad_cs(B[I + 5], B[I + 6], K[I + 7], a.l[5], bi);
+  mad_cs(A[I + 6], A[I + 7], K[I + 8], a.l[6], bi);
+  mad_cs(B[I + 7], B[I + 8], K[I + 9], a.l[7], bi);
+  uint32_t m = (E[I] + O[I] + K[I]) * F::INV;
+  mad_cs(A[I + 0], A[I + 1], K[I + 2], F::p(0), m);
+  mad_cs(B[I + 1], B[I + 2], K[I + 3], F::p(1), m);
+  mad_cs(A[I + 2], A[I + 3], K[I + 4], F::p(2), m);
+  mad_cs(B[I + 3], B[I + 4], K[I + 5], F::p(3), m);
+  mad_cs(A[I + 4], A[I + 5], K[I + 6], F::p(4), m);
+  mad_cs(B[I + 5], B[I + 6], K[I + 7], F::p(5), m);
+  mad_cs(A[I + 6], A[I + 7], K[I + 8], F::p(6), m);
+  mad_cs(B[I + 7], B[I + 8], K[I + 9], F::p(7), m);
+  // position I now sums to 0 mod 2^32: E[I] + O[I] + K[I] = c * 2^32 with
+  // c = carry32(E[I] + O[I]) + (K[I] != 0); c moves to position I+1
+  retire_cs(K[I + 1], E[I], O[I], K[I] ? 1u : 0u);
+}
+
+template <class F>
+NOVA_HD fe_t fe_mul_cs(const fe_t& a, const fe_t& b) {
+  uint32_t E[16], O[16], K[17];
+#pragma unroll
+  for (int i = 0; i < 16; i++) E[i] = O[i] = K[i] = 0;
+  K[16] = 0;
+  mont_round_cs<F, 0>(E, O, K, a, b.l[0]);
+  mont_round_cs<F, 1>(E, O, K, a, b.l[1]);
+  mont_round_cs<F, 2>(E, O, K, a, b.l[2]);
+  mont_round_cs<F, 3>(E, O, K, a, b.l[3]);
+  mont_round_cs<F, 4>(E, O, K, a, b.l[4]);
+  mont_round_cs<F, 5>(E, O, K, a, b.l[5]);
+  mont_round_cs<F, 6>(E, O, K, a, b.l[6]);
+  mont_round_cs<F, 7>(E, O, K, a, b.l[7]);
+  // result = positions 8..15 of E + O + K (< 2p < 2^256, so K[16] == 0 and no carry leaves)
+  uint32_t hiE[8], hiO[8], hiK[8], t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    hiE[i] = E[8 + i];
+    hiO[i] = O[8 + i];
+    hiK[i] = K[8 + i];
+  }
+  fe_t r;
+  add8(t, hiE, hiO);
+  add8(r.l, t, hiK);
+  fe_reduce_once<F>(r.l);
+  return r;
+}
+
+template <class F>
+NOVA_HD fe_t fe_mul(const fe_t& a, const fe_t& b) {
+#ifdef NOVA_MUL_CS
+  return fe_mul_cs<F>(a, b);
+#else
+  return fe_mul_chain<F>(a, b);
+#endif
 }
 
 template <class F>

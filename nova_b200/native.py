@@ -17,7 +17,8 @@ class B200Error(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libnova_b200.so")
+    # NOVA_B200_LIB selects another build of the same library (A/B timing of kernel variants)
+    return os.environ.get("NOVA_B200_LIB") or os.path.join(_HERE, "libnova_b200.so")
 
 
 # every symbol include/nova_b200.h declares: name -> argtypes (all return int unless noted)

@@ -10,11 +10,12 @@ static void fe_op(int op, const fe_t& a, const fe_t& b, fe_t& r) {
   switch (op) {
     case 0: r = fe_add<F>(a, b); break;
     case 1: r = fe_sub<F>(a, b); break;
-    case 2: r = fe_mul<F>(a, b); break;
+    case 2: r = fe_mul_chain<F>(a, b); break;
     case 3: r = fe_inv<F>(a); break;
     case 4: r = fe_to_mont<F>(a); break;
     case 5: r = fe_from_mont<F>(a); break;
     case 6: r = fe_neg<F>(a); break;
+    case 7: r = fe_mul_cs<F>(a, b); break;
   }
 }
 

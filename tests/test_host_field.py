@@ -36,7 +36,7 @@ def test_field_ops(hc, fid):
     A = b"".join(mont_bytes(p, a) for a, _ in pairs)
     B = b"".join(mont_bytes(p, b) for _, b in pairs)
     n = len(pairs)
-    for op, fn in [(0, lambda a, b: (a + b) % p), (1, lambda a, b: (a - b) % p), (2, lambda a, b: a * b % p),
+    for op, fn in [(0, lambda a, b: (a + b) % p), (1, lambda a, b: (a - b) % p), (2, lambda a, b: a * b % p), (7, lambda a, b: a * b % p),
                    (6, lambda a, b: (-a) % p)]:
         out = ctypes.create_string_buffer(32 * n)
         assert hc.hc_fe_op(fid, op, _buf(A), _buf(B), out, ctypes.c_size_t(n)) == 0

@@ -55,6 +55,15 @@ def main():
             best, avg = time_msm(ck, d_sc, n, d_out)
             cc = ctypes.c_int(0); nt = ctypes.c_int(0)
             lib().b200_ck_len(ck.handle, None, ctypes.byref(cc), ctypes.byref(nt))
+            L = lib()
+            check(L.b200_profile_enable(1)); check(L.b200_profile_reset())
+            time_msm(ck, d_sc, n, d_out, iters=3)
+            st = (ctypes.c_double * 5)(); mm = ctypes.c_uint64(0); ll = ctypes.c_uint64(0)
+            check(L.b200_profile_read(st, 5, ctypes.byref(mm), ctypes.byref(ll)))
+            check(L.b200_profile_enable(0))
+            stages = " ".join(f"{nm}={st[i] / max(1, mm.value):.3f}" for i, nm in
+                              enumerate(["digits", "sort", "acc", "fixup", "reduce"]))
+            print(f"  stages(ms): {stages}")
             print(f"  c={cc.value} tables={nt.value} register {treg*1e3:.0f} ms | msm best {best:.3f} ms avg {avg:.3f} ms "
                   f"-> {n/best/1e3:.1f} M pairs/s", flush=True)
             ck.release()

@@ -13,9 +13,9 @@ template <int OP>
 __global__ void probe(uint64_t* out, uint32_t a0, uint32_t b0, double d0) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t acc[ILP];
-  uint32_t lo[ILP], x = a0 + tid, y = b0 | 1;
+  uint32_t lo[ILP], hi[ILP], kk[ILP], x = a0 + tid, y = b0 | 1;
   double fd[ILP], da = d0 + tid * 1e-9, db = 1.0000001;
-  for (int k = 0; k < ILP; k++) { acc[k] = tid + k; lo[k] = tid * 7 + k; fd[k] = d0 + k; }
+  for (int k = 0; k < ILP; k++) { acc[k] = tid + k; lo[k] = tid * 7 + k; hi[k] = tid + 3 * k; kk[k] = k; fd[k] = d0 + k; }
   for (int i = 0; i < ITER; i++) {
 #pragma unroll
     for (int k = 0; k < ILP; k++) {
@@ -31,6 +31,12 @@ __global__ void probe(uint64_t* out, uint32_t a0, uint32_t b0, double d0) {
         asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(fd[k]) : "d"(da), "d"(db));
       } else if (OP == 5) {  // mad.hi
         asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(x), "r"(y));
+      } else if (OP == 7) {  // carry-save product: wide mad with carry-OUT only + addc into a counter
+        asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                     : "+r"(lo[k]), "+r"(hi[k]), "+r"(kk[k]) : "r"(x), "r"(y));
+      } else if (OP == 8) {  // wide mad with carry-out only, carry discarded into ONE shared counter per 2
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(lo[k]), "+r"(hi[k]) : "r"(x), "r"(y));
       } else if (OP == 6) {  // carry chain pair (the field.cuh pattern)
         asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
                      : "+r"(lo[k]), "+r"(lo[(k + 1) % ILP]) : "r"(x), "r"(y));
@@ -38,12 +44,12 @@ __global__ void probe(uint64_t* out, uint32_t a0, uint32_t b0, double d0) {
     }
   }
   uint64_t s = 0;
-  for (int k = 0; k < ILP; k++) s += acc[k] + lo[k] + (uint64_t)fd[k];
+  for (int k = 0; k < ILP; k++) s += acc[k] + lo[k] + hi[k] + kk[k] + (uint64_t)fd[k];
   out[tid] = s;
 }
 
 // the real thing: dependent fe_mul chains, NCH independent chains per thread
-template <int NCH>
+template <int NCH, int VAR>
 __global__ void __launch_bounds__(128) probe_femul(nova::fe_t* out, int iters) {
   using namespace nova;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(128) probe_femul(nova::fe_t* out, int iters) {
   x[0].l[7] &= 0x0fffffff; y.l[7] &= 0x0fffffff;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int k = 0; k < NCH; k++) x[k] = fe_mul<BN254_FQ>(x[k], y);
+    for (int k = 0; k < NCH; k++) x[k] = VAR ? fe_mul_cs<BN254_FQ>(x[k], y) : fe_mul_chain<BN254_FQ>(x[k], y);
   }
   fe_t s = x[0];
   for (int k = 1; k < NCH; k++) s = fe_add<BN254_FQ>(s, x[k]);
@@ -76,21 +82,21 @@ __global__ void probe_chain(uint32_t* out, uint32_t a0, uint32_t b0) {
   out[tid] = s;
 }
 
-template <int NCH>
+template <int NCH, int VAR = 0>
 void run_femul(int blocks_per_sm) {
   int dev; cudaGetDevice(&dev);
   cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
   int blocks = p.multiProcessorCount * blocks_per_sm, threads = 128, iters = 512;
   nova::fe_t* out; cudaMalloc(&out, (size_t)blocks * threads * 32);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  probe_femul<NCH><<<blocks, threads>>>(out, iters);
+  probe_femul<NCH, VAR><<<blocks, threads>>>(out, iters);
   cudaDeviceSynchronize();
   cudaEventRecord(e0);
-  probe_femul<NCH><<<blocks, threads>>>(out, iters);
+  probe_femul<NCH, VAR><<<blocks, threads>>>(out, iters);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   double muls = (double)blocks * threads * iters * NCH;
-  printf("fe_mul chains=%d warps/SM=%2d  %8.3f ms  %7.2f G mul/s  (%.0f wide-mults/clk/SM of 64)\n", NCH,
+  printf("%s chains=%d warps/SM=%2d  %8.3f ms  %7.2f G mul/s  (%.0f wide-mults/clk/SM of 64)\n", VAR ? "fe_mul_cs" : "fe_mul   ", NCH,
          blocks_per_sm * 4, ms, muls / ms / 1e6, muls * 136 / (ms * 1e-3) / 1.965e9 / p.multiProcessorCount);
   cudaFree(out);
 }
@@ -147,5 +153,10 @@ int main() {
   run_femul<1>(2); run_femul<1>(4); run_femul<1>(8);
   run_femul<2>(2); run_femul<2>(4);
   run_femul<4>(2);
+  run<7>("wide mad carry-out + addc", 1);
+  run<8>("wide mad carry-out only", 1);
+  run_femul<1, 1>(2); run_femul<1, 1>(4); run_femul<1, 1>(8);
+  run_femul<2, 1>(2); run_femul<2, 1>(4);
+  run_femul<4, 1>(2);
   return 0;
 }
