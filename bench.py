@@ -130,29 +130,63 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from nova_b200.sharding import shard_range
-    n_total = 1 << args.log2n
-    lo, hi = shard_range(n_total, rank, world)  # this rank's index range of (scalar, base) pairs
-    n = hi - lo
-    ck = nb.CommitmentKey.setup_synthetic(nb.Curve(CURVE), n, k0=K0 + lo, window_bits=args.window_bits)
-    sc_np = synth_scalars(n_total, seed=2)[lo:hi]
-
-    stream = torch.cuda.Stream()
-    sp = ctypes.c_void_p(stream.cuda_stream)
-    d_sc = torch.from_numpy(sc_np.view("uint8").reshape(-1)).cuda()
-    d_part = torch.zeros(96, dtype=torch.uint8, device="cuda")
-    d_all = torch.zeros(96 * world, dtype=torch.uint8, device="cuda")
-    d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
-
-    def step_device():
-        check(L.b200_msm_dev(ck.handle, 0, d_sc.data_ptr(), n, d_part.data_ptr(), sp))
-        if world > 1:
-            dist.all_gather_into_tensor(d_all, d_part)
-            check(L.b200_jacobian_sum_dev(CURVE, d_all.data_ptr(), world, d_out.data_ptr(), sp))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    d_part = torch.zeros(96, dtype=torch.uint8, device="cuda")
+    d_all = torch.zeros(96 * world, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
+
+    def sharded_msm_step(ck_, d_sc_, n_):
+        """One MSM of the whole vector: local Pippenger over this rank's index range, then (N > 1)
+        all-gather of the 96-byte partial points and a local sum on every rank."""
+        check(L.b200_msm_dev(ck_.handle, 0, d_sc_.data_ptr(), n_, d_part.data_ptr(), sp))
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_part)
+            check(L.b200_jacobian_sum_dev(CURVE, d_all.data_ptr(), world, d_out.data_ptr(), sp))
+
+    def time_other_size(log2n, steps, warmup):
+        """Same sharded MSM at another total size (BASELINE.json configs[3] names 2^22): device time
+        per step, max over ranks.  Reported beside the headline, never instead of it."""
+        nt = 1 << log2n
+        lo_, hi_ = shard_range(nt, rank, world)
+        n_ = hi_ - lo_
+        ck_ = nb.CommitmentKey.setup_synthetic(nb.Curve(CURVE), n_, k0=K0 + lo_)
+        d_sc_ = torch.from_numpy(synth_scalars(nt, seed=2)[lo_:hi_].view("uint8").reshape(-1)).cuda()
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                sharded_msm_step(ck_, d_sc_, n_)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(steps):
+                sharded_msm_step(ck_, d_sc_, n_)
+            b.record(stream)
+            barrier()
+        tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ck_.release()
+        del d_sc_
+        torch.cuda.empty_cache()
+        ms = float(tt.item()) / steps
+        return {"log2n": log2n, "pairs_per_step": nt, "ms_per_step": round(ms, 4), "value": nt / (ms * 1e-3),
+                "unit": UNIT, "steps": steps, "warmup": warmup}
+
+    n_total = 1 << args.log2n
+    lo, hi = shard_range(n_total, rank, world)  # this rank's index range of (scalar, base) pairs
+    n = hi - lo
+    ck = nb.CommitmentKey.setup_synthetic(nb.Curve(CURVE), n, k0=K0 + lo, window_bits=args.window_bits)
+    sc_np = synth_scalars(n_total, seed=2)[lo:hi]
+    d_sc = torch.from_numpy(sc_np.view("uint8").reshape(-1)).cuda()
+
+    def step_device():
+        sharded_msm_step(ck, d_sc, n)
 
     # ---------------- device-resident throughput ("value") --------------------------------------
     with torch.cuda.stream(stream):
@@ -216,6 +250,9 @@ def run_b200(args):
     e2e_ms_per_step = float(t.item()) / args.steps
     check(L.b200_host_free(h_ptr))
 
+    # ---------------- the same sharded MSM at the other sizes north_star names -------------------
+    other_sizes = [time_other_size(lg, steps=5, warmup=3) for lg in args.other_log2n if lg != args.log2n]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -278,6 +315,7 @@ def run_b200(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "prove_step_replay": prove_step,
+        "other_sizes": other_sizes,
     }
     print(json.dumps(out))
     if world > 1:
@@ -358,6 +396,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--other-log2n", type=lambda v: [int(x) for x in v.split(",") if x], default=[22, 24],
+                    help="also time the sharded MSM at these total sizes (reported under other_sizes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prove-step", action="store_true")
     args = ap.parse_args()

@@ -140,6 +140,12 @@ int b200_axpy_dev(int field_id, const void* a, const void* b, const void* r, siz
                   void* stream);
 int b200_vec_add_dev(int field_id, const void* a, const void* b, size_t n, void* out, void* stream);
 int b200_bind_top_dev(int field_id, void* z_inout, size_t n, const void* r, void* stream);
+/* out[i] = a[i]*b[i]   (TS[i] * (T[i]+r)^-1, spartan/ppsnark.rs:446-449) */
+int b200_vec_mul_dev(int field_id, const void* a, const void* b, size_t n, void* out, void* stream);
+/* LogUp fingerprints with the shift folded in: out[i] = val[i]*gamma + addr[i] + r; addr == NULL
+ * means the cell's own index i   (MemorySumcheckInstance::compute_oracles, ppsnark.rs:386-435) */
+int b200_logup_hash_dev(int field_id, const void* val, const void* addr_or_null, const void* gamma,
+                        const void* r, size_t n, void* out, void* stream);
 
 /* ---- sum-check rounds (spartan/sumcheck.rs) ------------------------------------------------
  * One call computes the O(N) sums of one round; the host keeps the O(1) algebra (claim

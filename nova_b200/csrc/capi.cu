@@ -754,6 +754,27 @@ int b200_axpy_dev(int fid, const void* a, const void* b, const void* r, size_t n
     return (int)B200_OK;
   });
 }
+int b200_vec_mul_dev(int fid, const void* a, const void* b, size_t n, void* out, void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (n == 0) return (int)B200_OK;
+    if (!a || !b || !out) return fail(B200_E_ARG, "null pointer");
+    ops->vec_mul(stream ? (cudaStream_t)stream : g_dev.stream, a, b, n, out);
+    count_launch(1);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
+int b200_logup_hash_dev(int fid, const void* val, const void* addr_or_null, const void* gamma,
+                        const void* r, size_t n, void* out, void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (n == 0) return (int)B200_OK;
+    if (!val || !gamma || !r || !out) return fail(B200_E_ARG, "null pointer");
+    ops->logup_hash(stream ? (cudaStream_t)stream : g_dev.stream, val, addr_or_null, gamma, r, n, out);
+    count_launch(1);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
 int b200_vec_add_dev(int fid, const void* a, const void* b, size_t n, void* out, void* stream) {
   return with_field(fid, [&](const field_ops* ops) {
     if (n == 0) return (int)B200_OK;

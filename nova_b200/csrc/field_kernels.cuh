@@ -6,6 +6,8 @@
 //   k_axpy        out = a + r*b                        src/r1cs/mod.rs:1044-1073 (W, E folds)
 //   k_vec_add     out = a + b                          src/r1cs/mod.rs:589-609 (Z = Z1 + Z2)
 //   k_bind_top    Z[i] += r*(Z[i+n/2] - Z[i])          src/spartan/polys/multilinear.rs:65-84
+//   k_vec_mul     out = a o b                          src/spartan/ppsnark.rs:446-449 (inv o TS)
+//   k_logup_hash  out = val*gamma + addr + r           src/spartan/ppsnark.rs:386-435 (T+r, W+r)
 #pragma once
 #include <cuda_runtime.h>
 #include "field.cuh"
@@ -50,6 +52,41 @@ __global__ void __launch_bounds__(256) k_vec_add(const void* __restrict__ a,
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
     fe_store(out, i, fe_add<F>(fe_load(a, i), fe_load(b, i)));
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_vec_mul(const void* __restrict__ a,
+                                                 const void* __restrict__ b, size_t n,
+                                                 void* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fe_store(out, i, fe_mul<F>(fe_load(a, i), fe_load(b, i)));
+  }
+}
+
+// LogUp fingerprint with the challenge shift folded in (MemorySumcheckInstance::compute_oracles,
+// ppsnark.rs:386-435): out[i] = val[i]*gamma + addr[i] + r, where addr == nullptr means the
+// memory's own address i (T[i] = mem[i]*gamma + i, `E::Scalar::from(i as u64)` at :394).
+template <class F>
+__global__ void __launch_bounds__(256) k_logup_hash(const void* __restrict__ val,
+                                                    const void* __restrict__ addr,
+                                                    const void* __restrict__ gamma_ptr,
+                                                    const void* __restrict__ r_ptr, size_t n,
+                                                    void* __restrict__ out) {
+  const fe_t gamma = fe_load(gamma_ptr, 0), r = fe_load(r_ptr, 0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fe_t a;
+    if (addr != nullptr) {
+      a = fe_load(addr, i);
+    } else {
+      fe_t c = fe_zero<F>();
+      c.l[0] = (uint32_t)i;
+      c.l[1] = (uint32_t)((uint64_t)i >> 32);
+      a = fe_to_mont<F>(c);
+    }
+    fe_store(out, i, fe_add<F>(fe_add<F>(fe_mul<F>(fe_load(val, i), gamma), a), r));
   }
 }
 

@@ -33,6 +33,9 @@ struct field_ops {
   void (*axpy)(cudaStream_t, const void* a, const void* b, const void* r, size_t n, void* out);
   void (*vec_add)(cudaStream_t, const void* a, const void* b, size_t n, void* out);
   void (*bind_top)(cudaStream_t, void* z, size_t n, const void* r);
+  void (*vec_mul)(cudaStream_t, const void* a, const void* b, size_t n, void* out);
+  void (*logup_hash)(cudaStream_t, const void* val, const void* addr_or_null, const void* gamma,
+                     const void* r, size_t n, void* out);
   void (*fold_halves)(cudaStream_t, const void* v, size_t half, const void* x_lo, const void* x_hi, void* out);
   void (*ipa_scalars)(cudaStream_t, const void* a, const void* w, size_t n, size_t nk, void* sL, void* sR);
   void (*ipa_weights)(cudaStream_t, void* w, size_t n, size_t nk, const void* r, const void* r_inv);

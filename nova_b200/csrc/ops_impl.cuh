@@ -130,6 +130,13 @@ struct ops_impl {
   static void vec_add(cudaStream_t s, const void* a, const void* b, size_t n, void* out) {
     k_vec_add<F><<<stream_grid(n, 256), 256, 0, s>>>(a, b, n, out);
   }
+  static void vec_mul(cudaStream_t s, const void* a, const void* b, size_t n, void* out) {
+    k_vec_mul<F><<<stream_grid(n, 256), 256, 0, s>>>(a, b, n, out);
+  }
+  static void logup_hash(cudaStream_t s, const void* val, const void* addr, const void* gamma,
+                         const void* r, size_t n, void* out) {
+    k_logup_hash<F><<<stream_grid(n, 256), 256, 0, s>>>(val, addr, gamma, r, n, out);
+  }
   static void bind_top(cudaStream_t s, void* z, size_t n, const void* r) {
     k_bind_top<F><<<stream_grid(n / 2, 256), 256, 0, s>>>(z, n / 2, r);
   }
@@ -271,7 +278,7 @@ struct ops_impl {
   }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
-                     sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top,
+                     sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, vec_mul, logup_hash,
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t};
   }

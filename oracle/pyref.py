@@ -504,6 +504,24 @@ class EqSumCheckInstance:
         q = self.eval_eq_left
         return e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p
 
+    def evaluation_points_cubic_with_two_inputs(self, A, B, claim):  # sumcheck.rs:972-1033
+        p = self.p
+        h = len(A) // 2
+        t0 = tinf = 0
+        for i in range(h):
+            f = self.factor(i)
+            t0 += (A[i] * B[i] - 1) * f
+            tinf += (A[h + i] - A[i]) * (B[h + i] - B[i]) * f
+        t0 %= p
+        tinf %= p
+        d = self.derive_deg2(t0, tinf, claim)
+        if d is not None:
+            return d
+        e0, slope, em1 = self.eq_tau_0_a_inf[self.round - 1]  # fallback sumcheck.rs:1134-1178
+        tm1 = sum(((2 * A[i] - A[h + i]) * (2 * B[i] - B[h + i]) - 1) * self.factor(i) for i in range(h)) % p
+        q = self.eval_eq_left
+        return e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p
+
     def evaluation_points_quadratic_with_one_input(self, A, claim):  # sumcheck.rs:1039-1080
         p = self.p
         h = len(A) // 2
