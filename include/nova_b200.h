@@ -62,6 +62,9 @@ int b200_dev_alloc(size_t bytes, void** dptr);
 int b200_dev_free(void* dptr);
 int b200_memcpy_h2d(void* dptr, const void* hptr, size_t bytes);
 int b200_memcpy_d2h(void* hptr, const void* dptr, size_t bytes);
+/* asynchronous on `stream` (NULL = the library's stream) */
+int b200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int b200_memset_dev(void* dptr, int byte, size_t bytes, void* stream);
 int b200_sync(void);
 
 /* per-stage device timing of the MSM pipeline (CUDA events on the launching stream) and a count

@@ -430,6 +430,23 @@ int b200_memcpy_d2h(void* hptr, const void* dptr, size_t bytes) {
   CU(cudaStreamSynchronize(g_dev.stream));
   return B200_OK;
 }
+int b200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (bytes == 0) return B200_OK;
+  if (!dst || !src) return fail(B200_E_ARG, "null pointer");
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice,
+                     stream ? (cudaStream_t)stream : g_dev.stream));
+  return B200_OK;
+}
+int b200_memset_dev(void* dptr, int byte, size_t bytes, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (bytes == 0) return B200_OK;
+  if (!dptr) return fail(B200_E_ARG, "null pointer");
+  CU(cudaMemsetAsync(dptr, byte, bytes, stream ? (cudaStream_t)stream : g_dev.stream));
+  return B200_OK;
+}
 int b200_sync(void) {
   int rc = ensure_init();
   if (rc) return rc;

@@ -32,6 +32,8 @@ SIGNATURES = {
     "b200_dev_free": [_P],
     "b200_memcpy_h2d": [_P, _P, c_size_t],
     "b200_memcpy_d2h": [_P, _P, c_size_t],
+    "b200_memcpy_d2d": [_P, _P, c_size_t, _P],
+    "b200_memset_dev": [_P, c_int, c_size_t, _P],
     "b200_sync": [],
     "b200_profile_enable": [c_int],
     "b200_profile_reset": [],

@@ -1,0 +1,472 @@
+"""Host-side mirror of the MicroSpartan (ppsnark) prover up to the batched opening claim
+(src/spartan/ppsnark.rs:1056-1355), with every O(N) step on the device:
+
+  R1CSShapeSparkRepr (::new, ::evaluation_oracles)             ppsnark.rs:113-198, 220-253
+  MemorySumcheckInstance (::compute_oracles, engine)           ppsnark.rs:328-670
+  InnerBatchedSumcheckInstance                                 ppsnark.rs:677-786
+  WitnessBoundSumcheck (masked eq, polys/masked_eq.rs:65-76)   ppsnark.rs:270-325
+  prove_helper (3 engines, 9 claims, one cubic per round)      ppsnark.rs:886-983
+  prove_core = RelaxedR1CSSNARK::prove minus EE::prove         ppsnark.rs:1056-1355
+
+The 16 size-N polynomials of the inner sum-check stay resident in HBM.  Per round the host enqueues
+the nine reductions (2 linear, 2 eq-cubic-3, 2 eq-cubic-2, 1 cubic, 1 eq-quadratic-1, 1 quadratic)
+into ONE result buffer, reads it back once (9 x 96 B), does the O(1) claim derivation / UniPoly /
+transcript work on Python integers exactly as the Rust host would, uploads the challenge once and
+enqueues the 16 binds.  The transcript is passed in (absorb_bytes / squeeze), as in spartan.py.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import fields
+from .native import check, lib
+from .provider import CommitmentKey, _cbuf, _jac_to_affine
+from .spartan import (SC_CUBIC, SC_EQ_CUBIC2, SC_EQ_CUBIC2_M1, SC_EQ_CUBIC3, SC_EQ_CUBIC3_M1, SC_EQ_QUAD1,
+                      SC_EQ_QUAD1_M1, SC_LINEAR, SC_NOUT, SC_QUADRATIC, DeviceVec, EqSumCheckInstance,
+                      SparseMatrix, UniPoly, _sc_eval_dev, update_claim)
+
+
+def to_repr(x: int) -> bytes:
+    return int(x).to_bytes(32, "little")  # canonical little-endian (traits.rs:323-327)
+
+
+class View:
+    """`n` field elements starting `off` elements into a DeviceVec (keeps the allocation alive)."""
+
+    def __init__(self, base: DeviceVec, off: int = 0):
+        self.base = base
+        self.ptr = ctypes.c_void_p(base.ptr.value + 32 * off)
+
+
+def dev_zeros(n: int) -> DeviceVec:
+    v = DeviceVec(32 * n)
+    check(lib().b200_memset_dev(v.ptr, 0, 32 * n, None))
+    return v
+
+
+def dev_copy(src, n: int) -> DeviceVec:
+    v = DeviceVec(32 * n)
+    check(lib().b200_memcpy_d2d(v.ptr, src.ptr, 32 * n, None))
+    return v
+
+
+def dev_padded(src, n_src: int, n: int) -> DeviceVec:
+    """padded() with e = 0 (ppsnark.rs:41-47)."""
+    v = dev_zeros(n)
+    check(lib().b200_memcpy_d2d(v.ptr, src.ptr, 32 * n_src, None))
+    return v
+
+
+def dev_scalar(fid: int, x: int) -> DeviceVec:
+    return DeviceVec.from_bytes(fields.to_mont_bytes(fid, x))
+
+
+def dev_u32(xs) -> DeviceVec:
+    raw = (ctypes.c_uint32 * max(len(xs), 1))(*xs)
+    v = DeviceVec(4 * max(len(xs), 1))
+    check(lib().b200_memcpy_h2d(v.ptr, raw, 4 * len(xs)))
+    return v
+
+
+class RoundSums:
+    """All reductions of one sum-check round in one result buffer, one read-back."""
+
+    def __init__(self, fid: int, cap: int = 16):
+        self.fid, self.out, self.nout = fid, DeviceVec(96 * cap), []
+
+    def add(self, form, A, B, C, length, L=None, R=None, shift=0) -> int:
+        k = len(self.nout)
+        dst = ctypes.c_void_p(self.out.ptr.value + 96 * k)
+        check(lib().b200_sc_eval_dev(self.fid, form, A.ptr, B.ptr if B else None, C.ptr if C else None, length,
+                                     L.ptr if L else None, R.ptr if R else None, shift, dst, None))
+        self.nout.append(SC_NOUT[form])
+        return k
+
+    def fetch(self):
+        raw = self.out.to_bytes(96 * len(self.nout))
+        res = [fields.unpack(self.fid, raw[96 * k:96 * k + 32 * n]) for k, n in enumerate(self.nout)]
+        self.nout = []
+        return res
+
+
+def _bind_all(fid, polys, length, r_dev):
+    for Z in polys:
+        check(lib().b200_bind_top_dev(fid, Z.ptr, length, r_dev.ptr, None))
+
+
+def commit_dev(curve, ck: CommitmentKey, v, n: int):
+    """CE::commit(ck, v, r = 0) of a device-resident vector -> affine (x, y) or None."""
+    out = DeviceVec(96)
+    check(lib().b200_commit_dev(ck.handle, v.ptr, n, None, out.ptr, None))
+    return _jac_to_affine(curve, out.to_bytes(96))
+
+
+def commitment_transcript_bytes(P) -> bytes:
+    """pedersen.rs:103-117: x || y || is_infinity."""
+    if P is None:
+        return to_repr(0) + to_repr(0) + b"\x01"
+    return to_repr(P[0]) + to_repr(P[1]) + b"\x00"
+
+
+# ---------------------------------------------------------------------------------------------
+class SparkRepr:
+    """R1CSShapeSparkRepr::new (ppsnark.rs:113-198); vectors uploaded once, index arrays kept as
+    u32 for the device gathers."""
+
+    def __init__(self, fid: int, A, B, C, num_cons: int, num_vars: int):
+        p = fields.MODULUS[fid]
+        total = len(A) + len(B) + len(C)
+        N = 1
+        while N < max(total, 2 * num_vars, num_cons):
+            N *= 2
+        self.fid, self.N = fid, N
+        row, col = [0] * N, [N - 1] * N
+        for i, (r, c, _) in enumerate(list(A) + list(B) + list(C)):
+            row[i], col[i] = r, c
+        vals = [[0] * N for _ in range(3)]
+        off = 0
+        for k, M in enumerate((A, B, C)):
+            for i, (_, _, v) in enumerate(M):
+                vals[k][off + i] = v % p
+            off += len(M)
+        ts_row, ts_col = [0] * N, [0] * N
+        for a in row:
+            ts_row[a] += 1
+        for a in col:
+            ts_col[a] += 1
+        up = lambda xs: DeviceVec.from_bytes(fields.pack(fid, xs))
+        self.row, self.col, self.ts_row, self.ts_col = up(row), up(col), up(ts_row), up(ts_col)
+        self.val_A, self.val_B, self.val_C = (up(v) for v in vals)
+        self.row_idx, self.col_idx = dev_u32(row), dev_u32(col)
+
+    def evaluation_oracles(self, r_outer_full: list, z, z_len: int):
+        """ppsnark.rs:220-253 -> (mem_row, mem_col, L_row, L_col), all of length N on the device."""
+        fid, N = self.fid, self.N
+        assert (1 << len(r_outer_full)) == N
+        mem_row = DeviceVec(32 * N)
+        check(lib().b200_eq_table_dev(fid, DeviceVec.from_bytes(fields.pack(fid, r_outer_full)).ptr,
+                                      len(r_outer_full), mem_row.ptr, None))
+        mem_col = dev_padded(z, z_len, N)
+        L_row, L_col = DeviceVec(32 * N), DeviceVec(32 * N)
+        check(lib().b200_gather_dev(mem_row.ptr, self.row_idx.ptr, N, L_row.ptr, None))
+        check(lib().b200_gather_dev(mem_col.ptr, self.col_idx.ptr, N, L_col.ptr, None))
+        return mem_row, mem_col, L_row, L_col
+
+
+def memory_compute_oracles(fid, r: int, gamma: int, N: int, mem_row, addr_row, L_row, ts_row, mem_col, addr_col,
+                           L_col, ts_col):
+    """MemorySumcheckInstance::compute_oracles without the commitments (ppsnark.rs:372-455).
+    Returns ([t_inv_row, w_inv_row, t_inv_col, w_inv_col], [t_row, w_row, t_col, w_col]) as Views.
+    Raises ValueError("InternalError") if an inversion meets zero (spartan/mod.rs:98-100)."""
+    g, rr = dev_scalar(fid, gamma), dev_scalar(fid, r)
+    flag = DeviceVec(4)
+    oracles, aux = [], []
+    for mem, addr, L, ts in ((mem_row, addr_row, L_row, ts_row), (mem_col, addr_col, L_col, ts_col)):
+        tw = DeviceVec(64 * N)  # (T + r) || (W + r)
+        check(lib().b200_logup_hash_dev(fid, mem.ptr, None, g.ptr, rr.ptr, N, tw.ptr, None))
+        check(lib().b200_logup_hash_dev(fid, L.ptr, addr.ptr, g.ptr, rr.ptr, N, View(tw, N).ptr, None))
+        inv = DeviceVec(64 * N)
+        check(lib().b200_batch_invert_dev(fid, tw.ptr, 2 * N, inv.ptr, flag.ptr, None))
+        if int.from_bytes(flag.to_bytes(4), "little"):
+            raise ValueError("InternalError")
+        check(lib().b200_vec_mul_dev(fid, inv.ptr, ts.ptr, N, inv.ptr, None))  # TS[i] / (T[i] + r)
+        oracles += [View(inv, 0), View(inv, N)]
+        aux += [View(tw, 0), View(tw, N)]
+    return oracles, aux
+
+
+# ---- the three engines ---------------------------------------------------------------------------
+class MemorySumcheckInstance:
+    def __init__(self, fid, N, polys_oracle, polys_aux, rhos, ts_row, ts_col):
+        self.fid, self.p, self.len = fid, fields.MODULUS[fid], N
+        self.t_inv_row, self.w_inv_row, self.t_inv_col, self.w_inv_col = (dev_copy(v, N) for v in polys_oracle)
+        self.t_row, self.w_row, self.t_col, self.w_col = polys_aux  # consumed (moved in the reference)
+        self.ts_row, self.ts_col = dev_copy(ts_row, N), dev_copy(ts_col, N)
+        self.eq = EqSumCheckInstance(fid, rhos)
+        self.running = [0] * 6
+        self.saved = [[0, 0, 0] for _ in range(6)]
+
+    def initial_claims(self):
+        return [0] * 6
+
+    def size(self):
+        return self.len
+
+    def enqueue(self, sums: RoundSums):
+        L, R, sh = self.eq._tables()
+        n = self.len
+        self._slots = [
+            sums.add(SC_LINEAR, self.t_inv_row, self.w_inv_row, None, n),
+            sums.add(SC_LINEAR, self.t_inv_col, self.w_inv_col, None, n),
+            sums.add(SC_EQ_CUBIC3, self.t_inv_row, self.t_row, self.ts_row, n, L, R, sh),
+            sums.add(SC_EQ_CUBIC2, self.w_inv_row, self.w_row, None, n, L, R, sh),
+            sums.add(SC_EQ_CUBIC3, self.t_inv_col, self.t_col, self.ts_col, n, L, R, sh),
+            sums.add(SC_EQ_CUBIC2, self.w_inv_col, self.w_col, None, n, L, R, sh),
+        ]
+
+    def _derived(self, j, t0, tinf):
+        d = self.eq._derive(t0, tinf, self.running[j], True)
+        if d is not None:
+            return list(d)
+        # tau = 0: third sum (sumcheck.rs:1082-1178)
+        L, R, sh = self.eq._tables()
+        A, B, C, form = {2: (self.t_inv_row, self.t_row, self.ts_row, SC_EQ_CUBIC3_M1),
+                         3: (self.w_inv_row, self.w_row, None, SC_EQ_CUBIC2_M1),
+                         4: (self.t_inv_col, self.t_col, self.ts_col, SC_EQ_CUBIC3_M1),
+                         5: (self.w_inv_col, self.w_col, None, SC_EQ_CUBIC2_M1)}[j]
+        (tm1,) = _sc_eval_dev(self.fid, form, A, B, C, self.len, L, R, sh)
+        e0, slope, em1 = self.eq.eq_tau_0_a_inf[self.eq.round - 1]
+        q, p = self.eq.eval_eq_left, self.p
+        return [e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p]
+
+    def evaluation_points(self, res):
+        s = self._slots
+        self.saved = [[res[s[0]][0], 0, res[s[0]][1]], [res[s[1]][0], 0, res[s[1]][1]]]
+        for j in range(2, 6):
+            self.saved.append(self._derived(j, res[s[j]][0], res[s[j]][1]))
+        return [list(e) for e in self.saved]
+
+    def bound(self, r, r_dev):
+        self.running = [update_claim(self.p, self.running[j], self.saved[j], r) for j in range(6)]
+        _bind_all(self.fid, [self.t_row, self.t_inv_row, self.w_row, self.w_inv_row, self.ts_row, self.t_col,
+                             self.t_inv_col, self.w_col, self.w_inv_col, self.ts_col], self.len, r_dev)
+        self.len //= 2
+        self.eq.bound(r)
+
+    def final_claims(self):
+        g = lambda v: _first(self.fid, v)
+        return [[g(self.t_inv_row), g(self.w_inv_row), g(self.ts_row)],
+                [g(self.t_inv_col), g(self.w_inv_col), g(self.ts_col)]]
+
+
+def _read1(view) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    check(lib().b200_memcpy_d2h(out, view.ptr, 32))
+    return out.raw
+
+
+def _first(fid, v) -> int:
+    return fields.unpack(fid, _read1(v))[0]
+
+
+class InnerBatchedSumcheckInstance:
+    def __init__(self, fid, N, claim, L_row, L_col, val, claim_E, r_outer, E):
+        p = fields.MODULUS[fid]
+        self.fid, self.p, self.len = fid, p, N
+        self.claim, self.claim_E = claim % p, claim_E % p
+        self.L_row, self.L_col, self.val, self.E = dev_copy(L_row, N), dev_copy(L_col, N), val, dev_copy(E, N)
+        self.eq = EqSumCheckInstance(fid, r_outer)
+        self.running_E, self.saved_E = claim_E % p, [0, 0, 0]
+
+    def initial_claims(self):
+        return [self.claim, self.claim_E]
+
+    def size(self):
+        return self.len
+
+    def enqueue(self, sums: RoundSums):
+        L, R, sh = self.eq._tables()
+        self._slots = [sums.add(SC_CUBIC, self.L_row, self.L_col, self.val, self.len),
+                       sums.add(SC_EQ_QUAD1, self.E, None, None, self.len, L, R, sh)]
+
+    def evaluation_points(self, res):
+        e0, bc, einf = res[self._slots[0]]
+        (t0,) = res[self._slots[1]]
+        d = self.eq._derive(t0, 0, self.running_E, False)
+        if d is None:  # tau = 0 (sumcheck.rs:1180-1213)
+            L, R, sh = self.eq._tables()
+            (tm1,) = _sc_eval_dev(self.fid, SC_EQ_QUAD1_M1, self.E, None, None, self.len, L, R, sh)
+            q0, _, qm1 = self.eq.eq_tau_0_a_inf[self.eq.round - 1]
+            q = self.eq.eval_eq_left
+            d = (q0 * q * t0 % self.p, 0, qm1 * q * tm1 % self.p)
+        self.saved_E = list(d)
+        return [[e0, bc, einf], [d[0], 0, d[2]]]
+
+    def bound(self, r, r_dev):
+        self.running_E = update_claim(self.p, self.running_E, self.saved_E, r)
+        _bind_all(self.fid, [self.L_row, self.L_col, self.val, self.E], self.len, r_dev)
+        self.len //= 2
+        self.eq.bound(r)
+
+    def final_claims(self):
+        return [[_first(self.fid, self.L_row), _first(self.fid, self.L_col)], [_first(self.fid, self.E)]]
+
+
+class WitnessBoundSumcheck:
+    def __init__(self, fid, N, tau: list, W_padded, num_vars: int):
+        m = num_vars.bit_length() - 1
+        assert m < N.bit_length() - 1  # ppsnark.rs:288
+        self.fid, self.len = fid, N
+        self.W = dev_copy(W_padded, N)
+        self.masked_eq = DeviceVec(32 * N)
+        check(lib().b200_eq_table_dev(fid, DeviceVec.from_bytes(fields.pack(fid, tau)).ptr, len(tau),
+                                      self.masked_eq.ptr, None))
+        check(lib().b200_memset_dev(self.masked_eq.ptr, 0, 32 << m, None))  # first 2^m entries -> 0
+
+    def initial_claims(self):
+        return [0]
+
+    def size(self):
+        return self.len
+
+    def enqueue(self, sums: RoundSums):
+        self._slot = sums.add(SC_QUADRATIC, self.masked_eq, self.W, None, self.len)
+
+    def evaluation_points(self, res):
+        e0, einf = res[self._slot]
+        return [[e0, 0, einf]]
+
+    def bound(self, r, r_dev):
+        _bind_all(self.fid, [self.W, self.masked_eq], self.len, r_dev)
+        self.len //= 2
+
+    def final_claims(self):
+        return [[_first(self.fid, self.W), _first(self.fid, self.masked_eq)]]
+
+
+def prove_helper(fid, mem, inner, witness, transcript):
+    """RelaxedR1CSSNARK::prove_helper (ppsnark.rs:886-983)."""
+    p = fields.MODULUS[fid]
+    assert mem.size() == inner.size() == witness.size()
+    claims = mem.initial_claims() + inner.initial_claims() + witness.initial_claims()
+    s = transcript.squeeze(b"r")
+    coeffs = [pow(s, i, p) for i in range(len(claims))]
+    e = sum(c * k for c, k in zip(claims, coeffs)) % p
+    rs, polys = [], []
+    sums = RoundSums(fid)
+    for _ in range(mem.size().bit_length() - 1):
+        for eng in (mem, inner, witness):
+            eng.enqueue(sums)
+        res = sums.fetch()
+        evals = mem.evaluation_points(res) + inner.evaluation_points(res) + witness.evaluation_points(res)
+        assert len(evals) == len(claims)
+        c0 = sum(evals[i][0] * coeffs[i] for i in range(len(evals))) % p
+        cb = sum(evals[i][1] * coeffs[i] for i in range(len(evals))) % p
+        ci = sum(evals[i][2] * coeffs[i] for i in range(len(evals))) % p
+        poly = UniPoly.from_evals_deg3(p, [c0, (e - c0) % p, cb, ci])
+        transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+        r = transcript.squeeze(b"c")
+        rs.append(r)
+        r_dev = dev_scalar(fid, r)
+        for eng in (mem, inner, witness):
+            eng.bound(r, r_dev)
+        e = poly.evaluate(r)
+        polys.append(poly.compress())
+    return polys, rs, mem.final_claims(), inner.final_claims(), witness.final_claims()
+
+
+def _prove_cubic3_resident(fid, claim, taus, A, B, C, length, transcript):
+    """SumcheckProof::prove_cubic_with_three_inputs (sumcheck.rs:446-507) on resident vectors."""
+    p = fields.MODULUS[fid]
+    eq = EqSumCheckInstance(fid, taus)
+    rs, polys = [], []
+    for _ in range(len(taus)):
+        e0, lead, em1 = eq.evaluation_points_cubic_with_three_inputs(A, B, C, length, claim)
+        poly = UniPoly.from_evals_deg3(p, [e0, (claim - e0) % p, lead, em1])
+        transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+        r = transcript.squeeze(b"c")
+        rs.append(r)
+        polys.append(poly.compress())
+        claim = poly.evaluate(r)
+        _bind_all(fid, (A, B, C), length, dev_scalar(fid, r))
+        eq.bound(r)
+        length //= 2
+    return polys, rs, [_first(fid, Z) for Z in (A, B, C)]
+
+
+def _mle_eval(fid, Z, ell, r_dev) -> int:
+    out = DeviceVec(32)
+    check(lib().b200_mle_eval_dev(fid, Z.ptr, ell, r_dev.ptr, out.ptr, None))
+    return fields.unpack(fid, out.to_bytes(32))[0]
+
+
+def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: dict, vk_digest: int, transcript):
+    """ppsnark.rs:1056-1355 up to (and excluding) EE::prove.
+
+    S: dict(num_cons, num_vars, A, B, C) with A/B/C `spartan.SparseMatrix` (regular, padded shape).
+    U: dict(comm_W, comm_E (affine or None), u, X: ints);  W: dict(W, E: Montgomery bytes).
+    Returns every proof field plus the batched opening polynomial (DeviceVec) and its value.
+    """
+    fid = curve.scalar_field
+    p = fields.MODULUS[fid]
+    num_cons, num_vars, N = S["num_cons"], S["num_vars"], spark.N
+    tr = transcript
+    tr.absorb_bytes(b"vk", to_repr(vk_digest % p))
+    tr.absorb_bytes(b"U", commitment_transcript_bytes(U["comm_W"]) + commitment_transcript_bytes(U["comm_E"])
+                    + to_repr(U["u"] % p) + b"".join(to_repr(x % p) for x in U["X"]))
+    u_dev = dev_scalar(fid, U["u"])
+    z_len = num_vars + 1 + len(U["X"])
+    z = DeviceVec.from_bytes(W["W"] + fields.pack(fid, [U["u"]] + list(U["X"])))
+    Wd, Ed = DeviceVec.from_bytes(W["W"]), DeviceVec.from_bytes(W["E"])
+    Az, Bz, Cz = (DeviceVec(32 * num_cons) for _ in range(3))
+    for M, out in ((S["A"], Az), (S["B"], Bz), (S["C"], Cz)):
+        check(lib().b200_spmv_dev(M.handle, z.ptr, None, out.ptr, None, None))
+    nro, nri = num_cons.bit_length() - 1, N.bit_length() - 1
+    tau = [tr.squeeze(b"t") for _ in range(nro)]
+    uCz_E = DeviceVec(32 * num_cons)
+    check(lib().b200_axpy_dev(fid, Ed.ptr, Cz.ptr, u_dev.ptr, num_cons, uCz_E.ptr, None))  # E + u*Cz
+    sc_outer, r_outer, claims_outer = _prove_cubic3_resident(fid, 0, tau, Az, Bz, uCz_E, num_cons, tr)
+    eAz, eBz = claims_outer[0], claims_outer[1]
+    eCz = _mle_eval(fid, Cz, nro, DeviceVec.from_bytes(fields.pack(fid, r_outer)))
+    eE_outer = (claims_outer[2] - U["u"] * eCz) % p
+    tr.absorb_bytes(b"e", b"".join(to_repr(x) for x in (eAz, eBz, eCz, eE_outer)))
+    r_pad = [tr.squeeze(b"p") for _ in range(nri - nro)]
+    r_full = r_pad + r_outer
+    factor = 1
+    for x in r_pad:
+        factor = factor * (1 - x) % p
+    E_p, W_p = dev_padded(Ed, num_cons, N), dev_padded(Wd, num_vars, N)
+    mem_row, mem_col, L_row, L_col = spark.evaluation_oracles(r_full, z, z_len)
+    comm_L_row, comm_L_col = commit_dev(curve, ck, L_row, N), commit_dev(curve, ck, L_col, N)
+    tr.absorb_bytes(b"e", commitment_transcript_bytes(comm_L_row) + commitment_transcript_bytes(comm_L_col))
+    c = tr.squeeze(b"c")
+    gamma = tr.squeeze(b"g")
+    r = tr.squeeze(b"r")
+    val = DeviceVec(32 * N)  # val_A + c val_B + c^2 val_C (ppsnark.rs:1183-1188)
+    _rlc_dev(fid, [spark.val_A, spark.val_B, spark.val_C], [1, c, c * c % p], N, val)
+    inner = InnerBatchedSumcheckInstance(fid, N, factor * (eAz + c * eBz + c * c * eCz), L_row, L_col, val,
+                                         factor * eE_outer, r_full, E_p)
+    mem_oracles, mem_aux = memory_compute_oracles(fid, r, gamma, N, mem_row, spark.row, L_row, spark.ts_row,
+                                                  mem_col, spark.col, L_col, spark.ts_col)
+    comm_mem = [commit_dev(curve, ck, v, N) for v in mem_oracles]
+    tr.absorb_bytes(b"l", b"".join(commitment_transcript_bytes(P) for P in comm_mem))
+    rho = [tr.squeeze(b"r") for _ in range(nri)]
+    mem = MemorySumcheckInstance(fid, N, mem_oracles, mem_aux, rho, spark.ts_row, spark.ts_col)
+    wit = WitnessBoundSumcheck(fid, N, r_full, W_p, num_vars)
+    sc_inner, r_inner, c_mem, c_inner, c_wit = prove_helper(fid, mem, inner, wit, tr)
+    ev = {
+        "eval_L_row": c_inner[0][0], "eval_L_col": c_inner[0][1], "eval_E": c_inner[1][0],
+        "eval_t_plus_r_inv_row": c_mem[0][0], "eval_w_plus_r_inv_row": c_mem[0][1], "eval_ts_row": c_mem[0][2],
+        "eval_t_plus_r_inv_col": c_mem[1][0], "eval_w_plus_r_inv_col": c_mem[1][1], "eval_ts_col": c_mem[1][2],
+        "eval_W": c_wit[0][0],
+    }
+    ri_dev = DeviceVec.from_bytes(fields.pack(fid, r_inner))
+    for name, v in (("eval_val_A", spark.val_A), ("eval_val_B", spark.val_B), ("eval_val_C", spark.val_C),
+                    ("eval_row", spark.row), ("eval_col", spark.col)):
+        ev[name] = _mle_eval(fid, v, nri, ri_dev)  # multi_evaluate_with, multilinear.rs:129-180
+    order = ["eval_W", "eval_E", "eval_L_row", "eval_L_col", "eval_val_A", "eval_val_B", "eval_val_C",
+             "eval_t_plus_r_inv_row", "eval_row", "eval_w_plus_r_inv_row", "eval_ts_row",
+             "eval_t_plus_r_inv_col", "eval_col", "eval_w_plus_r_inv_col", "eval_ts_col"]
+    eval_vec = [ev[k] for k in order]
+    poly_vec = [W_p, E_p, L_row, L_col, spark.val_A, spark.val_B, spark.val_C, mem_oracles[0], spark.row,
+                mem_oracles[1], spark.ts_row, mem_oracles[2], spark.col, mem_oracles[3], spark.ts_col]
+    tr.absorb_bytes(b"e", b"".join(to_repr(x) for x in eval_vec))
+    cb = tr.squeeze(b"c")
+    pw = [pow(cb, i, p) for i in range(len(poly_vec))]
+    batched = DeviceVec(32 * N)  # PolyEvalWitness::batch (spartan/mod.rs:232-277)
+    _rlc_dev(fid, poly_vec, pw, N, batched)
+    out = dict(ev)
+    out.update(comm_L_row=comm_L_row, comm_L_col=comm_L_col, comm_mem=comm_mem, sc_outer=sc_outer,
+               r_outer=r_outer, eval_Az_at_r_outer=eAz, eval_Bz_at_r_outer=eBz, eval_Cz_at_r_outer=eCz,
+               eval_E_at_r_outer=eE_outer, sc_inner_batched=sc_inner, r_inner_batched=r_inner,
+               batched_poly=batched, batched_eval=sum(a * b for a, b in zip(pw, eval_vec)) % p)
+    return out
+
+
+def _rlc_dev(fid, polys, coeffs, n, out):
+    k = len(polys)
+    ptrs = (ctypes.c_void_p * k)(*[v.ptr.value for v in polys])
+    lens = (ctypes.c_size_t * k)(*([n] * k))
+    cd = DeviceVec.from_bytes(fields.pack(fid, coeffs))
+    check(lib().b200_rlc_dev(fid, ptrs, lens, k, cd.ptr, n, out.ptr, None))
+    check(lib().b200_sync())  # `cd` and the pointer table must outlive the launch

@@ -4,36 +4,8 @@ checks (ppsnark.rs:1386-1600), and tampering with it must fail."""
 import pytest
 
 from oracle import ppsnark_ref as pr
+from oracle.ppsnark_ref import random_instance
 from oracle.pyref import CURVES, FIELD_MODULUS, SplitMix64
-
-
-def random_instance(p, rng, num_cons, num_vars, num_io, nnz_per_row=2):
-    """Random regular shape + satisfying relaxed witness (E absorbs the slack)."""
-    ncols = num_vars + 1 + num_io
-
-    def mat():
-        out = []
-        for r in range(num_cons):
-            cols = sorted({rng.next() % ncols for _ in range(nnz_per_row)})
-            for c in cols:
-                v = [1, p - 1, 2, rng.field(p)][rng.next() % 4]
-                out.append((r, c, v))
-        return out
-    A, B, C = mat(), mat(), mat()
-    Wv = [rng.field(p) for _ in range(num_vars)]
-    X = [rng.field(p) for _ in range(num_io)]
-    u = rng.field(p)
-    z = Wv + [u] + X
-
-    def mv(M):
-        out = [0] * num_cons
-        for (r, c, v) in M:
-            out[r] = (out[r] + v * z[c]) % p
-        return out
-    Az, Bz, Cz = mv(A), mv(B), mv(C)
-    E = [(a * b - u * c) % p for a, b, c in zip(Az, Bz, Cz)]
-    S = dict(num_cons=num_cons, num_vars=num_vars, A=A, B=B, C=C)
-    return S, dict(W=Wv, E=E), u, X
 
 
 @pytest.mark.parametrize("fid,num_cons,num_vars", [(0, 8, 8), (3, 16, 8), (1, 4, 16)])
