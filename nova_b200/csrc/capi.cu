@@ -112,6 +112,11 @@ struct ck_ctx {
   int m = 4;
   void* tables = nullptr;  // [F][n] affine
   workspace ws;
+  // Keys wide enough for 20-bit windows also carry 17-bit-window tables over their first 2^21
+  // bases: the same key commits vectors of very different lengths (W, E, T, the halving
+  // polynomials of HyperKZG, hyperkzg.rs:1083-1100), and a short MSM should not pay the
+  // 2^19-bucket reduction of the wide tables.
+  std::shared_ptr<ck_ctx> small;
   ~ck_ctx() {
     if (tables) cudaFree(tables);
     ws.release();
@@ -300,6 +305,9 @@ int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n,
   return B200_OK;
 }
 
+constexpr size_t SMALL_KEY_MAX = (size_t)1 << 21;
+constexpr int SMALL_KEY_WINDOW = 17;
+
 int choose_window(size_t n) {
   int lg = 0;
   while (((size_t)1 << lg) < n) lg++;
@@ -345,8 +353,19 @@ int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(g_dev.stream));
+  if (expand && window_bits == 0 && ck->c >= 20) {
+    size_t ns = n < SMALL_KEY_MAX ? n : SMALL_KEY_MAX;
+    int rc = register_key(curve_id, bases, bases_on_device, ns, h, SMALL_KEY_WINDOW, true, ck->small);
+    if (rc) return rc;
+  }
   out = ck;
   return B200_OK;
+}
+
+// the table set an MSM over ck[base_offset .. base_offset + n) runs on
+ck_ctx& route(ck_ctx& ck, size_t base_offset, size_t n) {
+  if (ck.small && base_offset + n <= ck.small->n) return *ck.small;
+  return ck;
 }
 
 template <class Fn>
@@ -587,7 +606,7 @@ int b200_msm(uint64_t handle, size_t base_offset, const void* scalars, size_t n,
   if (base_offset + n > ck->n)
     return fail(B200_E_RANGE, "msm slice [%zu, %zu) exceeds key length %zu", base_offset,
                 base_offset + n, ck->n);
-  return msm_host(*ck, base_offset, scalars, n, out);
+  return msm_host(route(*ck, base_offset, n), base_offset, scalars, n, out);
 }
 
 int b200_commit(uint64_t handle, const void* scalars, size_t n, const void* r, void* out) {
@@ -599,7 +618,7 @@ int b200_commit(uint64_t handle, const void* scalars, size_t n, const void* r, v
   if (n > ck->n)  // pedersen.rs:264 assert!(ck.ck.len() >= v.len())
     return fail(B200_E_RANGE, "commit of %zu scalars exceeds key length %zu", n, ck->n);
   if (r && !ck->has_h) return fail(B200_E_ARG, "key was registered without a blinding generator");
-  return msm_host(*ck, 0, scalars, n, out, r);
+  return msm_host(route(*ck, 0, n), 0, scalars, n, out, r);
 }
 
 int b200_msm_dev(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
@@ -612,10 +631,11 @@ int b200_msm_dev(uint64_t handle, size_t base_offset, const void* d_scalars, siz
   if (base_offset + n > ck->n)
     return fail(B200_E_RANGE, "msm slice [%zu, %zu) exceeds key length %zu", base_offset,
                 base_offset + n, ck->n);
-  std::lock_guard<std::mutex> lk(ck->mu);
-  rc = ensure_workspace(*ck, n ? n : 1, 1);
+  ck_ctx& t = route(*ck, base_offset, n);
+  std::lock_guard<std::mutex> lk(t.mu);
+  rc = ensure_workspace(t, n ? n : 1, 1);
   if (rc) return rc;
-  return enqueue_msm(*ck, base_offset, d_scalars, n, d_out,
+  return enqueue_msm(t, base_offset, d_scalars, n, d_out,
                      stream ? (cudaStream_t)stream : g_dev.stream);
 }
 
@@ -629,15 +649,16 @@ int b200_commit_dev(uint64_t handle, const void* d_scalars, size_t n, const void
   if (n > ck->n) return fail(B200_E_RANGE, "commit of %zu scalars exceeds key length %zu", n, ck->n);
   if (d_blind_or_null && !ck->has_h)
     return fail(B200_E_ARG, "key was registered without a blinding generator");
-  std::lock_guard<std::mutex> lk(ck->mu);
-  rc = ensure_workspace(*ck, n + 1, 1);
+  ck_ctx& t = route(*ck, 0, n);
+  std::lock_guard<std::mutex> lk(t.mu);
+  rc = ensure_workspace(t, n + 1, 1);
   if (rc) return rc;
   cudaStream_t s = stream ? (cudaStream_t)stream : g_dev.stream;
-  if (!d_blind_or_null) return enqueue_msm(*ck, 0, d_scalars, n, d_out, s);
+  if (!d_blind_or_null) return enqueue_msm(t, 0, d_scalars, n, d_out, s);
   // the blinding scalar must follow the vector in one buffer: stage both in the workspace
-  if (n) CU(cudaMemcpyAsync(ck->ws.scalars, d_scalars, n * 32, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync((char*)ck->ws.scalars + n * 32, d_blind_or_null, 32, cudaMemcpyDeviceToDevice, s));
-  return enqueue_msm(*ck, 0, ck->ws.scalars, n + 1, d_out, s, 0, true);
+  if (n) CU(cudaMemcpyAsync(t.ws.scalars, d_scalars, n * 32, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync((char*)t.ws.scalars + n * 32, d_blind_or_null, 32, cudaMemcpyDeviceToDevice, s));
+  return enqueue_msm(t, 0, t.ws.scalars, n + 1, d_out, s, 0, true);
 }
 
 int b200_msm_batch(uint64_t handle, const void* const* scalars, const size_t* lens, size_t k,
@@ -655,14 +676,21 @@ int b200_msm_batch(uint64_t handle, const void* const* scalars, const size_t* le
     if (lens[j] && !scalars[j]) return fail(B200_E_ARG, "null scalar vector %zu", j);
     if (lens[j] > nmax) nmax = lens[j];
   }
-  std::lock_guard<std::mutex> lk(ck->mu);
+  std::lock_guard<std::mutex> lk(ck->mu);  // lock order: wide tables, then (per vector) narrow
   rc = ensure_workspace(*ck, nmax, k);
   if (rc) return rc;
   cudaStream_t s = g_dev.stream;
   for (size_t j = 0; j < k; j++) {
+    ck_ctx& t = route(*ck, 0, lens[j]);
+    std::unique_lock<std::mutex> lt;
+    if (&t != ck.get()) {
+      lt = std::unique_lock<std::mutex>(t.mu);
+      rc = ensure_workspace(t, lens[j] ? lens[j] : 1, 1);
+      if (rc) return rc;
+    }
     if (lens[j])
-      CU(cudaMemcpyAsync(ck->ws.scalars, scalars[j], lens[j] * 32, cudaMemcpyHostToDevice, s));
-    rc = enqueue_msm(*ck, 0, ck->ws.scalars, lens[j], (char*)ck->ws.d_out + 96 * j, s);
+      CU(cudaMemcpyAsync(t.ws.scalars, scalars[j], lens[j] * 32, cudaMemcpyHostToDevice, s));
+    rc = enqueue_msm(t, 0, t.ws.scalars, lens[j], (char*)ck->ws.d_out + 96 * j, s);
     if (rc) return rc;
   }
   CU(cudaMemcpyAsync(ck->ws.h_out, ck->ws.d_out, 96 * k, cudaMemcpyDeviceToHost, s));
@@ -686,16 +714,17 @@ int b200_msm_small(uint64_t handle, size_t base_offset, const void* scalars, int
                 base_offset + n, ck->n);
   // max_bits only selects the algorithm in the reference (msm.rs:487-502); the digit stream
   // below skips zero windows, so every width takes the same path here.
-  std::lock_guard<std::mutex> lk(ck->mu);
-  rc = ensure_workspace(*ck, n ? n : 1, 1);
+  ck_ctx& t = route(*ck, base_offset, n);
+  std::lock_guard<std::mutex> lk(t.mu);
+  rc = ensure_workspace(t, n ? n : 1, 1);
   if (rc) return rc;
   cudaStream_t s = g_dev.stream;
-  if (n) CU(cudaMemcpyAsync(ck->ws.scalars, scalars, n * elem_bytes, cudaMemcpyHostToDevice, s));
-  rc = enqueue_msm(*ck, base_offset, ck->ws.scalars, n, ck->ws.d_out, s, elem_bytes);
+  if (n) CU(cudaMemcpyAsync(t.ws.scalars, scalars, n * elem_bytes, cudaMemcpyHostToDevice, s));
+  rc = enqueue_msm(t, base_offset, t.ws.scalars, n, t.ws.d_out, s, elem_bytes);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ck->ws.h_out, ck->ws.d_out, 96, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(t.ws.h_out, t.ws.d_out, 96, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  memcpy(out, ck->ws.h_out, 96);
+  memcpy(out, t.ws.h_out, 96);
   return B200_OK;
 }
 
@@ -745,7 +774,7 @@ int b200_msm_adhoc(int curve_id, const void* bases, const void* scalars, size_t 
   std::shared_ptr<ck_ctx> ck;
   rc = register_key(curve_id, bases, false, n, nullptr, 0, /*expand=*/false, ck);
   if (rc) return rc;
-  return msm_host(*ck, 0, scalars, n, out);
+  return msm_host(route(*ck, 0, n), 0, scalars, n, out);
 }
 
 // ---- field vectors ------------------------------------------------------------------------------

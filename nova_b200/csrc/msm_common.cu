@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(256) k_digits_small(const void* __restrict__ s
                                                       uint32_t B, int32_t* __restrict__ digits,
                                                       uint32_t* __restrict__ counts) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t v64;
-  switch (elem_bytes) {
+  const bool live = i < n;  // no early exit: the whole warp takes part in count_key
+  uint64_t v64 = 0;
+  if (live) switch (elem_bytes) {
     case 1: v64 = ((const uint8_t*)scalars)[i]; break;
     case 2: v64 = ((const uint16_t*)scalars)[i]; break;
     case 4: v64 = ((const uint32_t*)scalars)[i]; break;
@@ -138,11 +138,13 @@ __global__ void __launch_bounds__(256) k_digits_small(const void* __restrict__ s
       dgt = (int32_t)v;
       carry = 0;
     }
-    digits[(size_t)w * n + i] = dgt;
+    if (live) digits[(size_t)w * n + i] = dgt;
+    uint32_t key = NO_KEY;
     if (dgt != 0) {
       uint32_t mag = dgt < 0 ? (uint32_t)(-dgt) : (uint32_t)dgt;
-      atomicAdd(&counts[(uint32_t)(w % G) * B + (mag - 1)], 1u);
+      key = (uint32_t)(w % G) * B + (mag - 1);
     }
+    count_key(counts, key);
   }
 }
 
@@ -156,16 +158,22 @@ __global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ dig
                                                  uint64_t* __restrict__ entries) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int w = blockIdx.y;
-  if (i >= n) return;
-  int32_t dgt = digits[(size_t)w * n + i];
-  if (dgt == 0) return;
+  int32_t dgt = i < n ? digits[(size_t)w * n + i] : 0;  // no early exit (warp-wide match below)
   uint32_t sign = dgt < 0 ? 1u : 0u;
   uint32_t mag = sign ? (uint32_t)(-dgt) : (uint32_t)dgt;
-  uint32_t key = (uint32_t)(w % G) * B + (mag - 1);
+  uint32_t key = dgt != 0 ? (uint32_t)(w % G) * B + (mag - 1) : NO_KEY;
+  // warp-aggregated slot reservation: one atomic per distinct key per warp, lanes take
+  // consecutive slots by their rank inside the group (see count_key)
+  unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+  if (key == NO_KEY) return;
+  unsigned lane = threadIdx.x & 31u, leader = (unsigned)(__ffs(peers) - 1);
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   // the blinding scalar r rides along as one more (scalar, base) pair whose base is h
   size_t bi = (i == blind_i) ? h_index : base_offset + i;
   uint32_t idx = (uint32_t)((size_t)(w / G) * n_ck + bi);
-  uint32_t pos = atomicAdd(&cursor[key], 1u);
   entries[pos] = ((uint64_t)key << 32) | ((uint64_t)sign << 31) | idx;
 }
 

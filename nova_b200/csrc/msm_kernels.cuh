@@ -62,14 +62,26 @@ struct msm_plan {
 // ------------------------------------------------------------------------------------------
 // digits + histogram   (templated on the SCALAR field)
 // ------------------------------------------------------------------------------------------
+// Warp-aggregated bucket counting: lanes holding the same key elect one leader that adds the
+// group's size.  For uniform scalars every lane is its own group (one MATCH.ANY extra); for
+// witness-like vectors (bits, padding, one value repeated a million times) it divides the number
+// of atomics on the hot counters by up to 32.  `key` = NO_KEY for lanes without an entry; all 32
+// lanes of the warp must call.
+constexpr uint32_t NO_KEY = 0xFFFFFFFFu;
+__device__ __forceinline__ void count_key(uint32_t* counts, uint32_t key) {
+  unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+  if (key != NO_KEY && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1))
+    atomicAdd(&counts[key], (uint32_t)__popc(peers));
+}
+
 template <class S>
 __global__ void __launch_bounds__(256) k_digits(const void* __restrict__ scalars, size_t n, int c,
                                                 int W, int G, uint32_t B,
                                                 int32_t* __restrict__ digits,
                                                 uint32_t* __restrict__ counts) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  fe_t s = fe_from_mont<S>(fe_load(scalars, i));
+  const bool live = i < n;  // no early exit: the whole warp takes part in count_key
+  fe_t s = live ? fe_from_mont<S>(fe_load(scalars, i)) : fe_zero<S>();
   // sign fold: use p - s when that is the smaller integer (msm.rs:1-8 "signed scalar
   // decomposition"); small negative witness values then cost one bucket add, not W.
   uint32_t p[8], t[8];
@@ -108,12 +120,13 @@ __global__ void __launch_bounds__(256) k_digits(const void* __restrict__ scalars
       carry = 0;
     }
     if (neg) dgt = -dgt;
-    digits[(size_t)w * n + i] = dgt;
+    if (live) digits[(size_t)w * n + i] = dgt;
+    uint32_t key = NO_KEY;
     if (dgt != 0) {
       uint32_t mag = dgt < 0 ? (uint32_t)(-dgt) : (uint32_t)dgt;
-      uint32_t key = (uint32_t)(w % G) * B + (mag - 1);
-      atomicAdd(&counts[key], 1u);
+      key = (uint32_t)(w % G) * B + (mag - 1);
     }
+    count_key(counts, key);
   }
 }
 

@@ -52,7 +52,7 @@ struct field_ops {
   void (*rlc)(cudaStream_t, const void* const* polys, const size_t* lens, int k, const void* coeffs,
               size_t n, void* out);
   void (*kzg_fold)(cudaStream_t, const void* p, const void* x, size_t half, void* out);
-  // evals[q] = f(us[q]), q < nu <= 3, coalesced strided Horner; scratch >= SC_MAX_BLOCKS*3*32 B
+  // evals[q] = f(us[q]), q < nu <= 3, coalesced strided Horner; scratch >= POLY_EVAL_SCRATCH_ELEMS*32 B
   void (*poly_eval)(cudaStream_t, const void* f, size_t n, const void* us, int nu, void* scratch,
                     void* evals);
   // quotient f / (X - u) (n-1 coefficients); scratch >= poly_div_scratch_elems(n) * 32 B
@@ -66,6 +66,7 @@ struct field_ops {
                  void* out);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
+constexpr size_t POLY_EVAL_SCRATCH_ELEMS = (size_t)3 * (1 + SC_MAX_BLOCKS + 256) + (size_t)3 * SC_MAX_BLOCKS;
 constexpr int POLY_CHUNK_HOST = 64;  // must equal POLY_CHUNK in poly_kernels.cuh
 inline size_t poly_div_scratch_elems(size_t n) {
   size_t t1 = (n + POLY_CHUNK_HOST - 1) / POLY_CHUNK_HOST, t2 = (t1 + POLY_CHUNK_HOST - 1) / POLY_CHUNK_HOST;

@@ -227,8 +227,12 @@ struct ops_impl {
                           void* evals) {
     size_t need = (n + 255) / 256;
     int grid = (int)(need < (size_t)SC_MAX_BLOCKS ? (need ? need : 1) : SC_MAX_BLOCKS);
-    k_poly_eval_strided<F, NU><<<grid, 256, 0, s>>>(f, n, us, scratch);
-    k_form_final<F, NU><<<1, 256, 0, s>>>(scratch, grid, evals);
+    void* pw = scratch;                                                     // NU x (1 + grid + 256)
+    void* partials = (char*)scratch + (size_t)3 * (1 + SC_MAX_BLOCKS + 256) * 32;  // grid x NU
+    int np = NU * (1 + grid + 256);
+    k_poly_eval_powers<F><<<(np + 127) / 128, 128, 0, s>>>(us, NU, grid, (uint64_t)grid * 256, pw);
+    k_poly_eval_strided<F, NU><<<grid, 256, 0, s>>>(f, n, pw, partials);
+    k_form_final<F, NU><<<1, 256, 0, s>>>(partials, grid, evals);
   }
   static void poly_eval(cudaStream_t s, const void* f, size_t n, const void* us, int nu, void* scratch,
                         void* evals) {

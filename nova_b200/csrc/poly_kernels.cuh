@@ -304,19 +304,36 @@ NOVA_D fe_t fe_pow_u64(fe_t base, uint64_t e) {
 // and evaluates  A_t(y) = sum_k f[t + kT] y^k  with y = u^T by Horner (high k first); then
 //   f(u) = sum_t u^t A_t(u^T).   (hyperkzg.rs:1011-1019 computes the same value serially.)
 // Every coefficient is loaded once for all NU points; partials[blockIdx][q] feed k_form_final.
+//
+// The powers come from one small launch (k_poly_eval_powers) instead of two square-and-multiply
+// ladders in every thread (which cost more than the Horner steps themselves once each thread owns
+// only a few dozen coefficients, and ~180 dependent products of latency for short polynomials):
+//   pw[q][0] = u_q^T,   pw[q][1 + b] = u_q^(256 b) for b < grid,   pw[q][1 + grid + j] = u_q^j, j < 256
+// so u^t = pw[1 + blockIdx] * pw[1 + grid + threadIdx] is one product.
+template <class F>
+__global__ void __launch_bounds__(128) k_poly_eval_powers(const void* __restrict__ us, int nu,
+                                                          int grid, uint64_t T,
+                                                          void* __restrict__ pw) {
+  const int per = 1 + grid + 256;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nu * per) return;
+  int q = idx / per, j = idx % per;
+  uint64_t e = j == 0 ? T : (j <= grid ? (uint64_t)256 * (uint64_t)(j - 1) : (uint64_t)(j - 1 - grid));
+  fe_store(pw, (size_t)idx, fe_pow_u64<F>(fe_load(us, q), e));
+}
+
 template <class F, int NU>
 __global__ void __launch_bounds__(256) k_poly_eval_strided(const void* __restrict__ f, size_t n,
-                                                           const void* __restrict__ us,
+                                                           const void* __restrict__ pw,
                                                            void* __restrict__ partials) {
   __shared__ fe_t sm[8 * NU];
   const size_t T = (size_t)gridDim.x * blockDim.x;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  fe_t acc[NU], y[NU], ut[NU];
+  const size_t per = 1 + gridDim.x + 256;
+  fe_t acc[NU], y[NU];
 #pragma unroll
   for (int q = 0; q < NU; q++) {
-    fe_t u = fe_load(us, q);
-    y[q] = fe_pow_u64<F>(u, T);
-    ut[q] = fe_pow_u64<F>(u, t);
+    y[q] = fe_load(pw, q * per);
     acc[q] = fe_zero<F>();
   }
   if (t < n) {
@@ -326,9 +343,13 @@ __global__ void __launch_bounds__(256) k_poly_eval_strided(const void* __restric
 #pragma unroll
       for (int q = 0; q < NU; q++) acc[q] = fe_add<F>(fe_mul<F>(acc[q], y[q]), c);
     }
-  }
 #pragma unroll
-  for (int q = 0; q < NU; q++) acc[q] = fe_mul<F>(acc[q], ut[q]);
+    for (int q = 0; q < NU; q++) {
+      fe_t ut = fe_mul<F>(fe_load(pw, q * per + 1 + blockIdx.x),
+                          fe_load(pw, q * per + 1 + gridDim.x + threadIdx.x));
+      acc[q] = fe_mul<F>(acc[q], ut);
+    }
+  }
   block_sum<F, NU>(acc, sm);
   if (threadIdx.x == 0)
 #pragma unroll

@@ -61,7 +61,33 @@ def dev_scalar(fid: int, x: int) -> DeviceVec:
     return DeviceVec.from_bytes(fields.to_mont_bytes(fid, x))
 
 
+def dev_from_u64(fid: int, xs) -> DeviceVec:
+    """Small non-negative integers (numpy array / list of u64) -> Montgomery field vector, converted
+    on the device: canonical rows [x, 0, 0, 0] are multiplied by R^2 (axpy with a = 0)."""
+    import numpy as np
+    a = np.zeros((len(xs), 4), dtype=np.uint64)
+    a[:, 0] = np.asarray(xs, dtype=np.uint64)
+    n = len(xs)
+    raw = DeviceVec(32 * n)
+    check(lib().b200_memcpy_h2d(raw.ptr, a.ctypes.data_as(ctypes.c_void_p), 32 * n))
+    p = fields.MODULUS[fid]
+    r2 = DeviceVec.from_bytes((fields.R * fields.R % p).to_bytes(32, "little"))
+    zero = dev_zeros(n)
+    out = DeviceVec(32 * n)
+    check(lib().b200_axpy_dev(fid, zero.ptr, raw.ptr, r2.ptr, n, out.ptr, None))
+    check(lib().b200_sync())
+    return out
+
+
+def _as_dev(x) -> DeviceVec:
+    return x if hasattr(x, "ptr") else DeviceVec.from_bytes(x)
+
+
 def dev_u32(xs) -> DeviceVec:
+    if hasattr(xs, "ctypes"):  # numpy uint32 array
+        v = DeviceVec(4 * max(len(xs), 1))
+        check(lib().b200_memcpy_h2d(v.ptr, xs.ctypes.data_as(ctypes.c_void_p), 4 * len(xs)))
+        return v
     raw = (ctypes.c_uint32 * max(len(xs), 1))(*xs)
     v = DeviceVec(4 * max(len(xs), 1))
     check(lib().b200_memcpy_h2d(v.ptr, raw, 4 * len(xs)))
@@ -138,6 +164,36 @@ class SparkRepr:
         self.row, self.col, self.ts_row, self.ts_col = up(row), up(col), up(ts_row), up(ts_col)
         self.val_A, self.val_B, self.val_C = (up(v) for v in vals)
         self.row_idx, self.col_idx = dev_u32(row), dev_u32(col)
+
+    @classmethod
+    def from_numpy(cls, fid: int, rows, cols, vals_mont, num_cons: int, num_vars: int):
+        """Same representation built with numpy for large synthetic shapes: rows/cols are uint32
+        arrays over the concatenated entries of A, B, C; vals_mont = three (nnz_k, 4) uint64 arrays
+        of Montgomery coefficients."""
+        import numpy as np
+        self = cls.__new__(cls)
+        total = len(rows)
+        N = 1
+        while N < max(total, 2 * num_vars, num_cons):
+            N *= 2
+        self.fid, self.N = fid, N
+        row = np.zeros(N, dtype=np.uint32)
+        col = np.full(N, N - 1, dtype=np.uint32)
+        row[:total], col[:total] = rows, cols
+        self.row, self.col = dev_from_u64(fid, row), dev_from_u64(fid, col)
+        self.ts_row = dev_from_u64(fid, np.bincount(row, minlength=N))
+        self.ts_col = dev_from_u64(fid, np.bincount(col, minlength=N))
+        off, vs = 0, []
+        for v in vals_mont:
+            buf = np.zeros((N, 4), dtype=np.uint64)
+            buf[off:off + len(v)] = v
+            off += len(v)
+            d = DeviceVec(32 * N)
+            check(lib().b200_memcpy_h2d(d.ptr, buf.ctypes.data_as(ctypes.c_void_p), 32 * N))
+            vs.append(d)
+        self.val_A, self.val_B, self.val_C = vs
+        self.row_idx, self.col_idx = dev_u32(row), dev_u32(col)
+        return self
 
     def evaluation_oracles(self, r_outer_full: list, z, z_len: int):
         """ppsnark.rs:220-253 -> (mem_row, mem_col, L_row, L_col), all of length N on the device."""
@@ -380,13 +436,25 @@ def _mle_eval(fid, Z, ell, r_dev) -> int:
     return fields.unpack(fid, out.to_bytes(32))[0]
 
 
-def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: dict, vk_digest: int, transcript):
+def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: dict, vk_digest: int, transcript,
+               timings: dict | None = None):
     """ppsnark.rs:1056-1355 up to (and excluding) EE::prove.
 
     S: dict(num_cons, num_vars, A, B, C) with A/B/C `spartan.SparseMatrix` (regular, padded shape).
-    U: dict(comm_W, comm_E (affine or None), u, X: ints);  W: dict(W, E: Montgomery bytes).
+    U: dict(comm_W, comm_E (affine or None), u, X: ints);  W: dict(W, E: Montgomery bytes or
+    DeviceVec).  `timings`, if given, receives wall-clock seconds per phase (device synchronised
+    at the phase boundaries).
     Returns every proof field plus the batched opening polynomial (DeviceVec) and its value.
     """
+    import time
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if timings is not None:
+            check(lib().b200_sync())
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
     fid = curve.scalar_field
     p = fields.MODULUS[fid]
     num_cons, num_vars, N = S["num_cons"], S["num_vars"], spark.N
@@ -396,8 +464,11 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
                     + to_repr(U["u"] % p) + b"".join(to_repr(x % p) for x in U["X"]))
     u_dev = dev_scalar(fid, U["u"])
     z_len = num_vars + 1 + len(U["X"])
-    z = DeviceVec.from_bytes(W["W"] + fields.pack(fid, [U["u"]] + list(U["X"])))
-    Wd, Ed = DeviceVec.from_bytes(W["W"]), DeviceVec.from_bytes(W["E"])
+    Wd, Ed = _as_dev(W["W"]), _as_dev(W["E"])
+    z = DeviceVec(32 * z_len)
+    check(lib().b200_memcpy_d2d(z.ptr, Wd.ptr, 32 * num_vars, None))
+    check(lib().b200_memcpy_h2d(View(z, num_vars).ptr, _cbuf(fields.pack(fid, [U["u"]] + list(U["X"]))),
+                                32 * (1 + len(U["X"]))))
     Az, Bz, Cz = (DeviceVec(32 * num_cons) for _ in range(3))
     for M, out in ((S["A"], Az), (S["B"], Bz), (S["C"], Cz)):
         check(lib().b200_spmv_dev(M.handle, z.ptr, None, out.ptr, None, None))
@@ -405,11 +476,13 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
     tau = [tr.squeeze(b"t") for _ in range(nro)]
     uCz_E = DeviceVec(32 * num_cons)
     check(lib().b200_axpy_dev(fid, Ed.ptr, Cz.ptr, u_dev.ptr, num_cons, uCz_E.ptr, None))  # E + u*Cz
+    mark("spmv")
     sc_outer, r_outer, claims_outer = _prove_cubic3_resident(fid, 0, tau, Az, Bz, uCz_E, num_cons, tr)
     eAz, eBz = claims_outer[0], claims_outer[1]
     eCz = _mle_eval(fid, Cz, nro, DeviceVec.from_bytes(fields.pack(fid, r_outer)))
     eE_outer = (claims_outer[2] - U["u"] * eCz) % p
     tr.absorb_bytes(b"e", b"".join(to_repr(x) for x in (eAz, eBz, eCz, eE_outer)))
+    mark("outer_sumcheck")
     r_pad = [tr.squeeze(b"p") for _ in range(nri - nro)]
     r_full = r_pad + r_outer
     factor = 1
@@ -417,7 +490,9 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
         factor = factor * (1 - x) % p
     E_p, W_p = dev_padded(Ed, num_cons, N), dev_padded(Wd, num_vars, N)
     mem_row, mem_col, L_row, L_col = spark.evaluation_oracles(r_full, z, z_len)
+    mark("evaluation_oracles")
     comm_L_row, comm_L_col = commit_dev(curve, ck, L_row, N), commit_dev(curve, ck, L_col, N)
+    mark("commit_L")
     tr.absorb_bytes(b"e", commitment_transcript_bytes(comm_L_row) + commitment_transcript_bytes(comm_L_col))
     c = tr.squeeze(b"c")
     gamma = tr.squeeze(b"g")
@@ -428,12 +503,16 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
                                          factor * eE_outer, r_full, E_p)
     mem_oracles, mem_aux = memory_compute_oracles(fid, r, gamma, N, mem_row, spark.row, L_row, spark.ts_row,
                                                   mem_col, spark.col, L_col, spark.ts_col)
+    mark("memory_oracles")
     comm_mem = [commit_dev(curve, ck, v, N) for v in mem_oracles]
+    mark("commit_mem")
     tr.absorb_bytes(b"l", b"".join(commitment_transcript_bytes(P) for P in comm_mem))
     rho = [tr.squeeze(b"r") for _ in range(nri)]
     mem = MemorySumcheckInstance(fid, N, mem_oracles, mem_aux, rho, spark.ts_row, spark.ts_col)
     wit = WitnessBoundSumcheck(fid, N, r_full, W_p, num_vars)
+    mark("engines_setup")
     sc_inner, r_inner, c_mem, c_inner, c_wit = prove_helper(fid, mem, inner, wit, tr)
+    mark("inner_sumcheck")
     ev = {
         "eval_L_row": c_inner[0][0], "eval_L_col": c_inner[0][1], "eval_E": c_inner[1][0],
         "eval_t_plus_r_inv_row": c_mem[0][0], "eval_w_plus_r_inv_row": c_mem[0][1], "eval_ts_row": c_mem[0][2],
@@ -455,6 +534,7 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
     pw = [pow(cb, i, p) for i in range(len(poly_vec))]
     batched = DeviceVec(32 * N)  # PolyEvalWitness::batch (spartan/mod.rs:232-277)
     _rlc_dev(fid, poly_vec, pw, N, batched)
+    mark("final_evals_rlc")
     out = dict(ev)
     out.update(comm_L_row=comm_L_row, comm_L_col=comm_L_col, comm_mem=comm_mem, sc_outer=sc_outer,
                r_outer=r_outer, eval_Az_at_r_outer=eAz, eval_Bz_at_r_outer=eBz, eval_Cz_at_r_outer=eCz,

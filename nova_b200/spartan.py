@@ -22,7 +22,7 @@ import ctypes
 
 from . import fields
 from .native import B200Error, c_size_t, c_u64, check, lib
-from .provider import CommitmentKey, DlogGroup, _cbuf
+from .provider import CommitmentKey, Curve, DlogGroup, _cbuf, _jac_to_affine
 
 (SC_QUAD_PROD, SC_LINEAR, SC_QUADRATIC, SC_CUBIC, SC_EQ_CUBIC3, SC_EQ_CUBIC2, SC_EQ_QUAD1, SC_EQ_CUBIC3_M1,
  SC_EQ_CUBIC2_M1, SC_EQ_QUAD1_M1, SC_DOT_EQ) = range(11)
@@ -428,28 +428,75 @@ class SumcheckProof:
 # ---------------------------------------------------------------------------------------------
 # HyperKZG prover core (hyperkzg.rs:1076-1116 with the transcript challenges r, q given)
 # ---------------------------------------------------------------------------------------------
+def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r: int, q: int,
+                            timings: dict | None = None):
+    """The same on a polynomial that is already in HBM: folds, commitments, the 3-point
+    evaluations, the batch polynomial and the three quotients never leave the device; the host
+    receives ell-1 + 3 points and 3*ell scalars.  Returns (com, v, w, polys) with `polys` the
+    resident fold chain.  `timings` (optional) receives seconds per phase."""
+    import time
+    fid = Curve(curve).scalar_field
+    p = fields.MODULUS[fid]
+    ell = len(x)
+    n = 1 << ell
+    L = lib()
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if timings is not None:
+            check(L.b200_sync())
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
+    polys, lens = [P], [n]
+    for i in range(ell - 1):  # Phase 1: fold (hyperkzg.rs:1083-1095)
+        xi = DeviceVec.from_bytes(fields.to_mont_bytes(fid, x[ell - i - 1]))
+        nxt = DeviceVec(16 * lens[i])
+        check(L.b200_kzg_fold_dev(fid, polys[i].ptr, lens[i], xi.ptr, nxt.ptr, None))
+        polys.append(nxt)
+        lens.append(lens[i] // 2)
+    mark("fold")
+    pts = DeviceVec(96 * (ell + 2))
+    for i in range(1, ell):  # :1099-1100 batch_commit(polys[1..])
+        check(L.b200_commit_dev(ck.handle, polys[i].ptr, lens[i], None, ctypes.c_void_p(pts.ptr.value + 96 * (i - 1)), None))
+    raw = pts.to_bytes(96 * (ell - 1))
+    com = [_jac_to_affine(Curve(curve), raw[96 * j:96 * j + 96]) for j in range(ell - 1)]
+    mark("commit_folds")
+    u = [r % p, (-r) % p, r * r % p]  # :1105-1106
+    us = DeviceVec.from_bytes(fields.pack(fid, u))
+    ev = DeviceVec(96 * ell)
+    for i in range(ell):  # :1048-1056
+        check(L.b200_poly_eval_dev(fid, polys[i].ptr, lens[i], us.ptr, 3, ctypes.c_void_p(ev.ptr.value + 96 * i), None))
+    evb = ev.to_bytes(96 * ell)
+    v = [fields.unpack(fid, evb[96 * i:96 * i + 96]) for i in range(ell)]
+    mark("evals")
+    assert ell <= 32, "rlc of more than 32 polynomials"
+    qd = DeviceVec.from_bytes(fields.pack(fid, [pow(q, k, p) for k in range(ell)]))  # batch_challenge_powers
+    ptrs = (ctypes.c_void_p * ell)(*[v_.ptr.value for v_ in polys])
+    lns = (c_size_t * ell)(*lens)
+    Bpoly = DeviceVec(32 * n)
+    check(L.b200_rlc_dev(fid, ptrs, lns, ell, qd.ptr, n, Bpoly.ptr, None))  # :1028-1040
+    mark("batch_poly")
+    hs = []
+    for t, ut in enumerate(u):  # :1062-1065: w_t = commit(B / (X - u_t))
+        ud = DeviceVec.from_bytes(fields.to_mont_bytes(fid, ut))
+        h = DeviceVec(32 * max(n - 1, 1))
+        check(L.b200_poly_div_dev(fid, Bpoly.ptr, n, ud.ptr, h.ptr, None))
+        hs.append((h, ud))
+    mark("quotients")
+    for t, (h, _) in enumerate(hs):
+        check(L.b200_commit_dev(ck.handle, h.ptr, n - 1, None, ctypes.c_void_p(pts.ptr.value + 96 * (ell - 1 + t)), None))
+    raw = pts.to_bytes(96 * (ell + 2))
+    w = [_jac_to_affine(Curve(curve), raw[96 * (ell - 1 + t):96 * (ell + t)]) for t in range(3)]
+    mark("commit_quotients")
+    return com, v, w, polys
+
+
 def hyperkzg_prove_core(curve, ck: CommitmentKey, hat_P: bytes, x: list, r: int, q: int):
     """Returns (com[ell-1], v[ell][3], w[3]) for challenges r (evaluation points r, -r, r^2) and q
     (batching).  `x` is the evaluation point as integers."""
-    group = DlogGroup(curve)
-    fid = group.curve.scalar_field
-    p = fields.MODULUS[fid]
-    ell = len(x)
-    n = len(hat_P) // 32
-    assert n == 1 << ell  # hyperkzg.rs:1078
-    polys = [hat_P]
-    for i in range(ell - 1):  # Phase 1: fold (hyperkzg.rs:1083-1095)
-        polys.append(kzg_fold(fid, polys[i], fields.to_mont_bytes(fid, x[ell - i - 1])))
-    com = group.batch_vartime_multiscalar_mul(polys[1:], ck)  # :1099-1100
-    u = [r % p, (-r) % p, r * r % p]  # :1105-1106
-    us = fields.pack(fid, u)
-    v = [fields.unpack(fid, poly_eval(fid, f, us)) for f in polys]  # :1048-1056
-    qp = [pow(q, k, p) for k in range(len(polys))]  # batch_challenge_powers
-    Bpoly = rlc(fid, polys, fields.pack(fid, qp), n)  # :1028-1040
-    w = []
-    for ut in u:  # :1062-1065: w_t = commit(B / (X - u_t))
-        h = poly_div(fid, Bpoly, fields.to_mont_bytes(fid, ut))
-        w.append(group.vartime_multiscalar_mul(h, ck))
+    assert len(hat_P) // 32 == 1 << len(x)  # hyperkzg.rs:1078
+    com, v, w, _ = hyperkzg_prove_resident(curve, ck, DeviceVec.from_bytes(hat_P), x, r, q)
     return com, v, w
 
 

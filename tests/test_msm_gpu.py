@@ -219,3 +219,37 @@ def test_config4_size_2p22_closed_form(b200, oracle):
     lo = g.vartime_multiscalar_mul(sc[:32 * half], ck)
     hi = g.vartime_multiscalar_mul(bytes(32 * half) + sc[32 * half:], ck)
     assert c.add(lo, hi) == got
+
+
+def test_short_vectors_on_a_wide_key(b200, oracle):
+    """A key wide enough for 20-bit windows (n >= 2^22) routes MSMs that fit its first 2^21 bases
+    to a second, 17-bit-window table set (capi.cu route()).  The result must not depend on which
+    table set ran: compare with dedicated keys over the same bases, across the routing boundary,
+    with and without the blinding term."""
+    cid = 0
+    c = CURVES[cid]
+    big = b200.CommitmentKey.setup_synthetic(b200.Curve(cid), 1 << 22, with_h=True)
+    ce = b200.CommitmentEngine(cid)
+    sc = oracle.gen_scalars(c.scalar_field, 4242, (1 << 21) + 7)
+    for m in (1, 1000, (1 << 16) + 3, 1 << 21, (1 << 21) + 7):
+        own = b200.CommitmentKey.setup_synthetic(b200.Curve(cid), m)
+        assert ce.commit(big, sc[:32 * m], None) == ce.commit(own, sc[:32 * m], None), m
+        own.release()
+    # oracle anchor on the narrow path
+    bases = oracle.gen_bases(cid, 1000)
+    assert ce.commit(big, sc[:32000], None) == aff(c, oracle.msm(cid, sc[:32000], bases))
+    # r*h must come out the same through both table sets
+    r = oracle.gen_scalars(c.scalar_field, 5, 1)
+    zeros = bytes(32)
+    assert ce.commit(big, zeros * 10, r) == ce.commit(big, zeros * ((1 << 21) + 5), r)
+    # offset slices: inside the narrow range and straddling it
+    g = b200.DlogGroup(cid)
+    for off, m in ((12345, 5000), ((1 << 21) - 100, 300)):
+        own = b200.CommitmentKey.setup_synthetic(b200.Curve(cid), m, k0=0x5EED + off)
+        out = __import__("ctypes").create_string_buffer(96)
+        from nova_b200.native import check, lib
+        from nova_b200.provider import _cbuf, _jac_to_affine
+        check(lib().b200_msm(big.handle, off, _cbuf(sc[:32 * m]), m, out))
+        assert _jac_to_affine(b200.Curve(cid), out.raw) == ce.commit(own, sc[:32 * m], None)
+        own.release()
+    big.release()

@@ -38,6 +38,7 @@ def main():
     check(lib().b200_init(0))
     logs = [int(a) for a in sys.argv[1:] if a.isdigit()] or [16, 20]
     wins = [int(a[2:]) for a in sys.argv[1:] if a.startswith("c=")] or [0]
+    dist = ([a[5:] for a in sys.argv[1:] if a.startswith("dist=")] or ["uniform"])[0]
     cid = 0
     c = CURVES[cid]
     for lg in logs:
@@ -45,6 +46,14 @@ def main():
         t0 = time.time()
         bases = co.gen_bases(cid, n)
         sc = co.gen_scalars(c.scalar_field, 2, n)
+        if dist == "half_equal":  # ppsnark-style padding: the upper half repeats one full-width value
+            sc = sc[:16 * n] + sc[:32] * (n - n // 2)
+        elif dist == "bits":      # 0/1 witness
+            import random
+            rnd = random.Random(1)
+            one = co.field_from_u64(c.scalar_field, [1])
+            sc = b"".join(one if rnd.random() < 0.5 else bytes(32) for _ in range(n))
+        print(f"  scalar distribution: {dist}")
         d_sc = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda()
         d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
         print(f"n=2^{lg}: inputs generated in {time.time()-t0:.1f}s", flush=True)
