@@ -86,6 +86,7 @@ struct workspace {
   uint32_t* pkeys = nullptr;
   uint32_t* heavy = nullptr;
   uint32_t heavy_cap = 0;
+  void* hparts = nullptr;
   void* d_out = nullptr;   // result slots (device)
   void* h_out = nullptr;   // pinned mirror
   size_t out_slots = 0;
@@ -93,7 +94,7 @@ struct workspace {
   size_t idx_cap = 0;
   void release() {
     void* ptrs[] = {scalars, digits, counts, start, cursor, blocksums, entries, buckets,
-                    parts, rparts, sumscratch, pkeys, heavy, d_out, idx32};
+                    parts, rparts, sumscratch, pkeys, heavy, hparts, d_out, idx32};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (h_out) cudaFreeHost(h_out);
@@ -125,7 +126,7 @@ struct ck_ctx {
 
 // ---- optional per-stage device timing + launch accounting (for bench.py's roofline) ---------
 enum { ST_DIGITS = 0, ST_SORT, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_COUNT };
-const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 2, 3};
+const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 3, 3};
 struct profile_state {
   std::mutex mu;
   bool enabled = false;
@@ -197,7 +198,7 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
   // *_dev work that may still be using them)
   CU(cudaDeviceSynchronize());
   void** szbufs[] = {&w.scalars, (void**)&w.digits, (void**)&w.entries, &w.parts, (void**)&w.pkeys,
-                     (void**)&w.heavy};
+                     (void**)&w.heavy, &w.hparts};
   for (void** p : szbufs)
     if (*p) {
       cudaFree(*p);
@@ -208,6 +209,7 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
   size_t nseg = (entries + L_MIN - 1) / L_MIN;  // upper bound over every L this key will use
   w.heavy_cap = (uint32_t)(entries / ((size_t)HEAVY_PARTS * L_MIN) + 2);
   CU(cudaMalloc((void**)&w.heavy, ((size_t)w.heavy_cap + 1) * 4));
+  CU(cudaMalloc(&w.hparts, (size_t)w.heavy_cap * HEAVY_SPLIT * XYZZ_BYTES));
   CU(cudaMalloc(&w.scalars, n * 32));
   CU(cudaMalloc((void**)&w.digits, entries * sizeof(int32_t)));
   CU(cudaMalloc((void**)&w.entries, entries * sizeof(uint64_t)));
@@ -244,6 +246,7 @@ msm_plan make_plan(ck_ctx& ck, size_t base_offset, size_t n) {
   p.heavy = ck.ws.heavy;
   p.heavy_min = HEAVY_PARTS * (uint32_t)p.L;
   p.heavy_cap = ck.ws.heavy_cap;
+  p.hparts = ck.ws.hparts;
   p.digits = ck.ws.digits;
   p.counts = ck.ws.counts;
   p.start = ck.ws.start;

@@ -162,15 +162,21 @@ __global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ dig
   uint32_t sign = dgt < 0 ? 1u : 0u;
   uint32_t mag = sign ? (uint32_t)(-dgt) : (uint32_t)dgt;
   uint32_t key = dgt != 0 ? (uint32_t)(w % G) * B + (mag - 1) : NO_KEY;
-  // warp-aggregated slot reservation: one atomic per distinct key per warp, lanes take
-  // consecutive slots by their rank inside the group (see count_key)
-  unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
-  if (key == NO_KEY) return;
-  unsigned lane = threadIdx.x & 31u, leader = (unsigned)(__ffs(peers) - 1);
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  // slot reservation; warps that hold repeated keys aggregate (see count_key): one atomic per
+  // distinct key, lanes take consecutive slots by their rank inside the group
+  uint32_t pos;
+  if (!warp_has_repeats(key)) {
+    if (key == NO_KEY) return;
+    pos = atomicAdd(&cursor[key], 1u);
+  } else {
+    unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (key == NO_KEY) return;
+    unsigned lane = threadIdx.x & 31u, leader = (unsigned)(__ffs(peers) - 1);
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  }
   // the blinding scalar r rides along as one more (scalar, base) pair whose base is h
   size_t bi = (i == blind_i) ? h_index : base_offset + i;
   uint32_t idx = (uint32_t)((size_t)(w / G) * n_ck + bi);

@@ -55,20 +55,30 @@ struct msm_plan {
   void* rparts;        // [G*T] xyzz, T = B/m
   uint32_t* blocksums; // scan scratch
   uint32_t* heavy;     // [0] = count, [1..] = keys whose bucket spans > heavy_min entries
-  uint32_t heavy_min;  // entries; such buckets are joined by k_fixup_heavy (one block each)
+  uint32_t heavy_min;  // entries; such buckets are joined by k_fixup_heavy1/2
   uint32_t heavy_cap;  // capacity of the heavy list
+  void* hparts;        // [heavy_cap * HEAVY_SPLIT] xyzz: slice sums of the heavy buckets
 };
 
 // ------------------------------------------------------------------------------------------
 // digits + histogram   (templated on the SCALAR field)
 // ------------------------------------------------------------------------------------------
-// Warp-aggregated bucket counting: lanes holding the same key elect one leader that adds the
-// group's size.  For uniform scalars every lane is its own group (one MATCH.ANY extra); for
-// witness-like vectors (bits, padding, one value repeated a million times) it divides the number
-// of atomics on the hot counters by up to 32.  `key` = NO_KEY for lanes without an entry; all 32
-// lanes of the warp must call.
+// Warp-aggregated bucket counting for skewed scalars (bits, padding, one value repeated a million
+// times): lanes holding the same key elect one leader that adds the group's size, which divides
+// the atomics on a hot counter by up to 32.  MATCH.ANY is slow enough to cost ~0.1 ms per 2^20
+// uniform MSM, so a warp only takes that path when two NEIGHBOURING lanes hold the same key (one
+// shuffle + one vote): uniform digits practically never do, a bucket that owns >= 10 % of the
+// entries almost always does.  `key` = NO_KEY for lanes without an entry; all 32 lanes must call.
 constexpr uint32_t NO_KEY = 0xFFFFFFFFu;
+__device__ __forceinline__ bool warp_has_repeats(uint32_t key) {
+  uint32_t next = __shfl_down_sync(0xFFFFFFFFu, key, 1);
+  return __any_sync(0xFFFFFFFFu, key != NO_KEY && key == next && (threadIdx.x & 31u) != 31u);
+}
 __device__ __forceinline__ void count_key(uint32_t* counts, uint32_t key) {
+  if (!warp_has_repeats(key)) {
+    if (key != NO_KEY) atomicAdd(&counts[key], 1u);
+    return;
+  }
   unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
   if (key != NO_KEY && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1))
     atomicAdd(&counts[key], (uint32_t)__popc(peers));
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint64_t* __restrict__
 // segments t0..t1, so its partials can only sit in slots 2*t0 .. 2*t1+1; the G lanes stride over
 // that range and combine with a shuffle tree.  A bucket whose entries are interior to one segment
 // finds no matching slot (it was stored directly by k_accumulate); buckets above heavy_min are
-// left to k_fixup_heavy.
+// left to k_fixup_heavy1/2.
 template <class F>
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ start, uint32_t K,
                                                int L, uint32_t heavy_min, int G,
@@ -233,24 +243,31 @@ __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ star
   if (live && sub == 0 && found) PA::store(buckets, key, acc);
 }
 
-// Heavy buckets (skewed scalars: 0/1 witnesses, repeated values) would serialise the run-head
-// loop above, so each gets a whole block: the threads stride over the bucket's partial slots,
-// then tree-sum through shared memory.
+// Heavy buckets (skewed scalars: 0/1 witnesses, padding, one value repeated a million times) hold
+// thousands of boundary partials.  Stage 1 gives each heavy bucket HEAVY_SPLIT blocks: the threads
+// stride over one slice of the bucket's partial slots and tree-sum through shared memory into
+// hparts[h][slice]; stage 2 joins the HEAVY_SPLIT slice sums with a shuffle tree.  A lone warp
+// needs ~9 us per XYZZ addition, so the point is the length of the dependent chain: 16 K partials
+// are 4 strided adds + 8 tree levels + 4 join levels instead of 64 + 8.
+constexpr int HEAVY_SPLIT = 16;
 template <class F>
-__global__ void __launch_bounds__(256) k_fixup_heavy(const uint32_t* __restrict__ start, int L,
-                                                     const uint32_t* __restrict__ heavy,
-                                                     const void* __restrict__ parts,
-                                                     const uint32_t* __restrict__ pkeys,
-                                                     void* __restrict__ buckets) {
+__global__ void __launch_bounds__(256) k_fixup_heavy1(const uint32_t* __restrict__ start, int L,
+                                                      const uint32_t* __restrict__ heavy,
+                                                      const void* __restrict__ parts,
+                                                      const uint32_t* __restrict__ pkeys,
+                                                      void* __restrict__ hparts) {
   using PA = msm_arith<F>;
   __shared__ typename msm_arith<F>::pt sm[256];
-  const uint32_t nheavy = heavy[0];
-  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+  const uint32_t nitems = heavy[0] * HEAVY_SPLIT;
+  for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    uint32_t h = it / HEAVY_SPLIT, sl = it % HEAVY_SPLIT;
     uint32_t key = heavy[1 + h];
     size_t s0 = 2 * ((size_t)start[key] / L);
-    size_t s1 = 2 * (((size_t)start[key + 1] - 1) / L) + 1;
+    size_t s1 = 2 * (((size_t)start[key + 1] - 1) / L) + 2;  // one past the last slot
+    size_t per = (s1 - s0 + HEAVY_SPLIT - 1) / HEAVY_SPLIT;
+    size_t lo = s0 + sl * per, hi = lo + per < s1 ? lo + per : s1;
     typename PA::pt acc = PA::identity();
-    for (size_t k = s0 + threadIdx.x; k <= s1; k += blockDim.x) {
+    for (size_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
       if (pkeys[k] == key) {
         typename PA::pt o = PA::load(parts, k);
         PA::add(acc, o);
@@ -266,8 +283,26 @@ __global__ void __launch_bounds__(256) k_fixup_heavy(const uint32_t* __restrict_
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) PA::store(buckets, key, sm[0]);
+    if (threadIdx.x == 0) PA::store(hparts, it, sm[0]);
     __syncthreads();
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(32) k_fixup_heavy2(const uint32_t* __restrict__ heavy,
+                                                     const void* __restrict__ hparts,
+                                                     void* __restrict__ buckets) {
+  using PA = msm_arith<F>;
+  static_assert(HEAVY_SPLIT <= 32 && (HEAVY_SPLIT & (HEAVY_SPLIT - 1)) == 0, "one warp joins the slices");
+  const uint32_t nheavy = heavy[0];
+  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    typename PA::pt acc = PA::identity();
+    if (threadIdx.x < HEAVY_SPLIT) acc = PA::load(hparts, (size_t)h * HEAVY_SPLIT + threadIdx.x);
+    for (int d = HEAVY_SPLIT / 2; d > 0; d >>= 1) {
+      typename PA::pt o = PA::shfl_down(acc, d, 32);
+      if ((int)threadIdx.x < d) PA::add(acc, o);
+    }
+    if (threadIdx.x == 0) PA::store(buckets, heavy[1 + h], acc);
   }
 }
 

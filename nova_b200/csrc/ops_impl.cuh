@@ -73,7 +73,8 @@ struct ops_impl {
 #endif
       k_fixup<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(p.start, K, p.L, p.heavy_min, G, p.parts,
                                                                    p.pkeys, p.buckets);
-    k_fixup_heavy<F><<<148, 256, 0, s>>>(p.start, p.L, p.heavy, p.parts, p.pkeys, p.buckets);
+    k_fixup_heavy1<F><<<148 * 4, 256, 0, s>>>(p.start, p.L, p.heavy, p.parts, p.pkeys, p.hparts);
+    k_fixup_heavy2<F><<<148, 32, 0, s>>>(p.heavy, p.hparts, p.buckets);
   }
   static void index_bases(cudaStream_t s, void* bases, size_t n, const void* gen, uint64_t k0) {
     k_index_bases<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(bases, n, gen, k0);

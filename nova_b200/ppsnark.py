@@ -23,7 +23,7 @@ from .native import check, lib
 from .provider import CommitmentKey, _cbuf, _jac_to_affine
 from .spartan import (SC_CUBIC, SC_EQ_CUBIC2, SC_EQ_CUBIC2_M1, SC_EQ_CUBIC3, SC_EQ_CUBIC3_M1, SC_EQ_QUAD1,
                       SC_EQ_QUAD1_M1, SC_LINEAR, SC_NOUT, SC_QUADRATIC, DeviceVec, EqSumCheckInstance,
-                      SparseMatrix, UniPoly, _sc_eval_dev, update_claim)
+                      SparseMatrix, UniPoly, _challenge_dev, _sc_eval_dev, _small_buf, update_claim)
 
 
 def to_repr(x: int) -> bytes:
@@ -98,7 +98,7 @@ class RoundSums:
     """All reductions of one sum-check round in one result buffer, one read-back."""
 
     def __init__(self, fid: int, cap: int = 16):
-        self.fid, self.out, self.nout = fid, DeviceVec(96 * cap), []
+        self.fid, self.out, self.nout = fid, _small_buf("round_sums", 96 * cap), []
 
     def add(self, form, A, B, C, length, L=None, R=None, shift=0) -> int:
         k = len(self.nout)
@@ -403,7 +403,7 @@ def prove_helper(fid, mem, inner, witness, transcript):
         transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
         r = transcript.squeeze(b"c")
         rs.append(r)
-        r_dev = dev_scalar(fid, r)
+        r_dev = _challenge_dev(fid, r)
         for eng in (mem, inner, witness):
             eng.bound(r, r_dev)
         e = poly.evaluate(r)
@@ -424,7 +424,7 @@ def _prove_cubic3_resident(fid, claim, taus, A, B, C, length, transcript):
         rs.append(r)
         polys.append(poly.compress())
         claim = poly.evaluate(r)
-        _bind_all(fid, (A, B, C), length, dev_scalar(fid, r))
+        _bind_all(fid, (A, B, C), length, _challenge_dev(fid, r))
         eq.bound(r)
         length //= 2
     return polys, rs, [_first(fid, Z) for Z in (A, B, C)]

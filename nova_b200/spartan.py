@@ -236,8 +236,27 @@ class UniPoly:
         return b"".join(int(c).to_bytes(32, "little") for c in self.compress())
 
 
+_SMALL = {}
+
+
+def _small_buf(name: str, nbytes: int) -> "DeviceVec":
+    """Persistent few-byte device buffers (round results, the current challenge): allocating and
+    freeing them every sum-check round costs more than the round's kernels once the tables are
+    short (cudaFree synchronises the device)."""
+    v = _SMALL.get(name)
+    if v is None or v.nbytes < nbytes or not v.ptr:
+        v = _SMALL[name] = DeviceVec(nbytes)
+    return v
+
+
+def _challenge_dev(fid: int, r_int: int) -> "DeviceVec":
+    rdev = _small_buf("challenge", 32)
+    check(lib().b200_memcpy_h2d(rdev.ptr, _cbuf(fields.to_mont_bytes(fid, r_int)), 32))
+    return rdev
+
+
 def _sc_eval_dev(fid, form, A, B, C, length, eq_left, eq_right, shift) -> list:
-    out = DeviceVec(96)
+    out = _small_buf("sc_out", 96)
     check(lib().b200_sc_eval_dev(fid, form, A.ptr, B.ptr if B else None, C.ptr if C else None, length,
                                  eq_left.ptr if eq_left else None, eq_right.ptr if eq_right else None,
                                  shift, out.ptr, None))
@@ -246,9 +265,7 @@ def _sc_eval_dev(fid, form, A, B, C, length, eq_left, eq_right, shift) -> list:
 
 
 def _bind_dev(fid, Z: DeviceVec, length: int, r_int: int):
-    rdev = DeviceVec.from_bytes(fields.to_mont_bytes(fid, r_int))
-    check(lib().b200_bind_top_dev(fid, Z.ptr, length, rdev.ptr, None))
-    check(lib().b200_sync())
+    check(lib().b200_bind_top_dev(fid, Z.ptr, length, _challenge_dev(fid, r_int).ptr, None))
 
 
 class EqSumCheckInstance:
