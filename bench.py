@@ -271,6 +271,13 @@ def run_b200(args):
             traffic = json.load(open(tf)).get(f"log2n_{args.log2n}_gpus_{world}")
         except Exception:
             traffic = None
+    cc, nt = ctypes.c_int(0), ctypes.c_int(0)
+    check(L.b200_ck_len(ck.handle, None, ctypes.byref(cc), ctypes.byref(nt)))
+    # the pipe that actually bounds the kernel: 10 field products per XYZZ mixed addition (8M + 2S,
+    # madd-2008-s), one addition per non-zero digit; ceiling = the carry-chain
+    # multiplier's measured 64.2 G field-mul/s (tools/microbench.cu, profiles/r01l_microbench_carry_save.txt)
+    fe_muls = 10.0 * n * nt.value * (1.0 - 2.0 ** -cc.value)
+    mul_rate = fe_muls / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
     roofline = {
         "kernel": "k_accumulate<BN254_FQ>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,
         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
@@ -278,6 +285,9 @@ def run_b200(args):
         "note": "MSM is INT32-multiply bound, not HBM bound (DESIGN.md §Roofline); the HBM fraction is "
                 "reported because north_star asks for it",
         "stage_ms_per_msm": {k: round(stage_ms[i] / max(1, msms.value), 4) for i, k in enumerate(stage_names)},
+        "int_mul_pipe": {"achieved": round(mul_rate, 2), "peak": 64.2, "unit": "G field-mul/s",
+                         "frac": round(mul_rate / 64.2, 4), "window_bits": cc.value, "windows": nt.value,
+                         "peak_source": "measured fe_mul throughput of this multiplier (tools/microbench.cu)"},
     }
 
     # ---------------- CPU baseline beside it (N = 1 only) ---------------------------------------
@@ -296,6 +306,18 @@ def run_b200(args):
         prove_step = psr.gpu_replay(steps=5, warmup=2)
         if not args.no_cpu_baseline:
             prove_step["cpu_baseline"] = psr.cpu_replay(steps=1)
+
+    # ---------------- the two SNARK provers of BASELINE.json configs[3], configs[4] (replays) -----
+    snark_replays = {}
+    if world == 1 and not args.no_prove_step:
+        for name, mod, kw in (("hyperkzg_prove_2p22", "hyperkzg_replay", {"log2n": 22, "reps": 2}),
+                              ("ppsnark_prove_core_2p18", "ppsnark_replay", {"log2cons": 18, "reps": 2})):
+            try:
+                m = __import__(mod)
+                snark_replays[name] = m.gpu(**kw) if hasattr(m, "gpu") else m.run(**kw)
+            except Exception as e:  # never let a side measurement take the headline down
+                snark_replays[name] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -316,6 +338,7 @@ def run_b200(args):
         "cpu_baseline": cpu_baseline,
         "prove_step_replay": prove_step,
         "other_sizes": other_sizes,
+        "snark_replays": snark_replays,
     }
     print(json.dumps(out))
     if world > 1:
