@@ -104,6 +104,13 @@ int b200_commit(uint64_t ck_handle, const void* scalars_mont, size_t n, const vo
                 void* out_jacobian_mont);
 int b200_commit_dev(uint64_t ck_handle, const void* d_scalars_mont, size_t n,
                     const void* d_blind_mont_or_null, void* d_out_jacobian_mont, void* stream);
+/* k commitments (r = 0) of device-resident vectors over prefixes of one key, spread over the key's
+ * internal (stream, workspace) lanes so that the latency-bound tails of short MSMs overlap with the
+ * next vector's work -- HyperKZG's ell-1 halving polynomials (hyperkzg.rs:1099-1100), the L / R pair
+ * of an IPA round (ipa_pc.rs:222-238), the four memory oracles of ppsnark (ppsnark.rs:457-471).
+ * d_out = k x 96 B; ordered after prior work on `stream`, which waits for every lane on return. */
+int b200_commit_many_dev(uint64_t ck_handle, const void* const* d_scalars_mont, const size_t* lens,
+                         size_t k, void* d_out_jacobian_mont, void* stream);
 /* k MSMs over prefixes of the same key: vector j uses ck[..lens[j]] (traits.rs:82-90,
  * blitzar.rs:23-40, hyperkzg.rs:594-612 batch_commit).  out = k x 96 B. */
 int b200_msm_batch(uint64_t ck_handle, const void* const* scalars_mont, const size_t* lens,

@@ -113,6 +113,16 @@ struct ck_ctx {
   int m = 4;
   void* tables = nullptr;  // [F][n] affine
   workspace ws;
+  // extra (stream, workspace) lanes for calls that carry several independent MSMs
+  // (b200_commit_many_dev, b200_msm_batch): the latency-bound tails of short MSMs overlap with
+  // the next vector's sort / accumulate, and host->device staging overlaps with compute
+  struct lane {
+    workspace ws;
+    cudaStream_t s = nullptr;
+    cudaEvent_t done = nullptr;
+  };
+  static constexpr int NLANES = 4;
+  lane lanes[NLANES];
   // Keys wide enough for 20-bit windows also carry 17-bit-window tables over their first 2^21
   // bases: the same key commits vectors of very different lengths (W, E, T, the halving
   // polynomials of HyperKZG, hyperkzg.rs:1083-1100), and a short MSM should not pay the
@@ -121,6 +131,11 @@ struct ck_ctx {
   ~ck_ctx() {
     if (tables) cudaFree(tables);
     ws.release();
+    for (lane& l : lanes) {
+      l.ws.release();
+      if (l.done) cudaEventDestroy(l.done);
+      if (l.s) cudaStreamDestroy(l.s);
+    }
   }
 };
 
@@ -183,8 +198,7 @@ int segment_len(size_t entries) {
   return (int)(L < L_MIN ? L_MIN : L);
 }
 
-int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
-  workspace& w = ck.ws;
+int ensure_workspace(ck_ctx& ck, workspace& w, size_t n, size_t out_slots) {
   if (out_slots > w.out_slots) {
     if (w.d_out) cudaFree(w.d_out);
     if (w.h_out) cudaFreeHost(w.h_out);
@@ -230,7 +244,11 @@ int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
   return B200_OK;
 }
 
-msm_plan make_plan(ck_ctx& ck, size_t base_offset, size_t n) {
+int ensure_workspace(ck_ctx& ck, size_t n, size_t out_slots) {
+  return ensure_workspace(ck, ck.ws, n, out_slots);
+}
+
+msm_plan make_plan(ck_ctx& ck, workspace& ws, size_t base_offset, size_t n) {
   msm_plan p;
   p.n = n;
   p.n_ck = ck.stride;
@@ -243,26 +261,26 @@ msm_plan make_plan(ck_ctx& ck, size_t base_offset, size_t n) {
   p.B = ck.B;
   p.L = segment_len(n * (size_t)ck.W);
   p.m = ck.m;
-  p.heavy = ck.ws.heavy;
+  p.heavy = ws.heavy;
   p.heavy_min = HEAVY_PARTS * (uint32_t)p.L;
-  p.heavy_cap = ck.ws.heavy_cap;
-  p.hparts = ck.ws.hparts;
-  p.digits = ck.ws.digits;
-  p.counts = ck.ws.counts;
-  p.start = ck.ws.start;
-  p.cursor = ck.ws.cursor;
-  p.entries = ck.ws.entries;
-  p.buckets = ck.ws.buckets;
-  p.parts = ck.ws.parts;
-  p.pkeys = ck.ws.pkeys;
-  p.rparts = ck.ws.rparts;
-  p.blocksums = ck.ws.blocksums;
+  p.heavy_cap = ws.heavy_cap;
+  p.hparts = ws.hparts;
+  p.digits = ws.digits;
+  p.counts = ws.counts;
+  p.start = ws.start;
+  p.cursor = ws.cursor;
+  p.entries = ws.entries;
+  p.buckets = ws.buckets;
+  p.parts = ws.parts;
+  p.pkeys = ws.pkeys;
+  p.rparts = ws.rparts;
+  p.blocksums = ws.blocksums;
   return p;
 }
 
 // enqueue one full-width MSM on `s`; scalars and out are device pointers
-int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
-                cudaStream_t s, int small_elem_bytes = 0, bool blinded = false) {
+int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_scalars, size_t n,
+                void* d_out, cudaStream_t s, int small_elem_bytes = 0, bool blinded = false) {
   // blinded: d_scalars holds n-1 vector entries followed by r, whose base is h
   if (n == 0) {  // identity (msm.rs:228-230): z = 0
     CU(cudaMemsetAsync(d_out, 0, 96, s));
@@ -270,7 +288,7 @@ int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n,
   }
   const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
   const field_ops* bops = ops_for_field(CURVES[ck.curve].base_fid);
-  msm_plan p = make_plan(ck, base_offset, n);
+  msm_plan p = make_plan(ck, ws, base_offset, n);
   if (blinded) p.blind_i = n - 1;
   size_t K = (size_t)ck.G * ck.B;
   CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
@@ -306,6 +324,11 @@ int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n,
   for (int i = 0; i < ST_COUNT; i++) g_prof.launches += STAGE_KERNELS[i];
   CU(cudaGetLastError());
   return B200_OK;
+}
+
+int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
+                cudaStream_t s, int small_elem_bytes = 0, bool blinded = false) {
+  return enqueue_msm(ck, ck.ws, base_offset, d_scalars, n, d_out, s, small_elem_bytes, blinded);
 }
 
 constexpr size_t SMALL_KEY_MAX = (size_t)1 << 21;
@@ -664,6 +687,64 @@ int b200_commit_dev(uint64_t handle, const void* d_scalars, size_t n, const void
   return enqueue_msm(t, 0, t.ws.scalars, n + 1, d_out, s, 0, true);
 }
 
+// k independent MSMs over prefixes of one key, spread round-robin over the key's lanes.  Vector j
+// is read from vecs[j] (device memory, or host memory staged through the lane's workspace when
+// `from_host`); result j goes to d_out + 96 j.  Ordered after prior work on `s`; on return `s`
+// waits for every lane.  Caller holds ck.mu.
+static int enqueue_many(ck_ctx& ck, const void* const* vecs, const size_t* lens, size_t k,
+                        bool from_host, void* d_out, cudaStream_t s) {
+  std::unique_lock<std::mutex> lsmall;
+  if (ck.small) lsmall = std::unique_lock<std::mutex>(ck.small->mu);  // lock order: wide, narrow
+  cudaEvent_t start_ev = nullptr;
+  CU(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+  CU(cudaEventRecord(start_ev, s));
+  bool used[2][ck_ctx::NLANES] = {};
+  size_t next[2] = {0, 0};
+  int rc = B200_OK;
+  for (size_t j = 0; j < k && rc == B200_OK; j++) {
+    ck_ctx& t = route(ck, 0, lens[j]);
+    int which = &t == &ck ? 0 : 1;
+    int li = (int)(next[which]++ % ck_ctx::NLANES);
+    ck_ctx::lane& ln = t.lanes[li];
+    if (!ln.s) {
+      CU(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    }
+    if (!used[which][li]) {
+      CU(cudaStreamWaitEvent(ln.s, start_ev, 0));
+      used[which][li] = true;
+    }
+    rc = ensure_workspace(t, ln.ws, lens[j] ? lens[j] : 1, 1);
+    if (rc) break;
+    const void* src = vecs[j];
+    if (from_host && lens[j]) {
+      CU(cudaMemcpyAsync(ln.ws.scalars, vecs[j], lens[j] * 32, cudaMemcpyHostToDevice, ln.s));
+      src = ln.ws.scalars;
+    }
+    rc = enqueue_msm(t, ln.ws, 0, src, lens[j], (char*)d_out + 96 * j, ln.s);
+  }
+  for (int which = 0; which < 2; which++) {
+    ck_ctx* t = which == 0 ? &ck : ck.small.get();
+    for (int li = 0; t && li < ck_ctx::NLANES; li++)
+      if (used[which][li]) {
+        cudaEventRecord(t->lanes[li].done, t->lanes[li].s);
+        cudaStreamWaitEvent(s, t->lanes[li].done, 0);
+      }
+  }
+  cudaEventDestroy(start_ev);
+  return rc;
+}
+
+static int check_many(ck_ctx& ck, const void* const* vecs, const size_t* lens, size_t k) {
+  if (!vecs || !lens) return fail(B200_E_ARG, "null pointer");
+  for (size_t j = 0; j < k; j++) {
+    if (lens[j] > ck.n)
+      return fail(B200_E_RANGE, "batch vector %zu has %zu scalars, key has %zu", j, lens[j], ck.n);
+    if (lens[j] && !vecs[j]) return fail(B200_E_ARG, "null scalar vector %zu", j);
+  }
+  return B200_OK;
+}
+
 int b200_msm_batch(uint64_t handle, const void* const* scalars, const size_t* lens, size_t k,
                    void* out) {
   int rc = ensure_init();
@@ -671,35 +752,32 @@ int b200_msm_batch(uint64_t handle, const void* const* scalars, const size_t* le
   auto ck = get_ck(handle);
   if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
   if (k == 0) return B200_OK;
-  if (!scalars || !lens || !out) return fail(B200_E_ARG, "null pointer");
-  size_t nmax = 1;
-  for (size_t j = 0; j < k; j++) {
-    if (lens[j] > ck->n)
-      return fail(B200_E_RANGE, "batch vector %zu has %zu scalars, key has %zu", j, lens[j], ck->n);
-    if (lens[j] && !scalars[j]) return fail(B200_E_ARG, "null scalar vector %zu", j);
-    if (lens[j] > nmax) nmax = lens[j];
-  }
-  std::lock_guard<std::mutex> lk(ck->mu);  // lock order: wide tables, then (per vector) narrow
-  rc = ensure_workspace(*ck, nmax, k);
+  if (!out) return fail(B200_E_ARG, "null pointer");
+  if ((rc = check_many(*ck, scalars, lens, k))) return rc;
+  std::lock_guard<std::mutex> lk(ck->mu);
+  rc = ensure_workspace(*ck, 1, k);
   if (rc) return rc;
   cudaStream_t s = g_dev.stream;
-  for (size_t j = 0; j < k; j++) {
-    ck_ctx& t = route(*ck, 0, lens[j]);
-    std::unique_lock<std::mutex> lt;
-    if (&t != ck.get()) {
-      lt = std::unique_lock<std::mutex>(t.mu);
-      rc = ensure_workspace(t, lens[j] ? lens[j] : 1, 1);
-      if (rc) return rc;
-    }
-    if (lens[j])
-      CU(cudaMemcpyAsync(t.ws.scalars, scalars[j], lens[j] * 32, cudaMemcpyHostToDevice, s));
-    rc = enqueue_msm(t, 0, t.ws.scalars, lens[j], (char*)ck->ws.d_out + 96 * j, s);
-    if (rc) return rc;
-  }
+  rc = enqueue_many(*ck, scalars, lens, k, /*from_host=*/true, ck->ws.d_out, s);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(ck->ws.h_out, ck->ws.d_out, 96 * k, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   memcpy(out, ck->ws.h_out, 96 * k);
   return B200_OK;
+}
+
+int b200_commit_many_dev(uint64_t handle, const void* const* d_scalars, const size_t* lens, size_t k,
+                         void* d_out, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (k == 0) return B200_OK;
+  if (!d_out) return fail(B200_E_ARG, "null pointer");
+  if ((rc = check_many(*ck, d_scalars, lens, k))) return rc;
+  std::lock_guard<std::mutex> lk(ck->mu);
+  return enqueue_many(*ck, d_scalars, lens, k, /*from_host=*/false, d_out,
+                      stream ? (cudaStream_t)stream : g_dev.stream);
 }
 
 int b200_msm_small(uint64_t handle, size_t base_offset, const void* scalars, int elem_bytes, size_t n,

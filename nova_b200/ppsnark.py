@@ -23,7 +23,8 @@ from .native import check, lib
 from .provider import CommitmentKey, _cbuf, _jac_to_affine
 from .spartan import (SC_CUBIC, SC_EQ_CUBIC2, SC_EQ_CUBIC2_M1, SC_EQ_CUBIC3, SC_EQ_CUBIC3_M1, SC_EQ_QUAD1,
                       SC_EQ_QUAD1_M1, SC_LINEAR, SC_NOUT, SC_QUADRATIC, DeviceVec, EqSumCheckInstance,
-                      SparseMatrix, UniPoly, _challenge_dev, _sc_eval_dev, _small_buf, update_claim)
+                      SparseMatrix, UniPoly, _challenge_dev, _sc_eval_dev, _small_buf, commit_many_dev,
+                      update_claim)
 
 
 def to_repr(x: int) -> bytes:
@@ -491,7 +492,7 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
     E_p, W_p = dev_padded(Ed, num_cons, N), dev_padded(Wd, num_vars, N)
     mem_row, mem_col, L_row, L_col = spark.evaluation_oracles(r_full, z, z_len)
     mark("evaluation_oracles")
-    comm_L_row, comm_L_col = commit_dev(curve, ck, L_row, N), commit_dev(curve, ck, L_col, N)
+    comm_L_row, comm_L_col = commit_many_dev(curve, ck, [L_row, L_col], [N, N])
     mark("commit_L")
     tr.absorb_bytes(b"e", commitment_transcript_bytes(comm_L_row) + commitment_transcript_bytes(comm_L_col))
     c = tr.squeeze(b"c")
@@ -504,7 +505,7 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
     mem_oracles, mem_aux = memory_compute_oracles(fid, r, gamma, N, mem_row, spark.row, L_row, spark.ts_row,
                                                   mem_col, spark.col, L_col, spark.ts_col)
     mark("memory_oracles")
-    comm_mem = [commit_dev(curve, ck, v, N) for v in mem_oracles]
+    comm_mem = commit_many_dev(curve, ck, mem_oracles, [N] * 4)
     mark("commit_mem")
     tr.absorb_bytes(b"l", b"".join(commitment_transcript_bytes(P) for P in comm_mem))
     rho = [tr.squeeze(b"r") for _ in range(nri)]

@@ -255,6 +255,20 @@ def _challenge_dev(fid: int, r_int: int) -> "DeviceVec":
     return rdev
 
 
+def commit_many_dev(curve, ck: CommitmentKey, vecs: list, lens: list) -> list:
+    """CE::batch_commit with r = 0 on device-resident vectors (b200_commit_many_dev: the MSMs are
+    spread over the key's lanes so short ones overlap) -> affine points / None."""
+    k = len(vecs)
+    if k == 0:
+        return []
+    ptrs = (ctypes.c_void_p * k)(*[v.ptr.value for v in vecs])
+    lns = (c_size_t * k)(*lens)
+    out = _small_buf("commit_many", 96 * max(k, 32))
+    check(lib().b200_commit_many_dev(ck.handle, ptrs, lns, k, out.ptr, None))
+    raw = out.to_bytes(96 * k)
+    return [_jac_to_affine(Curve(curve), raw[96 * j:96 * j + 96]) for j in range(k)]
+
+
 def _sc_eval_dev(fid, form, A, B, C, length, eq_left, eq_right, shift) -> list:
     out = _small_buf("sc_out", 96)
     check(lib().b200_sc_eval_dev(fid, form, A.ptr, B.ptr if B else None, C.ptr if C else None, length,
@@ -473,11 +487,7 @@ def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r
         polys.append(nxt)
         lens.append(lens[i] // 2)
     mark("fold")
-    pts = DeviceVec(96 * (ell + 2))
-    for i in range(1, ell):  # :1099-1100 batch_commit(polys[1..])
-        check(L.b200_commit_dev(ck.handle, polys[i].ptr, lens[i], None, ctypes.c_void_p(pts.ptr.value + 96 * (i - 1)), None))
-    raw = pts.to_bytes(96 * (ell - 1))
-    com = [_jac_to_affine(Curve(curve), raw[96 * j:96 * j + 96]) for j in range(ell - 1)]
+    com = commit_many_dev(curve, ck, polys[1:], lens[1:])  # :1099-1100 batch_commit(polys[1..])
     mark("commit_folds")
     u = [r % p, (-r) % p, r * r % p]  # :1105-1106
     us = DeviceVec.from_bytes(fields.pack(fid, u))
@@ -501,10 +511,7 @@ def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r
         check(L.b200_poly_div_dev(fid, Bpoly.ptr, n, ud.ptr, h.ptr, None))
         hs.append((h, ud))
     mark("quotients")
-    for t, (h, _) in enumerate(hs):
-        check(L.b200_commit_dev(ck.handle, h.ptr, n - 1, None, ctypes.c_void_p(pts.ptr.value + 96 * (ell - 1 + t)), None))
-    raw = pts.to_bytes(96 * (ell + 2))
-    w = [_jac_to_affine(Curve(curve), raw[96 * (ell - 1 + t):96 * (ell + t)]) for t in range(3)]
+    w = commit_many_dev(curve, ck, [h for h, _ in hs], [n - 1] * 3)
     mark("commit_quotients")
     return com, v, w, polys
 

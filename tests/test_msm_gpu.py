@@ -242,6 +242,14 @@ def test_short_vectors_on_a_wide_key(b200, oracle):
     r = oracle.gen_scalars(c.scalar_field, 5, 1)
     zeros = bytes(32)
     assert ce.commit(big, zeros * 10, r) == ce.commit(big, zeros * ((1 << 21) + 5), r)
+    # several vectors in one call, spread over the lanes of both table sets (b200_commit_many_dev)
+    from nova_b200.spartan import DeviceVec, commit_many_dev
+    lens = [(1 << 21) + 7, 1 << 21, 70000, 4096, 33, 2, 1, 1000, 5, (1 << 16) + 3]
+    vecs = [DeviceVec.from_bytes(sc[32 * 3:32 * (3 + m)]) for m in lens]
+    many = commit_many_dev(cid, big, vecs, lens)
+    for m, got in zip(lens, many):
+        assert got == ce.commit(big, sc[32 * 3:32 * (3 + m)], None), m
+    assert ce.batch_commit(big, [sc[:32 * m] for m in lens[2:]]) == [ce.commit(big, sc[:32 * m], None) for m in lens[2:]]
     # offset slices: inside the narrow range and straddling it
     g = b200.DlogGroup(cid)
     for off, m in ((12345, 5000), ((1 << 21) - 100, 300)):
