@@ -60,6 +60,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
@@ -75,6 +76,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, wait_s=5.0):
+        """Call right before the timed region: waits until nvidia-smi is up and sampling (its start-up
+        must not fall inside the region: the fork and NVML initialisation stall kernel launches for
+        milliseconds), then remembers where the region's samples begin."""
+        if not self.proc:
+            return
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < wait_s:
+            time.sleep(0.02)
+        self.first = max(0, len(self.lines) - 1)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -86,7 +98,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -189,16 +201,18 @@ def run_b200(args):
         sharded_msm_step(ck, d_sc, n)
 
     # ---------------- device-resident throughput ("value") --------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # started before the warm-up so that its start-up cost stays outside the timing
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step_device()
         barrier()
         check(L.b200_profile_enable(1))
         check(L.b200_profile_reset())
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if rank == 0:
+            sampler.mark()
         barrier()
         e0.record(stream)
         for _ in range(args.steps):

@@ -145,24 +145,31 @@ const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 3, 3};
 struct profile_state {
   std::mutex mu;
   bool enabled = false;
-  cudaEvent_t ev[ST_COUNT + 1] = {};
+  // a ring of event sets, so that the host may run PROF_RING - 1 MSMs ahead of the device while
+  // timing is on (folding set k waits for the MSM that used it PROF_RING calls ago)
+  static constexpr int PROF_RING = 4;
+  cudaEvent_t ev[PROF_RING][ST_COUNT + 1] = {};
   bool have_events = false;
-  bool pending = false;        // events of the last MSM not folded in yet
+  bool pending[PROF_RING] = {};  // event set not folded in yet
+  int next = 0;
   double ms[ST_COUNT] = {};    // accumulated
   uint64_t msms = 0;
   uint64_t launches = 0;       // kernels launched by this library (always counted)
 } g_prof;
 
-void prof_fold_locked() {  // caller holds g_prof.mu
-  if (!g_prof.pending) return;
-  if (cudaEventSynchronize(g_prof.ev[ST_COUNT]) == cudaSuccess) {
+void prof_fold_set_locked(int k) {  // caller holds g_prof.mu
+  if (!g_prof.pending[k]) return;
+  if (cudaEventSynchronize(g_prof.ev[k][ST_COUNT]) == cudaSuccess) {
     for (int i = 0; i < ST_COUNT; i++) {
       float t = 0;
-      if (cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]) == cudaSuccess) g_prof.ms[i] += t;
+      if (cudaEventElapsedTime(&t, g_prof.ev[k][i], g_prof.ev[k][i + 1]) == cudaSuccess) g_prof.ms[i] += t;
     }
     g_prof.msms++;
   }
-  g_prof.pending = false;
+  g_prof.pending[k] = false;
+}
+void prof_fold_locked() {
+  for (int k = 0; k < profile_state::PROF_RING; k++) prof_fold_set_locked(k);
 }
 
 void count_launch(int k) {
@@ -295,15 +302,18 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
   CU(cudaMemsetAsync(p.heavy, 0, 4, s));
   std::lock_guard<std::mutex> plk(g_prof.mu);
   const bool prof = g_prof.enabled;
+  const int pset = g_prof.next;
   if (prof) {
-    prof_fold_locked();
     if (!g_prof.have_events) {
-      for (auto& e : g_prof.ev) CU(cudaEventCreate(&e));
+      for (auto& set : g_prof.ev)
+        for (auto& e : set) CU(cudaEventCreate(&e));
       g_prof.have_events = true;
     }
+    prof_fold_set_locked(pset);
+    g_prof.next = (pset + 1) % profile_state::PROF_RING;
   }
 #define STAGE_MARK(i) \
-  if (prof) CU(cudaEventRecord(g_prof.ev[i], s))
+  if (prof) CU(cudaEventRecord(g_prof.ev[pset][i], s))
   STAGE_MARK(ST_DIGITS);
   if (small_elem_bytes)
     msm_digits_small(s, d_scalars, small_elem_bytes, p);
@@ -320,7 +330,7 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
   bops->reduce(s, p, d_out);
   STAGE_MARK(ST_COUNT);
 #undef STAGE_MARK
-  if (prof) g_prof.pending = true;
+  if (prof) g_prof.pending[pset] = true;
   for (int i = 0; i < ST_COUNT; i++) g_prof.launches += STAGE_KERNELS[i];
   CU(cudaGetLastError());
   return B200_OK;
