@@ -663,3 +663,36 @@ def ipa_prove(curve: "Curve", ck, ck_c, comm_a, b_vec, c_claim, a_vec, transcrip
         L_vec.append(L)
         R_vec.append(R)
     return L_vec, R_vec, a[0]
+
+
+def ipa_verify(curve: "Curve", ck, ck_c, comm_a, b_vec, c_claim, L_vec, R_vec, a_hat, transcript) -> bool:
+    """InnerProductArgument::verify (provider/ipa_pc.rs:286-396), restated to pin `ipa_prove`."""
+    q = curve.q
+    n = len(b_vec)
+    if n != 1 << len(L_vec) or len(L_vec) != len(R_vec) or len(L_vec) >= 32:
+        return False
+    ck = list(ck[:n])
+    transcript.absorb_bytes(b"NoDS", b"IPA")
+    transcript.absorb_bytes(b"U", commitment_transcript_bytes(comm_a) + to_repr(c_claim % q))
+    r0 = transcript.squeeze(b"r")
+    ck_c_s = curve.mul(r0, ck_c)
+    P = curve.add(comm_a, curve.mul(c_claim % q, ck_c_s))
+    rs = []
+    for L, R in zip(L_vec, R_vec):
+        transcript.absorb_bytes(b"L", commitment_transcript_bytes(L))
+        transcript.absorb_bytes(b"R", commitment_transcript_bytes(R))
+        rs.append(transcript.squeeze(b"r"))
+    r_sq = [r * r % q for r in rs]
+    r_inv = [pow(r, -1, q) for r in rs]
+    r_inv_sq = [x * x % q for x in r_inv]
+    s = [0] * n  # the vector with the tensor structure, :335-350
+    s[0] = 1
+    for x in r_inv:
+        s[0] = s[0] * x % q
+    for i in range(1, n):
+        pos = i.bit_length() - 1
+        s[i] = s[i - (1 << pos)] * r_sq[(len(L_vec) - 1) - pos] % q
+    ck_hat = curve.msm_naive(s, ck)
+    b_hat = sum(x * y for x, y in zip(b_vec, s)) % q
+    P_hat = curve.msm_naive(r_sq + r_inv_sq + [1], list(L_vec) + list(R_vec) + [P])
+    return P_hat == curve.msm_naive([a_hat % q, a_hat * b_hat % q], [ck_hat, ck_c_s])
