@@ -186,6 +186,53 @@ int b200_sc_eval_dev(int field_id, int form, const void* A, const void* B, const
 int b200_sc_eval_sharded_dev(int field_id, int form, const void* A, const void* B, const void* C,
                              size_t local_len, const void* eq_left, const void* eq_right, int shift,
                              size_t id_mul, size_t id_add, void* out, void* stream);
+/* ---- sum-check round loops with the transcript on the device ----------------
+ * The reference interleaves, per round, an O(N) reduction, O(1) host algebra (UniPoly from the
+ * evaluation points, univariate.rs:89-154; claim derivation / bound of EqSumCheckInstance,
+ * sumcheck.rs:680-747, 1226-1231), `transcript.absorb(b"p", &poly)`, `transcript.squeeze(b"c")`
+ * (Keccak256Transcript, provider/keccak.rs:98-160, non-evm) and the binds.  These entry points put
+ * the O(1) part on the device too, so all rounds are enqueued back to back and the host reads the
+ * proof once.  Prover messages are byte-identical to the host path.
+ *
+ * b200_transcript = the serialisable part of Keccak256Transcript (keccak.rs:19-27) after the last
+ * squeeze; bytes absorbed since then travel separately as `pending` (= `transcript_buffer`,
+ * at most B200_SC_MAX_PENDING bytes -- squeeze on the host first if there are more). */
+typedef struct b200_transcript {
+  uint64_t round;         /* Keccak256Transcript::round */
+  unsigned char state[64]; /* Keccak256Transcript::state */
+} b200_transcript;
+#define B200_SC_MAX_PENDING 1984
+/* device-resident running state of one sum-check (144 bytes, 16-byte aligned) */
+typedef struct b200_sc_state {
+  unsigned char claim[32];  /* running claim, Montgomery */
+  unsigned char q[32];      /* EqSumCheckInstance::eval_eq_left, Montgomery (1 for plain kinds) */
+  uint64_t round;           /* transcript round counter */
+  unsigned char tstate[64]; /* transcript state */
+  uint64_t rounds_done;
+} b200_sc_state;
+enum { B200_SC_ROUND_QUAD_PROD = 0, B200_SC_ROUND_CUBIC3_EQ = 1, B200_SC_ROUND_CUBIC3_EQ_M1 = 2 };
+/* One round of O(1) prover work, asynchronous on `stream`: reads the reduction results d_res
+ * (QUAD_PROD: [sum A_lo B_lo, sum dA dB]; CUBIC3_EQ: [t(0), t(inf)]; CUBIC3_EQ_M1 (tau == 0):
+ * [t(0), t(inf), t(-1)]), builds the round polynomial, absorbs its compressed coefficients under
+ * `absorb_label`, squeezes under `squeeze_label`, updates claim / q / transcript in *d_state, and
+ * writes the compressed coefficients (2 or 3 x 32 B canonical little-endian = the proof bytes,
+ * univariate.rs:177-190) to d_poly_out and the challenge (Montgomery) to d_r_out, where the bind
+ * kernels of the same round read it. */
+int b200_sc_round_dev(int field_id, int kind, void* d_state, const void* d_res, const void* d_tau,
+                      const void* d_tau_inv, const void* d_pending, size_t pending_len,
+                      int absorb_label, int squeeze_label, void* d_poly_out, void* d_r_out, void* stream);
+/* SumcheckProof::prove_quad_prod (sumcheck.rs:199-242) in one call.  d_A, d_B: device polynomials
+ * of 2^num_rounds elements, bound in place (element 0 holds the final evaluation afterwards).
+ * Host outputs: polys_out [num_rounds][2][32] canonical LE, r_out [num_rounds][32] Montgomery,
+ * finals_out [2][32] Montgomery; *tr is advanced as the reference's transcript would be. */
+int b200_sumcheck_quad_prod(int field_id, const void* claim, int num_rounds, void* d_A, void* d_B,
+                            b200_transcript* tr, const void* pending, size_t pending_len,
+                            void* polys_out, void* r_out, void* finals_out);
+/* SumcheckProof::prove_cubic_with_three_inputs (sumcheck.rs:446-507): sum_x eq(tau,x)(A B - C).
+ * taus: num_rounds host scalars (Montgomery); polys_out [num_rounds][3][32]; finals_out [3][32]. */
+int b200_sumcheck_cubic3(int field_id, const void* claim, const void* taus, int num_rounds, void* d_A,
+                         void* d_B, void* d_C, b200_transcript* tr, const void* pending,
+                         size_t pending_len, void* polys_out, void* r_out, void* finals_out);
 /* EqPolynomial::evals_from_points (spartan/polys/eq.rs:54-73): out has 2^ell entries */
 int b200_eq_table(int field_id, const void* r, int ell, void* out);
 int b200_eq_table_dev(int field_id, const void* r, int ell, void* out, void* stream);

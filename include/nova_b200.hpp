@@ -192,5 +192,51 @@ inline std::vector<Scalar> sumcheck_eval(int field, int form, const std::vector<
   return std::vector<Scalar>(out, out + n);
 }
 
+
+// ---- sum-check round loops with the transcript on the device ------------------
+// The serialisable part of Keccak256Transcript (keccak.rs:19-27): `round`, `state`, and the bytes
+// absorbed since the last squeeze (`transcript_buffer`).
+struct TranscriptState {
+  b200_transcript tr{};
+  std::vector<unsigned char> pending;
+};
+struct SumcheckProofOut {
+  std::vector<std::vector<Scalar>> compressed_polys;  // canonical little-endian (the proof bytes)
+  std::vector<Scalar> r;                              // challenges (Montgomery)
+  std::vector<Scalar> final_evals;                    // Montgomery
+};
+namespace detail {
+template <class Call>
+inline SumcheckProofOut device_loop(TranscriptState& t, int num_rounds, int ncoef, int nfinals, Call call,
+                                    const char* what) {
+  std::vector<Scalar> polys((size_t)num_rounds * ncoef), rs(num_rounds), fin(nfinals);
+  check(call(&t.tr, t.pending.empty() ? nullptr : t.pending.data(), t.pending.size(), polys.data(), rs.data(),
+             fin.data()), what);
+  t.pending.clear();
+  SumcheckProofOut out;
+  for (int j = 0; j < num_rounds; j++)
+    out.compressed_polys.emplace_back(polys.begin() + (size_t)j * ncoef, polys.begin() + (size_t)(j + 1) * ncoef);
+  out.r = std::move(rs);
+  out.final_evals = std::move(fin);
+  return out;
+}
+}  // namespace detail
+// SumcheckProof::prove_quad_prod (sumcheck.rs:199-242); d_A / d_B are device polynomials, bound in place
+inline SumcheckProofOut prove_quad_prod(int field, const Scalar& claim, int num_rounds, void* d_A, void* d_B,
+                                        TranscriptState& t) {
+  return detail::device_loop(t, num_rounds, 2, 2, [&](b200_transcript* tr, const void* p, size_t n, void* polys,
+                                                      void* rs, void* fin) {
+    return b200_sumcheck_quad_prod(field, &claim, num_rounds, d_A, d_B, tr, p, n, polys, rs, fin);
+  }, "b200_sumcheck_quad_prod");
+}
+// SumcheckProof::prove_cubic_with_three_inputs (sumcheck.rs:446-507)
+inline SumcheckProofOut prove_cubic_with_three_inputs(int field, const Scalar& claim, const std::vector<Scalar>& taus,
+                                                      void* d_A, void* d_B, void* d_C, TranscriptState& t) {
+  return detail::device_loop(t, (int)taus.size(), 3, 3, [&](b200_transcript* tr, const void* p, size_t n,
+                                                            void* polys, void* rs, void* fin) {
+    return b200_sumcheck_cubic3(field, &claim, taus.data(), (int)taus.size(), d_A, d_B, d_C, tr, p, n, polys, rs, fin);
+  }, "b200_sumcheck_cubic3");
+}
+
 }  // namespace b200
 }  // namespace nova

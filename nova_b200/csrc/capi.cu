@@ -15,6 +15,7 @@
 #include "msm_kernels.cuh"
 #include "ops.cuh"
 #include "poly_kernels.cuh"
+#include "transcript.cuh"
 
 using namespace nova;
 
@@ -1027,3 +1028,4 @@ int b200_bind_top(int fid, void* z, size_t n, const void* r) {
 }  // extern "C"
 
 #include "capi_poly.inc"
+#include "capi_sumcheck.inc"

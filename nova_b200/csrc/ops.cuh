@@ -64,6 +64,13 @@ struct field_ops {
   void (*spmv_t)(cudaStream_t, const uint32_t* tptr, const uint32_t* trow, const uint32_t* tperm,
                  const int8_t* codes, const void* vals, size_t cols, size_t out_len, const void* rx,
                  void* out);
+  // one sum-check round of O(1) prover algebra + Fiat-Shamir on the device (transcript.cuh):
+  // round polynomial from the reduction results, Keccak transcript absorb/squeeze, challenge,
+  // new claim / eq bound.  kind: sc_round_kind; state: b200_sc_state (144 B, device)
+  void (*sc_round)(cudaStream_t, int kind, void* state, const void* res, const void* tau,
+                   const void* tau_inv, const void* pending, uint32_t pending_len, int absorb_label,
+                   int squeeze_label, void* out_poly, void* out_r);
+  void (*fe_inv_each)(cudaStream_t, const void* in, size_t n, void* out);  // 0 -> 0
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
 constexpr size_t POLY_EVAL_SCRATCH_ELEMS = (size_t)3 * (1 + SC_MAX_BLOCKS + 256) + (size_t)3 * SC_MAX_BLOCKS;

@@ -4,6 +4,7 @@
 #include "msm_kernels.cuh"
 #include "field_kernels.cuh"
 #include "poly_kernels.cuh"
+#include "transcript.cuh"
 
 namespace nova {
 
@@ -281,11 +282,21 @@ struct ops_impl {
                      void* out) {
     k_spmv_t<F><<<stream_grid(out_len, 256), 256, 0, s>>>(tptr, trow, tperm, codes, vals, cols, out_len, rx, out);
   }
+  static void sc_round(cudaStream_t s, int kind, void* state, const void* res, const void* tau,
+                       const void* tau_inv, const void* pending, uint32_t pending_len, int absorb_label,
+                       int squeeze_label, void* out_poly, void* out_r) {
+    k_sc_round<F><<<1, 32, 0, s>>>(kind, (sc_state*)state, res, tau, tau_inv, (const uint8_t*)pending,
+                                   pending_len, (uint8_t)absorb_label, (uint8_t)squeeze_label, out_poly, out_r);
+  }
+  static void fe_inv_each(cudaStream_t s, const void* in, size_t n, void* out) {
+    if (n) k_fe_inv_each<F><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(in, n, out);
+  }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, vec_mul, logup_hash,
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
-                     sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t};
+                     sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
+                     sc_round, fe_inv_each};
   }
 };
 

@@ -68,6 +68,9 @@ SIGNATURES = {
     "b200_sc_eval": [c_int, c_int, _P, _P, _P, c_size_t, _P, c_size_t, _P, c_size_t, c_int, _P],
     "b200_sc_eval_dev": [c_int, c_int, _P, _P, _P, c_size_t, _P, _P, c_int, _P, _P],
     "b200_sc_eval_sharded_dev": [c_int, c_int, _P, _P, _P, c_size_t, _P, _P, c_int, c_size_t, c_size_t, _P, _P],
+    "b200_sc_round_dev": [c_int, c_int, _P, _P, _P, _P, _P, c_size_t, c_int, c_int, _P, _P, _P],
+    "b200_sumcheck_quad_prod": [c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _P, _P, _P],
+    "b200_sumcheck_cubic3": [c_int, _P, _P, c_int, _P, _P, _P, _P, _P, c_size_t, _P, _P, _P],
     "b200_eq_table": [c_int, _P, c_int, _P],
     "b200_eq_table_dev": [c_int, _P, c_int, _P, _P],
     "b200_mle_eval": [c_int, _P, c_int, _P, _P],

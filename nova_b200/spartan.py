@@ -456,6 +456,55 @@ class SumcheckProof:
         return polys, rs, finals
 
 
+    # ---- the same two loops with the transcript on the device --------------------
+    # One FFI call each: every round's reduction, round algebra + Keccak and binds are enqueued back
+    # to back (csrc/capi_sumcheck.inc); the host reads the proof once.  `transcript` is any object
+    # with the serialisable fields of Keccak256Transcript (keccak.rs:19-27): `round`, `state`
+    # (64 bytes) and `buf` (bytes absorbed since the last squeeze); it is advanced in place.
+    @staticmethod
+    def _device_loop(fid, transcript, call, num_rounds, ncoef, nfinals):
+        tr = (ctypes.c_ubyte * 72)()
+        ctypes.memmove(tr, int(transcript.round).to_bytes(8, "little") + bytes(transcript.state), 72)
+        pending = bytes(transcript.buf)
+        polys = ctypes.create_string_buffer(32 * ncoef * num_rounds)
+        rs = ctypes.create_string_buffer(32 * num_rounds)
+        finals = ctypes.create_string_buffer(32 * nfinals)
+        check(call(tr, _cbuf(pending) if pending else None, len(pending), polys, rs, finals))
+        raw = bytes(tr)
+        transcript.round = int.from_bytes(raw[:8], "little")
+        transcript.state = raw[8:72]
+        transcript.buf = b""
+        coeffs = [int.from_bytes(polys.raw[32 * i:32 * i + 32], "little") for i in range(ncoef * num_rounds)]
+        return ([coeffs[ncoef * j:ncoef * (j + 1)] for j in range(num_rounds)], fields.unpack(fid, rs.raw),
+                fields.unpack(fid, finals.raw))
+
+    @staticmethod
+    def prove_quad_prod_device(fid, claim, num_rounds, poly_A, poly_B, transcript):
+        """sumcheck.rs:199-242 through b200_sumcheck_quad_prod.  poly_A / poly_B: bytes (uploaded) or
+        DeviceVec (bound in place)."""
+        A = poly_A if isinstance(poly_A, DeviceVec) else DeviceVec.from_bytes(poly_A)
+        B = poly_B if isinstance(poly_B, DeviceVec) else DeviceVec.from_bytes(poly_B)
+        cl = _cbuf(fields.to_mont_bytes(fid, claim))
+        return SumcheckProof._device_loop(
+            fid, transcript,
+            lambda tr, pend, plen, polys, rs, fin: lib().b200_sumcheck_quad_prod(
+                fid, cl, num_rounds, A.ptr, B.ptr, tr, pend, plen, polys, rs, fin),
+            num_rounds, 2, 2)
+
+    @staticmethod
+    def prove_cubic_with_three_inputs_device(fid, claim, taus, poly_A, poly_B, poly_C, transcript):
+        """sumcheck.rs:446-507 through b200_sumcheck_cubic3 (eq tables, 1/tau and the tau = 0
+        fall-back are handled inside the library)."""
+        A, B, C = (x if isinstance(x, DeviceVec) else DeviceVec.from_bytes(x) for x in (poly_A, poly_B, poly_C))
+        cl = _cbuf(fields.to_mont_bytes(fid, claim))
+        tb = _cbuf(fields.pack(fid, taus))
+        return SumcheckProof._device_loop(
+            fid, transcript,
+            lambda tr, pend, plen, polys, rs, fin: lib().b200_sumcheck_cubic3(
+                fid, cl, tb, len(taus), A.ptr, B.ptr, C.ptr, tr, pend, plen, polys, rs, fin),
+            len(taus), 3, 3)
+
+
 # ---------------------------------------------------------------------------------------------
 # HyperKZG prover core (hyperkzg.rs:1076-1116 with the transcript challenges r, q given)
 # ---------------------------------------------------------------------------------------------

@@ -235,3 +235,80 @@ extern "C" int hc_coop(int fid, int mode, const void* pts, size_t n, void* out) 
   }
   return 0;
 }
+
+// ---- device-side Fiat-Shamir (transcript.cuh): the kernel body of k_sc_round, run sequentially ----
+#include "../../nova_b200/csrc/transcript.cuh"
+
+extern "C" int hc_keccak256(const void* data, size_t len, void* out32) {
+  if (len > MSG_MAX_BYTES) return 1;
+  static msg_buf m;
+  msg_reset(m);
+  msg_put_bytes(m, (const uint8_t*)data, (uint32_t)len);
+  uint64_t d[4];
+  keccak256_msg(m, 0, 0, d);
+  memcpy(out32, d, 32);
+  return 0;
+}
+
+template <class F>
+static void from_uniform_t(const void* in64, void* out) {
+  uint64_t w[8];
+  memcpy(w, in64, 64);
+  fe_t r = fe_from_uniform<F>(w);
+  memcpy(out, &r, 32);
+}
+extern "C" int hc_from_uniform(int fid, const void* in64, void* out) {
+  switch (fid) {
+    case 0: from_uniform_t<BN254_FR>(in64, out); break;
+    case 1: from_uniform_t<BN254_FQ>(in64, out); break;
+    case 2: from_uniform_t<PALLAS_FP>(in64, out); break;
+    case 3: from_uniform_t<PALLAS_FQ>(in64, out); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+template <class F>
+static void sc_round_t(int kind, sc_state* st, const fe_t* res, const fe_t* tau, const fe_t* tau_inv,
+                       const uint8_t* pending, uint32_t pending_len, uint8_t la, uint8_t ls, fe_t* out_poly,
+                       fe_t* out_r) {
+  static msg_buf msg;
+  fe_t r3[3] = {res[0], res[1], kind == SC_ROUND_CUBIC3_EQ_M1 ? res[2] : fe_zero<F>()};
+  fe_t t = fe_zero<F>(), ti = fe_zero<F>();
+  if (kind != SC_ROUND_QUAD_PROD) {
+    t = *tau;
+    if (kind == SC_ROUND_CUBIC3_EQ) ti = *tau_inv;
+  }
+  sc_round_poly poly;
+  sc_round_build<F>(kind, *st, r3, t, ti, poly);
+  fe_t canon[3];
+  int ncoef = sc_round_compressed<F>(poly, canon);
+  uint32_t flip = sc_round_message(msg, pending, pending_len, la, canon, ncoef, *st, ls);
+  for (int k = 0; k < ncoef; k++) out_poly[k] = canon[k];
+  uint64_t digest[8], d[4];
+  for (int lane = 0; lane < 2; lane++) {
+    keccak256_msg(msg, flip, (uint8_t)lane, d);
+    for (int i = 0; i < 4; i++) digest[4 * lane + i] = d[i];
+  }
+  *out_r = sc_round_finish<F>(kind, *st, poly, digest);
+}
+extern "C" int hc_sc_round(int fid, int kind, void* state144, const void* res, const void* tau, const void* tau_inv,
+                           const void* pending, uint32_t pending_len, int absorb_label, int squeeze_label,
+                           void* out_poly, void* out_r) {
+  static_assert(sizeof(sc_state) == 144, "b200_sc_state layout");
+  sc_state st;
+  memcpy(&st, state144, 144);
+#define RUN(FT) sc_round_t<FT>(kind, &st, (const fe_t*)res, (const fe_t*)tau, (const fe_t*)tau_inv, \
+                               (const uint8_t*)pending, pending_len, (uint8_t)absorb_label, (uint8_t)squeeze_label, \
+                               (fe_t*)out_poly, (fe_t*)out_r)
+  switch (fid) {
+    case 0: RUN(BN254_FR); break;
+    case 1: RUN(BN254_FQ); break;
+    case 2: RUN(PALLAS_FP); break;
+    case 3: RUN(PALLAS_FQ); break;
+    default: return 1;
+  }
+#undef RUN
+  memcpy(state144, &st, 144);
+  return 0;
+}
