@@ -186,6 +186,29 @@ int b200_sc_eval_dev(int field_id, int form, const void* A, const void* B, const
 int b200_sc_eval_sharded_dev(int field_id, int form, const void* A, const void* B, const void* C,
                              size_t local_len, const void* eq_left, const void* eq_right, int shift,
                              size_t id_mul, size_t id_add, void* out, void* stream);
+/* CommitmentKey::new's validation loop (provider/hyperkzg.rs:113-119: every G1 base and h must be on
+ * the curve, else NovaError::InvalidCommitmentKey), run on the device while the key is on its way
+ * to HBM anyway.  *first_bad = SIZE_MAX when all n points satisfy y^2 = x^3 + b (the identity
+ * encoding (0,0) passes, as halo2curves' is_on_curve does), else the smallest offending index. */
+int b200_ck_validate(int curve_id, const void* bases, size_t n, size_t* first_bad);
+
+/* ---- streamed witness hand-off ----------------------------------------------
+ * WitnessCS::alloc only appends to aux_assignment (frontend/util_cs/witness_cs.rs:93-103); the
+ * finished vector becomes R1CSWitness::new(shape, aux) and is committed (frontend/r1cs.rs:40-50,
+ * r1cs/mod.rs:869-871).  A witness stream lets the host push every finished prefix while synthesis
+ * is still running: the chunk's host->device copy and its share of the MSM's first stage (signed
+ * window digits + bucket histogram) run on a side stream; `finish` runs the remaining stages and
+ * returns commit(ck, W, r_W).  Chunks must stay valid and unmodified until `finish` returns (use
+ * b200_host_alloc memory for copies that really overlap).  A short assignment is zero-extended to
+ * n as R1CSWitness::new_with_blind does (r1cs/mod.rs:847-848); appending past n is B200_E_RANGE.
+ * After `finish`, *d_witness (optional) is the device-resident W (n scalars, valid until
+ * `release`) for the folds / SpMVs that follow. */
+int b200_witness_begin(uint64_t ck_handle, size_t n, uint64_t* stream_handle);
+int b200_witness_append(uint64_t stream_handle, const void* scalars, size_t count);
+int b200_witness_finish(uint64_t stream_handle, const void* r_or_null, void* out_jacobian,
+                        void** d_witness_or_null);
+int b200_witness_release(uint64_t stream_handle);
+
 /* ---- sum-check round loops with the transcript on the device ----------------
  * The reference interleaves, per round, an O(N) reduction, O(1) host algebra (UniPoly from the
  * evaluation points, univariate.rs:89-154; claim derivation / bound of EqSumCheckInstance,

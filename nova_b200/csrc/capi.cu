@@ -288,8 +288,10 @@ msm_plan make_plan(ck_ctx& ck, workspace& ws, size_t base_offset, size_t n) {
 
 // enqueue one full-width MSM on `s`; scalars and out are device pointers
 int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_scalars, size_t n,
-                void* d_out, cudaStream_t s, int small_elem_bytes = 0, bool blinded = false) {
+                void* d_out, cudaStream_t s, int small_elem_bytes = 0, bool blinded = false,
+                bool digits_done = false) {
   // blinded: d_scalars holds n-1 vector entries followed by r, whose base is h
+  // digits_done: ws.digits / ws.counts were already filled chunk by chunk (b200_witness_append)
   if (n == 0) {  // identity (msm.rs:228-230): z = 0
     CU(cudaMemsetAsync(d_out, 0, 96, s));
     return B200_OK;
@@ -299,7 +301,7 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
   msm_plan p = make_plan(ck, ws, base_offset, n);
   if (blinded) p.blind_i = n - 1;
   size_t K = (size_t)ck.G * ck.B;
-  CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
+  if (!digits_done) CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
   CU(cudaMemsetAsync(p.heavy, 0, 4, s));
   std::lock_guard<std::mutex> plk(g_prof.mu);
   const bool prof = g_prof.enabled;
@@ -316,7 +318,9 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
 #define STAGE_MARK(i) \
   if (prof) CU(cudaEventRecord(g_prof.ev[pset][i], s))
   STAGE_MARK(ST_DIGITS);
-  if (small_elem_bytes)
+  if (digits_done)
+    ;
+  else if (small_elem_bytes)
     msm_digits_small(s, d_scalars, small_elem_bytes, p);
   else
     sops->digits(s, d_scalars, p);
@@ -1029,3 +1033,4 @@ int b200_bind_top(int fid, void* z, size_t n, const void* r) {
 
 #include "capi_poly.inc"
 #include "capi_sumcheck.inc"
+#include "capi_stream.inc"

@@ -33,6 +33,25 @@ NOVA_HD xyzz_t xyzz_identity() {
 NOVA_HD bool xyzz_is_identity(const xyzz_t& p) { return fe_is_zero(p.zz); }
 NOVA_HD bool affine_is_identity(const affine_t& p) { return fe_is_zero(p.x) && fe_is_zero(p.y); }
 
+// y^2 == x^3 + b, or the identity encoding (0,0): halo2curves `is_on_curve`, the check
+// CommitmentKey::new applies to every base (src/provider/hyperkzg.rs:113-119).  The four curves
+// have small integer b (3, -17, 5, 5: bn256_grumpkin.rs:35-41,80-86; pasta.rs:33-47), passed as a
+// signed integer and converted here.
+template <class F>
+NOVA_HD fe_t fe_from_small_int(int v) {
+  fe_t a = fe_zero<F>();
+  a.l[0] = (uint32_t)(v < 0 ? -v : v);
+  a = fe_to_mont<F>(a);
+  return v < 0 ? fe_neg<F>(a) : a;
+}
+template <class F>
+NOVA_HD bool affine_on_curve(const affine_t& p, const fe_t& b_mont) {
+  if (affine_is_identity(p)) return true;
+  fe_t lhs = fe_sqr<F>(p.y);
+  fe_t rhs = fe_add<F>(fe_mul<F>(fe_sqr<F>(p.x), p.x), b_mont);
+  return fe_eq(lhs, rhs);
+}
+
 // dbl-2008-s-1 (a = 0): 2M + 5S.  Precondition: not identity, y != 0 is NOT required
 // (y == 0 gives zz3 = 0, i.e. the identity, which is the correct answer for a 2-torsion point).
 template <class F>

@@ -84,13 +84,15 @@ __device__ __forceinline__ void count_key(uint32_t* counts, uint32_t key) {
     atomicAdd(&counts[key], (uint32_t)__popc(peers));
 }
 
+// Processes scalars [i0, i1) of a vector of n (the digit array is [W][n]): a whole MSM passes
+// (0, n); the streamed witness hand-off (b200_witness_append) passes each chunk as it arrives.
 template <class S>
-__global__ void __launch_bounds__(256) k_digits(const void* __restrict__ scalars, size_t n, int c,
-                                                int W, int G, uint32_t B,
+__global__ void __launch_bounds__(256) k_digits(const void* __restrict__ scalars, size_t i0, size_t i1,
+                                                size_t n, int c, int W, int G, uint32_t B,
                                                 int32_t* __restrict__ digits,
                                                 uint32_t* __restrict__ counts) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;  // no early exit: the whole warp takes part in count_key
+  size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < i1;  // no early exit: the whole warp takes part in count_key
   fe_t s = live ? fe_from_mont<S>(fe_load(scalars, i)) : fe_zero<S>();
   // sign fold: use p - s when that is the smaller integer (msm.rs:1-8 "signed scalar
   // decomposition"); small negative witness values then cost one bucket add, not W.
@@ -720,6 +722,20 @@ __global__ void __launch_bounds__(128) k_expand_key(void* __restrict__ tables, s
     for (int d = 0; d < shift; d++) PA::dbl(q);
     p = PA::to_affine(q);
     PA::store_table(tables, (size_t)t * n_ck + i, p);
+  }
+}
+
+// Key validation (hyperkzg.rs:113-119): the smallest index of a base that is not on the curve is
+// left in *first_bad (initialised to 0xFFFFFFFF by the caller).  64 B read per point, 3 products.
+template <class F>
+__global__ void __launch_bounds__(256) k_on_curve(const void* __restrict__ pts, size_t n, int b_small,
+                                                  uint32_t* __restrict__ first_bad) {
+  const fe_t b = fe_from_small_int<F>(b_small);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    affine_t p;
+    p.x = fe_load(pts, 2 * i);
+    p.y = fe_load(pts, 2 * i + 1);
+    if (!affine_on_curve<F>(p, b)) atomicMin(first_bad, (uint32_t)i);
   }
 }
 

@@ -71,6 +71,10 @@ struct field_ops {
                    const void* tau_inv, const void* pending, uint32_t pending_len, int absorb_label,
                    int squeeze_label, void* out_poly, void* out_r);
   void (*fe_inv_each)(cudaStream_t, const void* in, size_t n, void* out);  // 0 -> 0
+  // digits + histogram of scalars [i0, i1) of a p.n-long vector (streamed witness hand-off)
+  void (*digits_range)(cudaStream_t, const void* scalars, size_t i0, size_t i1, const msm_plan&);
+  // key validation: *first_bad = min index of an off-curve base (caller presets 0xFFFFFFFF)
+  void (*on_curve)(cudaStream_t, const void* pts, size_t n, int b_small, uint32_t* first_bad);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
 constexpr size_t POLY_EVAL_SCRATCH_ELEMS = (size_t)3 * (1 + SC_MAX_BLOCKS + 256) + (size_t)3 * SC_MAX_BLOCKS;

@@ -37,9 +37,13 @@ __global__ void __launch_bounds__(128) k_sum_points1(const void* __restrict__ ta
 template <class F>
 struct ops_impl {
   static void digits(cudaStream_t s, const void* scalars, const msm_plan& p) {
+    digits_range(s, scalars, 0, p.n, p);
+  }
+  static void digits_range(cudaStream_t s, const void* scalars, size_t i0, size_t i1, const msm_plan& p) {
+    if (i1 <= i0) return;
     int block = 256;
-    int grid = (int)((p.n + block - 1) / block);
-    k_digits<F><<<grid, block, 0, s>>>(scalars, p.n, p.c, p.W, p.G, p.B, p.digits, p.counts);
+    int grid = (int)((i1 - i0 + block - 1) / block);
+    k_digits<F><<<grid, block, 0, s>>>(scalars, i0, i1, p.n, p.c, p.W, p.G, p.B, p.digits, p.counts);
   }
   static void expand_key(cudaStream_t s, void* tables, size_t n_ck, int ntables, int shift) {
     int block = 128;
@@ -291,12 +295,15 @@ struct ops_impl {
   static void fe_inv_each(cudaStream_t s, const void* in, size_t n, void* out) {
     if (n) k_fe_inv_each<F><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(in, n, out);
   }
+  static void on_curve(cudaStream_t s, const void* pts, size_t n, int b_small, uint32_t* first_bad) {
+    if (n) k_on_curve<F><<<stream_grid(n, 256), 256, 0, s>>>(pts, n, b_small, first_bad);
+  }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, vec_mul, logup_hash,
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
-                     sc_round, fe_inv_each};
+                     sc_round, fe_inv_each, digits_range, on_curve};
   }
 };
 

@@ -95,6 +95,15 @@ class CommitmentKey:
         self.handle = handle.value
         return self
 
+    @staticmethod
+    def validate(curve: "Curve", bases: bytes):
+        """CommitmentKey::new's on-curve loop (hyperkzg.rs:113-119) on the device: returns None if
+        every base is on the curve, else the index of the first one that is not
+        (-> NovaError::InvalidCommitmentKey in the Rust shim)."""
+        bad = c_size_t(0)
+        check(lib().b200_ck_validate(int(curve), _cbuf(bases), len(bases) // 64, ctypes.byref(bad)))
+        return None if bad.value == ctypes.c_size_t(-1).value else bad.value
+
     def __len__(self):
         return self.n
 
@@ -182,6 +191,46 @@ class CommitmentEngine:
 
     def commit_sparse_binary(self, ck: CommitmentKey, non_zero_indices):
         return self.group.batch_add(ck, non_zero_indices)
+
+
+class WitnessStream:
+    """Streamed witness hand-off: `append` every finished prefix of
+    `aux_assignment` while synthesis is still running (witness_cs.rs:93-103 only appends), then
+    `finish(r_W)` returns commit(ck, W, r_W) exactly as frontend/r1cs.rs:40-50 would.  The chunk
+    copies and the MSM's digit/histogram stage overlap with the host's work."""
+
+    def __init__(self, ck: CommitmentKey, num_vars: int):
+        self.ck, self.n = ck, num_vars
+        h = c_u64(0)
+        check(lib().b200_witness_begin(ck.handle, num_vars, ctypes.byref(h)))
+        self.handle = h.value
+        self._keep = []  # chunk buffers must outlive the asynchronous copies
+        self.d_witness = None
+
+    def append(self, scalars: bytes):
+        assert len(scalars) % 32 == 0
+        buf = _cbuf(scalars)
+        self._keep.append(buf)
+        check(lib().b200_witness_append(self.handle, buf, len(scalars) // 32))
+
+    def finish(self, r: bytes | None = None):
+        out = ctypes.create_string_buffer(96)
+        dw = ctypes.c_void_p()
+        check(lib().b200_witness_finish(self.handle, _cbuf(r) if r else None, out, ctypes.byref(dw)))
+        self._keep.clear()
+        self.d_witness = dw
+        return _jac_to_affine(self.ck.curve, out.raw)
+
+    def release(self):
+        if self.handle:
+            check(lib().b200_witness_release(self.handle))
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 # ---- R1CS witness field arithmetic ------------------------------------------------------------

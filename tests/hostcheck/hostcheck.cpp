@@ -312,3 +312,20 @@ extern "C" int hc_sc_round(int fid, int kind, void* state144, const void* res, c
   memcpy(state144, &st, 144);
   return 0;
 }
+
+// ---- key validation (curve.cuh affine_on_curve) ----
+template <class F>
+static void on_curve_t(int b_small, const affine_t* pts, size_t n, unsigned char* ok) {
+  fe_t b = fe_from_small_int<F>(b_small);
+  for (size_t i = 0; i < n; i++) ok[i] = affine_on_curve<F>(pts[i], b) ? 1 : 0;
+}
+extern "C" int hc_on_curve(int fid, int b_small, const void* pts, size_t n, void* ok) {
+  switch (fid) {
+    case 0: on_curve_t<BN254_FR>(b_small, (const affine_t*)pts, n, (unsigned char*)ok); break;
+    case 1: on_curve_t<BN254_FQ>(b_small, (const affine_t*)pts, n, (unsigned char*)ok); break;
+    case 2: on_curve_t<PALLAS_FP>(b_small, (const affine_t*)pts, n, (unsigned char*)ok); break;
+    case 3: on_curve_t<PALLAS_FQ>(b_small, (const affine_t*)pts, n, (unsigned char*)ok); break;
+    default: return 1;
+  }
+  return 0;
+}

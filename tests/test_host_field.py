@@ -100,3 +100,26 @@ def test_quad_cooperative_ops(hc, cid):
         out = ctypes.create_string_buffer(96)
         hc.hc_coop(c.base_field, 1, _buf(c.affine_bytes(pts[4])), ctypes.c_size_t(k), out)
         assert c.jacobian_from_bytes(out.raw) == c.mul(1 << k, pts[4])
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_on_curve_check(hc, cid):
+    """affine_on_curve (the device side of CommitmentKey::new's validation, hyperkzg.rs:113-119):
+    curve points and the identity encoding pass, any corrupted coordinate fails."""
+    c = CURVES[cid]
+    b_small = {0: 3, 1: -17, 2: 5, 3: 5}[cid]
+    assert c.b % c.p == b_small % c.p
+    pts = c.bases_arith(16)
+    good = [c.affine_bytes(P) for P in pts] + [bytes(64)]
+    bad = []
+    for P in pts[:6]:
+        bad.append(c.affine_bytes((P[0], (P[1] + 1) % c.p)))
+        bad.append(c.affine_bytes(((P[0] + 1) % c.p, P[1])))
+    bad.append(c.affine_bytes((0, 1)))
+    data = b"".join(good + bad)
+    ok = ctypes.create_string_buffer(len(good) + len(bad))
+    assert hc.hc_on_curve(c.base_field, b_small, _buf(data), ctypes.c_size_t(len(good) + len(bad)), ok) == 0
+    flags = list(ok.raw)
+    assert flags[:len(good)] == [1] * len(good)
+    exp_bad = [1 if c.on_curve(c.affine_from_bytes(x)) else 0 for x in bad]
+    assert flags[len(good):] == exp_bad and sum(exp_bad) == 0

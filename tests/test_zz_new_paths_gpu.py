@@ -7,6 +7,9 @@ committed, so this file sorts LAST: with `pytest -x` a failure here cannot hide 
 * sum-check round loops with the Keccak transcript on the device (b200_sumcheck_quad_prod,
   b200_sumcheck_cubic3, b200_sc_round_dev): every prover message, challenge, final evaluation and the
   transcript state afterwards must equal the oracle's (sumcheck.rs:199-242, 446-507).
+* streamed witness hand-off (b200_witness_begin / append / finish): the commitment of a witness
+  pushed in ragged chunks equals commit(ck, W, r_W) of the whole vector and the oracle's MSM.
+* key validation (b200_ck_validate): the on-curve loop of CommitmentKey::new (hyperkzg.rs:113-119).
 """
 import pytest
 
@@ -103,3 +106,104 @@ def test_pending_limit_is_an_error(sp):
     t.absorb_bytes(b"big", bytes(4000))
     with pytest.raises(B200Error):
         sp.SumcheckProof.prove_quad_prod_device(fid, 1, 1, pack(p, [1, 2]), pack(p, [3, 4]), t)
+
+
+# ------------------------------------------------------------------ streamed witness hand-off ----
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,chunks", [(1, [1]), (37, [37]), (1000, [1, 2, 997]), (5000, [2500, 2500]),
+                                       (70001, [4096] * 17 + [369])])
+def test_witness_stream_commit_equals_whole_commit(b200, oracle, cid, n, chunks):
+    from oracle.pyref import CURVES
+    c = CURVES[cid]
+    bases = oracle.gen_bases(cid, n + 1)
+    ck = b200.CommitmentKey(b200.Curve(cid), bases[:64 * n], bases[64 * n:])
+    v = oracle.gen_scalars(c.scalar_field, 900 + n, n)
+    r = oracle.gen_scalars(c.scalar_field, 901, 1)
+    exp = c.affine_from_bytes(oracle.msm(cid, v + r, bases))
+    assert sum(chunks) == n
+    ws = b200.WitnessStream(ck, n)
+    off = 0
+    for k in chunks:
+        ws.append(v[32 * off:32 * (off + k)])
+        off += k
+    assert ws.finish(r) == exp
+    assert ws.d_witness  # resident W is handed back
+    from nova_b200.native import check, lib
+    import ctypes
+    back = ctypes.create_string_buffer(32 * n)
+    check(lib().b200_memcpy_d2h(back, ws.d_witness, 32 * n))
+    assert back.raw == v
+    ws.release()
+    assert b200.CommitmentEngine(cid).commit(ck, v, r) == exp  # the key's own workspace is untouched
+    # no blind: r = 0
+    ws = b200.WitnessStream(ck, n)
+    ws.append(v)
+    assert ws.finish(None) == c.affine_from_bytes(oracle.msm(cid, v, bases[:64 * n]))
+    ws.release()
+    ck.release()
+
+
+def test_witness_stream_zero_extends_and_rejects_overflow(b200, oracle):
+    """R1CSWitness::new_with_blind resizes the assignment to num_vars with zeros (r1cs/mod.rs:847-848)."""
+    from oracle.pyref import CURVES
+    from nova_b200.native import B200Error
+    cid, n = 0, 3000
+    c = CURVES[cid]
+    bases = oracle.gen_bases(cid, n)
+    ck = b200.CommitmentKey(b200.Curve(cid), bases)
+    v = oracle.gen_scalars(c.scalar_field, 33, 2000)
+    ws = b200.WitnessStream(ck, n)
+    ws.append(v[:32 * 1500])
+    ws.append(v[32 * 1500:])
+    with pytest.raises(B200Error):
+        ws.append(oracle.gen_scalars(c.scalar_field, 34, 1001))
+    assert ws.finish(None) == c.affine_from_bytes(oracle.msm(cid, v, bases[:64 * 2000]))
+    with pytest.raises(B200Error):
+        ws.finish(None)
+    ws.release()
+    with pytest.raises(B200Error):
+        b200.WitnessStream(ck, n + 1)
+    ck.release()
+
+
+def test_witness_stream_sparse_bits_witness(b200, oracle):
+    """A sha256-like witness: mostly 0/1 with a few full-width values, pushed in 8 chunks, on a key
+    large enough for the wide-window tables (2^19 -> 17-bit windows)."""
+    from oracle.pyref import CURVES, mont_bytes as mb
+    cid, n = 0, 1 << 19
+    c = CURVES[cid]
+    ck = b200.CommitmentKey.setup_synthetic(b200.Curve(cid), n)
+    rng = SplitMix64(4242)
+    one, zero = mb(c.q, 1), bytes(32)
+    parts = []
+    for i in range(n):
+        x = rng.next()
+        parts.append(mb(c.q, rng.field(c.q)) if x % 64 == 0 else (one if x & 1 else zero))
+    v = b"".join(parts)
+    ws = b200.WitnessStream(ck, n)
+    step = n // 8
+    for k in range(8):
+        ws.append(v[32 * k * step:32 * (k + 1) * step])
+    got = ws.finish(None)
+    ws.release()
+    assert got == b200.CommitmentEngine(cid).commit(ck, v, None)
+    # closed form against the synthetic key P_i = (k0 + i) G:  sum s_i (k0 + i) G
+    assert got == c.mul(oracle.dot_index(c.scalar_field, v), c.gen)
+    ck.release()
+
+
+# ------------------------------------------------------------------ key validation ---------------
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_ck_validate(b200, oracle, cid):
+    from oracle.pyref import CURVES
+    c = CURVES[cid]
+    n = 5000
+    bases = bytearray(oracle.gen_bases(cid, n))
+    assert b200.CommitmentKey.validate(b200.Curve(cid), bytes(bases)) is None
+    bases[64 * 77:64 * 78] = bytes(64)  # the identity encoding is accepted (halo2curves is_on_curve)
+    assert b200.CommitmentKey.validate(b200.Curve(cid), bytes(bases)) is None
+    x, y = c.affine_from_bytes(bytes(bases[64 * 4321:64 * 4322]))
+    bases[64 * 4321:64 * 4322] = c.affine_bytes((x, (y + 1) % c.p))
+    assert b200.CommitmentKey.validate(b200.Curve(cid), bytes(bases)) == 4321
+    bases[64 * 123:64 * 124] = c.affine_bytes(((x + 1) % c.p, y))
+    assert b200.CommitmentKey.validate(b200.Curve(cid), bytes(bases)) == 123
