@@ -207,6 +207,8 @@ int b200_witness_begin(uint64_t ck_handle, size_t n, uint64_t* stream_handle);
 int b200_witness_append(uint64_t stream_handle, const void* scalars, size_t count);
 int b200_witness_finish(uint64_t stream_handle, const void* r_or_null, void* out_jacobian,
                         void** d_witness_or_null);
+/* re-arm for the next witness of the same length (one per prove_step): keeps the workspace */
+int b200_witness_reset(uint64_t stream_handle);
 int b200_witness_release(uint64_t stream_handle);
 
 /* ---- sum-check round loops with the transcript on the device ----------------

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200_witness_begin": [c_u64, c_size_t, ctypes.POINTER(c_u64)],
     "b200_witness_append": [c_u64, _P, c_size_t],
     "b200_witness_finish": [c_u64, _P, _P, ctypes.POINTER(_P)],
+    "b200_witness_reset": [c_u64],
     "b200_witness_release": [c_u64],
     "b200_sc_round_dev": [c_int, c_int, _P, _P, _P, _P, _P, c_size_t, c_int, c_int, _P, _P, _P],
     "b200_sumcheck_quad_prod": [c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _P, _P, _P],

@@ -221,6 +221,12 @@ class WitnessStream:
         self.d_witness = dw
         return _jac_to_affine(self.ck.curve, out.raw)
 
+    def reset(self):
+        """Re-arm for the next step's witness (same num_vars); keeps the device workspace."""
+        check(lib().b200_witness_reset(self.handle))
+        self._keep.clear()
+        self.d_witness = None
+
     def release(self):
         if self.handle:
             check(lib().b200_witness_release(self.handle))

@@ -1,8 +1,9 @@
-"""GPU parity of the entry points added after this round's GPU budget was spent.
+"""GPU parity of the entry points added late in round 1.
 
-Their device code was validated on the CPU through the host build of the same headers
-(tests/test_host_transcript.py, tests/test_host_field.py) but had not run on a B200 when it was
-committed, so this file sorts LAST: with `pytest -x` a failure here cannot hide the rest of the suite.
+Their device code is also validated on the CPU through the host build of the same headers
+(tests/test_host_transcript.py, tests/test_host_field.py).  First run on a B200: 60 passed in 10 s
+(profiles/r01s_new_paths_pytest.log); the tests below the "added after that run" marker have not run
+on a GPU yet, which is why this file sorts LAST: with `pytest -x` a failure here cannot hide the rest.
 
 * sum-check round loops with the Keccak transcript on the device (b200_sumcheck_quad_prod,
   b200_sumcheck_cubic3, b200_sc_round_dev): every prover message, challenge, final evaluation and the
@@ -207,3 +208,24 @@ def test_ck_validate(b200, oracle, cid):
     assert b200.CommitmentKey.validate(b200.Curve(cid), bytes(bases)) == 4321
     bases[64 * 123:64 * 124] = c.affine_bytes(((x + 1) % c.p, y))
     assert b200.CommitmentKey.validate(b200.Curve(cid), bytes(bases)) == 123
+
+
+# ================================================================== added after that run =========
+def test_witness_stream_reset_reuse(b200, oracle):
+    """One stream object serves successive prove_steps (b200_witness_reset keeps the workspace)."""
+    from oracle.pyref import CURVES
+    cid, n = 0, 9000
+    c = CURVES[cid]
+    bases = oracle.gen_bases(cid, n + 1)
+    ck = b200.CommitmentKey(b200.Curve(cid), bases[:64 * n], bases[64 * n:])
+    ws = b200.WitnessStream(ck, n)
+    for step in range(3):
+        v = oracle.gen_scalars(c.scalar_field, 40 + step, n)
+        r = oracle.gen_scalars(c.scalar_field, 50 + step, 1) if step != 1 else None
+        for off in range(0, n, 2048):
+            ws.append(v[32 * off:32 * min(off + 2048, n)])
+        exp = c.affine_from_bytes(oracle.msm(cid, v + r, bases) if r else oracle.msm(cid, v, bases[:64 * n]))
+        assert ws.finish(r) == exp, step
+        ws.reset()
+    ws.release()
+    ck.release()
