@@ -329,3 +329,19 @@ extern "C" int hc_on_curve(int fid, int b_small, const void* pts, size_t n, void
   }
   return 0;
 }
+
+// ---- sum of two products with one reduction (field.cuh fe_mul2_add) ----
+template <class F>
+static void mul2_t(const fe_t* a, const fe_t* b, const fe_t* c, const fe_t* d, fe_t* r, size_t n) {
+  for (size_t i = 0; i < n; i++) r[i] = fe_mul2_add<F>(a[i], b[i], c[i], d[i]);
+}
+extern "C" int hc_mul2_add(int fid, const void* a, const void* b, const void* c, const void* d, void* r, size_t n) {
+  switch (fid) {
+    case 0: mul2_t<BN254_FR>((const fe_t*)a, (const fe_t*)b, (const fe_t*)c, (const fe_t*)d, (fe_t*)r, n); break;
+    case 1: mul2_t<BN254_FQ>((const fe_t*)a, (const fe_t*)b, (const fe_t*)c, (const fe_t*)d, (fe_t*)r, n); break;
+    case 2: mul2_t<PALLAS_FP>((const fe_t*)a, (const fe_t*)b, (const fe_t*)c, (const fe_t*)d, (fe_t*)r, n); break;
+    case 3: mul2_t<PALLAS_FQ>((const fe_t*)a, (const fe_t*)b, (const fe_t*)c, (const fe_t*)d, (fe_t*)r, n); break;
+    default: return 1;
+  }
+  return 0;
+}

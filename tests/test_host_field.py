@@ -58,8 +58,40 @@ def test_field_ops(hc, fid):
     assert out2.raw == raw
 
 
+@pytest.fixture(scope="module")
+def hc_y3():
+    """The same host build with the fused-y3 mixed addition the A/B kernel variant uses
+    (-DNOVA_MADD_FUSED_Y3: y3 through fe_mul2_add)."""
+    src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+    so = os.path.join(HERE, "hostcheck", "libhostcheck_y3.so")
+    csrc = os.path.join(HERE, "..", "nova_b200", "csrc")
+    hdrs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-DNOVA_MADD_FUSED_Y3", "-x", "c++",
+                               src, "-o", so])
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_xyzz_formulas_fused_y3(hc_y3, cid):
+    _xyzz_formulas(hc_y3, cid)
+    # a long random walk of mixed additions: 3000 points, compared with the affine group law
+    c = CURVES[cid]
+    pts = c.bases_arith(3000, k0=0x1234 + cid)
+    exp = None
+    for P in pts:
+        exp = c.add(exp, P)
+    out = ctypes.create_string_buffer(96)
+    hc_y3.hc_pt_sum(c.base_field, 0, _buf(b"".join(c.affine_bytes(P) for P in pts)), ctypes.c_size_t(len(pts)), out)
+    assert c.jacobian_from_bytes(out.raw) == exp
+
+
 @pytest.mark.parametrize("cid", [0, 1, 2, 3])
 def test_xyzz_formulas(hc, cid):
+    _xyzz_formulas(hc, cid)
+
+
+def _xyzz_formulas(hc, cid):
     """madd / add / dbl incl. the exceptional cases of msm.rs:92-113,130-155."""
     c = CURVES[cid]
     pts = c.bases_arith(20)
@@ -123,3 +155,23 @@ def test_on_curve_check(hc, cid):
     assert flags[:len(good)] == [1] * len(good)
     exp_bad = [1 if c.on_curve(c.affine_from_bytes(x)) else 0 for x in bad]
     assert flags[len(good):] == exp_bad and sum(exp_bad) == 0
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_sum_of_two_products_single_reduction(hc, fid):
+    """fe_mul2_add(a, b, c, d) == a*b + c*d (one Montgomery reduction for both products), incl. the
+    extreme operands p-1 that maximise every intermediate carry count."""
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(40 + fid)
+    edge = [0, 1, p - 1, p - 2, (1 << 256) % p, (p - (1 << 256) % p) % p, (1 << 255) % p, (1 << 128) - 1]
+    quads = list(itertools.product(edge, repeat=4)) + [tuple(rng.field(p) for _ in range(4)) for _ in range(4000)]
+    # Montgomery-form limbs that are all-ones-ish: values whose REPRESENTATION is p-1 (largest limbs)
+    big = from_mont(p, p - 1)
+    quads += [(big, big, big, big), (big, big, 0, 0), (0, 0, big, big)]
+    cols = [b"".join(mont_bytes(p, q[k]) for q in quads) for k in range(4)]
+    n = len(quads)
+    out = ctypes.create_string_buffer(32 * n)
+    assert hc.hc_mul2_add(fid, _buf(cols[0]), _buf(cols[1]), _buf(cols[2]), _buf(cols[3]), out, ctypes.c_size_t(n)) == 0
+    for i, (a, b, c, d) in enumerate(quads):
+        got = int.from_bytes(out.raw[32 * i:32 * i + 32], "little")
+        assert got < p and from_mont(p, got) == (a * b + c * d) % p, (a, b, c, d)
