@@ -399,7 +399,7 @@ def cpu_reference_run(log2n, steps, warmup, sc_np=None):
     for _ in range(steps):
         co.msm(CURVE, sc, bases, cores)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": round(dt * 1e3, 3),
             "sample": f"first 2^{n.bit_length() - 1} of the 2^{log2n} pairs, {steps} run(s), {dt * 1e3:.1f} ms each",
             "note": "C restatement of msm.rs (signed split + bit-width partition; halo2curves msm_best "
                     "restated as signed-digit Pippenger, c = ln(n)+2, (window x slice) jobs over all "
@@ -414,7 +414,7 @@ def run_reference(args):
     n_sample = cb["sample"]
     out = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64 limbs (256-bit prime-field / curve integers)",
         "data": "synthetic",
         "config": {"workload": f"BN254 G1 Pippenger MSM, 2^{args.log2n} uniform scalars, resident key "
