@@ -373,10 +373,18 @@ class SumcheckProof:
         k = len(claims)
         assert len(num_rounds) == k and len(polys) == k and len(eq_points) == k and len(coeffs) == k
         for i in range(k):
-            assert len(polys[i]) == 32 << num_rounds[i], f"poly size mismatch at index {i}"
+            if not isinstance(polys[i], DeviceVec):
+                assert len(polys[i]) == 32 << num_rounds[i], f"poly size mismatch at index {i}"
             assert len(eq_points[i]) == num_rounds[i], f"eq_point length mismatch at index {i}"
         nmax = max(num_rounds)
-        dev = [DeviceVec.from_bytes(P) for P in polys]
+
+        def working_copy(P, n):  # the loop binds in place; resident inputs are copied device-to-device
+            if not isinstance(P, DeviceVec):
+                return DeviceVec.from_bytes(P)
+            v = DeviceVec(32 * n)
+            check(lib().b200_memcpy_d2d(v.ptr, P.ptr, 32 * n, None))
+            return v
+        dev = [working_copy(P, 1 << nr) for P, nr in zip(polys, num_rounds)]
         lens = [1 << nr for nr in num_rounds]
         eqs = [EqSumCheckInstance(fid, pts) for pts in eq_points]
         running = list(claims)
