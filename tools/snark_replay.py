@@ -1,0 +1,120 @@
+#!/usr/bin/env python3
+"""Replay of spartan::snark::RelaxedR1CSSNARK::prove (snark.rs:113-256) + the HyperKZG evaluation argument
+at benchmark scale (BASELINE.json configs[3]: "HyperKZG CompressedSNARK prove, 2^22 witness"): the primary
+half of CompressedSNARK::prove (nova/mod.rs:862-881) on a synthetic regular R1CS shape, timed per phase
+on one B200, with the two sum-check loops either on the per-round host transcript or as one call each
+with the transcript on the device.
+
+    python tools/snark_replay.py [--log2cons 20] [--reps 2] [--host-transcript]
+
+Not included: circuit synthesis, the secondary (Grumpkin / IPA) half, the pairing-side verifier.
+Challenges come from a BLAKE2b stand-in on the host side (timing replay; bit-exactness with the Keccak
+transcript is covered by tests/test_zz_new_paths_gpu.py at small sizes).
+"""
+import argparse
+import ctypes
+import hashlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+from tools.ppsnark_replay import synth_matrix  # noqa: E402
+
+
+class ReplayTranscript:
+    """Has the serialisable fields of Keccak256Transcript (round, state[64], buf) so that the device
+    loops can continue it; host-side squeezes use BLAKE2b (timing only)."""
+
+    def __init__(self, p):
+        self.p, self.round, self.state, self.buf = p, 0, bytes(64), b""
+
+    def absorb_bytes(self, label, b):
+        self.buf += label + b
+
+    def squeeze(self, label):
+        out = hashlib.blake2b(self.buf + b"NoDS" + self.round.to_bytes(8, "little") + self.state + label).digest()
+        self.round, self.state, self.buf = self.round + 1, out, b""
+        return int.from_bytes(out, "little") % self.p
+
+
+def run(log2cons=20, reps=2, device_transcript=True, seed=7):
+    import nova_b200 as nb
+    from nova_b200 import fields, ppsnark as dp, snark as ds, spartan as sp
+    from nova_b200.native import check, lib
+    L = lib()
+    check(L.b200_init(0))
+    curve = nb.Curve(0)
+    fid = curve.scalar_field
+    p = fields.MODULUS[fid]
+    rng = np.random.default_rng(seed)
+    m = 1 << log2cons
+    num_cons = num_vars = m
+    num_io = 2
+    ncols = num_vars + 1 + num_io
+    table = np.frombuffer(b"".join(fields.to_mont_bytes(fid, v) for v in (1, p - 1, 2)), dtype=np.uint64).reshape(3, 4)
+    mats = {}
+    t0 = time.time()
+    for name, extra in (("A", 0.6), ("B", 0.3), ("C", 0.1)):
+        _, idx, ptr, codes = synth_matrix(rng, num_cons, ncols, extra)
+        v = np.ascontiguousarray(table[codes])
+        h = ctypes.c_uint64(0)
+        check(L.b200_spmv_register(fid, v.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                   ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), num_cons, ncols, ctypes.byref(h)))
+        mm = sp.SparseMatrix.__new__(sp.SparseMatrix)
+        mm.fid, mm.rows, mm.cols, mm.handle = fid, num_cons, ncols, h.value
+        mats[name] = mm
+    ck = nb.CommitmentKey.setup_synthetic(curve, m)
+    wide = rng.integers(0, 1 << 62, size=(num_vars, 4), dtype=np.uint64)
+    wide[:, 3] &= np.uint64((1 << 60) - 1)
+    Wd = sp.DeviceVec(32 * num_vars)
+    check(L.b200_memcpy_h2d(Wd.ptr, wide.ctypes.data_as(ctypes.c_void_p), 32 * num_vars))
+    u = int(rng.integers(1, 1 << 62))
+    X = [int(rng.integers(1, 1 << 62)) for _ in range(num_io)]
+    z = sp.DeviceVec(32 * ncols)
+    check(L.b200_memcpy_d2d(z.ptr, Wd.ptr, 32 * num_vars, None))
+    tail = fields.pack(fid, [u] + X)
+    check(L.b200_memcpy_h2d(dp.View(z, num_vars).ptr, ctypes.create_string_buffer(tail, len(tail)), len(tail)))
+    Az, Bz, Cz = (sp.DeviceVec(32 * num_cons) for _ in range(3))
+    for name, out in (("A", Az), ("B", Bz), ("C", Cz)):
+        check(L.b200_spmv_dev(mats[name].handle, z.ptr, None, out.ptr, None, None))
+    Ed = sp.DeviceVec(32 * num_cons)  # E = Az o Bz - u Cz: a satisfied relaxed instance
+    zero = dp.dev_zeros(num_cons)
+    check(L.b200_cross_term_dev(fid, Az.ptr, Bz.ptr, Cz.ptr, zero.ptr, None, dp.dev_scalar(fid, u).ptr, num_cons, Ed.ptr, None))
+    check(L.b200_sync())
+    U = dict(comm_W=dp.commit_dev(curve, ck, Wd, num_vars), comm_E=dp.commit_dev(curve, ck, Ed, num_cons), u=u, X=X)
+    S = dict(num_cons=num_cons, num_vars=num_vars, **mats)
+    setup_s = time.time() - t0
+    runs = []
+    for rep in range(reps + 1):
+        tm = {}
+        tr = ReplayTranscript(p)
+        t1 = time.perf_counter()
+        out = ds.prove_core(curve, ck, S, U, dict(W=Wd, E=Ed), 1, tr, device_transcript=device_transcript, timings=tm)
+        t2 = time.perf_counter()
+        r, q = tr.squeeze(b"r"), tr.squeeze(b"q")
+        sp.hyperkzg_prove_resident(curve, ck, out["batched_poly"], out["batched_x"], r, q)
+        check(L.b200_sync())
+        tm["hyperkzg_prove"] = time.perf_counter() - t2
+        tm["total"] = time.perf_counter() - t1
+        if rep:
+            runs.append(tm)
+        del out
+    best = min(runs, key=lambda t: t["total"])
+    return {"workload": "spartan::snark prove_core + HyperKZG prove replay, synthetic regular shape, BN254",
+            "num_cons": num_cons, "num_vars": num_vars, "device_transcript": device_transcript,
+            "setup_s": round(setup_s, 2), "reps": reps, "ms": {k: round(v * 1e3, 3) for k, v in best.items()},
+            "excluded": "circuit synthesis, secondary-curve half, verifier; BLAKE2b stand-in for host squeezes"}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log2cons", type=int, default=20)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--host-transcript", action="store_true")
+    a = ap.parse_args()
+    print(json.dumps(run(a.log2cons, a.reps, not a.host_transcript)))
