@@ -1,0 +1,163 @@
+"""A CPU stand-in for libnova_b200.so, for testing the HOST LOGIC of the Python mirror without a GPU.
+
+TEST INFRASTRUCTURE ONLY.  "Device memory" is host memory, and every `*_dev` entry point the mirror's
+composed provers call is answered by the C oracle on the bytes behind the pointers.  Installing it
+(`install()`, undone by `uninstall()`) makes `nova_b200.native.lib()` return this object, so the very
+same mirror code that drives the GPU (nova_b200/snark.py, spartan.py, ...) runs here and its glue --
+buffer sizes, offsets, argument order, transcript labels, claim bookkeeping -- is checked against the
+independent Python restatements.  It proves nothing about the CUDA kernels; the `-m gpu` tests do that.
+
+Only the subset the CPU tests need is implemented; anything else raises AttributeError loudly.
+"""
+import ctypes
+
+from oracle import coracle as co
+from oracle.pyref import CURVES, mont_bytes
+
+
+def _addr(x) -> int:
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if isinstance(x, ctypes.c_void_p):
+        return x.value or 0
+    if hasattr(x, "_obj"):  # ctypes.byref(obj)
+        return ctypes.addressof(x._obj)
+    return ctypes.addressof(x)
+
+
+def _rd(x, nbytes: int) -> bytes:
+    return ctypes.string_at(_addr(x), nbytes) if nbytes else b""
+
+
+def _wr(x, data: bytes):
+    if data:
+        ctypes.memmove(_addr(x), data, len(data))
+
+
+class EmulatedDevice:
+    def __init__(self):
+        self.allocs = {}    # address -> buffer (keeps it alive), gives sizes of whole allocations
+        self.mats = {}      # handle -> (fid, data, indices, indptr, rows, cols)
+        self.next_handle = 1
+        self.err = b""
+
+    # ---- library / memory ---------------------------------------------------------------------
+    def b200_init(self, device):
+        return 0
+
+    def b200_last_error(self):
+        return self.err
+
+    def b200_sync(self):
+        return 0
+
+    def b200_dev_alloc(self, nbytes, out_ptr):
+        buf = ctypes.create_string_buffer(max(int(nbytes), 1))
+        a = ctypes.addressof(buf)
+        self.allocs[a] = buf
+        out_ptr._obj.value = a
+        return 0
+
+    def b200_dev_free(self, p):
+        self.allocs.pop(_addr(p), None)
+        return 0
+
+    def b200_memcpy_h2d(self, d, h, n):
+        _wr(d, _rd(h, n))
+        return 0
+
+    def b200_memcpy_d2h(self, h, d, n):
+        _wr(h, _rd(d, n))
+        return 0
+
+    def b200_memcpy_d2d(self, dst, src, n, stream):
+        _wr(dst, _rd(src, n))
+        return 0
+
+    def b200_memset_dev(self, d, byte, n, stream):
+        _wr(d, bytes([byte]) * n)
+        return 0
+
+    def _size(self, p) -> int:
+        return len(self.allocs[_addr(p)])
+
+    # ---- field vectors ------------------------------------------------------------------------
+    def b200_axpy_dev(self, fid, a, b, r, n, out, stream):
+        _wr(out, co.axpy(fid, _rd(a, 32 * n), _rd(b, 32 * n), _rd(r, 32)))
+        return 0
+
+    def b200_bind_top_dev(self, fid, z, n, r, stream):
+        _wr(z, co.bind_top(fid, _rd(z, 32 * n), _rd(r, 32)))
+        return 0
+
+    def b200_sc_eval_dev(self, fid, form, A, B, C, length, eq_left, eq_right, shift, out, stream):
+        g = lambda p: _rd(p, 32 * length) if _addr(p) else None
+        tab = lambda p: _rd(p, self._size(p)) if _addr(p) else None
+        _wr(out, co.sc_eval(fid, form, g(A), g(B), g(C), tab(eq_left), tab(eq_right), shift))
+        return 0
+
+    def b200_eq_table_dev(self, fid, r, ell, out, stream):
+        _wr(out, co.eq_table(fid, _rd(r, 32 * ell)))
+        return 0
+
+    def b200_mle_eval_dev(self, fid, Z, ell, r, out, stream):
+        _wr(out, co.mle_eval(fid, _rd(Z, 32 << ell), _rd(r, 32 * ell)))
+        return 0
+
+    def b200_rlc_dev(self, fid, ptrs, lens, k, coeffs, n, out, stream):
+        polys = [_rd(ptrs[i], 32 * lens[i]) for i in range(k)]
+        _wr(out, co.rlc(fid, polys, _rd(coeffs, 32 * k), n))
+        return 0
+
+    # ---- sparse matrices ----------------------------------------------------------------------
+    def b200_spmv_register(self, fid, data, indices, indptr, rows, cols, out_handle):
+        ip = [int(indptr[i]) for i in range(rows + 1)]
+        nnz = ip[-1]
+        self.mats[self.next_handle] = (fid, _rd(data, 32 * nnz), [int(indices[i]) for i in range(nnz)], ip, rows, cols)
+        out_handle._obj.value = self.next_handle
+        self.next_handle += 1
+        return 0
+
+    def b200_spmv_release(self, handle):
+        self.mats.pop(handle, None)
+        return 0
+
+    def b200_spmv_dev(self, handle, z1, z2, o1, o2, stream):
+        fid, data, idx, ip, rows, cols = self.mats[handle]
+        _wr(o1, co.spmv(fid, data, idx, ip, _rd(z1, 32 * cols)))
+        if _addr(z2):
+            _wr(o2, co.spmv(fid, data, idx, ip, _rd(z2, 32 * cols)))
+        return 0
+
+    def b200_spmv_t_dev(self, handle, rx, out_len, out, stream):
+        fid, data, idx, ip, rows, cols = self.mats[handle]
+        _wr(out, co.spmv_t(fid, data, idx, ip, _rd(rx, 32 * rows), out_len))
+        return 0
+
+    # ---- group --------------------------------------------------------------------------------
+    def b200_msm_adhoc(self, curve_id, bases, scalars, n, out):
+        c = CURVES[curve_id]
+        aff = co.msm(curve_id, _rd(scalars, 32 * n), _rd(bases, 64 * n))
+        z = bytes(32) if aff == bytes(64) else mont_bytes(c.p, 1)
+        _wr(out, aff + z)  # Jacobian (x, y, 1) or the identity (z = 0)
+        return 0
+
+
+_saved = []
+
+
+def install() -> EmulatedDevice:
+    import nova_b200.native as native
+    dev = EmulatedDevice()
+    _saved.append(native._LIB)
+    native._LIB = dev
+    return dev
+
+
+def uninstall():
+    import nova_b200.native as native
+    from nova_b200 import spartan
+    spartan._SMALL.clear()  # cached scratch vectors point into the emulated memory
+    native._LIB = _saved.pop() if _saved else None

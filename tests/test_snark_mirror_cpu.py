@@ -1,0 +1,25 @@
+"""Host logic of nova_b200/snark.py (the mirror of spartan::snark::RelaxedR1CSSNARK::prove, snark.rs:113-256)
+on the CPU: the library is replaced by tests/emulated_device.py, which answers every `*_dev` call with the
+C oracle on host memory, so the mirror's glue (buffer sizes and offsets, argument order, transcript labels,
+batch_eval_reduce bookkeeping) is compared message by message with oracle/snark_ref.py.  The CUDA kernels
+themselves are covered by the `-m gpu` tests."""
+import gc
+
+import pytest
+
+import emulated_device
+
+
+@pytest.fixture()
+def emulated():
+    import nova_b200
+    dev = emulated_device.install()
+    yield nova_b200
+    gc.collect()
+    emulated_device.uninstall()
+
+
+@pytest.mark.parametrize("cid,num_cons,num_vars,num_io", [(0, 4, 4, 1), (0, 16, 8, 2), (1, 8, 16, 2), (3, 32, 32, 3)])
+def test_snark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars, num_io):
+    from snark_parity import run_case
+    run_case(emulated, oracle, cid, num_cons, num_vars, num_io, device_transcript=False)

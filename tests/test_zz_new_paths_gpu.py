@@ -235,53 +235,7 @@ def test_witness_stream_reset_reuse(b200, oracle):
 @pytest.mark.parametrize("cid,num_cons,num_vars,num_io", [(0, 4, 4, 1), (0, 16, 8, 2), (1, 8, 16, 2), (3, 32, 32, 3),
                                                           (0, 256, 128, 2)])
 def test_snark_prove_core_matches_oracle(b200, oracle, cid, num_cons, num_vars, num_io, device_transcript):
-    """spartan::snark::RelaxedR1CSSNARK::prove up to EE::prove (snark.rs:113-256, SURVEY §8a a32): every
-    message of the device pipeline equals oracle/snark_ref.py (pinned by the restated verifier,
-    tests/test_snark_oracle.py), the device proof passes that verifier, and the batched opening
-    polynomial evaluates / commits to the joint claim."""
-    from nova_b200 import snark as ds
-    from nova_b200 import spartan as sp
-    from oracle import snark_ref as sr
-    from oracle.ppsnark_ref import random_instance
-    from oracle.pyref import CURVES, from_mont_bytes, mle_evaluate
-    c = CURVES[cid]
-    fid, p = c.scalar_field, c.q
-    rng = SplitMix64(1300 + cid + num_cons)
-    S, W, u, X = random_instance(p, rng, num_cons, num_vars, num_io)
-    n_key = max(num_cons, num_vars)
-    bases = oracle.gen_bases(cid, n_key)
-
-    def commit_ref(v):
-        return c.affine_from_bytes(oracle.msm(cid, pack(p, v), bases[:64 * len(v)]))
-    U = dict(comm_W=commit_ref(W["W"]), comm_E=commit_ref(W["E"]), u=u, X=X)
-    ref = sr.prove_core(p, c, S, U, W, vk_digest=4242)
-
-    def csr(M, rows):
-        data, indices, indptr, k = [], [], [0], 0
-        for r in range(rows):
-            while k < len(M) and M[k][0] == r:
-                data.append(M[k][2])
-                indices.append(M[k][1])
-                k += 1
-            indptr.append(len(indices))
-        return data, indices, indptr
-    ncols = num_vars + 1 + num_io
-    mats = {}
-    for name in "ABC":
-        d, idx, ptr = csr(S[name], num_cons)
-        mats[name] = sp.SparseMatrix(fid, pack(p, d), idx, ptr, ncols)
-    Sd = dict(num_cons=num_cons, num_vars=num_vars, **mats)
-    tr = Keccak256Transcript(p, b"RelaxedR1CSSNARK")
-    got = ds.prove_core(b200.Curve(cid), None, Sd, U, dict(W=pack(p, W["W"]), E=pack(p, W["E"])), 4242, tr,
-                        device_transcript=device_transcript)
-    for k in ("sc_proof_outer", "claims_outer", "eval_E", "sc_proof_inner", "eval_W", "sc_proof_batch", "evals_batch",
-              "r_x", "r_y", "batched_x", "batched_e"):
-        assert list(got[k]) == list(ref[k]) if isinstance(ref[k], (list, tuple)) else got[k] == ref[k], k
-    assert got["batched_c"] == ref["batched_c"]
-    n = max(num_cons, num_vars)
-    bp = got["batched_poly"].to_bytes(32 * n)
-    poly = [from_mont_bytes(p, bp[i:i + 32]) for i in range(0, len(bp), 32)]
-    assert poly == ref["batched_poly"]
-    assert mle_evaluate(p, poly, got["batched_x"]) == got["batched_e"]
-    assert sr.verify_core(p, c, S, U, 4242, got) == (got["batched_c"], got["batched_x"], got["batched_e"])
-    assert tr.squeeze(b"x") == ref["transcript"].squeeze(b"x")  # EE::prove would start from the same state
+    """spartan::snark::RelaxedR1CSSNARK::prove up to EE::prove (snark.rs:113-256, SURVEY §8a a32) on the
+    device; the same check runs on the CPU against an emulated device (tests/test_snark_mirror_cpu.py)."""
+    from snark_parity import run_case
+    run_case(b200, oracle, cid, num_cons, num_vars, num_io, device_transcript)
