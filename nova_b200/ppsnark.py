@@ -201,12 +201,13 @@ class SparkRepr:
         fid, N = self.fid, self.N
         assert (1 << len(r_outer_full)) == N
         mem_row = DeviceVec(32 * N)
-        check(lib().b200_eq_table_dev(fid, DeviceVec.from_bytes(fields.pack(fid, r_outer_full)).ptr,
-                                      len(r_outer_full), mem_row.ptr, None))
+        r_dev = DeviceVec.from_bytes(fields.pack(fid, r_outer_full))  # named: must outlive the launches below
+        check(lib().b200_eq_table_dev(fid, r_dev.ptr, len(r_outer_full), mem_row.ptr, None))
         mem_col = dev_padded(z, z_len, N)
         L_row, L_col = DeviceVec(32 * N), DeviceVec(32 * N)
         check(lib().b200_gather_dev(mem_row.ptr, self.row_idx.ptr, N, L_row.ptr, None))
         check(lib().b200_gather_dev(mem_col.ptr, self.col_idx.ptr, N, L_col.ptr, None))
+        check(lib().b200_sync())  # r_dev is released on return
         return mem_row, mem_col, L_row, L_col
 
 
@@ -356,8 +357,8 @@ class WitnessBoundSumcheck:
         self.fid, self.len = fid, N
         self.W = dev_copy(W_padded, N)
         self.masked_eq = DeviceVec(32 * N)
-        check(lib().b200_eq_table_dev(fid, DeviceVec.from_bytes(fields.pack(fid, tau)).ptr, len(tau),
-                                      self.masked_eq.ptr, None))
+        self._tau_dev = DeviceVec.from_bytes(fields.pack(fid, tau))  # kept: the eq kernels read it asynchronously
+        check(lib().b200_eq_table_dev(fid, self._tau_dev.ptr, len(tau), self.masked_eq.ptr, None))
         check(lib().b200_memset_dev(self.masked_eq.ptr, 0, 32 << m, None))  # first 2^m entries -> 0
 
     def initial_claims(self):

@@ -40,6 +40,8 @@ class EmulatedDevice:
     def __init__(self):
         self.allocs = {}    # address -> buffer (keeps it alive), gives sizes of whole allocations
         self.mats = {}      # handle -> (fid, data, indices, indptr, rows, cols)
+        self.keys = {}      # handle -> (curve, bases, h or None)
+        self.graveyard = []
         self.next_handle = 1
         self.err = b""
 
@@ -61,7 +63,10 @@ class EmulatedDevice:
         return 0
 
     def b200_dev_free(self, p):
-        self.allocs.pop(_addr(p), None)
+        buf = self.allocs.pop(_addr(p), None)
+        if buf is not None:  # poison: a later read through a dangling pointer yields garbage, not stale data
+            ctypes.memset(buf, 0xEE, len(buf))
+            self.graveyard.append(buf)  # keep the pages mapped so that such a read cannot crash the test run
         return 0
 
     def b200_memcpy_h2d(self, d, h, n):
@@ -136,12 +141,41 @@ class EmulatedDevice:
         _wr(out, co.spmv_t(fid, data, idx, ip, _rd(rx, 32 * rows), out_len))
         return 0
 
+    def b200_vec_add_dev(self, fid, a, b, n, out, stream):
+        _wr(out, co.vec_add(fid, _rd(a, 32 * n), _rd(b, 32 * n)))
+        return 0
+
+    def b200_cross_term_dev(self, fid, az, bz, cz, e1, e2, u, n, t, stream):
+        g = lambda p: _rd(p, 32 * n)
+        _wr(t, co.cross_term(fid, g(az), g(bz), g(cz), g(e1), g(e2) if _addr(e2) else None, _rd(u, 32)))
+        return 0
+
+    # ---- commitment keys ----------------------------------------------------------------------
+    def b200_ck_register(self, curve_id, bases, n, h, window_bits, out_handle):
+        self.keys[self.next_handle] = (curve_id, _rd(bases, 64 * n), _rd(h, 64) if _addr(h) else None)
+        out_handle._obj.value = self.next_handle
+        self.next_handle += 1
+        return 0
+
+    def b200_ck_release(self, handle):
+        self.keys.pop(handle, None)
+        return 0
+
+    def _jacobian(self, curve_id, affine: bytes) -> bytes:
+        z = bytes(32) if affine == bytes(64) else mont_bytes(CURVES[curve_id].p, 1)
+        return affine + z  # (x, y, 1) or the identity (z = 0)
+
+    def b200_commit_dev(self, handle, scalars, n, blind, out, stream):
+        curve_id, bases, h = self.keys[handle]
+        sc, bs = _rd(scalars, 32 * n), bases[:64 * n]
+        if _addr(blind):
+            sc, bs = sc + _rd(blind, 32), bs + h
+        _wr(out, self._jacobian(curve_id, co.msm(curve_id, sc, bs)))
+        return 0
+
     # ---- group --------------------------------------------------------------------------------
     def b200_msm_adhoc(self, curve_id, bases, scalars, n, out):
-        c = CURVES[curve_id]
-        aff = co.msm(curve_id, _rd(scalars, 32 * n), _rd(bases, 64 * n))
-        z = bytes(32) if aff == bytes(64) else mont_bytes(c.p, 1)
-        _wr(out, aff + z)  # Jacobian (x, y, 1) or the identity (z = 0)
+        _wr(out, self._jacobian(curve_id, co.msm(curve_id, _rd(scalars, 32 * n), _rd(bases, 64 * n))))
         return 0
 
 

@@ -239,3 +239,12 @@ def test_snark_prove_core_matches_oracle(b200, oracle, cid, num_cons, num_vars, 
     device; the same check runs on the CPU against an emulated device (tests/test_snark_mirror_cpu.py)."""
     from snark_parity import run_case
     run_case(b200, oracle, cid, num_cons, num_vars, num_io, device_transcript)
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_r1cs_fold_fixture_on_device(b200, oracle, cid):
+    """The reference's folding fixture (nifs.rs:299-351: tiny cubic R1CS folded twice, is_sat_relaxed, then a
+    relaxed + relaxed fold) through nova_b200.r1cs with everything resident; the same body runs on the CPU
+    against the emulated device (tests/test_r1cs_mirror_cpu.py)."""
+    from r1cs_parity import run_tiny_fixture
+    run_tiny_fixture(b200, oracle, cid)

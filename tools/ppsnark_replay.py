@@ -107,7 +107,8 @@ def run(log2cons=18, curve_id=0, reps=3, seed=5):
         check(L.b200_spmv_dev(mats[name].handle, z.ptr, None, out.ptr, None, None))
     Ed = sp.DeviceVec(32 * num_cons)
     zero = dp.dev_zeros(num_cons)
-    check(L.b200_cross_term_dev(fid, Az.ptr, Bz.ptr, Cz.ptr, zero.ptr, None, dp.dev_scalar(fid, u).ptr, num_cons, Ed.ptr, None))
+    u_dev = dp.dev_scalar(fid, u)  # named: must outlive the launch
+    check(L.b200_cross_term_dev(fid, Az.ptr, Bz.ptr, Cz.ptr, zero.ptr, None, u_dev.ptr, num_cons, Ed.ptr, None))
     check(L.b200_sync())
     U = dict(comm_W=dp.commit_dev(curve, ck, Wd, num_vars), comm_E=dp.commit_dev(curve, ck, Ed, num_cons), u=u, X=X)
     S = dict(num_cons=num_cons, num_vars=num_vars, **mats)
