@@ -12,7 +12,7 @@ Only the subset the CPU tests need is implemented; anything else raises Attribut
 import ctypes
 
 from oracle import coracle as co
-from oracle.pyref import CURVES, mont_bytes
+from oracle.pyref import CURVES, FIELD_MODULUS, from_mont_bytes, mont_bytes
 
 
 def _addr(x) -> int:
@@ -116,6 +116,18 @@ class EmulatedDevice:
         _wr(out, co.rlc(fid, polys, _rd(coeffs, 32 * k), n))
         return 0
 
+    def b200_kzg_fold_dev(self, fid, p_, n, x, out, stream):
+        _wr(out, co.kzg_fold(fid, _rd(p_, 32 * n), _rd(x, 32)))
+        return 0
+
+    def b200_poly_eval_dev(self, fid, f, n, us, nu, evals, stream):
+        _wr(evals, co.poly_eval(fid, _rd(f, 32 * n), _rd(us, 32 * nu)))
+        return 0
+
+    def b200_poly_div_dev(self, fid, f, n, u, out, stream):
+        _wr(out, co.poly_div(fid, _rd(f, 32 * n), _rd(u, 32)))
+        return 0
+
     # ---- sparse matrices ----------------------------------------------------------------------
     def b200_spmv_register(self, fid, data, indices, indptr, rows, cols, out_handle):
         ip = [int(indptr[i]) for i in range(rows + 1)]
@@ -150,7 +162,47 @@ class EmulatedDevice:
         _wr(t, co.cross_term(fid, g(az), g(bz), g(cz), g(e1), g(e2) if _addr(e2) else None, _rd(u, 32)))
         return 0
 
+    def _ints(self, fid, p_, n):
+        P = FIELD_MODULUS[fid]
+        raw = _rd(p_, 32 * n)
+        return [from_mont_bytes(P, raw[32 * i:32 * i + 32]) for i in range(n)]
+
+    def _put(self, fid, p_, xs):
+        P = FIELD_MODULUS[fid]
+        _wr(p_, b"".join(mont_bytes(P, x) for x in xs))
+
+    def b200_vec_mul_dev(self, fid, a, b, n, out, stream):
+        P = FIELD_MODULUS[fid]
+        self._put(fid, out, [x * y % P for x, y in zip(self._ints(fid, a, n), self._ints(fid, b, n))])
+        return 0
+
+    def b200_logup_hash_dev(self, fid, val, addr, gamma, r, n, out, stream):
+        """out[i] = val[i] * gamma + addr[i] + r, addr == NULL meaning the cell's own index (ppsnark.rs:386-435)."""
+        P = FIELD_MODULUS[fid]
+        g, rr = self._ints(fid, gamma, 1)[0], self._ints(fid, r, 1)[0]
+        ad = self._ints(fid, addr, n) if _addr(addr) else list(range(n))
+        self._put(fid, out, [(v * g + a + rr) % P for v, a in zip(self._ints(fid, val, n), ad)])
+        return 0
+
+    def b200_batch_invert_dev(self, fid, inp, n, out, zero_flag, stream):
+        res = co.batch_invert(fid, _rd(inp, 32 * n))
+        _wr(zero_flag, (1 if res is None else 0).to_bytes(4, "little"))
+        if res is not None:
+            _wr(out, res)
+        return 0
+
+    def b200_gather_dev(self, table, idx, n, out, stream):
+        ix = (ctypes.c_uint32 * n).from_address(_addr(idx))
+        base = _addr(table)
+        _wr(out, b"".join(ctypes.string_at(base + 32 * int(ix[i]), 32) for i in range(n)))
+        return 0
+
     # ---- commitment keys ----------------------------------------------------------------------
+    def b200_commit_many_dev(self, handle, ptrs, lens, k, out, stream):
+        for j in range(k):
+            self.b200_commit_dev(handle, ptrs[j], lens[j], None, _addr(out) + 96 * j, stream)
+        return 0
+
     def b200_ck_register(self, curve_id, bases, n, h, window_bits, out_handle):
         self.keys[self.next_handle] = (curve_id, _rd(bases, 64 * n), _rd(h, 64) if _addr(h) else None)
         out_handle._obj.value = self.next_handle

@@ -1,0 +1,30 @@
+"""Host logic of nova_b200/spartan.py on the CPU through tests/emulated_device.py: the bodies of the GPU
+parity tests for the sum-check round loops (incl. tau = 0 fall-backs and prove_batch_eval with instances
+of different sizes) and for the HyperKZG prover core run unchanged against the emulated device."""
+import gc
+
+import pytest
+
+import emulated_device
+
+
+@pytest.fixture()
+def emulated():
+    import nova_b200
+    emulated_device.install()
+    yield nova_b200
+    gc.collect()
+    emulated_device.uninstall()
+
+
+def test_sumcheck_round_loops_host_logic(emulated, oracle):
+    import test_spartan_gpu as t
+    from nova_b200 import spartan
+    t.test_sumcheck_provers_match_reference_restatement(spartan, oracle, 0)
+    t.test_prove_batch_eval_matches_restatement(spartan, oracle)
+
+
+def test_hyperkzg_prove_core_host_logic(emulated, oracle):
+    import test_spartan_gpu as t
+    from nova_b200 import spartan
+    t.test_hyperkzg_prove_core(emulated, spartan, oracle)
