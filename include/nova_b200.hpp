@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -192,6 +193,157 @@ inline std::vector<Scalar> sumcheck_eval(int field, int form, const std::vector<
   return std::vector<Scalar>(out, out + n);
 }
 
+
+// ---- device-resident vectors and the folding step without host round trips ----
+// W, E and T stay in HBM between calls; only commitments (96 B) and challenges (32 B) cross the bus.
+// The O(1) instance algebra of RelaxedR1CSInstance::fold (u, X, and comm_W1 + r*comm_W2: two or three
+// commitment-sized scalar multiplications, r1cs/mod.rs:1237-1292) stays in the host's own curve library.
+class DeviceVec {
+ public:
+  DeviceVec() = default;
+  explicit DeviceVec(size_t n) : n_(n) { check(b200_dev_alloc(32 * (n ? n : 1), &p_), "b200_dev_alloc"); }
+  explicit DeviceVec(const std::vector<Scalar>& v) : DeviceVec(v.size()) {
+    if (!v.empty()) check(b200_memcpy_h2d(p_, v.data(), 32 * v.size()), "b200_memcpy_h2d");
+  }
+  DeviceVec(DeviceVec&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DeviceVec& operator=(DeviceVec&& o) noexcept {
+    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+    return *this;
+  }
+  DeviceVec(const DeviceVec&) = delete;
+  DeviceVec& operator=(const DeviceVec&) = delete;
+  ~DeviceVec() { release(); }
+  void* ptr() const { return p_; }
+  size_t len() const { return n_; }
+  std::vector<Scalar> to_host() const {
+    std::vector<Scalar> v(n_);
+    if (n_) check(b200_memcpy_d2h(v.data(), p_, 32 * n_), "b200_memcpy_d2h");
+    return v;
+  }
+  static DeviceVec zeros(size_t n) {
+    DeviceVec v(n);
+    if (n) { check(b200_memset_dev(v.p_, 0, 32 * n, nullptr), "b200_memset_dev"); check(b200_sync(), "b200_sync"); }
+    return v;
+  }
+ private:
+  void release() { if (p_) b200_dev_free(p_); p_ = nullptr; }
+  void* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+// CE::commit(ck, v, r) of a resident vector (pedersen.rs:263-270)
+template <class C>
+inline Point commit_resident(const CommitmentKey<C>& ck, const DeviceVec& v, const Scalar* r = nullptr) {
+  if (ck.len() < v.len()) throw std::logic_error("commitment key too short");  // pedersen.rs:264
+  DeviceVec out(3), blind;
+  if (r) blind = DeviceVec(std::vector<Scalar>{*r});
+  check(b200_commit_dev(ck.handle(), v.ptr(), v.len(), r ? blind.ptr() : nullptr, out.ptr(), nullptr), "b200_commit_dev");
+  Point P{};
+  check(b200_memcpy_d2h(&P, out.ptr(), 96), "b200_memcpy_d2h");  // synchronises: `blind` may now go
+  return P;
+}
+
+// CommitmentKey::new's on-curve loop (hyperkzg.rs:113-119): index of the first off-curve base, or SIZE_MAX
+template <class C>
+inline size_t validate_key(const std::vector<Affine>& ck) {
+  size_t bad = 0;
+  check(b200_ck_validate(C::curve, ck.data(), ck.size(), &bad), "b200_ck_validate");
+  return bad;
+}
+
+// Streamed witness hand-off (frontend/util_cs/witness_cs.rs:93-103 appends; frontend/r1cs.rs:40-50 commits)
+template <class C>
+class WitnessStream {
+ public:
+  WitnessStream(const CommitmentKey<C>& ck, size_t num_vars) : n_(num_vars) {
+    check(b200_witness_begin(ck.handle(), num_vars, &h_), "b200_witness_begin");
+  }
+  WitnessStream(const WitnessStream&) = delete;
+  ~WitnessStream() { if (h_) b200_witness_release(h_); }
+  // `chunk` must stay valid and unmodified until finish() returns (aux_assignment is append-only)
+  void append(const Scalar* chunk, size_t count) { check(b200_witness_append(h_, chunk, count), "b200_witness_append"); }
+  // -> commit(ck, W, r_W); *d_W (optional) = the resident witness, valid until reset() / destruction
+  Point finish(const Scalar* r_W = nullptr, void** d_W = nullptr) {
+    Point P{};
+    check(b200_witness_finish(h_, r_W, &P, d_W), "b200_witness_finish");
+    return P;
+  }
+  void reset() { check(b200_witness_reset(h_), "b200_witness_reset"); }  // next prove_step, same num_vars
+  size_t len() const { return n_; }
+ private:
+  uint64_t h_ = 0;
+  size_t n_;
+};
+
+struct RelaxedR1CSWitnessDev {  // r1cs/mod.rs:69-76 with W, E resident
+  DeviceVec W, E;
+  Scalar r_W{}, r_E{};
+};
+
+// R1CSShape with the matrices behind spmv handles and every vector resident (r1cs/mod.rs:407-431, 578-664)
+struct R1CSShapeDev {
+  const SparseMatrix &A, &B, &C;
+  int field;
+  size_t num_cons, num_vars, num_io;
+
+  // z = (W, u, X)
+  DeviceVec z(const DeviceVec& W, const Scalar& u, const std::vector<Scalar>& X) const {
+    if (W.len() != num_vars) throw std::invalid_argument("InvalidWitnessLength");  // r1cs/mod.rs:411-413
+    if (X.size() != num_io) throw std::invalid_argument("InvalidInputLength");
+    DeviceVec out(num_vars + 1 + num_io);
+    check(b200_memcpy_d2d(out.ptr(), W.ptr(), 32 * num_vars, nullptr), "b200_memcpy_d2d");
+    std::vector<Scalar> tail{u};
+    tail.insert(tail.end(), X.begin(), X.end());
+    check(b200_sync(), "b200_sync");
+    check(b200_memcpy_h2d((char*)out.ptr() + 32 * num_vars, tail.data(), 32 * tail.size()), "b200_memcpy_h2d");
+    return out;
+  }
+  std::array<DeviceVec, 3> multiply_vec(const DeviceVec& zv) const {
+    std::array<DeviceVec, 3> out{DeviceVec(num_cons), DeviceVec(num_cons), DeviceVec(num_cons)};
+    const SparseMatrix* M[3] = {&A, &B, &C};
+    for (int k = 0; k < 3; k++)
+      check(b200_spmv_dev(M[k]->handle(), zv.ptr(), nullptr, out[k].ptr(), nullptr, nullptr), "b200_spmv_dev");
+    return out;
+  }
+  // commit_T (E2 == nullptr, u2 = 1) / commit_T_relaxed: Z = Z1 + Z2, T = AZ o BZ - (u1+u2) CZ - E1 (- E2).
+  // `u_sum` = u1 + u2 is supplied by the caller (host field arithmetic).  -> (T resident, comm_T)
+  template <class Cv>
+  std::pair<DeviceVec, Point> commit_T(const CommitmentKey<Cv>& ck, const DeviceVec& Z1, const DeviceVec& Z2,
+                                       const Scalar& u_sum, const DeviceVec& E1, const DeviceVec* E2,
+                                       const Scalar* r_T) const {
+    const size_t zl = num_vars + 1 + num_io;
+    if (Z1.len() != zl || Z2.len() != zl || E1.len() != num_cons || (E2 && E2->len() != num_cons))
+      throw std::invalid_argument("InvalidWitnessLength");
+    DeviceVec Z(zl), T(num_cons), ud(std::vector<Scalar>{u_sum});
+    check(b200_vec_add_dev(field, Z1.ptr(), Z2.ptr(), zl, Z.ptr(), nullptr), "b200_vec_add_dev");
+    auto abc = multiply_vec(Z);
+    check(b200_cross_term_dev(field, abc[0].ptr(), abc[1].ptr(), abc[2].ptr(), E1.ptr(), E2 ? E2->ptr() : nullptr,
+                              ud.ptr(), num_cons, T.ptr(), nullptr), "b200_cross_term_dev");
+    Point cT = commit_resident(ck, T, r_T);  // its D2H synchronises: temporaries above may now go
+    return {std::move(T), cT};
+  }
+};
+
+// RelaxedR1CSWitness::fold / fold_relaxed on resident vectors (r1cs/mod.rs:1044-1107).  The blinds
+// r_W, r_E are host scalars: the caller folds them with its own field arithmetic.
+inline RelaxedR1CSWitnessDev fold_witness_resident(int field, const RelaxedR1CSWitnessDev& W1, const DeviceVec& W2,
+                                                   const DeviceVec& T, const Scalar& r, const DeviceVec* E2 = nullptr,
+                                                   const Scalar* r_squared = nullptr) {
+  if (W1.W.len() != W2.len()) throw std::invalid_argument("InvalidWitnessLength");  // r1cs/mod.rs:1054-1056
+  RelaxedR1CSWitnessDev out{DeviceVec(W1.W.len()), DeviceVec(W1.E.len())};
+  DeviceVec rd(std::vector<Scalar>{r});
+  check(b200_axpy_dev(field, W1.W.ptr(), W2.ptr(), rd.ptr(), W2.len(), out.W.ptr(), nullptr), "b200_axpy_dev");
+  check(b200_axpy_dev(field, W1.E.ptr(), T.ptr(), rd.ptr(), T.len(), out.E.ptr(), nullptr), "b200_axpy_dev");
+  if (E2) {  // + r^2 E2
+    if (!r_squared) throw std::logic_error("fold_relaxed needs r^2");
+    DeviceVec r2(std::vector<Scalar>{*r_squared}), tmp(W1.E.len());
+    check(b200_axpy_dev(field, out.E.ptr(), E2->ptr(), r2.ptr(), E2->len(), tmp.ptr(), nullptr), "b200_axpy_dev");
+    check(b200_sync(), "b200_sync");
+    out.E = std::move(tmp);
+  }
+  check(b200_sync(), "b200_sync");  // rd must outlive the launches
+  return out;
+}
 
 // ---- sum-check round loops with the transcript on the device ------------------
 // The serialisable part of Keccak256Transcript (keccak.rs:19-27): `round`, `state`, and the bytes

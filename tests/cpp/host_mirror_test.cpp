@@ -5,6 +5,7 @@
 //        host_mirror_test --compile-check                                   (no GPU: links only)
 #include <cstdio>
 #include <fstream>
+#include <memory>
 #include <thread>
 
 #include "../../include/nova_b200.hpp"
@@ -19,6 +20,57 @@ static std::vector<T> rd(std::ifstream& f) {
   return v;
 }
 
+// --fold <case.bin>: the device-resident folding step through the C++ layer (R1CSShapeDev::commit_T,
+// fold_witness_resident, WitnessStream, validate_key); the Python test checks the dumped results against
+// the oracle.  Case file: A, B, C as (data, indices, indptr), then W1, E1, W2, X1, X2, [u1, u_sum, r, r_T, r_W],
+// bases, h.
+static SparseMatrix* read_matrix(std::ifstream& f, int field, size_t cols) {
+  auto data = rd<Scalar>(f);
+  auto idx = rd<uint64_t>(f);
+  auto ptr = rd<uint64_t>(f);
+  return new SparseMatrix(field, data, idx, ptr, cols);
+}
+static int fold_mode(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  check(b200_init(0), "b200_init");
+  const int field = BN254::scalar_field;
+  auto dims = rd<uint64_t>(f);  // num_cons, num_vars, num_io
+  const size_t num_cons = dims[0], num_vars = dims[1], num_io = dims[2], cols = num_vars + 1 + num_io;
+  std::unique_ptr<SparseMatrix> A(read_matrix(f, field, cols)), B(read_matrix(f, field, cols)), C(read_matrix(f, field, cols));
+  auto W1 = rd<Scalar>(f), E1 = rd<Scalar>(f), W2 = rd<Scalar>(f), X1 = rd<Scalar>(f), X2 = rd<Scalar>(f), sc = rd<Scalar>(f);
+  auto bases = rd<Affine>(f);
+  auto h = rd<Affine>(f);
+  const Scalar &u1 = sc[0], &u_sum = sc[1], &r = sc[2], &r_T = sc[3], &r_W = sc[4], &one = sc[5];
+  CommitmentKey<BN254> ck(bases, &h[0]);
+  R1CSShapeDev S{*A, *B, *C, field, num_cons, num_vars, num_io};
+  size_t bad = validate_key<BN254>(bases);
+  // the fresh witness arrives through the stream in three ragged chunks
+  WitnessStream<BN254> ws(ck, num_vars);
+  size_t c1 = num_vars / 3, c2 = num_vars / 2;
+  ws.append(W2.data(), c1);
+  ws.append(W2.data() + c1, c2 - c1);
+  ws.append(W2.data() + c2, num_vars - c2);
+  void* dW2 = nullptr;
+  Point comm_W2 = ws.finish(&r_W, &dW2);
+  DeviceVec W2d(W2), W1d(W1), E1d(E1);
+  DeviceVec Z1 = S.z(W1d, u1, X1), Z2 = S.z(W2d, one, X2);
+  auto tc = S.commit_T(ck, Z1, Z2, u_sum, E1d, nullptr, &r_T);
+  RelaxedR1CSWitnessDev run{std::move(W1d), std::move(E1d)};
+  RelaxedR1CSWitnessDev folded = fold_witness_resident(field, run, W2d, tc.first, r);
+  auto T = tc.first.to_host(), Wf = folded.W.to_host(), Ef = folded.E.to_host();
+  std::ofstream o(std::string(path) + ".out", std::ios::binary);
+  auto dump = [&](const void* p, uint64_t n, size_t sz) { o.write((char*)&n, 8); o.write((const char*)p, n * sz); };
+  uint64_t b64 = bad;
+  dump(&b64, 1, 8);
+  dump(&comm_W2, 1, 96);
+  dump(&tc.second, 1, 96);
+  dump(T.data(), T.size(), 32);
+  dump(Wf.data(), Wf.size(), 32);
+  dump(Ef.data(), Ef.size(), 32);
+  std::printf("fold ok\n");
+  return 0;
+}
+
 // Jacobian -> compare with expected affine without inversion: X == x*Z^2, Y == y*Z^3 is checked on
 // the Python side; here we only dump the raw result bytes.
 int main(int argc, char** argv) {
@@ -27,6 +79,7 @@ int main(int argc, char** argv) {
     std::printf("compiled against %s\n", b200_version());
     return 0;
   }
+  if (std::string(argv[1]) == "--fold") return argc > 2 ? fold_mode(argv[2]) : 2;
   std::ifstream f(argv[1], std::ios::binary);
   check(b200_init(0), "b200_init");
   auto bases = rd<Affine>(f);
