@@ -28,8 +28,12 @@ def test_cpp_mirror_compiles_and_links():
 
 @pytest.mark.gpu
 def test_cpp_mirror_concurrent_commits(oracle, tmp_path):
-    from oracle.pyref import CURVES
     build()
+    check_concurrent_commits(EXE, oracle, tmp_path)
+
+
+def check_concurrent_commits(exe, oracle, tmp_path):
+    from oracle.pyref import CURVES
     cid, c = 0, CURVES[0]
     n = 6000
     bases = oracle.gen_bases(cid, n + 1)
@@ -40,7 +44,7 @@ def test_cpp_mirror_concurrent_commits(oracle, tmp_path):
         for blob, sz in ((bases[:64 * n], 64), (bases[64 * n:], 64), (sc, 32), (r, 32)):
             f.write(struct.pack("<Q", len(blob) // sz))
             f.write(blob)
-    out = subprocess.run([EXE, str(case)], capture_output=True, text=True)
+    out = subprocess.run([exe, str(case)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     raw = open(str(case) + ".out", "rb").read()
     (k,) = struct.unpack_from("<Q", raw, 0)
@@ -57,3 +61,96 @@ def test_cpp_mirror_concurrent_commits(oracle, tmp_path):
     off += 8 + 32 * nf
     (nz,) = struct.unpack_from("<Q", raw, off)
     assert raw[off + 8:off + 8 + 32 * nz] == oracle.bind_top(c.scalar_field, sc[:32 * (n & ~1)], r)
+
+
+# ---- the same executable source against the CPU emulation of the library (tests/cpp/emulated_b200.cpp) ----
+EXE_EMUL = os.path.join(ROOT, "tests", "cpp", "host_mirror_test_emul")
+EMUL_SO = os.path.join(ROOT, "tests", "cpp", "libemulated_b200.so")
+
+
+def build_emulated():
+    """host_mirror_test linked against libemulated_b200.so (C-ABI symbols answered by the C oracle): the C++
+    host layer of include/nova_b200.hpp runs on the CPU box."""
+    from oracle import coracle
+    coracle.lib()  # makes sure oracle/liboracle.so exists
+    odir = os.path.join(ROOT, "oracle")
+    cdir = os.path.join(ROOT, "tests", "cpp")
+    esrc = os.path.join(cdir, "emulated_b200.cpp")
+    hdrs = [os.path.join(ROOT, "include", f) for f in ("nova_b200.hpp", "nova_b200.h")]
+    if not os.path.exists(EMUL_SO) or any(os.path.getmtime(p) > os.path.getmtime(EMUL_SO) for p in [esrc] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", esrc, "-o", EMUL_SO, "-L" + odir, "-loracle",
+                               "-Wl,-rpath," + odir])
+    src = os.path.join(cdir, "host_mirror_test.cpp")
+    if not os.path.exists(EXE_EMUL) or any(os.path.getmtime(p) > os.path.getmtime(EXE_EMUL) for p in [src, EMUL_SO] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", src, "-o", EXE_EMUL, "-L" + cdir, "-lemulated_b200",
+                               "-Wl,-rpath," + cdir, "-Wl,-rpath," + odir])
+
+
+def test_cpp_mirror_host_logic_concurrent_commits_cpu(oracle, tmp_path):
+    """The C++ layer's commit / MSM / fold / bind wrappers, with commits issued from 8 threads, on the CPU."""
+    build_emulated()
+    check_concurrent_commits(EXE_EMUL, oracle, tmp_path)
+
+
+def test_cpp_mirror_host_logic_resident_folding_step_cpu(oracle, tmp_path):
+    """DeviceVec, WitnessStream, validate_key, R1CSShapeDev::commit_T and fold_witness_resident on the CPU."""
+    build_emulated()
+    check_fold(EXE_EMUL, oracle, tmp_path)
+
+
+def check_fold(exe, oracle, tmp_path):
+    """host_mirror_test --fold: the streamed commitment, T, comm_T and the folded W / E equal the oracle's
+    (r1cs/mod.rs:578-627, 1044-1069)."""
+    from oracle.ppsnark_ref import random_instance
+    from oracle.pyref import CURVES, SplitMix64, mont_bytes
+    from snark_parity import csr
+    cid, c = 0, CURVES[0]
+    fid, p = c.scalar_field, c.q
+    pack = lambda xs: b"".join(mont_bytes(p, x) for x in xs)
+    num_cons, num_vars, num_io = 128, 64, 2
+    rng = SplitMix64(2024)
+    S, W, u1, X1 = random_instance(p, rng, num_cons, num_vars, num_io)
+    W1, E1 = W["W"], W["E"]
+    W2 = [rng.field(p) for _ in range(num_vars)]
+    X2 = [rng.field(p) for _ in range(num_io)]
+    r, r_T, r_W = rng.field(p), rng.field(p), rng.field(p)
+    n_key = max(num_cons, num_vars)
+    bases = oracle.gen_bases(cid, n_key + 1)
+    case = tmp_path / "fold.bin"
+
+    def blob(b, sz):
+        return struct.pack("<Q", len(b) // sz) + b
+
+    def u64s(xs):
+        return struct.pack("<Q", len(xs)) + struct.pack(f"<{len(xs)}Q", *xs)
+    with open(case, "wb") as f:
+        f.write(u64s([num_cons, num_vars, num_io]))
+        for name in "ABC":
+            d, idx, ptr = csr(S[name], num_cons)
+            f.write(blob(pack(d), 32) + u64s(idx) + u64s(ptr))
+        for v in (W1, E1, W2, X1, X2, [u1, (u1 + 1) % p, r, r_T, r_W, 1]):
+            f.write(blob(pack(v), 32))
+        f.write(blob(bases[:64 * n_key], 64) + blob(bases[64 * n_key:], 64))
+    out = subprocess.run([exe, "--fold", str(case)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = open(str(case) + ".out", "rb").read()
+    off = 0
+
+    def take(sz):
+        nonlocal off
+        (n,) = struct.unpack_from("<Q", raw, off)
+        b = raw[off + 8:off + 8 + n * sz]
+        off += 8 + n * sz
+        return b
+    bad, comm_W2, comm_T, T, Wf, Ef = take(8), take(96), take(96), take(32), take(32), take(32)
+    assert struct.unpack("<Q", bad)[0] == (1 << 64) - 1  # every base is on the curve
+    h = bases[64 * n_key:]
+    aff = lambda jac: c.affine_from_bytes(oracle.jacobian_to_affine(cid, jac))
+    assert aff(comm_W2) == c.affine_from_bytes(oracle.msm(cid, pack(W2 + [r_W]), bases[:64 * num_vars] + h))
+    Z = pack([(a + b) % p for a, b in zip(W1 + [u1] + X1, W2 + [1] + X2)])
+    az, bz, cz = (oracle.spmv(fid, pack(d), idx, ptr, Z) for (d, idx, ptr) in (csr(S[k], num_cons) for k in "ABC"))
+    T_exp = oracle.cross_term(fid, az, bz, cz, pack(E1), None, pack([(u1 + 1) % p]))
+    assert T == T_exp
+    assert aff(comm_T) == c.affine_from_bytes(oracle.msm(cid, T_exp + pack([r_T]), bases[:64 * num_cons] + h))
+    assert Wf == oracle.axpy(fid, pack(W1), pack(W2), pack([r]))
+    assert Ef == oracle.axpy(fid, pack(E1), T_exp, pack([r]))
