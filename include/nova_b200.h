@@ -246,6 +246,34 @@ enum { B200_SC_ROUND_QUAD_PROD = 0, B200_SC_ROUND_CUBIC3_EQ = 1, B200_SC_ROUND_C
 int b200_sc_round_dev(int field_id, int kind, void* d_state, const void* d_res, const void* d_tau,
                       const void* d_tau_inv, const void* d_pending, size_t pending_len,
                       int absorb_label, int squeeze_label, void* d_poly_out, void* d_r_out, void* stream);
+/* One round of a BATCHED sum-check -- RelaxedR1CSSNARK::prove_helper of the MicroSpartan prover
+ * (spartan/ppsnark.rs:886-983): every claim's evaluation points [s(0), lead, s(-1)] (the eq-weighted
+ * ones derived from (t(0), t(inf)) and the claim's own running claim, sumcheck.rs:680-747), their
+ * combination with the fixed coefficients into one cubic, absorb / squeeze, update_claim for every
+ * running claim (sumcheck.rs:68-75) and the eq instances' bound values.  The host fills the descriptor
+ * per round (slots of the sums the reductions of this round wrote; third-sum slots for tau = 0 rounds)
+ * and enqueues reductions -> this call -> binds without reading anything back. */
+#define B200_SCB_MAX_CLAIMS 16
+#define B200_SCB_MAX_EQ 4
+enum { B200_SCB_RAW3 = 0, B200_SCB_LIN2 = 1, B200_SCB_EQ_DEG2 = 2, B200_SCB_EQ_DEG1 = 3 };
+typedef struct b200_scb_desc {
+  int32_t nclaims, neq;
+  int32_t kind[B200_SCB_MAX_CLAIMS];    /* B200_SCB_* */
+  int32_t slot[B200_SCB_MAX_CLAIMS];    /* element index (32-byte units) of the claim's sums; 3 elements readable */
+  int32_t slot_m1[B200_SCB_MAX_CLAIMS]; /* element index of t(-1) in a tau = 0 round, else -1 */
+  int32_t eq_of[B200_SCB_MAX_CLAIMS];   /* eq instance of an EQ claim */
+  const void* tau[B200_SCB_MAX_EQ];     /* device: this round's tau per eq instance (Montgomery) */
+  const void* tau_inv[B200_SCB_MAX_EQ]; /* device: its inverse (ignored when tau = 0) */
+} b200_scb_desc;
+typedef struct b200_scb_state {           /* device resident, 1296 bytes */
+  b200_sc_state head;                     /* head.claim = combined running claim; transcript; head.q unused */
+  unsigned char coeff[B200_SCB_MAX_CLAIMS][32]; /* batching coefficients (powers of s, ppsnark.rs:915-921) */
+  unsigned char claim[B200_SCB_MAX_CLAIMS][32]; /* running claims of the EQ claims */
+  unsigned char q[B200_SCB_MAX_EQ][32];         /* eval_eq_left per eq instance */
+} b200_scb_state;
+int b200_sc_round_batched_dev(int field_id, const b200_scb_desc* desc, const void* d_sums, void* d_state,
+                              const void* d_pending, size_t pending_len, int absorb_label, int squeeze_label,
+                              void* d_poly_out, void* d_r_out, void* stream);
 /* SumcheckProof::prove_quad_prod (sumcheck.rs:199-242) in one call.  d_A, d_B: device polynomials
  * of 2^num_rounds elements, bound in place (element 0 holds the final evaluation afterwards).
  * Host outputs: polys_out [num_rounds][2][32] canonical LE, r_out [num_rounds][32] Montgomery,

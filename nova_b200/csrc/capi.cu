@@ -16,6 +16,7 @@
 #include "ops.cuh"
 #include "poly_kernels.cuh"
 #include "transcript.cuh"
+#include "transcript_batched.cuh"
 
 using namespace nova;
 

@@ -73,6 +73,10 @@ struct field_ops {
   void (*fe_inv_each)(cudaStream_t, const void* in, size_t n, void* out);  // 0 -> 0
   // digits + histogram of scalars [i0, i1) of a p.n-long vector (streamed witness hand-off)
   void (*digits_range)(cudaStream_t, const void* scalars, size_t i0, size_t i1, const msm_plan&);
+  // one round of a batched sum-check (ppsnark prove_helper) on the device (transcript_batched.cuh);
+  // desc: scb_desc by value, state: scb_state (1296 B, device)
+  void (*sc_round_batched)(cudaStream_t, const void* desc, void* state, const void* sums, const void* pending,
+                           uint32_t pending_len, int absorb_label, int squeeze_label, void* out_poly, void* out_r);
   // key validation: *first_bad = min index of an off-curve base (caller presets 0xFFFFFFFF)
   void (*on_curve)(cudaStream_t, const void* pts, size_t n, int b_small, uint32_t* first_bad);
 };

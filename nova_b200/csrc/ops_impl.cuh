@@ -5,6 +5,7 @@
 #include "field_kernels.cuh"
 #include "poly_kernels.cuh"
 #include "transcript.cuh"
+#include "transcript_batched.cuh"
 
 namespace nova {
 
@@ -295,6 +296,11 @@ struct ops_impl {
   static void fe_inv_each(cudaStream_t s, const void* in, size_t n, void* out) {
     if (n) k_fe_inv_each<F><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(in, n, out);
   }
+  static void sc_round_batched(cudaStream_t s, const void* desc, void* state, const void* sums, const void* pending,
+                               uint32_t pending_len, int absorb_label, int squeeze_label, void* out_poly, void* out_r) {
+    k_sc_round_batched<F><<<1, 32, 0, s>>>(*(const scb_desc*)desc, (scb_state*)state, sums, (const uint8_t*)pending,
+                                           pending_len, (uint8_t)absorb_label, (uint8_t)squeeze_label, out_poly, out_r);
+  }
   static void on_curve(cudaStream_t s, const void* pts, size_t n, int b_small, uint32_t* first_bad) {
     if (n) k_on_curve<F><<<stream_grid(n, 256), 256, 0, s>>>(pts, n, b_small, first_bad);
   }
@@ -303,7 +309,7 @@ struct ops_impl {
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, vec_mul, logup_hash,
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
-                     sc_round, fe_inv_each, digits_range, on_curve};
+                     sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve};
   }
 };
 

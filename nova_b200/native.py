@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200_witness_reset": [c_u64],
     "b200_witness_release": [c_u64],
     "b200_sc_round_dev": [c_int, c_int, _P, _P, _P, _P, _P, c_size_t, c_int, c_int, _P, _P, _P],
+    "b200_sc_round_batched_dev": [c_int, _P, _P, _P, _P, c_size_t, c_int, c_int, _P, _P, _P],
     "b200_sumcheck_quad_prod": [c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _P, _P, _P],
     "b200_sumcheck_cubic3": [c_int, _P, _P, c_int, _P, _P, _P, _P, _P, c_size_t, _P, _P, _P],
     "b200_eq_table": [c_int, _P, c_int, _P],

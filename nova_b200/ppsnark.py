@@ -27,6 +27,18 @@ from .spartan import (SC_CUBIC, SC_EQ_CUBIC2, SC_EQ_CUBIC2_M1, SC_EQ_CUBIC3, SC_
                       update_claim)
 
 
+SCB_RAW3, SCB_LIN2, SCB_EQ_DEG2, SCB_EQ_DEG1 = range(4)  # b200_scb_desc.kind (include/nova_b200.h)
+SCB_MAX_CLAIMS, SCB_MAX_EQ = 16, 4
+
+
+class ScbDesc(ctypes.Structure):
+    """b200_scb_desc"""
+    _fields_ = [("nclaims", ctypes.c_int32), ("neq", ctypes.c_int32), ("kind", ctypes.c_int32 * SCB_MAX_CLAIMS),
+                ("slot", ctypes.c_int32 * SCB_MAX_CLAIMS), ("slot_m1", ctypes.c_int32 * SCB_MAX_CLAIMS),
+                ("eq_of", ctypes.c_int32 * SCB_MAX_CLAIMS), ("tau", ctypes.c_void_p * SCB_MAX_EQ),
+                ("tau_inv", ctypes.c_void_p * SCB_MAX_EQ)]
+
+
 def to_repr(x: int) -> bytes:
     return int(x).to_bytes(32, "little")  # canonical little-endian (traits.rs:323-327)
 
@@ -108,6 +120,10 @@ class RoundSums:
                                      L.ptr if L else None, R.ptr if R else None, shift, dst, None))
         self.nout.append(SC_NOUT[form])
         return k
+
+    def reset(self):
+        """Forget the slots without reading them back (the device-transcript loop never fetches)."""
+        self.nout = []
 
     def fetch(self):
         raw = self.out.to_bytes(96 * len(self.nout))
@@ -291,6 +307,37 @@ class MemorySumcheckInstance:
         self.len //= 2
         self.eq.bound(r)
 
+    # -- device-transcript loop (prove_helper_device): claim kinds, third sums for tau = 0, binds only --
+    KINDS = (SCB_LIN2, SCB_LIN2, SCB_EQ_DEG2, SCB_EQ_DEG2, SCB_EQ_DEG2, SCB_EQ_DEG2)
+
+    def eq_instances(self):
+        return [self.eq]
+
+    def claim_eq(self):
+        return [None, None, 0, 0, 0, 0]
+
+    def running_claims(self):
+        return list(self.running)
+
+    def enqueue_m1(self, sums: RoundSums):
+        """t(-1) of the four eq-weighted claims (sumcheck.rs:1082-1178), for a round whose tau is 0."""
+        L, R, sh = self.eq._tables()
+        n = self.len
+        return [None, None,
+                sums.add(SC_EQ_CUBIC3_M1, self.t_inv_row, self.t_row, self.ts_row, n, L, R, sh),
+                sums.add(SC_EQ_CUBIC2_M1, self.w_inv_row, self.w_row, None, n, L, R, sh),
+                sums.add(SC_EQ_CUBIC3_M1, self.t_inv_col, self.t_col, self.ts_col, n, L, R, sh),
+                sums.add(SC_EQ_CUBIC2_M1, self.w_inv_col, self.w_col, None, n, L, R, sh)]
+
+    def slots(self):
+        return list(self._slots)
+
+    def bound_device(self, r_dev):
+        _bind_all(self.fid, [self.t_row, self.t_inv_row, self.w_row, self.w_inv_row, self.ts_row, self.t_col,
+                             self.t_inv_col, self.w_col, self.w_inv_col, self.ts_col], self.len, r_dev)
+        self.len //= 2
+        self.eq.round += 1
+
     def final_claims(self):
         g = lambda v: _first(self.fid, v)
         return [[g(self.t_inv_row), g(self.w_inv_row), g(self.ts_row)],
@@ -346,6 +393,29 @@ class InnerBatchedSumcheckInstance:
         self.len //= 2
         self.eq.bound(r)
 
+    KINDS = (SCB_RAW3, SCB_EQ_DEG1)
+
+    def eq_instances(self):
+        return [self.eq]
+
+    def claim_eq(self):
+        return [None, 0]
+
+    def running_claims(self):
+        return [0, self.running_E]
+
+    def enqueue_m1(self, sums: RoundSums):
+        L, R, sh = self.eq._tables()
+        return [None, sums.add(SC_EQ_QUAD1_M1, self.E, None, None, self.len, L, R, sh)]
+
+    def slots(self):
+        return list(self._slots)
+
+    def bound_device(self, r_dev):
+        _bind_all(self.fid, [self.L_row, self.L_col, self.val, self.E], self.len, r_dev)
+        self.len //= 2
+        self.eq.round += 1
+
     def final_claims(self):
         return [[_first(self.fid, self.L_row), _first(self.fid, self.L_col)], [_first(self.fid, self.E)]]
 
@@ -375,6 +445,27 @@ class WitnessBoundSumcheck:
         return [[e0, 0, einf]]
 
     def bound(self, r, r_dev):
+        _bind_all(self.fid, [self.W, self.masked_eq], self.len, r_dev)
+        self.len //= 2
+
+    KINDS = (SCB_LIN2,)
+
+    def eq_instances(self):
+        return []
+
+    def claim_eq(self):
+        return [None]
+
+    def running_claims(self):
+        return [0]
+
+    def enqueue_m1(self, sums: RoundSums):
+        return [None]
+
+    def slots(self):
+        return [self._slot]
+
+    def bound_device(self, r_dev):
         _bind_all(self.fid, [self.W, self.masked_eq], self.len, r_dev)
         self.len //= 2
 
@@ -413,6 +504,81 @@ def prove_helper(fid, mem, inner, witness, transcript):
     return polys, rs, mem.final_claims(), inner.final_claims(), witness.final_claims()
 
 
+def prove_helper_device(fid, mem, inner, witness, transcript):
+    """prove_helper (ppsnark.rs:886-983) with the per-round algebra and the transcript on the device:
+    per round the nine reductions, one b200_sc_round_batched_dev and the sixteen binds are enqueued
+    without reading anything back; proof, challenges and transcript state are read once at the end.
+    `transcript` needs the serialisable fields `round`, `state`, `buf` (see spartan._device_loop)."""
+    p = fields.MODULUS[fid]
+    engines = (mem, inner, witness)
+    assert mem.size() == inner.size() == witness.size()
+    nr = mem.size().bit_length() - 1
+    claims = mem.initial_claims() + inner.initial_claims() + witness.initial_claims()
+    k = len(claims)
+    assert k <= SCB_MAX_CLAIMS
+    s = transcript.squeeze(b"r")
+    coeffs = [pow(s, i, p) for i in range(k)]
+    e = sum(c * cl for c, cl in zip(claims, coeffs)) % p
+    kinds = [kd for eng in engines for kd in eng.KINDS]
+    eqs, eq_of = [], []
+    for eng in engines:  # global numbering of the eq instances
+        base = len(eqs)
+        eqs += eng.eq_instances()
+        eq_of += [None if g is None else base + g for g in eng.claim_eq()]
+    assert len(eqs) <= SCB_MAX_EQ
+    running = [x for eng in engines for x in eng.running_claims()]
+    pad = lambda xs, n: list(xs) + [0] * (n - len(xs))
+    head = (fields.to_mont_bytes(fid, e) + bytes(32) + int(transcript.round).to_bytes(8, "little")
+            + bytes(transcript.state) + bytes(8))
+    state = DeviceVec.from_bytes(head + fields.pack(fid, pad(coeffs, SCB_MAX_CLAIMS)) + fields.pack(fid, pad(running, SCB_MAX_CLAIMS))
+                                 + fields.pack(fid, pad([1] * len(eqs), SCB_MAX_EQ)))
+    assert state.nbytes == 1296
+    tau_dev = [DeviceVec.from_bytes(fields.pack(fid, q.taus)) for q in eqs]
+    tinv_dev = [DeviceVec.from_bytes(fields.pack(fid, [pow(t, -1, p) if t % p else 0 for t in q.taus])) for q in eqs]
+    polys_dev, rs_dev = DeviceVec(96 * nr), DeviceVec(32 * nr)
+    pending = bytes(transcript.buf)
+    pend_dev = DeviceVec.from_bytes(pending) if pending else None
+    sums = RoundSums(fid)
+    L = lib()
+    for j in range(nr):
+        for eng in engines:
+            eng.enqueue(sums)
+        slots = [sl for eng in engines for sl in eng.slots()]
+        m1 = [None] * k
+        off = 0
+        for eng in engines:  # third sums for the eq instances whose tau is 0 in this round
+            qs = eng.eq_instances()
+            if any(q.taus[q.round - 1] % p == 0 for q in qs):
+                got = eng.enqueue_m1(sums)
+                for i, g in enumerate(eng.claim_eq()):
+                    if g is not None and qs[g].taus[qs[g].round - 1] % p == 0:
+                        m1[off + i] = got[i]
+            off += len(eng.KINDS)
+        d = ScbDesc()
+        d.nclaims, d.neq = k, len(eqs)
+        for i in range(k):
+            d.kind[i], d.slot[i] = kinds[i], 3 * slots[i]
+            d.slot_m1[i] = -1 if m1[i] is None else 3 * m1[i]
+            d.eq_of[i] = -1 if eq_of[i] is None else eq_of[i]
+        for g, q in enumerate(eqs):
+            d.tau[g] = tau_dev[g].ptr.value + 32 * (q.round - 1)
+            d.tau_inv[g] = tinv_dev[g].ptr.value + 32 * (q.round - 1)
+        check(L.b200_sc_round_batched_dev(fid, ctypes.byref(d), sums.out.ptr, state.ptr, pend_dev.ptr if (pend_dev and j == 0) else None,
+                                          len(pending) if j == 0 else 0, ord("p"), ord("c"), View(polys_dev, 3 * j).ptr,
+                                          View(rs_dev, j).ptr, None))
+        sums.reset()
+        r_dev = View(rs_dev, j)
+        for eng in engines:
+            eng.bound_device(r_dev)
+    raw_polys, raw_rs, raw_state = polys_dev.to_bytes(96 * nr), rs_dev.to_bytes(32 * nr), state.to_bytes(144)
+    transcript.round = int.from_bytes(raw_state[64:72], "little")
+    transcript.state = raw_state[72:136]
+    transcript.buf = b""
+    coeffs_out = [int.from_bytes(raw_polys[32 * i:32 * i + 32], "little") for i in range(3 * nr)]
+    polys = [coeffs_out[3 * j:3 * j + 3] for j in range(nr)]
+    return polys, fields.unpack(fid, raw_rs), mem.final_claims(), inner.final_claims(), witness.final_claims()
+
+
 def _prove_cubic3_resident(fid, claim, taus, A, B, C, length, transcript):
     """SumcheckProof::prove_cubic_with_three_inputs (sumcheck.rs:446-507) on resident vectors."""
     p = fields.MODULUS[fid]
@@ -439,7 +605,7 @@ def _mle_eval(fid, Z, ell, r_dev) -> int:
 
 
 def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: dict, vk_digest: int, transcript,
-               timings: dict | None = None):
+               timings: dict | None = None, device_transcript: bool = False):
     """ppsnark.rs:1056-1355 up to (and excluding) EE::prove.
 
     S: dict(num_cons, num_vars, A, B, C) with A/B/C `spartan.SparseMatrix` (regular, padded shape).
@@ -479,7 +645,11 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
     uCz_E = DeviceVec(32 * num_cons)
     check(lib().b200_axpy_dev(fid, Ed.ptr, Cz.ptr, u_dev.ptr, num_cons, uCz_E.ptr, None))  # E + u*Cz
     mark("spmv")
-    sc_outer, r_outer, claims_outer = _prove_cubic3_resident(fid, 0, tau, Az, Bz, uCz_E, num_cons, tr)
+    if device_transcript:  # one call, transcript on the device (b200_sumcheck_cubic3)
+        from .spartan import SumcheckProof
+        sc_outer, r_outer, claims_outer = SumcheckProof.prove_cubic_with_three_inputs_device(fid, 0, tau, Az, Bz, uCz_E, tr)
+    else:
+        sc_outer, r_outer, claims_outer = _prove_cubic3_resident(fid, 0, tau, Az, Bz, uCz_E, num_cons, tr)
     eAz, eBz = claims_outer[0], claims_outer[1]
     eCz = _mle_eval(fid, Cz, nro, DeviceVec.from_bytes(fields.pack(fid, r_outer)))
     eE_outer = (claims_outer[2] - U["u"] * eCz) % p
@@ -513,7 +683,8 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
     mem = MemorySumcheckInstance(fid, N, mem_oracles, mem_aux, rho, spark.ts_row, spark.ts_col)
     wit = WitnessBoundSumcheck(fid, N, r_full, W_p, num_vars)
     mark("engines_setup")
-    sc_inner, r_inner, c_mem, c_inner, c_wit = prove_helper(fid, mem, inner, wit, tr)
+    sc_inner, r_inner, c_mem, c_inner, c_wit = (prove_helper_device if device_transcript else prove_helper)(
+        fid, mem, inner, wit, tr)
     mark("inner_sumcheck")
     ev = {
         "eval_L_row": c_inner[0][0], "eval_L_col": c_inner[0][1], "eval_E": c_inner[1][0],

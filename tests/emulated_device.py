@@ -42,6 +42,7 @@ class EmulatedDevice:
         self.mats = {}      # handle -> (fid, data, indices, indptr, rows, cols)
         self.keys = {}      # handle -> (curve, bases, h or None)
         self.graveyard = []
+        self.hc = None
         self.next_handle = 1
         self.err = b""
 
@@ -128,6 +129,78 @@ class EmulatedDevice:
         _wr(out, co.poly_div(fid, _rd(f, 32 * n), _rd(u, 32)))
         return 0
 
+    # ---- sum-check loops with the transcript "on the device": the HOST BUILD of the round kernels -------
+    # (tests/hostcheck, the same headers the GPU runs) strung together as csrc/capi_sumcheck.inc does
+    def _hc(self):
+        if self.hc is None:
+            import os
+            import subprocess
+            here = os.path.dirname(os.path.abspath(__file__))
+            src, so = os.path.join(here, "hostcheck", "hostcheck.cpp"), os.path.join(here, "hostcheck", "libhostcheck.so")
+            csrc = os.path.join(here, "..", "nova_b200", "csrc")
+            deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+            if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+            self.hc = ctypes.CDLL(so)
+        return self.hc
+
+    def b200_sc_round_batched_dev(self, fid, desc, sums, state, pending, pending_len, la, ls, poly_out, r_out, stream):
+        rc = self._hc().hc_sc_round_batched(fid, ctypes.c_void_p(_addr(desc)), ctypes.c_void_p(_addr(state)),
+                                            ctypes.c_void_p(_addr(sums)), ctypes.c_void_p(_addr(pending)), int(pending_len),
+                                            la, ls, ctypes.c_void_p(_addr(poly_out)), ctypes.c_void_p(_addr(r_out)))
+        return 0 if rc == 0 else 1
+
+    def _sumcheck_loop(self, fid, kind_of, claim, num_rounds, polys, tr, pending, pending_len, polys_out, r_out,
+                       finals_out, ncoef, sums_of, taus=None):
+        P = FIELD_MODULUS[fid]
+        state = ctypes.create_string_buffer(_rd(claim, 32) + mont_bytes(P, 1) + _rd(tr, 72) + bytes(8), 144)
+        length = 1 << num_rounds
+        for j in range(num_rounds):
+            res = ctypes.create_string_buffer(sums_of(j, length), 96)
+            tau = tinv = None
+            if taus is not None:
+                tau = ctypes.create_string_buffer(mont_bytes(P, taus[j]), 32)
+                tinv = ctypes.create_string_buffer(mont_bytes(P, pow(taus[j], -1, P) if taus[j] else 0), 32)
+            rc = self._hc().hc_sc_round(fid, kind_of(j), state, res, tau, tinv, ctypes.c_void_p(_addr(pending) if j == 0 else 0),
+                                        int(pending_len) if j == 0 else 0, ord("p"), ord("c"),
+                                        ctypes.c_void_p(_addr(polys_out) + 32 * ncoef * j), ctypes.c_void_p(_addr(r_out) + 32 * j))
+            assert rc == 0
+            r = _rd(_addr(r_out) + 32 * j, 32)
+            for Z in polys:
+                _wr(Z, co.bind_top(fid, _rd(Z, 32 * length), r))
+            length //= 2
+        for k, Z in enumerate(polys):
+            _wr(_addr(finals_out) + 32 * k, _rd(Z, 32))
+        _wr(tr, state.raw[64:136])
+        return 0
+
+    def b200_sumcheck_quad_prod(self, fid, claim, num_rounds, A, B, tr, pending, pending_len, polys_out, r_out, finals_out):
+        sums = lambda j, n: co.sc_eval(fid, 0, _rd(A, 32 * n), _rd(B, 32 * n))
+        return self._sumcheck_loop(fid, lambda j: 0, claim, num_rounds, [A, B], tr, pending, pending_len, polys_out,
+                                   r_out, finals_out, 2, sums)
+
+    def b200_sumcheck_cubic3(self, fid, claim, taus_p, num_rounds, A, B, C, tr, pending, pending_len, polys_out, r_out,
+                             finals_out):
+        P = FIELD_MODULUS[fid]
+        l = num_rounds
+        raw = _rd(taus_p, 32 * l)
+        taus = [from_mont_bytes(P, raw[32 * i:32 * i + 32]) for i in range(l)]
+        fh, sh = l // 2, l - l // 2
+        tab = lambda lo, hi: co.eq_table(fid, raw[32 * lo:32 * hi])
+        left = [tab(fh - k, fh) for k in range(max(fh, 1))]
+        right = [tab(l - k, l) for k in range(sh + 1)]
+
+        def sums(j, n):
+            rnd = j + 1
+            L, R, shift = (left[fh - rnd], right[sh], sh) if rnd < fh else (None, right[l - rnd], 0)
+            g = lambda Z: _rd(Z, 32 * n)
+            out = co.sc_eval(fid, 4, g(A), g(B), g(C), L, R, shift)
+            if taus[j] == 0:
+                out += co.sc_eval(fid, 7, g(A), g(B), g(C), L, R, shift)
+            return out
+        return self._sumcheck_loop(fid, lambda j: 2 if taus[j] == 0 else 1, claim, num_rounds, [A, B, C], tr, pending,
+                                   pending_len, polys_out, r_out, finals_out, 3, sums, taus)
+
     # ---- sparse matrices ----------------------------------------------------------------------
     def b200_spmv_register(self, fid, data, indices, indptr, rows, cols, out_handle):
         ip = [int(indptr[i]) for i in range(rows + 1)]
@@ -205,6 +278,13 @@ class EmulatedDevice:
 
     def b200_ck_register(self, curve_id, bases, n, h, window_bits, out_handle):
         self.keys[self.next_handle] = (curve_id, _rd(bases, 64 * n), _rd(h, 64) if _addr(h) else None)
+        out_handle._obj.value = self.next_handle
+        self.next_handle += 1
+        return 0
+
+    def b200_ck_setup_synthetic(self, curve_id, gen, k0, n, with_h, window_bits, out_handle):
+        bases = co.gen_bases(curve_id, n + (1 if with_h else 0), int(k0))  # P_i = (k0 + i) G
+        self.keys[self.next_handle] = (curve_id, bases[:64 * n], bases[64 * n:] if with_h else None)
         out_handle._obj.value = self.next_handle
         self.next_handle += 1
         return 0

@@ -345,3 +345,65 @@ extern "C" int hc_mul2_add(int fid, const void* a, const void* b, const void* c,
   }
   return 0;
 }
+
+// ---- batched sum-check round (transcript_batched.cuh): the body of k_sc_round_batched, sequentially ----
+#include "../../nova_b200/csrc/transcript_batched.cuh"
+
+template <class F>
+static void sc_round_batched_t(const scb_desc& d, scb_state* state, const fe_t* sums, const uint8_t* pending,
+                               uint32_t pending_len, uint8_t la, uint8_t ls, fe_t* out_poly, fe_t* out_r) {
+  static msg_buf msg;
+  const scb_state st = *state;  // every "lane" reads the state of the round's start
+  fe_t evs[SCB_MAX_CLAIMS][3];
+  for (int i = 0; i < d.nclaims; i++) {
+    fe_t s[3] = {sums[d.slot[i]], sums[d.slot[i] + 1], sums[d.slot[i] + 2]};
+    fe_t tau = fe_zero<F>(), tau_inv = fe_zero<F>(), tm1 = fe_zero<F>();
+    const bool eqc = d.kind[i] >= SCB_EQ_DEG2;
+    const bool has_m1 = eqc && d.slot_m1[i] >= 0;
+    if (eqc) {
+      tau = *(const fe_t*)d.tau[d.eq_of[i]];
+      if (has_m1) tm1 = sums[d.slot_m1[i]];
+      else tau_inv = *(const fe_t*)d.tau_inv[d.eq_of[i]];
+    }
+    scb_claim_evals<F>(d, i, st, s, has_m1 ? &tm1 : nullptr, tau, tau_inv, evs[i]);
+  }
+  fe_t comb[3];
+  for (int k = 0; k < 3; k++) comb[k] = scb_combine<F>(d, st, evs, k);
+  sc_round_poly poly;
+  scb_poly<F>(st.head.claim, comb[0], comb[1], comb[2], poly);
+  fe_t canon[3];
+  sc_round_compressed<F>(poly, canon);
+  uint32_t flip = sc_round_message(msg, pending, pending_len, la, canon, 3, st.head, ls);
+  for (int k = 0; k < 3; k++) out_poly[k] = canon[k];
+  uint64_t digest[8], dg[4];
+  for (int lane = 0; lane < 2; lane++) {
+    keccak256_msg(msg, flip, (uint8_t)lane, dg);
+    for (int i = 0; i < 4; i++) digest[4 * lane + i] = dg[i];
+  }
+  sc_state head = st.head;
+  fe_t r = sc_round_finish<F>(SC_ROUND_QUAD_PROD, head, poly, digest);
+  for (int i = 0; i < d.nclaims; i++)
+    if (d.kind[i] >= SCB_EQ_DEG2) state->claim[i] = scb_update_claim<F>(st.claim[i], evs[i], r);
+  for (int g = 0; g < d.neq; g++) state->q[g] = scb_bound<F>(st.q[g], *(const fe_t*)d.tau[g], r);
+  state->head = head;
+  *out_r = r;
+}
+extern "C" int hc_sc_round_batched(int fid, const void* desc, void* state, const void* sums, const void* pending,
+                                   uint32_t pending_len, int absorb_label, int squeeze_label, void* out_poly,
+                                   void* out_r) {
+  static_assert(sizeof(scb_state) == 1296, "b200_scb_state layout");
+  static_assert(sizeof(scb_desc) == 8 + 4 * 4 * SCB_MAX_CLAIMS + 2 * 8 * SCB_MAX_EQ, "b200_scb_desc layout");
+  const scb_desc& d = *(const scb_desc*)desc;
+  if (d.nclaims < 1 || d.nclaims > SCB_MAX_CLAIMS || d.neq < 0 || d.neq > SCB_MAX_EQ) return 1;
+#define RUNB(FT) sc_round_batched_t<FT>(d, (scb_state*)state, (const fe_t*)sums, (const uint8_t*)pending, pending_len, \
+                                        (uint8_t)absorb_label, (uint8_t)squeeze_label, (fe_t*)out_poly, (fe_t*)out_r)
+  switch (fid) {
+    case 0: RUNB(BN254_FR); break;
+    case 1: RUNB(BN254_FQ); break;
+    case 2: RUNB(PALLAS_FP); break;
+    case 3: RUNB(PALLAS_FQ); break;
+    default: return 1;
+  }
+#undef RUNB
+  return 0;
+}

@@ -31,7 +31,7 @@ def csr(M, rows):
 
 
 @pytest.mark.parametrize("cid,num_cons,num_vars", [(0, 8, 8), (1, 16, 8), (3, 4, 16), (0, 64, 64), (2, 256, 128)])
-def test_prove_core_matches_oracle(b200, oracle, cid, num_cons, num_vars):
+def test_prove_core_matches_oracle(b200, oracle, cid, num_cons, num_vars, device_transcript=False):
     from nova_b200 import ppsnark as dp
     from nova_b200 import spartan as sp
     c = CURVES[cid]
@@ -57,7 +57,8 @@ def test_prove_core_matches_oracle(b200, oracle, cid, num_cons, num_vars):
     spark = dp.SparkRepr(fid, S["A"], S["B"], S["C"], num_cons, num_vars)
     assert spark.N == N
     Wd = dict(W=pack(p, W["W"]), E=pack(p, W["E"]))
-    got = dp.prove_core(b200.Curve(cid), ck, Sd, spark, U, Wd, 777, Keccak256Transcript(p, b"RelaxedR1CSSNARK"))
+    got = dp.prove_core(b200.Curve(cid), ck, Sd, spark, U, Wd, 777, Keccak256Transcript(p, b"RelaxedR1CSSNARK"),
+                        device_transcript=device_transcript)
 
     for k in ref:
         if k in ("batched_poly", "transcript"):

@@ -19,6 +19,56 @@ def emulated():
 
 
 @pytest.mark.parametrize("cid,num_cons,num_vars", [(0, 8, 8), (1, 16, 8), (3, 4, 16)])
-def test_ppsnark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars):
+@pytest.mark.parametrize("device_transcript", [False, True])
+def test_ppsnark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars, device_transcript):
+    """device_transcript=True: outer sum-check through the fused loop and the batched inner sum-check through
+    b200_sc_round_batched_dev, both answered by the HOST BUILD of the device round kernels."""
     import test_ppsnark_gpu
-    test_ppsnark_gpu.test_prove_core_matches_oracle(emulated, oracle, cid, num_cons, num_vars)
+    test_ppsnark_gpu.test_prove_core_matches_oracle(emulated, oracle, cid, num_cons, num_vars, device_transcript)
+
+
+@pytest.mark.parametrize("zero_rho,zero_outer", [((), ()), ((0,), ()), ((2,), (1,)), ((0, 3), (0, 3))])
+def test_batched_round_with_zero_taus(emulated, oracle, zero_rho, zero_outer):
+    """prove_helper with eq instances whose tau is 0 in some rounds (the third-sum fall-back,
+    sumcheck.rs:1082-1213): host-transcript loop, device-transcript loop and the oracle's prove_helper agree.
+    The engines are fed random polynomials directly (the prover does not check their consistency)."""
+    from nova_b200 import ppsnark as dp
+    from nova_b200 import spartan as sp
+    from oracle import ppsnark_ref as pr
+    from oracle.pyref import FIELD_MODULUS, Keccak256Transcript, SplitMix64, mont_bytes
+    fid, ell = 0, 4
+    p, N = FIELD_MODULUS[fid], 1 << ell
+    rng = SplitMix64(5150 + len(zero_rho) + 7 * len(zero_outer))
+    vec = lambda: [rng.field(p) for _ in range(N)]
+    pack = lambda xs: b"".join(mont_bytes(p, x) for x in xs)
+    oracles, aux, ts_row, ts_col = [vec() for _ in range(4)], [vec() for _ in range(4)], vec(), vec()
+    L_row, L_col, val, E, W = vec(), vec(), vec(), vec(), vec()
+    rhos = [0 if i in zero_rho else rng.field(p) for i in range(ell)]
+    r_outer = [0 if i in zero_outer else rng.field(p) for i in range(ell)]
+    claim, claim_E = rng.field(p), rng.field(p)
+    num_vars = 4
+
+    def ref_run():
+        mem = pr.MemorySumcheckInstance(p, oracles, aux, rhos, ts_row, ts_col)
+        inner = pr.InnerBatchedSumcheckInstance(p, claim, L_row, L_col, val, claim_E, r_outer, E)
+        wit = pr.WitnessBoundSumcheck(p, r_outer, W, num_vars)
+        tr = Keccak256Transcript(p, b"zt")
+        tr.absorb_scalar(b"k", 3)
+        return pr.prove_helper(p, mem, inner, wit, tr), tr.squeeze(b"after")
+
+    def dev_run(helper):
+        up = lambda v: sp.DeviceVec.from_bytes(pack(v))
+        mem = dp.MemorySumcheckInstance(fid, N, [up(v) for v in oracles], [up(v) for v in aux], rhos, up(ts_row), up(ts_col))
+        inner = dp.InnerBatchedSumcheckInstance(fid, N, claim, up(L_row), up(L_col), up(val), claim_E, r_outer, up(E))
+        wit = dp.WitnessBoundSumcheck(fid, N, r_outer, up(W), num_vars)
+        tr = Keccak256Transcript(p, b"zt")
+        tr.absorb_scalar(b"k", 3)
+        return helper(fid, mem, inner, wit, tr), tr.squeeze(b"after")
+
+    exp, exp_after = ref_run()
+    for helper in (dp.prove_helper, dp.prove_helper_device):
+        got, after = dev_run(helper)
+        assert [list(q) for q in got[0]] == [list(q) for q in exp[0]], helper.__name__
+        assert list(got[1]) == list(exp[1])
+        assert got[2:] == exp[2:]
+        assert after == exp_after

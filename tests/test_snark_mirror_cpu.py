@@ -20,6 +20,9 @@ def emulated():
 
 
 @pytest.mark.parametrize("cid,num_cons,num_vars,num_io", [(0, 4, 4, 1), (0, 16, 8, 2), (1, 8, 16, 2), (3, 32, 32, 3)])
-def test_snark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars, num_io):
+@pytest.mark.parametrize("device_transcript", [False, True])
+def test_snark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars, num_io, device_transcript):
+    """device_transcript=True: the emulated device strings the HOST BUILD of the round kernel together as
+    csrc/capi_sumcheck.inc does, so the mirror's marshalling of the transcript is covered too."""
     from snark_parity import run_case
-    run_case(emulated, oracle, cid, num_cons, num_vars, num_io, device_transcript=False)
+    run_case(emulated, oracle, cid, num_cons, num_vars, num_io, device_transcript=device_transcript)

@@ -257,3 +257,18 @@ def test_cpp_mirror_resident_folding_step(oracle, tmp_path):
     import test_cpp_mirror as tcm
     tcm.build()
     tcm.check_fold(tcm.EXE, oracle, tmp_path)
+
+
+@pytest.mark.parametrize("cid,num_cons,num_vars", [(0, 8, 8), (1, 16, 8), (3, 4, 16), (0, 64, 64)])
+def test_ppsnark_prove_core_device_transcript(b200, oracle, cid, num_cons, num_vars):
+    """The MicroSpartan prover core with the outer sum-check as one fused call and the batched inner sum-check
+    (prove_helper, ppsnark.rs:886-983) through b200_sc_round_batched_dev: every prover message equals the
+    oracle's.  CPU twin (host build of the kernels + emulated device): tests/test_ppsnark_mirror_cpu.py."""
+    import test_ppsnark_gpu
+    test_ppsnark_gpu.test_prove_core_matches_oracle(b200, oracle, cid, num_cons, num_vars, True)
+
+
+@pytest.mark.parametrize("zero_rho,zero_outer", [((), ()), ((0,), ()), ((2,), (1,)), ((0, 3), (0, 3))])
+def test_batched_round_with_zero_taus_on_device(b200, oracle, zero_rho, zero_outer):
+    import test_ppsnark_mirror_cpu as t
+    t.test_batched_round_with_zero_taus(b200, oracle, zero_rho, zero_outer)

@@ -27,18 +27,19 @@ import numpy as np
 
 
 class ReplayTranscript:
-    """absorb_bytes / squeeze with BLAKE2b: deterministic challenges for timing runs only."""
+    """absorb_bytes / squeeze with BLAKE2b: deterministic challenges for timing runs only.  Carries the
+    serialisable fields of Keccak256Transcript (round, state, buf) so the device loops can continue it."""
 
     def __init__(self, p):
-        self.p, self.h, self.round = p, hashlib.blake2b(b"ppsnark-replay"), 0
+        self.p, self.round, self.state, self.buf = p, 0, bytes(64), b""
 
     def absorb_bytes(self, label, b):
-        self.h.update(label + b)
+        self.buf += label + b
 
     def squeeze(self, label):
-        self.h.update(label + self.round.to_bytes(8, "little"))
-        self.round += 1
-        return int.from_bytes(self.h.digest(), "little") % self.p
+        out = hashlib.blake2b(self.buf + self.round.to_bytes(8, "little") + self.state + label).digest()
+        self.round, self.state, self.buf = self.round + 1, out, b""
+        return int.from_bytes(out, "little") % self.p
 
 
 def synth_matrix(rng, rows, cols, mean_extra):
@@ -53,7 +54,7 @@ def synth_matrix(rng, rows, cols, mean_extra):
     return r, indices, indptr, codes
 
 
-def run(log2cons=18, curve_id=0, reps=3, seed=5):
+def run(log2cons=18, curve_id=0, reps=3, seed=5, device_transcript=False):
     import nova_b200 as nb
     from nova_b200 import fields, ppsnark as dp, spartan as sp
     from nova_b200.native import check, lib
@@ -117,7 +118,8 @@ def run(log2cons=18, curve_id=0, reps=3, seed=5):
     for rep in range(reps + 1):
         tm = {}
         t1 = time.perf_counter()
-        out = dp.prove_core(curve, ck, S, spark, U, dict(W=Wd, E=Ed), 1, ReplayTranscript(p), timings=tm)
+        out = dp.prove_core(curve, ck, S, spark, U, dict(W=Wd, E=Ed), 1, ReplayTranscript(p), timings=tm,
+                            device_transcript=device_transcript)
         check(L.b200_sync())
         tm["total"] = time.perf_counter() - t1
         if rep:  # first pass warms the allocator and the key's workspace
@@ -136,5 +138,7 @@ if __name__ == "__main__":
     ap.add_argument("--log2cons", type=int, default=18)
     ap.add_argument("--curve", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--device-transcript", action="store_true",
+                    help="outer sum-check as one fused call, batched inner sum-check through b200_sc_round_batched_dev")
     a = ap.parse_args()
-    print(json.dumps(run(a.log2cons, a.curve, a.reps)))
+    print(json.dumps(run(a.log2cons, a.curve, a.reps, device_transcript=a.device_transcript)))
