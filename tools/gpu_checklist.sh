@@ -28,5 +28,6 @@ run sumcheck_replay  timeout 300  python tools/sumcheck_replay.py --log-n 20 --r
 run snark_dev        timeout 600  python tools/snark_replay.py --log2cons 20 --reps 2
 run snark_host       timeout 600  python tools/snark_replay.py --log2cons 20 --reps 2 --host-transcript
 run ppsnark_replay   timeout 600  python tools/ppsnark_replay.py --log2cons 18 --reps 2
+run ppsnark_dev      timeout 600  python tools/ppsnark_replay.py --log2cons 18 --reps 2 --device-transcript
 
 grep -h "passed\|failed\|error" "$OUT"/zz_new_paths.log "$OUT"/gpu_suite.log "$OUT"/y3_parity.log 2>/dev/null | tail -6 | tee -a "$OUT/summary.txt"
