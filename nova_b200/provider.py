@@ -77,6 +77,9 @@ class CommitmentKey:
                                      window_bits, ctypes.byref(handle)))
         self.handle = handle.value
         self.has_h = h is not None
+        # the host keeps `ck.ck` / `ck.h` as the reference does (pedersen.rs:32-38): commit_sparse gathers
+        # bases on the host (pedersen.rs:418-420) and the `+ h * r` terms are commitment-sized host work
+        self.bases, self.h = bases, h
 
     @classmethod
     def setup_synthetic(cls, curve: "Curve", n: int, k0: int = 0x5EED, with_h: bool = False,
@@ -93,6 +96,7 @@ class CommitmentKey:
         check(lib().b200_ck_setup_synthetic(int(curve), _cbuf(g), k0, n, int(with_h), window_bits,
                                             ctypes.byref(handle)))
         self.handle = handle.value
+        self.bases, self.h = None, None  # built on the device: no host copy
         return self
 
     @staticmethod
@@ -149,13 +153,14 @@ class DlogGroup:
         return [_jac_to_affine(self.curve, out.raw[96 * j:96 * j + 96]) for j in range(k)]
 
     def vartime_multiscalar_mul_small(self, scalars, ck: CommitmentKey, elem_bytes: int = 8,
-                                      max_num_bits: int = 0):
-        """msm_small / msm_small_with_max_num_bits (msm.rs:469-503) on integer scalars."""
+                                      max_num_bits: int = 0, base_offset: int = 0):
+        """msm_small / msm_small_with_max_num_bits (msm.rs:469-503) on integer scalars, over
+        ck[base_offset .. base_offset + len(scalars))."""
         n = len(scalars)
-        assert n <= len(ck)
+        assert base_offset + n <= len(ck)
         raw = b"".join(int(s).to_bytes(elem_bytes, "little") for s in scalars)
         out = ctypes.create_string_buffer(96)
-        check(lib().b200_msm_small(ck.handle, 0, _cbuf(raw), elem_bytes, n, max_num_bits, out))
+        check(lib().b200_msm_small(ck.handle, base_offset, _cbuf(raw), elem_bytes, n, max_num_bits, out))
         return _jac_to_affine(self.curve, out.raw)
 
     def batch_add(self, ck: CommitmentKey, one_indices) -> tuple | None:
@@ -189,8 +194,38 @@ class CommitmentEngine:
     def commit_small(self, ck: CommitmentKey, v, elem_bytes: int = 8):
         return self.group.vartime_multiscalar_mul_small(v, ck, elem_bytes)
 
-    def commit_sparse_binary(self, ck: CommitmentKey, non_zero_indices):
-        return self.group.batch_add(ck, non_zero_indices)
+    def _plus_blind(self, ck: CommitmentKey, P, r: bytes | None):
+        """P + h * r: the commitment-sized term the reference adds on the host (pedersen.rs:281, 300-302)."""
+        fid = self.curve.scalar_field
+        if not r or fields.from_mont_bytes(fid, r) == 0:
+            return P
+        assert ck.h is not None, "key has no blinding generator on the host"
+        bf = self.curve.base_field
+        Pb = bytes(64) if P is None else fields.to_mont_bytes(bf, P[0]) + fields.to_mont_bytes(bf, P[1])
+        return self.group.vartime_multiscalar_mul(fields.to_mont_bytes(fid, 1) + r, Pb + ck.h)
+
+    def commit_sparse_binary(self, ck: CommitmentKey, non_zero_indices, r: bytes | None = None):
+        """pedersen.rs:396-409: batch_add over the key + h * r."""
+        return self._plus_blind(ck, self.group.batch_add(ck, non_zero_indices), r)
+
+    def commit_small_range(self, ck: CommitmentKey, v, r: bytes | None, lo: int, hi: int, max_num_bits: int,
+                           elem_bytes: int = 8):
+        """pedersen.rs:285-305: msm_small_with_max_num_bits(v[lo..hi], ck[lo..hi]) + h * r."""
+        assert hi <= len(ck) and hi <= len(v)
+        P = self.group.vartime_multiscalar_mul_small(v[lo:hi], ck, elem_bytes, max_num_bits, base_offset=lo)
+        return self._plus_blind(ck, P, r)
+
+    def commit_sparse(self, ck: CommitmentKey, indices, scalars: bytes, r: bytes | None = None):
+        """pedersen.rs:411-427: gather ck[indices] on the host, one MSM over the gathered bases (+ h * r as
+        one more pair)."""
+        assert len(indices) * 32 == len(scalars)  # pedersen.rs:417
+        assert ck.bases is not None, "key has no host copy of its bases"
+        bases = b"".join(ck.bases[64 * i:64 * i + 64] for i in indices)
+        fid = self.curve.scalar_field
+        if r and fields.from_mont_bytes(fid, r):
+            assert ck.h is not None
+            scalars, bases = scalars + r, bases + ck.h
+        return self.group.vartime_multiscalar_mul(scalars, bases)
 
 
 class WitnessStream:

@@ -271,6 +271,18 @@ class EmulatedDevice:
         return 0
 
     # ---- commitment keys ----------------------------------------------------------------------
+    def b200_msm_small(self, handle, off, scalars, elem_bytes, n, max_bits, out):
+        curve_id, bases, _ = self.keys[handle]
+        raw = _rd(scalars, elem_bytes * n)
+        vals = [int.from_bytes(raw[elem_bytes * i:elem_bytes * (i + 1)], "little") for i in range(n)]
+        _wr(out, self._jacobian(curve_id, co.msm_small(curve_id, vals, bases[64 * off:64 * (off + n)], max_bits if max_bits > 0 else -1)))
+        return 0
+
+    def b200_msm_indices(self, handle, idx, m, out):
+        curve_id, bases, _ = self.keys[handle]
+        _wr(out, self._jacobian(curve_id, co.batch_add(curve_id, bases, [int(idx[i]) for i in range(m)])))
+        return 0
+
     def b200_commit_many_dev(self, handle, ptrs, lens, k, out, stream):
         for j in range(k):
             self.b200_commit_dev(handle, ptrs[j], lens[j], None, _addr(out) + 96 * j, stream)

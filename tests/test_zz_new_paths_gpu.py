@@ -272,3 +272,11 @@ def test_ppsnark_prove_core_device_transcript(b200, oracle, cid, num_cons, num_v
 def test_batched_round_with_zero_taus_on_device(b200, oracle, zero_rho, zero_outer):
     import test_ppsnark_mirror_cpu as t
     t.test_batched_round_with_zero_taus(b200, oracle, zero_rho, zero_outer)
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_commit_variants_on_device(b200, oracle, cid):
+    """commit_small_range, commit_sparse_binary, commit_sparse with and without the blind (pedersen.rs:285-305,
+    396-427) through the provider mirror; CPU twin: tests/test_provider_mirror_cpu.py."""
+    import commit_variants_parity
+    commit_variants_parity.run(b200, oracle, cid)
