@@ -146,7 +146,8 @@ class R1CSShape:
     def is_sat_relaxed(self, ck: CommitmentKey, U: RelaxedR1CSInstance, W: RelaxedR1CSWitness) -> bool:
         """r1cs/mod.rs:474-535: Az o Bz == u Cz + E row by row, and both commitments open."""
         self._check_lengths(U)
-        Az, Bz, Cz = self.multiply_vec_dev(self._z(W.W, U.u, U.X))
+        z = self._z(W.W, U.u, U.X)             # named: the SpMVs below read it asynchronously
+        Az, Bz, Cz = self.multiply_vec_dev(z)
         slack = DeviceVec(32 * self.num_cons)  # Az o Bz - u Cz - E must vanish
         u_dev = dev_scalar(self.fid, U.u)      # (kept in a variable: it must outlive the launch)
         check(lib().b200_cross_term_dev(self.fid, Az.ptr, Bz.ptr, Cz.ptr, W.E.ptr, None, u_dev.ptr,
