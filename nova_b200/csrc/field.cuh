@@ -514,6 +514,11 @@ NOVA_D void fe_store(void* base, size_t idx, const fe_t& a) {
   p[0] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
   p[1] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
 }
+#elif defined(NOVA_SIMT_HOST)
+// CPU run of the __global__ wrappers (tests/hostcheck/simt_host.h): plain memory accesses
+inline fe_t fe_load(const void* base, size_t idx) { return reinterpret_cast<const fe_t*>(base)[idx]; }
+inline fe_t fe_load_rw(const void* base, size_t idx) { return reinterpret_cast<const fe_t*>(base)[idx]; }
+inline void fe_store(void* base, size_t idx, const fe_t& a) { reinterpret_cast<fe_t*>(base)[idx] = a; }
 #endif
 
 }  // namespace nova

@@ -281,7 +281,7 @@ NOVA_HD fe_t sc_round_finish(int kind, sc_state& st, const sc_round_poly& p, con
   return r;
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(NOVA_SIMT_HOST)  // NOVA_SIMT_HOST: tests/hostcheck/simt_host.h
 // One warp: lanes 0 and 1 each compute one of the two squeeze hashes; the (cheap, redundant) field
 // algebra runs on both so that no result has to be broadcast.  <<<1, 32>>>.
 template <class F>

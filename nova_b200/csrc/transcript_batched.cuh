@@ -122,7 +122,7 @@ NOVA_HD fe_t scb_bound(const fe_t& q, const fe_t& tau, const fe_t& r) {
   return fe_mul<F>(q, f);
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(NOVA_SIMT_HOST)  // NOVA_SIMT_HOST: tests/hostcheck/simt_host.h
 // One warp.  Lane i < nclaims: claim i's evaluation points and claim update; lanes 0..2: one component of
 // the combination each; lanes 0/1: the two squeeze hashes; lanes g < neq: the eq bounds.  <<<1, 32>>>.
 template <class F>

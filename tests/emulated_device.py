@@ -43,6 +43,8 @@ class EmulatedDevice:
         self.keys = {}      # handle -> (curve, bases, h or None)
         self.graveyard = []
         self.hc = None
+        self.hc_simt = None
+        self.use_simt = False
         self.next_handle = 1
         self.err = b""
 
@@ -144,8 +146,23 @@ class EmulatedDevice:
             self.hc = ctypes.CDLL(so)
         return self.hc
 
+    def _hc_simt(self):
+        if self.hc_simt is None:
+            import os
+            import subprocess
+            here = os.path.dirname(os.path.abspath(__file__))
+            src, so = os.path.join(here, "hostcheck", "simt_check.cpp"), os.path.join(here, "hostcheck", "libhostcheck_simt.so")
+            csrc = os.path.join(here, "..", "nova_b200", "csrc")
+            deps = [src, os.path.join(here, "hostcheck", "simt_host.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+            if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+            self.hc_simt = ctypes.CDLL(so)
+        return self.hc_simt
+
     def b200_sc_round_batched_dev(self, fid, desc, sums, state, pending, pending_len, la, ls, poly_out, r_out, stream):
-        rc = self._hc().hc_sc_round_batched(fid, ctypes.c_void_p(_addr(desc)), ctypes.c_void_p(_addr(state)),
+        # use_simt: the real one-warp kernel on 32 host threads (tests/hostcheck/simt_host.h) instead of its body
+        fn = self._hc_simt().hc_simt_sc_round_batched if self.use_simt else self._hc().hc_sc_round_batched
+        rc = fn(fid, ctypes.c_void_p(_addr(desc)), ctypes.c_void_p(_addr(state)),
                                             ctypes.c_void_p(_addr(sums)), ctypes.c_void_p(_addr(pending)), int(pending_len),
                                             la, ls, ctypes.c_void_p(_addr(poly_out)), ctypes.c_void_p(_addr(r_out)))
         return 0 if rc == 0 else 1

@@ -28,6 +28,25 @@ def hc():
     return ctypes.CDLL(so)
 
 
+@pytest.fixture(scope="module")
+def hc_simt():
+    """The REAL kernel wrappers (k_sc_round, k_sc_round_batched) run as 32 host threads through the SIMT shim
+    (tests/hostcheck/simt_host.h): lane roles, shared-memory hand-offs and barriers are exercised too."""
+    src = os.path.join(HERE, "hostcheck", "simt_check.cpp")
+    so = os.path.join(HERE, "hostcheck", "libhostcheck_simt.so")
+    csrc = os.path.join(HERE, "..", "nova_b200", "csrc")
+    deps = [src, os.path.join(HERE, "hostcheck", "simt_host.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+    return ctypes.CDLL(so)
+
+
+@pytest.fixture(params=["sequential", "simt"])
+def round_fn(request, hc, hc_simt):
+    """The round step two ways: the kernel body called sequentially, and the real one-warp kernel on 32 threads."""
+    return hc.hc_sc_round if request.param == "sequential" else hc_simt.hc_simt_sc_round
+
+
 def _buf(b):
     return ctypes.create_string_buffer(b, len(b))
 
@@ -64,8 +83,8 @@ def test_from_uniform(hc, fid):
 class HostRoundEngine:
     """State + one call per round, exactly what the device loop keeps in `b200_sc_state`."""
 
-    def __init__(self, hc, fid, claim, transcript):
-        self.hc, self.fid, self.p = hc, fid, FIELD_MODULUS[fid]
+    def __init__(self, round_fn, fid, claim, transcript):
+        self.round_fn, self.fid, self.p = round_fn, fid, FIELD_MODULUS[fid]
         self.state = _buf(mont_bytes(self.p, claim) + mont_bytes(self.p, 1) + struct.pack("<Q", transcript.round) +
                           transcript.state + struct.pack("<Q", 0))
         assert len(self.state.raw) == 144
@@ -79,8 +98,8 @@ class HostRoundEngine:
         tinv = _buf(mont_bytes(p, pow(tau, -1, p))) if tau else None
         poly, r = ctypes.create_string_buffer(96), ctypes.create_string_buffer(32)
         pend = _buf(self.pending) if self.pending else None
-        assert self.hc.hc_sc_round(self.fid, kind, self.state, resb, taub, tinv, pend, len(self.pending), ord("p"),
-                                   ord("c"), poly, r) == 0
+        assert self.round_fn(self.fid, kind, self.state, resb, taub, tinv, pend, len(self.pending), ord("p"),
+                             ord("c"), poly, r) == 0
         self.pending = b""
         ncoef = 2 if kind == QUAD else 3
         coeffs = [int.from_bytes(poly.raw[32 * k:32 * k + 32], "little") for k in range(ncoef)]
@@ -97,7 +116,7 @@ class HostRoundEngine:
 
 @pytest.mark.parametrize("fid", [0, 1, 2, 3])
 @pytest.mark.parametrize("prefix_absorbs", [0, 3, 40])
-def test_quad_prod_proof_through_device_round_code(hc, fid, prefix_absorbs):
+def test_quad_prod_proof_through_device_round_code(round_fn, fid, prefix_absorbs):
     p = FIELD_MODULUS[fid]
     rng = SplitMix64(100 + fid + prefix_absorbs)
     l = 5
@@ -110,7 +129,7 @@ def test_quad_prod_proof_through_device_round_code(hc, fid, prefix_absorbs):
         t_ref.absorb_scalar(b"x", x)
         t_dev.absorb_scalar(b"x", x)
     exp_polys, exp_rs, exp_finals = pyref.prove_quad_prod(p, claim, l, A, B, t_ref)
-    eng = HostRoundEngine(hc, fid, claim, t_dev)
+    eng = HostRoundEngine(round_fn, fid, claim, t_dev)
     polys, rs = [], []
     for _ in range(l):
         h = len(A) // 2
@@ -128,7 +147,7 @@ def test_quad_prod_proof_through_device_round_code(hc, fid, prefix_absorbs):
 
 @pytest.mark.parametrize("fid", [0, 3])
 @pytest.mark.parametrize("zero_tau_at", [None, 0, 2, 5])
-def test_cubic3_eq_proof_through_device_round_code(hc, fid, zero_tau_at):
+def test_cubic3_eq_proof_through_device_round_code(round_fn, fid, zero_tau_at):
     """Includes tau = 0 rounds, where the reference takes the third-sum fall-back (sumcheck.rs:696-698)."""
     p = FIELD_MODULUS[fid]
     rng = SplitMix64(200 + fid)
@@ -144,7 +163,7 @@ def test_cubic3_eq_proof_through_device_round_code(hc, fid, zero_tau_at):
     t_ref.absorb_scalar(b"k", 9)
     t_dev.absorb_scalar(b"k", 9)
     exp_polys, exp_rs, exp_finals = pyref.prove_cubic_with_three_inputs(p, claim, taus, A, B, C, t_ref)
-    eng = HostRoundEngine(hc, fid, claim, t_dev)
+    eng = HostRoundEngine(round_fn, fid, claim, t_dev)
     eq = pyref.EqSumCheckInstance(p, taus)  # used for its table selection only
     polys, rs = [], []
     for j in range(l):

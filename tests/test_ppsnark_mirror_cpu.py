@@ -18,6 +18,16 @@ def emulated():
     emulated_device.uninstall()
 
 
+@pytest.fixture()
+def emulated_simt():
+    """Same, with b200_sc_round_batched_dev answered by the REAL kernel k_sc_round_batched on 32 host threads."""
+    import nova_b200
+    emulated_device.install().use_simt = True
+    yield nova_b200
+    gc.collect()
+    emulated_device.uninstall()
+
+
 @pytest.mark.parametrize("cid,num_cons,num_vars", [(0, 8, 8), (1, 16, 8), (3, 4, 16)])
 @pytest.mark.parametrize("device_transcript", [False, True])
 def test_ppsnark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars, device_transcript):
@@ -72,3 +82,15 @@ def test_batched_round_with_zero_taus(emulated, oracle, zero_rho, zero_outer):
         assert list(got[1]) == list(exp[1])
         assert got[2:] == exp[2:]
         assert after == exp_after
+
+
+@pytest.mark.parametrize("zero_rho,zero_outer", [((), ()), ((2,), (1,)), ((0, 3), (0, 3))])
+def test_batched_round_kernel_wrapper_on_32_threads(emulated_simt, oracle, zero_rho, zero_outer):
+    """The one-warp kernel wrapper itself (lane i = claim i, lanes 0..2 combine, lanes 0/1 hash, shared-memory
+    hand-offs between __syncwarp barriers) through the SIMT shim."""
+    test_batched_round_with_zero_taus(emulated_simt, oracle, zero_rho, zero_outer)
+
+
+def test_ppsnark_prove_core_kernel_wrapper_on_32_threads(emulated_simt, oracle):
+    import test_ppsnark_gpu
+    test_ppsnark_gpu.test_prove_core_matches_oracle(emulated_simt, oracle, 0, 8, 8, True)
