@@ -464,6 +464,56 @@ class SumcheckProof:
         return polys, rs, finals
 
 
+    @staticmethod
+    def prove_batched_cubic(fid, claim, taus, polys_A: list, polys_B: list, polys_C: list, alphas, transcript):
+        """sumcheck.rs:513-577: sum_x eq(tau, x) sum_i alpha_i (A_i B_i - C_i)(x) over K instance triples.
+        The inner polynomial is linear in the instances, so t(0), t(inf) (and t(-1) in a tau = 0 round) are
+        the alpha-combinations of the K single-instance reductions (form eq_cubic3), one launch pair each,
+        all read back at once.  -> (compressed polys, r, [[A_i(r), B_i(r), C_i(r)]])."""
+        p = fields.MODULUS[fid]
+        k = len(polys_A)
+        if k == 0:
+            raise ValueError("InvalidNumInstances")  # sumcheck.rs:524-526
+        assert k == len(polys_B) == len(polys_C) == len(alphas) and k <= 16
+        dev = [[P if isinstance(P, DeviceVec) else DeviceVec.from_bytes(P) for P in V] for V in (polys_A, polys_B, polys_C)]
+        length = 1 << len(taus)
+        eq = EqSumCheckInstance(fid, taus)
+        out = _small_buf("batched_cubic_sums", 96 * 16)
+        rs, polys = [], []
+
+        def sums(form, nout):
+            L, R, sh = eq._tables()
+            for i in range(k):
+                dst = ctypes.c_void_p(out.ptr.value + 96 * i)
+                check(lib().b200_sc_eval_dev(fid, form, dev[0][i].ptr, dev[1][i].ptr, dev[2][i].ptr, length,
+                                             L.ptr if L else None, R.ptr, sh, dst, None))
+            raw = out.to_bytes(96 * k)
+            per = [fields.unpack(fid, raw[96 * i:96 * i + 32 * nout]) for i in range(k)]
+            return [sum(a * v[c] for a, v in zip(alphas, per)) % p for c in range(nout)]
+        for _ in range(len(taus)):
+            t0, tinf = sums(SC_EQ_CUBIC3, 2)
+            d = eq._derive(t0, tinf, claim, True)
+            if d is None:  # tau = 0 (sumcheck.rs:838-890)
+                (tm1,) = sums(SC_EQ_CUBIC3_M1, 1)
+                e0c, slope, em1c = eq.eq_tau_0_a_inf[eq.round - 1]
+                q = eq.eval_eq_left
+                d = (e0c * q * t0 % p, slope * q * tinf % p, em1c * q * tm1 % p)
+            e0, lead, em1 = d
+            poly = UniPoly.from_evals_deg3(p, [e0, (claim - e0) % p, lead, em1])
+            transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+            r = transcript.squeeze(b"c")
+            rs.append(r)
+            polys.append(poly.compress())
+            claim = poly.evaluate(r)
+            r_dev = _challenge_dev(fid, r)
+            for V in dev:
+                for Z in V:
+                    check(lib().b200_bind_top_dev(fid, Z.ptr, length, r_dev.ptr, None))
+            eq.bound(r)
+            length //= 2
+        finals = [[fields.unpack(fid, dev[c][i].to_bytes(32))[0] for c in range(3)] for i in range(k)]
+        return polys, rs, finals
+
     # ---- the same two loops with the transcript on the device (SURVEY.md §8f-3) --------------------
     # One FFI call each: every round's reduction, round algebra + Keccak and binds are enqueued back
     # to back (csrc/capi_sumcheck.inc); the host reads the proof once.  `transcript` is any object

@@ -576,6 +576,53 @@ def prove_cubic_with_three_inputs(p, claim, taus, A, B, C, transcript):
     return polys, rs, [A[0], B[0], C[0]]
 
 
+def prove_batched_cubic(p, claim, taus, As, Bs, Cs, alphas, transcript):
+    """SumcheckProof::prove_batched_cubic (sumcheck.rs:513-577) with
+    EqSumCheckInstance::evaluation_points_batched_cubic (sumcheck.rs:755-835) and its tau = 0 fall-back
+    (:838-890): sum_x eq(tau, x) sum_i alpha_i (A_i B_i - C_i)(x) for K instance triples.
+    Returns (compressed polys, r, [[A_i(r), B_i(r), C_i(r)] for i])."""
+    As, Bs, Cs = [list(v) for v in As], [list(v) for v in Bs], [list(v) for v in Cs]
+    k = len(As)
+    assert k > 0 and k == len(Bs) == len(Cs) == len(alphas)
+    eq = EqSumCheckInstance(p, taus)
+    rs, polys = [], []
+    for _ in range(len(taus)):
+        h = len(As[0]) // 2
+        t0 = tinf = 0
+        for idx in range(h):  # the reference's per-index accumulation over the K instances
+            e0 = q = 0
+            for i in range(k):
+                e0 += alphas[i] * (As[i][idx] * Bs[i][idx] - Cs[i][idx])
+                q += alphas[i] * (As[i][h + idx] - As[i][idx]) * (Bs[i][h + idx] - Bs[i][idx])
+            f = eq.factor(idx)
+            t0 += e0 * f
+            tinf += q * f
+        t0 %= p
+        tinf %= p
+        d = eq.derive_deg2(t0, tinf, claim)
+        if d is None:  # tau = 0: third sum
+            e0c, slope, em1c = eq.eq_tau_0_a_inf[eq.round - 1]
+            tm1 = 0
+            for idx in range(h):
+                acc = 0
+                for i in range(k):
+                    ma, mb, mc = (2 * V[i][idx] - V[i][h + idx] for V in (As, Bs, Cs))
+                    acc += alphas[i] * (ma * mb - mc)
+                tm1 += acc * eq.factor(idx)
+            ql = eq.eval_eq_left
+            d = (e0c * ql * t0 % p, slope * ql * tinf % p, em1c * ql * tm1 % p)
+        e0, lead, em1 = d
+        poly = UniPoly.from_evals_deg3(p, [e0, (claim - e0) % p, lead, em1])
+        transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+        r = transcript.squeeze(b"c")
+        rs.append(r)
+        polys.append(poly.compressed())
+        claim = poly.evaluate(r)
+        As, Bs, Cs = ([bind_top(p, v, r) for v in V] for V in (As, Bs, Cs))
+        eq.bound(r)
+    return polys, rs, [[As[i][0], Bs[i][0], Cs[i][0]] for i in range(k)]
+
+
 def update_claim(p, claim, evals, r):
     """SumcheckProof::update_claim (sumcheck.rs:68-75)."""
     e0, c3, em1 = evals

@@ -12,7 +12,7 @@ import pytest
 
 from oracle.ppsnark_ref import eq_evaluate, sumcheck_verify
 from oracle.pyref import (FIELD_MODULUS, Keccak256Transcript, SplitMix64, eq_evals, mle_evaluate, prove_batch_eval,
-                          prove_cubic_with_three_inputs, prove_quad_prod)
+                          prove_batched_cubic, prove_cubic_with_three_inputs, prove_quad_prod)
 
 
 @pytest.mark.parametrize("fid,ell", [(0, 1), (0, 4), (3, 6)])
@@ -81,3 +81,30 @@ def test_batch_eval(fid, sizes):
     claim_bad = sum(c * pow(2, nmax - s, p) * k for c, s, k in zip(bad, sizes, coeffs)) % p
     e_bad, _ = sumcheck_verify(p, out, claim_bad, nmax, 2, Keccak256Transcript(p, b"t"))
     assert e_bad != expected % p
+
+
+@pytest.mark.parametrize("fid,k,ell,zero_tau", [(0, 1, 3, ()), (0, 3, 5, ()), (3, 2, 4, (0, 2))])
+def test_batched_cubic(fid, k, ell, zero_tau):
+    """prove_batched_cubic (sumcheck.rs:513-577): the verifier's final claim is
+    eq(tau, r) * sum_i alpha_i (A_i(r) B_i(r) - C_i(r)); with K = 1 and alpha = 1 it must coincide with
+    prove_cubic_with_three_inputs message by message."""
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(31 * fid + 7 * k + ell)
+    n = 1 << ell
+    As, Bs, Cs = ([[rng.field(p) for _ in range(n)] for _ in range(k)] for _ in range(3))
+    alphas = [rng.field(p) for _ in range(k)]
+    tau = [0 if i in zero_tau else rng.field(p) for i in range(ell)]
+    w = eq_evals(p, tau)
+    claim = sum(w[x] * sum(al * (A[x] * B[x] - C[x]) for al, A, B, C in zip(alphas, As, Bs, Cs)) for x in range(n)) % p
+    polys, rs, finals = prove_batched_cubic(p, claim, tau, As, Bs, Cs, alphas, Keccak256Transcript(p, b"t"))
+    e, rv = sumcheck_verify(p, polys, claim, ell, 3, Keccak256Transcript(p, b"t"))
+    assert rv == rs
+    for i in range(k):
+        assert finals[i] == [mle_evaluate(p, V[i], rs) for V in (As, Bs, Cs)]
+    assert e == eq_evaluate(p, tau, rs) * sum(al * (f[0] * f[1] - f[2]) for al, f in zip(alphas, finals)) % p
+    e_bad, _ = sumcheck_verify(p, polys, (claim + 1) % p, ell, 3, Keccak256Transcript(p, b"t"))
+    assert e_bad != e
+    if k == 1:
+        one = prove_batched_cubic(p, claim, tau, As, Bs, Cs, [1], Keccak256Transcript(p, b"t"))
+        ref = prove_cubic_with_three_inputs(p, claim, tau, As[0], Bs[0], Cs[0], Keccak256Transcript(p, b"t"))
+        assert (one[0], one[1], one[2][0]) == ref

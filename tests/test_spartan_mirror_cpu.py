@@ -28,3 +28,10 @@ def test_hyperkzg_prove_core_host_logic(emulated, oracle):
     import test_spartan_gpu as t
     from nova_b200 import spartan
     t.test_hyperkzg_prove_core(emulated, spartan, oracle)
+
+
+@pytest.mark.parametrize("k,l,zero", [(1, 3, ()), (3, 5, ()), (4, 6, (0, 3)), (16, 2, (1,))])
+def test_prove_batched_cubic_host_logic(emulated, oracle, k, l, zero):
+    import batched_cubic_parity
+    from nova_b200 import spartan
+    batched_cubic_parity.run(spartan, 0, k, l, zero)

@@ -280,3 +280,12 @@ def test_commit_variants_on_device(b200, oracle, cid):
     396-427) through the provider mirror; CPU twin: tests/test_provider_mirror_cpu.py."""
     import commit_variants_parity
     commit_variants_parity.run(b200, oracle, cid)
+
+
+@pytest.mark.parametrize("fid", [0, 3])
+@pytest.mark.parametrize("k,l,zero", [(1, 3, ()), (3, 9, ()), (4, 6, (0, 3)), (16, 2, (1,)), (2, 13, ())])
+def test_prove_batched_cubic_on_device(sp, fid, k, l, zero):
+    """SumcheckProof::prove_batched_cubic (sumcheck.rs:513-577) through the mirror; CPU twin in
+    tests/test_spartan_mirror_cpu.py."""
+    import batched_cubic_parity
+    batched_cubic_parity.run(sp, fid, k, l, zero)
