@@ -163,6 +163,10 @@ class DlogGroup:
         check(lib().b200_msm_small(ck.handle, base_offset, _cbuf(raw), elem_bytes, n, max_num_bits, out))
         return _jac_to_affine(self.curve, out.raw)
 
+    def batch_vartime_multiscalar_mul_small(self, scalars: list, ck: CommitmentKey, elem_bytes: int = 8) -> list:
+        """traits.rs:105-116 default: one msm_small per vector over bases[..len]."""
+        return [self.vartime_multiscalar_mul_small(v, ck, elem_bytes) for v in scalars]
+
     def batch_add(self, ck: CommitmentKey, one_indices) -> tuple | None:
         """msm.rs:689-708."""
         m = len(one_indices)
@@ -191,8 +195,13 @@ class CommitmentEngine:
         """traits/commitment.rs:94-104 default / hyperkzg.rs:594-612 with r = 0."""
         return self.group.batch_vartime_multiscalar_mul(vs, ck)
 
-    def commit_small(self, ck: CommitmentKey, v, elem_bytes: int = 8):
-        return self.group.vartime_multiscalar_mul_small(v, ck, elem_bytes)
+    def commit_small(self, ck: CommitmentKey, v, elem_bytes: int = 8, r: bytes | None = None):
+        """pedersen.rs:272-283 / hyperkzg.rs commit_small: msm_small + h * r."""
+        return self._plus_blind(ck, self.group.vartime_multiscalar_mul_small(v, ck, elem_bytes), r)
+
+    def batch_commit_small(self, ck: CommitmentKey, vs: list, elem_bytes: int = 8):
+        """hyperkzg.rs batch_commit_small with r = 0."""
+        return self.group.batch_vartime_multiscalar_mul_small(vs, ck, elem_bytes)
 
     def _plus_blind(self, ck: CommitmentKey, P, r: bytes | None):
         """P + h * r: the commitment-sized term the reference adds on the host (pedersen.rs:281, 300-302)."""

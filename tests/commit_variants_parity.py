@@ -32,4 +32,8 @@ def run(nb, oracle, cid):
         sc = [rng.field(p) for _ in idx]
         assert eng.commit_sparse(ck, idx, pack(sc), rb) == ref(sc, idx, blind)
     assert eng.commit_sparse(ck, [], b"", None) is None  # empty -> identity
+    # commit_small with a blind, batch_commit_small over ragged vectors (traits.rs:105-116)
+    assert eng.commit_small(ck, v, 8, pack([r])) == ref(v, range(n), r)
+    vs = [v[:k] for k in (0, 1, 17, n)]
+    assert eng.batch_commit_small(ck, vs) == [ref(x, range(len(x)), 0) if x else None for x in vs]
     ck.release()
