@@ -627,11 +627,56 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
   int rc = ensure_workspace(ck, n + 1, 1);
   if (rc) return rc;
   cudaStream_t s = g_dev.stream;
-  if (n) CU(cudaMemcpyAsync(ck.ws.scalars, scalars, n * 32, cudaMemcpyHostToDevice, s));
-  if (blind)
-    CU(cudaMemcpyAsync((char*)ck.ws.scalars + n * 32, blind, 32, cudaMemcpyHostToDevice, s));
-  rc = enqueue_msm(ck, base_offset, ck.ws.scalars, n + (blind ? 1 : 0), ck.ws.d_out, s, 0,
-                   blind != nullptr);
+  // Tuning hook (off by default, not yet measured): NOVA_B200_H2D_CHUNKS=k splits the upload into k pieces
+  // and runs the digit / histogram stage of piece i on a side stream while piece i+1 is still on the bus --
+  // the same chunked path b200_witness_append uses.  At most the digit stage (~0.12 ms of a 2^20 MSM) can hide.
+  static const int h2d_chunks = [] {
+    const char* e = getenv("NOVA_B200_H2D_CHUNKS");
+    int k = e ? atoi(e) : 1;
+    return k < 1 ? 1 : (k > 64 ? 64 : k);
+  }();
+  if (h2d_chunks > 1 && n >= ((size_t)1 << 16)) {
+    ck_ctx::lane& ln = ck.lanes[0];
+    if (!ln.s) {
+      CU(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    }
+    const size_t total = n + (blind ? 1 : 0);
+    const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
+    msm_plan p = make_plan(ck, ck.ws, base_offset, total);
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, s));  // order the side stream after earlier users of this workspace
+    CU(cudaStreamWaitEvent(ln.s, ev, 0));
+    CU(cudaMemsetAsync(p.counts, 0, (size_t)ck.G * ck.B * 4, ln.s));
+    const size_t per = (n + h2d_chunks - 1) / h2d_chunks;
+    auto piece = [&](const void* src, size_t lo, size_t hi) -> int {
+      CU(cudaMemcpyAsync((char*)ck.ws.scalars + 32 * lo, src, 32 * (hi - lo), cudaMemcpyHostToDevice, s));
+      CU(cudaEventRecord(ev, s));
+      CU(cudaStreamWaitEvent(ln.s, ev, 0));
+      sops->digits_range(ln.s, ck.ws.scalars, lo, hi, p);
+      count_launch(1);
+      return B200_OK;
+    };
+    for (size_t lo = 0; lo < n && rc == B200_OK; lo += per)
+      rc = piece((const char*)scalars + 32 * lo, lo, lo + per < n ? lo + per : n);
+    if (blind && rc == B200_OK) rc = piece(blind, n, n + 1);
+    if (rc) {
+      cudaEventDestroy(ev);
+      return rc;
+    }
+    CU(cudaEventRecord(ev, ln.s));
+    CU(cudaStreamWaitEvent(s, ev, 0));
+    cudaEventDestroy(ev);
+    rc = enqueue_msm(ck, ck.ws, base_offset, ck.ws.scalars, total, ck.ws.d_out, s, 0, blind != nullptr,
+                     /*digits_done=*/true);
+  } else {
+    if (n) CU(cudaMemcpyAsync(ck.ws.scalars, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    if (blind)
+      CU(cudaMemcpyAsync((char*)ck.ws.scalars + n * 32, blind, 32, cudaMemcpyHostToDevice, s));
+    rc = enqueue_msm(ck, base_offset, ck.ws.scalars, n + (blind ? 1 : 0), ck.ws.d_out, s, 0,
+                     blind != nullptr);
+  }
   if (rc) return rc;
   CU(cudaMemcpyAsync(ck.ws.h_out, ck.ws.d_out, 96, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));

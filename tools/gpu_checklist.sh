@@ -30,4 +30,10 @@ run snark_host       timeout 600  python tools/snark_replay.py --log2cons 20 --r
 run ppsnark_replay   timeout 600  python tools/ppsnark_replay.py --log2cons 18 --reps 2
 run ppsnark_dev      timeout 600  python tools/ppsnark_replay.py --log2cons 18 --reps 2 --device-transcript
 
+# 4. end-to-end commit: chunked upload overlapping the digit stage (tuning hook, off by default)
+run e2e_base         timeout 300  python tools/e2e_commit.py --log-n 20
+run e2e_chunks4      timeout 300  env NOVA_B200_H2D_CHUNKS=4 python tools/e2e_commit.py --log-n 20
+run e2e_chunks8      timeout 300  env NOVA_B200_H2D_CHUNKS=8 python tools/e2e_commit.py --log-n 20
+run e2e_chunks4_par  timeout 900  env NOVA_B200_H2D_CHUNKS=4 python -m pytest tests/test_msm_gpu.py -m gpu -x -q -p no:cacheprovider
+
 grep -h "passed\|failed\|error" "$OUT"/zz_new_paths.log "$OUT"/gpu_suite.log "$OUT"/y3_parity.log 2>/dev/null | tail -6 | tee -a "$OUT/summary.txt"
