@@ -118,3 +118,99 @@ def sharded_prove_cubic_with_three_inputs(engine, p: int, claim: int, taus: list
         eval_eq_left = eval_eq_left * (1 - tau - r + 2 * r * tau) % p  # EqSumCheckInstance::bound
     finals = [int.from_bytes(engine.download_canonical(h), "little") for h in (A, B, C)]
     return polys, rs, finals
+
+
+# ---------------------------------------------------------------------------------------------
+# the other pieces of SURVEY.md §8e: SpMV, the folding step, Horner evaluation, division by (X - u)
+# ---------------------------------------------------------------------------------------------
+def all_gather_var(b: bytes, group=None) -> list:
+    """Every rank's byte string, of possibly different lengths (index-range slices differ by one element)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [b]
+    lens = [int.from_bytes(x, "little") for x in all_gather_bytes(len(b).to_bytes(8, "little"), group)]
+    m = max(lens)
+    padded = all_gather_bytes(b + bytes(m - len(b)), group) if m else [b""] * world
+    return [x[:n] for x, n in zip(padded, lens)]
+
+
+class DeviceEngine:
+    """The per-rank engine of the functions below on a GPU: thin adapters over the host-pointer mirror calls
+    (every rank drives its own device).  The CPU tests pass an oracle-backed object with the same methods."""
+
+    def __init__(self, fid: int, curve=None):
+        from . import provider, spartan
+        self.fid, self.curve, self._sp, self._pv = fid, curve, spartan, provider
+
+    def matrix(self, data: bytes, indices, indptr, cols: int):
+        return self._sp.SparseMatrix(self.fid, data, indices, indptr, cols)
+
+    def spmv(self, mat, z: bytes) -> bytes:
+        return mat.multiply_vec(z)
+
+    def vec_add(self, a: bytes, b: bytes) -> bytes:
+        return self._pv.vec_add(self.fid, a, b)
+
+    def cross_term(self, az, bz, cz, e1, u: bytes, e2=None) -> bytes:
+        return self._pv.cross_term(self.fid, az, bz, cz, e1, u, e2)
+
+    def poly_eval(self, f: bytes, u: bytes) -> bytes:
+        return self._sp.poly_eval(self.fid, f, u)
+
+    def poly_div(self, f: bytes, u: bytes) -> bytes:
+        return self._sp.poly_div(self.fid, f, u)
+
+
+def sharded_multiply_vec(engine, mats_rows, z_local: bytes, group=None):
+    """R1CSShape::multiply_vec (src/r1cs/mod.rs:407-431) with the ROWS of A, B, C split by index range and z
+    split the same way: z is all-gathered once (n x 32 B), every rank multiplies its own rows.
+    mats_rows: this rank's (A, B, C) row slices as engine matrices.  -> (z, (Az, Bz, Cz) local rows)."""
+    z = b"".join(all_gather_var(z_local, group))
+    return z, tuple(engine.spmv(M, z) for M in mats_rows)
+
+
+def sharded_cross_term(engine, mats_rows, z1_local: bytes, z2_local: bytes, e1_rows: bytes, u_sum: bytes,
+                       e2_rows: bytes | None = None, group=None) -> bytes:
+    """The T of commit_T / commit_T_relaxed (src/r1cs/mod.rs:578-664) on row slices: Z1 + Z2 locally, one
+    all-gather of Z, local SpMV rows, local T rows.  T is born on the rank that owns the same index range of
+    the commitment key, so its MSM needs only the 96-byte partial exchange (all_gather_partials)."""
+    _, (az, bz, cz) = sharded_multiply_vec(engine, mats_rows, engine.vec_add(z1_local, z2_local), group)
+    return engine.cross_term(az, bz, cz, e1_rows, u_sum, e2_rows)
+
+
+def _mont(p: int, x: int) -> bytes:
+    return ((x % p) * (1 << 256) % p).to_bytes(32, "little")
+
+
+def _unmont(p: int, b: bytes) -> int:
+    return int.from_bytes(b, "little") * pow(1 << 256, -1, p) % p
+
+
+def sharded_poly_eval(engine, p: int, f_local: bytes, lo: int, u: int, group=None) -> int:
+    """f(u) for coefficients split by index range (the 3-point evaluations of hyperkzg.rs:1048-1056):
+    every rank evaluates its slice as a polynomial in X, scales by u^lo, and the `world` values are
+    all-gathered and added."""
+    v = _unmont(p, engine.poly_eval(f_local, _mont(p, u))) if f_local else 0
+    part = v * pow(u, lo, p) % p
+    return sum(int.from_bytes(x, "little") for x in all_gather_bytes(part.to_bytes(32, "little"), group)) % p
+
+
+def sharded_poly_div(engine, p: int, f_local: bytes, lo: int, hi: int, n: int, u: int, group=None) -> bytes:
+    """The quotient of f by (X - u) (hyperkzg.rs:961-999 `div_by_monomial`: h_{n-2} = f_{n-1},
+    h_{i-1} = f_i + u h_i) with f split by index range: rank g returns h[lo .. hi) (the last rank one entry
+    less, n - 1 in total).  With H_i = sum_{j >= i} f_j u^(j-i): every rank all-gathers its slice value
+    V_g = H restricted to its slice, the carry into rank g is C_g = sum_{k > g} V_k u^(lo_k - hi_g), and
+    dividing the slice extended by the coefficient C_g yields exactly h[lo .. hi)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    um = _mont(p, u)
+    v = _unmont(p, engine.poly_eval(f_local, um)) if f_local else 0
+    meta = all_gather_bytes(v.to_bytes(32, "little") + lo.to_bytes(8, "little") + hi.to_bytes(8, "little"), group)
+    rank = dist.get_rank(group) if world > 1 else 0
+    carry = 0
+    for k in range(rank + 1, world):
+        vk, lok = int.from_bytes(meta[k][:32], "little"), int.from_bytes(meta[k][32:40], "little")
+        carry = (carry + vk * pow(u, lok - hi, p)) % p
+    if not f_local:
+        return b""
+    q = engine.poly_div(f_local + _mont(p, carry), um)  # (hi - lo) entries: h[lo .. hi)
+    return q[:32 * (hi - lo - 1)] if hi == n else q

@@ -287,6 +287,27 @@ class EmulatedDevice:
         _wr(out, b"".join(ctypes.string_at(base + 32 * int(ix[i]), 32) for i in range(n)))
         return 0
 
+    # ---- host-pointer forms (same answers; "host" and "device" memory are the same thing here) ----
+    def b200_vec_add(self, fid, a, b, n, out):
+        return self.b200_vec_add_dev(fid, a, b, n, out, None)
+
+    def b200_cross_term(self, fid, az, bz, cz, e1, e2, u, n, t):
+        return self.b200_cross_term_dev(fid, az, bz, cz, e1, e2, u, n, t, None)
+
+    def b200_poly_eval(self, fid, f, n, us, nu, evals):
+        return self.b200_poly_eval_dev(fid, f, n, us, nu, evals, None)
+
+    def b200_poly_div(self, fid, f, n, u, out):
+        return self.b200_poly_div_dev(fid, f, n, u, out, None)
+
+    def b200_spmv_multi(self, handles, k, z1, z2, z_len, o1, o2):
+        for j in range(k):
+            if self.mats[handles[j]][5] != z_len:
+                self.err = b"InvalidWitnessLength"
+                return 1
+            self.b200_spmv_dev(handles[j], z1, z2, o1[j], o2[j] if _addr(z2) else None, None)
+        return 0
+
     # ---- commitment keys ----------------------------------------------------------------------
     def b200_msm_small(self, handle, off, scalars, elem_bytes, n, max_bits, out):
         curve_id, bases, _ = self.keys[handle]

@@ -289,3 +289,11 @@ def test_prove_batched_cubic_on_device(sp, fid, k, l, zero):
     tests/test_spartan_mirror_cpu.py."""
     import batched_cubic_parity
     batched_cubic_parity.run(sp, fid, k, l, zero)
+
+
+def test_sharded_pieces_two_ranks_on_device(tmp_path):
+    """SURVEY §8e pieces beyond the MSM and the sum-check -- SpMV / cross term on row slices, Horner evaluation
+    and division by (X - u) on index-range slices -- two gloo ranks, both driving cuda:0 through
+    nova_b200.sharding.DeviceEngine.  CPU twins: tests/test_sharding_pieces.py."""
+    import test_sharding_pieces as t
+    t.run_world(2, "gpu", tmp_path)
