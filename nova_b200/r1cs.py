@@ -204,3 +204,28 @@ def nifs_prove(ck: CommitmentKey, S: R1CSShape, U1: RelaxedR1CSInstance, W1: Rel
     U = fold_instance(S.curve, U1, U2, comm_T, r)
     W = fold_witness(S.fid, W1, W2, T, r_T, r, S.num_vars, S.num_cons)
     return comm_T, (U, W)
+
+
+class ResidentView:
+    """Non-owning handle on a device vector that something else keeps alive (e.g. the witness a
+    WitnessStream hands back); quacks like DeviceVec for the calls above (`.ptr`)."""
+
+    def __init__(self, ptr, owner):
+        self.ptr, self.owner = ptr, owner
+
+
+def fold_streamed_step(ck: CommitmentKey, S: R1CSShape, U1: RelaxedR1CSInstance, W1: RelaxedR1CSWitness, stream,
+                       chunks, X2: list, r_W: int, r_T: int, challenge):
+    """One folding step the way prove_step produces it (nova/mod.rs:456-564): the fresh witness arrives in
+    chunks while the circuit is synthesised (`stream`: provider.WitnessStream over S.num_vars; `chunks`: an
+    iterable of Montgomery byte strings, consumed as they are produced), its commitment comes out of
+    `stream.finish`, and the resident copy goes straight into NIFS::prove without touching the host again.
+    -> (U2, comm_T, (U, W)); call stream.reset() before the next step."""
+    fid = S.fid
+    for c in chunks:
+        stream.append(c)
+    comm_W2 = stream.finish(fields.to_mont_bytes(fid, r_W) if r_W else None)
+    U2 = R1CSInstance(comm_W2, list(X2))
+    W2 = R1CSWitness(ResidentView(stream.d_witness, stream), r_W)
+    comm_T, (U, W) = nifs_prove(ck, S, U1, W1, U2, W2, r_T, challenge)
+    return U2, comm_T, (U, W)

@@ -41,6 +41,7 @@ class EmulatedDevice:
         self.allocs = {}    # address -> buffer (keeps it alive), gives sizes of whole allocations
         self.mats = {}      # handle -> (fid, data, indices, indptr, rows, cols)
         self.keys = {}      # handle -> (curve, bases, h or None)
+        self.streams = {}   # handle -> streamed witness
         self.graveyard = []
         self.hc = None
         self.hc_simt = None
@@ -353,6 +354,44 @@ class EmulatedDevice:
         if _addr(blind):
             sc, bs = sc + _rd(blind, 32), bs + h
         _wr(out, self._jacobian(curve_id, co.msm(curve_id, sc, bs)))
+        return 0
+
+    # ---- streamed witness hand-off --------------------------------------------------------------
+    def b200_witness_begin(self, ck, n, out_handle):
+        buf = ctypes.create_string_buffer(max(32 * n, 1))
+        self.streams[self.next_handle] = dict(ck=ck, n=n, buf=buf, filled=0, done=False)
+        out_handle._obj.value = self.next_handle
+        self.next_handle += 1
+        return 0
+
+    def b200_witness_append(self, h, scalars, count):
+        w = self.streams[h]
+        if w["done"] or w["filled"] + count > w["n"]:
+            self.err = b"append overflows the witness"
+            return 5
+        ctypes.memmove(ctypes.addressof(w["buf"]) + 32 * w["filled"], _rd(scalars, 32 * count), 32 * count)
+        w["filled"] += count
+        return 0
+
+    def b200_witness_finish(self, h, r, out, d_witness):
+        w = self.streams[h]
+        if w["done"]:
+            self.err = b"witness stream already finished"
+            return 1
+        w["done"] = True
+        rc = self.b200_commit_dev(w["ck"], w["buf"], w["n"], r, out, None)
+        if d_witness is not None:
+            d_witness._obj.value = ctypes.addressof(w["buf"])
+        return rc
+
+    def b200_witness_reset(self, h):
+        w = self.streams[h]
+        ctypes.memset(w["buf"], 0, len(w["buf"]))
+        w["filled"], w["done"] = 0, False
+        return 0
+
+    def b200_witness_release(self, h):
+        self.streams.pop(h, None)
         return 0
 
     # ---- group --------------------------------------------------------------------------------

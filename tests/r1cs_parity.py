@@ -69,3 +69,37 @@ def run_tiny_fixture(nb, oracle, cid):
     assert (vec(W_c.W, NUM_VARS), vec(W_c.E, NUM_CONS), U_c.u, U_c.X) == (both[0], both[1], both[2], both[3])
     assert S.is_sat_relaxed(ck, U_c, W_c)
     ck.release()
+
+
+def run_streamed_steps(nb, oracle, cid):
+    """Three prove_step-like folds where the fresh witness reaches the device through ONE WitnessStream (chunks of
+    1 and 2 scalars, re-armed with reset() every step) and is folded from its resident copy."""
+    from nova_b200 import r1cs, spartan as sp
+    c = CURVES[cid]
+    fid, p = c.scalar_field, c.q
+    o = Oracle(oracle, fid)
+    rng = SplitMix64(170 + cid)
+    ncols = NUM_VARS + 1 + NUM_IO
+    mats = [sp.SparseMatrix(fid, pack(p, d), idx, ptr, ncols) for (d, idx, ptr) in (csr(M, NUM_CONS) for M in tiny_r1cs())]
+    S = r1cs.R1CSShape(nb.Curve(cid), *mats, NUM_CONS, NUM_VARS, NUM_IO)
+    n_key = max(NUM_CONS, NUM_VARS)
+    bases = oracle.gen_bases(cid, n_key + 1)
+    ck = nb.CommitmentKey(nb.Curve(cid), bases[:64 * n_key], bases[64 * n_key:])
+    U = r1cs.RelaxedR1CSInstance.default(NUM_IO)
+    W = r1cs.RelaxedR1CSWitness.default(NUM_VARS, NUM_CONS)
+    run = ([0] * NUM_VARS, [0] * NUM_CONS, 0, [0] * NUM_IO)
+    ws = nb.WitnessStream(ck, NUM_VARS)
+    for step, x in enumerate((rng.field(p), 3, 11)):
+        Wv, Xv = witness(p, x)
+        r_W, r_T, r = (0 if step == 1 else rng.field(p)), rng.field(p), rng.field(p)
+        chunks = [pack(p, Wv[:1]), pack(p, Wv[1:])]
+        U2, comm_T, (U, W) = r1cs.fold_streamed_step(ck, S, U, W, ws, chunks, Xv, r_W, r_T, lambda cT: r)
+        exp_comm = c.affine_from_bytes(oracle.msm(cid, pack(p, Wv + [r_W]), bases[:64 * NUM_VARS] + bases[64 * n_key:]))
+        assert U2.comm_W == exp_comm
+        run = o.fold(*run, Wv, Xv, r)
+        assert (o.ints(W.W.to_bytes(32 * NUM_VARS)), o.ints(W.E.to_bytes(32 * NUM_CONS)), U.u, U.X) == \
+               (run[0], run[1], run[2], run[3])
+        assert S.is_sat_relaxed(ck, U, W)
+        ws.reset()
+    ws.release()
+    ck.release()

@@ -21,3 +21,9 @@ def emulated():
 def test_fold_twice_then_relaxed_sat_host_logic(emulated, oracle, cid):
     from r1cs_parity import run_tiny_fixture
     run_tiny_fixture(emulated, oracle, cid)
+
+
+@pytest.mark.parametrize("cid", [0, 2])
+def test_streamed_witness_folding_steps_host_logic(emulated, oracle, cid):
+    from r1cs_parity import run_streamed_steps
+    run_streamed_steps(emulated, oracle, cid)

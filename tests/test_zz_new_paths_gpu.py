@@ -297,3 +297,11 @@ def test_sharded_pieces_two_ranks_on_device(tmp_path):
     nova_b200.sharding.DeviceEngine.  CPU twins: tests/test_sharding_pieces.py."""
     import test_sharding_pieces as t
     t.run_world(2, "gpu", tmp_path)
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_streamed_witness_folding_steps_on_device(b200, oracle, cid):
+    """prove_step-shaped folds: WitnessStream (re-armed every step) -> resident W2 -> NIFS::prove, everything
+    resident; CPU twin in tests/test_r1cs_mirror_cpu.py."""
+    from r1cs_parity import run_streamed_steps
+    run_streamed_steps(b200, oracle, cid)
