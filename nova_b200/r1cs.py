@@ -158,6 +158,39 @@ class R1CSShape:
                 and U.comm_E == self._commit(ck, W.E, self.num_cons, W.r_E))
 
 
+def sample_random_instance_witness(ck: CommitmentKey, S: R1CSShape, Z: bytes, r_W: int, r_E: int):
+    """R1CSShape::sample_random_instance_witness (r1cs/mod.rs:786-831) with the randomness supplied by the host
+    (Z = (W, u, X): num_vars + 1 + num_io random scalars, Montgomery bytes): E = AZ o BZ - u CZ on the device,
+    the two blinded commitments, -> (RelaxedR1CSInstance, RelaxedR1CSWitness)."""
+    fid = S.fid
+    zl = S.num_vars + 1 + S.num_io
+    assert len(Z) == 32 * zl
+    z = DeviceVec.from_bytes(Z)
+    tail = fields.unpack(fid, Z[32 * S.num_vars:])
+    u, X = tail[0], tail[1:]
+    Az, Bz, Cz = S.multiply_vec_dev(z)
+    E = DeviceVec(32 * S.num_cons)
+    zero, u_dev = dev_zeros(S.num_cons), dev_scalar(fid, u)
+    check(lib().b200_cross_term_dev(fid, Az.ptr, Bz.ptr, Cz.ptr, zero.ptr, None, u_dev.ptr, S.num_cons, E.ptr, None))
+    W = dev_copy(z, S.num_vars)
+    inst = RelaxedR1CSInstance(S._commit(ck, W, S.num_vars, r_W), S._commit(ck, E, S.num_cons, r_E), X, u)
+    return inst, RelaxedR1CSWitness(W, E, r_W, r_E)  # the commits above synchronised: temporaries may go
+
+
+def derandomize(ck: CommitmentKey, curve, U: RelaxedR1CSInstance, W: RelaxedR1CSWitness):
+    """RelaxedR1CSWitness::derandomize + RelaxedR1CSInstance::derandomize (r1cs/mod.rs:1131-1142, 1294-1310;
+    CE::derandomize, pedersen.rs:307-315): blinds set to zero, `h * r` subtracted from both commitments.
+    -> (U', W', r_W, r_E).  Needs the host copy of h (a key built from bytes)."""
+    curve = Curve(curve)
+    p = fields.MODULUS[curve.scalar_field]
+    assert ck.h is not None, "key has no blinding generator on the host"
+    bf = curve.base_field
+    h = (fields.from_mont_bytes(bf, ck.h[:32]), fields.from_mont_bytes(bf, ck.h[32:64]))
+    comm_W = _lincomb(curve, [(1, U.comm_W), ((-W.r_W) % p, h)]) if W.r_W else U.comm_W
+    comm_E = _lincomb(curve, [(1, U.comm_E), ((-W.r_E) % p, h)]) if W.r_E else U.comm_E
+    return (RelaxedR1CSInstance(comm_W, comm_E, list(U.X), U.u), RelaxedR1CSWitness(W.W, W.E, 0, 0), W.r_W, W.r_E)
+
+
 def fold_witness(fid: int, W1: RelaxedR1CSWitness, W2, T: DeviceVec, r_T: int, r: int, num_vars: int,
                  num_cons: int) -> RelaxedR1CSWitness:
     """RelaxedR1CSWitness::fold (W2: R1CSWitness) / fold_relaxed (W2: RelaxedR1CSWitness), r1cs/mod.rs:1044-1107."""

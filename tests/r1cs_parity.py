@@ -103,3 +103,47 @@ def run_streamed_steps(nb, oracle, cid):
         ws.reset()
     ws.release()
     ck.release()
+
+
+def run_compressed_half(nb, oracle, cid, num_cons=16, num_vars=8, num_io=2, device_transcript=False):
+    """The per-curve half of CompressedSNARK::prove (nova/mod.rs:813-881) at toy size: a satisfied running pair
+    is folded with a freshly sampled random pair (sample_random_instance_witness + NIFSRelaxed::prove),
+    derandomized, and handed to spartan::snark::prove; the restated verifier must accept the proof for the
+    derandomized instance."""
+    from nova_b200 import r1cs, snark as ds, spartan as sp
+    from oracle import snark_ref as sr
+    from oracle.ppsnark_ref import random_instance
+    from oracle.pyref import Keccak256Transcript
+    from snark_parity import csr as csr_rows
+    c = CURVES[cid]
+    fid, p = c.scalar_field, c.q
+    rng = SplitMix64(900 + cid + num_cons)
+    Sd, Wd, u, X = random_instance(p, rng, num_cons, num_vars, num_io)
+    ncols = num_vars + 1 + num_io
+    mats = []
+    for name in "ABC":
+        d, idx, ptr = csr_rows(Sd[name], num_cons)
+        mats.append(sp.SparseMatrix(fid, pack(p, d), idx, ptr, ncols))
+    S = r1cs.R1CSShape(nb.Curve(cid), *mats, num_cons, num_vars, num_io)
+    n_key = max(num_cons, num_vars)
+    bases = oracle.gen_bases(cid, n_key + 1)
+    ck = nb.CommitmentKey(nb.Curve(cid), bases[:64 * n_key], bases[64 * n_key:])
+    r_W, r_E = rng.field(p), rng.field(p)
+    W_run = r1cs.RelaxedR1CSWitness(sp.DeviceVec.from_bytes(pack(p, Wd["W"])), sp.DeviceVec.from_bytes(pack(p, Wd["E"])), r_W, r_E)
+    U_run = r1cs.RelaxedR1CSInstance(S._commit(ck, W_run.W, num_vars, r_W), S._commit(ck, W_run.E, num_cons, r_E), X, u)
+    assert S.is_sat_relaxed(ck, U_run, W_run)
+    Z = pack(p, [rng.field(p) for _ in range(ncols)])
+    U_rand, W_rand = r1cs.sample_random_instance_witness(ck, S, Z, rng.field(p), rng.field(p))
+    assert S.is_sat_relaxed(ck, U_rand, W_rand)
+    r = rng.field(p)
+    _, (U_n, W_n) = r1cs.nifs_prove(ck, S, U_run, W_run, U_rand, W_rand, rng.field(p), lambda cT: r)
+    assert S.is_sat_relaxed(ck, U_n, W_n)
+    U_d, W_d, _, _ = r1cs.derandomize(ck, nb.Curve(cid), U_n, W_n)
+    assert S.is_sat_relaxed(ck, U_d, W_d)  # commitments now open with zero blinds
+    tr = Keccak256Transcript(p, b"RelaxedR1CSSNARK")
+    Ssn = dict(num_cons=num_cons, num_vars=num_vars, A=mats[0], B=mats[1], C=mats[2])
+    Uc = dict(comm_W=U_d.comm_W, comm_E=U_d.comm_E, u=U_d.u, X=U_d.X)
+    proof = ds.prove_core(nb.Curve(cid), None, Ssn, Uc, dict(W=W_d.W, E=W_d.E), 99, tr, device_transcript=device_transcript)
+    joint = sr.verify_core(p, c, Sd, Uc, 99, proof)  # raises if either sum-check or the batch claim is wrong
+    assert joint == (proof["batched_c"], proof["batched_x"], proof["batched_e"])
+    ck.release()

@@ -27,3 +27,9 @@ def test_fold_twice_then_relaxed_sat_host_logic(emulated, oracle, cid):
 def test_streamed_witness_folding_steps_host_logic(emulated, oracle, cid):
     from r1cs_parity import run_streamed_steps
     run_streamed_steps(emulated, oracle, cid)
+
+
+@pytest.mark.parametrize("cid,device_transcript", [(0, False), (0, True), (1, False)])
+def test_compressed_snark_half_host_logic(emulated, oracle, cid, device_transcript):
+    from r1cs_parity import run_compressed_half
+    run_compressed_half(emulated, oracle, cid, device_transcript=device_transcript)

@@ -305,3 +305,11 @@ def test_streamed_witness_folding_steps_on_device(b200, oracle, cid):
     resident; CPU twin in tests/test_r1cs_mirror_cpu.py."""
     from r1cs_parity import run_streamed_steps
     run_streamed_steps(b200, oracle, cid)
+
+
+@pytest.mark.parametrize("cid,num_cons,num_vars,device_transcript", [(0, 16, 8, False), (0, 64, 64, True), (1, 32, 16, True)])
+def test_compressed_snark_half_on_device(b200, oracle, cid, num_cons, num_vars, device_transcript):
+    """One curve's half of CompressedSNARK::prove (nova/mod.rs:813-881): random pair sampled and folded in,
+    derandomized, spartan::snark proof accepted by the restated verifier.  CPU twin: tests/test_r1cs_mirror_cpu.py."""
+    from r1cs_parity import run_compressed_half
+    run_compressed_half(b200, oracle, cid, num_cons, num_vars, 2, device_transcript)
