@@ -162,3 +162,14 @@ def _prove_quad_prod_resident(fid, claim, num_rounds, A: DeviceVec, B: DeviceVec
         _bind_dev(fid, B, length, r)
         length //= 2
     return polys, rs, fields.unpack(fid, A.to_bytes(32)) + fields.unpack(fid, B.to_bytes(32))
+
+
+def prove(curve, ck: CommitmentKey, S: dict, U: dict, W: dict, vk_digest: int, transcript, device_transcript: bool = True,
+          timings: dict | None = None):
+    """The whole RelaxedR1CSSNARK::prove (snark.rs:113-256): prove_core, then EE::prove (HyperKZG,
+    hyperkzg.rs:926-1116) on the batched claim with the same transcript; `ck` must be the key the commitments in
+    U were made with.  -> the proof fields of prove_core plus `eval_arg` = (com, w, v)."""
+    from .spartan import hyperkzg_prove
+    proof = prove_core(curve, ck, S, U, W, vk_digest, transcript, device_transcript, timings)
+    proof["eval_arg"] = hyperkzg_prove(curve, ck, proof["batched_poly"], proof["batched_x"], transcript, timings)
+    return proof

@@ -566,12 +566,15 @@ class SumcheckProof:
 # ---------------------------------------------------------------------------------------------
 # HyperKZG prover core (hyperkzg.rs:1076-1116 with the transcript challenges r, q given)
 # ---------------------------------------------------------------------------------------------
-def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r: int, q: int,
-                            timings: dict | None = None):
+def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r, q,
+                            timings: dict | None = None, on_w=None):
     """The same on a polynomial that is already in HBM: folds, commitments, the 3-point
     evaluations, the batch polynomial and the three quotients never leave the device; the host
     receives ell-1 + 3 points and 3*ell scalars.  Returns (com, v, w, polys) with `polys` the
-    resident fold chain.  `timings` (optional) receives seconds per phase."""
+    resident fold chain.  `timings` (optional) receives seconds per phase.
+    `r` / `q` are the two challenges, or callables `r(com)` / `q(v)` that derive them from the messages
+    produced so far (the transcript steps of hyperkzg.rs:1099-1107, 1060); `on_w(w)` sees the quotient
+    commitments (verifier_second_challenge, :1068-1070)."""
     import time
     fid = Curve(curve).scalar_field
     p = fields.MODULUS[fid]
@@ -596,6 +599,8 @@ def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r
     mark("fold")
     com = commit_many_dev(curve, ck, polys[1:], lens[1:])  # :1099-1100 batch_commit(polys[1..])
     mark("commit_folds")
+    if callable(r):
+        r = r(com)
     u = [r % p, (-r) % p, r * r % p]  # :1105-1106
     us = DeviceVec.from_bytes(fields.pack(fid, u))
     ev = DeviceVec(96 * ell)
@@ -604,6 +609,8 @@ def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r
     evb = ev.to_bytes(96 * ell)
     v = [fields.unpack(fid, evb[96 * i:96 * i + 96]) for i in range(ell)]
     mark("evals")
+    if callable(q):
+        q = q(v)
     assert ell <= 32, "rlc of more than 32 polynomials"
     qd = DeviceVec.from_bytes(fields.pack(fid, [pow(q, k, p) for k in range(ell)]))  # batch_challenge_powers
     ptrs = (ctypes.c_void_p * ell)(*[v_.ptr.value for v_ in polys])
@@ -620,7 +627,35 @@ def hyperkzg_prove_resident(curve, ck: CommitmentKey, P: "DeviceVec", x: list, r
     mark("quotients")
     w = commit_many_dev(curve, ck, [h for h, _ in hs], [n - 1] * 3)
     mark("commit_quotients")
+    if on_w is not None:
+        on_w(w)
     return com, v, w, polys
+
+
+def _commitment_bytes(P) -> bytes:
+    """Commitment::to_transcript_bytes (hyperkzg.rs:233-248): x || y || is_infinity."""
+    if P is None:
+        return bytes(64) + b"\x01"
+    return int(P[0]).to_bytes(32, "little") + int(P[1]).to_bytes(32, "little") + b"\x00"
+
+
+def hyperkzg_prove(curve, ck: CommitmentKey, P: "DeviceVec", x: list, transcript, timings: dict | None = None):
+    """EvaluationEngine::prove (hyperkzg.rs:926-1116) with the transcript: r = H(com), q = H(v), and the second
+    verifier challenge squeezed after W so that the transcript ends in the verifier's state.
+    -> EvaluationArgument (com, w, v)."""
+    def r_of(com):  # compute_challenge, :861-865
+        transcript.absorb_bytes(b"c", b"".join(_commitment_bytes(C) for C in com))
+        return transcript.squeeze(b"c")
+
+    def q_of(v):    # get_batch_challenge, :869-880
+        transcript.absorb_bytes(b"v", b"".join(int(e).to_bytes(32, "little") for row in v for e in row))
+        return transcript.squeeze(b"r")
+
+    def after_w(w):  # verifier_second_challenge, :891-898
+        transcript.absorb_bytes(b"W", b"".join(_commitment_bytes(C) for C in w))
+        transcript.squeeze(b"d")
+    com, v, w, _ = hyperkzg_prove_resident(curve, ck, P, x, r_of, q_of, timings, after_w)
+    return com, w, v
 
 
 def hyperkzg_prove_core(curve, ck: CommitmentKey, hat_P: bytes, x: list, r: int, q: int):

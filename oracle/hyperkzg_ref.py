@@ -84,3 +84,50 @@ def verify_core(cid: int, tau: int, C, x: list, y: int, com, v, w, r: int, q: in
     L = c.msm_naive(scalars, points)
     R = c.add(c.add(w[0], c.mul(d0, w[1])), c.mul(d1, w[2]))
     return L == c.mul(tau, R)
+
+
+# ---- the same with the transcript (hyperkzg.rs:861-898, 1099-1107, 1060-1070; verify :1119-1242) ---------
+def _absorb_points(tr, label, pts):
+    from .pyref import commitment_transcript_bytes
+    tr.absorb_bytes(label, b"".join(commitment_transcript_bytes(P) for P in pts))
+
+
+def prove(cid: int, ck: bytes, hat_P: bytes, x: list, tr):
+    """EvaluationEngine::prove: r = H(com), q = H(v); squeezes the verifier's second challenge after W so that
+    prover and verifier leave the transcript in the same state.  -> (com, w, v)."""
+    from .pyref import to_repr
+    c = CURVES[cid]
+    fid, p = c.scalar_field, c.q
+    ell, n = len(x), len(hat_P) // 32
+    assert n == 1 << ell
+    polys = [hat_P]
+    for i in range(ell - 1):
+        polys.append(co.kzg_fold(fid, polys[i], mont_bytes(p, x[ell - i - 1])))
+    aff = c.affine_from_bytes
+    com = [aff(co.msm(cid, f, ck[:2 * len(f)])) for f in polys[1:]]
+    _absorb_points(tr, b"c", com)
+    r = tr.squeeze(b"c")
+    u = [r % p, (-r) % p, r * r % p]
+    v = [_ints(p, co.poly_eval(fid, f, _pack(p, u))) for f in polys]
+    tr.absorb_bytes(b"v", b"".join(to_repr(e) for row in v for e in row))
+    q = tr.squeeze(b"r")
+    B = co.rlc(fid, polys, _pack(p, [pow(q, k, p) for k in range(ell)]), n)
+    w = [aff(co.msm(cid, h, ck[:2 * len(h)])) for h in (co.poly_div(fid, B, mont_bytes(p, ut)) for ut in u)]
+    _absorb_points(tr, b"W", w)
+    tr.squeeze(b"d")
+    return com, w, v
+
+
+def verify(cid: int, tau: int, C, x: list, y: int, proof, tr) -> bool:
+    """EvaluationEngine::verify with the challenges re-derived from the transcript."""
+    from .pyref import to_repr
+    com, w, v = proof
+    _absorb_points(tr, b"c", com)
+    r = tr.squeeze(b"c")
+    tr.absorb_bytes(b"v", b"".join(to_repr(e) for row in v for e in row))
+    q = tr.squeeze(b"r")
+    _absorb_points(tr, b"W", w)
+    d0 = tr.squeeze(b"d")
+    if r == 0 or C is None:  # hyperkzg.rs:1138-1141
+        return False
+    return verify_core(cid, tau, C, x, y, com, v, w, r, q, d0)

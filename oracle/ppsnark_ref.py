@@ -372,6 +372,7 @@ def sparse_poly_evaluate(p, num_vars, Z, r):
     while nz < len(Z):
         nz *= 2
     nvz = nz.bit_length() - 1
+    assert num_vars - 1 - nvz >= 0, "public IO too long for the shape (usize underflow panic in the reference)"
     chis = eq_evals(p, r[num_vars - 1 - nvz:])
     partial = sum(z * c for z, c in zip(Z, chis)) % p
     common = 1

@@ -119,6 +119,10 @@ def prove_core(p, curve, S, U, W, vk_digest):
 
 def verify_core(p, curve, S, U, vk_digest, proof):
     """snark.rs:259-396 without EE::verify.  Returns the joint (C, x, e) or raises AssertionError."""
+    return _verify_core_with_transcript(p, curve, S, U, vk_digest, proof, {})
+
+
+def _verify_core_with_transcript(p, curve, S, U, vk_digest, proof, holder):
     num_cons, num_vars = S["num_cons"], S["num_vars"]
     nrx, nry = _log2(num_cons), _log2(num_vars) + 1
     tr = _start_transcript(p, U, vk_digest)
@@ -155,4 +159,29 @@ def verify_core(p, curve, S, U, vk_digest, proof):
     assert claim_batch_final == exp % p, "batch evaluation final claim (spartan/mod.rs:455-470)"
     tr.absorb_bytes(b"l", scalars_bytes(proof["evals_batch"]))
     c = tr.squeeze(b"c")
+    holder["tr"] = tr
     return batch_diff_size_instance(p, curve, [cm for (cm, _, _) in u_vec], proof["evals_batch"], num_rounds, r_b, c)
+
+
+# ---- the whole SNARK: prove_core + EE::prove (HyperKZG), verify_core + EE::verify ---------------------------
+def prove(p, curve, cid, ck_bytes, S, U, W, vk_digest):
+    """RelaxedR1CSSNARK::prove (snark.rs:113-256) with the HyperKZG evaluation argument
+    (hyperkzg.rs:926-1116) on the batched claim; `ck_bytes` = the SRS the commitments in U were made with."""
+    from . import hyperkzg_ref as hk
+    from .pyref import mont_bytes
+    proof = prove_core(p, curve, S, U, W, vk_digest)
+    hat_P = b"".join(mont_bytes(p, v) for v in proof["batched_poly"])
+    proof["eval_arg"] = hk.prove(cid, ck_bytes, hat_P, proof["batched_x"], proof["transcript"])
+    return proof
+
+
+def verify(p, curve, cid, tau, S, U, vk_digest, proof) -> bool:
+    """RelaxedR1CSSNARK::verify (snark.rs:259-396) incl. EE::verify, the pairing check replaced by the
+    equivalent group equation for a test SRS with known tau (oracle/hyperkzg_ref.py)."""
+    from . import hyperkzg_ref as hk
+    from .ppsnark_ref import commitments_bytes  # noqa: F401  (same encodings as verify_core)
+    tr_holder = {}
+
+    # verify_core re-derives the transcript; run it again here to continue into EE::verify
+    C, x, e = _verify_core_with_transcript(p, curve, S, U, vk_digest, proof, tr_holder)
+    return hk.verify(cid, tau, C, x, e, proof["eval_arg"], tr_holder["tr"])

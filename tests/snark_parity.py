@@ -58,3 +58,40 @@ def run_case(nb, oracle, cid, num_cons, num_vars, num_io, device_transcript):
     assert mle_evaluate(p, poly, got["batched_x"]) == got["batched_e"]
     assert sr.verify_core(p, c, S, U, 4242, got) == (got["batched_c"], got["batched_x"], got["batched_e"])
     assert tr.squeeze(b"x") == ref["transcript"].squeeze(b"x")  # EE::prove would start from the same state
+
+
+def run_full(nb, oracle, num_cons, num_vars, num_io, device_transcript):
+    """The whole RelaxedR1CSSNARK::prove on BN254 with the HyperKZG evaluation argument over a test SRS
+    [tau^i] G: the mirror's proof (incl. eval_arg) equals the oracle's and the restated verifier -- sum-check
+    claims, batch claim and the KZG opening equation -- accepts it."""
+    from nova_b200 import snark as ds
+    from nova_b200 import spartan as sp
+    from oracle import hyperkzg_ref as hk
+    cid = 0
+    c = CURVES[cid]
+    fid, p = c.scalar_field, c.q
+    rng = SplitMix64(2100 + num_cons + num_vars)
+    S, W, u, X = random_instance(p, rng, num_cons, num_vars, num_io)
+    tau = rng.field(p)
+    n_key = max(num_cons, num_vars)
+    srs = hk.setup_srs(cid, n_key, tau)
+
+    def commit_ref(v):
+        return c.affine_from_bytes(oracle.msm(cid, pack(p, v), srs[:64 * len(v)]))
+    U = dict(comm_W=commit_ref(W["W"]), comm_E=commit_ref(W["E"]), u=u, X=X)
+    ref = sr.prove(p, c, cid, srs, S, U, W, 555)
+    ncols = num_vars + 1 + num_io
+    mats = {}
+    for name in "ABC":
+        d, idx, ptr = csr(S[name], num_cons)
+        mats[name] = sp.SparseMatrix(fid, pack(p, d), idx, ptr, ncols)
+    ck = nb.CommitmentKey(nb.Curve(cid), srs)
+    tr = Keccak256Transcript(p, b"RelaxedR1CSSNARK")
+    got = ds.prove(nb.Curve(cid), ck, dict(num_cons=num_cons, num_vars=num_vars, **mats), U,
+                   dict(W=pack(p, W["W"]), E=pack(p, W["E"])), 555, tr, device_transcript=device_transcript)
+    com, w, v = got["eval_arg"]
+    rcom, rw, rv = ref["eval_arg"]
+    assert list(com) == list(rcom) and list(w) == list(rw) and [list(t) for t in v] == [list(t) for t in rv]
+    assert sr.verify(p, c, cid, tau, S, U, 555, got)
+    assert tr.squeeze(b"x") == ref["transcript"].squeeze(b"x")
+    ck.release()

@@ -4,7 +4,7 @@ SRS whose tau is known), and the reference's hand cases must hold (hyperkzg.rs:1
 import pytest
 
 from oracle import hyperkzg_ref as hk
-from oracle.pyref import CURVES, SplitMix64, mle_evaluate, mont_bytes
+from oracle.pyref import CURVES, Keccak256Transcript, SplitMix64, mle_evaluate, mont_bytes
 
 
 def pack(p, xs):
@@ -61,3 +61,49 @@ def test_reference_hand_cases(oracle):
     com, v, w = hk.prove_core(cid, ck, pack(p, poly), x, 77, 99)
     assert hk.verify_core(cid, tau, C, x, 28, com, v, w, 77, 99, 5)
     assert not hk.verify_core(cid, tau, C, x, 29, com, v, w, 77, 99, 5)
+
+
+def test_reference_hand_cases_with_the_transcript(oracle):
+    """test_hyperkzg_eval / test_hyperkzg_small (hyperkzg.rs:1265-1327) as the reference runs them: prover and
+    verifier each start a Keccak transcript b"TestEval" and derive r, q, d_0 from it."""
+    cid = 0
+    c = CURVES[cid]
+    p = c.q
+    tau = 0xABCDEF12345
+    ck = hk.setup_srs(cid, 4, tau)
+
+    def run(poly, pt, val):
+        C = c.affine_from_bytes(oracle.msm(cid, pack(p, poly), ck))
+        tp, tv = Keccak256Transcript(p, b"TestEval"), Keccak256Transcript(p, b"TestEval")
+        proof = hk.prove(cid, ck, pack(p, poly), pt, tp)
+        ok = hk.verify(cid, tau, C, pt, val, proof, tv)
+        assert tp.squeeze(b"s") == tv.squeeze(b"s")  # both sides end in the same transcript state
+        return ok
+    for pt, val, ok in (([0, 0], 1, True), ([0, 1], 2, True), ([1, 1], 4, True), ([0, 2], 3, True), ([2, 2], 9, True),
+                        ([2, 2], 50, False), ([0, 2], 4, False)):
+        assert run([1, 2, 2, 4], pt, val) == ok, (pt, val)
+    assert run([1, 2, 1, 4], [4, 3], 28) and not run([1, 2, 1, 4], [4, 3], 29)
+
+
+@pytest.mark.parametrize("ell", [4, 5, 6])
+def test_random_polys_with_the_transcript(oracle, ell):
+    """test_hyperkzg_large (hyperkzg.rs:1380-1416): random polynomial and point, prove -> verify, then a
+    tampered proof (one evaluation changed) must fail."""
+    cid = 0
+    c = CURVES[cid]
+    p = c.q
+    rng = SplitMix64(ell)
+    n = 1 << ell
+    tau = rng.field(p)
+    ck = hk.setup_srs(cid, n, tau)
+    poly = [rng.field(p) for _ in range(n)]
+    x = [rng.field(p) for _ in range(ell)]
+    y = mle_evaluate(p, poly, x)
+    C = c.affine_from_bytes(oracle.msm(cid, pack(p, poly), ck))
+    proof = hk.prove(cid, ck, pack(p, poly), x, Keccak256Transcript(p, b"TestEval"))
+    assert hk.verify(cid, tau, C, x, y, proof, Keccak256Transcript(p, b"TestEval"))
+    com, w, v = proof
+    v_bad = [list(t) for t in v]
+    v_bad[1][1] = (v_bad[1][1] + 1) % p
+    assert not hk.verify(cid, tau, C, x, y, (com, w, v_bad), Keccak256Transcript(p, b"TestEval"))
+    assert not hk.verify(cid, tau, C, x, y, proof, Keccak256Transcript(p, b"OtherLabel"))

@@ -26,3 +26,9 @@ def test_snark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars, 
     csrc/capi_sumcheck.inc does, so the mirror's marshalling of the transcript is covered too."""
     from snark_parity import run_case
     run_case(emulated, oracle, cid, num_cons, num_vars, num_io, device_transcript=device_transcript)
+
+
+@pytest.mark.parametrize("device_transcript", [False, True])
+def test_full_snark_with_hyperkzg_host_logic(emulated, oracle, device_transcript):
+    from snark_parity import run_full
+    run_full(emulated, oracle, 8, 8, 2, device_transcript)

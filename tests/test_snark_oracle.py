@@ -66,3 +66,31 @@ def test_tampered_messages_are_rejected(field, match):
         verify_core(p, c, S, U, 5, bad)
     with pytest.raises(AssertionError):
         verify_core(p, c, S, U, 6, proof)  # another vk digest: every challenge changes
+
+
+@pytest.mark.parametrize("num_cons,num_vars", [(8, 8), (4, 16)])
+def test_full_snark_with_hyperkzg_evaluation_argument(oracle, num_cons, num_vars):
+    """prove = prove_core + EE::prove, verify = verify_core + EE::verify over a test SRS [tau^i]G: the honest
+    proof verifies, a proof for another instance or with an altered evaluation argument does not."""
+    from oracle import hyperkzg_ref as hk
+    from oracle.pyref import mont_bytes
+    from oracle.snark_ref import prove, verify
+    cid = 0
+    c = CURVES[cid]
+    p = c.q
+    rng = SplitMix64(77 + num_cons)
+    S, W, u, X = random_instance(p, rng, num_cons, num_vars, 2)
+    tau = rng.field(p)
+    n_key = max(num_cons, num_vars)
+    ck = hk.setup_srs(cid, n_key, tau)
+    pack = lambda v: b"".join(mont_bytes(p, x) for x in v)
+    commit = lambda v: c.affine_from_bytes(oracle.msm(cid, pack(v), ck[:64 * len(v)]))
+    U = dict(comm_W=commit(W["W"]), comm_E=commit(W["E"]), u=u, X=X)
+    proof = prove(p, c, cid, ck, S, U, W, 31337)
+    assert verify(p, c, cid, tau, S, U, 31337, proof)
+    com, w, v = proof["eval_arg"]
+    bad = dict(proof, eval_arg=(com, [w[1], w[0], w[2]], v))
+    assert not verify(p, c, cid, tau, S, U, 31337, bad)
+    v2 = [list(t) for t in v]
+    v2[0][0] = (v2[0][0] + 1) % p
+    assert not verify(p, c, cid, tau, S, U, 31337, dict(proof, eval_arg=(com, w, v2)))

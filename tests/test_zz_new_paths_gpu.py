@@ -313,3 +313,12 @@ def test_compressed_snark_half_on_device(b200, oracle, cid, num_cons, num_vars, 
     derandomized, spartan::snark proof accepted by the restated verifier.  CPU twin: tests/test_r1cs_mirror_cpu.py."""
     from r1cs_parity import run_compressed_half
     run_compressed_half(b200, oracle, cid, num_cons, num_vars, 2, device_transcript)
+
+
+@pytest.mark.parametrize("num_cons,num_vars,device_transcript", [(8, 8, False), (64, 32, True), (4, 16, True)])
+def test_full_snark_with_hyperkzg_on_device(b200, oracle, num_cons, num_vars, device_transcript):
+    """RelaxedR1CSSNARK::prove incl. EE::prove (HyperKZG with the transcript) on the device: proof equal to the
+    oracle's and accepted by the restated verifier incl. the KZG opening equation.  CPU twin:
+    tests/test_snark_mirror_cpu.py."""
+    from snark_parity import run_full
+    run_full(b200, oracle, num_cons, num_vars, 2, device_transcript)
