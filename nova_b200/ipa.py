@@ -33,15 +33,22 @@ class InnerProductArgument:
         curve = Curve(curve)
         fid = curve.scalar_field
         q = fields.MODULUS[fid]
-        n = len(b_vec) // 32
-        if len(a_vec) != len(b_vec):
+        size = lambda v: v.nbytes if isinstance(v, DeviceVec) else len(v)
+        n = size(b_vec) // 32
+        if size(a_vec) != size(b_vec):
             raise ValueError("InvalidInputLength")  # ipa_pc.rs:187-189
         assert n and n & (n - 1) == 0 and n <= len(ck) and ck.has_h
         L = lib()
         transcript.absorb_bytes(b"NoDS", b"IPA")
         transcript.absorb_bytes(b"U", commitment_transcript_bytes(comm_a) + int(c_claim % q).to_bytes(32, "little"))
         r0 = transcript.squeeze(b"r")
-        a, b = DeviceVec.from_bytes(a_vec), DeviceVec.from_bytes(b_vec)
+        def working(v):  # the folds overwrite both vectors: resident inputs are copied device-to-device
+            if not isinstance(v, DeviceVec):
+                return DeviceVec.from_bytes(v)
+            c = DeviceVec(32 * n)
+            check(L.b200_memcpy_d2d(c.ptr, v.ptr, 32 * n, None))
+            return c
+        a, b = working(a_vec), working(b_vec)
         w, sL, sR = DeviceVec(32 * n), DeviceVec(32 * n), DeviceVec(32 * n)
         a2, b2 = DeviceVec(16 * n), DeviceVec(16 * n)
         out = DeviceVec(96 * 2)

@@ -165,11 +165,25 @@ def _prove_quad_prod_resident(fid, claim, num_rounds, A: DeviceVec, B: DeviceVec
 
 
 def prove(curve, ck: CommitmentKey, S: dict, U: dict, W: dict, vk_digest: int, transcript, device_transcript: bool = True,
-          timings: dict | None = None):
-    """The whole RelaxedR1CSSNARK::prove (snark.rs:113-256): prove_core, then EE::prove (HyperKZG,
-    hyperkzg.rs:926-1116) on the batched claim with the same transcript; `ck` must be the key the commitments in
-    U were made with.  -> the proof fields of prove_core plus `eval_arg` = (com, w, v)."""
-    from .spartan import hyperkzg_prove
+          timings: dict | None = None, ee: str = "hyperkzg"):
+    """The whole RelaxedR1CSSNARK::prove (snark.rs:113-256): prove_core, then EE::prove on the batched claim with
+    the same transcript; `ck` must be the key the commitments in U were made with.
+      ee = "hyperkzg": hyperkzg.rs:926-1116 (primary curve, S1)       -> eval_arg = (com, w, v)
+      ee = "ipa":      ipa_pc.rs:64-77, 174-285 (secondary curve, S2) -> eval_arg = (L_vec, R_vec, a_hat);
+                       `ck` must carry the generator ck_c as its blinding base."""
     proof = prove_core(curve, ck, S, U, W, vk_digest, transcript, device_transcript, timings)
-    proof["eval_arg"] = hyperkzg_prove(curve, ck, proof["batched_poly"], proof["batched_x"], transcript, timings)
+    if ee == "hyperkzg":
+        from .spartan import hyperkzg_prove
+        proof["eval_arg"] = hyperkzg_prove(curve, ck, proof["batched_poly"], proof["batched_x"], transcript, timings)
+    elif ee == "ipa":
+        from .ipa import InnerProductArgument
+        fid = Curve(curve).scalar_field
+        x = proof["batched_x"]
+        b_vec = DeviceVec(32 << len(x))  # EqPolynomial::new(point).evals(), ipa_pc.rs:73
+        x_dev = DeviceVec.from_bytes(fields.pack(fid, x))
+        check(lib().b200_eq_table_dev(fid, x_dev.ptr, len(x), b_vec.ptr, None))
+        proof["eval_arg"] = InnerProductArgument.prove(curve, ck, proof["batched_c"], b_vec, proof["batched_e"],
+                                                       proof["batched_poly"], transcript)
+    else:
+        raise ValueError(f"unknown evaluation engine {ee!r}")
     return proof

@@ -185,3 +185,24 @@ def verify(p, curve, cid, tau, S, U, vk_digest, proof) -> bool:
     # verify_core re-derives the transcript; run it again here to continue into EE::verify
     C, x, e = _verify_core_with_transcript(p, curve, S, U, vk_digest, proof, tr_holder)
     return hk.verify(cid, tau, C, x, e, proof["eval_arg"], tr_holder["tr"])
+
+
+def prove_ipa(p, curve, ck_pts, ck_c, S, U, W, vk_digest):
+    """The secondary-curve half of CompressedSNARK (S2 = snark + IPA, nova/mod.rs:872-880): prove_core, then
+    EvaluationEngine::prove of provider/ipa_pc.rs:64-77 -- an inner-product argument between the batched
+    polynomial and the eq table of the batched point."""
+    from .pyref import ipa_prove
+    proof = prove_core(p, curve, S, U, W, vk_digest)
+    b_vec = eq_evals(p, proof["batched_x"])
+    proof["eval_arg"] = ipa_prove(curve, ck_pts, ck_c, proof["batched_c"], b_vec, proof["batched_e"],
+                                  proof["batched_poly"], proof["transcript"])
+    return proof
+
+
+def verify_ipa(p, curve, ck_pts, ck_c, S, U, vk_digest, proof) -> bool:
+    """RelaxedR1CSSNARK::verify with the IPA evaluation engine (ipa_pc.rs:80-100, 286-396)."""
+    from .pyref import ipa_verify
+    holder = {}
+    C, x, e = _verify_core_with_transcript(p, curve, S, U, vk_digest, proof, holder)
+    L_vec, R_vec, a_hat = proof["eval_arg"]
+    return ipa_verify(curve, ck_pts, ck_c, C, eq_evals(p, x), e, L_vec, R_vec, a_hat, holder["tr"])

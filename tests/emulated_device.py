@@ -102,6 +102,10 @@ class EmulatedDevice:
         return 0
 
     def b200_sc_eval_dev(self, fid, form, A, B, C, length, eq_left, eq_right, shift, out, stream):
+        if form == 11:  # SC_DOT: plain inner product (provider/ipa_pc.rs:102-108)
+            P = FIELD_MODULUS[fid]
+            self._put(fid, out, [sum(x * y for x, y in zip(self._ints(fid, A, length), self._ints(fid, B, length))) % P])
+            return 0
         g = lambda p: _rd(p, 32 * length) if _addr(p) else None
         tab = lambda p: _rd(p, self._size(p)) if _addr(p) else None
         _wr(out, co.sc_eval(fid, form, g(A), g(B), g(C), tab(eq_left), tab(eq_right), shift))
@@ -288,7 +292,35 @@ class EmulatedDevice:
         _wr(out, b"".join(ctypes.string_at(base + 32 * int(ix[i]), 32) for i in range(n)))
         return 0
 
+    # ---- inner-product argument kernels (include/nova_b200.h "inner-product argument") -------------
+    def b200_fold_halves_dev(self, fid, v, n, x_lo, x_hi, out, stream):
+        P = FIELD_MODULUS[fid]
+        vs, lo, hi = self._ints(fid, v, n), self._ints(fid, x_lo, 1)[0], self._ints(fid, x_hi, 1)[0]
+        self._put(fid, out, [(vs[i] * lo + vs[i + n // 2] * hi) % P for i in range(n // 2)])
+        return 0
+
+    def b200_ipa_scalars_dev(self, fid, a, w, n, nk, sL, sR, stream):
+        P = FIELD_MODULUS[fid]
+        h = nk // 2
+        av, wv = self._ints(fid, a, nk), self._ints(fid, w, n)
+        self._put(fid, sL, [av[j % h] * wv[j] % P if j & h else 0 for j in range(n)])
+        self._put(fid, sR, [0 if j & h else av[(j % h) + h] * wv[j] % P for j in range(n)])
+        return 0
+
+    def b200_ipa_weights_dev(self, fid, w, n, nk, r, r_inv, stream):
+        P = FIELD_MODULUS[fid]
+        if nk == 0:
+            self._put(fid, w, [1] * n)
+            return 0
+        rv, ri = self._ints(fid, r, 1)[0], self._ints(fid, r_inv, 1)[0]
+        wv = self._ints(fid, w, n)
+        self._put(fid, w, [wv[j] * (rv if j & (nk // 2) else ri) % P for j in range(n)])
+        return 0
+
     # ---- host-pointer forms (same answers; "host" and "device" memory are the same thing here) ----
+    def b200_sc_eval(self, fid, form, A, B, C, length, eq_left, eq_left_len, eq_right, eq_right_len, shift, out):
+        return self.b200_sc_eval_dev(fid, form, A, B, C, length, eq_left, eq_right, shift, out, None)
+
     def b200_vec_add(self, fid, a, b, n, out):
         return self.b200_vec_add_dev(fid, a, b, n, out, None)
 

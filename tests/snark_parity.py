@@ -95,3 +95,37 @@ def run_full(nb, oracle, num_cons, num_vars, num_io, device_transcript):
     assert sr.verify(p, c, cid, tau, S, U, 555, got)
     assert tr.squeeze(b"x") == ref["transcript"].squeeze(b"x")
     ck.release()
+
+
+def run_full_ipa(nb, oracle, cid, num_cons, num_vars, num_io, device_transcript):
+    """The secondary-curve SNARK (S2 = spartan::snark + IPA, nova/mod.rs:872-880) over a Pedersen key: the
+    mirror's proof equals the oracle's and the restated verifier incl. the IPA check (ipa_pc.rs:286-396) accepts."""
+    from nova_b200 import snark as ds
+    from nova_b200 import spartan as sp
+    c = CURVES[cid]
+    fid, p = c.scalar_field, c.q
+    rng = SplitMix64(2300 + cid + num_cons)
+    S, W, u, X = random_instance(p, rng, num_cons, num_vars, num_io)
+    n_key = max(num_cons, num_vars)
+    pts = c.bases_arith(n_key + 1, k0=4242)
+    ck_pts, ck_c = pts[:n_key], pts[n_key]
+
+    def commit_ref(v):
+        return c.msm_naive(v, ck_pts[:len(v)])
+    U = dict(comm_W=commit_ref(W["W"]), comm_E=commit_ref(W["E"]), u=u, X=X)
+    ref = sr.prove_ipa(p, c, ck_pts, ck_c, S, U, W, 808)
+    assert sr.verify_ipa(p, c, ck_pts, ck_c, S, U, 808, ref)
+    ncols = num_vars + 1 + num_io
+    mats = {}
+    for name in "ABC":
+        d, idx, ptr = csr(S[name], num_cons)
+        mats[name] = sp.SparseMatrix(fid, pack(p, d), idx, ptr, ncols)
+    ck = nb.CommitmentKey(nb.Curve(cid), b"".join(c.affine_bytes(P) for P in ck_pts), c.affine_bytes(ck_c))
+    tr = Keccak256Transcript(p, b"RelaxedR1CSSNARK")
+    got = ds.prove(nb.Curve(cid), ck, dict(num_cons=num_cons, num_vars=num_vars, **mats), U,
+                   dict(W=pack(p, W["W"]), E=pack(p, W["E"])), 808, tr, device_transcript=device_transcript, ee="ipa")
+    assert tuple(got["eval_arg"]) == tuple(ref["eval_arg"])
+    assert sr.verify_ipa(p, c, ck_pts, ck_c, S, U, 808, got)
+    bad = dict(got, eval_arg=(got["eval_arg"][0], got["eval_arg"][1], (got["eval_arg"][2] + 1) % p))
+    assert not sr.verify_ipa(p, c, ck_pts, ck_c, S, U, 808, bad)
+    ck.release()

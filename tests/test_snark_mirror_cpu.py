@@ -32,3 +32,9 @@ def test_snark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars, 
 def test_full_snark_with_hyperkzg_host_logic(emulated, oracle, device_transcript):
     from snark_parity import run_full
     run_full(emulated, oracle, 8, 8, 2, device_transcript)
+
+
+@pytest.mark.parametrize("cid,device_transcript", [(1, False), (1, True), (3, False)])
+def test_full_snark_with_ipa_host_logic(emulated, oracle, cid, device_transcript):
+    from snark_parity import run_full_ipa
+    run_full_ipa(emulated, oracle, cid, 8, 8, 2, device_transcript)

@@ -35,3 +35,10 @@ def test_prove_batched_cubic_host_logic(emulated, oracle, k, l, zero):
     import batched_cubic_parity
     from nova_b200 import spartan
     batched_cubic_parity.run(spartan, 0, k, l, zero)
+
+
+@pytest.mark.parametrize("cid,l", [(1, 1), (1, 5), (3, 4), (0, 3)])
+def test_ipa_prover_host_logic(emulated, oracle, cid, l):
+    """nova_b200/ipa.py (the prover that never folds the key) on the emulated device: body of tests/test_ipa_gpu.py."""
+    import test_ipa_gpu
+    test_ipa_gpu.test_ipa_prove_matches_restatement(emulated, oracle, cid, l)

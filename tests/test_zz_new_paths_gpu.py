@@ -322,3 +322,11 @@ def test_full_snark_with_hyperkzg_on_device(b200, oracle, num_cons, num_vars, de
     tests/test_snark_mirror_cpu.py."""
     from snark_parity import run_full
     run_full(b200, oracle, num_cons, num_vars, 2, device_transcript)
+
+
+@pytest.mark.parametrize("cid,num_cons,num_vars,device_transcript", [(1, 8, 8, False), (1, 32, 16, True), (3, 16, 16, True)])
+def test_full_snark_with_ipa_on_device(b200, oracle, cid, num_cons, num_vars, device_transcript):
+    """S2 of CompressedSNARK: spartan::snark + the IPA evaluation engine on the secondary curve (Grumpkin / Vesta),
+    proof equal to the oracle's and accepted by the restated verifier.  CPU twin: tests/test_snark_mirror_cpu.py."""
+    from snark_parity import run_full_ipa
+    run_full_ipa(b200, oracle, cid, num_cons, num_vars, 2, device_transcript)
