@@ -1,16 +1,21 @@
-"""GPU parity of the entry points added late in round 1.
+"""GPU parity of the entry points and host flows added late in round 1.
 
-Their device code is also validated on the CPU through the host build of the same headers
-(tests/test_host_transcript.py, tests/test_host_field.py).  First run on a B200: 60 passed in 10 s
-(profiles/r01s_new_paths_pytest.log); the tests below the "added after that run" marker have not run
-on a GPU yet, which is why this file sorts LAST: with `pytest -x` a failure here cannot hide the rest.
+This file sorts LAST on purpose: with `pytest -x` a failure here cannot hide the rest of the suite.
 
-* sum-check round loops with the Keccak transcript on the device (b200_sumcheck_quad_prod,
-  b200_sumcheck_cubic3, b200_sc_round_dev): every prover message, challenge, final evaluation and the
-  transcript state afterwards must equal the oracle's (sumcheck.rs:199-242, 446-507).
-* streamed witness hand-off (b200_witness_begin / append / finish): the commitment of a witness
-  pushed in ragged chunks equals commit(ck, W, r_W) of the whole vector and the oracle's MSM.
-* key validation (b200_ck_validate): the on-curve loop of CommitmentKey::new (hyperkzg.rs:113-119).
+Ran on a B200 (60 passed in 10 s, profiles/r01s_new_paths_pytest.log) -- everything ABOVE the marker
+"added after that run":
+* sum-check round loops with the Keccak transcript on the device (b200_sumcheck_quad_prod, b200_sumcheck_cubic3)
+* streamed witness hand-off (b200_witness_begin / append / finish)
+* key validation (b200_ck_validate)
+
+Written after the GPU budget ran out -- everything BELOW the marker.  Each of these has a CPU twin that runs the
+same test body against the emulated device (tests/emulated_device.py, tests/cpp/emulated_b200.cpp), with the new
+device code exercised through its host build (tests/hostcheck, incl. the real kernel wrappers on 32 threads):
+* b200_witness_reset; the spartan::snark prover core and the whole SNARK with HyperKZG / IPA evaluation arguments;
+  the device-resident folding step (commit_T, NIFS, folds, is_sat_relaxed, streamed witness, one half of
+  CompressedSNARK::prove); the C++ mirror's resident layer; ppsnark with the batched device round
+  (b200_sc_round_batched_dev); prove_batched_cubic; the remaining CommitmentEngine methods; the multi-GPU pieces
+  beyond MSM and sum-check (two gloo ranks on one GPU).
 """
 import pytest
 
