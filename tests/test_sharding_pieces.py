@@ -16,8 +16,13 @@ def run_world(world, kind, tmp_path):
     out = str(tmp_path / f"pieces_{world}")
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "shard_pieces_worker.py"), str(r), str(world), str(port),
                                kind, out]) for r in range(world)]
-    for pr in procs:
-        assert pr.wait(timeout=300) == 0
+    try:
+        for pr in procs:
+            assert pr.wait(timeout=300) == 0
+    finally:
+        for pr in procs:  # a failed or stuck rank must not leave its peers waiting in a collective
+            if pr.poll() is None:
+                pr.kill()
     for r in range(world):
         assert open(f"{out}.{r}").read() == "OK"
 
