@@ -36,3 +36,20 @@ def test_snark_replay_runs(emulated, oracle, device_transcript):
     from tools import snark_replay
     out = snark_replay.run(log2cons=4, reps=1, device_transcript=device_transcript)
     assert out["ms"]["total"] > 0 and out["ms"]["hyperkzg_prove"] > 0
+
+
+@pytest.mark.parametrize("num_vars", [3, 5])
+def test_sumcheckeq_replay_matches_oracle(emulated, oracle, num_vars):
+    """The reference's `sumcheckeq` bench workload (benches/sumcheckeq.rs:24-115) through the mirror equals the
+    oracle's MemorySumcheckInstance round by round (taus[0] = 0 exercises the fall-back)."""
+    import sumcheckeq_replay
+    from oracle import ppsnark_ref as pr
+    from oracle.pyref import FIELD_MODULUS
+    p = FIELD_MODULUS[0]
+    n = 1 << num_vars
+    _, got = sumcheckeq_replay.run_sc(num_vars, collect=True)
+    vs = [[i * k % p for i in range(n)] for k in range(1, 9)]
+    inst = pr.MemorySumcheckInstance(p, vs[0:4], vs[4:8], [(-2 * i) % p for i in range(num_vars)], vs[0], vs[1])
+    for j in range(num_vars):
+        assert [list(e) for e in got[j]] == [list(e) for e in inst.evaluation_points()], j
+        inst.bound((-j) % p)

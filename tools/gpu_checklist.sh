@@ -28,6 +28,7 @@ run sumcheck_replay  timeout 300  python tools/sumcheck_replay.py --log-n 20 --r
 run snark_dev        timeout 600  python tools/snark_replay.py --log2cons 20 --reps 2
 run snark_host       timeout 600  python tools/snark_replay.py --log2cons 20 --reps 2 --host-transcript
 run ppsnark_replay   timeout 600  python tools/ppsnark_replay.py --log2cons 18 --reps 2
+run sumcheckeq       timeout 600  python tools/sumcheckeq_replay.py --min 10 --max 22 --reps 2
 run ppsnark_dev      timeout 600  python tools/ppsnark_replay.py --log2cons 18 --reps 2 --device-transcript
 
 # 4. end-to-end commit: chunked upload overlapping the digit stage (tuning hook, off by default)
