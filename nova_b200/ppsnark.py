@@ -712,7 +712,19 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
     out.update(comm_L_row=comm_L_row, comm_L_col=comm_L_col, comm_mem=comm_mem, sc_outer=sc_outer,
                r_outer=r_outer, eval_Az_at_r_outer=eAz, eval_Bz_at_r_outer=eBz, eval_Cz_at_r_outer=eCz,
                eval_E_at_r_outer=eE_outer, sc_inner_batched=sc_inner, r_inner_batched=r_inner,
-               batched_poly=batched, batched_eval=sum(a * b for a, b in zip(pw, eval_vec)) % p)
+               batched_poly=batched, batched_eval=sum(a * b for a, b in zip(pw, eval_vec)) % p, batch_challenge=cb)
+    return out
+
+
+def prove(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: dict, vk_digest: int, transcript,
+          timings: dict | None = None, device_transcript: bool = False):
+    """The whole RelaxedR1CSSNARK::prove of ppsnark.rs:1056-1385: prove_core, then EE::prove (HyperKZG with the
+    transcript) on the batched polynomial at r_inner_batched.  (The batched commitment sum_i c^i C_i of
+    PolyEvalInstance::batch is only an input of EE::prove for the transcript-free HyperKZG prover, which does
+    not use it: the caller / verifier forms it from the 15 commitments.)  -> proof fields + `eval_arg`."""
+    from .spartan import hyperkzg_prove
+    out = prove_core(curve, ck, S, spark, U, W, vk_digest, transcript, timings, device_transcript)
+    out["eval_arg"] = hyperkzg_prove(curve, ck, out["batched_poly"], out["r_inner_batched"], transcript, timings)
     return out
 
 

@@ -321,7 +321,7 @@ def prove_core(p, commit, S, spark, U, W, vk_digest):
     out.update(comm_L_row=comm_L_row, comm_L_col=comm_L_col, comm_mem=comm_mem, sc_outer=sc_outer,
                r_outer=r_outer, eval_Az_at_r_outer=eAz, eval_Bz_at_r_outer=eBz, eval_Cz_at_r_outer=eCz,
                eval_E_at_r_outer=eE_outer, sc_inner_batched=sc_inner, r_inner_batched=r_inner,
-               batched_poly=batched, batched_eval=batched_eval, transcript=tr)
+               batched_poly=batched, batched_eval=batched_eval, batch_challenge=cb, transcript=tr)
     return out
 
 
@@ -381,9 +381,12 @@ def sparse_poly_evaluate(p, num_vars, Z, r):
     return common * partial % p
 
 
-def verify_core(p, num_cons, num_vars, N, U, vk_digest, proof):
-    """Re-derives every challenge and checks both sum-check final claims.  Returns True / raises."""
+def verify_core(p, num_cons, num_vars, N, U, vk_digest, proof, holder=None):
+    """Re-derives every challenge and checks both sum-check final claims.  Returns True / raises.
+    `holder` (optional dict) receives the transcript so that the opening check can continue it."""
     tr = Keccak256Transcript(p, b"RelaxedR1CSSNARK")
+    if holder is not None:
+        holder["tr"] = tr
     tr.absorb_scalar(b"vk", vk_digest)
     tr.absorb_bytes(b"U", commitments_bytes([U["comm_W"], U["comm_E"]]) + to_repr(U["u"] % p) + scalars_bytes(U["X"]))
     nro, nri = num_cons.bit_length() - 1, N.bit_length() - 1
@@ -466,3 +469,51 @@ def random_instance(p, rng, num_cons, num_vars, num_io, nnz_per_row=2):
     E = [(a * b - u * c) % p for a, b, c in zip(Az, Bz, Cz)]
     S = dict(num_cons=num_cons, num_vars=num_vars, A=A, B=B, C=C)
     return S, dict(W=Wv, E=E), u, X
+
+
+# ---- the whole prover / verifier incl. the evaluation argument (ppsnark.rs:1305-1340, 1603-1655) -----------
+EVAL_ORDER = ["eval_W", "eval_E", "eval_L_row", "eval_L_col", "eval_val_A", "eval_val_B", "eval_val_C",
+              "eval_t_plus_r_inv_row", "eval_row", "eval_w_plus_r_inv_row", "eval_ts_row",
+              "eval_t_plus_r_inv_col", "eval_col", "eval_w_plus_r_inv_col", "eval_ts_col"]
+
+
+def shape_commitments(commit, spark):
+    """R1CSShapeSparkCommitment (ppsnark.rs:200-215): commitments to the seven preprocessed vectors."""
+    return {k: commit(getattr(spark, k)) for k in ("val_A", "val_B", "val_C", "row", "col", "ts_row", "ts_col")}
+
+
+def comm_vec_of(U, S_comm, proof):
+    cm = proof["comm_mem"]
+    return [U["comm_W"], U["comm_E"], proof["comm_L_row"], proof["comm_L_col"], S_comm["val_A"], S_comm["val_B"],
+            S_comm["val_C"], cm[0], S_comm["row"], cm[1], S_comm["ts_row"], cm[2], S_comm["col"], cm[3], S_comm["ts_col"]]
+
+
+def batch_commitment(p, curve, comm_vec, c):
+    """PolyEvalInstance::batch, the commitment part (spartan/mod.rs:346-368): sum_i c^i C_i."""
+    C = None
+    for i, cm in enumerate(comm_vec):
+        C = curve.add(C, curve.mul(pow(c, i, p), cm))
+    return C
+
+
+def prove(p, curve, cid, srs, commit, S, spark, U, W, vk_digest):
+    """RelaxedR1CSSNARK::prove of ppsnark.rs incl. EE::prove (HyperKZG, transcript-driven)."""
+    from . import hyperkzg_ref as hk
+    from .pyref import mont_bytes
+    out = prove_core(p, commit, S, spark, U, W, vk_digest)
+    hat_P = b"".join(mont_bytes(p, v) for v in out["batched_poly"])
+    out["eval_arg"] = hk.prove(cid, srs, hat_P, out["r_inner_batched"], out["transcript"])
+    return out
+
+
+def verify(p, curve, cid, tau, num_cons, num_vars, N, U, S_comm, vk_digest, proof) -> bool:
+    from . import hyperkzg_ref as hk
+    holder = {}
+    verify_core(p, num_cons, num_vars, N, U, vk_digest, proof, holder)
+    tr = holder["tr"]
+    eval_vec = [proof[k] for k in EVAL_ORDER]
+    tr.absorb_bytes(b"e", scalars_bytes(eval_vec))
+    c = tr.squeeze(b"c")
+    C = batch_commitment(p, curve, comm_vec_of(U, S_comm, proof), c)
+    e = sum(pow(c, i, p) * v for i, v in enumerate(eval_vec)) % p
+    return hk.verify(cid, tau, C, proof["r_inner_batched"], e, proof["eval_arg"], tr)

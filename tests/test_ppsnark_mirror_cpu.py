@@ -94,3 +94,9 @@ def test_batched_round_kernel_wrapper_on_32_threads(emulated_simt, oracle, zero_
 def test_ppsnark_prove_core_kernel_wrapper_on_32_threads(emulated_simt, oracle):
     import test_ppsnark_gpu
     test_ppsnark_gpu.test_prove_core_matches_oracle(emulated_simt, oracle, 0, 8, 8, True)
+
+
+@pytest.mark.parametrize("num_cons,num_vars,device_transcript", [(8, 8, False), (8, 8, True)])
+def test_whole_ppsnark_with_hyperkzg_host_logic(emulated, oracle, num_cons, num_vars, device_transcript):
+    import ppsnark_full_parity
+    ppsnark_full_parity.run(emulated, oracle, num_cons, num_vars, device_transcript)

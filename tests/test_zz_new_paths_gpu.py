@@ -335,3 +335,11 @@ def test_full_snark_with_ipa_on_device(b200, oracle, cid, num_cons, num_vars, de
     proof equal to the oracle's and accepted by the restated verifier.  CPU twin: tests/test_snark_mirror_cpu.py."""
     from snark_parity import run_full_ipa
     run_full_ipa(b200, oracle, cid, num_cons, num_vars, 2, device_transcript)
+
+
+@pytest.mark.parametrize("num_cons,num_vars,device_transcript", [(8, 8, False), (16, 8, True), (64, 64, True)])
+def test_whole_ppsnark_with_hyperkzg_on_device(b200, oracle, num_cons, num_vars, device_transcript):
+    """ppsnark::RelaxedR1CSSNARK::prove incl. EE::prove (HyperKZG) over a test SRS; proof equal to the oracle's
+    and accepted by the restated verifier incl. the batched opening.  CPU twin: tests/test_ppsnark_mirror_cpu.py."""
+    import ppsnark_full_parity
+    ppsnark_full_parity.run(b200, oracle, num_cons, num_vars, device_transcript)
