@@ -15,8 +15,7 @@ commitment-sized group operations per fold.
 """
 from __future__ import annotations
 
-import ctypes
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 from . import fields
 from .native import check, lib
@@ -86,7 +85,6 @@ class R1CSShape:
     num_cons: int
     num_vars: int
     num_io: int
-    _scratch: dict = field(default_factory=dict)
 
     @property
     def fid(self) -> int:

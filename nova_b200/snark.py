@@ -26,7 +26,7 @@ import ctypes
 
 from . import fields
 from .native import check, lib
-from .ppsnark import (View, _as_dev, _mle_eval, _prove_cubic3_resident, _rlc_dev, commitment_transcript_bytes, dev_copy,
+from .ppsnark import (View, _as_dev, _mle_eval, _prove_cubic3_resident, _rlc_dev, commitment_transcript_bytes,
                       dev_scalar, dev_zeros, to_repr)
 from .provider import CommitmentKey, Curve, DlogGroup, _cbuf
 from .spartan import DeviceVec, SumcheckProof

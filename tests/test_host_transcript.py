@@ -11,7 +11,7 @@ import subprocess
 import pytest
 
 from oracle import pyref
-from oracle.pyref import FIELD_MODULUS, Keccak256Transcript, SplitMix64, from_mont, keccak256, mont_bytes, to_repr
+from oracle.pyref import FIELD_MODULUS, Keccak256Transcript, SplitMix64, from_mont, keccak256, mont_bytes
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 QUAD, CUBIC3_EQ, CUBIC3_EQ_M1 = 0, 1, 2
