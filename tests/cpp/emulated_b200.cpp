@@ -30,6 +30,10 @@ int orc_on_curve(int curve, const void* pt, const void* b_mont);
 int orc_sc_eval(int fid, int form, const void* a, const void* b, const void* c, size_t len, const void* eql, const void* eqr,
                 int shift, void* out);
 int orc_spmv(int fid, const void* data, const uint64_t* indices, const uint64_t* indptr, size_t rows, const void* z, void* out);
+int orc_eq_table(int fid, const void* r, int ell, void* out);
+// the HOST BUILD of the device round kernel (tests/hostcheck/hostcheck.cpp, from nova_b200/csrc/transcript.cuh)
+int hc_sc_round(int fid, int kind, void* state144, const void* res, const void* tau, const void* tau_inv, const void* pending,
+                uint32_t pending_len, int absorb_label, int squeeze_label, void* out_poly, void* out_r);
 }
 
 namespace {
@@ -223,6 +227,69 @@ int b200_spmv_multi(const uint64_t* hs, size_t k, const void* z1, const void* z2
     if (rc) return rc;
   }
   return B200_OK;
+}
+
+// sum-check loops with the transcript "on the device": reductions and binds from the oracle, the round step from
+// the host build of k_sc_round's body, strung together as csrc/capi_sumcheck.inc does
+static int sumcheck_loop(int f, const void* claim, int l, void* const* polys, int npoly, int ncoef, b200_transcript* tr,
+                         const void* pending, size_t plen, void* polys_out, void* r_out, void* finals_out,
+                         const unsigned char* taus) {
+  unsigned char state[144];
+  uint64_t one = 1;
+  memcpy(state, claim, 32);
+  orc_field_from_u64(f, &one, 1, state + 32);
+  memcpy(state + 64, &tr->round, 8);
+  memcpy(state + 72, tr->state, 64);
+  memset(state + 136, 0, 8);
+  const int fh = l / 2, sh = l - fh;
+  std::vector<std::vector<unsigned char>> left, right;
+  std::vector<unsigned char> tinv;
+  if (taus) {
+    for (int k = 0; k < (fh > 0 ? fh : 1); k++) { left.emplace_back((size_t)32 << k); orc_eq_table(f, taus + 32 * (fh - k), k, left[k].data()); }
+    for (int k = 0; k <= sh; k++) { right.emplace_back((size_t)32 << k); orc_eq_table(f, taus + 32 * (l - k), k, right[k].data()); }
+    tinv.resize(32 * l);
+    orc_fe_op(f, 3, taus, taus, tinv.data(), l);  // inverses (0 -> 0)
+  }
+  size_t len = (size_t)1 << l;
+  for (int j = 0; j < l; j++, len >>= 1) {
+    unsigned char res[96] = {0};
+    int kind = 0;
+    if (!taus) {
+      orc_sc_eval(f, 0, polys[0], polys[1], nullptr, len, nullptr, nullptr, 0, res);
+    } else {
+      const int rnd = j + 1;
+      const void *L = nullptr, *R;
+      int shift = 0;
+      if (rnd < fh) { L = left[fh - rnd].data(); R = right[sh].data(); shift = sh; } else R = right[l - rnd].data();
+      bool zero = true;
+      for (int b = 0; b < 32; b++) zero &= taus[32 * j + b] == 0;
+      orc_sc_eval(f, 4, polys[0], polys[1], polys[2], len, L, R, shift, res);
+      if (zero) orc_sc_eval(f, 7, polys[0], polys[1], polys[2], len, L, R, shift, res + 64);
+      kind = zero ? 2 : 1;
+    }
+    if (hc_sc_round(f, kind, state, res, taus ? taus + 32 * j : nullptr, taus ? tinv.data() + 32 * j : nullptr,
+                    j == 0 ? pending : nullptr, j == 0 ? (uint32_t)plen : 0u, 'p', 'c', (char*)polys_out + 32 * ncoef * j,
+                    (char*)r_out + 32 * j))
+      return fail(B200_E_ARG, "hc_sc_round failed");
+    for (int k = 0; k < npoly; k++) orc_bind_top(f, polys[k], len, (char*)r_out + 32 * j);
+  }
+  for (int k = 0; k < npoly; k++) memcpy((char*)finals_out + 32 * k, polys[k], 32);
+  memcpy(&tr->round, state + 64, 8);
+  memcpy(tr->state, state + 72, 64);
+  return B200_OK;
+}
+int b200_sumcheck_quad_prod(int f, const void* claim, int num_rounds, void* A, void* B, b200_transcript* tr, const void* pending,
+                            size_t plen, void* polys_out, void* r_out, void* finals_out) {
+  if (plen > B200_SC_MAX_PENDING) return fail(B200_E_ARG, "pending transcript bytes exceed the limit");
+  void* polys[2] = {A, B};
+  return sumcheck_loop(f, claim, num_rounds, polys, 2, 2, tr, pending, plen, polys_out, r_out, finals_out, nullptr);
+}
+int b200_sumcheck_cubic3(int f, const void* claim, const void* taus, int num_rounds, void* A, void* B, void* C, b200_transcript* tr,
+                         const void* pending, size_t plen, void* polys_out, void* r_out, void* finals_out) {
+  if (plen > B200_SC_MAX_PENDING) return fail(B200_E_ARG, "pending transcript bytes exceed the limit");
+  void* polys[3] = {A, B, C};
+  return sumcheck_loop(f, claim, num_rounds, polys, 3, 3, tr, pending, plen, polys_out, r_out, finals_out,
+                       (const unsigned char*)taus);
 }
 
 // streamed witness hand-off

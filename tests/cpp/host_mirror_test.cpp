@@ -71,6 +71,41 @@ static int fold_mode(const char* path) {
   return 0;
 }
 
+// --sumcheck <case.bin>: the two fused sum-check loops through the C++ wrappers (prove_quad_prod,
+// prove_cubic_with_three_inputs with a TranscriptState carrying pending absorbs); dumps every prover message and the
+// transcript afterwards for the Python test to compare with the oracle.  Case: [l], A, B, C, taus, [claim_q, claim_c],
+// transcript (72 bytes as 9 u64), pending bytes.
+static int sumcheck_mode(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  check(b200_init(0), "b200_init");
+  const int field = BN254::scalar_field;
+  auto dims = rd<uint64_t>(f);
+  auto A = rd<Scalar>(f), B = rd<Scalar>(f), C = rd<Scalar>(f), taus = rd<Scalar>(f), claims = rd<Scalar>(f);
+  auto trw = rd<uint64_t>(f);
+  auto pending = rd<unsigned char>(f);
+  const int l = (int)dims[0];
+  std::ofstream o(std::string(path) + ".out", std::ios::binary);
+  auto dump = [&](const void* p, uint64_t n, size_t sz) { o.write((char*)&n, 8); o.write((const char*)p, n * sz); };
+  for (int which = 0; which < 2; which++) {
+    TranscriptState t;
+    memcpy(&t.tr, trw.data(), sizeof(b200_transcript));
+    t.pending = pending;
+    DeviceVec dA(A), dB(B), dC(C);
+    SumcheckProofOut out = which == 0 ? prove_quad_prod(field, claims[0], l, dA.ptr(), dB.ptr(), t)
+                                      : prove_cubic_with_three_inputs(field, claims[1], taus, dA.ptr(), dB.ptr(), dC.ptr(), t);
+    std::vector<Scalar> flat;
+    for (auto& q : out.compressed_polys) flat.insert(flat.end(), q.begin(), q.end());
+    dump(flat.data(), flat.size(), 32);
+    dump(out.r.data(), out.r.size(), 32);
+    dump(out.final_evals.data(), out.final_evals.size(), 32);
+    dump(&t.tr, 1, sizeof(b200_transcript));
+    uint64_t left = t.pending.size();
+    dump(&left, 1, 8);
+  }
+  std::printf("sumcheck ok\n");
+  return 0;
+}
+
 // Jacobian -> compare with expected affine without inversion: X == x*Z^2, Y == y*Z^3 is checked on
 // the Python side; here we only dump the raw result bytes.
 int main(int argc, char** argv) {
@@ -80,6 +115,7 @@ int main(int argc, char** argv) {
     return 0;
   }
   if (std::string(argv[1]) == "--fold") return argc > 2 ? fold_mode(argv[2]) : 2;
+  if (std::string(argv[1]) == "--sumcheck") return argc > 2 ? sumcheck_mode(argv[2]) : 2;
   std::ifstream f(argv[1], std::ios::binary);
   check(b200_init(0), "b200_init");
   auto bases = rd<Affine>(f);

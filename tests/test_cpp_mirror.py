@@ -78,12 +78,19 @@ def build_emulated():
     esrc = os.path.join(cdir, "emulated_b200.cpp")
     hdrs = [os.path.join(ROOT, "include", f) for f in ("nova_b200.hpp", "nova_b200.h")]
     if not os.path.exists(EMUL_SO) or any(os.path.getmtime(p) > os.path.getmtime(EMUL_SO) for p in [esrc] + hdrs):
+        hdir = os.path.join(ROOT, "tests", "hostcheck")  # host build of the device round kernel (hc_sc_round)
+        hsrc, hso = os.path.join(hdir, "hostcheck.cpp"), os.path.join(hdir, "libhostcheck.so")
+        csrc = os.path.join(ROOT, "nova_b200", "csrc")
+        hdeps = [hsrc] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+        if not os.path.exists(hso) or any(os.path.getmtime(p) > os.path.getmtime(hso) for p in hdeps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-x", "c++", hsrc, "-o", hso])
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", esrc, "-o", EMUL_SO, "-L" + odir, "-loracle",
-                               "-Wl,-rpath," + odir])
+                               "-L" + hdir, "-lhostcheck", "-Wl,-rpath," + odir, "-Wl,-rpath," + hdir])
     src = os.path.join(cdir, "host_mirror_test.cpp")
     if not os.path.exists(EXE_EMUL) or any(os.path.getmtime(p) > os.path.getmtime(EXE_EMUL) for p in [src, EMUL_SO] + hdrs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", src, "-o", EXE_EMUL, "-L" + cdir, "-lemulated_b200",
-                               "-Wl,-rpath," + cdir, "-Wl,-rpath," + odir])
+                               "-Wl,-rpath," + cdir, "-Wl,-rpath," + odir,
+                               "-Wl,-rpath," + os.path.join(ROOT, "tests", "hostcheck")])
 
 
 def test_cpp_mirror_host_logic_concurrent_commits_cpu(oracle, tmp_path):
@@ -154,3 +161,61 @@ def check_fold(exe, oracle, tmp_path):
     assert aff(comm_T) == c.affine_from_bytes(oracle.msm(cid, T_exp + pack([r_T]), bases[:64 * num_cons] + h))
     assert Wf == oracle.axpy(fid, pack(W1), pack(W2), pack([r]))
     assert Ef == oracle.axpy(fid, pack(E1), T_exp, pack([r]))
+
+
+def test_cpp_mirror_host_logic_sumcheck_loops_cpu(oracle, tmp_path):
+    """prove_quad_prod / prove_cubic_with_three_inputs of include/nova_b200.hpp (TranscriptState with pending absorbs)
+    on the CPU: the emulated library strings the host build of the device round kernel together."""
+    build_emulated()
+    check_sumcheck(EXE_EMUL, oracle, tmp_path)
+
+
+def check_sumcheck(exe, oracle, tmp_path):
+    from oracle.pyref import (FIELD_MODULUS, Keccak256Transcript, SplitMix64, from_mont_bytes, mont_bytes,
+                              prove_cubic_with_three_inputs, prove_quad_prod)
+    fid, l = 0, 6
+    p = FIELD_MODULUS[fid]
+    pack = lambda xs: b"".join(mont_bytes(p, x) for x in xs)
+    rng = SplitMix64(606)
+    n = 1 << l
+    A, B, C = ([rng.field(p) for _ in range(n)] for _ in range(3))
+    taus = [rng.field(p) for _ in range(l)]
+    taus[2] = 0  # a tau = 0 round
+    cq, cc = rng.field(p), rng.field(p)
+
+    def fresh():
+        t = Keccak256Transcript(p, b"cpp")
+        t.absorb_scalar(b"a", 5)
+        t.squeeze(b"x")
+        t.absorb_scalar(b"b", 7)  # left pending
+        return t
+    t0 = fresh()
+    case = tmp_path / "sc.bin"
+    blob = lambda b, sz: struct.pack("<Q", len(b) // sz) + b
+    with open(case, "wb") as f:
+        f.write(struct.pack("<QQ", 1, l))
+        for v in (A, B, C, taus, [cq, cc]):
+            f.write(blob(pack(v), 32))
+        f.write(blob(struct.pack("<Q", t0.round) + t0.state, 8))
+        f.write(blob(t0.buf, 1))
+    out = subprocess.run([exe, "--sumcheck", str(case)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = open(str(case) + ".out", "rb").read()
+    off = 0
+
+    def take(sz):
+        nonlocal off
+        (k,) = struct.unpack_from("<Q", raw, off)
+        b = raw[off + 8:off + 8 + k * sz]
+        off += 8 + k * sz
+        return b
+    canon = lambda b: [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
+    mont = lambda b: [from_mont_bytes(p, b[i:i + 32]) for i in range(0, len(b), 32)]
+    for which, ncoef in ((0, 2), (1, 3)):
+        t = fresh()
+        exp = prove_quad_prod(p, cq, l, A, B, t) if which == 0 else prove_cubic_with_three_inputs(p, cc, taus, A, B, C, t)
+        polys, rs, finals, trb, left = take(32), take(32), take(32), take(72), take(8)
+        flat = canon(polys)
+        assert [flat[ncoef * j:ncoef * (j + 1)] for j in range(l)] == [list(q) for q in exp[0]]
+        assert mont(rs) == list(exp[1]) and mont(finals) == list(exp[2])
+        assert struct.unpack("<Q", trb[:8])[0] == t.round and trb[8:] == t.state and struct.unpack("<Q", left)[0] == 0

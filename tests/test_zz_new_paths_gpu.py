@@ -343,3 +343,11 @@ def test_whole_ppsnark_with_hyperkzg_on_device(b200, oracle, num_cons, num_vars,
     and accepted by the restated verifier incl. the batched opening.  CPU twin: tests/test_ppsnark_mirror_cpu.py."""
     import ppsnark_full_parity
     ppsnark_full_parity.run(b200, oracle, num_cons, num_vars, device_transcript)
+
+
+def test_cpp_mirror_sumcheck_loops(oracle, tmp_path):
+    """The C++ wrappers of the fused sum-check loops (prove_quad_prod, prove_cubic_with_three_inputs with a pending
+    transcript buffer and a tau = 0 round) on the GPU; CPU twin in tests/test_cpp_mirror.py."""
+    import test_cpp_mirror as tcm
+    tcm.build()
+    tcm.check_sumcheck(tcm.EXE, oracle, tmp_path)
