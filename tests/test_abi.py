@@ -57,3 +57,24 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read().replace("`oracle/`", "")
                 m = bad.search(txt)
                 assert m is None or f == "__init__.py", f"{f} reaches into the oracle: {m.group(0)!r}"
+
+
+def test_struct_layouts_match_the_python_binding(tmp_path):
+    """The structs that cross the ABI by pointer (b200_transcript, b200_sc_state, b200_scb_desc, b200_scb_state):
+    sizes and field offsets as a C compiler sees include/nova_b200.h == what nova_b200's ctypes code assumes."""
+    import ctypes
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nova_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200_transcript), '
+                   'offsetof(b200_transcript, state), sizeof(b200_sc_state), offsetof(b200_sc_state, round), '
+                   'offsetof(b200_sc_state, tstate), sizeof(b200_scb_desc), offsetof(b200_scb_desc, tau), '
+                   'sizeof(b200_scb_state), offsetof(b200_scb_state, coeff), offsetof(b200_scb_state, q));return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    from nova_b200.ppsnark import ScbDesc
+    assert got[0] == 72 and got[1] == 8            # spartan._device_loop packs round (8) + state (64)
+    assert got[2] == 144 and got[3] == 64 and got[4] == 72   # head of the state the mirrors read back
+    assert got[5] == ctypes.sizeof(ScbDesc) and got[6] == ScbDesc.tau.offset
+    assert got[7] == 1296 and got[8] == 144 and got[9] == 144 + 512 + 512

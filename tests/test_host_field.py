@@ -175,3 +175,25 @@ def test_sum_of_two_products_single_reduction(hc, fid):
     for i, (a, b, c, d) in enumerate(quads):
         got = int.from_bytes(out.raw[32 * i:32 * i + 32], "little")
         assert got < p and from_mont(p, got) == (a * b + c * d) % p, (a, b, c, d)
+
+
+def test_field_identities_property_based(hc):
+    """hypothesis: for random 256-bit inputs (reduced mod p) the host build of the device multiplier satisfies
+    mul2_add(a, b, c, d) == mul(a, b) + mul(c, d) and distributes over addition, on all four fields."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(0, 3), st.lists(st.integers(0, (1 << 256) - 1), min_size=4, max_size=4))
+    def prop(fid, xs):
+        p = FIELD_MODULUS[fid]
+        a, b, c, d = (x % p for x in xs)
+        col = lambda v: _buf(mont_bytes(p, v))
+        out = ctypes.create_string_buffer(32)
+        assert hc.hc_mul2_add(fid, col(a), col(b), col(c), col(d), out, ctypes.c_size_t(1)) == 0
+        assert from_mont(p, int.from_bytes(out.raw, "little")) == (a * b + c * d) % p
+        m1, m2 = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        hc.hc_fe_op(fid, 2, col((a + c) % p), col(b), m1, ctypes.c_size_t(1))
+        hc.hc_mul2_add(fid, col(a), col(b), col(c), col(b), m2, ctypes.c_size_t(1))
+        assert m1.raw == m2.raw  # (a + c) b == a b + c b, bit for bit
+    prop()
