@@ -447,9 +447,210 @@ NOVA_HD fe_t fe_mul(const fe_t& a, const fe_t& b) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------
+// Dedicated squaring (A/B variant, -DNOVA_SQR_DEDICATED; NOT the default until it is timed on a GPU).
+// a^2 = sum_i a_i^2 2^(64 i) + 2 sum_{i<j} a_i a_j 2^(32 (i+j)): 28 cross products + 8 squares, then the 64
+// products of the Montgomery reduction = 100 wide products instead of 128.  Same even/odd accumulators as the
+// multiplier: a_i a_j lands in E when i + j is even, in O when it is odd; for a fixed j the partners i < j of
+// each parity form ONE carry chain of 1..4 products whose carry-out limb is still untouched at that point
+// (the chains are issued in increasing j).  After doubling both accumulators (plain shifts, ALU pipe) the eight
+// squares go into E as one chain, and eight reduce-only rounds use the multiplier's own chains.
+// ---------------------------------------------------------------------------------------
+
+// X[OFF .. OFF+2NP-1] += (x0 .. x_{NP-1}) * y, product k on limbs (OFF+2k, OFF+2k+1); X[OFF+2NP] += carry-out
+template <int OFF, int NP, int N>
+NOVA_HD void chain_mad_n(uint32_t (&X)[N], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+  static_assert(NP >= 1 && NP <= 4 && OFF + 2 * NP < N, "chain does not fit the accumulator");
+#ifdef __CUDA_ARCH__
+  if constexpr (NP == 1) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(X[OFF + 0]), "+r"(X[OFF + 1]), "+r"(X[OFF + 2])
+        : "r"(x0), "r"(y));
+  } else if constexpr (NP == 2) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(X[OFF + 0]), "+r"(X[OFF + 1]), "+r"(X[OFF + 2]), "+r"(X[OFF + 3]), "+r"(X[OFF + 4])
+        : "r"(x0), "r"(x1), "r"(y));
+  } else if constexpr (NP == 3) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(X[OFF + 0]), "+r"(X[OFF + 1]), "+r"(X[OFF + 2]), "+r"(X[OFF + 3]), "+r"(X[OFF + 4]),
+          "+r"(X[OFF + 5]), "+r"(X[OFF + 6])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(y));
+  } else {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(X[OFF + 0]), "+r"(X[OFF + 1]), "+r"(X[OFF + 2]), "+r"(X[OFF + 3]), "+r"(X[OFF + 4]),
+          "+r"(X[OFF + 5]), "+r"(X[OFF + 6]), "+r"(X[OFF + 7]), "+r"(X[OFF + 8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+  }
+#else
+  const uint32_t xs[4] = {x0, x1, x2, x3};
+  uint64_t cf = 0;
+  for (int k = 0; k < NP; k++) {
+    uint64_t prod = (uint64_t)xs[k] * y;
+    uint64_t t = (uint64_t)X[OFF + 2 * k] + (uint32_t)prod + cf;
+    X[OFF + 2 * k] = (uint32_t)t;
+    cf = t >> 32;
+    t = (uint64_t)X[OFF + 2 * k + 1] + (prod >> 32) + cf;
+    X[OFF + 2 * k + 1] = (uint32_t)t;
+    cf = t >> 32;
+  }
+  X[OFF + 2 * NP] += (uint32_t)cf;
+#endif
+}
+
+// X[0 .. 15] += a_k^2 on limbs (2k, 2k+1), k = 0..7, as one carry chain; X[16] += carry-out
+NOVA_HD void chain_sqr_diag(uint32_t (&X)[17], const fe_t& a) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32 %0, %17, %17, %0;\n\t"
+      "madc.hi.cc.u32 %1, %17, %17, %1;\n\t"
+      "madc.lo.cc.u32 %2, %18, %18, %2;\n\t"
+      "madc.hi.cc.u32 %3, %18, %18, %3;\n\t"
+      "madc.lo.cc.u32 %4, %19, %19, %4;\n\t"
+      "madc.hi.cc.u32 %5, %19, %19, %5;\n\t"
+      "madc.lo.cc.u32 %6, %20, %20, %6;\n\t"
+      "madc.hi.cc.u32 %7, %20, %20, %7;\n\t"
+      "madc.lo.cc.u32 %8, %21, %21, %8;\n\t"
+      "madc.hi.cc.u32 %9, %21, %21, %9;\n\t"
+      "madc.lo.cc.u32 %10, %22, %22, %10;\n\t"
+      "madc.hi.cc.u32 %11, %22, %22, %11;\n\t"
+      "madc.lo.cc.u32 %12, %23, %23, %12;\n\t"
+      "madc.hi.cc.u32 %13, %23, %23, %13;\n\t"
+      "madc.lo.cc.u32 %14, %24, %24, %14;\n\t"
+      "madc.hi.cc.u32 %15, %24, %24, %15;\n\t"
+      "addc.u32 %16, %16, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
+        "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(X[12]), "+r"(X[13]), "+r"(X[14]), "+r"(X[15]),
+        "+r"(X[16])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+#else
+  uint64_t cf = 0;
+  for (int k = 0; k < 8; k++) {
+    uint64_t prod = (uint64_t)a.l[k] * a.l[k];
+    uint64_t t = (uint64_t)X[2 * k] + (uint32_t)prod + cf;
+    X[2 * k] = (uint32_t)t;
+    cf = t >> 32;
+    t = (uint64_t)X[2 * k + 1] + (prod >> 32) + cf;
+    X[2 * k + 1] = (uint32_t)t;
+    cf = t >> 32;
+  }
+  X[16] += (uint32_t)cf;
+#endif
+}
+
+// cross products of column j: partners i < j with i = j (mod 2) go to E, the others to O
+template <int J>
+NOVA_HD void sqr_cross(uint32_t (&E)[17], uint32_t (&O)[17], const fe_t& a) {
+  constexpr int SAME0 = J & 1;            // first partner of the same parity as J
+  constexpr int NSAME = J / 2;            // i = SAME0, SAME0 + 2, ... < J
+  constexpr int OTH0 = 1 - (J & 1);
+  constexpr int NOTH = (J + 1) / 2;
+  const uint32_t y = a.l[J];
+  auto limb = [&](int i) { return i < 8 ? a.l[i] : 0u; };
+  if constexpr (NSAME > 0)  // positions i + J even
+    chain_mad_n<SAME0 + J, NSAME>(E, limb(SAME0), limb(SAME0 + 2), limb(SAME0 + 4), limb(SAME0 + 6), y);
+  if constexpr (NOTH > 0)   // positions i + J odd
+    chain_mad_n<OTH0 + J, NOTH>(O, limb(OTH0), limb(OTH0 + 2), limb(OTH0 + 4), limb(OTH0 + 6), y);
+}
+
+// reduce-only round I: m = (position I incl. the carry retired from position I-1) * INV, then + m p
+template <class F, int I>
+NOVA_HD void mont_reduce_round(uint32_t (&E)[17], uint32_t (&O)[17]) {
+  uint32_t c = 0;
+  if constexpr (I > 0) c = (uint32_t)(((uint64_t)E[I - 1] + O[I - 1]) >> 32);
+  const uint32_t m = (E[I] + O[I] + c) * F::INV;
+  if constexpr ((I & 1) == 0) {
+    if constexpr (I == 0)
+      chain_mad<I, false>(E, F::p(0), F::p(2), F::p(4), F::p(6), m);
+    else
+      chain_mad<I, true>(E, F::p(0), F::p(2), F::p(4), F::p(6), m, E[I - 1], O[I - 1]);
+    chain_mad<I + 1, false>(O, F::p(1), F::p(3), F::p(5), F::p(7), m);
+  } else {
+    chain_mad<I, true>(O, F::p(0), F::p(2), F::p(4), F::p(6), m, E[I - 1], O[I - 1]);
+    chain_mad<I + 1, false>(E, F::p(1), F::p(3), F::p(5), F::p(7), m);
+  }
+}
+
+template <class F>
+NOVA_HD fe_t fe_sqr_dedicated(const fe_t& a) {
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) E[i] = O[i] = 0;
+  sqr_cross<1>(E, O, a);
+  sqr_cross<2>(E, O, a);
+  sqr_cross<3>(E, O, a);
+  sqr_cross<4>(E, O, a);
+  sqr_cross<5>(E, O, a);
+  sqr_cross<6>(E, O, a);
+  sqr_cross<7>(E, O, a);
+#pragma unroll
+  for (int i = 16; i > 0; i--) {  // double both halves of the cross sum (E + O < 2^511)
+    E[i] = (E[i] << 1) | (E[i - 1] >> 31);
+    O[i] = (O[i] << 1) | (O[i - 1] >> 31);
+  }
+  E[0] <<= 1;
+  O[0] <<= 1;
+  chain_sqr_diag(E, a);
+  // T = E + O (< p^2).  The reduce-only chains end with a non-propagating `limb I+8 += carry`, which is only
+  // safe while that limb holds a small carry count -- true in the multiplier, not on top of T's data limbs.  So
+  // the reduction runs on fresh accumulators seeded with the LOW halves of E and O (the invariant of the
+  // integrated multiplier is restored: limb I+8 is untouched when round I starts), and T's high half is added
+  // afterwards:  (T + sum m_i p 2^(32 i)) / 2^256 = (E_hi + O_hi) + (E_lo + O_lo + sum m_i p 2^(32 i)) / 2^256.
+  uint32_t RE[17], RO[17];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    RE[i] = E[i];
+    RO[i] = O[i];
+  }
+#pragma unroll
+  for (int i = 8; i < 17; i++) RE[i] = RO[i] = 0;
+  mont_reduce_round<F, 0>(RE, RO);
+  mont_reduce_round<F, 1>(RE, RO);
+  mont_reduce_round<F, 2>(RE, RO);
+  mont_reduce_round<F, 3>(RE, RO);
+  mont_reduce_round<F, 4>(RE, RO);
+  mont_reduce_round<F, 5>(RE, RO);
+  mont_reduce_round<F, 6>(RE, RO);
+  mont_reduce_round<F, 7>(RE, RO);
+  uint32_t lo[8], hiE[8], hiO[8], hi[8];
+  add8_cin(lo, &RE[8], &RO[8], RE[7], RO[7]);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    hiE[i] = E[8 + i];
+    hiO[i] = O[8 + i];
+  }
+  add8(hi, hiE, hiO);  // every partial sum is <= the final value < 2p < 2^256: no carry leaves
+  fe_t r;
+  add8(r.l, hi, lo);
+  fe_reduce_once<F>(r.l);
+  return r;
+}
+
 template <class F>
 NOVA_HD fe_t fe_sqr(const fe_t& a) {
+#if defined(NOVA_SQR_DEDICATED) && !defined(NOVA_MUL_CS)
+  return fe_sqr_dedicated<F>(a);
+#else
   return fe_mul<F>(a, a);
+#endif
 }
 
 // Montgomery <-> canonical

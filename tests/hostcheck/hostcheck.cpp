@@ -16,6 +16,7 @@ static void fe_op(int op, const fe_t& a, const fe_t& b, fe_t& r) {
     case 5: r = fe_from_mont<F>(a); break;
     case 6: r = fe_neg<F>(a); break;
     case 7: r = fe_mul_cs<F>(a, b); break;
+    case 8: r = fe_sqr_dedicated<F>(a); break;
   }
 }
 

@@ -197,3 +197,23 @@ def test_field_identities_property_based(hc):
         hc.hc_mul2_add(fid, col(a), col(b), col(c), col(b), m2, ctypes.c_size_t(1))
         assert m1.raw == m2.raw  # (a + c) b == a b + c b, bit for bit
     prop()
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_dedicated_squaring(hc, fid):
+    """fe_sqr_dedicated (28 cross products + 8 squares + reduce-only rounds; A/B variant -DNOVA_SQR_DEDICATED)
+    == a^2, incl. Montgomery REPRESENTATIONS made of all-ones limb patterns, which maximise every carry."""
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(60 + fid)
+    reprs = [0, 1, p - 1, p - 2]
+    for k in range(1, 254):
+        reprs += [(1 << k) - 1, p - (1 << k), ((1 << k) - 1) << 1]
+    reprs += [int("ffffffff" * w + "00000000" * (7 - w), 16) for w in range(8)]      # ones in the low limbs
+    reprs += [int("7fffffff" + "ffffffff" * 6 + "fffffffe", 16) % p, int("55555555" * 8, 16) % p, int("aaaaaaaa" * 8, 16) % p]
+    vals = [from_mont(p, r % p) for r in reprs] + [rng.field(p) for _ in range(3000)]
+    A = b"".join(mont_bytes(p, a) for a in vals)
+    out = ctypes.create_string_buffer(len(A))
+    assert hc.hc_fe_op(fid, 8, _buf(A), _buf(A), out, ctypes.c_size_t(len(vals))) == 0
+    for i, a in enumerate(vals):
+        got = int.from_bytes(out.raw[32 * i:32 * i + 32], "little")
+        assert got < p and from_mont(p, got) == a * a % p, hex(a)

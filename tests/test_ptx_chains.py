@@ -166,7 +166,7 @@ def write_back(ops_out, vals, env):
 def blocks():
     text = open(SRC).read()
     stmts = [(ln, parse_asm(body)) for ln, body in _asm_statements(text)]
-    assert len(stmts) == 7, "a chain was added or removed in field.cuh: extend this test"
+    assert len(stmts) == 12, "a chain was added or removed in field.cuh: extend this test"
     return stmts
 
 
@@ -239,3 +239,32 @@ def test_carry_save_primitives(blocks):
         before = dict(env)
         write_back(outs, run_ptx(instrs, bind(outs, ins, env)), env)
         assert env["k_next"] == before["k_next"] + ((before["e"] + before["o"]) >> 32) + before["kz"]
+
+
+def test_variable_length_chains_of_the_dedicated_squaring(blocks):
+    """chain_mad_n<OFF, NP>: X[OFF .. OFF+2NP-1] += (x0 .. x_{NP-1}) * y, carry into X[OFF+2NP]; chain_sqr_diag:
+    X[0..15] += a_k^2 on limbs (2k, 2k+1), carry into X[16]."""
+    for NP in (1, 2, 3, 4):
+        instrs, outs, ins = blocks[6 + NP][1]
+        assert len(outs) == 2 * NP + 1 and len(ins) == NP + 1
+        for _ in range(300):
+            OFF = RND.randrange(0, 17 - 2 * NP)
+            X = [r32() for _ in range(17)]
+            X[OFF + 2 * NP] = RND.randrange(0, 4)  # untouched / small when the chain is issued (see field.cuh)
+            env = dict(OFF=OFF, X=list(X), x0=r32(), x1=r32(), x2=r32(), x3=r32(), y=r32())
+            write_back(outs, run_ptx(instrs, bind(outs, ins, env)), env)
+            exp = value(X[OFF:OFF + 2 * NP + 1]) + sum(env[f"x{k}"] * env["y"] << (64 * k) for k in range(NP))
+            assert value(env["X"][OFF:OFF + 2 * NP + 1]) == exp
+            assert env["X"][:OFF] == X[:OFF] and env["X"][OFF + 2 * NP + 1:] == X[OFF + 2 * NP + 1:]
+    instrs, outs, ins = blocks[11][1]
+    assert len(outs) == 17 and len(ins) == 8
+
+    class A:  # the operand expressions read a.l[k]
+        pass
+    for _ in range(300):
+        a = A()
+        a.l = [r32() for _ in range(8)]
+        X = [r32() for _ in range(16)] + [RND.randrange(0, 3)]
+        env = dict(X=list(X), a=a)
+        write_back(outs, run_ptx(instrs, bind(outs, ins, env)), env)
+        assert value(env["X"]) == value(X) + sum(a.l[k] * a.l[k] << (64 * k) for k in range(8))

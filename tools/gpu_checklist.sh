@@ -5,6 +5,7 @@
 # Everything lands in gpurun_out/checklist/ ; nothing here is a bench value (bench.py is the bench).
 # Before calling: build the A/B variant HERE (it travels as a .so):
 #     make -C nova_b200/csrc variant VARIANT=y3 VFLAGS=-DNOVA_MADD_FUSED_Y3 -j8
+#     make -C nova_b200/csrc variant VARIANT=y3sq "VFLAGS=-DNOVA_MADD_FUSED_Y3 -DNOVA_SQR_DEDICATED" -j8
 set -u
 OUT=gpurun_out/checklist
 mkdir -p "$OUT"
@@ -21,6 +22,11 @@ if [ -f nova_b200/libnova_b200_y3.so ]; then
   run base_devtime   timeout 300  python tools/devtime.py 20 22
 else
   echo "libnova_b200_y3.so missing: build the variant first" | tee -a "$OUT/summary.txt"
+fi
+
+if [ -f nova_b200/libnova_b200_y3sq.so ]; then   # + dedicated squaring (static profile: fewer IMAD, more registers)
+  run y3sq_parity    timeout 900  env NOVA_B200_LIB=nova_b200/libnova_b200_y3sq.so python -m pytest tests/test_msm_gpu.py tests/test_fieldvec_gpu.py -m gpu -x -q -p no:cacheprovider
+  run y3sq_devtime   timeout 300  env NOVA_B200_LIB=nova_b200/libnova_b200_y3sq.so python tools/devtime.py 20 22
 fi
 
 # 3. prover replays: host transcript vs device transcript, streamed witness reuse
