@@ -611,32 +611,27 @@ NOVA_HD fe_t fe_sqr_dedicated(const fe_t& a) {
   chain_sqr_diag(E, a);
   // T = E + O (< p^2).  The reduce-only chains end with a non-propagating `limb I+8 += carry`, which is only
   // safe while that limb holds a small carry count -- true in the multiplier, not on top of T's data limbs.  So
-  // the reduction runs on fresh accumulators seeded with the LOW halves of E and O (the invariant of the
-  // integrated multiplier is restored: limb I+8 is untouched when round I starts), and T's high half is added
-  // afterwards:  (T + sum m_i p 2^(32 i)) / 2^256 = (E_hi + O_hi) + (E_lo + O_lo + sum m_i p 2^(32 i)) / 2^256.
-  uint32_t RE[17], RO[17];
+  // T's high half is set aside first and the reduction runs on the LOW halves of E and O with zeroed high limbs
+  // (the invariant of the integrated multiplier is restored: limb I+8 is untouched when round I starts); the
+  // high half is added afterwards:  (T + sum m_i p 2^(32 i)) / 2^256 = (E_hi + O_hi) + (E_lo + O_lo + sum m_i p 2^(32 i)) / 2^256.
+  uint32_t hiE[8], hiO[8], lo[8], hi[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    RE[i] = E[i];
-    RO[i] = O[i];
-  }
-#pragma unroll
-  for (int i = 8; i < 17; i++) RE[i] = RO[i] = 0;
-  mont_reduce_round<F, 0>(RE, RO);
-  mont_reduce_round<F, 1>(RE, RO);
-  mont_reduce_round<F, 2>(RE, RO);
-  mont_reduce_round<F, 3>(RE, RO);
-  mont_reduce_round<F, 4>(RE, RO);
-  mont_reduce_round<F, 5>(RE, RO);
-  mont_reduce_round<F, 6>(RE, RO);
-  mont_reduce_round<F, 7>(RE, RO);
-  uint32_t lo[8], hiE[8], hiO[8], hi[8];
-  add8_cin(lo, &RE[8], &RO[8], RE[7], RO[7]);
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < 8; i++) {  // set T's high half aside and reduce the low half in place
     hiE[i] = E[8 + i];
     hiO[i] = O[8 + i];
+    E[8 + i] = 0;
+    O[8 + i] = 0;
   }
+  E[16] = O[16] = 0;  // (E, O <= T < 2^512: limb 16 carried nothing)
+  mont_reduce_round<F, 0>(E, O);
+  mont_reduce_round<F, 1>(E, O);
+  mont_reduce_round<F, 2>(E, O);
+  mont_reduce_round<F, 3>(E, O);
+  mont_reduce_round<F, 4>(E, O);
+  mont_reduce_round<F, 5>(E, O);
+  mont_reduce_round<F, 6>(E, O);
+  mont_reduce_round<F, 7>(E, O);
+  add8_cin(lo, &E[8], &O[8], E[7], O[7]);
   add8(hi, hiE, hiO);  // every partial sum is <= the final value < 2p < 2^256: no carry leaves
   fe_t r;
   add8(r.l, hi, lo);
