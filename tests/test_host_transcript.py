@@ -200,3 +200,21 @@ def test_eq_tables_are_contiguous_tau_slices():
             assert tab == pyref.eq_evals(p, taus[fh - k:fh])
         for k, tab in enumerate(eq.poly_eq_right):
             assert tab == pyref.eq_evals(p, taus[l - k:l])
+
+
+def test_keccak_and_from_uniform_property_based(hc):
+    """hypothesis: Keccak-256 of arbitrary messages up to the buffer limit and from_uniform of arbitrary 64 bytes."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.binary(min_size=0, max_size=2175), st.integers(0, 3), st.binary(min_size=64, max_size=64))
+    def prop(msg, fid, wide):
+        out = ctypes.create_string_buffer(32)
+        assert hc.hc_keccak256(_buf(msg) if msg else None, ctypes.c_size_t(len(msg)), out) == 0
+        assert out.raw == keccak256(msg)
+        p = FIELD_MODULUS[fid]
+        o2 = ctypes.create_string_buffer(32)
+        assert hc.hc_from_uniform(fid, _buf(wide), o2) == 0
+        assert from_mont(p, int.from_bytes(o2.raw, "little")) == int.from_bytes(wide, "little") % p
+    prop()
