@@ -45,7 +45,9 @@ enum {
   B200_E_HANDLE = 3,   /* unknown / released handle */
   B200_E_NOMEM = 4,    /* device memory exhausted */
   B200_E_RANGE = 5,    /* slice outside the registered key (pedersen.rs:264 assert) */
-  B200_E_ZERO = 6      /* batch_invert met a zero (NovaError::InternalError, spartan/mod.rs:98-100) */
+  B200_E_ZERO = 6,     /* batch_invert met a zero (NovaError::InternalError, spartan/mod.rs:98-100) */
+  B200_E_POINT = 7     /* a key point is non-canonical or off the curve (NovaError::InvalidCommitmentKey,
+                          hyperkzg.rs:113-119; PtauFileError::PointNotOnCurve, ptau.rs:386-388) */
 };
 
 /* ---- library / device ------------------------------------------------------------------ */
@@ -81,6 +83,15 @@ int b200_profile_read(double* stage_ms, int nstages, uint64_t* msms, uint64_t* l
  * window_bits = 0 picks c from n.  Keys are immutable after registration. */
 int b200_ck_register(int curve_id, const void* bases_affine_mont, size_t n,
                      const void* h_affine_mont_or_null, int window_bits, uint64_t* ck_handle);
+/* The same registration for points that arrive from OUTSIDE the process -- CommitmentEngine::load_setup ->
+ * read_ptau -> read_points (hyperkzg.rs:658-675, ptau.rs:372-438): every G1 point must have canonical
+ * coordinates (read_raw) and lie on the curve, else PtauFileError::PointNotOnCurve.  The raw section bytes of
+ * a PTAU file ARE this library's base layout (write_raw = in-memory Montgomery limbs, ptau.rs:197-208), so the
+ * section goes to HBM unchanged, is validated there (one pass, 64 B and three products per point) and only then
+ * expanded.  On an invalid point: B200_E_POINT, *first_bad = its index (n = the blinding generator), no key. */
+int b200_ck_register_checked(int curve_id, const void* bases_affine_mont, size_t n,
+                             const void* h_affine_mont_or_null, int window_bits, uint64_t* ck_handle,
+                             size_t* first_bad);
 /* test/bench key: bases[i] = (k0 + i) * G generated on the device (the analogue of the
  * reference's test-only setups, hyperkzg.rs:357-376 / curve_property_tests.rs:186-194);
  * with_h != 0 appends h = (k0 + n) * G as the blinding generator. */
@@ -189,7 +200,8 @@ int b200_sc_eval_sharded_dev(int field_id, int form, const void* A, const void* 
 /* CommitmentKey::new's validation loop (provider/hyperkzg.rs:113-119: every G1 base and h must be on
  * the curve, else NovaError::InvalidCommitmentKey), run on the device while the key is on its way
  * to HBM anyway.  *first_bad = SIZE_MAX when all n points satisfy y^2 = x^3 + b (the identity
- * encoding (0,0) passes, as halo2curves' is_on_curve does), else the smallest offending index. */
+ * encoding (0,0) passes, as halo2curves' is_on_curve does), else the smallest offending index.  A coordinate
+ * >= p also counts as offending (it cannot be an in-memory field element; read_raw refuses it, ptau.rs:381). */
 int b200_ck_validate(int curve_id, const void* bases, size_t n, size_t* first_bad);
 
 /* ---- streamed witness hand-off ----------------------------------------------

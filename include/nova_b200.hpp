@@ -56,6 +56,22 @@ class CommitmentKey {
   CommitmentKey(const std::vector<Affine>& ck, const Affine* h = nullptr, int window_bits = 0) : n_(ck.size()) {
     check(b200_ck_register(C::curve, ck.data(), ck.size(), h, window_bits, &handle_), "b200_ck_register");
   }
+  // Points from outside the process (load_setup -> read_ptau, hyperkzg.rs:658-675, ptau.rs:372-438): validated in
+  // HBM before the tables are built.  Throws InvalidCommitmentKey with the index of the first bad point.
+  struct InvalidCommitmentKey : std::runtime_error {
+    size_t index;
+    explicit InvalidCommitmentKey(size_t i)
+        : std::runtime_error("InvalidCommitmentKey: point " + std::to_string(i) + " is non-canonical or off the curve"),
+          index(i) {}
+  };
+  struct Untrusted {};
+  CommitmentKey(Untrusted, const std::vector<Affine>& ck, const Affine* h = nullptr, int window_bits = 0)
+      : n_(ck.size()) {
+    size_t bad = 0;
+    int rc = b200_ck_register_checked(C::curve, ck.data(), ck.size(), h, window_bits, &handle_, &bad);
+    if (rc == B200_E_POINT) throw InvalidCommitmentKey(bad);
+    check(rc, "b200_ck_register_checked");
+  }
   CommitmentKey(const CommitmentKey&) = delete;
   CommitmentKey& operator=(const CommitmentKey&) = delete;
   ~CommitmentKey() { if (handle_) b200_ck_release(handle_); }

@@ -347,6 +347,13 @@ int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n,
   return enqueue_msm(ck, ck.ws, base_offset, d_scalars, n, d_out, s, small_elem_bytes, blinded);
 }
 
+struct dev_flag {
+  uint32_t* p = nullptr;
+  ~dev_flag() {
+    if (p) cudaFree(p);
+  }
+};
+
 constexpr size_t SMALL_KEY_MAX = (size_t)1 << 21;
 constexpr int SMALL_KEY_WINDOW = 17;
 
@@ -363,8 +370,13 @@ int choose_window(size_t n) {
   return c;
 }
 
+// b of y^2 = x^3 + b per curve id (bn256_grumpkin.rs:35-41,80-86; pasta.rs:33-47)
+constexpr int CURVE_B_SMALL[4] = {3, -17, 5, 5};
+
+// first_bad != nullptr: validate the raw points (bases, then h) where they land in HBM, before the tables are
+// built from them; an invalid point ends the registration with B200_E_POINT and its index in *first_bad.
 int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n, const void* h,
-                 int window_bits, bool expand, std::shared_ptr<ck_ctx>& out) {
+                 int window_bits, bool expand, std::shared_ptr<ck_ctx>& out, size_t* first_bad = nullptr) {
   if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
   if (bases == nullptr || n == 0) return fail(B200_E_ARG, "empty commitment key");
   if (window_bits != 0 && (window_bits < 2 || window_bits > 24))
@@ -389,6 +401,24 @@ int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n
                      g_dev.stream));
   if (h)
     CU(cudaMemcpyAsync((char*)ck->tables + n * 64, h, 64, cudaMemcpyHostToDevice, g_dev.stream));
+  if (first_bad) {
+    *first_bad = SIZE_MAX;
+    dev_flag flag;
+    CU(cudaMalloc(&flag.p, 4));
+    CU(cudaMemsetAsync(flag.p, 0xFF, 4, g_dev.stream));
+    ops_for_field(CURVES[curve_id].base_fid)
+        ->on_curve(g_dev.stream, ck->tables, ck->stride, CURVE_B_SMALL[curve_id], flag.p);
+    count_launch(1);
+    CU(cudaGetLastError());
+    uint32_t bad = 0;
+    CU(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, g_dev.stream));
+    CU(cudaStreamSynchronize(g_dev.stream));
+    if (bad != 0xFFFFFFFFu) {
+      *first_bad = bad;
+      return fail(B200_E_POINT, "key point %u%s has a non-canonical coordinate or is not on the curve", bad,
+                  (h && bad == n) ? " (the blinding generator)" : "");
+    }
+  }
   {  // converts table 0 to the kernels' table format and builds tables 1..F-1
     const field_ops* bops = ops_for_field(CURVES[curve_id].base_fid);
     bops->expand_key(g_dev.stream, ck->tables, ck->stride, ck->F, ck->c * ck->G);
@@ -562,6 +592,21 @@ int b200_ck_register(int curve_id, const void* bases, size_t n, const void* h, i
   if (!handle) return fail(B200_E_ARG, "null handle pointer");
   std::shared_ptr<ck_ctx> ck;
   rc = register_key(curve_id, bases, false, n, h, window_bits, true, ck);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_handles_mu);
+  *handle = g_next_handle++;
+  g_handles[*handle] = ck;
+  return B200_OK;
+}
+
+int b200_ck_register_checked(int curve_id, const void* bases, size_t n, const void* h, int window_bits,
+                             uint64_t* handle, size_t* first_bad) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!handle || !first_bad) return fail(B200_E_ARG, "null pointer");
+  *handle = 0;
+  std::shared_ptr<ck_ctx> ck;
+  rc = register_key(curve_id, bases, false, n, h, window_bits, true, ck, first_bad);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_handles_mu);
   *handle = g_next_handle++;

@@ -52,6 +52,13 @@ NOVA_HD bool affine_on_curve(const affine_t& p, const fe_t& b_mont) {
   return fe_eq(lhs, rhs);
 }
 
+// A point as it arrives from a file or another process: both coordinates canonical AND on the curve
+// (read_points, provider/ptau.rs:372-392; in-memory halo2curves points are canonical by construction).
+template <class F>
+NOVA_HD bool affine_valid_raw(const affine_t& p, const fe_t& b_mont) {
+  return fe_is_canonical<F>(p.x) && fe_is_canonical<F>(p.y) && affine_on_curve<F>(p, b_mont);
+}
+
 // dbl-2008-s-1 (a = 0): 2M + 5S.  Precondition: not identity, y != 0 is NOT required
 // (y == 0 gives zz3 = 0, i.e. the identity, which is the correct answer for a 2-torsion point).
 template <class F>

@@ -211,6 +211,14 @@ NOVA_HD bool fe_eq(const fe_t& a, const fe_t& b) {
           (a.l[4] ^ b.l[4]) | (a.l[5] ^ b.l[5]) | (a.l[6] ^ b.l[6]) | (a.l[7] ^ b.l[7])) == 0;
 }
 
+// a < p as an integer: what SerdeObject::read_raw accepts as a coordinate (provider/ptau.rs:381-383)
+template <class F>
+NOVA_HD bool fe_is_canonical(const fe_t& a) {
+  uint32_t p[8], t[8];
+  load_p<F>(p);
+  return sub8(t, a.l, p) != 0;
+}
+
 // conditional subtract of p: r in [0, 2p) -> [0, p)
 template <class F>
 NOVA_HD void fe_reduce_once(uint32_t (&r)[8]) {

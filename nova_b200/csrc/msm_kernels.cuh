@@ -725,8 +725,8 @@ __global__ void __launch_bounds__(128) k_expand_key(void* __restrict__ tables, s
   }
 }
 
-// Key validation (hyperkzg.rs:113-119): the smallest index of a base that is not on the curve is
-// left in *first_bad (initialised to 0xFFFFFFFF by the caller).  64 B read per point, 3 products.
+// Key validation (hyperkzg.rs:113-119, ptau.rs:372-392): the smallest index of a base that has a non-canonical
+// coordinate or is not on the curve is left in *first_bad (initialised to 0xFFFFFFFF by the caller).  64 B read per point, 3 products.
 template <class F>
 __global__ void __launch_bounds__(256) k_on_curve(const void* __restrict__ pts, size_t n, int b_small,
                                                   uint32_t* __restrict__ first_bad) {
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(256) k_on_curve(const void* __restrict__ pts, 
     affine_t p;
     p.x = fe_load(pts, 2 * i);
     p.y = fe_load(pts, 2 * i + 1);
-    if (!affine_on_curve<F>(p, b)) atomicMin(first_bad, (uint32_t)i);
+    if (!affine_valid_raw<F>(p, b)) atomicMin(first_bad, (uint32_t)i);
   }
 }
 

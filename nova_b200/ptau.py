@@ -1,0 +1,361 @@
+"""PTAU files <-> device-resident commitment keys ("PTAU loading onto device").
+
+Host-side mirror of `src/provider/ptau.rs` (`read_ptau` :402-438, `write_ptau` :217-269, `read_meta_data`
+:271-327, `read_header` :329-370, `check_sanity_of_ptau_file` :441-455) and of
+`CommitmentEngine::{load_setup, save_setup}` for HyperKZG (hyperkzg.rs:657-689), with the reference's error
+type (`PtauFileError`, ptau.rs:100-151) as an exception hierarchy.
+
+What moves to the device: the G1 section.  `write_raw` / `read_raw` (ptau.rs:197-208, 372-392) are the in-memory
+Montgomery limbs of halo2curves, i.e. exactly the 64-byte base layout of include/nova_b200.h -- the section is
+handed to `b200_ck_register_checked` unchanged, validated in HBM (canonical coordinates + curve equation, the two
+checks of `read_points`) and expanded into the window tables only if every point passed.  The two G2 points of
+the verifier key (`tau_H`) are O(1) control-plane data and are checked here on the host (curve equation over
+Fq2 and [r]P = O, ptau.rs:424-435); `h = from_label(label, 1)` (hyperkzg.rs:672) stays with the caller.
+"""
+from __future__ import annotations
+
+import ctypes
+import io
+import struct
+
+from . import fields
+from .native import c_size_t, c_u64, check, lib
+from .provider import CommitmentKey, Curve, _cbuf
+
+PTAU_VERSION = 1          # ptau.rs:161
+NUM_SECTIONS_FULL = 11    # ptau.rs:163
+NUM_SECTIONS_PRUNED = 3   # ptau.rs:165
+MAX_PPOT_POWER = 28       # ptau.rs:168
+B200_E_POINT = 7
+
+
+class PtauFileError(Exception):
+    """ptau.rs:100-151"""
+
+
+class InvalidHead(PtauFileError):
+    pass
+
+
+class UnsupportedVersion(PtauFileError):
+    def __init__(self, version):
+        super().__init__(f"Unsupported version {version}")
+        self.version = version
+
+
+class InvalidNumSections(PtauFileError):
+    def __init__(self, n):
+        super().__init__(f"Invalid number of sections {n}")
+        self.num_sections = n
+
+
+class InvalidPrime(PtauFileError):
+    def __init__(self, modulus):
+        super().__init__(f"Invalid base prime {modulus:#x}")
+        self.modulus = modulus
+
+
+class InsufficientPowerForG1(PtauFileError):
+    def __init__(self, power, required):
+        super().__init__(f"Insufficient power for G1 (power {power}, required {required})")
+        self.power, self.required = power, required
+
+
+class InsufficientPowerForG2(PtauFileError):
+    def __init__(self, power, required):
+        super().__init__(f"Insufficient power for G2 (power {power}, required {required})")
+        self.power, self.required = power, required
+
+
+class PointNotOnCurve(PtauFileError):
+    pass
+
+
+class PointNotInSubgroup(PtauFileError):
+    pass
+
+
+class IoError(PtauFileError):
+    """io::Error: short reads, and read_raw's refusal of a non-canonical coordinate"""
+
+
+# ---------------------------------------------------------------------------------------------
+# little helpers over a seekable binary reader (byteorder::ReadBytesExt, LittleEndian)
+# ---------------------------------------------------------------------------------------------
+def _read_exact(reader, n: int) -> bytes:
+    b = reader.read(n)
+    if b is None or len(b) != n:
+        raise IoError("failed to fill whole buffer")
+    return b
+
+
+def _u32(reader) -> int:
+    return struct.unpack("<I", _read_exact(reader, 4))[0]
+
+
+def _i64(reader) -> int:
+    return struct.unpack("<q", _read_exact(reader, 8))[0]
+
+
+def read_meta_data(reader) -> dict:
+    """ptau.rs:271-327 -> positions of sections 1 (header), 2 (TauG1), 3 (TauG2)"""
+    try:
+        if _read_exact(reader, 4).decode("utf-8") != "ptau":
+            raise InvalidHead("Invalid magic string")
+    except UnicodeDecodeError as e:
+        raise PtauFileError(f"Utf8Error: {e}") from e
+    version = _u32(reader)
+    if version != PTAU_VERSION:
+        raise UnsupportedVersion(version)
+    num_sections = _u32(reader)
+    if num_sections not in (NUM_SECTIONS_FULL, NUM_SECTIONS_PRUNED):
+        raise InvalidNumSections(num_sections)
+    pos = {1: 0, 2: 0, 3: 0}
+    for _ in range(num_sections):
+        sid = _u32(reader)
+        size = _i64(reader)
+        if sid in pos:
+            pos[sid] = reader.tell()
+        reader.seek(size, io.SEEK_CUR)
+    assert pos[1] != 0 and pos[2] != 0 and pos[3] != 0  # the reference's assert_ne!s (ptau.rs:318-320)
+    return dict(pos_header=pos[1], pos_tau_g1=pos[2], pos_tau_g2=pos[3])
+
+
+def read_header(reader, num_g1: int, num_g2: int, base_modulus: int) -> int:
+    """ptau.rs:329-370; returns the power"""
+    n8 = _u32(reader)
+    modulus = int.from_bytes(_read_exact(reader, n8), "little")
+    if modulus != base_modulus:
+        raise InvalidPrime(modulus)
+    power = _u32(reader)
+    max_num_g2 = 1 << power
+    max_num_g1 = max_num_g2 * 2 - 1
+    if num_g1 > max_num_g1:
+        raise InsufficientPowerForG1(power, max_num_g1)
+    if num_g2 > max_num_g2:
+        raise InsufficientPowerForG2(power, max_num_g2)
+    return power
+
+
+def check_sanity_of_ptau_file(path, num_g1: int, num_g2: int, curve: Curve = Curve.BN254_G1) -> None:
+    """ptau.rs:441-455"""
+    try:
+        f = open(path, "rb")
+    except OSError as e:
+        raise IoError(str(e)) from e
+    with f:
+        meta = read_meta_data(f)
+        f.seek(meta["pos_header"])
+        read_header(f, num_g1, num_g2, fields.MODULUS[Curve(curve).base_field])
+
+
+# ---------------------------------------------------------------------------------------------
+# G2 of bn256 on the host: E'(Fq2): y^2 = x^3 + 3/(9+u), Fq2 = Fq[u]/(u^2+1).  O(1) points per key.
+# ---------------------------------------------------------------------------------------------
+_Q = fields.MODULUS[fields.BN254_FQ]
+_R_ORDER = fields.MODULUS[fields.BN254_FR]
+_INV82 = pow(82, -1, _Q)
+_B2 = (27 * _INV82 % _Q, (-3 * _INV82) % _Q)  # 3 / (9 + u) = 3 (9 - u) / 82
+
+
+def _f2_mul(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % _Q, (a[0] * b[1] + a[1] * b[0]) % _Q)
+
+
+def _f2_add(a, b):
+    return ((a[0] + b[0]) % _Q, (a[1] + b[1]) % _Q)
+
+
+def _f2_sub(a, b):
+    return ((a[0] - b[0]) % _Q, (a[1] - b[1]) % _Q)
+
+
+def _f2_inv(a):
+    n = pow(a[0] * a[0] + a[1] * a[1], -1, _Q)
+    return (a[0] * n % _Q, (-a[1]) * n % _Q)
+
+
+def g2_on_curve(P) -> bool:
+    """P = (x, y) with x, y in Fq2 as (c0, c1); None = identity (is_on_curve accepts it)"""
+    if P is None:
+        return True
+    x, y = P
+    return _f2_mul(y, y) == _f2_add(_f2_mul(_f2_mul(x, x), x), _B2)
+
+
+def _g2_add(P, Q):
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    (x1, y1), (x2, y2) = P, Q
+    if x1 == x2:
+        if _f2_add(y1, y2) == (0, 0):
+            return None
+        xx = _f2_mul(x1, x1)
+        lam = _f2_mul(_f2_add(_f2_add(xx, xx), xx), _f2_inv(_f2_add(y1, y1)))
+    else:
+        lam = _f2_mul(_f2_sub(y2, y1), _f2_inv(_f2_sub(x2, x1)))
+    x3 = _f2_sub(_f2_sub(_f2_mul(lam, lam), x1), x2)
+    return (x3, _f2_sub(_f2_mul(lam, _f2_sub(x1, x3)), y1))
+
+
+def g2_mul(P, k: int):
+    acc = None
+    for bit in bin(k)[2:]:
+        acc = _g2_add(acc, acc)
+        if bit == "1":
+            acc = _g2_add(acc, P)
+    return acc
+
+
+def g2_is_torsion_free(P) -> bool:
+    """CofactorGroup::is_torsion_free (ptau.rs:431): [r]P = O"""
+    return g2_mul(P, _R_ORDER) is None
+
+
+def g2_from_raw(b: bytes):
+    """128 bytes = x.c0, x.c1, y.c0, y.c1, each 32-byte little-endian Montgomery limbs (SerdeObject::read_raw);
+    a coordinate >= q is read_raw's io::Error.  All-zero = identity."""
+    cs = []
+    for k in range(4):
+        v = int.from_bytes(b[32 * k:32 * k + 32], "little")
+        if v >= _Q:
+            raise IoError("non-canonical G2 coordinate")
+        cs.append(v * pow(fields.R, -1, _Q) % _Q)
+    if cs == [0, 0, 0, 0]:
+        return None
+    return ((cs[0], cs[1]), (cs[2], cs[3]))
+
+
+def g2_to_raw(P) -> bytes:
+    if P is None:
+        return bytes(128)
+    (x, y) = P
+    return b"".join(fields.to_mont_bytes(fields.BN254_FQ, c) for c in (x[0], x[1], y[0], y[1]))
+
+
+# bn256 G2 generator (halo2curves bn256; the EIP-197 constants)
+G2_GENERATOR = (
+    (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+     11559732032986387107991004021392285783925812861821192530917403151452391805634),
+    (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+     4082367875863433681332203403145435568316851327593401208105741076214120093531),
+)
+
+
+def _check_g2(g2_raw: bytes, num_g2: int) -> None:
+    """read_points::<G2> then the torsion loop, in the reference's order (ptau.rs:421-435): every point is
+    parsed and checked on-curve first, subgroup membership afterwards."""
+    pts = []
+    for k in range(num_g2):
+        P = g2_from_raw(g2_raw[128 * k:128 * k + 128])
+        if not g2_on_curve(P):
+            raise PointNotOnCurve("Point is not on the curve")
+        pts.append(P)
+    for P in pts:
+        if not g2_is_torsion_free(P):
+            raise PointNotInSubgroup("Point is not in the prime-order subgroup")
+
+
+# ---------------------------------------------------------------------------------------------
+# read / write
+# ---------------------------------------------------------------------------------------------
+def _read_sections(reader, num_g1: int, num_g2: int, curve: Curve):
+    meta = read_meta_data(reader)
+    reader.seek(meta["pos_header"])
+    read_header(reader, num_g1, num_g2, fields.MODULUS[curve.base_field])
+    reader.seek(meta["pos_tau_g1"])
+    g1 = _read_exact(reader, 64 * num_g1)
+    reader.seek(meta["pos_tau_g2"])
+    g2 = _read_exact(reader, 128 * num_g2)
+    return g1, g2
+
+
+def _classify_bad_g1(curve: Curve, g1: bytes, idx: int) -> PtauFileError:
+    """The device reports the first point that fails either check of read_points; which of the two it was
+    (read_raw's canonicity -> io::Error, or is_on_curve -> PointNotOnCurve) is decided from its 64 bytes."""
+    p = fields.MODULUS[curve.base_field]
+    pt = g1[64 * idx:64 * idx + 64]
+    if any(int.from_bytes(pt[k:k + 32], "little") >= p for k in (0, 32)):
+        return IoError(f"non-canonical coordinate in G1 point {idx}")
+    return PointNotOnCurve(f"Point is not on the curve (G1 point {idx})")
+
+
+def read_ptau(reader, num_g1: int, num_g2: int, curve: Curve = Curve.BN254_G1):
+    """ptau.rs:402-438 -> (g1 raw bytes, g2 raw bytes), every point validated: G1 on the device
+    (`b200_ck_validate`), G2 on the host.  `load_setup` below is the form that leaves the key resident."""
+    curve = Curve(curve)
+    if num_g2 and curve != Curve.BN254_G1:
+        raise ValueError("G2 sections are defined for bn256 only")
+    g1, g2 = _read_sections(reader, num_g1, num_g2, curve)
+    if num_g1:
+        bad = CommitmentKey.validate(curve, g1)
+        if bad is not None:
+            raise _classify_bad_g1(curve, g1, bad)
+    _check_g2(g2, num_g2)
+    return g1, g2
+
+
+def write_ptau(writer, g1_raw: bytes, g2_raw: bytes, power: int, curve: Curve = Curve.BN254_G1) -> None:
+    """ptau.rs:217-269, byte for byte (the writer trusts its caller, ptau.rs:212-216)"""
+    n8 = 32
+    w = writer.write
+    w(b"ptau")
+    w(struct.pack("<II", PTAU_VERSION, NUM_SECTIONS_FULL))
+    w(struct.pack("<Iq", 1, 4 + n8 + 4))
+    w(struct.pack("<I", n8))
+    w(fields.MODULUS[Curve(curve).base_field].to_bytes(n8, "little"))
+    w(struct.pack("<I", power))
+    w(struct.pack("<Iq", 0, 0))
+    for sid in range(4, NUM_SECTIONS_FULL):
+        w(struct.pack("<Iq", sid, 0))
+    w(struct.pack("<Iq", 2, len(g1_raw)))
+    w(g1_raw)
+    w(struct.pack("<Iq", 3, len(g2_raw)))
+    w(g2_raw)
+
+
+def _next_power_of_two(n: int) -> int:
+    return 1 if n <= 1 else 1 << (n - 1).bit_length()
+
+
+def load_setup(reader, h: bytes | None, n: int, window_bits: int = 0) -> CommitmentKey:
+    """`CommitmentEngine::load_setup` of HyperKZG (hyperkzg.rs:657-675): num = n.next_power_of_two() G1 points
+    and 2 G2 points; ck = the G1 points, tau_H = the LAST G2 point, h = from_label(label, 1) -- derived by the
+    caller and passed in (64 raw bytes, validated with the key; None for a key that never blinds).
+    The G1 section goes to HBM once and is validated there; returns the resident key with `.tau_H` (128 raw
+    bytes)."""
+    curve = Curve.BN254_G1
+    num = _next_power_of_two(n)
+    g1, g2 = _read_sections(reader, num, 2, curve)
+    handle, bad = c_u64(0), c_size_t(0)
+    rc = lib().b200_ck_register_checked(int(curve), _cbuf(g1), num, _cbuf(h) if h else None, window_bits,
+                                        ctypes.byref(handle), ctypes.byref(bad))
+    if rc == B200_E_POINT:
+        if h and bad.value == num:
+            raise PointNotOnCurve("the blinding generator h is not a valid point")
+        raise _classify_bad_g1(curve, g1, bad.value)
+    check(rc)
+    ck = CommitmentKey.__new__(CommitmentKey)
+    ck.curve, ck.n, ck.handle, ck.has_h = curve, num, handle.value, h is not None
+    ck.bases, ck.h = g1, h
+    try:
+        _check_g2(g2, 2)
+    except PtauFileError:
+        ck.release()
+        raise
+    ck.tau_H = g2[128:256]
+    return ck
+
+
+def save_setup(ck: CommitmentKey, writer) -> None:
+    """`save_setup` (hyperkzg.rs:677-689): g2 = [tau_H, tau_H], power = log2(next_power_of_two(len)) + 1"""
+    if ck.bases is None:
+        raise ValueError("this key was generated on the device and has no host copy of its bases")
+    tau_h = getattr(ck, "tau_H", None)
+    if tau_h is None:
+        raise ValueError("key has no tau_H")
+    power = (_next_power_of_two(ck.n).bit_length() - 1) + 1
+    write_ptau(writer, ck.bases, tau_h + tau_h, power, ck.curve)
+

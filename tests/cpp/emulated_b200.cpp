@@ -164,16 +164,35 @@ int b200_msm_indices(uint64_t h, const uint64_t* idx, size_t m, void* out) {
   to_jacobian(k->curve, aff, out);
   return B200_OK;
 }
-int b200_ck_validate(int curve, const void* bases, size_t n, size_t* first_bad) {
+// smallest index of a point with a non-canonical coordinate or off the curve (k_on_curve's contract)
+static size_t first_invalid(int curve, const unsigned char* pts, size_t n) {
   static const int64_t B[4] = {3, -17, 5, 5};
   uint64_t mag = (uint64_t)(B[curve] < 0 ? -B[curve] : B[curve]);
-  unsigned char b[32];
+  unsigned char b[32], canon[64];
   orc_field_from_u64(BASE_FIELD[curve], &mag, 1, b);
   if (B[curve] < 0) orc_fe_op(BASE_FIELD[curve], 6, b, b, b, 1);
-  *first_bad = SIZE_MAX;
-  for (size_t i = 0; i < n; i++)
-    if (orc_on_curve(curve, (const char*)bases + 64 * i, b) != 1) { *first_bad = i; break; }
+  for (size_t i = 0; i < n; i++) {
+    // canonical <=> converting out of and back into Montgomery form reproduces the bytes
+    unsigned char back[64];
+    orc_fe_op(BASE_FIELD[curve], 5, pts + 64 * i, pts + 64 * i, canon, 2);
+    orc_fe_op(BASE_FIELD[curve], 4, canon, canon, back, 2);
+    if (memcmp(back, pts + 64 * i, 64) != 0) return i;
+    if (orc_on_curve(curve, pts + 64 * i, b) != 1) return i;
+  }
+  return SIZE_MAX;
+}
+int b200_ck_validate(int curve, const void* bases, size_t n, size_t* first_bad) {
+  *first_bad = first_invalid(curve, (const unsigned char*)bases, n);
   return B200_OK;
+}
+int b200_ck_register_checked(int curve, const void* bases, size_t n, const void* h, int wb, uint64_t* handle,
+                             size_t* first_bad) {
+  if (curve < 0 || curve > 3 || !bases || !n || !handle || !first_bad) return fail(B200_E_ARG, "bad key");
+  *handle = 0;
+  *first_bad = first_invalid(curve, (const unsigned char*)bases, n);
+  if (*first_bad == SIZE_MAX && h && first_invalid(curve, (const unsigned char*)h, 1) == 0) *first_bad = n;
+  if (*first_bad != SIZE_MAX) return fail(B200_E_POINT, "key point is non-canonical or not on the curve");
+  return b200_ck_register(curve, bases, n, h, wb, handle);
 }
 
 // field vectors (host and "device" pointers are the same thing here)

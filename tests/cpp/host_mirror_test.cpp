@@ -41,7 +41,18 @@ static int fold_mode(const char* path) {
   auto bases = rd<Affine>(f);
   auto h = rd<Affine>(f);
   const Scalar &u1 = sc[0], &u_sum = sc[1], &r = sc[2], &r_T = sc[3], &r_W = sc[4], &one = sc[5];
-  CommitmentKey<BN254> ck(bases, &h[0]);
+  // the key arrives "from a file": validated on the device before its tables are built
+  CommitmentKey<BN254> ck(CommitmentKey<BN254>::Untrusted{}, bases, &h[0]);
+  uint64_t rejected_at = UINT64_MAX;  // ... and a copy with one corrupted point is refused with that point's index
+  {
+    auto broken = bases;
+    broken[bases.size() / 2].y.limbs[0] ^= 1;
+    try {
+      CommitmentKey<BN254> nope(CommitmentKey<BN254>::Untrusted{}, broken, &h[0]);
+    } catch (const CommitmentKey<BN254>::InvalidCommitmentKey& e) {
+      rejected_at = e.index;
+    }
+  }
   R1CSShapeDev S{*A, *B, *C, field, num_cons, num_vars, num_io};
   size_t bad = validate_key<BN254>(bases);
   // the fresh witness arrives through the stream in three ragged chunks
@@ -62,6 +73,7 @@ static int fold_mode(const char* path) {
   auto dump = [&](const void* p, uint64_t n, size_t sz) { o.write((char*)&n, 8); o.write((const char*)p, n * sz); };
   uint64_t b64 = bad;
   dump(&b64, 1, 8);
+  dump(&rejected_at, 1, 8);
   dump(&comm_W2, 1, 96);
   dump(&tc.second, 1, 96);
   dump(T.data(), T.size(), 32);

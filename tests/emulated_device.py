@@ -365,6 +365,30 @@ class EmulatedDevice:
         self.next_handle += 1
         return 0
 
+    def _first_invalid(self, curve_id, raw: bytes):
+        """smallest index of a point with a non-canonical coordinate or off the curve (k_on_curve's contract)"""
+        c = CURVES[curve_id]
+        for i in range(len(raw) // 64):
+            x, y = (int.from_bytes(raw[64 * i + k:64 * i + k + 32], "little") for k in (0, 32))
+            if x >= c.p or y >= c.p or not c.on_curve(c.affine_from_bytes(raw[64 * i:64 * i + 64])):
+                return i
+        return None
+
+    def b200_ck_validate(self, curve_id, bases, n, first_bad):
+        bad = self._first_invalid(curve_id, _rd(bases, 64 * n))
+        first_bad._obj.value = (1 << 64) - 1 if bad is None else bad
+        return 0
+
+    def b200_ck_register_checked(self, curve_id, bases, n, h, window_bits, out_handle, first_bad):
+        raw = _rd(bases, 64 * n) + (_rd(h, 64) if _addr(h) else b"")
+        bad = self._first_invalid(curve_id, raw)
+        first_bad._obj.value = (1 << 64) - 1 if bad is None else bad
+        out_handle._obj.value = 0
+        if bad is not None:
+            self.err = f"key point {bad} has a non-canonical coordinate or is not on the curve".encode()
+            return 7
+        return self.b200_ck_register(curve_id, bases, n, h, window_bits, out_handle)
+
     def b200_ck_setup_synthetic(self, curve_id, gen, k0, n, with_h, window_bits, out_handle):
         bases = co.gen_bases(curve_id, n + (1 if with_h else 0), int(k0))  # P_i = (k0 + i) G
         self.keys[self.next_handle] = (curve_id, bases[:64 * n], bases[64 * n:] if with_h else None)
@@ -387,6 +411,19 @@ class EmulatedDevice:
             sc, bs = sc + _rd(blind, 32), bs + h
         _wr(out, self._jacobian(curve_id, co.msm(curve_id, sc, bs)))
         return 0
+
+    def b200_msm_dev(self, handle, off, scalars, n, out, stream):
+        curve_id, bases, _ = self.keys[handle]
+        if off + n > len(bases) // 64:
+            return 5
+        _wr(out, self._jacobian(curve_id, co.msm(curve_id, _rd(scalars, 32 * n), bases[64 * off:64 * (off + n)])))
+        return 0
+
+    def b200_msm(self, handle, off, scalars, n, out):
+        return self.b200_msm_dev(handle, off, scalars, n, out, None)
+
+    def b200_commit(self, handle, scalars, n, blind, out):  # host pointers: the same thing here
+        return self.b200_commit_dev(handle, scalars, n, blind, out, None)
 
     # ---- streamed witness hand-off --------------------------------------------------------------
     def b200_witness_begin(self, ck, n, out_handle):

@@ -314,11 +314,11 @@ extern "C" int hc_sc_round(int fid, int kind, void* state144, const void* res, c
   return 0;
 }
 
-// ---- key validation (curve.cuh affine_on_curve) ----
+// ---- key validation (curve.cuh affine_valid_raw: canonical coordinates and on the curve; what k_on_curve runs) ----
 template <class F>
 static void on_curve_t(int b_small, const affine_t* pts, size_t n, unsigned char* ok) {
   fe_t b = fe_from_small_int<F>(b_small);
-  for (size_t i = 0; i < n; i++) ok[i] = affine_on_curve<F>(pts[i], b) ? 1 : 0;
+  for (size_t i = 0; i < n; i++) ok[i] = affine_valid_raw<F>(pts[i], b) ? 1 : 0;
 }
 extern "C" int hc_on_curve(int fid, int b_small, const void* pts, size_t n, void* ok) {
   switch (fid) {

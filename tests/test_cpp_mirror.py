@@ -149,8 +149,11 @@ def check_fold(exe, oracle, tmp_path):
         b = raw[off + 8:off + 8 + n * sz]
         off += 8 + n * sz
         return b
-    bad, comm_W2, comm_T, T, Wf, Ef = take(8), take(96), take(96), take(32), take(32), take(32)
+    bad, rejected_at = take(8), take(8)
+    comm_W2, comm_T, T, Wf, Ef = take(96), take(96), take(32), take(32), take(32)
     assert struct.unpack("<Q", bad)[0] == (1 << 64) - 1  # every base is on the curve
+    # the untrusted-key constructor refused the copy whose middle point was corrupted, naming that point
+    assert struct.unpack("<Q", rejected_at)[0] == n_key // 2
     h = bases[64 * n_key:]
     aff = lambda jac: c.affine_from_bytes(oracle.jacobian_to_affine(cid, jac))
     assert aff(comm_W2) == c.affine_from_bytes(oracle.msm(cid, pack(W2 + [r_W]), bases[:64 * num_vars] + h))

@@ -136,8 +136,9 @@ def test_quad_cooperative_ops(hc, cid):
 
 @pytest.mark.parametrize("cid", [0, 1, 2, 3])
 def test_on_curve_check(hc, cid):
-    """affine_on_curve (the device side of CommitmentKey::new's validation, hyperkzg.rs:113-119):
-    curve points and the identity encoding pass, any corrupted coordinate fails."""
+    """affine_valid_raw (the device side of CommitmentKey::new's validation, hyperkzg.rs:113-119, and of
+    read_points, ptau.rs:372-392): curve points and the identity encoding pass, any corrupted coordinate fails,
+    and so does a coordinate that is congruent to a valid one but not canonical (x + p: read_raw refuses it)."""
     c = CURVES[cid]
     b_small = {0: 3, 1: -17, 2: 5, 3: 5}[cid]
     assert c.b % c.p == b_small % c.p
@@ -148,13 +149,22 @@ def test_on_curve_check(hc, cid):
         bad.append(c.affine_bytes((P[0], (P[1] + 1) % c.p)))
         bad.append(c.affine_bytes(((P[0] + 1) % c.p, P[1])))
     bad.append(c.affine_bytes((0, 1)))
+    n_plain_bad = len(bad)
+    for k, P in enumerate(pts[6:10]):
+        raw = c.affine_bytes(P)
+        x, y = int.from_bytes(raw[:32], "little"), int.from_bytes(raw[32:], "little")
+        if k & 1:
+            bad.append((x + c.p).to_bytes(32, "little") + raw[32:])
+        else:
+            bad.append(raw[:32] + (y + c.p).to_bytes(32, "little"))
     data = b"".join(good + bad)
     ok = ctypes.create_string_buffer(len(good) + len(bad))
     assert hc.hc_on_curve(c.base_field, b_small, _buf(data), ctypes.c_size_t(len(good) + len(bad)), ok) == 0
     flags = list(ok.raw)
     assert flags[:len(good)] == [1] * len(good)
-    exp_bad = [1 if c.on_curve(c.affine_from_bytes(x)) else 0 for x in bad]
-    assert flags[len(good):] == exp_bad and sum(exp_bad) == 0
+    exp_bad = [1 if c.on_curve(c.affine_from_bytes(x)) else 0 for x in bad[:n_plain_bad]]
+    assert flags[len(good):len(good) + n_plain_bad] == exp_bad and sum(exp_bad) == 0
+    assert flags[len(good) + n_plain_bad:] == [0] * 4  # non-canonical
 
 
 @pytest.mark.parametrize("fid", [0, 1, 2, 3])

@@ -351,3 +351,22 @@ def test_cpp_mirror_sumcheck_loops(oracle, tmp_path):
     import test_cpp_mirror as tcm
     tcm.build()
     tcm.check_sumcheck(tcm.EXE, oracle, tmp_path)
+
+
+def test_ptau_load_setup_on_device(b200, oracle, tmp_path):
+    """PTAU file -> device-resident key (src/provider/ptau.rs, hyperkzg.rs:657-689): the reference's four read_ptau
+    tests, header / truncation / non-canonical errors and the save_setup -> load_setup -> commit round trip, with
+    the G1 section validated by k_on_curve in HBM (b200_ck_register_checked).  CPU twin: tests/test_ptau_cpu.py."""
+    import ptau_parity
+    from nova_b200 import ptau
+    ptau_parity.run_reference_cases(ptau)
+    ptau_parity.run_format_errors(ptau)
+    ptau_parity.run_setup_round_trip(ptau, oracle, tmp_path)
+
+
+def test_checked_registration_names_the_first_bad_point(b200, oracle):
+    """b200_ck_register_checked on 2^14 points: clean key registers and commits; with two points corrupted the call
+    fails with B200_E_POINT and first_bad = the smaller index; a bad blinding generator reports index n.
+    CPU twin: tests/test_ptau_cpu.py."""
+    import ptau_parity
+    ptau_parity.run_checked_registration(oracle, 1 << 14, 9000, 12000)
