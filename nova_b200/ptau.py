@@ -349,6 +349,88 @@ def load_setup(reader, h: bytes | None, n: int, window_bits: int = 0) -> Commitm
     return ck
 
 
+def load_setup_sharded(reader, h: bytes | None, n: int, rank: int, world: int, group=None, window_bits: int = 0):
+    """`load_setup` for one process per GPU (GPU g owns ck[g n/G .. (g+1) n/G) for the life of
+    the key): every rank seeks to ITS index range of the TauG1 section and reads, uploads and validates only
+    that slice -- file and PCIe traffic are divided by `world`, no rank ever holds the whole key.  The verdict
+    is made global with one all-gather of (first bad global index, error class) so that every rank raises the
+    same error the unsharded loader would (the smallest offending index decides, as in read_points' loop).
+    Rank 0's slice carries the blinding generator h (the `r * h` term is added once).
+    -> (resident key over the slice with `.tau_H`, lo, hi)"""
+    from .sharding import all_gather_bytes, shard_range
+    curve = Curve.BN254_G1
+    num = _next_power_of_two(n)
+    meta = read_meta_data(reader)
+    reader.seek(meta["pos_header"])
+    read_header(reader, num, 2, fields.MODULUS[curve.base_field])
+    lo, hi = shard_range(num, rank, world)
+    if hi == lo:
+        raise ValueError(f"rank {rank} of {world} owns no point of a {num}-point key")
+    reader.seek(meta["pos_tau_g1"] + 64 * lo)
+    g1 = _read_exact(reader, 64 * (hi - lo))
+    reader.seek(meta["pos_tau_g2"])
+    g2 = _read_exact(reader, 256)
+    my_h = h if rank == 0 else None
+    handle, bad = c_u64(0), c_size_t(0)
+    rc = lib().b200_ck_register_checked(int(curve), _cbuf(g1), hi - lo, _cbuf(my_h) if my_h else None, window_bits,
+                                        ctypes.byref(handle), ctypes.byref(bad))
+    NONE = (1 << 64) - 1
+    verdict, kind = NONE, 0  # kind: 1 = PointNotOnCurve, 2 = non-canonical (io error), 3 = the blinding generator
+    if rc == B200_E_POINT:
+        if my_h and bad.value == hi - lo:
+            verdict, kind = num, 3  # after every G1 point, as in the unsharded order
+        else:
+            verdict = lo + bad.value
+            kind = 2 if isinstance(_classify_bad_g1(curve, g1, bad.value), IoError) else 1
+    else:
+        check(rc)
+    votes = all_gather_bytes(verdict.to_bytes(8, "little") + bytes([kind]), group)
+    first, first_kind = min((int.from_bytes(v[:8], "little"), v[8]) for v in votes)
+    ck = None
+    if rc == 0:
+        ck = CommitmentKey.__new__(CommitmentKey)
+        ck.curve, ck.n, ck.handle, ck.has_h = curve, hi - lo, handle.value, my_h is not None
+        ck.bases, ck.h = g1, my_h
+    try:
+        if first != NONE:
+            if first_kind == 3:
+                raise PointNotOnCurve("the blinding generator h is not a valid point")
+            if first_kind == 2:
+                raise IoError(f"non-canonical coordinate in G1 point {first}")
+            raise PointNotOnCurve(f"Point is not on the curve (G1 point {first})")
+        _check_g2(g2, 2)  # the same two points on every rank: the same verdict everywhere
+    except PtauFileError:
+        if ck is not None:
+            ck.release()
+        raise
+    ck.tau_H = g2[128:256]
+    return ck, lo, hi
+
+
+def sharded_commit(ck_slice: CommitmentKey, lo: int, hi: int, v_local: bytes, r: bytes | None, rank: int,
+                   group=None):
+    """`CE::commit(ck, v, r)` over a key loaded with `load_setup_sharded`: `v_local` = this rank's v[lo .. hi)
+    clipped to len(v); every rank reduces its pairs to one point (rank 0 also adds r * h in the same pass), the
+    96-byte partials are all-gathered and added.  -> affine (x, y) or None, on every rank."""
+    import torch
+
+    from .provider import _jac_to_affine
+    from .sharding import all_gather_partials
+    from .spartan import DeviceVec
+    m = len(v_local) // 32
+    assert m <= hi - lo
+    out = ctypes.create_string_buffer(96)
+    check(lib().b200_commit(ck_slice.handle, _cbuf(v_local), m, _cbuf(r) if (r and rank == 0) else None, out))
+    parts = all_gather_partials(torch.frombuffer(bytearray(out.raw), dtype=torch.uint8), group)
+    world = parts.numel() // 96
+    d_parts, d_total = DeviceVec.from_bytes(parts.numpy().tobytes()), DeviceVec(96)
+    check(lib().b200_jacobian_sum_dev(int(ck_slice.curve), d_parts.ptr, world, d_total.ptr, None))
+    total = d_total.to_bytes()  # (the download synchronises; both buffers are still alive here)
+    d_parts.free()
+    d_total.free()
+    return _jac_to_affine(ck_slice.curve, total)
+
+
 def save_setup(ck: CommitmentKey, writer) -> None:
     """`save_setup` (hyperkzg.rs:677-689): g2 = [tau_H, tau_H], power = log2(next_power_of_two(len)) + 1"""
     if ck.bases is None:

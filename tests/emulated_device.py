@@ -422,6 +422,15 @@ class EmulatedDevice:
     def b200_msm(self, handle, off, scalars, n, out):
         return self.b200_msm_dev(handle, off, scalars, n, out, None)
 
+    def b200_jacobian_sum_dev(self, curve_id, pts, k, out, stream):
+        c = CURVES[curve_id]
+        acc = None
+        raw = _rd(pts, 96 * k)
+        for j in range(k):
+            acc = c.add(acc, c.jacobian_from_bytes(raw[96 * j:96 * j + 96]))
+        _wr(out, self._jacobian(curve_id, c.affine_bytes(acc)))
+        return 0
+
     def b200_commit(self, handle, scalars, n, blind, out):  # host pointers: the same thing here
         return self.b200_commit_dev(handle, scalars, n, blind, out, None)
 

@@ -370,3 +370,10 @@ def test_checked_registration_names_the_first_bad_point(b200, oracle):
     CPU twin: tests/test_ptau_cpu.py."""
     import ptau_parity
     ptau_parity.run_checked_registration(oracle, 1 << 14, 9000, 12000)
+
+
+def test_sharded_ptau_loading_two_ranks_on_device(tmp_path):
+    """load_setup_sharded + sharded_commit with two gloo ranks driving the same GPU: slice keys validated in HBM,
+    the combined commitment, the error agreement.  CPU twin: tests/test_ptau_sharded.py."""
+    import test_ptau_sharded
+    test_ptau_sharded.run_world(2, "gpu", tmp_path)
