@@ -2,7 +2,8 @@
 
 Host-side mirror of `src/provider/ptau.rs` (`read_ptau` :402-438, `write_ptau` :217-269, `read_meta_data`
 :271-327, `read_header` :329-370, `check_sanity_of_ptau_file` :441-455) and of
-`CommitmentEngine::{load_setup, save_setup}` for HyperKZG (hyperkzg.rs:657-689), with the reference's error
+`CommitmentEngine::{load_setup, save_setup}` for HyperKZG (hyperkzg.rs:657-689) and Pedersen
+(pedersen.rs:317-340, 383-393), with the reference's error
 type (`PtauFileError`, ptau.rs:100-151) as an exception hierarchy.
 
 What moves to the device: the G1 section.  `write_raw` / `read_raw` (ptau.rs:197-208, 372-392) are the in-memory
@@ -429,6 +430,61 @@ def sharded_commit(ck_slice: CommitmentKey, lo: int, hi: int, v_local: bytes, r:
     d_parts.free()
     d_total.free()
     return _jac_to_affine(ck_slice.curve, total)
+
+
+# ---------------------------------------------------------------------------------------------
+# Pedersen key files (provider/pedersen.rs:27-28, 317-340, 383-393): "PEDERSEN_KEY", then h, then the bases,
+# all as raw points read with read_points
+# ---------------------------------------------------------------------------------------------
+KEY_FILE_HEAD = b"PEDERSEN_KEY"
+_CURVE_B = {0: 3, 1: -17, 2: 5, 3: 5}  # bn256_grumpkin.rs:35-41,80-86; pasta.rs:33-47
+
+
+def _host_point_error(curve: Curve, pt: bytes, what: str):
+    """read_points' two checks for ONE point on the host (the blinding generator, which the file stores first)"""
+    fid = curve.base_field
+    p = fields.MODULUS[fid]
+    if any(int.from_bytes(pt[k:k + 32], "little") >= p for k in (0, 32)):
+        return IoError(f"non-canonical coordinate in {what}")
+    x, y = fields.from_mont_bytes(fid, pt[:32]), fields.from_mont_bytes(fid, pt[32:])
+    if (x, y) != (0, 0) and (y * y - x * x * x - _CURVE_B[int(curve)]) % p != 0:
+        return PointNotOnCurve(f"Point is not on the curve ({what})")
+    return None
+
+
+def pedersen_load_setup(reader, n: int, curve: Curve, window_bits: int = 0) -> CommitmentKey:
+    """`CommitmentEngine::load_setup` of Pedersen (pedersen.rs:317-340): head, then num + 1 points with
+    num = n.next_power_of_two(); the FIRST point is h, the rest is ck.  The bases go to HBM once and are
+    validated there."""
+    curve = Curve(curve)
+    num = _next_power_of_two(n)
+    if _read_exact(reader, 12) != KEY_FILE_HEAD:
+        raise InvalidHead("Invalid magic string")
+    pts = _read_exact(reader, 64 * (num + 1))
+    h, bases = pts[:64], pts[64:]
+    err = _host_point_error(curve, h, "h, point 0 of the file")
+    if err:
+        raise err
+    handle, bad = c_u64(0), c_size_t(0)
+    rc = lib().b200_ck_register_checked(int(curve), _cbuf(bases), num, _cbuf(h), window_bits,
+                                        ctypes.byref(handle), ctypes.byref(bad))
+    if rc == B200_E_POINT:
+        e = _classify_bad_g1(curve, bases, min(bad.value, num - 1))
+        raise type(e)(f"{e} [point {bad.value + 1} of the file]")
+    check(rc)
+    ck = CommitmentKey.__new__(CommitmentKey)
+    ck.curve, ck.n, ck.handle, ck.has_h = curve, num, handle.value, True
+    ck.bases, ck.h = bases, h
+    return ck
+
+
+def pedersen_save_setup(ck: CommitmentKey, writer) -> None:
+    """pedersen.rs:383-393"""
+    if ck.bases is None or ck.h is None:
+        raise ValueError("this key has no host copy of its bases / blinding generator")
+    writer.write(KEY_FILE_HEAD)
+    writer.write(ck.h)
+    writer.write(ck.bases)
 
 
 def save_setup(ck: CommitmentKey, writer) -> None:

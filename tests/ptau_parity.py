@@ -215,3 +215,49 @@ def run_checked_registration(oracle, n, bad_lo, bad_hi):
     assert b"point" in L.b200_last_error()
     rc, handle, bad = reg(bases[:64 * n], bases[64 * n:64 * n + 32] + bytes(32))
     assert (rc, handle, bad) == (7, 0, n)
+
+
+def run_pedersen_key_file(ptau, oracle, cid):
+    """pedersen.rs:317-340, 383-393: save -> load (h first), commit through the loaded key, and the file errors"""
+    from nova_b200 import provider
+    c = CURVES[cid]
+    p = c.q
+    n = 24  # -> 32 bases + h
+    pts = oracle.gen_bases(cid, 33, 4242)
+    bases, h = pts[:64 * 32], pts[64 * 32:]
+    src = provider.CommitmentKey(provider.Curve(cid), bases, h)
+    buf = io.BytesIO()
+    ptau.pedersen_save_setup(src, buf)
+    src.release()
+    data = buf.getvalue()
+    assert data == b"PEDERSEN_KEY" + h + bases
+    ck = ptau.pedersen_load_setup(io.BytesIO(data), n, provider.Curve(cid))
+    assert (ck.n, ck.h, ck.bases) == (32, h, bases)
+    rng = SplitMix64(31 + cid)
+    v = [rng.field(p) for _ in range(n)]
+    r = rng.field(p)
+    got = provider.CommitmentEngine(provider.Curve(cid)).commit(ck, b"".join(mont_bytes(p, x) for x in v), mont_bytes(p, r))
+    assert got == c.add(c.msm_naive(v, [c.affine_from_bytes(bases[64 * i:64 * i + 64]) for i in range(n)]),
+                        c.mul(r, c.affine_from_bytes(h)))
+    ck.release()
+    with pytest.raises(ptau.InvalidHead):
+        ptau.pedersen_load_setup(io.BytesIO(b"PEDERSEN_KEZ" + data[12:]), n, provider.Curve(cid))
+    with pytest.raises(ptau.IoError):
+        ptau.pedersen_load_setup(io.BytesIO(data[:-1]), n, provider.Curve(cid))
+    with pytest.raises(ptau.IoError):  # a key file for fewer generators than asked for
+        ptau.pedersen_load_setup(io.BytesIO(data), 33, provider.Curve(cid))
+    bad = bytearray(data)
+    bad[12 + 64 * 20 + 5] ^= 1  # point 20 of the file = base 19
+    with pytest.raises(ptau.PointNotOnCurve, match="point 20 of the file"):
+        ptau.pedersen_load_setup(io.BytesIO(bytes(bad)), n, provider.Curve(cid))
+    bad = bytearray(data)
+    bad[12 + 40] ^= 1  # h
+    with pytest.raises(ptau.PointNotOnCurve, match="point 0"):
+        ptau.pedersen_load_setup(io.BytesIO(bytes(bad)), n, provider.Curve(cid))
+    # h non-canonical AND a base off the curve: the reference meets h first -> io error
+    bad = bytearray(data)
+    hx = int.from_bytes(h[:32], "little") + c.p
+    bad[12:44] = hx.to_bytes(32, "little")
+    bad[12 + 64 * 7 + 1] ^= 1
+    with pytest.raises(ptau.IoError):
+        ptau.pedersen_load_setup(io.BytesIO(bytes(bad)), n, provider.Curve(cid))

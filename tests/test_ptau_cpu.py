@@ -49,3 +49,8 @@ def test_save_load_setup_round_trip(ptau, oracle, tmp_path):
 
 def test_checked_registration(ptau, oracle):
     ptau_parity.run_checked_registration(oracle, 1 << 9, 300, 450)
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3])
+def test_pedersen_key_file(ptau, oracle, cid):
+    ptau_parity.run_pedersen_key_file(ptau, oracle, cid)

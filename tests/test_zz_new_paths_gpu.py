@@ -377,3 +377,12 @@ def test_sharded_ptau_loading_two_ranks_on_device(tmp_path):
     the combined commitment, the error agreement.  CPU twin: tests/test_ptau_sharded.py."""
     import test_ptau_sharded
     test_ptau_sharded.run_world(2, "gpu", tmp_path)
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3])
+def test_pedersen_key_file_on_device(b200, oracle, cid):
+    """Pedersen key file (pedersen.rs:317-340, 383-393) -> resident key on Grumpkin / Pallas / Vesta, validated in
+    HBM; CPU twin: tests/test_ptau_cpu.py."""
+    import ptau_parity
+    from nova_b200 import ptau
+    ptau_parity.run_pedersen_key_file(ptau, oracle, cid)
