@@ -214,3 +214,218 @@ def sharded_poly_div(engine, p: int, f_local: bytes, lo: int, hi: int, n: int, u
         return b""
     q = engine.poly_div(f_local + _mont(p, carry), um)  # (hi - lo) entries: h[lo .. hi)
     return q[:32 * (hi - lo - 1)] if hi == n else q
+
+
+# ---------------------------------------------------------------------------------------------
+# HyperKZG EvaluationEngine::prove over `world` GPUs (SURVEY.md §8d config C4, §8e rows "HyperKZG fold",
+# "Horner evals / div-by-monomial", "MSM")
+# ---------------------------------------------------------------------------------------------
+class HostStagedComm:
+    """Collectives on device buffers staged through the host (works with any torch.distributed backend that
+    takes CPU tensors, i.e. gloo): D2H of the local piece, all-gather, H2D of the result.  The four small
+    exchanges of the prover move a few hundred bytes; only the fold-chain gather is bulk data."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def gather_bytes(self, b: bytes) -> list:
+        return all_gather_bytes(b, self.group)
+
+    def gather_dev(self, vec, nbytes: int):
+        """every rank's `nbytes` of `vec`, concatenated in rank order, as a new device vector"""
+        from .spartan import DeviceVec
+        return DeviceVec.from_bytes(b"".join(all_gather_bytes(vec.to_bytes(nbytes), self.group)))
+
+
+class _CudaView:
+    """zero-copy view of a raw device allocation for torch (CUDA array interface, version 2)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class NcclComm:
+    """The same two collectives on NCCL, device to device: the library's allocations are viewed as torch tensors
+    (no copy) and all-gathered over NVLink; the small host-side exchanges go through a CUDA staging tensor.
+    The library works on its own stream, torch/NCCL on torch's: both sides are synchronised around every
+    collective (six per proof).  STATUS: written for the multi-GPU box, not yet run (tests/test_zz_new_paths_gpu.py
+    skips it on a single-GPU box); the gloo path above is the tested one."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def gather_bytes(self, b: bytes) -> list:
+        t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        out = torch.empty(len(b) * self.world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        raw = out.cpu().numpy().tobytes()
+        return [raw[len(b) * k:len(b) * (k + 1)] for k in range(self.world)]
+
+    def gather_dev(self, vec, nbytes: int):
+        from .native import check, lib
+        from .spartan import DeviceVec
+        out = DeviceVec(nbytes * self.world)
+        check(lib().b200_sync())  # the producer kernels of `vec` ran on the library's stream
+        src = torch.as_tensor(_CudaView(vec.ptr.value, nbytes), device="cuda")
+        dst = torch.as_tensor(_CudaView(out.ptr.value, nbytes * self.world), device="cuda")
+        dist.all_gather_into_tensor(dst, src, group=self.group)
+        torch.cuda.current_stream().synchronize()
+        return out
+
+
+def sharded_hyperkzg_prove(curve, ck, P_local, x: list, r, q, comm, on_w=None):
+    """`EvaluationEngine::prove` of HyperKZG (hyperkzg.rs:926-1116; the single-GPU mirror is
+    spartan.hyperkzg_prove_resident) with the polynomial split by INDEX RANGE over comm.world ranks (a power of
+    two): rank g holds P[g n/G .. (g+1) n/G) in `P_local` (a DeviceVec).  `ck` is the FULL key, resident on
+    every GPU (level i of the fold chain lives on indices [0, n/2^i), so the slices a rank commits move towards
+    the front of the key; 3.5 GB of tables at 2^22 against 180 GB of HBM).
+
+      fold        local: the pairs (2j, 2j+1) are adjacent, so a slice of level i folds into the same rank's
+                  slice of level i+1 -- until a level has one element per rank, which is all-gathered and the
+                  short tail (G elements) continues replicated
+      com_i       per-rank partial MSM over ck[lo_i .. hi_i) (b200_msm_dev with a base offset), ONE all-gather of
+                  the (levels x 96 B) partials, local sum
+      v_i(u_t)    local Horner on the slice, scaled by u_t^lo_i, one all-gather of 3 values per level
+      B           = sum_k q^k P_k zero-extended, by index range of P_0: the levels k >= 1 (n - G elements in all)
+                  are all-gathered once -- the only bulk exchange -- and every rank combines its own range
+      h_t, w_t    division by (X - u_t) on index ranges with a carry from the ranks to the right (one all-gather
+                  of 3 values), partial MSMs over ck[lo_0 .. hi_0), one all-gather of 3 partials
+
+    `r`, `q`, `on_w` as in hyperkzg_prove_resident (values or transcript callables; the transcript runs
+    replicated on every rank).  Returns (com, v, w) identical on every rank and to the unsharded prover."""
+    import ctypes
+
+    from . import fields
+    from .native import c_size_t, check, lib
+    from .provider import Curve, _jac_to_affine
+    from .spartan import DeviceVec
+    L = lib()
+    curve = Curve(curve)
+    fid = curve.scalar_field
+    p = fields.MODULUS[fid]
+    G, g = comm.world, comm.rank
+    ell = len(x)
+    n = 1 << ell
+    assert G & (G - 1) == 0 and 2 * G <= n, "world must be a power of two with at least two elements per rank"
+    nloc = n // G
+    base_ptr = lambda v, k: ctypes.c_void_p(v.ptr.value + 32 * k)
+
+    def affine_sum(parts: list):
+        """sum of Jacobian points given as 96-byte strings -> affine"""
+        d, out = DeviceVec.from_bytes(b"".join(parts)), DeviceVec(96)
+        check(L.b200_jacobian_sum_dev(int(curve), d.ptr, len(parts), out.ptr, None))
+        raw = out.to_bytes()
+        d.free()
+        out.free()
+        return _jac_to_affine(curve, raw)
+
+    # ---- Phase 1: the fold chain (hyperkzg.rs:1083-1095) -------------------------------------------
+    # level i: (vector, local length, sharded?).  Sharded levels hold indices [g len_i/G, (g+1) len_i/G).
+    levels = [(P_local, nloc, True)]
+    for i in range(ell - 1):
+        vec, ln, sharded = levels[-1]
+        if sharded and ln == 1:  # one element per rank: replicate the tail
+            vec, ln, sharded = comm.gather_dev(vec, 32), G, False
+            levels[-1] = (vec, ln, sharded)
+        xi = DeviceVec.from_bytes(fields.to_mont_bytes(fid, x[ell - i - 1]))
+        nxt = DeviceVec(16 * ln)
+        check(L.b200_kzg_fold_dev(fid, vec.ptr, ln, xi.ptr, nxt.ptr, None))
+        check(L.b200_sync())  # xi is released on return
+        levels.append((nxt, ln // 2, sharded))
+    full_len = lambda i: n >> i
+    lo_of = lambda i: g * (full_len(i) // G)
+
+    # ---- com_i = commit(P_i), i = 1 .. ell-1 (:1099-1100) ------------------------------------------
+    parts = DeviceVec(96 * max(ell - 1, 1))
+    for i in range(1, ell):
+        vec, ln, sharded = levels[i]
+        if sharded:
+            check(L.b200_msm_dev(ck.handle, lo_of(i), vec.ptr, ln, ctypes.c_void_p(parts.ptr.value + 96 * (i - 1)), None))
+        else:  # replicated tail: every rank commits the whole (short) vector itself
+            check(L.b200_msm_dev(ck.handle, 0, vec.ptr, ln, ctypes.c_void_p(parts.ptr.value + 96 * (i - 1)), None))
+    mine = parts.to_bytes(96 * (ell - 1))
+    allp = comm.gather_bytes(mine) if ell > 1 else [b""]
+    com = []
+    for i in range(1, ell):
+        sl = slice(96 * (i - 1), 96 * i)
+        if levels[i][2]:
+            com.append(affine_sum([a[sl] for a in allp]))
+        else:
+            com.append(_jac_to_affine(curve, mine[sl]))
+    if callable(r):
+        r = r(com)
+    u = [r % p, (-r) % p, r * r % p]  # :1105-1106
+    us = DeviceVec.from_bytes(fields.pack(fid, u))
+
+    # ---- v[i][t] = P_i(u_t) (:1048-1056) ------------------------------------------------------------
+    ev = DeviceVec(96 * ell)
+    for i in range(ell):
+        vec, ln, _ = levels[i]
+        check(L.b200_poly_eval_dev(fid, vec.ptr, ln, us.ptr, 3, ctypes.c_void_p(ev.ptr.value + 96 * i), None))
+    loc = [fields.unpack(fid, ev.to_bytes(96 * ell)[96 * i:96 * i + 96]) for i in range(ell)]
+    scaled = b"".join(int(loc[i][t] * pow(u[t], lo_of(i), p) % p).to_bytes(32, "little")
+                      for i in range(ell) for t in range(3))
+    allv = comm.gather_bytes(scaled)
+    v = []
+    for i in range(ell):
+        if levels[i][2]:
+            v.append([sum(int.from_bytes(a[32 * (3 * i + t):32 * (3 * i + t) + 32], "little") for a in allv) % p
+                      for t in range(3)])
+        else:
+            v.append(list(loc[i]))
+    if callable(q):
+        q = q(v)
+
+    # ---- B = sum_k q^k P_k on this rank's index range [lo_0, hi_0) (:1028-1040) ----------------------
+    lo0, hi0 = g * nloc, (g + 1) * nloc
+    srcs, coef = [base_ptr(P_local, 0)], [1]
+    lens = [nloc]
+    gathered = []
+    for k in range(1, ell):
+        vec, ln, sharded = levels[k]
+        if full_len(k) <= lo0:
+            if sharded:  # still takes part in the collective
+                gathered.append(comm.gather_dev(vec, 32 * ln))
+            continue
+        whole = comm.gather_dev(vec, 32 * ln) if sharded else vec
+        if sharded:
+            gathered.append(whole)
+        srcs.append(base_ptr(whole, lo0))
+        lens.append(min(hi0, full_len(k)) - lo0)
+        coef.append(pow(q, k, p))
+    assert len(srcs) <= 32, "rlc of more than 32 polynomials"
+    qd = DeviceVec.from_bytes(fields.pack(fid, coef))
+    Bloc = DeviceVec(32 * (nloc + 1))  # one spare slot: the carry coefficient of the division below
+    ptrs = (ctypes.c_void_p * len(srcs))(*[s_.value for s_ in srcs])
+    lns = (c_size_t * len(srcs))(*lens)
+    check(L.b200_rlc_dev(fid, ptrs, lns, len(srcs), qd.ptr, nloc, Bloc.ptr, None))
+
+    # ---- h_t = B / (X - u_t), w_t = commit(h_t) (:1062-1065) ----------------------------------------
+    bev = DeviceVec(96)
+    check(L.b200_poly_eval_dev(fid, Bloc.ptr, nloc, us.ptr, 3, bev.ptr, None))
+    mine_v = fields.unpack(fid, bev.to_bytes(96))
+    allb = comm.gather_bytes(b"".join(int(e).to_bytes(32, "little") for e in mine_v))
+    wparts = DeviceVec(96 * 3)
+    cnt = nloc - 1 if g == G - 1 else nloc  # h has n - 1 coefficients: the last rank owns one less
+    keep = []
+    for t in range(3):
+        carry = 0  # sum over ranks k > g of V_k(u_t) u_t^(lo_k - hi_0)
+        for k in range(g + 1, G):
+            vk = int.from_bytes(allb[k][32 * t:32 * t + 32], "little")
+            carry = (carry + vk * pow(u[t], (k - g - 1) * nloc, p)) % p
+        cd = DeviceVec.from_bytes(fields.to_mont_bytes(fid, carry))
+        check(L.b200_memcpy_d2d(base_ptr(Bloc, nloc), cd.ptr, 32, None))
+        ud = DeviceVec.from_bytes(fields.to_mont_bytes(fid, u[t]))
+        h = DeviceVec(32 * nloc)
+        check(L.b200_poly_div_dev(fid, Bloc.ptr, nloc + 1, ud.ptr, h.ptr, None))  # -> h[lo_0 .. hi_0)
+        check(L.b200_msm_dev(ck.handle, lo0, h.ptr, cnt, ctypes.c_void_p(wparts.ptr.value + 96 * t), None))
+        keep.append((cd, ud, h))
+    allw = comm.gather_bytes(wparts.to_bytes(96 * 3))  # (the download synchronises: `keep` may go now)
+    w = [affine_sum([a[96 * t:96 * t + 96] for a in allw]) for t in range(3)]
+    if on_w is not None:
+        on_w(w)
+    return com, v, w

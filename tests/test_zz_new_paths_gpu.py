@@ -386,3 +386,19 @@ def test_pedersen_key_file_on_device(b200, oracle, cid):
     import ptau_parity
     from nova_b200 import ptau
     ptau_parity.run_pedersen_key_file(ptau, oracle, cid)
+
+
+def test_sharded_hyperkzg_two_ranks_on_device(tmp_path):
+    """sharded_hyperkzg_prove with two gloo ranks driving the same GPU (host-staged collectives): every prover
+    message and the transcript equal to the unsharded oracle's.  CPU twin: tests/test_hyperkzg_sharded.py."""
+    import test_hyperkzg_sharded
+    test_hyperkzg_sharded.run_world(2, "gpu", tmp_path)
+
+
+def test_sharded_hyperkzg_nccl(tmp_path):
+    """the same over NCCL with one GPU per rank (NcclComm); needs at least two GPUs"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import test_hyperkzg_sharded
+    test_hyperkzg_sharded.run_world(2, "nccl", tmp_path)
