@@ -43,4 +43,12 @@ run e2e_chunks4      timeout 300  env NOVA_B200_H2D_CHUNKS=4 python tools/e2e_co
 run e2e_chunks8      timeout 300  env NOVA_B200_H2D_CHUNKS=8 python tools/e2e_commit.py --log-n 20
 run e2e_chunks4_par  timeout 900  env NOVA_B200_H2D_CHUNKS=4 python -m pytest tests/test_msm_gpu.py -m gpu -x -q -p no:cacheprovider
 
+# 5. multi-GPU box only (gpurun --gpus 2): HyperKZG over two GPUs, NCCL and host-staged collectives
+NG=$(python -c "import torch; print(torch.cuda.device_count())" 2>/dev/null || echo 1)
+if [ "$NG" -ge 2 ]; then
+  run hkzg_1gpu      timeout 600  python tools/hyperkzg_sharded_replay.py --log2n 22
+  run hkzg_2gpu_nccl timeout 600  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/hyperkzg_sharded_replay.py --log2n 22 --comm nccl
+  run hkzg_2gpu_host timeout 600  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 tools/hyperkzg_sharded_replay.py --log2n 22 --comm host
+fi
+
 grep -h "passed\|failed\|error" "$OUT"/zz_new_paths.log "$OUT"/gpu_suite.log "$OUT"/y3_parity.log 2>/dev/null | tail -6 | tee -a "$OUT/summary.txt"
