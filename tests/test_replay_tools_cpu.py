@@ -53,3 +53,13 @@ def test_sumcheckeq_replay_matches_oracle(emulated, oracle, num_vars):
     for j in range(num_vars):
         assert [list(e) for e in got[j]] == [list(e) for e in inst.evaluation_points()], j
         inst.bound((-j) % p)
+
+
+def test_sharded_hyperkzg_replay_prints_the_single_gpu_digest(emulated, oracle):
+    """tools/hyperkzg_sharded_replay.py as a single rank and tools/hyperkzg_replay.py agree on the digest of the
+    proof (same key, polynomial and challenges) -- the cross-check the two tools are meant to give on the GPU."""
+    import hyperkzg_replay
+    import hyperkzg_sharded_replay
+    a = hyperkzg_sharded_replay.main(["--log2n", "6", "--reps", "1", "--comm", "host"])
+    b = hyperkzg_replay.gpu(log2n=6, reps=1)
+    assert a["digest"] == b["digest"] and a["n_gpus"] == 1

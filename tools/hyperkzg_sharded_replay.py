@@ -23,17 +23,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2n", type=int, default=22)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--comm", choices=["nccl", "host"], default="nccl")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(local)
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl" if a.comm == "nccl" else "gloo", rank=rank, world_size=world)
     import nova_b200 as nb
@@ -67,14 +68,17 @@ def main():
             dt = float(t.item())
         if rep:
             times.append(dt)
+    out = None
     if rank == 0:
-        print(json.dumps({"workload": f"HyperKZG prove core, BN254, 2^{a.log2n} uniform scalars, {world} GPU(s), "
+        out = ({"workload": f"HyperKZG prove core, BN254, 2^{a.log2n} uniform scalars, {world} GPU(s), "
                                       f"index-range sharding, comm={a.comm if world > 1 else 'none'}",
                           "n_gpus": world, "log2n": a.log2n, "ms_best": round(min(times) * 1e3, 3),
                           "ms_all": [round(t * 1e3, 3) for t in times], "timing": "wall clock, max over ranks",
-                          "digest": [com[0][0] % (1 << 64), w[2][0] % (1 << 64)]}))
+                          "digest": [com[0][0] % (1 << 64), w[2][0] % (1 << 64)]})
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":
