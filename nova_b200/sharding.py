@@ -160,6 +160,27 @@ class DeviceEngine:
     def poly_div(self, f: bytes, u: bytes) -> bytes:
         return self._sp.poly_div(self.fid, f, u)
 
+    def axpy(self, a: bytes, b: bytes, r: bytes) -> bytes:
+        return self._pv.fold_witness(self.fid, a, b, r)
+
+    def msm_partial(self, ck, base_offset: int, scalars: bytes) -> bytes:
+        """sum_i scalars[i] * ck[base_offset + i] as a 96-byte Jacobian point (identity for no scalars)"""
+        import ctypes
+
+        from .native import check, lib
+        out = ctypes.create_string_buffer(96)
+        check(lib().b200_msm(ck.handle, base_offset, self._pv._cbuf(scalars), len(scalars) // 32, out))
+        return out.raw
+
+    def point_sum(self, parts: list):
+        from .native import check, lib
+        d, out = self._sp.DeviceVec.from_bytes(b"".join(parts)), self._sp.DeviceVec(96)
+        check(lib().b200_jacobian_sum_dev(int(self.curve), d.ptr, len(parts), out.ptr, None))
+        raw = out.to_bytes()
+        d.free()
+        out.free()
+        return self._pv._jac_to_affine(self._pv.Curve(self.curve), raw)
+
 
 def sharded_multiply_vec(engine, mats_rows, z_local: bytes, group=None):
     """R1CSShape::multiply_vec (src/r1cs/mod.rs:407-431) with the ROWS of A, B, C split by index range and z
@@ -176,6 +197,32 @@ def sharded_cross_term(engine, mats_rows, z1_local: bytes, z2_local: bytes, e1_r
     the commitment key, so its MSM needs only the 96-byte partial exchange (all_gather_partials)."""
     _, (az, bz, cz) = sharded_multiply_vec(engine, mats_rows, engine.vec_add(z1_local, z2_local), group)
     return engine.cross_term(az, bz, cz, e1_rows, u_sum, e2_rows)
+
+
+def sharded_fold_step(engine, p: int, ck, mats_rows, rows: tuple, wrange: tuple, z1_local: bytes, z2_local: bytes,
+                      W1_local: bytes, E1_rows: bytes, W2_local: bytes, u_sum: bytes, challenge, group=None):
+    """The folding half of `prove_step` (nova/mod.rs:456-564: commit(W2), `commit_T` r1cs/mod.rs:578-627,
+    `RelaxedR1CSWitness::fold` :1044-1069) with every vector split by index range over the ranks:
+    W by [wlo, whi) = `wrange`, the rows of A, B, C, E and T by [rlo, rhi) = `rows`, z like the matrices' columns
+    (`z*_local`).  `ck` is a key that holds ck[0 .. max(num_vars, num_cons)) -- the full key, or any key whose
+    indices line up with the global ones.
+      1. partial commitments of W2 (over ck[wlo..whi)) and, after the one all-gather of Z and the local rows of
+         T, of T (over ck[rlo..rhi)): ONE all-gather of 2 x 96 bytes, local sums -> comm_W2, comm_T
+      2. r = challenge(comm_W2, comm_T) -- the random-oracle step, replicated on every rank
+      3. W = W1 + r W2 and E = E1 + r T on the local slices, no exchange.
+    `engine` adds two methods to the ones of `sharded_cross_term`: msm_partial(ck, base_offset, scalars) -> 96-byte
+    Jacobian partial, point_sum(list of 96-byte points) -> affine, and axpy(a, b, r) -> a + r b.
+    -> (comm_W2, comm_T, r, W_local, E_rows, T_rows)"""
+    rlo, rhi = rows
+    wlo, whi = wrange
+    T_rows = sharded_cross_term(engine, mats_rows, z1_local, z2_local, E1_rows, u_sum, None, group)
+    part = engine.msm_partial(ck, wlo, W2_local) + engine.msm_partial(ck, rlo, T_rows)
+    allp = all_gather_bytes(part, group)
+    comm_W2 = engine.point_sum([a[:96] for a in allp])
+    comm_T = engine.point_sum([a[96:] for a in allp])
+    r = challenge(comm_W2, comm_T)
+    rm = _mont(p, r)
+    return comm_W2, comm_T, r, engine.axpy(W1_local, W2_local, rm), engine.axpy(E1_rows, T_rows, rm), T_rows
 
 
 def _mont(p: int, x: int) -> bytes:

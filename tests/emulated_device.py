@@ -97,6 +97,9 @@ class EmulatedDevice:
         _wr(out, co.axpy(fid, _rd(a, 32 * n), _rd(b, 32 * n), _rd(r, 32)))
         return 0
 
+    def b200_axpy(self, fid, a, b, r, n, out):  # host pointers: the same thing here
+        return self.b200_axpy_dev(fid, a, b, r, n, out, None)
+
     def b200_bind_top_dev(self, fid, z, n, r, stream):
         _wr(z, co.bind_top(fid, _rd(z, 32 * n), _rd(r, 32)))
         return 0

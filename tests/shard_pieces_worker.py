@@ -32,6 +32,24 @@ class OracleEngine:
     def poly_div(self, f, u):
         return self.co.poly_div(self.fid, f, u)
 
+    def axpy(self, a, b, r):
+        return self.co.axpy(self.fid, a, b, r)
+
+    def msm_partial(self, ck, base_offset, scalars):  # ck: (curve id, bases); affine result as a Jacobian z = 1
+        from oracle.pyref import CURVES, mont_bytes
+        cid, bases = ck
+        n = len(scalars) // 32
+        aff = self.co.msm(cid, scalars, bases[64 * base_offset:64 * (base_offset + n)]) if n else bytes(64)
+        return aff + (bytes(32) if aff == bytes(64) else mont_bytes(CURVES[cid].p, 1))
+
+    def point_sum(self, parts):
+        from oracle.pyref import CURVES
+        c = CURVES[0]
+        acc = None
+        for b in parts:
+            acc = c.add(acc, c.jacobian_from_bytes(b))
+        return acc
+
 
 def main():
     rank, world, port, kind, outpath = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5]
@@ -97,6 +115,35 @@ def main():
                                         pack(e2[rlo:rhi]) if e2 else None)
         T_exp = co.cross_term(fid, az, bz, cz, pack(W["E"]), pack(e2) if e2 else None, usum)
         ok &= T_local == T_exp[32 * rlo:32 * rhi]
+    # ---- the folding half of prove_step over the ranks (commit W2, commit_T, folds) ----
+    from oracle.pyref import CURVES
+    cid, c = 0, CURVES[0]
+    n_key = max(num_cons, num_vars)
+    bases = co.gen_bases(cid, n_key)
+    if kind in ("gpu", "emulated"):
+        from nova_b200 import provider
+        eng.curve = cid
+        ck = provider.CommitmentKey(provider.Curve(cid), bases)
+    else:
+        ck = (cid, bases)
+    wlo, whi = sh.shard_range(num_vars, rank, world)
+    seen = []
+
+    def challenge(comm_W2, comm_T):
+        seen.append((comm_W2, comm_T))
+        return 0x1234567 * (1 + (comm_T[0] % 97))  # any function of the messages: must agree on every rank
+    usum = pack([(u1 + 1) % p])
+    comm_W2, comm_T, r, W_loc, E_loc, T_loc = sh.sharded_fold_step(
+        eng, p, ck, mats, (rlo, rhi), (wlo, whi), pack(z1[zlo:zhi]), pack(z2[zlo:zhi]), pack(W["W"][wlo:whi]),
+        pack(W["E"][rlo:rhi]), pack(W2[wlo:whi]), usum, challenge)
+    T_exp = co.cross_term(fid, az, bz, cz, pack(W["E"]), None, usum)
+    aff = c.affine_from_bytes
+    ok &= comm_W2 == aff(co.msm(cid, pack(W2), bases)) and comm_T == aff(co.msm(cid, T_exp, bases))
+    ok &= T_loc == T_exp[32 * rlo:32 * rhi]
+    rm = mont_bytes(p, r)
+    ok &= W_loc == co.axpy(fid, pack(W["W"]), pack(W2), rm)[32 * wlo:32 * whi]
+    ok &= E_loc == co.axpy(fid, pack(W["E"]), T_exp, rm)[32 * rlo:32 * rhi]
+    ok &= len(seen) == 1
     open(f"{outpath}.{rank}", "w").write("OK" if ok else "MISMATCH")
     dist.barrier()
     dist.destroy_process_group()
