@@ -377,22 +377,26 @@ def load_setup_sharded(reader, h: bytes | None, n: int, rank: int, world: int, g
                                         ctypes.byref(handle), ctypes.byref(bad))
     NONE = (1 << 64) - 1
     verdict, kind = NONE, 0  # kind: 1 = PointNotOnCurve, 2 = non-canonical (io error), 3 = the blinding generator
-    if rc == B200_E_POINT:
+    ck, lib_error = None, ""
+    if rc == 0:
+        ck = CommitmentKey.__new__(CommitmentKey)
+        ck.curve, ck.n, ck.handle, ck.has_h = curve, hi - lo, handle.value, my_h is not None
+        ck.bases, ck.h = g1, my_h
+    elif rc == B200_E_POINT:
         if my_h and bad.value == hi - lo:
             verdict, kind = num, 3  # after every G1 point, as in the unsharded order
         else:
             verdict = lo + bad.value
             kind = 2 if isinstance(_classify_bad_g1(curve, g1, bad.value), IoError) else 1
-    else:
-        check(rc)
-    votes = all_gather_bytes(verdict.to_bytes(8, "little") + bytes([kind]), group)
-    first, first_kind = min((int.from_bytes(v[:8], "little"), v[8]) for v in votes)
-    ck = None
-    if rc == 0:
-        ck = CommitmentKey.__new__(CommitmentKey)
-        ck.curve, ck.n, ck.handle, ck.has_h = curve, hi - lo, handle.value, my_h is not None
-        ck.bases, ck.h = g1, my_h
+    else:  # a library / CUDA error on this rank: every rank must still reach the collective and stop
+        lib_error = lib().b200_last_error().decode()
+        verdict, kind = 0, 4
     try:
+        votes = all_gather_bytes(verdict.to_bytes(8, "little") + bytes([kind]), group)
+        if any(v[8] == 4 for v in votes):
+            failed = [k for k, v in enumerate(votes) if v[8] == 4]
+            raise IoError(f"key registration failed on rank(s) {failed}" + (f": {lib_error}" if lib_error else ""))
+        first, first_kind = min((int.from_bytes(v[:8], "little"), v[8]) for v in votes)
         if first != NONE:
             if first_kind == 3:
                 raise PointNotOnCurve("the blinding generator h is not a valid point")
@@ -400,7 +404,7 @@ def load_setup_sharded(reader, h: bytes | None, n: int, rank: int, world: int, g
                 raise IoError(f"non-canonical coordinate in G1 point {first}")
             raise PointNotOnCurve(f"Point is not on the curve (G1 point {first})")
         _check_g2(g2, 2)  # the same two points on every rank: the same verdict everywhere
-    except PtauFileError:
+    except Exception:
         if ck is not None:
             ck.release()
         raise
