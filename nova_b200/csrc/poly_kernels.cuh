@@ -14,7 +14,9 @@
 //                                                            1011-1019, 961-999
 //   PrecomputedSparseMatrix::multiply_vec(_pair)             src/r1cs/sparse.rs:136-230
 #pragma once
+#if !defined(NOVA_SIMT_HOST)  // tests/hostcheck/simt_host.h supplies the few CUDA names the kernels use
 #include <cuda_runtime.h>
+#endif
 #include "field.cuh"
 
 namespace nova {

@@ -49,3 +49,63 @@ extern "C" int hc_simt_sc_round_batched(int fid, const void* desc, void* state, 
   }
   return 0;
 }
+
+// ---- the two-stage reduction kernels of the sum-check forms (poly_kernels.cuh: k_form_reduce with every
+// sc_form, then k_form_final) as <<<grid, 256>>> blocks of host threads: grid-stride loops, warp shuffles,
+// the shared-memory stage and the eq factor with its shard mapping run as written.  Mirrors
+// ops_impl.cuh sc_launch / capi_poly.inc b200_sc_eval_sharded_dev. ----
+#include "../../nova_b200/csrc/poly_kernels.cuh"
+
+template <class F, int FORM>
+static void simt_sc_form(const void* A, const void* B, const void* C, size_t len, const void* eq_left,
+                         const void* eq_right, int shift, size_t id_mul, size_t id_add, unsigned grid, void* out) {
+  constexpr int NOUT = sc_form_nout(FORM);
+  sc_form<F, FORM> f;
+  f.A = A;
+  f.B = B;
+  f.C = C;
+  f.h = len / 2;
+  f.eq.left = eq_left;
+  f.eq.right = eq_right;
+  f.eq.shift = shift;
+  f.eq.mask = ((size_t)1 << shift) - 1;
+  f.eq.id_mul = id_mul;
+  f.eq.id_add = id_add;
+  const size_t count = (FORM == SC_DOT_EQ || FORM == SC_DOT) ? len : len / 2;
+  std::vector<fe_t> partials((size_t)grid * NOUT);
+  simt_launch_grid(grid, 256, [&] { k_form_reduce<F, NOUT, sc_form<F, FORM>>(f, count, partials.data()); });
+  simt_launch_grid(1, 256, [&] { k_form_final<F, NOUT>(partials.data(), (int)grid, out); });
+}
+
+template <class F>
+static int simt_sc_eval_t(int form, const void* A, const void* B, const void* C, size_t len, const void* l,
+                          const void* r, int shift, size_t id_mul, size_t id_add, unsigned grid, void* out) {
+#define SC_CASE(X) \
+  case X: simt_sc_form<F, X>(A, B, C, len, l, r, shift, id_mul, id_add, grid, out); return 0
+  switch (form) {
+    SC_CASE(SC_QUAD_PROD);
+    SC_CASE(SC_LINEAR);
+    SC_CASE(SC_QUADRATIC);
+    SC_CASE(SC_CUBIC);
+    SC_CASE(SC_EQ_CUBIC3);
+    SC_CASE(SC_EQ_CUBIC2);
+    SC_CASE(SC_EQ_QUAD1);
+    SC_CASE(SC_EQ_CUBIC3_M1);
+    SC_CASE(SC_EQ_CUBIC2_M1);
+    SC_CASE(SC_EQ_QUAD1_M1);
+    SC_CASE(SC_DOT_EQ);
+    SC_CASE(SC_DOT);
+    default: return 1;
+  }
+#undef SC_CASE
+}
+
+extern "C" int hc_simt_sc_eval(int fid, int form, const void* A, const void* B, const void* C, size_t len,
+                               const void* eq_left, const void* eq_right, int shift, size_t id_mul, size_t id_add,
+                               unsigned grid, void* out) {
+  switch (fid) {
+    case 0: return simt_sc_eval_t<BN254_FR>(form, A, B, C, len, eq_left, eq_right, shift, id_mul, id_add, grid, out);
+    case 3: return simt_sc_eval_t<PALLAS_FQ>(form, A, B, C, len, eq_left, eq_right, shift, id_mul, id_add, grid, out);
+    default: return 1;
+  }
+}
