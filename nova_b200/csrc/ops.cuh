@@ -4,6 +4,7 @@
 // a `field_ops` table so the C ABI (capi.cu) is template-free and the four translation units
 // compile in parallel.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
@@ -81,6 +82,14 @@ struct field_ops {
   void (*on_curve)(cudaStream_t, const void* pts, size_t n, int b_small, uint32_t* first_bad);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
+// NOVA_B200_SC_SEG=1 selects the segmented reduction of the eq-weighted sum-check forms (k_form_reduce_eqseg)
+inline bool sc_segmented_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("NOVA_B200_SC_SEG");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
 constexpr size_t POLY_EVAL_SCRATCH_ELEMS = (size_t)3 * (1 + SC_MAX_BLOCKS + 256) + (size_t)3 * SC_MAX_BLOCKS;
 constexpr int POLY_CHUNK_HOST = 64;  // must equal POLY_CHUNK in poly_kernels.cuh
 inline size_t poly_div_scratch_elems(size_t n) {

@@ -179,6 +179,16 @@ struct ops_impl {
     f.eq.id_add = id_add;
     size_t need = (count + 255) / 256;
     int grid = (int)(need < (size_t)SC_MAX_BLOCKS ? (need ? need : 1) : SC_MAX_BLOCKS);
+    if constexpr (sc_form<F, FORM>::eq_weighted) {
+      // opt-in segmented reduction (see k_form_reduce_eqseg): split tables, unsharded, >= 4 indices per thread
+      if (sc_segmented_enabled() && eq_left != nullptr && id_mul == 1 && shift >= 10) {
+        size_t nseg = (count + ((size_t)1 << shift) - 1) >> shift;
+        grid = (int)(nseg < (size_t)SC_MAX_BLOCKS ? nseg : SC_MAX_BLOCKS);
+        k_form_reduce_eqseg<F, NOUT, sc_form<F, FORM>><<<grid, 256, 0, s>>>(f, count, scratch);
+        k_form_final<F, NOUT><<<1, 256, 0, s>>>(scratch, grid, out);
+        return;
+      }
+    }
     k_form_reduce<F, NOUT, sc_form<F, FORM>><<<grid, 256, 0, s>>>(f, count, scratch);
     k_form_final<F, NOUT><<<1, 256, 0, s>>>(scratch, grid, out);
   }

@@ -130,8 +130,6 @@ struct sc_form {
   NOVA_D void operator()(size_t id, fe_t (&acc)[N]) const {
     if constexpr (FORM == SC_DOT) {
       acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), fe_load(B, id)));
-    } else if constexpr (FORM == SC_DOT_EQ) {
-      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), eq.get<F>(id)));
     } else if constexpr (FORM == SC_QUAD_PROD) {
       fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
       acc[0] = fe_add<F>(acc[0], fe_mul<F>(al, bl));
@@ -154,19 +152,29 @@ struct sc_form {
       acc[1] = fe_add<F>(acc[1], fe_mul<F>(fe_mul<F>(da, db), dc));
       acc[2] = fe_add<F>(acc[2], fe_mul<F>(fe_mul<F>(fe_sub<F>(al, da), fe_sub<F>(bl, db)),
                                            fe_sub<F>(cl, dc)));
-    } else if constexpr (FORM == SC_EQ_CUBIC3 || FORM == SC_EQ_CUBIC2) {
+    } else {  // eq-weighted forms: the un-weighted terms times f = eq(id)
+      fe_t x[N];
+      unweighted(id, x);
+      fe_t f = eq.get<F>(id);
+#pragma unroll
+      for (int k = 0; k < N; k++) acc[k] = fe_add<F>(acc[k], fe_mul<F>(x[k], f));
+    }
+  }
+  // the terms of an eq-weighted form before the weight: t0 / tinf (or the single t) of index `id`
+  static constexpr bool eq_weighted = FORM >= SC_EQ_CUBIC3 && FORM <= SC_DOT_EQ;
+  template <int N>
+  NOVA_D void unweighted(size_t id, fe_t (&x)[N]) const {
+    if constexpr (FORM == SC_EQ_CUBIC3 || FORM == SC_EQ_CUBIC2) {
       fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
       fe_t e0 = fe_mul<F>(al, bl);
       if constexpr (FORM == SC_EQ_CUBIC3)
         e0 = fe_sub<F>(e0, fe_load(C, id));
       else
         e0 = fe_sub<F>(e0, fe_one<F>());
-      fe_t q = fe_mul<F>(fe_sub<F>(ah, al), fe_sub<F>(bh, bl));
-      fe_t f = eq.get<F>(id);
-      acc[0] = fe_add<F>(acc[0], fe_mul<F>(e0, f));
-      acc[1] = fe_add<F>(acc[1], fe_mul<F>(q, f));
-    } else if constexpr (FORM == SC_EQ_QUAD1) {
-      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), eq.get<F>(id)));
+      x[0] = e0;
+      x[1] = fe_mul<F>(fe_sub<F>(ah, al), fe_sub<F>(bh, bl));
+    } else if constexpr (FORM == SC_EQ_QUAD1 || FORM == SC_DOT_EQ) {
+      x[0] = fe_load(A, id);
     } else if constexpr (FORM == SC_EQ_CUBIC3_M1 || FORM == SC_EQ_CUBIC2_M1) {
       fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
       fe_t am = fe_sub<F>(fe_dbl<F>(al), ah), bm = fe_sub<F>(fe_dbl<F>(bl), bh);
@@ -177,13 +185,61 @@ struct sc_form {
       } else {
         e = fe_sub<F>(e, fe_one<F>());
       }
-      acc[0] = fe_add<F>(acc[0], fe_mul<F>(e, eq.get<F>(id)));
+      x[0] = e;
     } else if constexpr (FORM == SC_EQ_QUAD1_M1) {
       fe_t al = fe_load(A, id), ah = fe_load(A, id + h);
-      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_sub<F>(fe_dbl<F>(al), ah), eq.get<F>(id)));
+      x[0] = fe_sub<F>(fe_dbl<F>(al), ah);
     }
   }
 };
+
+// Segmented form of the same reduction for the eq-weighted sums (opt-in, NOVA_B200_SC_SEG=1; not yet timed):
+//   sum_id left[id >> shift] right[id & mask] X(id)  =  sum_hi left[hi] * ( sum_lo right[lo] X(hi, lo) )
+// -- the order the reference's split-eq loops use (sumcheck.rs:900-966).  A block walks whole segments of 2^shift
+// indices, so the product left * right per index disappears (one product by left[hi] per thread and segment
+// instead), and two indices share one Montgomery reduction through fe_mul2_add.  Field sums are exact, so the
+// result is bit-identical to k_form_reduce's.  Needs the split tables (left != nullptr), an unsharded index
+// (id_mul == 1) and segments of at least a few indices per thread; the launcher checks.
+template <class F, int NOUT, class Form>
+__global__ void __launch_bounds__(256) k_form_reduce_eqseg(Form form, size_t count, void* partials) {
+  __shared__ fe_t sm[8 * NOUT];
+  fe_t acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) acc[k] = fe_zero<F>();
+  const size_t seg = (size_t)1 << form.eq.shift;
+  const size_t nseg = (count + seg - 1) / seg;
+  const size_t T = blockDim.x;
+  for (size_t s = blockIdx.x; s < nseg; s += gridDim.x) {
+    const size_t base = s * seg;
+    const size_t end = base + seg < count ? base + seg : count;
+    fe_t in[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) in[k] = fe_zero<F>();
+    size_t id = base + threadIdx.x;
+    for (; id + T < end; id += 2 * T) {  // indices id and id + T together
+      fe_t xa[NOUT], xb[NOUT];
+      form.unweighted(id, xa);
+      form.unweighted(id + T, xb);
+      const fe_t ra = fe_load(form.eq.right, id - base), rb = fe_load(form.eq.right, id + T - base);
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) in[k] = fe_add<F>(in[k], fe_mul2_add<F>(xa[k], ra, xb[k], rb));
+    }
+    if (id < end) {
+      fe_t xa[NOUT];
+      form.unweighted(id, xa);
+      const fe_t ra = fe_load(form.eq.right, id - base);
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) in[k] = fe_add<F>(in[k], fe_mul<F>(xa[k], ra));
+    }
+    const fe_t lf = fe_load(form.eq.left, s);
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) acc[k] = fe_add<F>(acc[k], fe_mul<F>(in[k], lf));
+  }
+  block_sum<F, NOUT>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) fe_store(partials, (size_t)blockIdx.x * NOUT + k, acc[k]);
+}
 
 constexpr int sc_form_nout(int form) {
   return form == SC_CUBIC ? 3

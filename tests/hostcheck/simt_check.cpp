@@ -109,3 +109,47 @@ extern "C" int hc_simt_sc_eval(int fid, int form, const void* A, const void* B, 
     default: return 1;
   }
 }
+
+// the segmented reduction of the eq-weighted forms (k_form_reduce_eqseg), launched as ops_impl.cuh sc_launch does
+// when NOVA_B200_SC_SEG=1: one block per segment of 2^shift indices (at most `grid` blocks)
+template <class F, int FORM>
+static void simt_sc_form_seg(const void* A, const void* B, const void* C, size_t len, const void* eq_left,
+                             const void* eq_right, int shift, unsigned grid, void* out) {
+  constexpr int NOUT = sc_form_nout(FORM);
+  sc_form<F, FORM> f;
+  f.A = A;
+  f.B = B;
+  f.C = C;
+  f.h = len / 2;
+  f.eq.left = eq_left;
+  f.eq.right = eq_right;
+  f.eq.shift = shift;
+  f.eq.mask = ((size_t)1 << shift) - 1;
+  f.eq.id_mul = 1;
+  f.eq.id_add = 0;
+  const size_t count = FORM == SC_DOT_EQ ? len : len / 2;
+  std::vector<fe_t> partials((size_t)grid * NOUT);
+  simt_launch_grid(grid, 256, [&] { k_form_reduce_eqseg<F, NOUT, sc_form<F, FORM>>(f, count, partials.data()); });
+  simt_launch_grid(1, 256, [&] { k_form_final<F, NOUT>(partials.data(), (int)grid, out); });
+}
+
+extern "C" int hc_simt_sc_eval_seg(int fid, int form, const void* A, const void* B, const void* C, size_t len,
+                                   const void* eq_left, const void* eq_right, int shift, unsigned grid, void* out) {
+  if (fid != 0 && fid != 3) return 1;
+#define SEG_CASE(X)                                                                                   \
+  case X:                                                                                             \
+    if (fid == 0) simt_sc_form_seg<BN254_FR, X>(A, B, C, len, eq_left, eq_right, shift, grid, out);   \
+    else simt_sc_form_seg<PALLAS_FQ, X>(A, B, C, len, eq_left, eq_right, shift, grid, out);          \
+    return 0
+  switch (form) {
+    SEG_CASE(SC_EQ_CUBIC3);
+    SEG_CASE(SC_EQ_CUBIC2);
+    SEG_CASE(SC_EQ_QUAD1);
+    SEG_CASE(SC_EQ_CUBIC3_M1);
+    SEG_CASE(SC_EQ_CUBIC2_M1);
+    SEG_CASE(SC_EQ_QUAD1_M1);
+    SEG_CASE(SC_DOT_EQ);
+    default: return 1;
+  }
+#undef SEG_CASE
+}

@@ -89,3 +89,22 @@ def test_sharded_index_mapping(hc_simt, form):
     for id_add in range(3):
         got = run_form(hc_simt, fid, form, A, B, C, length, left, right, shift, 3, id_add, 1)
         assert got == co.sc_eval(fid, form, A, B, C, left, right, shift, 3, id_add)
+
+
+@pytest.mark.parametrize("fid,form", [(0, f) for f in EQ_FORMS] + [(3, 4), (3, 10)])
+def test_segmented_eq_reduction_is_bit_identical(hc_simt, fid, form):
+    """k_form_reduce_eqseg (opt-in NOVA_B200_SC_SEG=1): sum_hi left[hi] * sum_lo right[lo] X with pairs of indices
+    sharing one reduction (fe_mul2_add) equals the flat sum -- with full segments, a ragged last segment, an odd
+    number of indices per thread (the unpaired tail) and fewer blocks than segments."""
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(5000 + 10 * fid + form)
+    vec = lambda n: b"".join(mont_bytes(p, rng.field(p)) for _ in range(n))
+    shift = 10  # segments of 1024 indices = 4 per thread
+    for count, grid in ((2 * 1024 + 700, 3), (2 * 1024 + 300, 2), (1024 + 1, 1)):
+        length = count if form == 10 else 2 * count
+        A, B, C = vec(length), vec(length), vec(length)
+        left, right = vec(4), vec(1 << shift)
+        out = ctypes.create_string_buffer(96)
+        assert hc_simt.hc_simt_sc_eval_seg(fid, form, _buf(A), _buf(B), _buf(C), ctypes.c_size_t(length), _buf(left),
+                                           _buf(right), shift, grid, out) == 0
+        assert out.raw[:32 * SC_NOUT[form]] == co.sc_eval(fid, form, A, B, C, left, right, shift), (count, grid)

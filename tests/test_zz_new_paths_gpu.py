@@ -402,3 +402,19 @@ def test_sharded_hyperkzg_nccl(tmp_path):
         pytest.skip("needs two GPUs")
     import test_hyperkzg_sharded
     test_hyperkzg_sharded.run_world(2, "nccl", tmp_path)
+
+
+@pytest.mark.parametrize("seg", ["0", "1"])
+def test_segmented_eq_reduction_on_device(seg):
+    """NOVA_B200_SC_SEG=1 (k_form_reduce_eqseg: per-segment sums, pairs of indices sharing one reduction) gives
+    the same t(0) / t(inf) / t(-1) sums as the default kernel and the oracle, on every eq-weighted form at a size
+    where it is taken; in a subprocess because the switch is read once.  CPU twin: tests/test_host_kernels.py
+    (the kernel itself on host threads)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, NOVA_B200_SC_SEG=seg)
+    out = subprocess.run([sys.executable, os.path.join(here, "sc_seg_worker.py")], env=env, capture_output=True,
+                         text=True, timeout=280)
+    assert out.returncode == 0 and ("SEG OK" if seg == "1" else "FLAT OK") in out.stdout, out.stdout + out.stderr

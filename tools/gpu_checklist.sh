@@ -37,6 +37,12 @@ run ppsnark_replay   timeout 600  python tools/ppsnark_replay.py --log2cons 18 -
 run sumcheckeq       timeout 600  python tools/sumcheckeq_replay.py --min 10 --max 22 --reps 2
 run ppsnark_dev      timeout 600  python tools/ppsnark_replay.py --log2cons 18 --reps 2 --device-transcript
 
+# 3b. segmented eq reductions (NOVA_B200_SC_SEG=1): parity of the sum-check suites under the switch, then A/B timing
+run scseg_parity     timeout 900  env NOVA_B200_SC_SEG=1 python -m pytest tests/test_spartan_gpu.py tests/test_ppsnark_gpu.py -m gpu -x -q -p no:cacheprovider
+run scseg_sumcheck   timeout 300  env NOVA_B200_SC_SEG=1 python tools/sumcheck_replay.py --log-n 22 --reps 3
+run scflat_sumcheck  timeout 300  python tools/sumcheck_replay.py --log-n 22 --reps 3
+run scseg_ppsnark    timeout 600  env NOVA_B200_SC_SEG=1 python tools/ppsnark_replay.py --log2cons 18 --reps 2
+
 # 4. end-to-end commit: chunked upload overlapping the digit stage (tuning hook, off by default)
 run e2e_base         timeout 300  python tools/e2e_commit.py --log-n 20
 run e2e_chunks4      timeout 300  env NOVA_B200_H2D_CHUNKS=4 python tools/e2e_commit.py --log-n 20
