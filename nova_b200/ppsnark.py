@@ -107,8 +107,29 @@ def dev_u32(xs) -> DeviceVec:
     return v
 
 
+class Shard:
+    """Cyclic sharding of the sum-check tables over `world` ranks: rank `rank` holds the global
+    entries rank, rank + world, ...; `reduce(list of ints) -> list of ints` adds the ranks' partial sums."""
+
+    def __init__(self, rank: int, world: int, reduce):
+        self.rank, self.world, self.reduce = rank, world, reduce
+
+
+_SHARD = None  # set by prove_helper_sharded for the duration of the sharded rounds
+
+
+def _sc_eval_one(fid, form, A, B, C, length, L, R, shift) -> list:
+    """one reduction read back at once (the tau = 0 third sums); sharded when a Shard is active"""
+    if _SHARD is None:
+        return _sc_eval_dev(fid, form, A, B, C, length, L, R, shift)
+    sums = RoundSums(fid)
+    sums.add(form, A, B, C, length, L, R, shift)
+    return sums.fetch()[0]
+
+
 class RoundSums:
-    """All reductions of one sum-check round in one result buffer, one read-back."""
+    """All reductions of one sum-check round in one result buffer, one read-back (and, when the tables are
+    sharded, one exchange of the partial sums)."""
 
     def __init__(self, fid: int, cap: int = 16):
         self.fid, self.out, self.nout = fid, _small_buf("round_sums", 96 * cap), []
@@ -116,8 +137,12 @@ class RoundSums:
     def add(self, form, A, B, C, length, L=None, R=None, shift=0) -> int:
         k = len(self.nout)
         dst = ctypes.c_void_p(self.out.ptr.value + 96 * k)
-        check(lib().b200_sc_eval_dev(self.fid, form, A.ptr, B.ptr if B else None, C.ptr if C else None, length,
-                                     L.ptr if L else None, R.ptr if R else None, shift, dst, None))
+        a = (self.fid, form, A.ptr, B.ptr if B else None, C.ptr if C else None, length,
+             L.ptr if L else None, R.ptr if R else None, shift)
+        if _SHARD is None:
+            check(lib().b200_sc_eval_dev(*a, dst, None))
+        else:  # local index j stands for the global index j * world + rank
+            check(lib().b200_sc_eval_sharded_dev(*a, _SHARD.world, _SHARD.rank, dst, None))
         self.nout.append(SC_NOUT[form])
         return k
 
@@ -129,6 +154,10 @@ class RoundSums:
         raw = self.out.to_bytes(96 * len(self.nout))
         res = [fields.unpack(self.fid, raw[96 * k:96 * k + 32 * n]) for k, n in enumerate(self.nout)]
         self.nout = []
+        if _SHARD is not None:
+            flat = _SHARD.reduce([x for r in res for x in r])
+            it = iter(flat)
+            res = [[next(it) for _ in r] for r in res]
         return res
 
 
@@ -288,7 +317,7 @@ class MemorySumcheckInstance:
                          3: (self.w_inv_row, self.w_row, None, SC_EQ_CUBIC2_M1),
                          4: (self.t_inv_col, self.t_col, self.ts_col, SC_EQ_CUBIC3_M1),
                          5: (self.w_inv_col, self.w_col, None, SC_EQ_CUBIC2_M1)}[j]
-        (tm1,) = _sc_eval_dev(self.fid, form, A, B, C, self.len, L, R, sh)
+        (tm1,) = _sc_eval_one(self.fid, form, A, B, C, self.len, L, R, sh)
         e0, slope, em1 = self.eq.eq_tau_0_a_inf[self.eq.round - 1]
         q, p = self.eq.eval_eq_left, self.p
         return [e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p]
@@ -306,6 +335,8 @@ class MemorySumcheckInstance:
                              self.t_inv_col, self.w_col, self.w_inv_col, self.ts_col], self.len, r_dev)
         self.len //= 2
         self.eq.bound(r)
+
+    TABLES = ("t_row", "t_inv_row", "w_row", "w_inv_row", "ts_row", "t_col", "t_inv_col", "w_col", "w_inv_col", "ts_col")
 
     # -- device-transcript loop (prove_helper_device): claim kinds, third sums for tau = 0, binds only --
     KINDS = (SCB_LIN2, SCB_LIN2, SCB_EQ_DEG2, SCB_EQ_DEG2, SCB_EQ_DEG2, SCB_EQ_DEG2)
@@ -380,7 +411,7 @@ class InnerBatchedSumcheckInstance:
         d = self.eq._derive(t0, 0, self.running_E, False)
         if d is None:  # tau = 0 (sumcheck.rs:1180-1213)
             L, R, sh = self.eq._tables()
-            (tm1,) = _sc_eval_dev(self.fid, SC_EQ_QUAD1_M1, self.E, None, None, self.len, L, R, sh)
+            (tm1,) = _sc_eval_one(self.fid, SC_EQ_QUAD1_M1, self.E, None, None, self.len, L, R, sh)
             q0, _, qm1 = self.eq.eq_tau_0_a_inf[self.eq.round - 1]
             q = self.eq.eval_eq_left
             d = (q0 * q * t0 % self.p, 0, qm1 * q * tm1 % self.p)
@@ -393,6 +424,7 @@ class InnerBatchedSumcheckInstance:
         self.len //= 2
         self.eq.bound(r)
 
+    TABLES = ("L_row", "L_col", "val", "E")
     KINDS = (SCB_RAW3, SCB_EQ_DEG1)
 
     def eq_instances(self):
@@ -448,7 +480,16 @@ class WitnessBoundSumcheck:
         _bind_all(self.fid, [self.W, self.masked_eq], self.len, r_dev)
         self.len //= 2
 
+    TABLES = ("W", "masked_eq")
     KINDS = (SCB_LIN2,)
+
+    @classmethod
+    def from_shards(cls, fid, n_local: int, W_local, masked_eq_local):
+        """this rank's cyclic shard of W (padded) and of the masked eq table (ppsnark.rs:270-300)"""
+        self = cls.__new__(cls)
+        self.fid, self.len = fid, n_local
+        self.W, self.masked_eq = dev_copy(W_local, n_local), dev_copy(masked_eq_local, n_local)
+        return self
 
     def eq_instances(self):
         return []
@@ -501,6 +542,66 @@ def prove_helper(fid, mem, inner, witness, transcript):
             eng.bound(r, r_dev)
         e = poly.evaluate(r)
         polys.append(poly.compress())
+    return polys, rs, mem.final_claims(), inner.final_claims(), witness.final_claims()
+
+
+def prove_helper_sharded(fid, mem, inner, witness, transcript, rank: int, world: int, gather):
+    """`prove_helper` (ppsnark.rs:886-983) with the sixteen tables sharded CYCLICALLY over `world` ranks (a power
+    of two): the engines are built from this rank's shards (local length N / world; the eq instances from the
+    full point).  Per round every rank reduces its shard (nine sums; the eq weight uses the global index), the
+    partial sums are exchanged with ONE all-gather (`gather(bytes) -> list of every rank's bytes`), the O(1)
+    algebra and the transcript run replicated, and the binds need no exchange (i and i + len/2 are co-resident
+    under the cyclic layout).  When one element per rank is left the tables are all-gathered (16 x world
+    elements) and the last log2(world) rounds run replicated.  Every rank returns what `prove_helper` returns."""
+    global _SHARD
+    p = fields.MODULUS[fid]
+    assert world & (world - 1) == 0
+    engines = (mem, inner, witness)
+
+    def reduce(vals):
+        raw = b"".join(int(v).to_bytes(32, "little") for v in vals)
+        parts = gather(raw)
+        return [sum(int.from_bytes(q[32 * k:32 * k + 32], "little") for q in parts) % p for k in range(len(vals))]
+
+    def replicate_tail():
+        for eng in engines:
+            for name in eng.TABLES:
+                old = getattr(eng, name)
+                setattr(eng, name, DeviceVec.from_bytes(b"".join(gather(_read1(old)))))
+            eng.len = world
+
+    assert mem.size() == inner.size() == witness.size()
+    n_rounds = (mem.size() * world).bit_length() - 1
+    claims = mem.initial_claims() + inner.initial_claims() + witness.initial_claims()
+    s = transcript.squeeze(b"r")
+    coeffs = [pow(s, i, p) for i in range(len(claims))]
+    e = sum(c * k for c, k in zip(claims, coeffs)) % p
+    rs, polys = [], []
+    sums = RoundSums(fid)
+    _SHARD = Shard(rank, world, reduce) if world > 1 else None
+    try:
+        for _ in range(n_rounds):
+            if _SHARD is not None and mem.size() == 1:
+                replicate_tail()
+                _SHARD = None
+            for eng in engines:
+                eng.enqueue(sums)
+            res = sums.fetch()
+            evals = mem.evaluation_points(res) + inner.evaluation_points(res) + witness.evaluation_points(res)
+            c0 = sum(evals[i][0] * coeffs[i] for i in range(len(evals))) % p
+            cb = sum(evals[i][1] * coeffs[i] for i in range(len(evals))) % p
+            ci = sum(evals[i][2] * coeffs[i] for i in range(len(evals))) % p
+            poly = UniPoly.from_evals_deg3(p, [c0, (e - c0) % p, cb, ci])
+            transcript.absorb_bytes(b"p", poly.to_transcript_bytes())
+            r = transcript.squeeze(b"c")
+            rs.append(r)
+            r_dev = _challenge_dev(fid, r)
+            for eng in engines:
+                eng.bound(r, r_dev)
+            e = poly.evaluate(r)
+            polys.append(poly.compress())
+    finally:
+        _SHARD = None
     return polys, rs, mem.final_claims(), inner.final_claims(), witness.final_claims()
 
 

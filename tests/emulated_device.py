@@ -114,6 +114,12 @@ class EmulatedDevice:
         _wr(out, co.sc_eval(fid, form, g(A), g(B), g(C), tab(eq_left), tab(eq_right), shift))
         return 0
 
+    def b200_sc_eval_sharded_dev(self, fid, form, A, B, C, length, eq_left, eq_right, shift, id_mul, id_add, out, stream):
+        g = lambda p: _rd(p, 32 * length) if _addr(p) else None
+        tab = lambda p: _rd(p, self._size(p)) if _addr(p) else None
+        _wr(out, co.sc_eval(fid, form, g(A), g(B), g(C), tab(eq_left), tab(eq_right), shift, id_mul, id_add))
+        return 0
+
     def b200_eq_table_dev(self, fid, r, ell, out, stream):
         _wr(out, co.eq_table(fid, _rd(r, 32 * ell)))
         return 0

@@ -418,3 +418,10 @@ def test_segmented_eq_reduction_on_device(seg):
     out = subprocess.run([sys.executable, os.path.join(here, "sc_seg_worker.py")], env=env, capture_output=True,
                          text=True, timeout=280)
     assert out.returncode == 0 and ("SEG OK" if seg == "1" else "FLAT OK") in out.stdout, out.stdout + out.stderr
+
+
+def test_sharded_batched_sumcheck_two_ranks_on_device(tmp_path):
+    """ppsnark.prove_helper_sharded with two gloo ranks driving the same GPU: cyclic shards, b200_sc_eval_sharded_dev
+    for all nine sums, one exchange per round, replicated tail.  CPU twin: tests/test_ppsnark_sharded.py."""
+    import test_ppsnark_sharded
+    test_ppsnark_sharded.run_world(2, "gpu", tmp_path)
