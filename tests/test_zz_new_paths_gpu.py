@@ -15,7 +15,10 @@ device code exercised through its host build (tests/hostcheck, incl. the real ke
   the device-resident folding step (commit_T, NIFS, folds, is_sat_relaxed, streamed witness, one half of
   CompressedSNARK::prove); the C++ mirror's resident layer; ppsnark with the batched device round
   (b200_sc_round_batched_dev); prove_batched_cubic; the remaining CommitmentEngine methods; the multi-GPU pieces
-  beyond MSM and sum-check (two gloo ranks on one GPU).
+  beyond MSM and sum-check (two gloo ranks on one GPU);
+* PTAU / Pedersen key files -> resident keys validated in HBM (b200_ck_register_checked, nova_b200/ptau.py), also
+  one index range per rank; HyperKZG prove, the ppsnark batched sum-check and the folding step over two ranks;
+  the segmented eq reductions (NOVA_B200_SC_SEG=1, in a subprocess).
 """
 import pytest
 
