@@ -115,14 +115,11 @@ class Shard:
         self.rank, self.world, self.reduce = rank, world, reduce
 
 
-_SHARD = None  # set by prove_helper_sharded for the duration of the sharded rounds
-
-
-def _sc_eval_one(fid, form, A, B, C, length, L, R, shift) -> list:
-    """one reduction read back at once (the tau = 0 third sums); sharded when a Shard is active"""
-    if _SHARD is None:
+def _sc_eval_one(shard, fid, form, A, B, C, length, L, R, shift) -> list:
+    """one reduction read back at once (the tau = 0 third sums); `shard`: the engine's Shard or None"""
+    if shard is None:
         return _sc_eval_dev(fid, form, A, B, C, length, L, R, shift)
-    sums = RoundSums(fid)
+    sums = RoundSums(fid, shard=shard)
     sums.add(form, A, B, C, length, L, R, shift)
     return sums.fetch()[0]
 
@@ -131,18 +128,18 @@ class RoundSums:
     """All reductions of one sum-check round in one result buffer, one read-back (and, when the tables are
     sharded, one exchange of the partial sums)."""
 
-    def __init__(self, fid: int, cap: int = 16):
-        self.fid, self.out, self.nout = fid, _small_buf("round_sums", 96 * cap), []
+    def __init__(self, fid: int, cap: int = 16, shard: "Shard | None" = None):
+        self.fid, self.out, self.nout, self.shard = fid, _small_buf("round_sums", 96 * cap), [], shard
 
     def add(self, form, A, B, C, length, L=None, R=None, shift=0) -> int:
         k = len(self.nout)
         dst = ctypes.c_void_p(self.out.ptr.value + 96 * k)
         a = (self.fid, form, A.ptr, B.ptr if B else None, C.ptr if C else None, length,
              L.ptr if L else None, R.ptr if R else None, shift)
-        if _SHARD is None:
+        if self.shard is None:
             check(lib().b200_sc_eval_dev(*a, dst, None))
         else:  # local index j stands for the global index j * world + rank
-            check(lib().b200_sc_eval_sharded_dev(*a, _SHARD.world, _SHARD.rank, dst, None))
+            check(lib().b200_sc_eval_sharded_dev(*a, self.shard.world, self.shard.rank, dst, None))
         self.nout.append(SC_NOUT[form])
         return k
 
@@ -154,8 +151,8 @@ class RoundSums:
         raw = self.out.to_bytes(96 * len(self.nout))
         res = [fields.unpack(self.fid, raw[96 * k:96 * k + 32 * n]) for k, n in enumerate(self.nout)]
         self.nout = []
-        if _SHARD is not None:
-            flat = _SHARD.reduce([x for r in res for x in r])
+        if self.shard is not None:
+            flat = self.shard.reduce([x for r in res for x in r])
             it = iter(flat)
             res = [[next(it) for _ in r] for r in res]
         return res
@@ -280,6 +277,8 @@ def memory_compute_oracles(fid, r: int, gamma: int, N: int, mem_row, addr_row, L
 
 # ---- the three engines ---------------------------------------------------------------------------
 class MemorySumcheckInstance:
+    shard = None  # a Shard while prove_helper_sharded runs the sharded rounds on this engine
+
     def __init__(self, fid, N, polys_oracle, polys_aux, rhos, ts_row, ts_col):
         self.fid, self.p, self.len = fid, fields.MODULUS[fid], N
         self.t_inv_row, self.w_inv_row, self.t_inv_col, self.w_inv_col = (dev_copy(v, N) for v in polys_oracle)
@@ -317,7 +316,7 @@ class MemorySumcheckInstance:
                          3: (self.w_inv_row, self.w_row, None, SC_EQ_CUBIC2_M1),
                          4: (self.t_inv_col, self.t_col, self.ts_col, SC_EQ_CUBIC3_M1),
                          5: (self.w_inv_col, self.w_col, None, SC_EQ_CUBIC2_M1)}[j]
-        (tm1,) = _sc_eval_one(self.fid, form, A, B, C, self.len, L, R, sh)
+        (tm1,) = _sc_eval_one(self.shard, self.fid, form, A, B, C, self.len, L, R, sh)
         e0, slope, em1 = self.eq.eq_tau_0_a_inf[self.eq.round - 1]
         q, p = self.eq.eval_eq_left, self.p
         return [e0 * q * t0 % p, slope * q * tinf % p, em1 * q * tm1 % p]
@@ -386,6 +385,8 @@ def _first(fid, v) -> int:
 
 
 class InnerBatchedSumcheckInstance:
+    shard = None
+
     def __init__(self, fid, N, claim, L_row, L_col, val, claim_E, r_outer, E):
         p = fields.MODULUS[fid]
         self.fid, self.p, self.len = fid, p, N
@@ -411,7 +412,7 @@ class InnerBatchedSumcheckInstance:
         d = self.eq._derive(t0, 0, self.running_E, False)
         if d is None:  # tau = 0 (sumcheck.rs:1180-1213)
             L, R, sh = self.eq._tables()
-            (tm1,) = _sc_eval_one(self.fid, SC_EQ_QUAD1_M1, self.E, None, None, self.len, L, R, sh)
+            (tm1,) = _sc_eval_one(self.shard, self.fid, SC_EQ_QUAD1_M1, self.E, None, None, self.len, L, R, sh)
             q0, _, qm1 = self.eq.eq_tau_0_a_inf[self.eq.round - 1]
             q = self.eq.eval_eq_left
             d = (q0 * q * t0 % self.p, 0, qm1 * q * tm1 % self.p)
@@ -453,6 +454,8 @@ class InnerBatchedSumcheckInstance:
 
 
 class WitnessBoundSumcheck:
+    shard = None
+
     def __init__(self, fid, N, tau: list, W_padded, num_vars: int):
         m = num_vars.bit_length() - 1
         assert m < N.bit_length() - 1  # ppsnark.rs:288
@@ -553,7 +556,6 @@ def prove_helper_sharded(fid, mem, inner, witness, transcript, rank: int, world:
     algebra and the transcript run replicated, and the binds need no exchange (i and i + len/2 are co-resident
     under the cyclic layout).  When one element per rank is left the tables are all-gathered (16 x world
     elements) and the last log2(world) rounds run replicated.  Every rank returns what `prove_helper` returns."""
-    global _SHARD
     p = fields.MODULUS[fid]
     assert world & (world - 1) == 0
     engines = (mem, inner, witness)
@@ -577,13 +579,17 @@ def prove_helper_sharded(fid, mem, inner, witness, transcript, rank: int, world:
     coeffs = [pow(s, i, p) for i in range(len(claims))]
     e = sum(c * k for c, k in zip(claims, coeffs)) % p
     rs, polys = [], []
-    sums = RoundSums(fid)
-    _SHARD = Shard(rank, world, reduce) if world > 1 else None
+    shard = Shard(rank, world, reduce) if world > 1 else None
+    sums = RoundSums(fid, shard=shard)
+    for eng in engines:
+        eng.shard = shard
     try:
         for _ in range(n_rounds):
-            if _SHARD is not None and mem.size() == 1:
+            if shard is not None and mem.size() == 1:
                 replicate_tail()
-                _SHARD = None
+                shard = sums.shard = None
+                for eng in engines:
+                    eng.shard = None
             for eng in engines:
                 eng.enqueue(sums)
             res = sums.fetch()
@@ -601,7 +607,8 @@ def prove_helper_sharded(fid, mem, inner, witness, transcript, rank: int, world:
             e = poly.evaluate(r)
             polys.append(poly.compress())
     finally:
-        _SHARD = None
+        for eng in engines:
+            eng.shard = None
     return polys, rs, mem.final_claims(), inner.final_claims(), witness.final_claims()
 
 
