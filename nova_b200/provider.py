@@ -82,6 +82,14 @@ class CommitmentKey:
         self.bases, self.h = bases, h
 
     @classmethod
+    def from_handle(cls, curve: "Curve", handle: int, bases: bytes | None, h: bytes | None, n: int) -> "CommitmentKey":
+        """Wrap a key the library has already registered (e.g. through b200_ck_register_checked)."""
+        self = cls.__new__(cls)
+        self.curve, self.n, self.handle, self.has_h = Curve(curve), n, handle, h is not None
+        self.bases, self.h = bases, h
+        return self
+
+    @classmethod
     def setup_synthetic(cls, curve: "Curve", n: int, k0: int = 0x5EED, with_h: bool = False,
                         window_bits: int = 0) -> "CommitmentKey":
         """Test/bench key bases[i] = (k0+i)*G built on the device (cf. hyperkzg.rs:357-376)."""

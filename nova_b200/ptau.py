@@ -338,9 +338,7 @@ def load_setup(reader, h: bytes | None, n: int, window_bits: int = 0) -> Commitm
             raise PointNotOnCurve("the blinding generator h is not a valid point")
         raise _classify_bad_g1(curve, g1, bad.value)
     check(rc)
-    ck = CommitmentKey.__new__(CommitmentKey)
-    ck.curve, ck.n, ck.handle, ck.has_h = curve, num, handle.value, h is not None
-    ck.bases, ck.h = g1, h
+    ck = CommitmentKey.from_handle(curve, handle.value, g1, h, num)
     try:
         _check_g2(g2, 2)
     except PtauFileError:
@@ -379,9 +377,7 @@ def load_setup_sharded(reader, h: bytes | None, n: int, rank: int, world: int, g
     verdict, kind = NONE, 0  # kind: 1 = PointNotOnCurve, 2 = non-canonical (io error), 3 = the blinding generator
     ck, lib_error = None, ""
     if rc == 0:
-        ck = CommitmentKey.__new__(CommitmentKey)
-        ck.curve, ck.n, ck.handle, ck.has_h = curve, hi - lo, handle.value, my_h is not None
-        ck.bases, ck.h = g1, my_h
+        ck = CommitmentKey.from_handle(curve, handle.value, g1, my_h, hi - lo)
     elif rc == B200_E_POINT:
         if my_h and bad.value == hi - lo:
             verdict, kind = num, 3  # after every G1 point, as in the unsharded order
@@ -476,10 +472,7 @@ def pedersen_load_setup(reader, n: int, curve: Curve, window_bits: int = 0) -> C
         e = _classify_bad_g1(curve, bases, min(bad.value, num - 1))
         raise type(e)(f"{e} [point {bad.value + 1} of the file]")
     check(rc)
-    ck = CommitmentKey.__new__(CommitmentKey)
-    ck.curve, ck.n, ck.handle, ck.has_h = curve, num, handle.value, True
-    ck.bases, ck.h = bases, h
-    return ck
+    return CommitmentKey.from_handle(curve, handle.value, bases, h, num)
 
 
 def pedersen_save_setup(ck: CommitmentKey, writer) -> None:
