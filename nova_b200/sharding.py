@@ -50,7 +50,7 @@ def all_gather_bytes(b: bytes, group=None) -> list:
 
 
 def sharded_prove_cubic_with_three_inputs(engine, p: int, claim: int, taus: list, A, B, C, transcript,
-                                          rank: int, world: int, group=None):
+                                          rank: int, world: int, group=None, gather=None):
     """`SumcheckProof::prove_cubic_with_three_inputs` (src/spartan/sumcheck.rs:446-507) with the three
     tables sharded cyclically over `world` ranks.
 
@@ -63,7 +63,11 @@ def sharded_prove_cubic_with_three_inputs(engine, p: int, claim: int, taus: list
     no exchange because (i, i + len/2) are co-resident under the cyclic layout.  When one element per
     rank is left, the `world` values are all-gathered and the last log2(world) rounds run replicated.
     Every rank returns the same (compressed polys, challenges, final evaluations).
+    `gather(bytes) -> list of every rank's bytes` replaces the default host all-gather (e.g. NcclComm.gather_bytes
+    when the process group is NCCL, which takes no CPU tensors).
     """
+    if gather is None:
+        gather = lambda b: all_gather_bytes(b, group)
     from .spartan import UniPoly  # O(1) host algebra shared with the single-GPU prover
 
     l = len(taus)
@@ -78,7 +82,7 @@ def sharded_prove_cubic_with_three_inputs(engine, p: int, claim: int, taus: list
     for rnd in range(1, l + 1):
         if local_len == 1 and id_mul > 1:
             # global length == world: replicate the tail on every rank
-            parts = [all_gather_bytes(engine.download(h, 1), group) for h in (A, B, C)]
+            parts = [gather(engine.download(h, 1)) for h in (A, B, C)]
             A, B, C = (engine.upload(b"".join(pp)) for pp in parts)
             local_len, id_mul, id_add = world, 1, 0
         left, right, shift = eq.tables(rnd)
@@ -88,7 +92,7 @@ def sharded_prove_cubic_with_three_inputs(engine, p: int, claim: int, taus: list
             if id_mul == 1:
                 return vals
             raw = b"".join(int(v).to_bytes(32, "little") for v in vals)
-            allv = all_gather_bytes(raw, group)
+            allv = gather(raw)
             return [sum(int.from_bytes(x[32 * k:32 * k + 32], "little") for x in allv) % p
                     for k in range(len(vals))]
 
