@@ -304,6 +304,10 @@ int b200_eq_table_dev(int field_id, const void* r, int ell, void* out, void* str
 /* MultilinearPolynomial::evaluate_with (spartan/polys/multilinear.rs:98-127): out = Z(r) */
 int b200_mle_eval(int field_id, const void* Z, int ell, const void* r, void* out);
 int b200_mle_eval_dev(int field_id, const void* Z, int ell, const void* r, void* out, void* stream);
+/* MultilinearPolynomial::multi_evaluate_with (multilinear.rs:129-180): k polynomials of 2^ell entries at the
+ * same point; the two sqrt-sized eq tables are built once, out receives k values (device pointers). */
+int b200_mle_eval_multi_dev(int field_id, const void* const* d_Zs, size_t k, int ell, const void* d_r,
+                            void* d_out, void* stream);
 /* batch_invert (spartan/mod.rs:54-145); B200_E_ZERO if an element is zero */
 int b200_batch_invert(int field_id, const void* in, size_t n, void* out);
 int b200_batch_invert_dev(int field_id, const void* in, size_t n, void* out, int* d_zero_flag,

@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200_eq_table_dev": [c_int, _P, c_int, _P, _P],
     "b200_mle_eval": [c_int, _P, c_int, _P, _P],
     "b200_mle_eval_dev": [c_int, _P, c_int, _P, _P, _P],
+    "b200_mle_eval_multi_dev": [c_int, _P, c_size_t, c_int, _P, _P, _P],
     "b200_batch_invert": [c_int, _P, c_size_t, _P],
     "b200_batch_invert_dev": [c_int, _P, c_size_t, _P, _P, _P],
     "b200_rlc": [c_int, ctypes.POINTER(_P), ctypes.POINTER(c_size_t), c_size_t, _P, c_size_t, _P],

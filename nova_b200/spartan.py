@@ -255,6 +255,18 @@ def _challenge_dev(fid: int, r_int: int) -> "DeviceVec":
     return rdev
 
 
+def mle_eval_multi_dev(fid: int, vecs: list, ell: int, r_dev: "DeviceVec") -> list:
+    """MultilinearPolynomial::multi_evaluate_with (multilinear.rs:129-180) on device-resident polynomials of
+    2^ell entries: one pair of sqrt-sized eq tables for all of them, one read-back of the k values."""
+    k = len(vecs)
+    if k == 0:
+        return []
+    ptrs = (ctypes.c_void_p * k)(*[v.ptr.value for v in vecs])
+    out = DeviceVec(32 * k)
+    check(lib().b200_mle_eval_multi_dev(fid, ptrs, k, ell, r_dev.ptr, out.ptr, None))
+    return fields.unpack(fid, out.to_bytes(32 * k))
+
+
 def commit_many_dev(curve, ck: CommitmentKey, vecs: list, lens: list) -> list:
     """CE::batch_commit with r = 0 on device-resident vectors (b200_commit_many_dev: the MSMs are
     spread over the key's lanes so short ones overlap) -> affine points / None."""

@@ -128,6 +128,11 @@ class EmulatedDevice:
         _wr(out, co.mle_eval(fid, _rd(Z, 32 << ell), _rd(r, 32 * ell)))
         return 0
 
+    def b200_mle_eval_multi_dev(self, fid, ptrs, k, ell, r, out, stream):
+        rr = _rd(r, 32 * ell)
+        _wr(out, b"".join(co.mle_eval(fid, _rd(ptrs[j], 32 << ell), rr) for j in range(k)))
+        return 0
+
     def b200_rlc_dev(self, fid, ptrs, lens, k, coeffs, n, out, stream):
         polys = [_rd(ptrs[i], 32 * lens[i]) for i in range(k)]
         _wr(out, co.rlc(fid, polys, _rd(coeffs, 32 * k), n))

@@ -42,3 +42,10 @@ def test_ipa_prover_host_logic(emulated, oracle, cid, l):
     """nova_b200/ipa.py (the prover that never folds the key) on the emulated device: body of tests/test_ipa_gpu.py."""
     import test_ipa_gpu
     test_ipa_gpu.test_ipa_prove_matches_restatement(emulated, oracle, cid, l)
+
+
+@pytest.mark.parametrize("fid", [0, 3])
+def test_multi_evaluate_with_host_logic(emulated, oracle, fid):
+    import mle_multi_parity
+    from nova_b200 import spartan
+    mle_multi_parity.run(spartan, fid)

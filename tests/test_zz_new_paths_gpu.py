@@ -428,3 +428,11 @@ def test_sharded_batched_sumcheck_two_ranks_on_device(tmp_path):
     for all nine sums, one exchange per round, replicated tail.  CPU twin: tests/test_ppsnark_sharded.py."""
     import test_ppsnark_sharded
     test_ppsnark_sharded.run_world(2, "gpu", tmp_path)
+
+
+@pytest.mark.parametrize("fid", [0, 3])
+def test_multi_evaluate_with_on_device(sp, fid):
+    """b200_mle_eval_multi_dev (multi_evaluate_with, multilinear.rs:129-180) with the reference's test cases incl.
+    the known values; CPU twin: tests/test_spartan_mirror_cpu.py."""
+    import mle_multi_parity
+    mle_multi_parity.run(sp, fid)
