@@ -31,6 +31,17 @@ def test_library_exports_every_declared_symbol():
         assert s in SIGNATURES or s in STRING_FUNCS, f"{s} has no ctypes signature in nova_b200/native.py"
 
 
+def test_variant_libraries_are_not_stale():
+    """A/B builds of the library (nova_b200/libnova_b200_<variant>.so, selected with NOVA_B200_LIB) that are lying
+    around must export the current ABI: a variant built before an entry point was added would fail at load time
+    on the GPU box."""
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "nova_b200", "libnova_b200_*.so")):
+        L = ctypes.CDLL(path)
+        missing = [s for s in declared_symbols() if not hasattr(L, s)]
+        assert not missing, f"{os.path.basename(path)} is stale (rebuild: make -C nova_b200/csrc variant ...): {missing}"
+
+
 def test_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
