@@ -379,7 +379,7 @@ NOVA_HD void mad_cs(uint32_t& lo, uint32_t& hi, uint32_t& k, uint32_t x, uint32_
 // k_next += carry32(e + o) + kz   (kz in {0,1})
 NOVA_HD void retire_cs(uint32_t& k_next, uint32_t e, uint32_t o, uint32_t kz) {
 #ifdef __CUDA_ARCH__
-  uint32_t t;
+  [[maybe_unused]] uint32_t t;  // scratch of the add.cc; only its carry is used
   asm("add.cc.u32 %1, %2, %3;\n\t"
       "addc.u32 %0, %0, %4;"
       : "+r"(k_next), "=r"(t)
