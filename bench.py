@@ -40,6 +40,14 @@ UNIT = "pairs/s"
 ALG_BYTES_PER_PAIR = 96  # 32 B scalar + 64 B affine base, each read once
 
 
+def msm_config(log2n):
+    """The workload description, identical in both arms (the driver compares the dicts)."""
+    return {"workload": f"BN254 G1 Pippenger MSM, 2^{log2n} uniform scalars, resident key (BASELINE.json configs[1])",
+            "log2n": log2n, "pairs_per_step": 1 << log2n,
+            "l2": "GPU arm: working set (window tables 64*15*n B + sort buffers) >> 126 MB L2, no flush needed; "
+                  "CPU arm: 96 MiB of inputs >> host caches"}
+
+
 def synth_scalars(n, seed):
     """n x 32 B little-endian values uniform in [0, 2^253): every 32-byte string below the
     modulus is the Montgomery representation of exactly one field element, so this is a
@@ -264,6 +272,13 @@ def run_b200(args):
     e2e_ms_per_step = float(t.item()) / args.steps
     check(L.b200_host_free(h_ptr))
 
+    # ---------------- the timed results are CHECKED (outside every timed region) -------------------
+    # bases are P_i = (K0 + i) G, so the MSM must equal [sum_i s_i (K0 + i)] G: one scalar-mul on the oracle side
+    result_check = None
+    if rank == 0:
+        result_check = closed_form_check(args.log2n, (d_out if world > 1 else d_part).cpu().numpy().tobytes(),
+                                         out_host.raw if world == 1 else h_pinned_t.numpy().tobytes())
+
     # ---------------- the same sharded MSM at the other sizes north_star names -------------------
     other_sizes = [time_other_size(lg, steps=5, warmup=3) for lg in args.other_log2n if lg != args.log2n]
 
@@ -309,28 +324,23 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_run(args.log2n, steps=2, warmup=1, sc_np=sc_np)
 
-    # ---------------- secondary metric of BASELINE.json: prove_step (kernel-sequence replay) -----
-    prove_step = None
+    # ---------------- the prover workloads of BASELINE.json configs[2..4], each timed AND checked -----
+    # (tools/workloads.py: prove_step replay vs the C oracle, HyperKZG 2^22 and ppsnark 2^18 proofs accepted by the
+    #  restated verifiers).  `bench.py --workload X --gpus N` runs one of them alone, also over N GPUs.
+    workloads_out = {}
     if world == 1 and not args.no_prove_step:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import prove_step_replay as psr
         ck.release()
         del d_sc
         torch.cuda.empty_cache()
-        prove_step = psr.gpu_replay(steps=5, warmup=2)
-        if not args.no_cpu_baseline:
-            prove_step["cpu_baseline"] = psr.cpu_replay(steps=1)
-
-    # ---------------- the two SNARK provers of BASELINE.json configs[3], configs[4] (replays) -----
-    snark_replays = {}
-    if world == 1 and not args.no_prove_step:
-        for name, mod, kw in (("hyperkzg_prove_2p22", "hyperkzg_replay", {"log2n": 22, "reps": 2}),
-                              ("ppsnark_prove_core_2p18", "ppsnark_replay", {"log2cons": 18, "reps": 2})):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import workloads as wl
+        for name, fn in (("prove_step", lambda: wl.prove_step(steps=5, warmup=2, check_parity=not args.no_cpu_baseline)),
+                         ("hyperkzg_prove_2p22", lambda: wl.hyperkzg(log2n=22, steps=2, warmup=1)),
+                         ("ppsnark_prove_2p18", lambda: wl.ppsnark(log2cons=18, steps=2, warmup=1))):
             try:
-                m = __import__(mod)
-                snark_replays[name] = m.gpu(**kw) if hasattr(m, "gpu") else m.run(**kw)
+                workloads_out[name] = fn()
             except Exception as e:  # never let a side measurement take the headline down
-                snark_replays[name] = {"error": f"{type(e).__name__}: {e}"}
+                workloads_out[name] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
 
     out = {
@@ -338,10 +348,8 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit prime-field / curve integers)",
         "data": "synthetic",
-        "config": {"workload": f"BN254 G1 Pippenger MSM, 2^{args.log2n} uniform scalars, resident key "
-                               f"(BASELINE.json configs[1])",
-                   "log2n": args.log2n, "pairs_per_step": n_total, "sharding": f"index-range x{world}",
-                   "l2": "working set (window tables 64*16*n B + sort buffers) >> 126 MB L2; no flush needed"},
+        "config": msm_config(args.log2n),
+        "sharding": f"index-range x{world}",
         "clocks": clocks,
         "e2e": {"value": n_total / (e2e_ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_per_step,
                 "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
@@ -350,13 +358,30 @@ def run_b200(args):
         "gpu_launches": int(launches.value),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "prove_step_replay": prove_step,
+        "result_check": result_check,
+        "parity_checked": bool(result_check and result_check["ok"]),
         "other_sizes": other_sizes,
-        "snark_replays": snark_replays,
+        "workloads": workloads_out,
     }
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def closed_form_check(log2n, device_result_jac, e2e_result_jac):
+    """Checker (oracle side): expected = [sum_i s_i (K0 + i) mod r] G for the bench's scalars."""
+    from nova_b200.provider import Curve, _jac_to_affine
+    from oracle import coracle as co
+    from oracle.pyref import CURVES
+    c = CURVES[CURVE]
+    sc = synth_scalars(1 << log2n, seed=2).tobytes()
+    k = co.dot_index(SCALAR_FIELD, sc, K0)
+    exp = c.affine_from_bytes(co.scalar_mul(CURVE, c.affine_bytes(c.gen), k))
+    got_dev = _jac_to_affine(Curve(CURVE), device_result_jac)
+    got_e2e = _jac_to_affine(Curve(CURVE), e2e_result_jac)
+    return {"device_result_equals_closed_form": bool(got_dev == exp), "e2e_result_equals_closed_form": bool(got_e2e == exp),
+            "ok": bool(got_dev == exp and got_e2e == exp),
+            "checker": "oracle: [sum_i s_i (k0+i)] G by one scalar multiplication (bases are (k0+i) G)"}
 
 
 def effective_cores():
@@ -417,12 +442,114 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64 limbs (256-bit prime-field / curve integers)",
         "data": "synthetic",
-        "config": {"workload": f"BN254 G1 Pippenger MSM, 2^{args.log2n} uniform scalars, resident key "
-                               f"(BASELINE.json configs[1])", "log2n": args.log2n, "sample": n_sample},
+        "config": msm_config(args.log2n),
+        "sample": n_sample,
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
+
+
+WORKLOAD_METRICS = {
+    "hyperkzg": ("HyperKZG EvaluationEngine::prove time (BN254, BASELINE.json configs[3])", "ms"),
+    "ppsnark": ("ppsnark RelaxedR1CSSNARK::prove time (BN254, BASELINE.json configs[4])", "ms"),
+    "prove_step": ("RecursiveSNARK::prove_step kernel-sequence time (BN254/Grumpkin, BASELINE.json configs[2])", "ms"),
+}
+
+
+def workload_config(args):
+    if args.workload == "hyperkzg":
+        return {"workload": f"HyperKZG prove, 2^{args.log2n} uniform BN254 scalars", "log2n": args.log2n}
+    if args.workload == "ppsnark":
+        return {"workload": f"ppsnark prove, sha256-like synthetic shape, 2^{args.log2cons} constraints",
+                "log2cons": args.log2cons}
+    return {"workload": "prove_step kernel-sequence replay, MinRoot-sized shapes (2.07e5 / 1.05e4 constraints)"}
+
+
+def run_workload(args):
+    """bench.py --workload {hyperkzg, ppsnark, prove_step} [--gpus N]: one prover workload of BASELINE.json
+    configs[2..4], timed and then checked by the restated verifier / the C oracle (tools/workloads.py)."""
+    import torch
+    import torch.distributed as dist
+
+    from nova_b200.native import check, lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    L = lib()
+    check(L.b200_init(local_rank))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import workloads as wl
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.mark()
+    check(L.b200_profile_reset())
+    if args.workload == "hyperkzg":
+        res = wl.hyperkzg(log2n=args.log2n, steps=args.steps, warmup=args.warmup)
+        ms, e2e_ms = res["ms_per_proof"], res["e2e_ms_per_proof"]
+        h2d, d2h = res["h2d_bytes_per_proof"] // world, res["d2h_bytes_per_proof"]
+    elif args.workload == "ppsnark":
+        if world > 1:
+            raise SystemExit("--workload ppsnark runs on one GPU (its multi-GPU pieces are covered by tests/test_ppsnark_sharded.py)")
+        res = wl.ppsnark(log2cons=args.log2cons, steps=args.steps, warmup=args.warmup)
+        ms = e2e_ms = res["ms_per_proof"]
+        h2d, d2h = 0, 0
+    else:
+        if world > 1:
+            raise SystemExit("--workload prove_step runs on one GPU (BASELINE.json configs[2]: 1xB200)")
+        res = wl.prove_step(steps=args.steps, warmup=args.warmup)
+        ms = e2e_ms = res["ms_per_step"]
+        h2d, d2h = res["h2d_bytes_per_step"], res["d2h_bytes_per_step"]
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctypes.c_uint64(0)
+    check(L.b200_profile_read(None, 0, None, ctypes.byref(launches)))
+    if rank == 0:
+        metric, unit = WORKLOAD_METRICS[args.workload]
+        print(json.dumps({
+            "metric": metric, "value": ms, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (256-bit prime-field / curve integers)", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": e2e_ms, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches.value), "parity_checked": res["parity_checked"], "detail": res}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_workload_reference(args):
+    """--impl reference --workload X: the same op sequence through the C restatement on the host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    metric, unit = WORKLOAD_METRICS[args.workload]
+    base = {"impl": "reference", "metric": metric, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 limbs (256-bit prime-field / curve integers)", "data": "synthetic",
+            "config": workload_config(args)}
+    if args.workload == "hyperkzg":
+        import hyperkzg_replay
+        lg = min(args.log2n, 20)  # bounded sample: the 2^20 prover takes ~3 s on 16 cores; scaled linearly above
+        cb = hyperkzg_replay.cpu(lg)
+        v = cb["ms"]["total"] * (1 << (args.log2n - lg))
+        cb = {"value": v, "unit": unit, "cores": cb["cores"], "kind": "port",
+              "sample": f"whole prover at 2^{lg}, scaled x{1 << (args.log2n - lg)} to 2^{args.log2n}", "phases_ms": cb["ms"]}
+    elif args.workload == "prove_step":
+        import prove_step_replay as psr
+        r = psr.cpu_replay(steps=max(1, min(args.steps, 3)))
+        v = r["ms_per_step"]
+        cb = {"value": v, "unit": unit, "cores": r["cores"], "kind": "port", "sample": "the full step"}
+    else:
+        print(json.dumps(dict(base, unavailable="the whole-prover CPU restatement of ppsnark is Python big-integer code "
+                                                "(oracle/ppsnark_ref.py, the parity checker): not a timing baseline")))
+        return
+    print(json.dumps(dict(base, value=v, ms_per_step=v, cpu_baseline=cb,
+                          e2e={"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})))
 
 
 def main():
@@ -435,12 +562,21 @@ def main():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--other-log2n", type=lambda v: [int(x) for x in v.split(",") if x], default=[22, 24],
                     help="also time the sharded MSM at these total sizes (reported under other_sizes)")
+    ap.add_argument("--workload", default="msm", choices=["msm", "hyperkzg", "ppsnark", "prove_step"],
+                    help="msm = the headline (BASELINE.json configs[1]); the others time AND check one prover workload")
+    ap.add_argument("--log2cons", type=int, default=18, help="--workload ppsnark: log2 of the constraint count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prove-step", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload != "msm":
+        if args.workload == "hyperkzg" and "--log2n" not in sys.argv:
+            args.log2n = 22
+        if "--steps" not in sys.argv:
+            args.steps = 3
+        (run_workload_reference if args.impl == "reference" else run_workload)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

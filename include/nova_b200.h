@@ -97,6 +97,15 @@ int b200_ck_register_checked(int curve_id, const void* bases_affine_mont, size_t
  * with_h != 0 appends h = (k0 + n) * G as the blinding generator. */
 int b200_ck_setup_synthetic(int curve_id, const void* generator_affine_mont, uint64_t k0, size_t n,
                             int with_h, int window_bits, uint64_t* ck_handle);
+/* test/bench SRS: bases[i] = [tau^i] G generated on the device -- the reference's test-only KZG setup
+ * (hyperkzg.rs:357-376 `setup_from_rng`: powers of a sampled tau).  A prover run at benchmark scale over such a
+ * key can be checked by the restated verifier with the pairing replaced by L = [tau] R (oracle/hyperkzg_ref.py). */
+int b200_ck_setup_tau(int curve_id, const void* generator_affine_mont, const void* tau_mont, size_t n,
+                      int window_bits, uint64_t* ck_handle);
+/* copies ck[offset .. offset + n) (affine, Montgomery: the layout b200_ck_register takes) back to host memory;
+ * what `CommitmentKey::ck()` (traits.rs / hyperkzg.rs:98-110) gives a Rust caller.  The tests hand a
+ * device-generated key to the CPU oracle with it. */
+int b200_ck_export_bases(uint64_t ck_handle, size_t offset, size_t n, void* out_host);
 int b200_ck_release(uint64_t ck_handle);
 int b200_ck_len(uint64_t ck_handle, size_t* n, int* window_bits, int* num_tables);
 

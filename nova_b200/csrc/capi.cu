@@ -641,6 +641,48 @@ int b200_ck_setup_synthetic(int curve_id, const void* gen_affine, uint64_t k0, s
   return B200_OK;
 }
 
+int b200_ck_setup_tau(int curve_id, const void* gen_affine, const void* tau_mont, size_t n, int window_bits,
+                      uint64_t* handle) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
+  if (!gen_affine || !tau_mont || !handle || n == 0) return fail(B200_E_ARG, "bad argument");
+  dev_buf bases, gen, tau, pw;
+  if ((rc = bases.alloc(n * 64)) || (rc = gen.alloc(64)) || (rc = tau.alloc(32)) || (rc = pw.alloc(n * 32))) return rc;
+  CU(cudaMemcpyAsync(gen.p, gen_affine, 64, cudaMemcpyHostToDevice, g_dev.stream));
+  CU(cudaMemcpyAsync(tau.p, tau_mont, 32, cudaMemcpyHostToDevice, g_dev.stream));
+  ops_for_field(CURVES[curve_id].scalar_fid)->powers_canonical(g_dev.stream, tau.p, n, pw.p);
+  ops_for_field(CURVES[curve_id].base_fid)->scalar_bases(g_dev.stream, bases.p, n, gen.p, pw.p);
+  count_launch(2);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(g_dev.stream));
+  std::shared_ptr<ck_ctx> ck;
+  rc = register_key(curve_id, bases.p, true, n, nullptr, window_bits, true, ck);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_handles_mu);
+  *handle = g_next_handle++;
+  g_handles[*handle] = ck;
+  return B200_OK;
+}
+
+int b200_ck_export_bases(uint64_t handle, size_t offset, size_t n, void* out_host) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (offset + n > ck->n) return fail(B200_E_RANGE, "export [%zu, %zu) exceeds key length %zu", offset, offset + n, ck->n);
+  if (n == 0) return B200_OK;
+  if (!out_host) return fail(B200_E_ARG, "null pointer");
+#if defined(NOVA_MSM_ARITH29)
+  return fail(B200_E_ARG, "b200_ck_export_bases: table 0 is not in the boundary format in this build");
+#else
+  std::lock_guard<std::mutex> lk(ck->mu);
+  CU(cudaMemcpyAsync(out_host, (const char*)ck->tables + offset * 64, n * 64, cudaMemcpyDeviceToHost, g_dev.stream));
+  CU(cudaStreamSynchronize(g_dev.stream));
+  return B200_OK;
+#endif
+}
+
 int b200_ck_release(uint64_t handle) {
   std::shared_ptr<ck_ctx> ck;
   {

@@ -108,9 +108,11 @@ NOVA_HD void xyzz_madd(xyzz_t& acc, const fe_t& px, const fe_t& py) {
   fe_t ppp = fe_mul<F>(p, pp);
   fe_t q = fe_mul<F>(acc.x, pp);
   fe_t x3 = fe_sub<F>(fe_sub<F>(fe_sqr<F>(r), ppp), fe_dbl<F>(q));
-#if defined(NOVA_MADD_FUSED_Y3)
+#if !defined(NOVA_MADD_SPLIT_Y3)
   // y3 = r (q - x3) + (-y1) ppp as ONE sum-of-products reduction (fe_mul2_add): 192 instead of
-  // 256 wide products, -5 % of the mixed addition.  A/B build: make variant VFLAGS=-DNOVA_MADD_FUSED_Y3
+  // 256 wide products, -5 % of the mixed addition.  Measured on B200 (profiles/r02a_variants.md): k_accumulate
+  // 2.627 -> 2.486 ms at 2^20, 9.08 -> 8.60 ms at 2^22; the two-product form stays buildable with
+  // -DNOVA_MADD_SPLIT_Y3 (make variant VARIANT=split VFLAGS=-DNOVA_MADD_SPLIT_Y3).
   fe_t y3 = fe_mul2_add<F>(r, fe_sub<F>(q, x3), fe_neg<F>(acc.y), ppp);
 #else
   fe_t y3 = fe_sub<F>(fe_mul<F>(r, fe_sub<F>(q, x3)), fe_mul<F>(acc.y, ppp));

@@ -698,6 +698,35 @@ __global__ void __launch_bounds__(128) k_index_bases(void* __restrict__ bases, s
   fe_store(bases, 2 * i + 1, y);
 }
 
+// Test/bench SRS: bases[i] = [s_i] G for canonical (non-Montgomery) 256-bit scalars s_i, affine.  With
+// s_i = tau^i this is the reference's test-only KZG setup (hyperkzg.rs:357-376 `setup_from_rng`:
+// powers of a sampled tau times the generator), which lets a bench-scale proof be checked by the
+// restated verifier with the pairing replaced by L = [tau] R.  254 doublings + ~127 mixed adds +
+// one inversion per point; a 2^22-point key costs ~0.3 s.
+template <class F>
+__global__ void __launch_bounds__(128) k_scalar_bases(void* __restrict__ bases, size_t n,
+                                                      const void* __restrict__ gen,
+                                                      const void* __restrict__ scalars) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_t gx = fe_load(gen, 0), gy = fe_load(gen, 1);
+  fe_t k = fe_load(scalars, i);
+  xyzz_t acc = xyzz_identity<F>();
+  for (int b = 255; b >= 0; b--) {
+    xyzz_dbl<F>(acc);
+    if ((k.l[b >> 5] >> (b & 31)) & 1u) xyzz_madd<F>(acc, gx, gy);
+  }
+  fe_t x = fe_zero<F>(), y = fe_zero<F>();
+  if (!xyzz_is_identity(acc)) {
+    fe_t iz3 = fe_inv<F>(acc.zzz);
+    fe_t iz2 = fe_mul<F>(fe_sqr<F>(acc.zz), fe_sqr<F>(iz3));
+    x = fe_mul<F>(acc.x, iz2);
+    y = fe_mul<F>(acc.y, iz3);
+  }
+  fe_store(bases, 2 * i, x);
+  fe_store(bases, 2 * i + 1, y);
+}
+
 // ------------------------------------------------------------------------------------------
 // key expansion:  tables[t][i] = 2^(shift*t) * bases[i]  (affine; identity stays (0,0))
 // ------------------------------------------------------------------------------------------

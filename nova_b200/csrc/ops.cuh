@@ -80,6 +80,9 @@ struct field_ops {
                            uint32_t pending_len, int absorb_label, int squeeze_label, void* out_poly, void* out_r);
   // key validation: *first_bad = min index of an off-curve base (caller presets 0xFFFFFFFF)
   void (*on_curve)(cudaStream_t, const void* pts, size_t n, int b_small, uint32_t* first_bad);
+  // test SRS (hyperkzg.rs:357-376): out[i] = u^i canonical (scalar field) ; bases[i] = [scalars[i]] G (base field)
+  void (*powers_canonical)(cudaStream_t, const void* u_mont, size_t n, void* out);
+  void (*scalar_bases)(cudaStream_t, void* bases, size_t n, const void* gen_affine, const void* scalars_canonical);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
 // NOVA_B200_SC_SEG=1 selects the segmented reduction of the eq-weighted sum-check forms (k_form_reduce_eqseg)

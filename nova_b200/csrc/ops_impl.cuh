@@ -314,12 +314,19 @@ struct ops_impl {
   static void on_curve(cudaStream_t s, const void* pts, size_t n, int b_small, uint32_t* first_bad) {
     if (n) k_on_curve<F><<<stream_grid(n, 256), 256, 0, s>>>(pts, n, b_small, first_bad);
   }
+  static void powers_canonical(cudaStream_t s, const void* u, size_t n, void* out) {
+    if (n) k_powers_canonical<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(u, n, out);
+  }
+  static void scalar_bases(cudaStream_t s, void* bases, size_t n, const void* gen, const void* scalars) {
+    if (n) k_scalar_bases<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(bases, n, gen, scalars);
+  }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, vec_mul, logup_hash,
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
-                     sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve};
+                     sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve,
+                     powers_canonical, scalar_bases};
   }
 };
 

@@ -494,6 +494,16 @@ __global__ void k_fe_pow(const void* __restrict__ u, uint64_t e, void* __restric
   if (blockIdx.x == 0 && threadIdx.x == 0) fe_store(out, 0, fe_pow_u64<F>(fe_load(u, 0), e));
 }
 
+// out[i] = u^i as a CANONICAL integer (not Montgomery), i < n: the scalars of the test SRS [tau^i] G
+// (k_scalar_bases in msm_kernels.cuh; hyperkzg.rs:357-376)
+template <class F>
+__global__ void __launch_bounds__(128) k_powers_canonical(const void* __restrict__ u, size_t n,
+                                                          void* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_store(out, i, fe_from_mont<F>(fe_pow_u64<F>(fe_load(u, 0), (uint64_t)i)));
+}
+
 // quotient by (X - u): h[k-1] = B[k] + u*h[k], h[n-1] := 0  (hyperkzg.rs:961-999); chunk c starts
 // from the carry H_c computed above.  out[k] = h[k] for k < out_len (n-1 for the quotient; n when the
 // same recurrence is reused one level up to spread carries over the level-1 chunks).

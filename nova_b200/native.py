@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200_ck_register": [c_int, _P, c_size_t, _P, c_int, ctypes.POINTER(c_u64)],
     "b200_ck_register_checked": [c_int, _P, c_size_t, _P, c_int, ctypes.POINTER(c_u64), ctypes.POINTER(c_size_t)],
     "b200_ck_setup_synthetic": [c_int, _P, c_u64, c_size_t, c_int, c_int, ctypes.POINTER(c_u64)],
+    "b200_ck_setup_tau": [c_int, _P, _P, c_size_t, c_int, ctypes.POINTER(c_u64)],
+    "b200_ck_export_bases": [c_u64, c_size_t, c_size_t, _P],
     "b200_ck_release": [c_u64],
     "b200_ck_len": [c_u64, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
     "b200_msm": [c_u64, c_size_t, _P, c_size_t, _P],

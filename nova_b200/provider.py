@@ -107,6 +107,29 @@ class CommitmentKey:
         self.bases, self.h = None, None  # built on the device: no host copy
         return self
 
+    @classmethod
+    def setup_tau(cls, curve: "Curve", n: int, tau: int, window_bits: int = 0) -> "CommitmentKey":
+        """Test/bench SRS ck[i] = [tau^i] G built on the device (hyperkzg.rs:357-376 `setup_from_rng`)."""
+        self = cls.__new__(cls)
+        self.curve = Curve(curve)
+        self.n, self.has_h = n, False
+        gen = GENERATORS[int(curve)]
+        fid = self.curve.base_field
+        g = fields.to_mont_bytes(fid, gen[0]) + fields.to_mont_bytes(fid, gen[1])
+        handle = c_u64(0)
+        check(lib().b200_ck_setup_tau(int(curve), _cbuf(g), _cbuf(fields.to_mont_bytes(self.curve.scalar_field, tau)),
+                                      n, window_bits, ctypes.byref(handle)))
+        self.handle = handle.value
+        self.bases, self.h = None, None
+        return self
+
+    def export_bases(self, offset: int = 0, n: int | None = None) -> bytes:
+        """ck[offset .. offset + n) as affine Montgomery bytes (the layout `CommitmentKey(curve, bases)` takes)."""
+        n = self.n - offset if n is None else n
+        out = ctypes.create_string_buffer(64 * n)
+        check(lib().b200_ck_export_bases(self.handle, offset, n, out))
+        return out.raw
+
     @staticmethod
     def validate(curve: "Curve", bases: bytes):
         """CommitmentKey::new's on-curve loop (hyperkzg.rs:113-119) on the device: returns None if

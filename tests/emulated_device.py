@@ -73,6 +73,12 @@ class EmulatedDevice:
             self.graveyard.append(buf)  # keep the pages mapped so that such a read cannot crash the test run
         return 0
 
+    def b200_host_alloc(self, nbytes, out_ptr):
+        return self.b200_dev_alloc(nbytes, out_ptr)
+
+    def b200_host_free(self, p):
+        return self.b200_dev_free(p)
+
     def b200_memcpy_h2d(self, d, h, n):
         _wr(d, _rd(h, n))
         return 0
@@ -408,6 +414,22 @@ class EmulatedDevice:
         self.keys[self.next_handle] = (curve_id, bases[:64 * n], bases[64 * n:] if with_h else None)
         out_handle._obj.value = self.next_handle
         self.next_handle += 1
+        return 0
+
+    def b200_ck_setup_tau(self, curve_id, gen, tau_mont, n, window_bits, out_handle):
+        from oracle import hyperkzg_ref as hk
+        c = CURVES[curve_id]
+        tau = from_mont_bytes(c.q, _rd(tau_mont, 32))
+        self.keys[self.next_handle] = (curve_id, hk.setup_srs(curve_id, n, tau), None)  # ck[i] = [tau^i] G
+        out_handle._obj.value = self.next_handle
+        self.next_handle += 1
+        return 0
+
+    def b200_ck_export_bases(self, handle, offset, n, out):
+        _, bases, _ = self.keys[handle]
+        if 64 * (offset + n) > len(bases):
+            return 5
+        _wr(out, bases[64 * offset:64 * (offset + n)])
         return 0
 
     def b200_ck_release(self, handle):

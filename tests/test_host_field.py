@@ -60,20 +60,20 @@ def test_field_ops(hc, fid):
 
 @pytest.fixture(scope="module")
 def hc_y3():
-    """The same host build with the fused-y3 mixed addition the A/B kernel variant uses
-    (-DNOVA_MADD_FUSED_Y3: y3 through fe_mul2_add)."""
+    """The same host build with the OTHER form of y3 in the mixed addition (two products, two reductions:
+    -DNOVA_MADD_SPLIT_Y3); the default build computes y3 through fe_mul2_add (one reduction)."""
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-    so = os.path.join(HERE, "hostcheck", "libhostcheck_y3.so")
+    so = os.path.join(HERE, "hostcheck", "libhostcheck_splity3.so")
     csrc = os.path.join(HERE, "..", "nova_b200", "csrc")
     hdrs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-DNOVA_MADD_FUSED_Y3", "-x", "c++",
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-DNOVA_MADD_SPLIT_Y3", "-x", "c++",
                                src, "-o", so])
     return ctypes.CDLL(so)
 
 
 @pytest.mark.parametrize("cid", [0, 1, 2, 3])
-def test_xyzz_formulas_fused_y3(hc_y3, cid):
+def test_xyzz_formulas_split_y3(hc_y3, cid):
     _xyzz_formulas(hc_y3, cid)
     # a long random walk of mixed additions: 3000 points, compared with the affine group law
     c = CURVES[cid]

@@ -63,3 +63,20 @@ def test_sharded_hyperkzg_replay_prints_the_single_gpu_digest(emulated, oracle):
     a = hyperkzg_sharded_replay.main(["--log2n", "6", "--reps", "1", "--comm", "host"])
     b = hyperkzg_replay.gpu(log2n=6, reps=1)
     assert a["digest"] == b["digest"] and a["n_gpus"] == 1
+
+
+def test_hyperkzg_workload_is_checked_by_the_verifier(emulated, oracle):
+    """tools/workloads.hyperkzg (bench.py --workload hyperkzg) at toy size on the emulated device: the proof is
+    accepted by the restated verifier for C, y computed by the oracle, a tampered one is rejected."""
+    import workloads
+    out = workloads.hyperkzg(log2n=5, steps=1, warmup=0)
+    assert out["parity_checked"] and out["parity"]["verifier_accepts"] and out["parity"]["verifier_rejects_tampered"]
+    assert out["ms_per_proof"] > 0 and out["e2e_ms_per_proof"] > 0
+
+
+@pytest.mark.parametrize("device_transcript", [False, True])
+def test_ppsnark_workload_is_checked_by_the_verifier(emulated, oracle, device_transcript):
+    import workloads
+    out = workloads.ppsnark(log2cons=4, steps=1, warmup=0, device_transcript=device_transcript)
+    assert out["parity_checked"], out["parity"]
+    assert out["parity"]["instance_commitments_equal_oracle"] and out["parity"]["verifier_rejects_tampered"]

@@ -75,7 +75,7 @@ def make_sides():
     return Side(1, 1, SECONDARY_CONS, 100), Side(0, 0, PRIMARY_CONS, 200)  # (Grumpkin/Fq, BN254/Fr)
 
 
-def gpu_replay(steps=5, warmup=2):
+def gpu_replay(steps=5, warmup=2, return_outputs=False):
     import torch
 
     import nova_b200 as nb
@@ -144,12 +144,26 @@ def gpu_replay(steps=5, warmup=2):
             step()
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / steps
-    return {"ms_per_step": ms, "primary_constraints": PRIMARY_CONS, "secondary_constraints": SECONDARY_CONS,
-            "ops_per_step": "4 MSM + 6 SpMV + 2 cross-term + 4 fold + 2 vec-add, fresh W uploaded, 4 commitments read back",
-            "excluded": "circuit synthesis, Poseidon RO, control flow (host side of the real prover)"}
+    res = {"ms_per_step": ms, "primary_constraints": PRIMARY_CONS, "secondary_constraints": SECONDARY_CONS,
+           "ops_per_step": "4 MSM + 6 SpMV + 2 cross-term + 4 fold + 2 vec-add, fresh W uploaded, 4 commitments read back",
+           "excluded": "circuit synthesis, Poseidon RO, control flow (host side of the real prover)",
+           "h2d_bytes_per_step": sum(32 * s.vars for s in sides), "d2h_bytes_per_step": 2 * 192}
+    if return_outputs:  # what the step produced, for the parity check against cpu_replay (tools/workloads.py)
+        import hashlib
+
+        from nova_b200.provider import Curve, _jac_to_affine
+        outs = {}
+        for s, d in zip(sides, st):
+            raw = bytes(d["comm"].cpu().numpy().tobytes())
+            outs[f"curve{s.curve}"] = {
+                "comm_W2": str(_jac_to_affine(Curve(s.curve), raw[:96])), "comm_T": str(_jac_to_affine(Curve(s.curve), raw[96:])),
+                "W_fold_sha256": hashlib.sha256(d["Wf"].cpu().numpy().tobytes()).hexdigest(),
+                "E_fold_sha256": hashlib.sha256(d["Ef"].cpu().numpy().tobytes()).hexdigest()}
+        res["outputs"] = outs
+    return res
 
 
-def cpu_replay(steps=1):
+def cpu_replay(steps=1, return_outputs=False):
     from oracle import coracle as co
     cores = os.cpu_count() or 1
     try:  # honour a cgroup CPU quota (the GPU boxes expose 128 CPUs with a 16-CPU quota)
@@ -169,12 +183,14 @@ def cpu_replay(steps=1):
         prep.append((bases, mats))
     B = lambda b: ctypes.create_string_buffer(bytes(b), len(b))
 
+    results = {}
+
     def step():
         for s, (bases, mats) in zip(sides, prep):
             W2, W1, E1 = s.W2.tobytes(), s.W1.tobytes(), s.E1.tobytes()
             Z1 = W1 + s.X1.tobytes()
             Z2 = W2 + s.X2.tobytes()
-            co.msm(s.curve, W2, bases[:64 * s.vars], cores)
+            cw = co.msm(s.curve, W2, bases[:64 * s.vars], cores)
             Z = ctypes.create_string_buffer(len(Z1))
             L.orc_vec_par(s.fid, 2, B(Z1), B(Z2), None, None, None, None, ctypes.c_size_t(s.zlen), Z, cores)
             outs = []
@@ -185,17 +201,26 @@ def cpu_replay(steps=1):
                 outs.append(o)
             T = ctypes.create_string_buffer(32 * s.cons)
             L.orc_vec_par(s.fid, 0, outs[0], outs[1], outs[2], B(E1), None, B(s.u.tobytes()), ctypes.c_size_t(s.cons), T, cores)
-            co.msm(s.curve, T.raw, bases[:64 * s.cons], cores)
+            ct = co.msm(s.curve, T.raw, bases[:64 * s.cons], cores)
             Wf = ctypes.create_string_buffer(32 * s.vars)
             L.orc_vec_par(s.fid, 1, B(W1), B(W2), None, None, None, B(s.r.tobytes()), ctypes.c_size_t(s.vars), Wf, cores)
             Ef = ctypes.create_string_buffer(32 * s.cons)
             L.orc_vec_par(s.fid, 1, B(E1), T, None, None, None, B(s.r.tobytes()), ctypes.c_size_t(s.cons), Ef, cores)
+            if return_outputs:
+                import hashlib
+
+                from oracle.pyref import CURVES
+                aff = CURVES[s.curve].affine_from_bytes
+                results[f"curve{s.curve}"] = {"comm_W2": str(aff(cw)), "comm_T": str(aff(ct)),
+                                           "W_fold_sha256": hashlib.sha256(Wf.raw).hexdigest(),
+                                           "E_fold_sha256": hashlib.sha256(Ef.raw).hexdigest()}
 
     step()  # warm-up
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     return {"ms_per_step": (time.perf_counter() - t0) * 1e3 / steps, "cores": cores, "kind": "port",
+            **({"outputs": results} if return_outputs else {}),
             "note": "same op sequence through the C restatement (threaded MSM / SpMV / vector kernels); includes "
                     "Python buffer copies of ~60 MB per step"}
 
