@@ -46,6 +46,7 @@ enum {
   B200_E_NOMEM = 4,    /* device memory exhausted */
   B200_E_RANGE = 5,    /* slice outside the registered key (pedersen.rs:264 assert) */
   B200_E_ZERO = 6,     /* batch_invert met a zero (NovaError::InternalError, spartan/mod.rs:98-100) */
+  B200_E_PEER = 8,     /* a peer GPU never delivered its partial sum to the exchange buffer (multi-GPU MSM) */
   B200_E_POINT = 7     /* a key point is non-canonical or off the curve (NovaError::InvalidCommitmentKey,
                           hyperkzg.rs:113-119; PtauFileError::PointNotOnCurve, ptau.rs:386-388) */
 };
@@ -149,6 +150,29 @@ int b200_msm_adhoc(int curve_id, const void* bases_affine_mont, const void* scal
  * per-GPU partial MSMs (NCCL has no group-law reduction operator) */
 int b200_jacobian_sum_dev(int curve_id, const void* d_points_jacobian, size_t k,
                           void* d_out_jacobian, void* stream);
+
+/* ---- the sharded MSM with its collective fused into the reduction (traits.rs:77-117 over N GPUs) --
+ * One process per GPU (or one host thread per GPU): every rank holds a key over ITS index range of the bases and an
+ * exchange buffer all peers can write over NVLink.  b200_msm_sharded_dev runs the local Pippenger pipeline and its
+ * last kernel writes the rank's partial sum straight into every peer's buffer (peer stores), waits for the peers'
+ * partials and adds them in a fixed order: every rank ends with the same Jacobian coordinates, without an NCCL call
+ * or an extra launch on the critical path ("allreduce" of group elements = all-to-all of 128 bytes + local sum).
+ *
+ *   b200_peer_buffer_alloc   a zeroed exchange buffer on this device (cudaMalloc, so that it can be exported)
+ *   b200_ipc_export / open / close   CUDA IPC handle (64 bytes) of a device allocation / its mapping in another
+ *                            process; ranks exchange the handles out of band (torch.distributed, MPI, a pipe)
+ *   b200_peer_group_create   bufs[r] = rank r's buffer as mapped HERE (bufs[rank] = the local one), world <= 8
+ *   b200_msm_sharded_dev     all ranks must call it in the same order (the epoch counter lives in the group)
+ *   b200_peer_group_status   B200_E_PEER if a wait ever timed out (~2 s) instead of hanging the GPU */
+int b200_peer_buffer_alloc(void** dptr);
+int b200_ipc_export(const void* dptr, void* handle64_out);
+int b200_ipc_open(const void* handle64, void** dptr);
+int b200_ipc_close(void* dptr);
+int b200_peer_group_create(int rank, int world, void* const* bufs, uint64_t* group);
+int b200_peer_group_release(uint64_t group);
+int b200_peer_group_status(uint64_t group);
+int b200_msm_sharded_dev(uint64_t ck_handle, size_t base_offset, const void* d_scalars_mont, size_t n,
+                         uint64_t group, void* d_out_jacobian, void* stream);
 
 /* ---- R1CS witness field arithmetic (host-pointer forms) ---------------------------------- */
 /* t[i] = az[i]*bz[i] - u*cz[i] - e1[i] (- e2[i] if e2 != NULL)   (r1cs/mod.rs:614-620,650-657) */

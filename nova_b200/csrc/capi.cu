@@ -290,16 +290,25 @@ msm_plan make_plan(ck_ctx& ck, workspace& ws, size_t base_offset, size_t n) {
 // enqueue one full-width MSM on `s`; scalars and out are device pointers
 int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_scalars, size_t n,
                 void* d_out, cudaStream_t s, int small_elem_bytes = 0, bool blinded = false,
-                bool digits_done = false) {
+                bool digits_done = false, const msm_peer* peer = nullptr) {
   // blinded: d_scalars holds n-1 vector entries followed by r, whose base is h
   // digits_done: ws.digits / ws.counts were already filled chunk by chunk (b200_witness_append)
+  const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
+  const field_ops* bops = ops_for_field(CURVES[ck.curve].base_fid);
   if (n == 0) {  // identity (msm.rs:228-230): z = 0
+    if (peer && peer->world > 1) {  // the peers still wait for this rank's (empty) partial
+      msm_plan p0 = make_plan(ck, ws, base_offset, 0);
+      p0.peer = *peer;
+      bops->exchange_identity(s, p0, d_out);
+      count_launch(1);
+      CU(cudaGetLastError());
+      return B200_OK;
+    }
     CU(cudaMemsetAsync(d_out, 0, 96, s));
     return B200_OK;
   }
-  const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
-  const field_ops* bops = ops_for_field(CURVES[ck.curve].base_fid);
   msm_plan p = make_plan(ck, ws, base_offset, n);
+  if (peer) p.peer = *peer;
   if (blinded) p.blind_i = n - 1;
   size_t K = (size_t)ck.G * ck.B;
   if (!digits_done) CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
@@ -1004,6 +1013,114 @@ int b200_msm_adhoc(int curve_id, const void* bases, const void* scalars, size_t 
   rc = register_key(curve_id, bases, false, n, nullptr, 0, /*expand=*/false, ck);
   if (rc) return rc;
   return msm_host(route(*ck, 0, n), 0, scalars, n, out);
+}
+
+// ---- sharded MSM with the collective fused into the reduction ---------------------------------------
+namespace {
+struct peer_group {
+  std::mutex mu;
+  msm_peer desc;
+};
+std::mutex g_groups_mu;
+std::map<uint64_t, std::shared_ptr<peer_group>> g_groups;
+uint64_t g_next_group = 1;
+}  // namespace
+
+int b200_peer_buffer_alloc(void** dptr) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!dptr) return fail(B200_E_ARG, "null pointer");
+  CU(cudaMalloc(dptr, MSM_PEER_BUF_BYTES));
+  CU(cudaMemset(*dptr, 0, MSM_PEER_BUF_BYTES));
+  return B200_OK;
+}
+int b200_ipc_export(const void* dptr, void* handle64_out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!dptr || !handle64_out) return fail(B200_E_ARG, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries IPC handles as 64 bytes");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+  memcpy(handle64_out, &h, 64);
+  return B200_OK;
+}
+int b200_ipc_open(const void* handle64, void** dptr) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!handle64 || !dptr) return fail(B200_E_ARG, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200_OK;
+}
+int b200_ipc_close(void* dptr) {
+  if (!dptr) return B200_OK;
+  CU(cudaIpcCloseMemHandle(dptr));
+  return B200_OK;
+}
+int b200_peer_group_create(int rank, int world, void* const* bufs, uint64_t* group) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!bufs || !group) return fail(B200_E_ARG, "null pointer");
+  if (world < 1 || world > MSM_PEER_MAX || rank < 0 || rank >= world)
+    return fail(B200_E_ARG, "peer group of %d ranks (rank %d): world must be 1..%d", world, rank, MSM_PEER_MAX);
+  auto g = std::make_shared<peer_group>();
+  g->desc.world = world;
+  g->desc.rank = rank;
+  for (int r = 0; r < world; r++) {
+    if (!bufs[r]) return fail(B200_E_ARG, "null exchange buffer for rank %d", r);
+    g->desc.buf[r] = bufs[r];
+  }
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  *group = g_next_group++;
+  g_groups[*group] = g;
+  return B200_OK;
+}
+int b200_peer_group_release(uint64_t group) {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  if (!g_groups.erase(group)) return fail(B200_E_HANDLE, "unknown peer group %llu", (unsigned long long)group);
+  return B200_OK;
+}
+static std::shared_ptr<peer_group> get_group(uint64_t h) {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  auto it = g_groups.find(h);
+  return it == g_groups.end() ? nullptr : it->second;
+}
+int b200_peer_group_status(uint64_t group) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto g = get_group(group);
+  if (!g) return fail(B200_E_HANDLE, "unknown peer group %llu", (unsigned long long)group);
+  unsigned long long err = 0;
+  CU(cudaMemcpy(&err, (const char*)g->desc.buf[g->desc.rank] + MSM_PEER_ERR_OFF, 8, cudaMemcpyDeviceToHost));
+  if (err) return fail(B200_E_PEER, "a peer never delivered its partial sum (epoch %llu): exchange timed out", err);
+  return B200_OK;
+}
+
+int b200_msm_sharded_dev(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, uint64_t group,
+                         void* d_out, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  auto g = get_group(group);
+  if (!g) return fail(B200_E_HANDLE, "unknown peer group %llu", (unsigned long long)group);
+  if (!d_out || (n && !d_scalars)) return fail(B200_E_ARG, "null pointer");
+  if (base_offset + n > ck->n)
+    return fail(B200_E_RANGE, "msm slice [%zu, %zu) exceeds key length %zu", base_offset, base_offset + n, ck->n);
+#if defined(NOVA_MSM_ARITH29)
+  return fail(B200_E_ARG, "the fused exchange needs the default (8x32-bit) arithmetic build");
+#else
+  ck_ctx& t = route(*ck, base_offset, n);
+  std::lock_guard<std::mutex> glk(g->mu);
+  std::lock_guard<std::mutex> lk(t.mu);
+  rc = ensure_workspace(t, n ? n : 1, 1);
+  if (rc) return rc;
+  msm_peer peer = g->desc;
+  peer.epoch = ++g->desc.epoch;
+  return enqueue_msm(t, t.ws, base_offset, d_scalars, n, d_out, stream ? (cudaStream_t)stream : g_dev.stream, 0,
+                     false, false, &peer);
+#endif
 }
 
 // ---- field vectors ------------------------------------------------------------------------------

@@ -30,6 +30,20 @@ namespace nova {
 
 constexpr uint32_t KEY_INVALID = 0xffffffffu;
 
+// Multi-GPU epilogue of the sharded MSM (SURVEY.md §8e "allreduce of partial sums"): every rank owns one
+// exchange buffer that all peers can write over NVLink (CUDA IPC between processes, peer access inside one).
+// Layout of a buffer:  slots[2][MSM_PEER_MAX] XYZZ (128 B each; the set is chosen by the epoch's parity), then
+// flags[MSM_PEER_MAX] u64 (flag[r] = last epoch whose partial rank r has delivered), then one u64 error word.
+constexpr int MSM_PEER_MAX = 8;
+constexpr size_t MSM_PEER_FLAGS_OFF = (size_t)2 * MSM_PEER_MAX * 128;
+constexpr size_t MSM_PEER_ERR_OFF = MSM_PEER_FLAGS_OFF + (size_t)MSM_PEER_MAX * 8;
+constexpr size_t MSM_PEER_BUF_BYTES = MSM_PEER_ERR_OFF + 8;
+struct msm_peer {
+  int world = 1, rank = 0;
+  unsigned long long epoch = 0;   // strictly increasing per call, the same on every rank
+  void* buf[MSM_PEER_MAX] = {};   // buf[r] = rank r's exchange buffer as mapped in THIS process
+};
+
 struct msm_plan {
   // problem
   size_t n;            // scalars in this call
@@ -58,6 +72,7 @@ struct msm_plan {
   uint32_t heavy_min;  // entries; such buckets are joined by k_fixup_heavy1/2
   uint32_t heavy_cap;  // capacity of the heavy list
   void* hparts;        // [heavy_cap * HEAVY_SPLIT] xyzz: slice sums of the heavy buckets
+  msm_peer peer;       // world > 1: the reduction's last kernel also exchanges and sums the ranks' partials
 };
 
 // ------------------------------------------------------------------------------------------
@@ -198,6 +213,160 @@ __global__ void __launch_bounds__(128) k_accumulate(const uint64_t* __restrict__
     pkeys[2 * t + 1] = cur_key;
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// The same accumulation with the gathered points STAGED IN SHARED MEMORY BY THE TMA UNIT
+// (north_star: "TMA staging of bucket windows into shared memory").  Every lane owns one 64-byte
+// slot per pipeline stage; it issues `cp.async.bulk.shared.global` (1-D bulk copy, 64 B, 16-B
+// aligned on both sides) for the table point of entry k + ACC_TMA_DEPTH - 1 while it adds entry
+// k, and the copies of one warp and stage complete on one mbarrier (expect_tx = 64 B x issuing
+// lanes, one arrival by the elected lane).  The point then comes from shared memory (4 x
+// LDS.128) instead of living in 16 registers across the previous addition.
+// Stage reuse needs no "empty" barrier: a lane refills slot (k + D - 1) % D only after the
+// addition of entry k - 1 -- the last reader of that slot -- has issued, and a lane reads and
+// writes only its own slots.
+// Run-time A/B against k_accumulate: NOVA_B200_ACC_TMA=1 (ops_impl.cuh); DESIGN.md §4 has the
+// measured verdict.
+// ------------------------------------------------------------------------------------------
+constexpr int ACC_TMA_DEPTH = 3;
+#if defined(__CUDACC__) && !defined(NOVA_MSM_ARITH29)
+NOVA_D uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+NOVA_D void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(arrivals) : "memory");
+}
+NOVA_D void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes)
+               : "memory");
+}
+NOVA_D void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(smem_addr_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion is signalled on `bar` (complete_tx)
+NOVA_D void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate_tma(const uint64_t* __restrict__ entries,
+                                                        const uint32_t* __restrict__ start, uint32_t K,
+                                                        const void* __restrict__ tables, int L,
+                                                        void* __restrict__ buckets, void* __restrict__ parts,
+                                                        uint32_t* __restrict__ pkeys) {
+  using PA = msm_arith<F>;
+  static_assert(sizeof(typename PA::aff) == 64, "one table point = one 64-byte bulk copy");
+  __shared__ __align__(128) uint4 slots[ACC_TMA_DEPTH][128][4];  // [stage][thread][64 B]
+  __shared__ __align__(8) uint64_t bars[4][ACC_TMA_DEPTH];       // [warp][stage]
+  const uint32_t M = start[K];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int st = 0; st < ACC_TMA_DEPTH; st++) mbar_init(&bars[warp][st], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t seg_start = t * (size_t)L;
+  const bool active = seg_start < M;
+  size_t seg_end = seg_start + L < M ? seg_start + L : M;
+  const int len = active ? (int)(seg_end - seg_start) : 0;
+  // trip count of the warp = its longest segment (all lanes run the barrier protocol together)
+  int wlen = len;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    int o = __shfl_xor_sync(0xffffffffu, wlen, d);
+    wlen = o > wlen ? o : wlen;
+  }
+  if (wlen == 0) return;
+
+  // issue the copy of entry j (if this lane has one) into stage j % D; returns the entry
+  auto issue = [&](int j) -> uint64_t {
+    const bool mine = j < len;
+    uint64_t ent = mine ? entries[seg_start + j] : 0;
+    const int st = j % ACC_TMA_DEPTH;  // (callers pass consecutive j: strength-reduced by the compiler)
+    unsigned who = __ballot_sync(0xffffffffu, mine);
+    if (who) {
+      if (lane == (int)(__ffs(who) - 1)) mbar_arrive_expect_tx(&bars[warp][st], 64u * (uint32_t)__popc(who));
+      __syncwarp();
+      if (mine)
+        tma_load_1d(&slots[st][threadIdx.x][0],
+                    (const char*)tables + (size_t)((uint32_t)ent & 0x7fffffffu) * 64, 64, &bars[warp][st]);
+    }
+    return ent;
+  };
+
+  // entries in flight (key | sign | table index), oldest first; rotated by register moves so that the
+  // loop body -- one inlined mixed addition, ~37 KB of code -- exists once
+  static_assert(ACC_TMA_DEPTH == 3, "the rotation below is written for three stages");
+  uint64_t e0 = issue(0), e1 = issue(1);
+
+  typename PA::pt acc = PA::identity();
+  uint32_t cur_key = active ? (uint32_t)(e0 >> 32) : 0;
+  bool first = true;
+  int st = 0;  // k % ACC_TMA_DEPTH
+  uint32_t phase = 0;  // (k / ACC_TMA_DEPTH) & 1
+#pragma unroll 1
+  for (int k = 0; k < wlen; k++) {
+    const uint64_t e2 = issue(k + 2);  // refills the stage that entry k - 1 used
+    // a stage is armed only if some lane had an entry for it: the ballot is warp-uniform
+    if (__ballot_sync(0xffffffffu, k < len)) mbar_wait_parity(&bars[warp][st], phase);
+    if (k < len) {
+      const uint64_t ent = e0;
+      const uint32_t key = (uint32_t)(ent >> 32);
+      const bool sign = (ent >> 31) & 1;
+      typename PA::aff cur;
+      {
+        const uint4* sp = &slots[st][threadIdx.x][0];
+        uint4 a = sp[0], b = sp[1], c = sp[2], d = sp[3];
+        cur.x.l[0] = a.x; cur.x.l[1] = a.y; cur.x.l[2] = a.z; cur.x.l[3] = a.w;
+        cur.x.l[4] = b.x; cur.x.l[5] = b.y; cur.x.l[6] = b.z; cur.x.l[7] = b.w;
+        cur.y.l[0] = c.x; cur.y.l[1] = c.y; cur.y.l[2] = c.z; cur.y.l[3] = c.w;
+        cur.y.l[4] = d.x; cur.y.l[5] = d.y; cur.y.l[6] = d.z; cur.y.l[7] = d.w;
+      }
+      if (key != cur_key) {
+        if (first) {
+          PA::store(parts, 2 * t, acc);
+          pkeys[2 * t] = cur_key;
+          first = false;
+        } else {
+          PA::store(buckets, cur_key, acc);
+        }
+        acc = PA::identity();
+        cur_key = key;
+      }
+      if (!PA::aff_is_identity(cur)) {  // identity bases are skipped (msm.rs:247)
+        if (sign) PA::neg_aff(cur);
+        PA::madd(acc, cur);
+      }
+    }
+    e0 = e1;
+    e1 = e2;
+    if (++st == ACC_TMA_DEPTH) {
+      st = 0;
+      phase ^= 1u;
+    }
+  }
+  if (!active) return;
+  if (first) {
+    PA::store(parts, 2 * t, acc);
+    pkeys[2 * t] = cur_key;
+    pkeys[2 * t + 1] = KEY_INVALID;
+  } else {
+    PA::store(parts, 2 * t + 1, acc);
+    pkeys[2 * t + 1] = cur_key;
+  }
+}
+#endif  // __CUDACC__ && !NOVA_MSM_ARITH29
 
 // G threads per bucket key (G a power of two <= 32, chosen by the host from the expected number of
 // partials per bucket): join the boundary partials of that bucket.  The bucket's entries span
@@ -586,10 +755,63 @@ __global__ void __launch_bounds__(256) k_red_merge_q(const void* __restrict__ pa
   if (threadIdx.x == 0) xyzz_store(merged, (size_t)g * nd * 16 + dv, acc);
 }
 
+// Fused compute + collective epilogue of the sharded MSM.  Called by the whole (single) block of
+// k_red_final_q with quad 0 holding this rank's partial sum:
+//   publish  lanes r < world store the partial into rank r's slot[epoch & 1][rank] (peer stores over NVLink for
+//            r != rank), fence at system scope, then set rank r's flag[rank] = epoch
+//   wait     lane r spins (acquire, system scope) until the LOCAL flag[r] reaches the epoch
+//   sum      quad q < world loads slot q from the local buffer; a fixed binary tree of cooperative additions over
+//            the ranks gives every rank bit-identical coordinates
+// No NCCL call and no extra launch on the critical path.  Two slot sets suffice: a peer can only deliver epoch
+// e + 2 after it has seen this rank's epoch e + 1, which this rank publishes after it finished summing epoch e.
+// A peer that never delivers trips the bounded spin: the error word is set (b200 reports B200_E_PEER at the next
+// host read) instead of hanging the GPU.
+template <class F>
+NOVA_D xyzz_t peer_exchange_sum(const xyzz_t& mine, const msm_peer& peer, xyzz_t* sm /* >= MSM_PEER_MAX */,
+                                const quad_comm_dev& cm) {
+  const int tid = threadIdx.x, quad = tid >> 2;
+  const int set = (int)(peer.epoch & 1ull);
+  if (tid == 0) sm[0] = mine;
+  __syncthreads();
+  if (tid < peer.world) {
+    char* dst = (char*)peer.buf[tid];
+    xyzz_store(dst, (size_t)set * MSM_PEER_MAX + peer.rank, sm[0]);
+    __threadfence_system();
+    volatile unsigned long long* flag = (volatile unsigned long long*)(dst + MSM_PEER_FLAGS_OFF) + peer.rank;
+    *flag = peer.epoch;
+    // wait for rank `tid`'s partial in the local buffer
+    char* loc = (char*)peer.buf[peer.rank];
+    const unsigned long long* lflag = (const unsigned long long*)(loc + MSM_PEER_FLAGS_OFF) + tid;
+    unsigned long long seen = 0;
+    long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(lflag) : "memory");
+      if (seen >= peer.epoch) break;
+      if (clock64() - t0 > (1ll << 32)) {  // ~2 s at 1.9 GHz
+        *(volatile unsigned long long*)(loc + MSM_PEER_ERR_OFF) = peer.epoch;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  xyzz_t acc = xyzz_identity<F>();
+  if (quad < peer.world) acc = xyzz_load((const char*)peer.buf[peer.rank], (size_t)set * MSM_PEER_MAX + quad);
+  for (int s = MSM_PEER_MAX / 2; s > 0; s >>= 1) {
+    if (quad < 2 * s && cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+    if (quad < s && quad + s < peer.world) {
+      xyzz_t o = sm[quad + s];
+      coop_add<F>(acc, o, cm);
+    }
+    __syncthreads();
+  }
+  return acc;  // quad 0 holds the total
+}
+
 // Stage 3: one block, one quad per (d, v), d < nd <= 6: weighted sums, 16^d scaling, combine
 template <class F>
 __global__ void __launch_bounds__(384) k_red_final_q(const void* __restrict__ merged, int G, int bits, int c,
-                                                     void* __restrict__ out_jac) {
+                                                     void* __restrict__ out_jac, const msm_peer peer) {
   __shared__ xyzz_t sm[96];
   quad_comm_dev cm;
   const int nd = (bits + 3) / 4;  // <= 6
@@ -642,6 +864,7 @@ __global__ void __launch_bounds__(384) k_red_final_q(const void* __restrict__ me
     }
     __syncthreads();
   }
+  if (peer.world > 1) total = peer_exchange_sum<F>(total, peer, sm, cm);  // every rank leaves with the same sum
   if (threadIdx.x == 0) {
     fe_t X, Y, Z;
     xyzz_to_jacobian<F>(total, X, Y, Z);

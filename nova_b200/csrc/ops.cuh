@@ -83,6 +83,8 @@ struct field_ops {
   // test SRS (hyperkzg.rs:357-376): out[i] = u^i canonical (scalar field) ; bases[i] = [scalars[i]] G (base field)
   void (*powers_canonical)(cudaStream_t, const void* u_mont, size_t n, void* out);
   void (*scalar_bases)(cudaStream_t, void* bases, size_t n, const void* gen_affine, const void* scalars_canonical);
+  // sharded MSM whose rank has no pairs: publish the identity and sum the peers' partials (plan.peer)
+  void (*exchange_identity)(cudaStream_t, const msm_plan&, void* out_jac);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
 // NOVA_B200_SC_SEG=1 selects the segmented reduction of the eq-weighted sum-check forms (k_form_reduce_eqseg)

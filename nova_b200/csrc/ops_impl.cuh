@@ -57,6 +57,17 @@ struct ops_impl {
     size_t nseg = (max_entries + p.L - 1) / p.L;
     int block = 128;
     int grid = (int)((nseg + block - 1) / block);
+#if !defined(NOVA_MSM_ARITH29)
+    // run-time A/B: NOVA_B200_ACC_TMA=1 stages the gathered points in shared memory with cp.async.bulk + mbarrier
+    static const bool use_tma = [] {
+      const char* e = getenv("NOVA_B200_ACC_TMA");
+      return e != nullptr && e[0] == '1';
+    }();
+    if (use_tma) {
+      k_accumulate_tma<F><<<grid, block, 0, s>>>(p.entries, p.start, K, tables, p.L, p.buckets, p.parts, p.pkeys);
+      return;
+    }
+#endif
     k_accumulate<F><<<grid, block, 0, s>>>(p.entries, p.start, K, tables, p.L, p.buckets, p.parts,
                                            p.pkeys);
   }
@@ -102,7 +113,7 @@ struct ops_impl {
       k_red_digits_q<F><<<g1, 256, 0, s>>>(p.start, p.B, bits, p.buckets, p.rparts);
       dim3 g2((unsigned)(nd * 16), (unsigned)p.G);
       k_red_merge_q<F><<<g2, 256, 0, s>>>(p.rparts, nd, nsplit, merged);
-      k_red_final_q<F><<<1, 384, 0, s>>>(merged, p.G, bits, p.c, out_jac);
+      k_red_final_q<F><<<1, 384, 0, s>>>(merged, p.G, bits, p.c, out_jac, p.peer);
       return;
     }
 #endif
@@ -320,13 +331,18 @@ struct ops_impl {
   static void scalar_bases(cudaStream_t s, void* bases, size_t n, const void* gen, const void* scalars) {
     if (n) k_scalar_bases<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(bases, n, gen, scalars);
   }
+  static void exchange_identity(cudaStream_t s, const msm_plan& p, void* out_jac) {
+#if !defined(NOVA_MSM_ARITH29)
+    k_red_final_q<F><<<1, 384, 0, s>>>(nullptr, 0, 4, 4, out_jac, p.peer);  // G = 0: the local partial is the identity
+#endif
+  }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
                      sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, vec_mul, logup_hash,
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
                      sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve,
-                     powers_canonical, scalar_bases};
+                     powers_canonical, scalar_bases, exchange_identity};
   }
 };
 

@@ -480,3 +480,73 @@ def sharded_hyperkzg_prove(curve, ck, P_local, x: list, r, q, comm, on_w=None):
     if on_w is not None:
         on_w(w)
     return com, v, w
+
+
+# ---------------------------------------------------------------------------------------------
+# The sharded MSM with its collective fused into the reduction kernel (b200_msm_sharded_dev)
+# ---------------------------------------------------------------------------------------------
+class PeerGroup:
+    """One exchange buffer per rank, mapped into every other rank's process with CUDA IPC (NVLink peer stores):
+    the last kernel of each rank's MSM writes its partial sum into all peers' buffers, waits for theirs and adds
+    them in a fixed order (csrc/msm_kernels.cuh `peer_exchange_sum`).  torch.distributed is used ONCE, here, to
+    exchange the 64-byte IPC handles; the MSM steps themselves make no NCCL call.  All ranks must issue their
+    `msm` calls in the same order."""
+
+    def __init__(self, group=None):
+        import ctypes
+
+        from .native import c_u64, check, lib
+        L = lib()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.buf = ctypes.c_void_p()
+        check(L.b200_peer_buffer_alloc(ctypes.byref(self.buf)))
+        h = ctypes.create_string_buffer(64)
+        check(L.b200_ipc_export(self.buf, h))
+        if self.world == 1:
+            handles = [h.raw]
+        elif dist.get_backend(group) == "nccl":
+            handles = NcclComm(group).gather_bytes(h.raw)
+        else:
+            handles = all_gather_bytes(h.raw, group)
+        self.mapped = []
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = self.buf.value
+            else:
+                p = ctypes.c_void_p()
+                check(L.b200_ipc_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)))
+                self.mapped.append(p)
+                ptrs[r] = p.value
+        g = c_u64(0)
+        check(L.b200_peer_group_create(self.rank, self.world, ptrs, ctypes.byref(g)))
+        self.handle = g.value
+        if dist.is_initialized():
+            dist.barrier(group)  # every buffer is mapped everywhere before the first exchange
+
+    def msm(self, ck, base_offset: int, d_scalars: int, n: int, d_out: int, stream=None):
+        """sum over ALL ranks of  sum_i scalars_r[i] * ck_r[base_offset + i]  -> d_out (96-byte Jacobian), on every
+        rank, bit-identical.  d_scalars / d_out: device addresses; asynchronous on `stream`."""
+        import ctypes
+
+        from .native import check, lib
+        check(lib().b200_msm_sharded_dev(ck.handle, base_offset, ctypes.c_void_p(d_scalars), n, self.handle,
+                                         ctypes.c_void_p(d_out), stream))
+
+    def status(self):
+        from .native import check, lib
+        check(lib().b200_peer_group_status(self.handle))
+
+    def close(self):
+        from .native import check, lib
+        L = lib()
+        if self.handle:
+            check(L.b200_sync())
+            if dist.is_initialized():
+                dist.barrier()  # nobody unmaps a buffer a peer may still write
+            check(L.b200_peer_group_release(self.handle))
+            self.handle = 0
+            for p in self.mapped:
+                L.b200_ipc_close(p)
+            L.b200_dev_free(self.buf)

@@ -436,3 +436,38 @@ def test_multi_evaluate_with_on_device(sp, fid):
     the known values; CPU twin: tests/test_spartan_mirror_cpu.py."""
     import mle_multi_parity
     mle_multi_parity.run(sp, fid)
+
+
+def _run_peer_world(world, kind, tmp_path):
+    import subprocess
+    import sys as _sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = 29700 + (os.getpid() % 1500) + world * 13
+    out = str(tmp_path / f"peer_{world}")
+    procs = [subprocess.Popen([_sys.executable, os.path.join(here, "peer_msm_worker.py"), str(r), str(world), str(port),
+                               kind, out]) for r in range(world)]
+    try:
+        for pr in procs:
+            assert pr.wait(timeout=300) == 0
+    finally:
+        for pr in procs:
+            if pr.poll() is None:
+                pr.kill()
+    for r in range(world):
+        assert open(f"{out}.{r}").read() == "OK"
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_sharded_msm_ranks_on_one_device(world, tmp_path):
+    """b200_msm_sharded_dev: the reduction's last kernel publishes the rank's partial into every peer's exchange
+    buffer (CUDA IPC), waits and sums -- here between processes that share cuda:0; results must equal the closed
+    form of the whole vector and be bit-identical on every rank, over several epochs and with an empty rank."""
+    _run_peer_world(world, "gpu", tmp_path)
+
+
+def test_fused_sharded_msm_nccl_ranks(tmp_path):
+    """the same with one GPU per rank (peer stores over NVLink); needs >= 2 GPUs"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_peer_world(2, "nccl", tmp_path)
