@@ -162,11 +162,22 @@ def run_b200(args):
     d_all = torch.zeros(96 * world, dtype=torch.uint8, device="cuda")
     d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
 
+    peer_group = None
+    if world > 1 and args.exchange == "fused":
+        from nova_b200.sharding import PeerGroup
+        peer_group = PeerGroup()  # exchange buffers mapped across the ranks (CUDA IPC); the only set-up collective
+
     def sharded_msm_step(ck_, d_sc_, n_):
-        """One MSM of the whole vector: local Pippenger over this rank's index range, then (N > 1)
-        all-gather of the 96-byte partial points and a local sum on every rank."""
-        check(L.b200_msm_dev(ck_.handle, 0, d_sc_.data_ptr(), n_, d_part.data_ptr(), sp))
-        if world > 1:
+        """One MSM of the whole vector: local Pippenger over this rank's index range; with N > 1 the reduction's
+        last kernel writes the rank's partial sum into every peer's exchange buffer over NVLink, waits for the
+        peers' and adds them (b200_msm_sharded_dev) -- no NCCL call per step.  --exchange nccl keeps the round-1
+        form (all-gather of 96-byte partials + b200_jacobian_sum_dev) for A/B."""
+        if world == 1:
+            check(L.b200_msm_dev(ck_.handle, 0, d_sc_.data_ptr(), n_, d_part.data_ptr(), sp))
+        elif peer_group is not None:
+            peer_group.msm(ck_, 0, d_sc_.data_ptr(), n_, d_out.data_ptr(), sp)
+        else:
+            check(L.b200_msm_dev(ck_.handle, 0, d_sc_.data_ptr(), n_, d_part.data_ptr(), sp))
             dist.all_gather_into_tensor(d_all, d_part)
             check(L.b200_jacobian_sum_dev(CURVE, d_all.data_ptr(), world, d_out.data_ptr(), sp))
 
@@ -282,6 +293,9 @@ def run_b200(args):
     # ---------------- the same sharded MSM at the other sizes north_star names -------------------
     other_sizes = [time_other_size(lg, steps=5, warmup=3) for lg in args.other_log2n if lg != args.log2n]
 
+    if peer_group is not None:
+        peer_group.status()  # B200_E_PEER if any exchange ever timed out
+        peer_group.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -349,12 +363,15 @@ def run_b200(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (256-bit prime-field / curve integers)",
         "data": "synthetic",
         "config": msm_config(args.log2n),
-        "sharding": f"index-range x{world}",
+        "sharding": f"index-range x{world}" + ("" if world == 1 else
+                                                  (", partial sums exchanged by peer stores inside the reduction kernel"
+                                                   if peer_group is not None else ", NCCL all-gather + local sum")),
         "clocks": clocks,
         "e2e": {"value": n_total / (e2e_ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_per_step,
                 "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
                 "api": "b200_commit (host pointers, pinned)" if world == 1 else
-                       "b200_memcpy_h2d + b200_msm_dev + NCCL all_gather + b200_jacobian_sum_dev + D2H"},
+                       ("b200_memcpy_h2d + b200_msm_sharded_dev + D2H" if peer_group is not None else
+                        "b200_memcpy_h2d + b200_msm_dev + NCCL all_gather + b200_jacobian_sum_dev + D2H")},
         "gpu_launches": int(launches.value),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
@@ -565,6 +582,8 @@ def main():
     ap.add_argument("--workload", default="msm", choices=["msm", "hyperkzg", "ppsnark", "prove_step"],
                     help="msm = the headline (BASELINE.json configs[1]); the others time AND check one prover workload")
     ap.add_argument("--log2cons", type=int, default=18, help="--workload ppsnark: log2 of the constraint count")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: how the ranks' partial sums are combined (fused = peer stores inside the reduction kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prove-step", action="store_true")
     args = ap.parse_args()

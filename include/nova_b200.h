@@ -151,6 +151,12 @@ int b200_msm_adhoc(int curve_id, const void* bases_affine_mont, const void* scal
 int b200_jacobian_sum_dev(int curve_id, const void* d_points_jacobian, size_t k,
                           void* d_out_jacobian, void* stream);
 
+/* ---- host-side Keccak-256 (no device work) ---------------------------------------------------------------
+ * The digest the reference's transcript is built from (sha3::Keccak256, src/provider/keccak.rs:14, 66-95; known answer
+ * keccak.rs:279-288).  The transcript stays on the host between device calls; the Python and C++ host layers hash
+ * through this entry point.  A Rust host uses its own `sha3` crate and never calls it. */
+int b200_keccak256(const void* data, size_t len, void* out32);
+
 /* ---- the sharded MSM with its collective fused into the reduction (traits.rs:77-117 over N GPUs) --
  * One process per GPU (or one host thread per GPU): every rank holds a key over ITS index range of the bases and an
  * exchange buffer all peers can write over NVLink.  b200_msm_sharded_dev runs the local Pippenger pipeline and its
@@ -165,6 +171,7 @@ int b200_jacobian_sum_dev(int curve_id, const void* d_points_jacobian, size_t k,
  *   b200_msm_sharded_dev     all ranks must call it in the same order (the epoch counter lives in the group)
  *   b200_peer_group_status   B200_E_PEER if a wait ever timed out (~2 s) instead of hanging the GPU */
 int b200_peer_buffer_alloc(void** dptr);
+int b200_peer_buffer_free(void* dptr);
 int b200_ipc_export(const void* dptr, void* handle64_out);
 int b200_ipc_open(const void* handle64, void** dptr);
 int b200_ipc_close(void* dptr);

@@ -56,6 +56,7 @@ struct device_state {
   bool ready = false;
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool pool = true;
 } g_dev;
 
 int ensure_init() {
@@ -71,9 +72,31 @@ int ensure_init() {
                 e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
   CU(cudaSetDevice(g_dev.device));
   CU(cudaStreamCreateWithFlags(&g_dev.stream, cudaStreamNonBlocking));
+  // b200_dev_alloc / b200_dev_free and the library's own temporaries come from the device's stream-ordered pool
+  // (cudaMallocAsync on the library stream): a prover allocates and drops dozens of vectors per proof, and
+  // cudaMalloc / cudaFree cost milliseconds each and synchronise the device (HyperKZG 2^22: 1012 -> ~70 ms per
+  // proof, profiles/r02c).  The pool keeps what it has been given (release threshold = max).  NOVA_B200_POOL=0
+  // restores plain cudaMalloc / cudaFree.
+  const char* pe = getenv("NOVA_B200_POOL");
+  g_dev.pool = !(pe && pe[0] == '0');
+  if (g_dev.pool) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_dev.device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      g_dev.pool = false;
+      cudaGetLastError();
+    }
+  }
   g_dev.ready = true;
   return B200_OK;
 }
+
+cudaError_t pool_alloc(void** p, size_t bytes) {
+  return g_dev.pool ? cudaMallocAsync(p, bytes ? bytes : 1, g_dev.stream) : cudaMalloc(p, bytes ? bytes : 1);
+}
+cudaError_t pool_free(void* p) { return g_dev.pool ? cudaFreeAsync(p, g_dev.stream) : cudaFree(p); }
 
 // ---------------------------------------------------------------------------------------------
 // commitment-key context
@@ -94,7 +117,13 @@ struct workspace {
   size_t out_slots = 0;
   uint32_t* idx32 = nullptr;
   size_t idx_cap = 0;
+  // stream hand-off: the last stream that enqueued work on these buffers and an event recorded after it.  A call
+  // that arrives on ANOTHER stream waits for that event first (two *_dev calls on one key with different caller
+  // streams, or a *_dev call followed by a host-pointer call on the library stream, never overlap on the buffers).
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t busy = nullptr;
   void release() {
+    if (busy) cudaEventDestroy(busy);
     void* ptrs[] = {scalars, digits, counts, start, cursor, blocksums, entries, buckets,
                     parts, rparts, sumscratch, pkeys, heavy, hparts, d_out, idx32};
     for (void* p : ptrs)
@@ -196,15 +225,46 @@ constexpr int L_MIN = 32;
 constexpr size_t ACC_THREADS = (size_t)148 * 16 * 32 * 3;
 constexpr uint32_t HEAVY_PARTS = 96;  // buckets spanning more segments than this get a block
 
-int segment_len(size_t entries) {
+size_t acc_threads() {
   // tuning hook: NOVA_B200_ACC_WAVES overrides the number of full-GPU waves of accumulate threads
   static const size_t threads = [] {
     const char* e = getenv("NOVA_B200_ACC_WAVES");
     double w = e ? atof(e) : 0.0;
     return w > 0.0 ? (size_t)(148.0 * 16 * 32 * w) : ACC_THREADS;
   }();
-  size_t L = (entries + threads - 1) / threads;
-  return (int)(L < L_MIN ? L_MIN : L);
+  return threads;
+}
+size_t acc_lmin() {
+  // tuning hook: NOVA_B200_ACC_LMIN lowers the floor of the segment length for small MSMs (8 .. L_MIN)
+  static const size_t lmin = [] {
+    const char* e = getenv("NOVA_B200_ACC_LMIN");
+    int v = e ? atoi(e) : L_MIN;
+    return (size_t)(v < 8 ? 8 : (v > L_MIN ? L_MIN : v));
+  }();
+  return lmin;
+}
+int segment_len(size_t entries) {
+  size_t L = (entries + acc_threads() - 1) / acc_threads();
+  return (int)(L < acc_lmin() ? acc_lmin() : L);
+}
+// upper bound of the number of segments of ANY MSM with at most `entries` entries: L grows with the entry count
+// once the thread target is met, so the count saturates at the thread target
+size_t max_segments(size_t entries) {
+  size_t by_floor = (entries + acc_lmin() - 1) / acc_lmin();
+  size_t cap = acc_threads() + 256;
+  return by_floor < cap ? by_floor : cap;
+}
+
+// order stream `s` after the last user of `w` (no-op when that was `s` itself)
+int ws_acquire(workspace& w, cudaStream_t s) {
+  if (w.busy && w.last_stream != s) CU(cudaStreamWaitEvent(s, w.busy, 0));
+  return B200_OK;
+}
+int ws_release(workspace& w, cudaStream_t s) {
+  if (!w.busy) CU(cudaEventCreateWithFlags(&w.busy, cudaEventDisableTiming));
+  CU(cudaEventRecord(w.busy, s));
+  w.last_stream = s;
+  return B200_OK;
 }
 
 int ensure_workspace(ck_ctx& ck, workspace& w, size_t n, size_t out_slots) {
@@ -229,8 +289,8 @@ int ensure_workspace(ck_ctx& ck, workspace& w, size_t n, size_t out_slots) {
     }
   size_t K = (size_t)ck.G * ck.B;
   size_t entries = n * (size_t)ck.W;
-  size_t nseg = (entries + L_MIN - 1) / L_MIN;  // upper bound over every L this key will use
-  w.heavy_cap = (uint32_t)(entries / ((size_t)HEAVY_PARTS * L_MIN) + 2);
+  size_t nseg = max_segments(entries);  // upper bound over every L this key will use
+  w.heavy_cap = (uint32_t)(nseg / HEAVY_PARTS + 2);
   CU(cudaMalloc((void**)&w.heavy, ((size_t)w.heavy_cap + 1) * 4));
   CU(cudaMalloc(&w.hparts, (size_t)w.heavy_cap * HEAVY_SPLIT * XYZZ_BYTES));
   CU(cudaMalloc(&w.scalars, n * 32));
@@ -295,6 +355,10 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
   // digits_done: ws.digits / ws.counts were already filled chunk by chunk (b200_witness_append)
   const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
   const field_ops* bops = ops_for_field(CURVES[ck.curve].base_fid);
+  {
+    int arc = ws_acquire(ws, s);
+    if (arc) return arc;
+  }
   if (n == 0) {  // identity (msm.rs:228-230): z = 0
     if (peer && peer->world > 1) {  // the peers still wait for this rank's (empty) partial
       msm_plan p0 = make_plan(ck, ws, base_offset, 0);
@@ -348,7 +412,7 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
   if (prof) g_prof.pending[pset] = true;
   for (int i = 0; i < ST_COUNT; i++) g_prof.launches += STAGE_KERNELS[i];
   CU(cudaGetLastError());
-  return B200_OK;
+  return ws_release(ws, s);
 }
 
 int enqueue_msm(ck_ctx& ck, size_t base_offset, const void* d_scalars, size_t n, void* d_out,
@@ -462,10 +526,10 @@ int with_field(int field_id, Fn fn) {
 struct dev_buf {
   void* p = nullptr;
   ~dev_buf() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
   }
   int alloc(size_t bytes) {
-    CU(cudaMalloc(&p, bytes ? bytes : 1));
+    CU(pool_alloc(&p, bytes));
     return B200_OK;
   }
 };
@@ -509,11 +573,14 @@ int b200_host_free(void* ptr) {
 int b200_dev_alloc(size_t bytes, void** dptr) {
   int rc = ensure_init();
   if (rc) return rc;
-  CU(cudaMalloc(dptr, bytes ? bytes : 1));
+  CU(pool_alloc(dptr, bytes));
   return B200_OK;
 }
 int b200_dev_free(void* dptr) {
-  CU(cudaFree(dptr));
+  if (!dptr) return B200_OK;
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(pool_free(dptr));
   return B200_OK;
 }
 int b200_memcpy_h2d(void* dptr, const void* hptr, size_t bytes) {
@@ -723,7 +790,8 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
   int rc = ensure_workspace(ck, n + 1, 1);
   if (rc) return rc;
   cudaStream_t s = g_dev.stream;
-  // Tuning hook (off by default, not yet measured): NOVA_B200_H2D_CHUNKS=k splits the upload into k pieces
+  if ((rc = ws_acquire(ck.ws, s))) return rc;
+  // Tuning hook (measured, profiles/r02a: -2 %): NOVA_B200_H2D_CHUNKS=k splits the upload into k pieces
   // and runs the digit / histogram stage of piece i on a side stream while piece i+1 is still on the bus --
   // the same chunked path b200_witness_append uses.  At most the digit stage (~0.12 ms of a 2^20 MSM) can hide.
   static const int h2d_chunks = [] {
@@ -731,7 +799,56 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
     int k = e ? atoi(e) : 1;
     return k < 1 ? 1 : (k > 64 ? 64 : k);
   }();
-  if (h2d_chunks > 1 && n >= ((size_t)1 << 16)) {
+  // Slice pipeline (default for n >= 2^19): the vector is cut into k index ranges, each a complete MSM on its own
+  // lane (stream + workspace) that starts as soon as ITS bytes have landed, so that sort + accumulate of slice j
+  // overlap the upload of slice j+1 and the latency-bound tails of the early slices hide under the later slices'
+  // accumulation; the k partial points are added by one small kernel.  Measured (profiles/r02c): 2^20 from pinned
+  // memory 3.86 -> see DESIGN.md §5.  NOVA_B200_E2E_SLICES=1 restores the single-shot path.
+  static const int e2e_slices = [] {
+    const char* e = getenv("NOVA_B200_E2E_SLICES");
+    int k = e ? atoi(e) : 4;
+    return k < 1 ? 1 : (k > ck_ctx::NLANES ? ck_ctx::NLANES : k);
+  }();
+  if (e2e_slices > 1 && h2d_chunks == 1 && n >= ((size_t)1 << 19)) {
+    const int k = e2e_slices;
+    rc = ensure_workspace(ck, 1, (size_t)k + 1);
+    if (rc) return rc;
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, s));
+    const size_t per = (n + k - 1) / k;
+    int used = 0;
+    for (int j = 0; j < k && rc == B200_OK; j++) {
+      const size_t lo = (size_t)j * per, hi = lo + per < n ? lo + per : n;
+      if (lo >= hi) break;
+      const bool last = hi == n;
+      ck_ctx::lane& ln = ck.lanes[j];
+      if (!ln.s) {
+        CU(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+      }
+      CU(cudaStreamWaitEvent(ln.s, ev, 0));
+      rc = ensure_workspace(ck, ln.ws, hi - lo + 1, 1);
+      if (rc) break;
+      if ((rc = ws_acquire(ln.ws, ln.s))) break;
+      CU(cudaMemcpyAsync(ln.ws.scalars, (const char*)scalars + 32 * lo, 32 * (hi - lo), cudaMemcpyHostToDevice, ln.s));
+      const bool with_blind = last && blind != nullptr;
+      if (with_blind)
+        CU(cudaMemcpyAsync((char*)ln.ws.scalars + 32 * (hi - lo), blind, 32, cudaMemcpyHostToDevice, ln.s));
+      rc = enqueue_msm(ck, ln.ws, base_offset + lo, ln.ws.scalars, hi - lo + (with_blind ? 1 : 0),
+                       (char*)ck.ws.d_out + 96 * (j + 1), ln.s, 0, with_blind);
+      used = j + 1;
+    }
+    for (int j = 0; j < used; j++) {
+      cudaEventRecord(ck.lanes[j].done, ck.lanes[j].s);
+      cudaStreamWaitEvent(s, ck.lanes[j].done, 0);
+    }
+    cudaEventDestroy(ev);
+    if (rc) return rc;
+    ops_for_field(CURVES[ck.curve].base_fid)->jacobian_sum(s, (char*)ck.ws.d_out + 96, used, ck.ws.d_out);
+    count_launch(1);
+    CU(cudaGetLastError());
+  } else if (h2d_chunks > 1 && n >= ((size_t)1 << 16)) {
     ck_ctx::lane& ln = ck.lanes[0];
     if (!ln.s) {
       CU(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
@@ -838,6 +955,7 @@ int b200_commit_dev(uint64_t handle, const void* d_scalars, size_t n, const void
   if (rc) return rc;
   cudaStream_t s = stream ? (cudaStream_t)stream : g_dev.stream;
   if (!d_blind_or_null) return enqueue_msm(t, 0, d_scalars, n, d_out, s);
+  if ((rc = ws_acquire(t.ws, s))) return rc;
   // the blinding scalar must follow the vector in one buffer: stage both in the workspace
   if (n) CU(cudaMemcpyAsync(t.ws.scalars, d_scalars, n * 32, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync((char*)t.ws.scalars + n * 32, d_blind_or_null, 32, cudaMemcpyDeviceToDevice, s));
@@ -874,6 +992,7 @@ static int enqueue_many(ck_ctx& ck, const void* const* vecs, const size_t* lens,
     rc = ensure_workspace(t, ln.ws, lens[j] ? lens[j] : 1, 1);
     if (rc) break;
     const void* src = vecs[j];
+    if ((rc = ws_acquire(ln.ws, ln.s))) break;
     if (from_host && lens[j]) {
       CU(cudaMemcpyAsync(ln.ws.scalars, vecs[j], lens[j] * 32, cudaMemcpyHostToDevice, ln.s));
       src = ln.ws.scalars;
@@ -957,6 +1076,7 @@ int b200_msm_small(uint64_t handle, size_t base_offset, const void* scalars, int
   rc = ensure_workspace(t, n ? n : 1, 1);
   if (rc) return rc;
   cudaStream_t s = g_dev.stream;
+  if ((rc = ws_acquire(t.ws, s))) return rc;
   if (n) CU(cudaMemcpyAsync(t.ws.scalars, scalars, n * elem_bytes, cudaMemcpyHostToDevice, s));
   rc = enqueue_msm(t, base_offset, t.ws.scalars, n, t.ws.d_out, s, elem_bytes);
   if (rc) return rc;
@@ -1015,6 +1135,38 @@ int b200_msm_adhoc(int curve_id, const void* bases, const void* scalars, size_t 
   return msm_host(route(*ck, 0, n), 0, scalars, n, out);
 }
 
+// ---- host-side Keccak-256 for the transcript mirror ---------------------------------------------------
+// The Fiat-Shamir transcript (src/provider/keccak.rs:31-160) stays on the HOST between device calls (HyperKZG,
+// ppsnark, NIFS); in the Rust integration the `sha3` crate does this.  The Python / C++ host layers call this
+// function instead of hashing in the interpreter (a pure-Python permutation costs ~0.5 ms; a HyperKZG proof
+// absorbs ~4 KB).  Plain C, no device work; pinned by keccak.rs:279-288 through nova_b200/transcript.py's tests.
+int b200_keccak256(const void* data, size_t len, void* out32) {
+  if (!out32 || (len && !data)) return fail(B200_E_ARG, "null pointer");
+  const size_t rate = 136;
+  uint64_t st[25] = {};
+  const uint8_t* p = (const uint8_t*)data;
+  auto absorb_block = [&](const uint8_t* blk) {
+    for (size_t i = 0; i < rate / 8; i++) {
+      uint64_t w;
+      memcpy(&w, blk + 8 * i, 8);  // little-endian host (x86-64 / aarch64)
+      st[i] ^= w;
+    }
+    nova::keccak_f1600(st);  // the permutation the device transcript uses, compiled for the host (transcript.cuh)
+  };
+  while (len >= rate) {
+    absorb_block(p);
+    p += rate;
+    len -= rate;
+  }
+  uint8_t last[136] = {};
+  if (len) memcpy(last, p, len);
+  last[len] ^= 0x01;        // original Keccak padding (sha3::Keccak256, not SHA3-256's 0x06)
+  last[rate - 1] ^= 0x80;
+  absorb_block(last);
+  memcpy(out32, st, 32);
+  return B200_OK;
+}
+
 // ---- sharded MSM with the collective fused into the reduction ---------------------------------------
 namespace {
 struct peer_group {
@@ -1032,6 +1184,10 @@ int b200_peer_buffer_alloc(void** dptr) {
   if (!dptr) return fail(B200_E_ARG, "null pointer");
   CU(cudaMalloc(dptr, MSM_PEER_BUF_BYTES));
   CU(cudaMemset(*dptr, 0, MSM_PEER_BUF_BYTES));
+  return B200_OK;
+}
+int b200_peer_buffer_free(void* dptr) {
+  if (dptr) CU(cudaFree(dptr));
   return B200_OK;
 }
 int b200_ipc_export(const void* dptr, void* handle64_out) {

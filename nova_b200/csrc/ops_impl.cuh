@@ -97,7 +97,11 @@ struct ops_impl {
     k_index_bases<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(bases, n, gen, k0);
   }
   static void jacobian_sum(cudaStream_t s, const void* pts, int k, void* out_jac) {
+#if !defined(NOVA_MSM_ARITH29)
+    k_jacobian_sum_q<F><<<1, 32, 0, s>>>(pts, k, out_jac);
+#else
     k_jacobian_sum<F><<<1, 32, 0, s>>>(pts, k, out_jac);
+#endif
   }
   static void reduce(cudaStream_t s, const msm_plan& p, void* out_jac) {
     int bits = p.c - 1;  // bucket index bits

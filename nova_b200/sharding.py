@@ -549,4 +549,4 @@ class PeerGroup:
             self.handle = 0
             for p in self.mapped:
                 L.b200_ipc_close(p)
-            L.b200_dev_free(self.buf)
+            L.b200_peer_buffer_free(self.buf)

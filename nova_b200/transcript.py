@@ -61,7 +61,18 @@ def _permute(s: list) -> list:
 
 
 def keccak256(data: bytes) -> bytes:
-    """Keccak-256 with the original 0x01 padding (sha3::Keccak256, keccak.rs:14), rate 136 bytes."""
+    """Keccak-256 with the original 0x01 padding (sha3::Keccak256, keccak.rs:14): the library's host-side C
+    implementation (b200_keccak256; no GPU involved).  `keccak256_py` below is the same function in the
+    interpreter, kept as the independent cross-check of the C code (tests/test_transcript_mirror_cpu.py)."""
+    import ctypes
+
+    from .native import check, lib
+    out = ctypes.create_string_buffer(32)
+    check(lib().b200_keccak256(data, len(data), out))
+    return out.raw
+
+
+def keccak256_py(data: bytes) -> bytes:
     rate = 136
     padded = bytearray(data)
     padded.append(0x01)

@@ -20,6 +20,8 @@ device code exercised through its host build (tests/hostcheck, incl. the real ke
   one index range per rank; HyperKZG prove, the ppsnark batched sum-check and the folding step over two ranks;
   the segmented eq reductions (NOVA_B200_SC_SEG=1, in a subprocess).
 """
+import os
+
 import pytest
 
 from oracle.pyref import (FIELD_MODULUS, Keccak256Transcript, SplitMix64, eq_evals, mont_bytes,
