@@ -220,7 +220,8 @@ std::shared_ptr<ck_ctx> get_ck(uint64_t h) {
 
 constexpr size_t XYZZ_BYTES = 144;  // 36 words (pa29); pa32 uses the first 128
 constexpr int SUM_THREADS = 148 * 128;
-constexpr int L_MIN = 32;
+constexpr int L_MIN = 32;        // sizing bound of the segment length
+constexpr int L_FLOOR_DEFAULT = 16;  // default floor: a 2^17-pair shard gains 4 % over 32 (profiles/r02d)
 // accumulate threads are sized to ~3 full waves of 148 SMs x 16 warps x 32 lanes
 constexpr size_t ACC_THREADS = (size_t)148 * 16 * 32 * 3;
 constexpr uint32_t HEAVY_PARTS = 96;  // buckets spanning more segments than this get a block
@@ -238,7 +239,7 @@ size_t acc_lmin() {
   // tuning hook: NOVA_B200_ACC_LMIN lowers the floor of the segment length for small MSMs (8 .. L_MIN)
   static const size_t lmin = [] {
     const char* e = getenv("NOVA_B200_ACC_LMIN");
-    int v = e ? atoi(e) : L_MIN;
+    int v = e ? atoi(e) : L_FLOOR_DEFAULT;
     return (size_t)(v < 8 ? 8 : (v > L_MIN ? L_MIN : v));
   }();
   return lmin;
@@ -784,6 +785,20 @@ int b200_ck_len(uint64_t handle, size_t* n, int* window_bits, int* num_tables) {
 }
 
 // ---- MSM --------------------------------------------------------------------------------------
+// Lane streams carry DECREASING priority with the lane index: when several MSMs are in flight, the latency-bound tail
+// kernels (a handful of blocks) of the MSM on lane j are dispatched ahead of the thousands of queued accumulate blocks
+// of the MSM on lane j + 1 instead of behind them -- without this the block scheduler serialises the lanes.
+static int lane_stream(ck_ctx::lane& ln, int index) {
+  if (ln.s) return B200_OK;
+  int least = 0, greatest = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));  // numerically lower = higher priority
+  int prio = greatest + index;
+  if (prio > least) prio = least;
+  CU(cudaStreamCreateWithPriority(&ln.s, cudaStreamNonBlocking, prio));
+  CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+  return B200_OK;
+}
+
 static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t n, void* out,
                     const void* blind = nullptr) {
   std::lock_guard<std::mutex> lk(ck.mu);
@@ -823,10 +838,7 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
       if (lo >= hi) break;
       const bool last = hi == n;
       ck_ctx::lane& ln = ck.lanes[j];
-      if (!ln.s) {
-        CU(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-      }
+      if ((rc = lane_stream(ln, j))) break;
       CU(cudaStreamWaitEvent(ln.s, ev, 0));
       rc = ensure_workspace(ck, ln.ws, hi - lo + 1, 1);
       if (rc) break;
@@ -850,10 +862,7 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
     CU(cudaGetLastError());
   } else if (h2d_chunks > 1 && n >= ((size_t)1 << 16)) {
     ck_ctx::lane& ln = ck.lanes[0];
-    if (!ln.s) {
-      CU(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-    }
+    if ((rc = lane_stream(ln, 0))) return rc;
     const size_t total = n + (blind ? 1 : 0);
     const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
     msm_plan p = make_plan(ck, ck.ws, base_offset, total);
@@ -981,10 +990,7 @@ static int enqueue_many(ck_ctx& ck, const void* const* vecs, const size_t* lens,
     int which = &t == &ck ? 0 : 1;
     int li = (int)(next[which]++ % ck_ctx::NLANES);
     ck_ctx::lane& ln = t.lanes[li];
-    if (!ln.s) {
-      CU(cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-    }
+    if ((rc = lane_stream(ln, li))) break;
     if (!used[which][li]) {
       CU(cudaStreamWaitEvent(ln.s, start_ev, 0));
       used[which][li] = true;

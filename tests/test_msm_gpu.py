@@ -230,7 +230,7 @@ def test_short_vectors_on_a_wide_key(b200, oracle):
     c = CURVES[cid]
     big = b200.CommitmentKey.setup_synthetic(b200.Curve(cid), 1 << 22, with_h=True)
     ce = b200.CommitmentEngine(cid)
-    sc = oracle.gen_scalars(c.scalar_field, 4242, (1 << 21) + 7)
+    sc = oracle.gen_scalars(c.scalar_field, 4242, (1 << 21) + 7 + 3)  # + 3: the vectors below start at element 3
     for m in (1, 1000, (1 << 16) + 3, 1 << 21, (1 << 21) + 7):
         own = b200.CommitmentKey.setup_synthetic(b200.Curve(cid), m)
         assert ce.commit(big, sc[:32 * m], None) == ce.commit(own, sc[:32 * m], None), m
@@ -246,6 +246,7 @@ def test_short_vectors_on_a_wide_key(b200, oracle):
     from nova_b200.spartan import DeviceVec, commit_many_dev
     lens = [(1 << 21) + 7, 1 << 21, 70000, 4096, 33, 2, 1, 1000, 5, (1 << 16) + 3]
     vecs = [DeviceVec.from_bytes(sc[32 * 3:32 * (3 + m)]) for m in lens]
+    assert all(v.nbytes == 32 * m for v, m in zip(vecs, lens))  # (a short slice would make the device read past its end)
     many = commit_many_dev(cid, big, vecs, lens)
     for m, got in zip(lens, many):
         assert got == ce.commit(big, sc[32 * 3:32 * (3 + m)], None), m
