@@ -181,6 +181,20 @@ int b200_peer_group_status(uint64_t group);
 int b200_msm_sharded_dev(uint64_t ck_handle, size_t base_offset, const void* d_scalars_mont, size_t n,
                          uint64_t group, void* d_out_jacobian, void* stream);
 
+/* ---- ONE process, N GPUs behind one call ("b200_init(device_count) + a key sharded across GPUs") ----
+ * A host that calls CommitmentEngine::commit / DlogGroupExt::vartime_multiscalar_mul once (traits.rs:77-117,
+ * pedersen.rs:263-270) gets the whole node: the key is distributed block-cyclically over the devices (every prefix
+ * ck[..n] stays balanced), each device receives its strided slice of the scalars with one 2-D copy, runs the
+ * Pippenger pipeline on its own stream, and the partial sums are exchanged by peer stores over NVLink inside the
+ * last reduction kernel.  devices_or_null = NULL selects devices 0 .. ndev-1 (ndev <= 8).  Thread-safe; calls are
+ * serialised (one MSM occupies all devices).  out = sum_i scalars[i] * ck[i] (+ r * h), Jacobian, 96 bytes. */
+int b200_mgpu_init(int ndev, const int* devices_or_null);
+int b200_mgpu_ck_register(int curve_id, const void* bases_affine_mont, size_t n, const void* h_affine_mont_or_null,
+                          int window_bits, uint64_t* mgpu_key);
+int b200_mgpu_ck_release(uint64_t mgpu_key);
+int b200_mgpu_commit(uint64_t mgpu_key, const void* scalars_mont, size_t n, const void* r_mont_or_null,
+                     void* out_jacobian_mont);
+
 /* ---- R1CS witness field arithmetic (host-pointer forms) ---------------------------------- */
 /* t[i] = az[i]*bz[i] - u*cz[i] - e1[i] (- e2[i] if e2 != NULL)   (r1cs/mod.rs:614-620,650-657) */
 int b200_cross_term(int field_id, const void* az, const void* bz, const void* cz, const void* e1,

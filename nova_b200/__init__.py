@@ -14,6 +14,7 @@ from .provider import (  # noqa: F401
     CommitmentKey,
     Curve,
     DlogGroup,
+    MultiGpuCommitmentKey,
     WitnessStream,
     bind_poly_var_top,
     cross_term,

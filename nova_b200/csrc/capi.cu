@@ -351,7 +351,7 @@ msm_plan make_plan(ck_ctx& ck, workspace& ws, size_t base_offset, size_t n) {
 // enqueue one full-width MSM on `s`; scalars and out are device pointers
 int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_scalars, size_t n,
                 void* d_out, cudaStream_t s, int small_elem_bytes = 0, bool blinded = false,
-                bool digits_done = false, const msm_peer* peer = nullptr) {
+                bool digits_done = false, const msm_peer* peer = nullptr, bool profile_ok = true) {
   // blinded: d_scalars holds n-1 vector entries followed by r, whose base is h
   // digits_done: ws.digits / ws.counts were already filled chunk by chunk (b200_witness_append)
   const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
@@ -379,7 +379,7 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
   if (!digits_done) CU(cudaMemsetAsync(p.counts, 0, K * 4, s));
   CU(cudaMemsetAsync(p.heavy, 0, 4, s));
   std::lock_guard<std::mutex> plk(g_prof.mu);
-  const bool prof = g_prof.enabled;
+  const bool prof = g_prof.enabled && profile_ok;  // (the stage events belong to the library's own device)
   const int pset = g_prof.next;
   if (prof) {
     if (!g_prof.have_events) {
@@ -450,7 +450,13 @@ constexpr int CURVE_B_SMALL[4] = {3, -17, 5, 5};
 // first_bad != nullptr: validate the raw points (bases, then h) where they land in HBM, before the tables are
 // built from them; an invalid point ends the registration with B200_E_POINT and its index in *first_bad.
 int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n, const void* h,
-                 int window_bits, bool expand, std::shared_ptr<ck_ctx>& out, size_t* first_bad = nullptr) {
+                 int window_bits, bool expand, std::shared_ptr<ck_ctx>& out, size_t* first_bad = nullptr,
+                 cudaStream_t st = nullptr, size_t src_pitch_points = 0, size_t src_block_points = 0) {
+  // st: the stream of the CURRENT device the key is built on (nullptr = the library stream).
+  // src_pitch_points / src_block_points != 0: `bases` is a strided view -- block i of src_block_points points sits at
+  // bases + i * src_pitch_points * 64 (the block-cyclic slice one device of a multi-GPU key owns); the last block
+  // may be short.
+  if (!st) st = g_dev.stream;
   if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
   if (bases == nullptr || n == 0) return fail(B200_E_ARG, "empty commitment key");
   if (window_bits != 0 && (window_bits < 2 || window_bits > 24))
@@ -470,23 +476,32 @@ int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n
   if ((size_t)ck->F * ck->stride >= ((size_t)1 << 31))
     return fail(B200_E_RANGE, "key too large for 31-bit table indices (%zu x %d)", n, ck->F);
   CU(cudaMalloc(&ck->tables, (size_t)ck->F * ck->stride * 64));
-  CU(cudaMemcpyAsync(ck->tables, bases, n * 64,
-                     bases_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                     g_dev.stream));
+  const cudaMemcpyKind kind = bases_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (src_block_points == 0) {
+    CU(cudaMemcpyAsync(ck->tables, bases, n * 64, kind, st));
+  } else {
+    const size_t full = n / src_block_points, rest = n % src_block_points;
+    if (full)
+      CU(cudaMemcpy2DAsync(ck->tables, src_block_points * 64, bases, src_pitch_points * 64, src_block_points * 64, full,
+                           kind, st));
+    if (rest)
+      CU(cudaMemcpyAsync((char*)ck->tables + full * src_block_points * 64,
+                         (const char*)bases + full * src_pitch_points * 64, rest * 64, kind, st));
+  }
   if (h)
-    CU(cudaMemcpyAsync((char*)ck->tables + n * 64, h, 64, cudaMemcpyHostToDevice, g_dev.stream));
+    CU(cudaMemcpyAsync((char*)ck->tables + n * 64, h, 64, cudaMemcpyHostToDevice, st));
   if (first_bad) {
     *first_bad = SIZE_MAX;
     dev_flag flag;
     CU(cudaMalloc(&flag.p, 4));
-    CU(cudaMemsetAsync(flag.p, 0xFF, 4, g_dev.stream));
+    CU(cudaMemsetAsync(flag.p, 0xFF, 4, st));
     ops_for_field(CURVES[curve_id].base_fid)
-        ->on_curve(g_dev.stream, ck->tables, ck->stride, CURVE_B_SMALL[curve_id], flag.p);
+        ->on_curve(st, ck->tables, ck->stride, CURVE_B_SMALL[curve_id], flag.p);
     count_launch(1);
     CU(cudaGetLastError());
     uint32_t bad = 0;
-    CU(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, g_dev.stream));
-    CU(cudaStreamSynchronize(g_dev.stream));
+    CU(cudaMemcpyAsync(&bad, flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (bad != 0xFFFFFFFFu) {
       *first_bad = bad;
       return fail(B200_E_POINT, "key point %u%s has a non-canonical coordinate or is not on the curve", bad,
@@ -495,13 +510,14 @@ int register_key(int curve_id, const void* bases, bool bases_on_device, size_t n
   }
   {  // converts table 0 to the kernels' table format and builds tables 1..F-1
     const field_ops* bops = ops_for_field(CURVES[curve_id].base_fid);
-    bops->expand_key(g_dev.stream, ck->tables, ck->stride, ck->F, ck->c * ck->G);
+    bops->expand_key(st, ck->tables, ck->stride, ck->F, ck->c * ck->G);
     CU(cudaGetLastError());
   }
-  CU(cudaStreamSynchronize(g_dev.stream));
+  CU(cudaStreamSynchronize(st));
   if (expand && window_bits == 0 && ck->c >= 20) {
     size_t ns = n < SMALL_KEY_MAX ? n : SMALL_KEY_MAX;
-    int rc = register_key(curve_id, bases, bases_on_device, ns, h, SMALL_KEY_WINDOW, true, ck->small);
+    if (src_block_points) return fail(B200_E_ARG, "strided keys carry one table set");
+    int rc = register_key(curve_id, bases, bases_on_device, ns, h, SMALL_KEY_WINDOW, true, ck->small, nullptr, st);
     if (rc) return rc;
   }
   out = ck;
@@ -811,20 +827,21 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
   // the same chunked path b200_witness_append uses.  At most the digit stage (~0.12 ms of a 2^20 MSM) can hide.
   static const int h2d_chunks = [] {
     const char* e = getenv("NOVA_B200_H2D_CHUNKS");
-    int k = e ? atoi(e) : 1;
+    int k = e ? atoi(e) : 4;  // default 4: -2 % end to end at 2^20 and 2^22 (profiles/r02a)
     return k < 1 ? 1 : (k > 64 ? 64 : k);
   }();
-  // Slice pipeline (default for n >= 2^19): the vector is cut into k index ranges, each a complete MSM on its own
-  // lane (stream + workspace) that starts as soon as ITS bytes have landed, so that sort + accumulate of slice j
-  // overlap the upload of slice j+1 and the latency-bound tails of the early slices hide under the later slices'
-  // accumulation; the k partial points are added by one small kernel.  Measured (profiles/r02c): 2^20 from pinned
-  // memory 3.86 -> see DESIGN.md §5.  NOVA_B200_E2E_SLICES=1 restores the single-shot path.
+  // Slice pipeline (n >= 2^23): the vector is cut into k index ranges, each a complete MSM on its own lane (stream +
+  // workspace) that starts as soon as ITS bytes have landed, so that the pipeline of slice j overlaps the upload of
+  // slice j+1; the k partial points are added by one small kernel.  Measured (profiles/r02d): 2^24 from pinned memory
+  // 50.9 -> 45.5 ms; at 2^20 - 2^22 it LOSES (3.98 -> 3.95 .. 4.56 ms at 2^20: a quarter-size MSM runs at lower
+  // efficiency and the lanes' kernels do not overlap -- each accumulate grid already fills the GPU for several waves),
+  // so smaller vectors take the single-shot path with the chunked upload below.  NOVA_B200_E2E_SLICES=1 disables it.
   static const int e2e_slices = [] {
     const char* e = getenv("NOVA_B200_E2E_SLICES");
     int k = e ? atoi(e) : 4;
     return k < 1 ? 1 : (k > ck_ctx::NLANES ? ck_ctx::NLANES : k);
   }();
-  if (e2e_slices > 1 && h2d_chunks == 1 && n >= ((size_t)1 << 19)) {
+  if (e2e_slices > 1 && n >= ((size_t)1 << 23)) {
     const int k = e2e_slices;
     rc = ensure_workspace(ck, 1, (size_t)k + 1);
     if (rc) return rc;
@@ -1282,6 +1299,218 @@ int b200_msm_sharded_dev(uint64_t handle, size_t base_offset, const void* d_scal
   peer.epoch = ++g->desc.epoch;
   return enqueue_msm(t, t.ws, base_offset, d_scalars, n, d_out, stream ? (cudaStream_t)stream : g_dev.stream, 0,
                      false, false, &peer);
+#endif
+}
+
+// ---- ONE process, N GPUs: a commitment key sharded over the devices behind a single call -----------------
+// What SURVEY.md §8b asked of the boundary: a Rust host calls DlogGroupExt::vartime_multiscalar_mul /
+// CommitmentEngine::commit ONCE (src/provider/traits.rs:77-117, pedersen.rs:263-270) and the node's GPUs share the
+// work.  The key is distributed BLOCK-CYCLICALLY (blocks of MGPU_BLOCK points: device d owns blocks d, d + D, ...),
+// so every prefix ck[..n] -- the reference commits prefixes of one key all the time -- is balanced over the devices,
+// and a device's scalars are a strided view of the caller's vector: one cudaMemcpy2DAsync per device.  One host thread
+// drives all devices (every step is asynchronous); the partial sums are exchanged by peer stores inside each device's
+// last reduction kernel (peer_exchange_sum, peer access enabled between all pairs) and every device ends with the sum.
+namespace {
+constexpr size_t MGPU_BLOCK = 4096;
+struct mgpu_state {
+  std::mutex mu;
+  bool ready = false;
+  int ndev = 0;
+  int dev[MSM_PEER_MAX] = {};
+  cudaStream_t stream[MSM_PEER_MAX] = {};
+  void* xbuf[MSM_PEER_MAX] = {};
+  void* out_dev[MSM_PEER_MAX] = {};  // 96-byte result slot per device
+  void* out_host = nullptr;          // pinned
+  unsigned long long epoch = 0;
+} g_mgpu;
+struct mgpu_key {
+  int curve = 0;
+  size_t n = 0;
+  bool has_h = false;
+  std::shared_ptr<ck_ctx> part[MSM_PEER_MAX];
+};
+std::mutex g_mkeys_mu;
+std::map<uint64_t, std::shared_ptr<mgpu_key>> g_mkeys;
+uint64_t g_next_mkey = 1;
+
+// points of the first n that device d of D owns under the block-cyclic distribution
+size_t mgpu_count(size_t n, int d, int D) {
+  const size_t round = MGPU_BLOCK * (size_t)D;
+  const size_t rem = n % round;
+  size_t extra = rem > (size_t)d * MGPU_BLOCK ? rem - (size_t)d * MGPU_BLOCK : 0;
+  if (extra > MGPU_BLOCK) extra = MGPU_BLOCK;
+  return (n / round) * MGPU_BLOCK + extra;
+}
+struct device_guard {  // restores the library's own device on every exit path
+  ~device_guard() { cudaSetDevice(g_dev.device); }
+};
+}  // namespace
+
+int b200_mgpu_init(int ndev, const int* devices_or_null) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (ndev < 1 || ndev > MSM_PEER_MAX) return fail(B200_E_ARG, "ndev %d outside 1..%d", ndev, MSM_PEER_MAX);
+  std::lock_guard<std::mutex> lk(g_mgpu.mu);
+  if (g_mgpu.ready) {
+    if (g_mgpu.ndev != ndev) return fail(B200_E_ARG, "already initialised with %d devices", g_mgpu.ndev);
+    return B200_OK;
+  }
+  int have = 0;
+  CU(cudaGetDeviceCount(&have));
+  device_guard guard;
+  for (int d = 0; d < ndev; d++) {
+    int id = devices_or_null ? devices_or_null[d] : d;
+    if (id < 0 || id >= have) return fail(B200_E_ARG, "device %d not present (%d visible)", id, have);
+    g_mgpu.dev[d] = id;
+  }
+  for (int d = 0; d < ndev; d++) {
+    CU(cudaSetDevice(g_mgpu.dev[d]));
+    CU(cudaStreamCreateWithFlags(&g_mgpu.stream[d], cudaStreamNonBlocking));
+    CU(cudaMalloc(&g_mgpu.xbuf[d], MSM_PEER_BUF_BYTES));
+    CU(cudaMemset(g_mgpu.xbuf[d], 0, MSM_PEER_BUF_BYTES));
+    CU(cudaMalloc(&g_mgpu.out_dev[d], 96));
+    for (int e = 0; e < ndev; e++) {
+      if (g_mgpu.dev[e] == g_mgpu.dev[d]) continue;
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, g_mgpu.dev[d], g_mgpu.dev[e]));
+      if (!can) return fail(B200_E_CUDA, "device %d cannot access device %d (no NVLink / P2P path)", g_mgpu.dev[d], g_mgpu.dev[e]);
+      cudaError_t pe = cudaDeviceEnablePeerAccess(g_mgpu.dev[e], 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(B200_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", g_mgpu.dev[d], g_mgpu.dev[e], cudaGetErrorString(pe));
+      cudaGetLastError();
+    }
+  }
+  CU(cudaMallocHost(&g_mgpu.out_host, 96));
+  g_mgpu.ndev = ndev;
+  g_mgpu.ready = true;
+  return B200_OK;
+}
+
+int b200_mgpu_ck_register(int curve_id, const void* bases, size_t n, const void* h, int window_bits, uint64_t* key) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!g_mgpu.ready) return fail(B200_E_ARG, "b200_mgpu_init has not been called");
+  if (curve_id < 0 || curve_id > 3) return fail(B200_E_ARG, "unknown curve id %d", curve_id);
+  if (!bases || !key || n == 0) return fail(B200_E_ARG, "bad argument");
+  std::lock_guard<std::mutex> lk(g_mgpu.mu);
+  device_guard guard;
+  auto mk = std::make_shared<mgpu_key>();
+  mk->curve = curve_id;
+  mk->n = n;
+  mk->has_h = h != nullptr;
+  const int D = g_mgpu.ndev;
+  for (int d = 0; d < D; d++) {
+    size_t nd = mgpu_count(n, d, D);
+    if (nd == 0 && !(d == 0 && h)) continue;  // this device owns nothing of this (tiny) key
+    CU(cudaSetDevice(g_mgpu.dev[d]));
+    if (nd == 0) return fail(B200_E_ARG, "key of %zu points is too small to carry a blinding generator on %d devices", n, D);
+    rc = register_key(curve_id, (const char*)bases + (size_t)d * MGPU_BLOCK * 64, false, nd, d == 0 ? h : nullptr,
+                      window_bits, true, mk->part[d], nullptr, g_mgpu.stream[d], MGPU_BLOCK * (size_t)D, MGPU_BLOCK);
+    if (rc) return rc;
+  }
+  std::lock_guard<std::mutex> lk2(g_mkeys_mu);
+  *key = g_next_mkey++;
+  g_mkeys[*key] = mk;
+  return B200_OK;
+}
+
+int b200_mgpu_ck_release(uint64_t key) {
+  std::shared_ptr<mgpu_key> mk;
+  {
+    std::lock_guard<std::mutex> lk(g_mkeys_mu);
+    auto it = g_mkeys.find(key);
+    if (it == g_mkeys.end()) return fail(B200_E_HANDLE, "unknown multi-GPU key %llu", (unsigned long long)key);
+    mk = it->second;
+    g_mkeys.erase(it);
+  }
+  std::lock_guard<std::mutex> lk(g_mgpu.mu);  // wait for an in-flight call
+  device_guard guard;
+  for (int d = 0; d < g_mgpu.ndev; d++) {
+    cudaSetDevice(g_mgpu.dev[d]);
+    cudaStreamSynchronize(g_mgpu.stream[d]);
+  }
+  return B200_OK;
+}
+
+int b200_mgpu_commit(uint64_t key, const void* scalars, size_t n, const void* r, void* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!g_mgpu.ready) return fail(B200_E_ARG, "b200_mgpu_init has not been called");
+  std::shared_ptr<mgpu_key> mk;
+  {
+    std::lock_guard<std::mutex> lk(g_mkeys_mu);
+    auto it = g_mkeys.find(key);
+    if (it == g_mkeys.end()) return fail(B200_E_HANDLE, "unknown multi-GPU key %llu", (unsigned long long)key);
+    mk = it->second;
+  }
+  if (!out || (n && !scalars)) return fail(B200_E_ARG, "null pointer");
+  if (n > mk->n) return fail(B200_E_RANGE, "commit of %zu scalars exceeds key length %zu", n, mk->n);
+  if (r && !mk->has_h) return fail(B200_E_ARG, "key was registered without a blinding generator");
+#if defined(NOVA_MSM_ARITH29)
+  return fail(B200_E_ARG, "the fused exchange needs the default (8x32-bit) arithmetic build");
+#else
+  std::lock_guard<std::mutex> lk(g_mgpu.mu);
+  device_guard guard;
+  const int D = g_mgpu.ndev;
+  msm_peer peer;
+  peer.world = D;
+  peer.epoch = ++g_mgpu.epoch;
+  for (int d = 0; d < D; d++) peer.buf[d] = g_mgpu.xbuf[d];
+  const field_ops* bops = ops_for_field(CURVES[mk->curve].base_fid);
+  // workspaces first: a (re)allocation synchronises its device, and by then the other devices' last kernels may
+  // already be spinning on this device's partial
+  for (int d = 0; d < D; d++) {
+    ck_ctx* part = mk->part[d].get();
+    const size_t nd = mgpu_count(n, d, D);
+    if (!part || (nd == 0 && !(d == 0 && r))) continue;
+    CU(cudaSetDevice(g_mgpu.dev[d]));
+    std::lock_guard<std::mutex> plk(part->mu);
+    if ((rc = ensure_workspace(*part, part->ws, nd + 1, 1))) return rc;
+  }
+  for (int d = 0; d < D; d++) {
+    CU(cudaSetDevice(g_mgpu.dev[d]));
+    cudaStream_t s = g_mgpu.stream[d];
+    peer.rank = d;
+    const size_t nd = mgpu_count(n, d, D);
+    const bool blind = d == 0 && r != nullptr;
+    ck_ctx* part = mk->part[d].get();
+    if ((nd == 0 && !blind) || !part) {  // nothing here: deliver the identity so that the peers' sums complete
+      msm_plan p0{};
+      p0.peer = peer;
+      bops->exchange_identity(s, p0, g_mgpu.out_dev[d]);
+      count_launch(1);
+      CU(cudaGetLastError());
+      continue;
+    }
+    std::lock_guard<std::mutex> plk(part->mu);
+    rc = ensure_workspace(*part, part->ws, nd + 1, 1);
+    if (rc) return rc;
+    if ((rc = ws_acquire(part->ws, s))) return rc;
+    const size_t full = nd / MGPU_BLOCK, rest = nd % MGPU_BLOCK;
+    const char* src = (const char*)scalars + (size_t)d * MGPU_BLOCK * 32;
+    if (full)
+      CU(cudaMemcpy2DAsync(part->ws.scalars, MGPU_BLOCK * 32, src, MGPU_BLOCK * (size_t)D * 32, MGPU_BLOCK * 32, full,
+                           cudaMemcpyHostToDevice, s));
+    if (rest)
+      CU(cudaMemcpyAsync((char*)part->ws.scalars + full * MGPU_BLOCK * 32, src + full * MGPU_BLOCK * (size_t)D * 32,
+                         rest * 32, cudaMemcpyHostToDevice, s));
+    if (blind) CU(cudaMemcpyAsync((char*)part->ws.scalars + nd * 32, r, 32, cudaMemcpyHostToDevice, s));
+    rc = enqueue_msm(*part, part->ws, 0, part->ws.scalars, nd + (blind ? 1 : 0), g_mgpu.out_dev[d], s, 0, blind, false,
+                     &peer, /*profile_ok=*/false);
+    if (rc) return rc;
+  }
+  CU(cudaSetDevice(g_mgpu.dev[0]));
+  CU(cudaMemcpyAsync(g_mgpu.out_host, g_mgpu.out_dev[0], 96, cudaMemcpyDeviceToHost, g_mgpu.stream[0]));
+  for (int d = 0; d < D; d++) {  // the caller's buffer is free again and every device has finished its part
+    CU(cudaSetDevice(g_mgpu.dev[d]));
+    CU(cudaStreamSynchronize(g_mgpu.stream[d]));
+  }
+  unsigned long long err = 0;
+  CU(cudaSetDevice(g_mgpu.dev[0]));
+  CU(cudaMemcpy(&err, (const char*)g_mgpu.xbuf[0] + MSM_PEER_ERR_OFF, 8, cudaMemcpyDeviceToHost));
+  if (err) return fail(B200_E_PEER, "a device never delivered its partial sum (epoch %llu)", err);
+  memcpy(out, g_mgpu.out_host, 96);
+  return B200_OK;
 #endif
 }
 

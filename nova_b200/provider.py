@@ -350,3 +350,38 @@ def bind_poly_var_top(fid: int, z: bytes, r: bytes) -> bytes:
     buf = _cbuf(z)
     check(lib().b200_bind_top(fid, buf, n, _cbuf(r)))
     return bytes(buf[:32 * (n // 2)])
+
+
+class MultiGpuCommitmentKey:
+    """A commitment key sharded block-cyclically over the GPUs of ONE process (b200_mgpu_*): `commit` is the single
+    call a `CommitmentEngine::commit` / `vartime_multiscalar_mul` makes, the library fans it out over the devices
+    and exchanges the partial sums over NVLink inside the reduction kernels (include/nova_b200.h)."""
+
+    def __init__(self, curve: "Curve", bases: bytes, h: bytes | None = None, devices=None, ndev: int | None = None,
+                 window_bits: int = 0):
+        L = lib()
+        devs = list(devices) if devices is not None else list(range(ndev or 1))
+        arr = (ctypes.c_int * len(devs))(*devs)
+        check(L.b200_mgpu_init(len(devs), arr))
+        self.curve, self.n, self.has_h = Curve(curve), len(bases) // 64, h is not None
+        handle = c_u64(0)
+        check(L.b200_mgpu_ck_register(int(curve), _cbuf(bases), self.n, _cbuf(h) if h else None, window_bits,
+                                      ctypes.byref(handle)))
+        self.handle = handle.value
+
+    def commit(self, v: bytes, r: bytes | None = None):
+        """-> affine point (x, y) as integers, or None for the identity"""
+        out = ctypes.create_string_buffer(96)
+        check(lib().b200_mgpu_commit(self.handle, _cbuf(v), len(v) // 32, _cbuf(r) if r else None, out))
+        return _jac_to_affine(self.curve, out.raw)
+
+    def release(self):
+        if self.handle:
+            check(lib().b200_mgpu_ck_release(self.handle))
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

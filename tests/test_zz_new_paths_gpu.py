@@ -473,3 +473,31 @@ def test_fused_sharded_msm_nccl_ranks(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run_peer_world(2, "nccl", tmp_path)
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0]])
+def test_one_process_multi_gpu_commit(devices, tmp_path):
+    """b200_mgpu_*: one process, one call, the key block-cyclic over `devices` (here virtual devices that share
+    cuda:0 -- the same code path as N physical GPUs: per-device streams, keys, workspaces, peer exchange inside the
+    reduction kernels).  Run in a subprocess: the multi-GPU layer is initialised once per process."""
+    import subprocess
+    import sys as _sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([_sys.executable, os.path.join(here, "mgpu_commit_worker.py"), ",".join(map(str, devices))],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_one_process_all_gpus_commit(tmp_path):
+    """the same over every physical GPU of the box (needs >= 2)"""
+    import subprocess
+    import sys as _sys
+
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([_sys.executable, os.path.join(here, "mgpu_commit_worker.py"), ",".join(map(str, range(n)))],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
