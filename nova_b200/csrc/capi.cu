@@ -172,7 +172,7 @@ struct ck_ctx {
 
 // ---- optional per-stage device timing + launch accounting (for bench.py's roofline) ---------
 enum { ST_DIGITS = 0, ST_SORT, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_COUNT };
-const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 3, 3};
+const int STAGE_KERNELS[ST_COUNT] = {1, 4, 1, 3, 2};  // reduce: merge + final (+ one per level, added per call)
 struct profile_state {
   std::mutex mu;
   bool enabled = false;
@@ -412,6 +412,7 @@ int enqueue_msm(ck_ctx& ck, workspace& ws, size_t base_offset, const void* d_sca
 #undef STAGE_MARK
   if (prof) g_prof.pending[pset] = true;
   for (int i = 0; i < ST_COUNT; i++) g_prof.launches += STAGE_KERNELS[i];
+  g_prof.launches += (ck.c - 1 + 3) / 4 - 1;  // the hierarchical reduction launches one kernel per level below the top
   CU(cudaGetLastError());
   return ws_release(ws, s);
 }

@@ -755,6 +755,141 @@ __global__ void __launch_bounds__(256) k_red_merge_q(const void* __restrict__ pa
   if (threadIdx.x == 0) xyzz_store(merged, (size_t)g * nd * 16 + dv, acc);
 }
 
+// ------------------------------------------------------------------------------------------
+// Hierarchical form of the radix-16 digit sums (default; the flat k_red_digits_q above reads every
+// bucket once per digit position = nd additions per bucket, this one does 2 + 2/16 + ...):
+//   level l works on X^(l) (X^(0) = the buckets, N_l = 2^(bits - 4 l) points) and produces
+//     pass A   S_l[v]   = sum_j X^(l)[16 j + v]           (the digit sums of position l)
+//     pass B   X^(l+1)[j] = sum_v X^(l)[16 j + v]          (the input of the next level)
+//   the top level (N <= 16) IS its own digit-sum array.
+// sum_b (b+1) B_b = S_all + sum_l 16^l sum_v v S_l[v]  as before (k_red_final_q is unchanged).
+// One launch per level: blockIdx.y < 16 -> pass A for digit value v = blockIdx.y (blockIdx.x = slice of the
+// groups, 64 quads stride over it and tree-sum), blockIdx.y == 16 -> pass B (four quads per group: 3 serial
+// cooperative additions each, then a 2-level tree), blockIdx.z = bucket group.
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) k_red_level_q(const uint32_t* __restrict__ start_or_null, uint32_t key_base_stride,
+                                                     const void* __restrict__ X, uint32_t N, int nsplit,
+                                                     void* __restrict__ parts /* [G][16][nsplit] */,
+                                                     void* __restrict__ next /* [G][N/16] */) {
+  __shared__ xyzz_t sm[64];
+  quad_comm_dev cm;
+  const int quad = threadIdx.x >> 2;
+  const uint32_t g = blockIdx.z;
+  const uint32_t groups = N >> 4;
+  const size_t xbase = (size_t)g * N;
+  // level 0 reads the bucket array, where an empty bucket holds stale data: its emptiness comes from the offsets
+  auto load = [&](uint32_t i) -> xyzz_t {
+    if (start_or_null) {
+      const uint32_t key = g * key_base_stride + i;
+      if (start_or_null[key + 1] == start_or_null[key]) return xyzz_identity<F>();
+    }
+    return xyzz_load(X, xbase + i);
+  };
+  if (blockIdx.y == 16) {  // pass B: group sums, four quads per group (3 serial additions each, then a 2-level tree)
+    const uint32_t j = blockIdx.x * 16 + (quad >> 2);
+    const int sub = quad & 3;
+    const bool live = j < groups;  // uniform within a quad
+    xyzz_t acc = xyzz_identity<F>();
+    if (live) {
+      acc = load(16 * j + 4 * sub);
+      for (int k = 1; k < 4; k++) {
+        xyzz_t o = load(16 * j + 4 * sub + k);
+        coop_add<F>(acc, o, cm);
+      }
+    }
+    if (cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+    if (live && sub < 2) {
+      xyzz_t o = sm[quad + 2];
+      coop_add<F>(acc, o, cm);
+    }
+    __syncthreads();
+    if (sub < 2 && cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+    if (live && sub == 0) {
+      xyzz_t o = sm[quad + 1];
+      coop_add<F>(acc, o, cm);
+      if (cm.lane() == 0) xyzz_store(next, (size_t)g * groups + j, acc);
+    }
+    return;
+  }
+  if ((int)blockIdx.x >= nsplit) return;
+  const uint32_t v = blockIdx.y;
+  const uint32_t per = (groups + nsplit - 1) / nsplit;
+  const uint32_t lo = blockIdx.x * per, hi = lo + per < groups ? lo + per : groups;
+  xyzz_t acc = xyzz_identity<F>();
+  for (uint32_t j = lo + quad; j < hi; j += 64) {
+    xyzz_t o = load(16 * j + v);
+    coop_add<F>(acc, o, cm);
+  }
+  if (cm.lane() == 0) sm[quad] = acc;
+  __syncthreads();
+  for (int s = 32; s > 0; s >>= 1) {
+    if (quad < s) {
+      xyzz_t o = sm[quad + s];
+      coop_add<F>(acc, o, cm);
+    }
+    __syncthreads();
+    if (quad < s && cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) xyzz_store(parts, ((size_t)g * 16 + v) * nsplit + blockIdx.x, acc);
+}
+
+// merged[g][d][v] for all digit positions: d < nd - 1 -> tree sum of level d's nsplit[d] partials; d = nd - 1 (the top
+// level, N_top <= 16 points) -> the point itself.  Block (d * 16 + v, g).
+struct red_levels {
+  int nd;
+  int nsplit[8];          // per level (unused for the top level)
+  unsigned parts_off[8];  // offset (in points) of level d's parts inside the scratch area
+  unsigned top_off;       // offset of X^(nd-1) (dense), or 0xFFFFFFFF when the top level is level 0 (= the buckets)
+  unsigned top_n;         // N of the top level
+};
+template <class F>
+__global__ void __launch_bounds__(256) k_red_merge_levels_q(const void* __restrict__ scratch, const red_levels lv,
+                                                            const uint32_t* __restrict__ start, uint32_t B,
+                                                            const void* __restrict__ buckets, int G,
+                                                            void* __restrict__ merged) {
+  __shared__ xyzz_t sm[64];
+  quad_comm_dev cm;
+  const int d = blockIdx.x >> 4, v = blockIdx.x & 15, g = blockIdx.y;
+  const int quad = threadIdx.x >> 2;
+  xyzz_t acc = xyzz_identity<F>();
+  if (d == lv.nd - 1) {
+    if (threadIdx.x == 0) {
+      if ((unsigned)v < lv.top_n) {
+        if (lv.top_off == 0xFFFFFFFFu) {
+          uint32_t key = (uint32_t)g * B + v;
+          if (start[key + 1] > start[key]) acc = xyzz_load(buckets, key);
+        } else {
+          acc = xyzz_load(scratch, (size_t)lv.top_off + (size_t)g * lv.top_n + v);
+        }
+      }
+      xyzz_store(merged, ((size_t)g * lv.nd + d) * 16 + v, acc);
+    }
+    return;
+  }
+  const int nsplit = lv.nsplit[d];
+  const size_t base = (size_t)lv.parts_off[d] + ((size_t)g * 16 + v) * nsplit;
+  for (int x = quad; x < nsplit; x += 64) {
+    xyzz_t o = xyzz_load(scratch, base + x);
+    coop_add<F>(acc, o, cm);
+  }
+  if (cm.lane() == 0) sm[quad] = acc;
+  __syncthreads();
+  for (int s = 32; s > 0; s >>= 1) {
+    if (quad < s && s < nsplit) {
+      xyzz_t o = sm[quad + s];
+      coop_add<F>(acc, o, cm);
+    }
+    __syncthreads();
+    if (quad < s && cm.lane() == 0) sm[quad] = acc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) xyzz_store(merged, ((size_t)g * lv.nd + d) * 16 + v, acc);
+}
+
 // Fused compute + collective epilogue of the sharded MSM.  Called by the whole (single) block of
 // k_red_final_q with quad 0 holding this rank's partial sum:
 //   publish  lanes r < world store the partial into rank r's slot[epoch & 1][rank] (peer stores over NVLink for

@@ -106,6 +106,49 @@ struct ops_impl {
   static void reduce(cudaStream_t s, const msm_plan& p, void* out_jac) {
     int bits = p.c - 1;  // bucket index bits
 #if !defined(NOVA_MSM_ARITH29)
+    // NOVA_B200_RED_FLAT=1 forces the round-1 form (every bucket read once per digit position), =0 the hierarchical
+    // form; default: hierarchical from NOVA_B200_RED_HIER_BITS bucket-index bits on (measured, profiles/r02d)
+    static const int flat_mode = [] {
+      const char* e = getenv("NOVA_B200_RED_FLAT");
+      return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+    }();
+    static const int hier_bits = [] {
+      const char* e = getenv("NOVA_B200_RED_HIER_BITS");
+      return e ? atoi(e) : 18;
+    }();
+    const bool flat = flat_mode == 1 || (flat_mode == -1 && bits < hier_bits);
+    if (bits >= 1 && bits <= 24 && !flat) {  // hierarchical radix-16 digit sums (k_red_level_q)
+      red_levels lv{};
+      lv.nd = (bits + 3) / 4;
+      size_t off = 0;  // in points (128 B) inside p.rparts
+      uint32_t N = p.B;
+      const void* X = p.buckets;
+      for (int l = 0; l < lv.nd - 1; l++) {
+        const uint32_t groups = N >> 4;
+        int nsplit = (int)((groups + 511) / 512);  // ~8 serial additions per quad before the block tree
+        if (nsplit < 1) nsplit = 1;
+        lv.nsplit[l] = nsplit;
+        lv.parts_off[l] = (unsigned)off;
+        char* parts = (char*)p.rparts + off * 128;
+        off += (size_t)p.G * 16 * nsplit;
+        char* next = (char*)p.rparts + off * 128;
+        const unsigned next_off = (unsigned)off;
+        off += (size_t)p.G * groups;
+        unsigned gx = (unsigned)nsplit, gb = (groups + 15) / 16;
+        dim3 grid(gx > gb ? gx : gb, 17u, (unsigned)p.G);
+        k_red_level_q<F><<<grid, 256, 0, s>>>(l == 0 ? p.start : nullptr, p.B, X, N, nsplit, parts, next);
+        X = next;
+        N = groups;
+        lv.top_off = next_off;
+      }
+      if (lv.nd == 1) lv.top_off = 0xFFFFFFFFu;
+      lv.top_n = N;
+      char* merged = (char*)p.rparts + off * 128;
+      dim3 g2((unsigned)(lv.nd * 16), (unsigned)p.G);
+      k_red_merge_levels_q<F><<<g2, 256, 0, s>>>(p.rparts, lv, p.start, p.B, p.buckets, p.G, merged);
+      k_red_final_q<F><<<1, 384, 0, s>>>(merged, p.G, bits, p.c, out_jac, p.peer);
+      return;
+    }
     if (bits >= 1 && bits <= 24) {  // radix-16 digit sums, quad-cooperative point operations
       int nd = (bits + 3) / 4;
       uint32_t count = p.B >> (bits < 4 ? bits : 4);  // buckets per digit value (full-width digits)
