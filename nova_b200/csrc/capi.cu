@@ -154,6 +154,18 @@ struct ck_ctx {
   };
   static constexpr int NLANES = 4;
   lane lanes[NLANES];
+  // host-pointer calls (b200_msm / b200_commit / b200_msm_small) each take one of these slots -- own workspace, own
+  // stream pair -- and hold only the slot's mutex: the 4-7 commitments the reference issues concurrently from rayon
+  // threads (src/spartan/ppsnark.rs:457-470, src/r1cs/mod.rs:509-512) overlap on the device (uploads, sorts and the
+  // latency-bound tails of one call under the accumulation of another) instead of queueing on one key-wide mutex.
+  struct host_slot {
+    std::mutex mu;
+    workspace ws;
+    cudaStream_t s = nullptr, side = nullptr;
+  };
+  static constexpr int NSLOTS = 4;
+  host_slot slots[NSLOTS];
+  unsigned next_slot = 0;  // guarded by mu
   // Keys wide enough for 20-bit windows also carry 17-bit-window tables over their first 2^21
   // bases: the same key commits vectors of very different lengths (W, E, T, the halving
   // polynomials of HyperKZG, hyperkzg.rs:1083-1100), and a short MSM should not pay the
@@ -166,6 +178,11 @@ struct ck_ctx {
       l.ws.release();
       if (l.done) cudaEventDestroy(l.done);
       if (l.s) cudaStreamDestroy(l.s);
+    }
+    for (host_slot& h : slots) {
+      h.ws.release();
+      if (h.s) cudaStreamDestroy(h.s);
+      if (h.side) cudaStreamDestroy(h.side);
     }
   }
 };
@@ -788,6 +805,9 @@ int b200_ck_release(uint64_t handle) {
     g_handles.erase(it);
   }
   std::lock_guard<std::mutex> lk(ck->mu);  // wait for in-flight calls
+  for (ck_ctx* t : {ck.get(), ck->small.get()})
+    if (t)
+      for (ck_ctx::host_slot& h : t->slots) std::lock_guard<std::mutex> wait(h.mu);
   cudaSetDevice(g_dev.device);
   return B200_OK;
 }
@@ -818,11 +838,7 @@ static int lane_stream(ck_ctx::lane& ln, int index) {
 
 static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t n, void* out,
                     const void* blind = nullptr) {
-  std::lock_guard<std::mutex> lk(ck.mu);
-  int rc = ensure_workspace(ck, n + 1, 1);
-  if (rc) return rc;
-  cudaStream_t s = g_dev.stream;
-  if ((rc = ws_acquire(ck.ws, s))) return rc;
+  int rc = B200_OK;
   // Tuning hook (measured, profiles/r02a: -2 %): NOVA_B200_H2D_CHUNKS=k splits the upload into k pieces
   // and runs the digit / histogram stage of piece i on a side stream while piece i+1 is still on the bus --
   // the same chunked path b200_witness_append uses.  At most the digit stage (~0.12 ms of a 2^20 MSM) can hide.
@@ -843,9 +859,12 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
     return k < 1 ? 1 : (k > ck_ctx::NLANES ? ck_ctx::NLANES : k);
   }();
   if (e2e_slices > 1 && n >= ((size_t)1 << 23)) {
+    std::lock_guard<std::mutex> lk(ck.mu);  // the lanes belong to the key
+    cudaStream_t s = g_dev.stream;
     const int k = e2e_slices;
     rc = ensure_workspace(ck, 1, (size_t)k + 1);
     if (rc) return rc;
+    if ((rc = ws_acquire(ck.ws, s))) return rc;
     cudaEvent_t ev = nullptr;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, s));
@@ -878,23 +897,51 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
     ops_for_field(CURVES[ck.curve].base_fid)->jacobian_sum(s, (char*)ck.ws.d_out + 96, used, ck.ws.d_out);
     count_launch(1);
     CU(cudaGetLastError());
-  } else if (h2d_chunks > 1 && n >= ((size_t)1 << 16)) {
-    ck_ctx::lane& ln = ck.lanes[0];
-    if ((rc = lane_stream(ln, 0))) return rc;
+    CU(cudaMemcpyAsync(ck.ws.h_out, ck.ws.d_out, 96, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(out, ck.ws.h_out, 96);
+    return B200_OK;
+  }
+  // one host slot per call: a free one if there is any, else wait for the next in turn
+  ck_ctx::host_slot* slot = nullptr;
+  for (ck_ctx::host_slot& h : ck.slots)
+    if (h.mu.try_lock()) {
+      slot = &h;
+      break;
+    }
+  if (!slot) {
+    unsigned turn;
+    {
+      std::lock_guard<std::mutex> lk(ck.mu);
+      turn = ck.next_slot++ % ck_ctx::NSLOTS;
+    }
+    slot = &ck.slots[turn];
+    slot->mu.lock();
+  }
+  std::lock_guard<std::mutex> slk(slot->mu, std::adopt_lock);
+  if (!slot->s) {
+    CU(cudaStreamCreateWithFlags(&slot->s, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&slot->side, cudaStreamNonBlocking));
+  }
+  workspace& W = slot->ws;
+  cudaStream_t s = slot->s;
+  if ((rc = ensure_workspace(ck, W, n + 1, 1))) return rc;
+  if (h2d_chunks > 1 && n >= ((size_t)1 << 16)) {
+    cudaStream_t side = slot->side;
     const size_t total = n + (blind ? 1 : 0);
     const field_ops* sops = ops_for_field(CURVES[ck.curve].scalar_fid);
-    msm_plan p = make_plan(ck, ck.ws, base_offset, total);
+    msm_plan p = make_plan(ck, W, base_offset, total);
     cudaEvent_t ev = nullptr;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ev, s));  // order the side stream after earlier users of this workspace
-    CU(cudaStreamWaitEvent(ln.s, ev, 0));
-    CU(cudaMemsetAsync(p.counts, 0, (size_t)ck.G * ck.B * 4, ln.s));
+    CU(cudaStreamWaitEvent(side, ev, 0));
+    CU(cudaMemsetAsync(p.counts, 0, (size_t)ck.G * ck.B * 4, side));
     const size_t per = (n + h2d_chunks - 1) / h2d_chunks;
     auto piece = [&](const void* src, size_t lo, size_t hi) -> int {
-      CU(cudaMemcpyAsync((char*)ck.ws.scalars + 32 * lo, src, 32 * (hi - lo), cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync((char*)W.scalars + 32 * lo, src, 32 * (hi - lo), cudaMemcpyHostToDevice, s));
       CU(cudaEventRecord(ev, s));
-      CU(cudaStreamWaitEvent(ln.s, ev, 0));
-      sops->digits_range(ln.s, ck.ws.scalars, lo, hi, p);
+      CU(cudaStreamWaitEvent(side, ev, 0));
+      sops->digits_range(side, W.scalars, lo, hi, p);
       count_launch(1);
       return B200_OK;
     };
@@ -905,22 +952,19 @@ static int msm_host(ck_ctx& ck, size_t base_offset, const void* scalars, size_t 
       cudaEventDestroy(ev);
       return rc;
     }
-    CU(cudaEventRecord(ev, ln.s));
+    CU(cudaEventRecord(ev, side));
     CU(cudaStreamWaitEvent(s, ev, 0));
     cudaEventDestroy(ev);
-    rc = enqueue_msm(ck, ck.ws, base_offset, ck.ws.scalars, total, ck.ws.d_out, s, 0, blind != nullptr,
-                     /*digits_done=*/true);
+    rc = enqueue_msm(ck, W, base_offset, W.scalars, total, W.d_out, s, 0, blind != nullptr, /*digits_done=*/true);
   } else {
-    if (n) CU(cudaMemcpyAsync(ck.ws.scalars, scalars, n * 32, cudaMemcpyHostToDevice, s));
-    if (blind)
-      CU(cudaMemcpyAsync((char*)ck.ws.scalars + n * 32, blind, 32, cudaMemcpyHostToDevice, s));
-    rc = enqueue_msm(ck, base_offset, ck.ws.scalars, n + (blind ? 1 : 0), ck.ws.d_out, s, 0,
-                     blind != nullptr);
+    if (n) CU(cudaMemcpyAsync(W.scalars, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    if (blind) CU(cudaMemcpyAsync((char*)W.scalars + n * 32, blind, 32, cudaMemcpyHostToDevice, s));
+    rc = enqueue_msm(ck, W, base_offset, W.scalars, n + (blind ? 1 : 0), W.d_out, s, 0, blind != nullptr);
   }
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ck.ws.h_out, ck.ws.d_out, 96, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(W.h_out, W.d_out, 96, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  memcpy(out, ck.ws.h_out, 96);
+  memcpy(out, W.h_out, 96);
   return B200_OK;
 }
 

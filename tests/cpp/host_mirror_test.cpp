@@ -118,6 +118,69 @@ static int sumcheck_mode(const char* path) {
   return 0;
 }
 
+// --concurrency <log2n> [threads]: the same `threads` commitments issued from ONE thread one after the other and from
+// `threads` threads at once (what rayon does in the reference: src/spartan/ppsnark.rs:457-470); the results must be the
+// same points and the ratio of the two wall times is printed.  Synthetic key, pinned host scalars.
+#include <chrono>
+static int concurrency_mode(int log2n, int nthreads) {
+  check(b200_init(0), "b200_init");
+  const size_t n = (size_t)1 << log2n;
+  // generator of BN254 G1 (1, 2) in Montgomery form is not needed here: any valid affine point works as the seed of
+  // the synthetic key -- take it from a one-point key the library builds from the curve generator it is given
+  unsigned char gen[64] = {0};
+  {  // (1, 2) in Montgomery form: R mod q and 2R mod q for BN254 Fq
+    const uint64_t one[4] = {0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full};
+    const uint64_t two[4] = {0xa6ba871b8b1e1b3aull, 0x14f1d651eb8e167bull, 0xccdd46def0f28c58ull, 0x1c14ef83340fbe5eull};
+    memcpy(gen, one, 32);
+    memcpy(gen + 32, two, 32);
+  }
+  uint64_t ck = 0;
+  check(b200_ck_setup_synthetic(0, gen, 0x5EED, n, 0, 0, &ck), "ck_setup_synthetic");
+  std::vector<void*> bufs(nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    check(b200_host_alloc(32 * n, &bufs[t]), "host_alloc");
+    uint64_t* w = (uint64_t*)bufs[t];
+    uint64_t x = 0x9E3779B97F4A7C15ull * (t + 1);
+    for (size_t i = 0; i < 4 * n; i++) {  // xorshift words; top limb masked below the modulus
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+      w[i] = (i % 4 == 3) ? (x & 0x0FFFFFFFFFFFFFFFull) : x;
+    }
+  }
+  std::vector<Point> serial(nthreads), conc(nthreads);
+  auto commit = [&](int t, Point* out) { check(b200_commit(ck, bufs[t], n, nullptr, out), "commit"); };
+  for (int t = 0; t < nthreads; t++) commit(t, &serial[t]);  // warm-up (workspaces)
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&, t] { commit(t, &conc[t]); });
+    for (auto& x : th) x.join();
+  }
+  const int reps = 5;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; r++)
+    for (int t = 0; t < nthreads; t++) commit(t, &serial[t]);
+  auto t1 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; r++) {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&, t] { commit(t, &conc[t]); });
+    for (auto& x : th) x.join();
+  }
+  auto t2 = std::chrono::steady_clock::now();
+  double ms_serial = std::chrono::duration<double, std::milli>(t1 - t0).count() / reps;
+  double ms_conc = std::chrono::duration<double, std::milli>(t2 - t1).count() / reps;
+  // same points?  compare cross-multiplied (Jacobian coordinates differ between runs): done by the Python side from the dump
+  std::printf("{\"what\": \"%d commits of 2^%d scalars, serial vs %d threads\", \"ms_serial\": %.4f, \"ms_concurrent\": %.4f, "
+              "\"speedup\": %.3f}\n", nthreads, log2n, nthreads, ms_serial, ms_conc, ms_serial / ms_conc);
+  FILE* f = std::fopen("/tmp/concurrency_points.bin", "wb");
+  if (f) {
+    std::fwrite(serial.data(), sizeof(Point), nthreads, f);
+    std::fwrite(conc.data(), sizeof(Point), nthreads, f);
+    std::fclose(f);
+  }
+  for (void* b : bufs) b200_host_free(b);
+  b200_ck_release(ck);
+  return 0;
+}
+
 // Jacobian -> compare with expected affine without inversion: X == x*Z^2, Y == y*Z^3 is checked on
 // the Python side; here we only dump the raw result bytes.
 int main(int argc, char** argv) {
@@ -128,6 +191,8 @@ int main(int argc, char** argv) {
   }
   if (std::string(argv[1]) == "--fold") return argc > 2 ? fold_mode(argv[2]) : 2;
   if (std::string(argv[1]) == "--sumcheck") return argc > 2 ? sumcheck_mode(argv[2]) : 2;
+  if (std::string(argv[1]) == "--concurrency")
+    return argc > 2 ? concurrency_mode(std::atoi(argv[2]), argc > 3 ? std::atoi(argv[3]) : 4) : 2;
   std::ifstream f(argv[1], std::ios::binary);
   check(b200_init(0), "b200_init");
   auto bases = rd<Affine>(f);

@@ -222,3 +222,22 @@ def check_sumcheck(exe, oracle, tmp_path):
         assert [flat[ncoef * j:ncoef * (j + 1)] for j in range(l)] == [list(q) for q in exp[0]]
         assert mont(rs) == list(exp[1]) and mont(finals) == list(exp[2])
         assert struct.unpack("<Q", trb[:8])[0] == t.round and trb[8:] == t.state and struct.unpack("<Q", left)[0] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log2n", [14, 18])
+def test_cpp_concurrent_commits_overlap_and_agree(log2n):
+    """host_mirror_test --concurrency: 4 commitments issued from one thread in turn and from 4 threads at once
+    (rayon in the reference: ppsnark.rs:457-470) give the same points; each call takes its own host slot (workspace +
+    streams) of the key, so the calls overlap on the device -- the measured ratio is printed (profiles/r02e)."""
+    import json
+
+    from nova_b200.provider import Curve, _jac_to_affine
+    build()
+    out = subprocess.check_output([EXE, "--concurrency", str(log2n), "4"], text=True, timeout=300)
+    res = json.loads(out.strip().splitlines()[-1])
+    raw = open("/tmp/concurrency_points.bin", "rb").read()
+    pts = [_jac_to_affine(Curve(0), raw[96 * i:96 * i + 96]) for i in range(8)]
+    assert pts[:4] == pts[4:] and len(set(pts[:4])) == 4
+    assert res["ms_serial"] > 0 and res["ms_concurrent"] > 0
+    print(res)
