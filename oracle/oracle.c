@@ -86,8 +86,8 @@ static inline void fe_neg(const orc_field_t* F, fe* r, const fe* a) {
   sub4(r->l, F->p, a->l);
 }
 static inline void fe_dbl(const orc_field_t* F, fe* r, const fe* a) { fe_add(F, r, a, a); }
-/* CIOS Montgomery product */
-static inline void fe_mul(const orc_field_t* F, fe* r, const fe* a, const fe* b) {
+/* CIOS Montgomery product, portable form (unsigned __int128) */
+static inline void fe_mul_portable(const orc_field_t* F, fe* r, const fe* a, const fe* b) {
   uint64_t t[6] = {0, 0, 0, 0, 0, 0};
   for (int i = 0; i < 4; i++) {
     u128 c = 0;
@@ -112,6 +112,190 @@ static inline void fe_mul(const orc_field_t* F, fe* r, const fe* a, const fe* b)
   }
   if (t[4] || geq(t, F->p)) sub4(r->l, t, F->p); else memcpy(r->l, t, 32);
 }
+/* The same product on the mulx / adcx-style path (BMI2 + ADX): what halo2curves' `asm` feature (README.md:54, "up to
+ * 50 %") gives the reference on x86-64 -- so that the CPU baseline is not flattered by a slow multiplier.  Per row:
+ * four mulx, the low halves on the adcx carry chain and the high halves on the adox chain (inline assembly: gcc's
+ * _addcarry_u64 intrinsics serialise the two chains and come out no faster than the portable form).  Selected at run time
+ * (cpu_has_adx; ORACLE_NO_ADX=1 forces the portable form); bit-identical to it (tests/test_oracle_golden.py). */
+#if defined(__x86_64__)
+/* CIOS rows fully unrolled; accumulators rotate through r11-r15, rbx (generated, see the comment above):
+ *   row i:    (t0..t5) += a * b[i]           mulx + adcx (low halves) / adox (high halves), two carry chains
+ *             m = t0 * inv ; (t0..t5) += m * p   -> t0 == 0, the register is reused as the next row's t5 */
+__attribute__((target("bmi2,adx"))) static void fe_mul_adx(const orc_field_t* F, fe* r, const fe* a, const fe* b) {
+  uint64_t t[5];
+  const uint64_t inv = F->inv;
+  __asm__ volatile(
+      "xorl %%r11d, %%r11d\n\t"
+      "xorl %%r12d, %%r12d\n\t"
+      "xorl %%r13d, %%r13d\n\t"
+      "xorl %%r14d, %%r14d\n\t"
+      "xorl %%r15d, %%r15d\n\t"
+      "xorl %%ebx, %%ebx\n\t"
+      "movq 0(%[b]), %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r11\n\t"
+      "adoxq %%r9, %%r12\n\t"
+      "mulxq 8(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r12\n\t"
+      "adoxq %%r9, %%r13\n\t"
+      "mulxq 16(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r13\n\t"
+      "adoxq %%r9, %%r14\n\t"
+      "mulxq 24(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "adcxq %%r10, %%r15\n\t"
+      "adoxq %%r10, %%rbx\n\t"
+      "adcxq %%r10, %%rbx\n\t"
+      "movq %%r11, %%rdx\n\t"
+      "imulq %[inv], %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r11\n\t"
+      "adoxq %%r9, %%r12\n\t"
+      "mulxq 8(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r12\n\t"
+      "adoxq %%r9, %%r13\n\t"
+      "mulxq 16(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r13\n\t"
+      "adoxq %%r9, %%r14\n\t"
+      "mulxq 24(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "adcxq %%r10, %%r15\n\t"
+      "adoxq %%r10, %%rbx\n\t"
+      "adcxq %%r10, %%rbx\n\t"
+      "movq 8(%[b]), %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r12\n\t"
+      "adoxq %%r9, %%r13\n\t"
+      "mulxq 8(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r13\n\t"
+      "adoxq %%r9, %%r14\n\t"
+      "mulxq 16(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "mulxq 24(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r15\n\t"
+      "adoxq %%r9, %%rbx\n\t"
+      "adcxq %%r10, %%rbx\n\t"
+      "adoxq %%r10, %%r11\n\t"
+      "adcxq %%r10, %%r11\n\t"
+      "movq %%r12, %%rdx\n\t"
+      "imulq %[inv], %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r12\n\t"
+      "adoxq %%r9, %%r13\n\t"
+      "mulxq 8(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r13\n\t"
+      "adoxq %%r9, %%r14\n\t"
+      "mulxq 16(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "mulxq 24(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r15\n\t"
+      "adoxq %%r9, %%rbx\n\t"
+      "adcxq %%r10, %%rbx\n\t"
+      "adoxq %%r10, %%r11\n\t"
+      "adcxq %%r10, %%r11\n\t"
+      "movq 16(%[b]), %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r13\n\t"
+      "adoxq %%r9, %%r14\n\t"
+      "mulxq 8(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "mulxq 16(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r15\n\t"
+      "adoxq %%r9, %%rbx\n\t"
+      "mulxq 24(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%rbx\n\t"
+      "adoxq %%r9, %%r11\n\t"
+      "adcxq %%r10, %%r11\n\t"
+      "adoxq %%r10, %%r12\n\t"
+      "adcxq %%r10, %%r12\n\t"
+      "movq %%r13, %%rdx\n\t"
+      "imulq %[inv], %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r13\n\t"
+      "adoxq %%r9, %%r14\n\t"
+      "mulxq 8(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "mulxq 16(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r15\n\t"
+      "adoxq %%r9, %%rbx\n\t"
+      "mulxq 24(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%rbx\n\t"
+      "adoxq %%r9, %%r11\n\t"
+      "adcxq %%r10, %%r11\n\t"
+      "adoxq %%r10, %%r12\n\t"
+      "adcxq %%r10, %%r12\n\t"
+      "movq 24(%[b]), %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "mulxq 8(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r15\n\t"
+      "adoxq %%r9, %%rbx\n\t"
+      "mulxq 16(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%rbx\n\t"
+      "adoxq %%r9, %%r11\n\t"
+      "mulxq 24(%[a]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r11\n\t"
+      "adoxq %%r9, %%r12\n\t"
+      "adcxq %%r10, %%r12\n\t"
+      "adoxq %%r10, %%r13\n\t"
+      "adcxq %%r10, %%r13\n\t"
+      "movq %%r14, %%rdx\n\t"
+      "imulq %[inv], %%rdx\n\t"
+      "xorl %%r10d, %%r10d\n\t"
+      "mulxq 0(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r14\n\t"
+      "adoxq %%r9, %%r15\n\t"
+      "mulxq 8(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r15\n\t"
+      "adoxq %%r9, %%rbx\n\t"
+      "mulxq 16(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%rbx\n\t"
+      "adoxq %%r9, %%r11\n\t"
+      "mulxq 24(%[p]), %%r8, %%r9\n\t"
+      "adcxq %%r8, %%r11\n\t"
+      "adoxq %%r9, %%r12\n\t"
+      "adcxq %%r10, %%r12\n\t"
+      "adoxq %%r10, %%r13\n\t"
+      "adcxq %%r10, %%r13\n\t"
+      "movq %%r15, 0(%[out])\n\t"
+      "movq %%rbx, 8(%[out])\n\t"
+      "movq %%r11, 16(%[out])\n\t"
+      "movq %%r12, 24(%[out])\n\t"
+      "movq %%r13, 32(%[out])\n\t"
+      :
+      : [a] "r"(a->l), [b] "r"(b->l), [p] "r"(F->p), [inv] "m"(inv), [out] "r"(t)
+      : "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "rbx", "cc", "memory");
+  if (t[4] || geq(t, F->p)) sub4(r->l, t, F->p); else memcpy(r->l, t, 32);
+}
+static int g_have_adx = -1;
+static inline int cpu_has_adx(void) {
+  if (g_have_adx < 0) {
+    const char* e = getenv("ORACLE_NO_ADX");
+    g_have_adx = (e == NULL || e[0] != '1') && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx");
+  }
+  return g_have_adx;
+}
+static inline void fe_mul(const orc_field_t* F, fe* r, const fe* a, const fe* b) {
+  if (cpu_has_adx()) fe_mul_adx(F, r, a, b);
+  else fe_mul_portable(F, r, a, b);
+}
+#else
+static inline void fe_mul(const orc_field_t* F, fe* r, const fe* a, const fe* b) { fe_mul_portable(F, r, a, b); }
+#endif
 static inline void fe_sqr(const orc_field_t* F, fe* r, const fe* a) { fe_mul(F, r, a, a); }
 static void fe_one(const orc_field_t* F, fe* r) { memcpy(r->l, F->r, 32); }
 static void fe_from_mont(const orc_field_t* F, fe* r, const fe* a) {

@@ -207,3 +207,27 @@ def test_sumcheck_kats_and_c_vs_python():
         assert ints(co.bind_top(fid, pk(A), mont_bytes(p, r))) == pyref.bind_top(p, A, r)
         A, B, C = pyref.bind_top(p, A, r), pyref.bind_top(p, B, r), pyref.bind_top(p, C, r)
         eq.bound(r)
+
+
+def test_adx_and_portable_multipliers_agree():
+    """oracle.c has two Montgomery multipliers (mulx/adcx/adox inline assembly, selected when the CPU has BMI2 + ADX, and
+    the portable unsigned __int128 form): the same field products and the same MSM, bit for bit, in a second
+    interpreter with ORACLE_NO_ADX=1.  (The tests above run on whichever this host selects.)"""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    prog = ("import sys, hashlib; sys.path.insert(0, %r)\n"
+            "from oracle import coracle as co\n"
+            "h = hashlib.sha256()\n"
+            "for fid in range(4):\n"
+            "    A, B = co.gen_scalars(fid, 5, 4096), co.gen_scalars(fid, 6, 4096)\n"
+            "    h.update(co.fe_op(fid, 2, A, B)); h.update(co.fe_op(fid, 3, A))\n"
+            "for cid in range(4):\n"
+            "    h.update(co.msm(cid, co.gen_scalars({0: 0, 1: 1, 2: 3, 3: 2}[cid], 9, 3000), co.gen_bases(cid, 3000)))\n"
+            "print(h.hexdigest())\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, ORACLE_NO_ADX=flag)
+        outs.append(subprocess.check_output([sys.executable, "-c", prog], env=env, text=True).strip())
+    assert outs[0] == outs[1] and len(outs[0]) == 64
