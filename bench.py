@@ -445,7 +445,8 @@ def cpu_reference_run(log2n, steps, warmup, sc_np=None):
             "sample": f"first 2^{n.bit_length() - 1} of the 2^{log2n} pairs, {steps} run(s), {dt * 1e3:.1f} ms each",
             "note": "C restatement of msm.rs (signed split + bit-width partition; halo2curves msm_best "
                     "restated as signed-digit Pippenger, c = ln(n)+2, (window x slice) jobs over all "
-                    "cores), pthreads, __int128 Montgomery (~21 ns/mul on a 2.1 GHz Xeon), no hand asm"}
+                    "cores), pthreads; Montgomery products on the mulx/adcx/adox path (inline assembly -- what halo2curves' "
+                    "`asm` feature gives the reference) when the CPU has BMI2 + ADX, unsigned __int128 otherwise"}
 
 
 def run_reference(args):
