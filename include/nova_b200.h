@@ -181,6 +181,26 @@ int b200_peer_group_status(uint64_t group);
 int b200_msm_sharded_dev(uint64_t ck_handle, size_t base_offset, const void* d_scalars_mont, size_t n,
                          uint64_t group, void* d_out_jacobian, void* stream);
 
+/* ---- Poseidon random oracle on the device ----------------------------------------------------
+ * `PoseidonRO::squeeze` (src/provider/poseidon.rs:93-127): the sponge over the vendored neptune permutation
+ * (src/frontend/gadgets/poseidon/), IO pattern [Absorb(n), Squeeze(1)], Simplex mode -- the hash NIFS::prove draws the
+ * folding challenge from (src/nova/nifs.rs:47-63).  The constants (PoseidonConstants::new_with_strength_and_type(
+ * Standard, Sponge): R_F, R_P, Grain-LFSR round constants, Cauchy MDS) come from the host (nova_b200/poseidon.py mirrors
+ * their generation) in Montgomery form: rc[(R_F + R_P) * (arity + 1)], mds[(arity + 1)^2] row-major.
+ * out = three field elements: the full hash (Montgomery), the challenge = its low num_bits bits (bit num_bits - 1
+ * forced when start_with_one; Montgomery, same field), and the challenge as a canonical integer -- which
+ * b200_to_mont_dev turns into an element of the OTHER curve's field (base_as_scalar), so that
+ * commit_T -> absorb -> r -> fold can be enqueued without a host round trip. */
+int b200_poseidon_register(int field_id, int arity, int r_f, int r_p, const void* rc_mont, const void* mds_mont,
+                           uint64_t* poseidon_handle);
+int b200_poseidon_release(uint64_t poseidon_handle);
+int b200_poseidon_ro(uint64_t poseidon_handle, const void* elems_mont, size_t n, int num_bits, int start_with_one,
+                     void* out96);
+int b200_poseidon_ro_dev(uint64_t poseidon_handle, const void* d_elems_mont, size_t n, int num_bits, int start_with_one,
+                         void* d_out96, void* stream);
+/* out[i] = in[i] as a Montgomery element of field_id, in[i] a canonical integer < p */
+int b200_to_mont_dev(int field_id, const void* d_canonical, size_t n, void* d_out, void* stream);
+
 /* ---- ONE process, N GPUs behind one call ("b200_init(device_count) + a key sharded across GPUs") ----
  * A host that calls CommitmentEngine::commit / DlogGroupExt::vartime_multiscalar_mul once (traits.rs:77-117,
  * pedersen.rs:263-270) gets the whole node: the key is distributed block-cyclically over the devices (every prefix

@@ -1347,6 +1347,114 @@ int b200_msm_sharded_dev(uint64_t handle, size_t base_offset, const void* d_scal
 #endif
 }
 
+// ---- Poseidon random oracle on the device (src/provider/poseidon.rs:41-127) ---------------
+namespace {
+struct poseidon_ctx {
+  int fid = 0, t = 0, r_f = 0, r_p = 0;
+  void *rc = nullptr, *mds = nullptr;
+  ~poseidon_ctx() {
+    if (rc) cudaFree(rc);
+    if (mds) cudaFree(mds);
+  }
+};
+std::mutex g_pos_mu;
+std::map<uint64_t, std::shared_ptr<poseidon_ctx>> g_pos;
+uint64_t g_next_pos = 1;
+
+// IOPattern([Absorb(n), Squeeze(1)]).value(0) (sponge/api.rs:27-109): u128 arithmetic mod 2^128
+void poseidon_tag(uint32_t n, unsigned char out32[32]) {
+  typedef unsigned __int128 u128;
+  const u128 base = (u128)0 - 159;
+  u128 x_i = 1, state = 0;
+  auto update = [&](uint32_t a) {
+    x_i *= base;
+    state += x_i * (u128)a;
+  };
+  if (n) update(n + (1u << 31));  // Absorb(n); a zero-count op is skipped (finish_op)
+  update(1);                      // Squeeze(1)
+  update(0);                      // domain separator
+  memset(out32, 0, 32);
+  memcpy(out32, &state, 16);
+}
+}  // namespace
+
+int b200_poseidon_register(int fid, int arity, int r_f, int r_p, const void* rc_mont, const void* mds_mont, uint64_t* handle) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!ops_for_field(fid)) return fail(B200_E_ARG, "unknown field id %d", fid);
+  if (arity < 1 || arity + 1 > 25 || r_f < 2 || (r_f & 1) || r_p < 0 || !rc_mont || !mds_mont || !handle)
+    return fail(B200_E_ARG, "bad Poseidon parameters (arity %d, R_F %d, R_P %d)", arity, r_f, r_p);
+  auto c = std::make_shared<poseidon_ctx>();
+  c->fid = fid;
+  c->t = arity + 1;
+  c->r_f = r_f;
+  c->r_p = r_p;
+  const size_t nrc = (size_t)(r_f + r_p) * c->t, nm = (size_t)c->t * c->t;
+  CU(cudaMalloc(&c->rc, nrc * 32));
+  CU(cudaMalloc(&c->mds, nm * 32));
+  CU(cudaMemcpyAsync(c->rc, rc_mont, nrc * 32, cudaMemcpyHostToDevice, g_dev.stream));
+  CU(cudaMemcpyAsync(c->mds, mds_mont, nm * 32, cudaMemcpyHostToDevice, g_dev.stream));
+  CU(cudaStreamSynchronize(g_dev.stream));
+  std::lock_guard<std::mutex> lk(g_pos_mu);
+  *handle = g_next_pos++;
+  g_pos[*handle] = c;
+  return B200_OK;
+}
+int b200_poseidon_release(uint64_t handle) {
+  std::lock_guard<std::mutex> lk(g_pos_mu);
+  if (!g_pos.erase(handle)) return fail(B200_E_HANDLE, "unknown Poseidon handle %llu", (unsigned long long)handle);
+  return B200_OK;
+}
+int b200_poseidon_ro_dev(uint64_t handle, const void* d_elems, size_t n, int num_bits, int start_with_one, void* d_out96,
+                         void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  std::shared_ptr<poseidon_ctx> c;
+  {
+    std::lock_guard<std::mutex> lk(g_pos_mu);
+    auto it = g_pos.find(handle);
+    if (it == g_pos.end()) return fail(B200_E_HANDLE, "unknown Poseidon handle %llu", (unsigned long long)handle);
+    c = it->second;
+  }
+  if (!d_out96 || (n && !d_elems)) return fail(B200_E_ARG, "null pointer");
+  if (num_bits < 1 || num_bits > 250) return fail(B200_E_ARG, "num_bits %d outside 1..250", num_bits);
+  if (n >= (1u << 31)) return fail(B200_E_ARG, "too many elements");
+  cudaStream_t s = stream ? (cudaStream_t)stream : g_dev.stream;
+  unsigned char tag[32];
+  poseidon_tag((uint32_t)n, tag);
+  void* d_tag = nullptr;  // stream-ordered scratch for the 32-byte tag
+  CU(cudaMallocAsync(&d_tag, 32, s));
+  CU(cudaMemcpyAsync(d_tag, tag, 32, cudaMemcpyHostToDevice, s));  // (pageable source: staged before the call returns)
+  ops_for_field(c->fid)->poseidon_ro(s, c->t, c->r_f, c->r_p, c->rc, c->mds, d_elems, (uint32_t)n, d_tag, num_bits,
+                                     start_with_one, d_out96);
+  count_launch(1);
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_tag, s));
+  return B200_OK;
+}
+int b200_poseidon_ro(uint64_t handle, const void* elems_mont, size_t n, int num_bits, int start_with_one, void* out96) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!out96 || (n && !elems_mont)) return fail(B200_E_ARG, "null pointer");
+  dev_buf in, out;
+  if ((rc = in.alloc(n * 32 + 32)) || (rc = out.alloc(96))) return rc;
+  if (n) CU(cudaMemcpyAsync(in.p, elems_mont, n * 32, cudaMemcpyHostToDevice, g_dev.stream));
+  rc = b200_poseidon_ro_dev(handle, in.p, n, num_bits, start_with_one, out.p, g_dev.stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out96, out.p, 96, cudaMemcpyDeviceToHost, g_dev.stream));
+  CU(cudaStreamSynchronize(g_dev.stream));
+  return B200_OK;
+}
+int b200_to_mont_dev(int fid, const void* d_canonical, size_t n, void* d_out, void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (n && (!d_canonical || !d_out)) return fail(B200_E_ARG, "null pointer");
+    ops->to_mont(stream ? (cudaStream_t)stream : g_dev.stream, d_canonical, n, d_out);
+    count_launch(1);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
+
 // ---- ONE process, N GPUs: a commitment key sharded over the devices behind a single call -----------------
 // What SURVEY.md §8b asked of the boundary: a Rust host calls DlogGroupExt::vartime_multiscalar_mul /
 // CommitmentEngine::commit ONCE (src/provider/traits.rs:77-117, pedersen.rs:263-270) and the node's GPUs share the

@@ -83,6 +83,10 @@ struct field_ops {
   // test SRS (hyperkzg.rs:357-376): out[i] = u^i canonical (scalar field) ; bases[i] = [scalars[i]] G (base field)
   void (*powers_canonical)(cudaStream_t, const void* u_mont, size_t n, void* out);
   void (*scalar_bases)(cudaStream_t, void* bases, size_t n, const void* gen_affine, const void* scalars_canonical);
+  // Poseidon RO squeeze on the device (poseidon.cuh): t, r_f, r_p; rc / mds Montgomery; out = [hash, challenge, canonical challenge]
+  void (*poseidon_ro)(cudaStream_t, int t, int r_f, int r_p, const void* rc, const void* mds, const void* elems, uint32_t n,
+                      const void* tag_canonical, int num_bits, int start_with_one, void* out);
+  void (*to_mont)(cudaStream_t, const void* in_canonical, size_t n, void* out);
   // sharded MSM whose rank has no pairs: publish the identity and sum the peers' partials (plan.peer)
   void (*exchange_identity)(cudaStream_t, const msm_plan&, void* out_jac);
 };

@@ -6,6 +6,7 @@
 #include "poly_kernels.cuh"
 #include "transcript.cuh"
 #include "transcript_batched.cuh"
+#include "poseidon.cuh"
 
 namespace nova {
 
@@ -378,6 +379,14 @@ struct ops_impl {
   static void scalar_bases(cudaStream_t s, void* bases, size_t n, const void* gen, const void* scalars) {
     if (n) k_scalar_bases<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(bases, n, gen, scalars);
   }
+  static void poseidon_ro(cudaStream_t s, int t, int r_f, int r_p, const void* rc, const void* mds, const void* elems,
+                          uint32_t n, const void* tag, int num_bits, int start_with_one, void* out) {
+    poseidon_desc d{t, r_f, r_p};
+    k_poseidon_ro<F><<<1, 32 * t, 0, s>>>(d, rc, mds, elems, n, tag, num_bits, start_with_one, out);
+  }
+  static void to_mont(cudaStream_t s, const void* in, size_t n, void* out) {
+    if (n) k_to_mont<F><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, n, out);
+  }
   static void exchange_identity(cudaStream_t s, const msm_plan& p, void* out_jac) {
 #if !defined(NOVA_MSM_ARITH29)
     k_red_final_q<F><<<1, 384, 0, s>>>(nullptr, 0, 4, 4, out_jac, p.peer);  // G = 0: the local partial is the identity
@@ -389,7 +398,7 @@ struct ops_impl {
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
                      sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve,
-                     powers_canonical, scalar_bases, exchange_identity};
+                     powers_canonical, scalar_bases, poseidon_ro, to_mont, exchange_identity};
   }
 };
 

@@ -42,6 +42,11 @@ SIGNATURES = {
     "b200_ck_register": [c_int, _P, c_size_t, _P, c_int, ctypes.POINTER(c_u64)],
     "b200_ck_register_checked": [c_int, _P, c_size_t, _P, c_int, ctypes.POINTER(c_u64), ctypes.POINTER(c_size_t)],
     "b200_ck_setup_synthetic": [c_int, _P, c_u64, c_size_t, c_int, c_int, ctypes.POINTER(c_u64)],
+    "b200_poseidon_register": [c_int, c_int, c_int, c_int, _P, _P, ctypes.POINTER(c_u64)],
+    "b200_poseidon_release": [c_u64],
+    "b200_poseidon_ro": [c_u64, _P, c_size_t, c_int, c_int, _P],
+    "b200_poseidon_ro_dev": [c_u64, _P, c_size_t, c_int, c_int, _P, _P],
+    "b200_to_mont_dev": [c_int, _P, c_size_t, _P, _P],
     "b200_mgpu_init": [c_int, ctypes.POINTER(c_int)],
     "b200_mgpu_ck_register": [c_int, _P, c_size_t, _P, c_int, ctypes.POINTER(c_u64)],
     "b200_mgpu_ck_release": [c_u64],
