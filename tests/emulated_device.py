@@ -432,6 +432,46 @@ class EmulatedDevice:
         _wr(out, bases[64 * offset:64 * (offset + n)])
         return 0
 
+    # ---- Poseidon RO (answered by oracle/poseidon_ref.py) ----------------------------------------------------
+    def b200_poseidon_register(self, fid, arity, r_f, r_p, rc, mds, out_handle):
+        from oracle import poseidon_ref as pr
+        P = FIELD_MODULUS[fid]
+        c = pr.cached_constants(P, arity)
+        t = arity + 1
+        got_rc = [from_mont_bytes(P, _rd(rc, 32 * (r_f + r_p) * t)[32 * i:32 * i + 32]) for i in range((r_f + r_p) * t)]
+        got_m = [from_mont_bytes(P, _rd(mds, 32 * t * t)[32 * i:32 * i + 32]) for i in range(t * t)]
+        if (r_f, r_p) != (c.r_f, c.r_p) or got_rc != c.rc or got_m != [x for row in c.m for x in row]:
+            self.err = b"Poseidon constants differ from the oracle's"
+            return 1
+        if not hasattr(self, "poseidon"):
+            self.poseidon = {}
+        self.poseidon[self.next_handle] = (fid, arity)
+        out_handle._obj.value = self.next_handle
+        self.next_handle += 1
+        return 0
+
+    def b200_poseidon_ro_dev(self, handle, elems, n, num_bits, start_with_one, out, stream):
+        from oracle import poseidon_ref as pr
+        fid, arity = self.poseidon[handle]
+        P = FIELD_MODULUS[fid]
+        raw = _rd(elems, 32 * n)
+        ro = pr.PoseidonRO(P, arity)
+        for i in range(n):
+            ro.absorb(from_mont_bytes(P, raw[32 * i:32 * i + 32]))
+        c = ro.squeeze(num_bits, bool(start_with_one))
+        h = ro.state[0]
+        _wr(out, mont_bytes(P, h) + mont_bytes(P, c) + c.to_bytes(32, "little"))
+        return 0
+
+    def b200_poseidon_ro(self, handle, elems, n, num_bits, start_with_one, out):
+        return self.b200_poseidon_ro_dev(handle, elems, n, num_bits, start_with_one, out, None)
+
+    def b200_to_mont_dev(self, fid, src, n, dst, stream):
+        P = FIELD_MODULUS[fid]
+        raw = _rd(src, 32 * n)
+        _wr(dst, b"".join(mont_bytes(P, int.from_bytes(raw[32 * i:32 * i + 32], "little")) for i in range(n)))
+        return 0
+
     def b200_ck_release(self, handle):
         self.keys.pop(handle, None)
         return 0

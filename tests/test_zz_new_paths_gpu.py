@@ -501,3 +501,20 @@ def test_one_process_all_gpus_commit(tmp_path):
     out = subprocess.run([_sys.executable, os.path.join(here, "mgpu_commit_worker.py"), ",".join(map(str, range(n)))],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+@pytest.mark.parametrize("arity", [5, 24])
+def test_poseidon_ro_on_device(b200, fid, arity):
+    """k_poseidon_ro (csrc/poseidon.cuh) == oracle/poseidon_ref.py: all four fields, the wide and the narrow sponge,
+    inputs around the rate (several permutations while absorbing), two consecutive squeezes."""
+    import poseidon_parity
+    from nova_b200 import poseidon
+    poseidon.PoseidonConstants._cache.clear()
+    poseidon_parity.run_ro(b200, fid, arity)
+
+
+@pytest.mark.parametrize("cid", [0, 1, 2, 3])
+def test_poseidon_nifs_challenge_on_device(b200, oracle, cid):
+    import poseidon_parity
+    poseidon_parity.run_nifs_challenge(b200, oracle, cid)
