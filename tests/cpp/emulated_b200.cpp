@@ -27,6 +27,7 @@ int orc_bind_top(int fid, void* z, size_t n, const void* r);
 int orc_field_from_u64(int fid, const uint64_t* v, size_t n, void* out);
 int orc_fe_op(int fid, int op, const void* a, const void* b, void* out, size_t n);
 int orc_on_curve(int curve, const void* pt, const void* b_mont);
+int orc_gen_bases(int curve, const void* gen, const uint64_t* k0, size_t n, void* out);
 int orc_sc_eval(int fid, int form, const void* a, const void* b, const void* c, size_t len, const void* eql, const void* eqr,
                 int shift, void* out);
 int orc_spmv(int fid, const void* data, const uint64_t* indices, const uint64_t* indptr, size_t rows, const void* z, void* out);
@@ -110,6 +111,15 @@ int b200_ck_register(int curve, const void* bases, size_t n, const void* h, int,
   return B200_OK;
 }
 int b200_ck_release(uint64_t h) { std::lock_guard<std::mutex> lk(g_mu); return g_keys.erase(h) ? B200_OK : B200_E_HANDLE; }
+int b200_host_alloc(size_t bytes, void** p) { *p = malloc(bytes ? bytes : 1); return *p ? B200_OK : B200_E_NOMEM; }
+int b200_host_free(void* p) { free(p); return B200_OK; }
+int b200_ck_setup_synthetic(int curve, const void* gen, uint64_t k0, size_t n, int with_h, int, uint64_t* handle) {
+  if (curve < 0 || curve > 3 || !gen || !n || !handle) return fail(B200_E_ARG, "bad key");
+  std::vector<unsigned char> pts(64 * (n + 1));
+  uint64_t k[4] = {k0, 0, 0, 0};
+  if (orc_gen_bases(curve, gen, k, n + 1, pts.data())) return fail(B200_E_ARG, "orc_gen_bases failed");  // P_i = (k0 + i) G
+  return b200_ck_register(curve, pts.data(), n, with_h ? pts.data() + 64 * n : nullptr, 0, handle);
+}
 
 int b200_msm(uint64_t h, size_t off, const void* scalars, size_t n, void* out) {
   auto k = lookup(g_keys, h);

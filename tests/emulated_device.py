@@ -73,6 +73,11 @@ class EmulatedDevice:
             self.graveyard.append(buf)  # keep the pages mapped so that such a read cannot crash the test run
         return 0
 
+    def b200_keccak256(self, data, n, out):
+        from oracle.pyref import keccak256
+        _wr(out, keccak256(bytes(data[:n]) if isinstance(data, (bytes, bytearray)) else _rd(data, n)))
+        return 0
+
     def b200_host_alloc(self, nbytes, out_ptr):
         return self.b200_dev_alloc(nbytes, out_ptr)
 

@@ -37,6 +37,18 @@ __global__ void probe(uint64_t* out, uint32_t a0, uint32_t b0, double d0) {
       } else if (OP == 8) {  // wide mad with carry-out only, carry discarded into ONE shared counter per 2
         asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
                      : "+r"(lo[k]), "+r"(hi[k]) : "r"(x), "r"(y));
+      } else if (OP == 9) {  // co-issue probe: one carry-chain pair AND one independent DFMA per slot
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                     : "+r"(lo[k]), "+r"(lo[(k + 1) % ILP]) : "r"(x), "r"(y));
+        asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(fd[k]) : "d"(da), "d"(db));
+      } else if (OP == 10) {  // co-issue probe: one carry-less wide product AND one DFMA per slot
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
+        asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(fd[k]) : "d"(da), "d"(db));
+      } else if (OP == 11) {  // two DFMAs per carry-chain pair
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                     : "+r"(lo[k]), "+r"(lo[(k + 1) % ILP]) : "r"(x), "r"(y));
+        asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(fd[k]) : "d"(da), "d"(db));
+        asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(fd[(k + 3) % ILP]) : "d"(db), "d"(da));
       } else if (OP == 6) {  // carry chain pair (the field.cuh pattern)
         asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
                      : "+r"(lo[k]), "+r"(lo[(k + 1) % ILP]) : "r"(x), "r"(y));
@@ -149,6 +161,9 @@ int main() {
   run<2>("add.u32 (IADD3)", 1);
   run<3>("add.u64", 1);
   run<4>("fma.rz.f64 (DFMA)", 1);
+  run<9>("chain pair + 1 DFMA (slots)", 1);
+  run<10>("IMAD.WIDE + 1 DFMA (slots)", 1);
+  run<11>("chain pair + 2 DFMA (slots)", 1);
   run_chain();
   run_femul<1>(2); run_femul<1>(4); run_femul<1>(8);
   run_femul<2>(2); run_femul<2>(4);
