@@ -316,10 +316,10 @@ def run_b200(args):
             traffic = None
     cc, nt = ctypes.c_int(0), ctypes.c_int(0)
     check(L.b200_ck_len(ck.handle, None, ctypes.byref(cc), ctypes.byref(nt)))
-    # the pipe that actually bounds the kernel: 10 field products per XYZZ mixed addition (8M + 2S,
-    # madd-2008-s), one addition per non-zero digit; ceiling = the carry-chain
-    # multiplier's measured 64.2 G field-mul/s (tools/microbench.cu, profiles/r01l_microbench_carry_save.txt)
-    fe_muls = 10.0 * n * nt.value * (1.0 - 2.0 ** -cc.value)
+    # the pipe that actually bounds the kernel: an XYZZ mixed addition (madd-2008-s: 8M + 2S) costs 9.5 full
+    # Montgomery products here (y3 = r(q - x3) - y1 ppp shares ONE reduction between its two products), one addition
+    # per non-zero digit; ceiling = the carry-chain multiplier's measured 64.2 G field-mul/s (tools/microbench.cu)
+    fe_muls = 9.5 * n * nt.value * (1.0 - 2.0 ** -cc.value)
     mul_rate = fe_muls / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
     roofline = {
         "kernel": "k_accumulate<BN254_FQ>", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,

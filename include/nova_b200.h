@@ -130,6 +130,11 @@ int b200_commit_dev(uint64_t ck_handle, const void* d_scalars_mont, size_t n,
  * next vector's work -- HyperKZG's ell-1 halving polynomials (hyperkzg.rs:1099-1100), the L / R pair
  * of an IPA round (ipa_pc.rs:222-238), the four memory oracles of ppsnark (ppsnark.rs:457-471).
  * d_out = k x 96 B; ordered after prior work on `stream`, which waits for every lane on return. */
+/* the same for slices that do not start at the front of the key: MSM j runs over ck[base_offsets[j] .. + lens[j]).
+ * What a rank of the sharded HyperKZG prover needs (its slice of every fold level sits at a different offset;
+ * nova_b200/sharding.py), and the three quotient commitments of one proof. */
+int b200_msm_many_dev(uint64_t ck_handle, const size_t* base_offsets, const void* const* d_scalars_mont,
+                      const size_t* lens, size_t k, void* d_out_jacobian_mont, void* stream);
 int b200_commit_many_dev(uint64_t ck_handle, const void* const* d_scalars_mont, const size_t* lens,
                          size_t k, void* d_out_jacobian_mont, void* stream);
 /* k MSMs over prefixes of the same key: vector j uses ck[..lens[j]] (traits.rs:82-90,

@@ -1038,7 +1038,7 @@ int b200_commit_dev(uint64_t handle, const void* d_scalars, size_t n, const void
 // `from_host`); result j goes to d_out + 96 j.  Ordered after prior work on `s`; on return `s`
 // waits for every lane.  Caller holds ck.mu.
 static int enqueue_many(ck_ctx& ck, const void* const* vecs, const size_t* lens, size_t k,
-                        bool from_host, void* d_out, cudaStream_t s) {
+                        bool from_host, void* d_out, cudaStream_t s, const size_t* offsets = nullptr) {
   std::unique_lock<std::mutex> lsmall;
   if (ck.small) lsmall = std::unique_lock<std::mutex>(ck.small->mu);  // lock order: wide, narrow
   cudaEvent_t start_ev = nullptr;
@@ -1048,7 +1048,8 @@ static int enqueue_many(ck_ctx& ck, const void* const* vecs, const size_t* lens,
   size_t next[2] = {0, 0};
   int rc = B200_OK;
   for (size_t j = 0; j < k && rc == B200_OK; j++) {
-    ck_ctx& t = route(ck, 0, lens[j]);
+    const size_t off = offsets ? offsets[j] : 0;
+    ck_ctx& t = route(ck, off, lens[j]);
     int which = &t == &ck ? 0 : 1;
     int li = (int)(next[which]++ % ck_ctx::NLANES);
     ck_ctx::lane& ln = t.lanes[li];
@@ -1065,7 +1066,7 @@ static int enqueue_many(ck_ctx& ck, const void* const* vecs, const size_t* lens,
       CU(cudaMemcpyAsync(ln.ws.scalars, vecs[j], lens[j] * 32, cudaMemcpyHostToDevice, ln.s));
       src = ln.ws.scalars;
     }
-    rc = enqueue_msm(t, ln.ws, 0, src, lens[j], (char*)d_out + 96 * j, ln.s);
+    rc = enqueue_msm(t, ln.ws, off, src, lens[j], (char*)d_out + 96 * j, ln.s);
   }
   for (int which = 0; which < 2; which++) {
     ck_ctx* t = which == 0 ? &ck : ck.small.get();
@@ -1122,6 +1123,25 @@ int b200_commit_many_dev(uint64_t handle, const void* const* d_scalars, const si
   std::lock_guard<std::mutex> lk(ck->mu);
   return enqueue_many(*ck, d_scalars, lens, k, /*from_host=*/false, d_out,
                       stream ? (cudaStream_t)stream : g_dev.stream);
+}
+
+int b200_msm_many_dev(uint64_t handle, const size_t* base_offsets, const void* const* d_scalars, const size_t* lens,
+                      size_t k, void* d_out, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  auto ck = get_ck(handle);
+  if (!ck) return fail(B200_E_HANDLE, "unknown key handle %llu", (unsigned long long)handle);
+  if (k == 0) return B200_OK;
+  if (!d_out || !base_offsets || !d_scalars || !lens) return fail(B200_E_ARG, "null pointer");
+  for (size_t j = 0; j < k; j++) {
+    if (base_offsets[j] + lens[j] > ck->n)
+      return fail(B200_E_RANGE, "msm %zu: slice [%zu, %zu) exceeds key length %zu", j, base_offsets[j],
+                  base_offsets[j] + lens[j], ck->n);
+    if (lens[j] && !d_scalars[j]) return fail(B200_E_ARG, "null scalar vector %zu", j);
+  }
+  std::lock_guard<std::mutex> lk(ck->mu);
+  return enqueue_many(*ck, d_scalars, lens, k, /*from_host=*/false, d_out,
+                      stream ? (cudaStream_t)stream : g_dev.stream, base_offsets);
 }
 
 int b200_msm_small(uint64_t handle, size_t base_offset, const void* scalars, int elem_bytes, size_t n,

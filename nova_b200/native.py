@@ -70,6 +70,7 @@ SIGNATURES = {
     "b200_commit": [c_u64, _P, c_size_t, _P, _P],
     "b200_commit_dev": [c_u64, _P, c_size_t, _P, _P, _P],
     "b200_commit_many_dev": [c_u64, ctypes.POINTER(_P), ctypes.POINTER(c_size_t), c_size_t, _P, _P],
+    "b200_msm_many_dev": [c_u64, ctypes.POINTER(c_size_t), ctypes.POINTER(_P), ctypes.POINTER(c_size_t), c_size_t, _P, _P],
     "b200_fold_halves_dev": [c_int, _P, c_size_t, _P, _P, _P, _P],
     "b200_ipa_scalars_dev": [c_int, _P, _P, c_size_t, c_size_t, _P, _P, _P],
     "b200_ipa_weights_dev": [c_int, _P, c_size_t, c_size_t, _P, _P, _P],

@@ -392,12 +392,12 @@ def sharded_hyperkzg_prove(curve, ck, P_local, x: list, r, q, comm, on_w=None):
 
     # ---- com_i = commit(P_i), i = 1 .. ell-1 (:1099-1100) ------------------------------------------
     parts = DeviceVec(96 * max(ell - 1, 1))
-    for i in range(1, ell):
-        vec, ln, sharded = levels[i]
-        if sharded:
-            check(L.b200_msm_dev(ck.handle, lo_of(i), vec.ptr, ln, ctypes.c_void_p(parts.ptr.value + 96 * (i - 1)), None))
-        else:  # replicated tail: every rank commits the whole (short) vector itself
-            check(L.b200_msm_dev(ck.handle, 0, vec.ptr, ln, ctypes.c_void_p(parts.ptr.value + 96 * (i - 1)), None))
+    if ell > 1:  # all levels in one call: the MSMs are spread over the key's lanes, their latency-bound tails overlap
+        k = ell - 1
+        offs = (c_size_t * k)(*[lo_of(i) if levels[i][2] else 0 for i in range(1, ell)])  # replicated tail: offset 0
+        ptrs = (ctypes.c_void_p * k)(*[levels[i][0].ptr.value for i in range(1, ell)])
+        lns = (c_size_t * k)(*[levels[i][1] for i in range(1, ell)])
+        check(L.b200_msm_many_dev(ck.handle, offs, ptrs, lns, k, parts.ptr, None))
     mine = parts.to_bytes(96 * (ell - 1))
     allp = comm.gather_bytes(mine) if ell > 1 else [b""]
     com = []
@@ -473,8 +473,11 @@ def sharded_hyperkzg_prove(curve, ck, P_local, x: list, r, q, comm, on_w=None):
         ud = DeviceVec.from_bytes(fields.to_mont_bytes(fid, u[t]))
         h = DeviceVec(32 * nloc)
         check(L.b200_poly_div_dev(fid, Bloc.ptr, nloc + 1, ud.ptr, h.ptr, None))  # -> h[lo_0 .. hi_0)
-        check(L.b200_msm_dev(ck.handle, lo0, h.ptr, cnt, ctypes.c_void_p(wparts.ptr.value + 96 * t), None))
         keep.append((cd, ud, h))
+    offs3 = (c_size_t * 3)(lo0, lo0, lo0)
+    ptrs3 = (ctypes.c_void_p * 3)(*[kp[2].ptr.value for kp in keep])
+    lns3 = (c_size_t * 3)(cnt, cnt, cnt)
+    check(L.b200_msm_many_dev(ck.handle, offs3, ptrs3, lns3, 3, wparts.ptr, None))
     allw = comm.gather_bytes(wparts.to_bytes(96 * 3))  # (the download synchronises: `keep` may go now)
     w = [affine_sum([a[96 * t:96 * t + 96] for a in allw]) for t in range(3)]
     if on_w is not None:

@@ -384,6 +384,13 @@ class EmulatedDevice:
             self.b200_commit_dev(handle, ptrs[j], lens[j], None, _addr(out) + 96 * j, stream)
         return 0
 
+    def b200_msm_many_dev(self, handle, offsets, ptrs, lens, k, out, stream):
+        for j in range(k):
+            rc = self.b200_msm_dev(handle, offsets[j], ptrs[j], lens[j], _addr(out) + 96 * j, stream)
+            if rc:
+                return rc
+        return 0
+
     def b200_ck_register(self, curve_id, bases, n, h, window_bits, out_handle):
         self.keys[self.next_handle] = (curve_id, _rd(bases, 64 * n), _rd(h, 64) if _addr(h) else None)
         out_handle._obj.value = self.next_handle
