@@ -118,7 +118,8 @@ def read_meta_data(reader) -> dict:
         if sid in pos:
             pos[sid] = reader.tell()
         reader.seek(size, io.SEEK_CUR)
-    assert pos[1] != 0 and pos[2] != 0 and pos[3] != 0  # the reference's assert_ne!s (ptau.rs:318-320)
+    if 0 in (pos[1], pos[2], pos[3]):  # the reference's assert_ne!s (ptau.rs:318-320): unconditional, also under -O
+        raise InvalidNumSections(num_sections)
     return dict(pos_header=pos[1], pos_tau_g1=pos[2], pos_tau_g2=pos[3])
 
 
@@ -362,9 +363,9 @@ def load_setup_sharded(reader, h: bytes | None, n: int, rank: int, world: int, g
     meta = read_meta_data(reader)
     reader.seek(meta["pos_header"])
     read_header(reader, num, 2, fields.MODULUS[curve.base_field])
+    if world > num:  # decided identically on EVERY rank, before any rank-dependent branch: nobody is left in a collective
+        raise ValueError(f"{world} ranks for a {num}-point key: some rank would own no point")
     lo, hi = shard_range(num, rank, world)
-    if hi == lo:
-        raise ValueError(f"rank {rank} of {world} owns no point of a {num}-point key")
     reader.seek(meta["pos_tau_g1"] + 64 * lo)
     g1 = _read_exact(reader, 64 * (hi - lo))
     reader.seek(meta["pos_tau_g2"])
