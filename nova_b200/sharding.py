@@ -43,6 +43,14 @@ def all_gather_bytes(b: bytes, group=None) -> list:
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return [b]
+    if dist.get_backend(group) == "nccl":  # NCCL moves device tensors only: stage the few bytes through the GPU
+        if not b:
+            return [b""] * world
+        t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        out = torch.empty(len(b) * world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(out, t, group=group)
+        raw = out.cpu().numpy().tobytes()
+        return [raw[len(b) * k:len(b) * (k + 1)] for k in range(world)]
     t = torch.frombuffer(bytearray(b), dtype=torch.uint8)
     out = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(out, t, group=group)

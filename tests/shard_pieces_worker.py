@@ -56,7 +56,10 @@ def main():
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if kind == "nccl":  # one GPU per rank, collectives over NVLink
+        import torch
+        torch.cuda.set_device(rank)
+    dist.init_process_group("nccl" if kind == "nccl" else "gloo", rank=rank, world_size=world)
     from nova_b200 import sharding as sh
     from oracle import coracle as co
     from oracle.ppsnark_ref import random_instance
@@ -65,13 +68,13 @@ def main():
     fid = 0
     p = FIELD_MODULUS[fid]
     pack = lambda xs: b"".join(mont_bytes(p, x) for x in xs)
-    if kind in ("gpu", "emulated"):
+    if kind in ("gpu", "emulated", "nccl"):
         import nova_b200
         if kind == "emulated":  # the real DeviceEngine adapters, the library answered by the oracle
             import emulated_device
             emulated_device.install()
         from nova_b200.native import check, lib
-        check(lib().b200_init(0))
+        check(lib().b200_init(rank if kind == "nccl" else 0))
         eng = sh.DeviceEngine(fid)
     else:
         eng = OracleEngine(fid)
@@ -120,7 +123,7 @@ def main():
     cid, c = 0, CURVES[0]
     n_key = max(num_cons, num_vars)
     bases = co.gen_bases(cid, n_key)
-    if kind in ("gpu", "emulated"):
+    if kind in ("gpu", "emulated", "nccl"):
         from nova_b200 import provider
         eng.curve = cid
         ck = provider.CommitmentKey(provider.Curve(cid), bases)

@@ -14,7 +14,10 @@ def main():
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if kind == "nccl":  # one GPU per rank, collectives over NVLink
+        import torch
+        torch.cuda.set_device(rank)
+    dist.init_process_group("nccl" if kind == "nccl" else "gloo", rank=rank, world_size=world)
     import nova_b200  # noqa: F401
     if kind == "emulated":
         import emulated_device
@@ -25,7 +28,7 @@ def main():
     from nova_b200.native import check, lib
     from oracle import ppsnark_ref as pr
     from oracle.pyref import FIELD_MODULUS, Keccak256Transcript, SplitMix64, eq_evals, mont_bytes
-    check(lib().b200_init(0))
+    check(lib().b200_init(rank if kind == "nccl" else 0))
     fid = 0
     p = FIELD_MODULUS[fid]
     pack = lambda xs: b"".join(mont_bytes(p, x) for x in xs)

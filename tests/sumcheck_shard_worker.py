@@ -52,7 +52,10 @@ def main():
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if engine_kind == "nccl":  # one GPU per rank
+        import torch
+        torch.cuda.set_device(rank)
+    dist.init_process_group("nccl" if engine_kind == "nccl" else "gloo", rank=rank, world_size=world)
     from nova_b200.sharding import cyclic_shard, sharded_prove_cubic_with_three_inputs
     from oracle.pyref import FIELD_MODULUS, Keccak256Transcript, SplitMix64, mont_bytes, prove_cubic_with_three_inputs
     p = FIELD_MODULUS[fid]
@@ -64,11 +67,11 @@ def main():
         taus[0] = 0
         taus[l - 1] = 0
     claim = rng.field(p)
-    if engine_kind == "gpu":
+    if engine_kind in ("gpu", "nccl"):
         import nova_b200  # noqa: F401
         from nova_b200.native import check, lib
         from nova_b200.spartan import DeviceSumcheckEngine
-        check(lib().b200_init(0))
+        check(lib().b200_init(rank if engine_kind == "nccl" else 0))
         eng = DeviceSumcheckEngine(fid)
     else:
         eng = OracleEngine(fid)

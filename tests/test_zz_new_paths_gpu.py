@@ -518,3 +518,18 @@ def test_poseidon_ro_on_device(b200, fid, arity):
 def test_poseidon_nifs_challenge_on_device(b200, oracle, cid):
     import poseidon_parity
     poseidon_parity.run_nifs_challenge(b200, oracle, cid)
+
+
+def test_sharded_provers_over_nccl(tmp_path):
+    """SURVEY §8e rows beyond the MSM on REAL multi-GPU hardware (one GPU per rank, NCCL): the batched inner sum-check of
+    ppsnark on cyclic shards (prove_helper_sharded), the outer cubic sum-check, and the SpMV / cross-term / folding-step /
+    Horner / division pieces -- each equal to the unsharded oracle message for message.  Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import test_ppsnark_sharded
+    import test_sharding_pieces
+    import test_sumcheck_sharded
+    test_ppsnark_sharded.run_world(2, "nccl", tmp_path)
+    test_sharding_pieces.run_world(2, "nccl", tmp_path)
+    test_sumcheck_sharded.run_world(2, "nccl", 0, 10, 0, tmp_path)
