@@ -117,6 +117,73 @@ NOVA_HD void keccak256_msg(const msg_buf& m, uint32_t flip_pos, uint8_t flip, ui
   for (int i = 0; i < 4; i++) out[i] = a[i];
 }
 
+#if defined(__CUDACC__) || defined(NOVA_SIMT_HOST)
+// ---------------------------------------------------------------------------------------------
+// Keccak-f[1600] spread over one warp: lane i < 25 holds state word i (= x + 5 y); every step of a round is one or two
+// 64-bit shuffles instead of a 25-word loop on a single lane, so a permutation is ~24 x 9 dependent shuffles (~3 us)
+// rather than ~6 k dependent instructions on one lane (~15 us) -- the one-lane hash was half of a sum-check round
+// (profiles/r02a).  All 32 lanes must call; lanes 25..31 mirror lane 0's pattern and hold garbage.
+// ---------------------------------------------------------------------------------------------
+NOVA_D uint64_t warp_get64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+NOVA_D uint64_t rotl64v(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+
+NOVA_D void keccak_f1600_warp(uint64_t& a) {
+  constexpr uint64_t RC[24] = {
+      0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
+      0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+      0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
+      0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+      0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+      0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  constexpr int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  const int lane = (int)(threadIdx.x & 31u);
+  const int l = lane < 25 ? lane : 0;
+  const int x = l % 5, y = l / 5;
+  const int row = 5 * y;
+  const int up1 = (l + 5) % 25, up2 = (l + 10) % 25, up3 = (l + 15) % 25, up4 = (l + 20) % 25;  // same column
+  const int col_m1 = row + (x + 4) % 5, col_p1 = row + (x + 1) % 5, col_p2 = row + (x + 2) % 5;
+  // rho + pi as a gather: B[X][Y] = rot(A[x][y]) with X = y, Y = 2x + 3y  =>  x = X + 3Y, y = X (mod 5)
+  const int src_pi = ((x + 3 * y) % 5) + 5 * x;
+  int rot = 0;
+#pragma unroll
+  for (int k = 0; k < 25; k++)
+    if (k == src_pi) rot = ROT[k];
+  for (int round = 0; round < 24; round++) {
+    uint64_t c = a ^ warp_get64(a, up1) ^ warp_get64(a, up2) ^ warp_get64(a, up3) ^ warp_get64(a, up4);
+    a ^= warp_get64(c, col_m1) ^ rotl64v(warp_get64(c, col_p1), 1);
+    uint64_t b = rotl64v(warp_get64(a, src_pi), rot);
+    a = b ^ (~warp_get64(b, col_p1) & warp_get64(b, col_p2));
+    if (lane == 0) a ^= RC[round];
+  }
+}
+
+// Keccak-256 of `m` (same padding / flip convention as keccak256_msg) computed by the whole warp; every lane returns
+// the four digest words.
+NOVA_D void keccak256_msg_warp(const msg_buf& m, uint32_t flip_pos, uint8_t flip, uint64_t (&out)[4]) {
+  const int lane = (int)(threadIdx.x & 31u);
+  uint64_t a = 0;
+  const uint32_t nblocks = m.len / (8 * KECCAK_RATE_WORDS) + 1;
+  const uint32_t pad_w = m.len >> 3, last_w = nblocks * KECCAK_RATE_WORDS - 1, flip_w = flip_pos >> 3;
+  for (uint32_t b = 0; b < nblocks; b++) {
+    if (lane < KECCAK_RATE_WORDS) {
+      uint32_t wi = b * KECCAK_RATE_WORDS + lane;
+      uint64_t v = m.w[wi];
+      if (wi == pad_w) v ^= (uint64_t)0x01 << (8 * (m.len & 7));
+      if (wi == last_w) v ^= (uint64_t)0x80 << 56;
+      if (wi == flip_w) v ^= (uint64_t)flip << (8 * (flip_pos & 7));
+      a ^= v;
+    }
+    keccak_f1600_warp(a);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = warp_get64(a, i);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // field helpers
 // ---------------------------------------------------------------------------------------------
@@ -282,8 +349,8 @@ NOVA_HD fe_t sc_round_finish(int kind, sc_state& st, const sc_round_poly& p, con
 }
 
 #if defined(__CUDACC__) || defined(NOVA_SIMT_HOST)  // NOVA_SIMT_HOST: tests/hostcheck/simt_host.h
-// One warp: lanes 0 and 1 each compute one of the two squeeze hashes; the (cheap, redundant) field
-// algebra runs on both so that no result has to be broadcast.  <<<1, 32>>>.
+// One warp: the (cheap, redundant) field algebra runs on every lane so that no result has to be broadcast; the two
+// squeeze hashes are computed by the whole warp (keccak_f1600_warp).  <<<1, 32>>>.
 template <class F>
 __global__ void __launch_bounds__(32) k_sc_round(int kind, sc_state* __restrict__ state,
                                                  const void* __restrict__ res,
@@ -293,7 +360,6 @@ __global__ void __launch_bounds__(32) k_sc_round(int kind, sc_state* __restrict_
                                                  uint8_t absorb_label, uint8_t squeeze_label,
                                                  void* __restrict__ out_poly, void* __restrict__ out_r) {
   __shared__ msg_buf msg;
-  __shared__ uint64_t digest_sh[8];
   __shared__ uint32_t flip_pos_sh;
   const unsigned lane = threadIdx.x;
   sc_state st = *state;
@@ -315,14 +381,17 @@ __global__ void __launch_bounds__(32) k_sc_round(int kind, sc_state* __restrict_
     for (int k = 0; k < ncoef; k++) fe_store(out_poly, k, canon[k]);
   }
   __syncwarp();
-  if (lane < 2) {
-    uint64_t d[4];
-    keccak256_msg(msg, flip_pos_sh, (uint8_t)lane, d);
-    for (int i = 0; i < 4; i++) digest_sh[4 * lane + i] = d[i];
-  }
-  __syncwarp();
+  // the two squeeze hashes (they differ in the last message byte), each computed by the whole warp
   uint64_t digest[8];
-  for (int i = 0; i < 8; i++) digest[i] = digest_sh[i];
+  {
+    uint64_t d0[4], d1[4];
+    keccak256_msg_warp(msg, flip_pos_sh, 0, d0);
+    keccak256_msg_warp(msg, flip_pos_sh, 1, d1);
+    for (int i = 0; i < 4; i++) {
+      digest[i] = d0[i];
+      digest[4 + i] = d1[i];
+    }
+  }
   fe_t r = sc_round_finish<F>(kind, st, poly, digest);
   if (lane == 0) {
     *state = st;

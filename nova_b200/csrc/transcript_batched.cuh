@@ -132,7 +132,6 @@ __global__ void __launch_bounds__(32) k_sc_round_batched(scb_desc d, scb_state* 
                                                          uint8_t absorb_label, uint8_t squeeze_label,
                                                          void* __restrict__ out_poly, void* __restrict__ out_r) {
   __shared__ msg_buf msg;
-  __shared__ uint64_t digest_sh[8];
   __shared__ uint32_t flip_pos_sh;
   __shared__ fe_t ev_sh[SCB_MAX_CLAIMS][3];
   __shared__ fe_t comb_sh[3];
@@ -169,14 +168,16 @@ __global__ void __launch_bounds__(32) k_sc_round_batched(scb_desc d, scb_state* 
     for (int k = 0; k < 3; k++) fe_store(out_poly, k, canon[k]);
   }
   __syncwarp();
-  if (lane < 2) {
-    uint64_t dg[4];
-    keccak256_msg(msg, flip_pos_sh, (uint8_t)lane, dg);
-    for (int i = 0; i < 4; i++) digest_sh[4 * lane + i] = dg[i];
-  }
-  __syncwarp();
   uint64_t digest[8];
-  for (int i = 0; i < 8; i++) digest[i] = digest_sh[i];
+  {
+    uint64_t d0[4], d1[4];
+    keccak256_msg_warp(msg, flip_pos_sh, 0, d0);
+    keccak256_msg_warp(msg, flip_pos_sh, 1, d1);
+    for (int i = 0; i < 4; i++) {
+      digest[i] = d0[i];
+      digest[4 + i] = d1[i];
+    }
+  }
   sc_state head = st_sh.head;  // every lane computes the same r and e; lane 0 stores them
   fe_t r = sc_round_finish<F>(SC_ROUND_QUAD_PROD, head, poly, digest);
   __syncwarp();                // all reads of st_sh are done

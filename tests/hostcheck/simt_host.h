@@ -7,6 +7,7 @@
 #pragma once
 #define NOVA_SIMT_HOST 1
 #include <array>
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <memory>
@@ -19,24 +20,23 @@ struct simt_dim3 { unsigned x = 0, y = 0, z = 0; };
 inline thread_local simt_dim3 threadIdx, blockIdx;
 inline simt_dim3 blockDim{32, 1, 1}, gridDim{1, 1, 1};
 
+// sense-reversing barrier that spins with yield: the warp-parallel Keccak of the round kernels crosses thousands of
+// barriers per call, and a mutex + condition variable costs ~50 us per crossing with 32 threads on a few cores
 class simt_barrier {
  public:
   explicit simt_barrier(int n) : n_(n) {}
   void wait() {
-    std::unique_lock<std::mutex> lk(mu_);
-    int gen = gen_;
-    if (++count_ == n_) {
-      count_ = 0;
-      gen_++;
-      cv_.notify_all();
+    const int gen = gen_.load(std::memory_order_acquire);
+    if (count_.fetch_add(1, std::memory_order_acq_rel) + 1 == n_) {
+      count_.store(0, std::memory_order_relaxed);
+      gen_.store(gen + 1, std::memory_order_release);
     } else {
-      cv_.wait(lk, [&] { return gen != gen_; });
+      while (gen_.load(std::memory_order_acquire) == gen) std::this_thread::yield();
     }
   }
  private:
-  std::mutex mu_;
-  std::condition_variable cv_;
-  int n_, count_ = 0, gen_ = 0;
+  int n_;
+  std::atomic<int> count_{0}, gen_{0};
 };
 inline simt_barrier*& simt_current_barrier() { static simt_barrier* b = nullptr; return b; }
 
@@ -68,6 +68,18 @@ inline uint32_t __shfl_down_sync(unsigned, uint32_t v, int delta) {
   b->warps[w]->wait();
   uint32_t r = l + (unsigned)delta < 32 ? b->slots[w][l + delta] : v;
   b->warps[w]->wait();
+  return r;
+}
+// arbitrary source lane (every lane of the warp must call it)
+inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) {
+  simt_block* b = simt_current_block();
+  static std::array<uint32_t, 32> lone_slots;  // simt_launch_warp has no block context: one warp, one slot array
+  std::array<uint32_t, 32>& slots = b ? b->slots[threadIdx.x >> 5] : lone_slots;
+  unsigned l = threadIdx.x & 31;
+  slots[l] = v;
+  __syncwarp();
+  uint32_t r = slots[(unsigned)src & 31u];
+  __syncwarp();
   return r;
 }
 inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
