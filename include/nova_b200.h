@@ -240,6 +240,8 @@ int b200_axpy_dev(int field_id, const void* a, const void* b, const void* r, siz
                   void* stream);
 int b200_vec_add_dev(int field_id, const void* a, const void* b, size_t n, void* out, void* stream);
 int b200_bind_top_dev(int field_id, void* z_inout, size_t n, const void* r, void* stream);
+/* the same for k tables of one length in one launch: the 16 binds of a batched sum-check round (ppsnark.rs:960-966) */
+int b200_bind_top_multi_dev(int field_id, void* const* d_tables, size_t k, size_t n, const void* d_r, void* stream);
 /* out[i] = a[i]*b[i]   (TS[i] * (T[i]+r)^-1, spartan/ppsnark.rs:446-449) */
 int b200_vec_mul_dev(int field_id, const void* a, const void* b, size_t n, void* out, void* stream);
 /* LogUp fingerprints with the shift folded in: out[i] = val[i]*gamma + addr[i] + r; addr == NULL

@@ -13,6 +13,7 @@
 
 #include "../../include/nova_b200.h"
 #include "msm_kernels.cuh"
+#include "field_kernels.cuh"
 #include "ops.cuh"
 #include "poly_kernels.cuh"
 #include "transcript.cuh"
@@ -1748,6 +1749,24 @@ int b200_bind_top_dev(int fid, void* z, size_t n, const void* r, void* stream) {
     if (!z || !r) return fail(B200_E_ARG, "null pointer");
     ops->bind_top(stream ? (cudaStream_t)stream : g_dev.stream, z, n, r);
     count_launch(1);
+    CU(cudaGetLastError());
+    return (int)B200_OK;
+  });
+}
+
+int b200_bind_top_multi_dev(int fid, void* const* zs, size_t k, size_t n, const void* r, void* stream) {
+  return with_field(fid, [&](const field_ops* ops) {
+    if (k == 0 || n < 2) return (int)B200_OK;
+    if (n & 1) return fail(B200_E_ARG, "bind_top needs an even length, got %zu", n);
+    if (!zs || !r) return fail(B200_E_ARG, "null pointer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : g_dev.stream;
+    for (size_t j = 0; j < k; j += BIND_MULTI_MAX) {
+      const int cnt = (int)(k - j < (size_t)BIND_MULTI_MAX ? k - j : (size_t)BIND_MULTI_MAX);
+      for (int i = 0; i < cnt; i++)
+        if (!zs[j + i]) return fail(B200_E_ARG, "null table %zu", j + i);
+      ops->bind_top_multi(s, zs + j, cnt, n, r);
+      count_launch(1);
+    }
     CU(cudaGetLastError());
     return (int)B200_OK;
   });

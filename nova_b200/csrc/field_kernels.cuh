@@ -102,6 +102,22 @@ __global__ void __launch_bounds__(256) k_bind_top(void* z, size_t half,
   }
 }
 
+// the same for up to BIND_MULTI_MAX tables of one length in ONE launch (blockIdx.y = table): a batched sum-check binds
+// 16 polynomials per round (ppsnark.rs:960-966) -- sixteen launches per round are pure launch latency once the tables are short
+constexpr int BIND_MULTI_MAX = 32;
+struct bind_multi_args {
+  void* z[BIND_MULTI_MAX];
+};
+template <class F>
+__global__ void __launch_bounds__(256) k_bind_top_multi(bind_multi_args a, size_t half, const void* __restrict__ r_ptr) {
+  const fe_t r = fe_load(r_ptr, 0);
+  void* z = a.z[blockIdx.y];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    fe_t lo = fe_load_rw(z, i), hi = fe_load_rw(z, i + half);
+    fe_store(z, i, fe_add<F>(lo, fe_mul<F>(r, fe_sub<F>(hi, lo))));
+  }
+}
+
 // ---- inner-product argument helpers (provider/ipa_pc.rs:174-285, restated without key folding) --
 // out[i] = v[i]*x_lo + v[i+half]*x_hi   (a' = a_L r + r^-1 a_R ; b' = b_L r^-1 + r b_R, ipa_pc.rs:244-254)
 template <class F>

@@ -34,6 +34,7 @@ struct field_ops {
   void (*axpy)(cudaStream_t, const void* a, const void* b, const void* r, size_t n, void* out);
   void (*vec_add)(cudaStream_t, const void* a, const void* b, size_t n, void* out);
   void (*bind_top)(cudaStream_t, void* z, size_t n, const void* r);
+  void (*bind_top_multi)(cudaStream_t, void* const* zs, int k, size_t n, const void* r);  // k <= 32 tables of length n
   void (*vec_mul)(cudaStream_t, const void* a, const void* b, size_t n, void* out);
   void (*logup_hash)(cudaStream_t, const void* val, const void* addr_or_null, const void* gamma,
                      const void* r, size_t n, void* out);

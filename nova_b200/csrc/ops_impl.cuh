@@ -206,6 +206,14 @@ struct ops_impl {
   static void bind_top(cudaStream_t s, void* z, size_t n, const void* r) {
     k_bind_top<F><<<stream_grid(n / 2, 256), 256, 0, s>>>(z, n / 2, r);
   }
+  static void bind_top_multi(cudaStream_t s, void* const* zs, int k, size_t n, const void* r) {
+    bind_multi_args a{};
+    for (int i = 0; i < k; i++) a.z[i] = zs[i];
+    int gx = stream_grid(n / 2, 256, 8);
+    int per = (148 * 8 + k - 1) / k;  // keep the whole launch near 8 waves of blocks
+    if (gx > per) gx = per < 1 ? 1 : per;
+    k_bind_top_multi<F><<<dim3((unsigned)gx, (unsigned)k), 256, 0, s>>>(a, n / 2, r);
+  }
   static void fold_halves(cudaStream_t s, const void* v, size_t half, const void* x_lo, const void* x_hi,
                           void* out) {
     k_fold_halves<F><<<stream_grid(half, 256), 256, 0, s>>>(v, half, x_lo, x_hi, out);
@@ -394,7 +402,7 @@ struct ops_impl {
   }
   static constexpr field_ops table() {
     return field_ops{F::ID,  digits,       expand_key, accumulate, fixup,   reduce,
-                     sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, vec_mul, logup_hash,
+                     sum_points, jacobian_sum, index_bases, cross_term, axpy,       vec_add, bind_top, bind_top_multi, vec_mul, logup_hash,
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
                      sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve,

@@ -88,6 +88,7 @@ SIGNATURES = {
     "b200_vec_mul_dev": [c_int, _P, _P, c_size_t, _P, _P],
     "b200_logup_hash_dev": [c_int, _P, _P, _P, _P, c_size_t, _P, _P],
     "b200_bind_top_dev": [c_int, _P, c_size_t, _P, _P],
+    "b200_bind_top_multi_dev": [c_int, ctypes.POINTER(_P), c_size_t, c_size_t, _P, _P],
     "b200_sc_eval": [c_int, c_int, _P, _P, _P, c_size_t, _P, c_size_t, _P, c_size_t, c_int, _P],
     "b200_sc_eval_dev": [c_int, c_int, _P, _P, _P, c_size_t, _P, _P, c_int, _P, _P],
     "b200_sc_eval_sharded_dev": [c_int, c_int, _P, _P, _P, c_size_t, _P, _P, c_int, c_size_t, c_size_t, _P, _P],

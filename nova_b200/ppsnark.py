@@ -159,8 +159,10 @@ class RoundSums:
 
 
 def _bind_all(fid, polys, length, r_dev):
-    for Z in polys:
-        check(lib().b200_bind_top_dev(fid, Z.ptr, length, r_dev.ptr, None))
+    """bind_poly_var_top of several tables of one length with the same challenge: ONE launch (b200_bind_top_multi_dev)"""
+    polys = list(polys)
+    ptrs = (ctypes.c_void_p * len(polys))(*[Z.ptr.value for Z in polys])
+    check(lib().b200_bind_top_multi_dev(fid, ptrs, len(polys), length, r_dev.ptr, None))
 
 
 def commit_dev(curve, ck: CommitmentKey, v, n: int):

@@ -111,6 +111,13 @@ class EmulatedDevice:
     def b200_axpy(self, fid, a, b, r, n, out):  # host pointers: the same thing here
         return self.b200_axpy_dev(fid, a, b, r, n, out, None)
 
+    def b200_bind_top_multi_dev(self, fid, zs, k, n, r, stream):
+        for j in range(k):
+            rc = self.b200_bind_top_dev(fid, zs[j], n, r, stream)
+            if rc:
+                return rc
+        return 0
+
     def b200_bind_top_dev(self, fid, z, n, r, stream):
         _wr(z, co.bind_top(fid, _rd(z, 32 * n), _rd(r, 32)))
         return 0
