@@ -406,5 +406,65 @@ inline SumcheckProofOut prove_cubic_with_three_inputs(int field, const Scalar& c
   }, "b200_sumcheck_cubic3");
 }
 
+// ---- one process, all GPUs of the node (b200_mgpu_*): the single call a CommitmentEngine::commit makes ------------
+// The key is distributed block-cyclically over the devices; every commit of a prefix ck[..n] is fanned out inside the
+// library and the partial sums are exchanged over NVLink inside the reduction kernels (include/nova_b200.h).
+template <class C>
+class MultiGpuCommitmentKey {
+ public:
+  // devices: explicit device ids, or empty for 0 .. ndev-1
+  MultiGpuCommitmentKey(const std::vector<Affine>& bases, const Affine* h, int ndev, const std::vector<int>& devices = {})
+      : n_(bases.size()) {
+    check(b200_mgpu_init(ndev, devices.empty() ? nullptr : devices.data()), "b200_mgpu_init");
+    check(b200_mgpu_ck_register(C::curve, bases.data(), bases.size(), h, 0, &handle_), "b200_mgpu_ck_register");
+  }
+  ~MultiGpuCommitmentKey() {
+    if (handle_) b200_mgpu_ck_release(handle_);
+  }
+  MultiGpuCommitmentKey(const MultiGpuCommitmentKey&) = delete;
+  MultiGpuCommitmentKey& operator=(const MultiGpuCommitmentKey&) = delete;
+  size_t len() const { return n_; }
+  // CommitmentEngineTrait::commit (pedersen.rs:263-270); r = nullptr: vartime_multiscalar_mul over ck[..v.len()]
+  Point commit(const std::vector<Scalar>& v, const Scalar* r = nullptr) const {
+    if (v.size() > n_) throw std::logic_error("commit: vector longer than the key");  // pedersen.rs:264
+    Point out;
+    check(b200_mgpu_commit(handle_, v.data(), v.size(), r, &out), "b200_mgpu_commit");
+    return out;
+  }
+
+ private:
+  uint64_t handle_ = 0;
+  size_t n_;
+};
+
+// ---- Poseidon random oracle with the squeeze on the device (ROTrait for PoseidonRO, provider/poseidon.rs:60-127) --------
+// The constants (R_F, R_P, Grain-LFSR round constants, Cauchy MDS; Montgomery form) are the caller's: a Rust host passes
+// its `PoseidonConstantsCircuit`, the Python mirror derives them (nova_b200/poseidon.py).
+class PoseidonRO {
+ public:
+  PoseidonRO(int field, int arity, int r_f, int r_p, const std::vector<Scalar>& round_constants, const std::vector<Scalar>& mds)
+      : field_(field) {
+    check(b200_poseidon_register(field, arity, r_f, r_p, round_constants.data(), mds.data(), &handle_), "b200_poseidon_register");
+  }
+  ~PoseidonRO() {
+    if (handle_) b200_poseidon_release(handle_);
+  }
+  PoseidonRO(const PoseidonRO&) = delete;
+  PoseidonRO& operator=(const PoseidonRO&) = delete;
+  void absorb(const Scalar& e) { state_.push_back(e); }
+  // -> (challenge as a Montgomery element of `field`, challenge as a canonical integer); the state becomes [hash]
+  std::pair<Scalar, Scalar> squeeze(int num_bits, bool start_with_one = false) {
+    Scalar out[3];
+    check(b200_poseidon_ro(handle_, state_.data(), state_.size(), num_bits, start_with_one ? 1 : 0, out), "b200_poseidon_ro");
+    state_.assign(1, out[0]);
+    return {out[1], out[2]};
+  }
+
+ private:
+  int field_;
+  uint64_t handle_ = 0;
+  std::vector<Scalar> state_;
+};
+
 }  // namespace b200
 }  // namespace nova

@@ -111,6 +111,17 @@ int b200_ck_register(int curve, const void* bases, size_t n, const void* h, int,
   return B200_OK;
 }
 int b200_ck_release(uint64_t h) { std::lock_guard<std::mutex> lk(g_mu); return g_keys.erase(h) ? B200_OK : B200_E_HANDLE; }
+// one process, N GPUs: on the CPU the "devices" are one oracle
+int b200_device_count(int* n) { *n = 1; return B200_OK; }
+int b200_mgpu_init(int ndev, const int*) { return ndev >= 1 && ndev <= 8 ? B200_OK : B200_E_ARG; }
+int b200_mgpu_ck_register(int curve, const void* bases, size_t n, const void* h, int wb, uint64_t* key) {
+  return b200_ck_register(curve, bases, n, h, wb, key);
+}
+int b200_mgpu_ck_release(uint64_t key) { return b200_ck_release(key); }
+int b200_commit(uint64_t h, const void* scalars, size_t n, const void* r, void* out);
+int b200_mgpu_commit(uint64_t key, const void* scalars, size_t n, const void* r, void* out) {
+  return b200_commit(key, scalars, n, r, out);
+}
 int b200_host_alloc(size_t bytes, void** p) { *p = malloc(bytes ? bytes : 1); return *p ? B200_OK : B200_E_NOMEM; }
 int b200_host_free(void* p) { free(p); return B200_OK; }
 int b200_ck_setup_synthetic(int curve, const void* gen, uint64_t k0, size_t n, int with_h, int, uint64_t* handle) {

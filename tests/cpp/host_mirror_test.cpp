@@ -181,6 +181,38 @@ static int concurrency_mode(int log2n, int nthreads) {
   return 0;
 }
 
+// --mgpu <case.bin> <ndev>: MultiGpuCommitmentKey (one process, ndev devices -- virtual devices on one GPU are allowed) against
+// the single-device CommitmentKey on the same key and vectors; dumps both sets of points for the Python side.
+static int mgpu_mode(const char* path, int ndev) {
+  std::ifstream f(path, std::ios::binary);
+  check(b200_init(0), "b200_init");
+  auto bases = rd<Affine>(f);
+  auto h = rd<Affine>(f);
+  auto scalars = rd<Scalar>(f);
+  auto r = rd<Scalar>(f);
+  std::vector<int> devs(ndev, 0);  // all on device 0 unless the box has more
+  int have = 0;
+  b200_device_count(&have);
+  for (int d = 0; d < ndev; d++) devs[d] = have > 1 ? d % have : 0;
+  MultiGpuCommitmentKey<BN254> mk(bases, &h[0], ndev, devs);
+  CommitmentKey<BN254> ck(bases, &h[0]);
+  std::vector<Point> a, b;
+  for (size_t len : {scalars.size(), scalars.size() / 2 + 1, (size_t)1, (size_t)0}) {
+    std::vector<Scalar> v(scalars.begin(), scalars.begin() + len);
+    a.push_back(mk.commit(v, &r[0]));
+    b.push_back(CommitmentEngine<BN254>::commit(ck, v, &r[0]));
+    a.push_back(mk.commit(v));
+    b.push_back(DlogGroup<BN254>::vartime_multiscalar_mul(v, ck));
+  }
+  std::ofstream o(std::string(path) + ".out", std::ios::binary);
+  uint64_t n = a.size();
+  o.write((char*)&n, 8);
+  o.write((char*)a.data(), n * sizeof(Point));
+  o.write((char*)b.data(), n * sizeof(Point));
+  std::printf("mgpu ok %d devices\n", ndev);
+  return 0;
+}
+
 // Jacobian -> compare with expected affine without inversion: X == x*Z^2, Y == y*Z^3 is checked on
 // the Python side; here we only dump the raw result bytes.
 int main(int argc, char** argv) {
@@ -191,6 +223,7 @@ int main(int argc, char** argv) {
   }
   if (std::string(argv[1]) == "--fold") return argc > 2 ? fold_mode(argv[2]) : 2;
   if (std::string(argv[1]) == "--sumcheck") return argc > 2 ? sumcheck_mode(argv[2]) : 2;
+  if (std::string(argv[1]) == "--mgpu") return argc > 3 ? mgpu_mode(argv[2], std::atoi(argv[3])) : 2;
   if (std::string(argv[1]) == "--concurrency")
     return argc > 2 ? concurrency_mode(std::atoi(argv[2]), argc > 3 ? std::atoi(argv[3]) : 4) : 2;
   std::ifstream f(argv[1], std::ios::binary);

@@ -241,3 +241,37 @@ def test_cpp_concurrent_commits_overlap_and_agree(log2n):
     assert pts[:4] == pts[4:] and len(set(pts[:4])) == 4
     assert res["ms_serial"] > 0 and res["ms_concurrent"] > 0
     print(res)
+
+
+def check_mgpu(exe, oracle, tmp_path, ndev):
+    """host_mirror_test --mgpu: MultiGpuCommitmentKey == CommitmentKey on the same inputs (and == the oracle)"""
+    from nova_b200.provider import Curve, _jac_to_affine
+    from oracle.pyref import CURVES
+    cid, c = 0, CURVES[0]
+    n = 9000
+    bases = oracle.gen_bases(cid, n + 1)
+    sc = oracle.gen_scalars(c.scalar_field, 21, n)
+    r = oracle.gen_scalars(c.scalar_field, 22, 1)
+    case = tmp_path / "mgpu.bin"
+    with open(case, "wb") as f:
+        for blob, size in ((bases[:64 * n], 64), (bases[64 * n:], 64), (sc, 32), (r, 32)):
+            f.write((len(blob) // size).to_bytes(8, "little") + blob)
+    out = subprocess.check_output([exe, "--mgpu", str(case), str(ndev)], text=True, timeout=300)
+    assert "mgpu ok" in out
+    raw = open(str(case) + ".out", "rb").read()
+    k = int.from_bytes(raw[:8], "little")
+    pts = [_jac_to_affine(Curve(cid), raw[8 + 96 * i:8 + 96 * i + 96]) for i in range(2 * k)]
+    assert pts[:k] == pts[k:]
+    assert pts[1] == c.affine_from_bytes(oracle.msm(cid, sc, bases[:64 * n]))
+
+
+def test_cpp_mirror_multi_gpu_key_host_logic_cpu(oracle, tmp_path):
+    build_emulated()
+    check_mgpu(EXE_EMUL, oracle, tmp_path, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndev", [1, 3])
+def test_cpp_mirror_multi_gpu_key(oracle, tmp_path, ndev):
+    build()
+    check_mgpu(EXE, oracle, tmp_path, ndev)
