@@ -367,6 +367,37 @@ typedef struct b200_scb_state {           /* device resident, 1296 bytes */
 int b200_sc_round_batched_dev(int field_id, const b200_scb_desc* desc, const void* d_sums, void* d_state,
                               const void* d_pending, size_t pending_len, int absorb_label, int squeeze_label,
                               void* d_poly_out, void* d_r_out, void* stream);
+/* A whole batched sum-check in one call: RelaxedR1CSSNARK::prove_helper (src/spartan/ppsnark.rs:886-983) -- per round
+ * every engine's evaluation points, their combination with the powers of one challenge, the cubic, the transcript
+ * (absorb b"p", squeeze b"c"), the claim updates and the binds -- for claims expressed as sum forms over a set of
+ * device tables of 2^num_rounds elements (bound in place).  Per round: all sums in two launches, the round kernel, one
+ * bind launch; the last NOVA_B200_SC_TAIL_BITS (default 8) variables run inside one kernel.
+ *   kind[i]    B200_SCB_*: how claim i's sums become its evaluation points [s(0), lead, s(-1)]
+ *   form[i]    sum form (sc_form_id 0..9: SC_QUAD_PROD .. SC_EQ_QUAD1_M1) over tables tab[i][0..2] (-1 = unused)
+ *   form_m1[i] eq claims: the third-sum form (7..9) for rounds whose tau is 0 (sumcheck.rs:1082-1213)
+ *   eq_of[i]   eq claims: the EqSumCheckInstance (sumcheck.rs:590-747) weighting the sum; taus[g]: its num_rounds taus
+ * Host inputs (Montgomery): coeffs [nclaims] (powers of the batching challenge, ppsnark.rs:915-921), claim (their
+ * combination with the initial claims), running [nclaims] (initial claims; used by the eq claims).
+ * Host outputs: polys_out [num_rounds][3][32] canonical LE, r_out [num_rounds][32] Montgomery, finals_out
+ * [ntables][32] Montgomery (element 0 of every table after the last bind); *tr advances as the reference's. */
+#define B200_SCP_MAX_TABLES 24
+typedef struct b200_scp_program {
+  int32_t nclaims, neq, ntables, num_rounds;
+  int32_t kind[B200_SCB_MAX_CLAIMS];
+  int32_t form[B200_SCB_MAX_CLAIMS];
+  int32_t form_m1[B200_SCB_MAX_CLAIMS];
+  int32_t eq_of[B200_SCB_MAX_CLAIMS];
+  int32_t tab[B200_SCB_MAX_CLAIMS][3];
+  void* tables[B200_SCP_MAX_TABLES];     /* device */
+  const void* taus[B200_SCB_MAX_EQ];     /* host, Montgomery */
+} b200_scp_program;
+/* tuning: how many trailing variables of b200_sumcheck_batched run inside one kernel (0 = none; default 8 or
+ * NOVA_B200_SC_TAIL_BITS).  bits < 0 only queries.  Returns the previous value. */
+#define B200_SC_TAIL_MAX_BITS 14
+int b200_sumcheck_tail_bits(int bits);
+int b200_sumcheck_batched(int field_id, const b200_scp_program* prog, const void* coeffs, const void* claim,
+                          const void* running, b200_transcript* tr, const void* pending, size_t pending_len,
+                          void* polys_out, void* r_out, void* finals_out);
 /* SumcheckProof::prove_quad_prod (sumcheck.rs:199-242) in one call.  d_A, d_B: device polynomials
  * of 2^num_rounds elements, bound in place (element 0 holds the final evaluation afterwards).
  * Host outputs: polys_out [num_rounds][2][32] canonical LE, r_out [num_rounds][32] Montgomery,

@@ -2,6 +2,7 @@
 // Template-free: all kernels are reached through the per-field launcher tables (ops.cuh).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include "poly_kernels.cuh"
 #include "transcript.cuh"
 #include "transcript_batched.cuh"
+#include "sumcheck_tail.cuh"
 
 using namespace nova;
 

@@ -12,6 +12,8 @@
 namespace nova {
 
 struct msm_plan;
+struct multi_args;     // poly_kernels.cuh
+struct scb_tail_args;  // sumcheck_tail.cuh
 
 struct field_ops {
   int field_id;
@@ -90,8 +92,16 @@ struct field_ops {
   void (*to_mont)(cudaStream_t, const void* in_canonical, size_t n, void* out);
   // sharded MSM whose rank has no pairs: publish the identity and sum the peers' partials (plan.peer)
   void (*exchange_identity)(cudaStream_t, const msm_plan&, void* out_jac);
+  // all sums of a batched sum-check round in two launches: out[3 y + k] = output k of sum y;
+  // scratch >= sc_multi_scratch_elems(n sums) * 32 B
+  void (*sc_reduce_multi)(cudaStream_t, const multi_args&, void* scratch, void* out);
+  // every remaining round of a batched sum-check in one CTA (sumcheck_tail.cuh); sums: 6 * 16 elements of scratch
+  void (*scb_tail)(cudaStream_t, const scb_tail_args&, void* state, void* sums, const void* pending,
+                   uint32_t pending_len, int absorb_label, int squeeze_label, void* polys, void* rs);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
+constexpr int SC_MULTI_BLOCKS = 148 * 2;  // blocks per sum of sc_reduce_multi (times <= 32 sums in grid.y)
+inline size_t sc_multi_scratch_elems(int nsums) { return (size_t)nsums * SC_MULTI_BLOCKS * 3; }
 // NOVA_B200_SC_SEG=1 selects the segmented reduction of the eq-weighted sum-check forms (k_form_reduce_eqseg)
 inline bool sc_segmented_enabled() {
   static const bool on = [] {

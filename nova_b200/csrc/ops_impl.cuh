@@ -7,6 +7,7 @@
 #include "transcript.cuh"
 #include "transcript_batched.cuh"
 #include "poseidon.cuh"
+#include "sumcheck_tail.cuh"
 
 namespace nova {
 
@@ -378,6 +379,17 @@ struct ops_impl {
     k_sc_round_batched<F><<<1, 32, 0, s>>>(*(const scb_desc*)desc, (scb_state*)state, sums, (const uint8_t*)pending,
                                            pending_len, (uint8_t)absorb_label, (uint8_t)squeeze_label, out_poly, out_r);
   }
+  static void sc_reduce_multi(cudaStream_t s, const multi_args& a, void* scratch, void* out) {
+    size_t need = (a.h + 255) / 256;
+    unsigned gx = (unsigned)(need < (size_t)SC_MULTI_BLOCKS ? (need ? need : 1) : SC_MULTI_BLOCKS);
+    k_form_reduce_multi<F><<<dim3(gx, (unsigned)a.n), 256, 0, s>>>(a, scratch);
+    k_form_final_multi<F><<<dim3(1, (unsigned)a.n), 256, 0, s>>>(scratch, (int)gx, out);
+  }
+  static void scb_tail(cudaStream_t s, const scb_tail_args& a, void* state, void* sums, const void* pending,
+                       uint32_t pending_len, int absorb_label, int squeeze_label, void* polys, void* rs) {
+    k_scb_tail<F><<<1, SCB_TAIL_THREADS, 0, s>>>(a, (scb_state*)state, sums, (const uint8_t*)pending, pending_len,
+                                                (uint8_t)absorb_label, (uint8_t)squeeze_label, polys, rs);
+  }
   static void on_curve(cudaStream_t s, const void* pts, size_t n, int b_small, uint32_t* first_bad) {
     if (n) k_on_curve<F><<<stream_grid(n, 256), 256, 0, s>>>(pts, n, b_small, first_bad);
   }
@@ -406,7 +418,8 @@ struct ops_impl {
                      fold_halves, ipa_scalars, ipa_weights, fill_one,
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
                      sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve,
-                     powers_canonical, scalar_bases, poseidon_ro, to_mont, exchange_identity};
+                     powers_canonical, scalar_bases, poseidon_ro, to_mont, exchange_identity,
+                     sc_reduce_multi, scb_tail};
   }
 };
 

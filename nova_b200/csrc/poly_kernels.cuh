@@ -121,32 +121,37 @@ enum sc_form_id {
   SC_DOT = 11,        // sum A[id] B[id]  (inner_product, provider/ipa_pc.rs:102-108)
 };
 
-template <class F, int FORM>
+// RW: the tables are read through the coherent path (fe_load_rw) -- for a kernel that also binds them (k_scb_tail)
+template <class F, int FORM, bool RW = false>
 struct sc_form {
+  static NOVA_D fe_t ld(const void* base, size_t idx) {
+    if constexpr (RW) return fe_load_rw(base, idx);
+    else return fe_load(base, idx);
+  }
   const void *A, *B, *C;
   size_t h;
   eq_factor eq;
   template <int N>
   NOVA_D void operator()(size_t id, fe_t (&acc)[N]) const {
     if constexpr (FORM == SC_DOT) {
-      acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_load(A, id), fe_load(B, id)));
+      acc[0] = fe_add<F>(acc[0], fe_mul<F>(ld(A, id), ld(B, id)));
     } else if constexpr (FORM == SC_QUAD_PROD) {
-      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t al = ld(A, id), ah = ld(A, id + h), bl = ld(B, id), bh = ld(B, id + h);
       acc[0] = fe_add<F>(acc[0], fe_mul<F>(al, bl));
       acc[1] = fe_add<F>(acc[1], fe_mul<F>(fe_sub<F>(ah, al), fe_sub<F>(bh, bl)));
     } else if constexpr (FORM == SC_LINEAR) {
-      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t al = ld(A, id), ah = ld(A, id + h), bl = ld(B, id), bh = ld(B, id + h);
       acc[0] = fe_add<F>(acc[0], fe_sub<F>(al, bl));
       fe_t am = fe_sub<F>(fe_dbl<F>(al), ah), bm = fe_sub<F>(fe_dbl<F>(bl), bh);
       acc[1] = fe_add<F>(acc[1], fe_sub<F>(am, bm));
     } else if constexpr (FORM == SC_QUADRATIC) {
-      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t al = ld(A, id), ah = ld(A, id + h), bl = ld(B, id), bh = ld(B, id + h);
       acc[0] = fe_add<F>(acc[0], fe_mul<F>(al, bl));
       fe_t am = fe_sub<F>(fe_dbl<F>(al), ah), bm = fe_sub<F>(fe_dbl<F>(bl), bh);
       acc[1] = fe_add<F>(acc[1], fe_mul<F>(am, bm));
     } else if constexpr (FORM == SC_CUBIC) {
-      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
-      fe_t cl = fe_load(C, id), ch = fe_load(C, id + h);
+      fe_t al = ld(A, id), ah = ld(A, id + h), bl = ld(B, id), bh = ld(B, id + h);
+      fe_t cl = ld(C, id), ch = ld(C, id + h);
       fe_t da = fe_sub<F>(ah, al), db = fe_sub<F>(bh, bl), dc = fe_sub<F>(ch, cl);
       acc[0] = fe_add<F>(acc[0], fe_mul<F>(fe_mul<F>(al, bl), cl));
       acc[1] = fe_add<F>(acc[1], fe_mul<F>(fe_mul<F>(da, db), dc));
@@ -165,29 +170,29 @@ struct sc_form {
   template <int N>
   NOVA_D void unweighted(size_t id, fe_t (&x)[N]) const {
     if constexpr (FORM == SC_EQ_CUBIC3 || FORM == SC_EQ_CUBIC2) {
-      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t al = ld(A, id), ah = ld(A, id + h), bl = ld(B, id), bh = ld(B, id + h);
       fe_t e0 = fe_mul<F>(al, bl);
       if constexpr (FORM == SC_EQ_CUBIC3)
-        e0 = fe_sub<F>(e0, fe_load(C, id));
+        e0 = fe_sub<F>(e0, ld(C, id));
       else
         e0 = fe_sub<F>(e0, fe_one<F>());
       x[0] = e0;
       x[1] = fe_mul<F>(fe_sub<F>(ah, al), fe_sub<F>(bh, bl));
     } else if constexpr (FORM == SC_EQ_QUAD1 || FORM == SC_DOT_EQ) {
-      x[0] = fe_load(A, id);
+      x[0] = ld(A, id);
     } else if constexpr (FORM == SC_EQ_CUBIC3_M1 || FORM == SC_EQ_CUBIC2_M1) {
-      fe_t al = fe_load(A, id), ah = fe_load(A, id + h), bl = fe_load(B, id), bh = fe_load(B, id + h);
+      fe_t al = ld(A, id), ah = ld(A, id + h), bl = ld(B, id), bh = ld(B, id + h);
       fe_t am = fe_sub<F>(fe_dbl<F>(al), ah), bm = fe_sub<F>(fe_dbl<F>(bl), bh);
       fe_t e = fe_mul<F>(am, bm);
       if constexpr (FORM == SC_EQ_CUBIC3_M1) {
-        fe_t cl = fe_load(C, id), ch = fe_load(C, id + h);
+        fe_t cl = ld(C, id), ch = ld(C, id + h);
         e = fe_sub<F>(e, fe_sub<F>(fe_dbl<F>(cl), ch));
       } else {
         e = fe_sub<F>(e, fe_one<F>());
       }
       x[0] = e;
     } else if constexpr (FORM == SC_EQ_QUAD1_M1) {
-      fe_t al = fe_load(A, id), ah = fe_load(A, id + h);
+      fe_t al = ld(A, id), ah = ld(A, id + h);
       x[0] = fe_sub<F>(fe_dbl<F>(al), ah);
     }
   }
@@ -241,10 +246,104 @@ __global__ void __launch_bounds__(256) k_form_reduce_eqseg(Form form, size_t cou
     for (int k = 0; k < NOUT; k++) fe_store(partials, (size_t)blockIdx.x * NOUT + k, acc[k]);
 }
 
-constexpr int sc_form_nout(int form) {
+NOVA_HD constexpr int sc_form_nout(int form) {
   return form == SC_CUBIC ? 3
          : (form == SC_EQ_QUAD1 || form == SC_DOT_EQ || form == SC_DOT || form >= SC_EQ_CUBIC3_M1) ? 1
                                                                                 : 2;
+}
+
+// ------------------------------------------------------------------------------------------
+// All sums of one round of a BATCHED sum-check in one launch (prove_helper, ppsnark.rs:886-983: nine claims over
+// sixteen tables of one length): grid = (blocks, sums), block (x, y) reduces a slice of sum y.  Two launches per
+// round (this + k_form_final_multi) instead of two per sum.  Forms 0..9 only (the pair forms: count = len / 2).
+// ------------------------------------------------------------------------------------------
+constexpr int SC_MULTI_MAX = 32;
+struct multi_sum {
+  int32_t form;   // sc_form_id
+  int32_t shift;  // eq split (eq_factor)
+  const void *A, *B, *C;
+  const void *eq_left, *eq_right;
+};
+struct multi_args {
+  int32_t n;      // sums
+  size_t h;       // half length = index count of every sum
+  size_t id_mul, id_add;
+  multi_sum s[SC_MULTI_MAX];
+};
+
+template <class F, int FORM, bool RW>
+NOVA_D void multi_run(const multi_sum& m, size_t h, size_t id_mul, size_t id_add, size_t first, size_t stride,
+                      fe_t (&acc)[3]) {
+  constexpr int NOUT = sc_form_nout(FORM);
+  sc_form<F, FORM, RW> f;
+  f.A = m.A;
+  f.B = m.B;
+  f.C = m.C;
+  f.h = h;
+  f.eq.left = m.eq_left;
+  f.eq.right = m.eq_right;
+  f.eq.shift = m.shift;
+  f.eq.mask = ((size_t)1 << m.shift) - 1;
+  f.eq.id_mul = id_mul;
+  f.eq.id_add = id_add;
+  fe_t x[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) x[k] = fe_zero<F>();
+  for (size_t id = first; id < h; id += stride) f(id, x);
+#pragma unroll
+  for (int k = 0; k < NOUT; k++) acc[k] = x[k];
+}
+
+// acc = this thread's share of sum m (unused outputs stay zero)
+template <class F, bool RW>
+NOVA_D void multi_dispatch(const multi_sum& m, size_t h, size_t id_mul, size_t id_add, size_t first, size_t stride,
+                           fe_t (&acc)[3]) {
+#define NOVA_MULTI_CASE(X) \
+  case X: multi_run<F, X, RW>(m, h, id_mul, id_add, first, stride, acc); break
+  switch (m.form) {
+    NOVA_MULTI_CASE(SC_QUAD_PROD);
+    NOVA_MULTI_CASE(SC_LINEAR);
+    NOVA_MULTI_CASE(SC_QUADRATIC);
+    NOVA_MULTI_CASE(SC_CUBIC);
+    NOVA_MULTI_CASE(SC_EQ_CUBIC3);
+    NOVA_MULTI_CASE(SC_EQ_CUBIC2);
+    NOVA_MULTI_CASE(SC_EQ_QUAD1);
+    NOVA_MULTI_CASE(SC_EQ_CUBIC3_M1);
+    NOVA_MULTI_CASE(SC_EQ_CUBIC2_M1);
+    NOVA_MULTI_CASE(SC_EQ_QUAD1_M1);
+    default: break;
+  }
+#undef NOVA_MULTI_CASE
+}
+
+// partials[(y * gridDim.x + x) * 3 + k]
+template <class F>
+__global__ void __launch_bounds__(256) k_form_reduce_multi(const multi_args a, void* __restrict__ partials) {
+  __shared__ fe_t sm[8 * 3];
+  fe_t acc[3] = {fe_zero<F>(), fe_zero<F>(), fe_zero<F>()};
+  multi_dispatch<F, false>(a.s[blockIdx.y], a.h, a.id_mul, a.id_add, (size_t)blockIdx.x * blockDim.x + threadIdx.x,
+                           (size_t)gridDim.x * blockDim.x, acc);
+  block_sum<F, 3>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < 3; k++) fe_store(partials, ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + k, acc[k]);
+}
+
+// block y: out[3 y + k] = sum over the nblocks partials of sum y (all three slots are written; a form with fewer
+// outputs leaves zeros behind them)
+template <class F>
+__global__ void __launch_bounds__(256) k_form_final_multi(const void* __restrict__ partials, int nblocks,
+                                                          void* __restrict__ out) {
+  __shared__ fe_t sm[8 * 3];
+  fe_t acc[3] = {fe_zero<F>(), fe_zero<F>(), fe_zero<F>()};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      acc[k] = fe_add<F>(acc[k], fe_load_rw(partials, ((size_t)blockIdx.y * nblocks + b) * 3 + k));
+  block_sum<F, 3>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < 3; k++) fe_store(out, (size_t)blockIdx.y * 3 + k, acc[k]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -124,20 +124,24 @@ NOVA_HD fe_t scb_bound(const fe_t& q, const fe_t& tau, const fe_t& r) {
 
 #if defined(__CUDACC__) || defined(NOVA_SIMT_HOST)  // NOVA_SIMT_HOST: tests/hostcheck/simt_host.h
 // One warp.  Lane i < nclaims: claim i's evaluation points and claim update; lanes 0..2: one component of
-// the combination each; lanes 0/1: the two squeeze hashes; lanes g < neq: the eq bounds.  <<<1, 32>>>.
+// the combination each; the whole warp: the two squeeze hashes; lanes g < neq: the eq bounds.
+struct scb_round_smem {
+  msg_buf msg;
+  uint32_t flip_pos;
+  fe_t ev[SCB_MAX_CLAIMS][3];
+  fe_t comb[3];
+  scb_state st;
+};
+
 template <class F>
-__global__ void __launch_bounds__(32) k_sc_round_batched(scb_desc d, scb_state* __restrict__ state,
-                                                         const void* __restrict__ sums,
-                                                         const uint8_t* __restrict__ pending, uint32_t pending_len,
-                                                         uint8_t absorb_label, uint8_t squeeze_label,
-                                                         void* __restrict__ out_poly, void* __restrict__ out_r) {
-  __shared__ msg_buf msg;
-  __shared__ uint32_t flip_pos_sh;
-  __shared__ fe_t ev_sh[SCB_MAX_CLAIMS][3];
-  __shared__ fe_t comb_sh[3];
-  __shared__ scb_state st_sh;
-  const int lane = (int)threadIdx.x;
-  if (lane == 0) st_sh = *state;
+NOVA_D void scb_round_warp(const scb_desc& d, scb_state* __restrict__ state, const void* __restrict__ sums,
+                           const uint8_t* __restrict__ pending, uint32_t pending_len, uint8_t absorb_label,
+                           uint8_t squeeze_label, void* __restrict__ out_poly, void* __restrict__ out_r,
+                           scb_round_smem& sh) {
+  const int lane = (int)(threadIdx.x & 31u);
+  static_assert(sizeof(scb_state) % 4 == 0, "word copy");
+  for (unsigned w = lane; w < sizeof(scb_state) / 4; w += 32)
+    reinterpret_cast<uint32_t*>(&sh.st)[w] = reinterpret_cast<const uint32_t*>(state)[w];
   __syncwarp();
   fe_t tau = fe_zero<F>(), tau_inv = fe_zero<F>();
   fe_t ev[3] = {fe_zero<F>(), fe_zero<F>(), fe_zero<F>()};
@@ -153,43 +157,54 @@ __global__ void __launch_bounds__(32) k_sc_round_batched(scb_desc d, scb_state* 
       if (has_m1) tm1 = fe_load_rw(sums, (size_t)d.slot_m1[lane]);
       else tau_inv = fe_load_rw(d.tau_inv[d.eq_of[lane]], 0);
     }
-    scb_claim_evals<F>(d, lane, st_sh, s, has_m1 ? &tm1 : nullptr, tau, tau_inv, ev);
-    for (int k = 0; k < 3; k++) ev_sh[lane][k] = ev[k];
+    scb_claim_evals<F>(d, lane, sh.st, s, has_m1 ? &tm1 : nullptr, tau, tau_inv, ev);
+    for (int k = 0; k < 3; k++) sh.ev[lane][k] = ev[k];
   }
   __syncwarp();
-  if (lane < 3) comb_sh[lane] = scb_combine<F>(d, st_sh, ev_sh, lane);
+  if (lane < 3) sh.comb[lane] = scb_combine<F>(d, sh.st, sh.ev, lane);
   __syncwarp();
   sc_round_poly poly;
-  scb_poly<F>(st_sh.head.claim, comb_sh[0], comb_sh[1], comb_sh[2], poly);
+  scb_poly<F>(sh.st.head.claim, sh.comb[0], sh.comb[1], sh.comb[2], poly);
   fe_t canon[3];
   sc_round_compressed<F>(poly, canon);
   if (lane == 0) {
-    flip_pos_sh = sc_round_message(msg, pending, pending_len, absorb_label, canon, 3, st_sh.head, squeeze_label);
+    sh.flip_pos = sc_round_message(sh.msg, pending, pending_len, absorb_label, canon, 3, sh.st.head, squeeze_label);
     for (int k = 0; k < 3; k++) fe_store(out_poly, k, canon[k]);
   }
   __syncwarp();
   uint64_t digest[8];
   {
     uint64_t d0[4], d1[4];
-    keccak256_msg_warp(msg, flip_pos_sh, 0, d0);
-    keccak256_msg_warp(msg, flip_pos_sh, 1, d1);
+    keccak256_msg_warp(sh.msg, sh.flip_pos, 0, d0);
+    keccak256_msg_warp(sh.msg, sh.flip_pos, 1, d1);
     for (int i = 0; i < 4; i++) {
       digest[i] = d0[i];
       digest[4 + i] = d1[i];
     }
   }
-  sc_state head = st_sh.head;  // every lane computes the same r and e; lane 0 stores them
+  sc_state head = sh.st.head;  // every lane computes the same r and e; lane 0 stores them
   fe_t r = sc_round_finish<F>(SC_ROUND_QUAD_PROD, head, poly, digest);
-  __syncwarp();                // all reads of st_sh are done
-  if (is_eq_claim) state->claim[lane] = scb_update_claim<F>(st_sh.claim[lane], ev, r);
+  __syncwarp();                // all reads of sh.st are done
+  if (is_eq_claim) state->claim[lane] = scb_update_claim<F>(sh.st.claim[lane], ev, r);
   if (lane < d.neq) {
     fe_t t = fe_load_rw(d.tau[lane], 0);
-    state->q[lane] = scb_bound<F>(st_sh.q[lane], t, r);
+    state->q[lane] = scb_bound<F>(sh.st.q[lane], t, r);
   }
   if (lane == 0) {
     state->head = head;
     fe_store(out_r, 0, r);
   }
+}
+
+// <<<1, 32>>>
+template <class F>
+__global__ void __launch_bounds__(32) k_sc_round_batched(scb_desc d, scb_state* __restrict__ state,
+                                                         const void* __restrict__ sums,
+                                                         const uint8_t* __restrict__ pending, uint32_t pending_len,
+                                                         uint8_t absorb_label, uint8_t squeeze_label,
+                                                         void* __restrict__ out_poly, void* __restrict__ out_r) {
+  __shared__ scb_round_smem sh;
+  scb_round_warp<F>(d, state, sums, pending, pending_len, absorb_label, squeeze_label, out_poly, out_r, sh);
 }
 #endif
 

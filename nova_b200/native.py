@@ -102,6 +102,8 @@ SIGNATURES = {
     "b200_sc_round_batched_dev": [c_int, _P, _P, _P, _P, c_size_t, c_int, c_int, _P, _P, _P],
     "b200_sumcheck_quad_prod": [c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _P, _P, _P],
     "b200_sumcheck_cubic3": [c_int, _P, _P, c_int, _P, _P, _P, _P, _P, c_size_t, _P, _P, _P],
+    "b200_sumcheck_tail_bits": [c_int],
+    "b200_sumcheck_batched": [c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P, _P],
     "b200_eq_table": [c_int, _P, c_int, _P],
     "b200_eq_table_dev": [c_int, _P, c_int, _P, _P],
     "b200_mle_eval": [c_int, _P, c_int, _P, _P],

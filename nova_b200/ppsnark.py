@@ -39,6 +39,18 @@ class ScbDesc(ctypes.Structure):
                 ("tau_inv", ctypes.c_void_p * SCB_MAX_EQ)]
 
 
+SCP_MAX_TABLES = 24
+
+
+class ScpProgram(ctypes.Structure):
+    """b200_scp_program"""
+    _fields_ = [("nclaims", ctypes.c_int32), ("neq", ctypes.c_int32), ("ntables", ctypes.c_int32),
+                ("num_rounds", ctypes.c_int32), ("kind", ctypes.c_int32 * SCB_MAX_CLAIMS),
+                ("form", ctypes.c_int32 * SCB_MAX_CLAIMS), ("form_m1", ctypes.c_int32 * SCB_MAX_CLAIMS),
+                ("eq_of", ctypes.c_int32 * SCB_MAX_CLAIMS), ("tab", (ctypes.c_int32 * 3) * SCB_MAX_CLAIMS),
+                ("tables", ctypes.c_void_p * SCP_MAX_TABLES), ("taus", ctypes.c_void_p * SCB_MAX_EQ)]
+
+
 def to_repr(x: int) -> bytes:
     return int(x).to_bytes(32, "little")  # canonical little-endian (traits.rs:323-327)
 
@@ -341,6 +353,13 @@ class MemorySumcheckInstance:
 
     # -- device-transcript loop (prove_helper_device): claim kinds, third sums for tau = 0, binds only --
     KINDS = (SCB_LIN2, SCB_LIN2, SCB_EQ_DEG2, SCB_EQ_DEG2, SCB_EQ_DEG2, SCB_EQ_DEG2)
+    # per claim: (sum form, third-sum form, tables A / B / C) -- what enqueue / enqueue_m1 launch, as data
+    PROGRAM = ((SC_LINEAR, -1, ("t_inv_row", "w_inv_row", None)),
+               (SC_LINEAR, -1, ("t_inv_col", "w_inv_col", None)),
+               (SC_EQ_CUBIC3, SC_EQ_CUBIC3_M1, ("t_inv_row", "t_row", "ts_row")),
+               (SC_EQ_CUBIC2, SC_EQ_CUBIC2_M1, ("w_inv_row", "w_row", None)),
+               (SC_EQ_CUBIC3, SC_EQ_CUBIC3_M1, ("t_inv_col", "t_col", "ts_col")),
+               (SC_EQ_CUBIC2, SC_EQ_CUBIC2_M1, ("w_inv_col", "w_col", None)))
 
     def eq_instances(self):
         return [self.eq]
@@ -429,6 +448,7 @@ class InnerBatchedSumcheckInstance:
 
     TABLES = ("L_row", "L_col", "val", "E")
     KINDS = (SCB_RAW3, SCB_EQ_DEG1)
+    PROGRAM = ((SC_CUBIC, -1, ("L_row", "L_col", "val")), (SC_EQ_QUAD1, SC_EQ_QUAD1_M1, ("E", None, None)))
 
     def eq_instances(self):
         return [self.eq]
@@ -487,6 +507,7 @@ class WitnessBoundSumcheck:
 
     TABLES = ("W", "masked_eq")
     KINDS = (SCB_LIN2,)
+    PROGRAM = ((SC_QUADRATIC, -1, ("masked_eq", "W", None)),)
 
     @classmethod
     def from_shards(cls, fid, n_local: int, W_local, masked_eq_local):
@@ -615,7 +636,76 @@ def prove_helper_sharded(fid, mem, inner, witness, transcript, rank: int, world:
 
 
 def prove_helper_device(fid, mem, inner, witness, transcript):
-    """prove_helper (ppsnark.rs:886-983) with the per-round algebra and the transcript on the device:
+    """prove_helper (ppsnark.rs:886-983) as ONE library call (b200_sumcheck_batched): the engines describe their
+    claims as data (PROGRAM / KINDS / claim_eq), the library runs every round -- all sums in two launches, the round
+    kernel, one bind launch, the short rounds inside one kernel -- and the proof is read back once.
+    `transcript` needs the serialisable fields `round`, `state`, `buf` (see spartan._device_loop)."""
+    p = fields.MODULUS[fid]
+    engines = (mem, inner, witness)
+    assert mem.size() == inner.size() == witness.size()
+    nr = mem.size().bit_length() - 1
+    claims = mem.initial_claims() + inner.initial_claims() + witness.initial_claims()
+    k = len(claims)
+    assert k <= SCB_MAX_CLAIMS
+    s = transcript.squeeze(b"r")
+    coeffs = [pow(s, i, p) for i in range(k)]
+    e = sum(c * cl for c, cl in zip(claims, coeffs)) % p
+    prog = ScpProgram()
+    tables, index = [], {}
+    eqs = []
+    i = 0
+    for eng in engines:
+        base = len(eqs)
+        eqs += eng.eq_instances()
+        for (form, form_m1, names), kind, g in zip(eng.PROGRAM, eng.KINDS, eng.claim_eq()):
+            prog.kind[i], prog.form[i], prog.form_m1[i] = kind, form, form_m1
+            prog.eq_of[i] = -1 if g is None else base + g
+            for c, name in enumerate(names):
+                if name is None:
+                    prog.tab[i][c] = -1
+                    continue
+                key = (id(eng), name)
+                if key not in index:
+                    index[key] = len(tables)
+                    tables.append(getattr(eng, name))
+                prog.tab[i][c] = index[key]
+            i += 1
+        for name in eng.TABLES:  # tables no claim reads are still bound every round (none today)
+            if (id(eng), name) not in index:
+                index[(id(eng), name)] = len(tables)
+                tables.append(getattr(eng, name))
+    assert i == k and len(tables) <= SCP_MAX_TABLES and len(eqs) <= SCB_MAX_EQ
+    prog.nclaims, prog.neq, prog.ntables, prog.num_rounds = k, len(eqs), len(tables), nr
+    for t, Z in enumerate(tables):
+        prog.tables[t] = Z.ptr.value
+    tau_bufs = [_cbuf(fields.pack(fid, q.taus)) for q in eqs]
+    for g, buf in enumerate(tau_bufs):
+        prog.taus[g] = ctypes.addressof(buf)
+    running = [x for eng in engines for x in eng.running_claims()]
+    tr = (ctypes.c_ubyte * 72)()
+    ctypes.memmove(tr, int(transcript.round).to_bytes(8, "little") + bytes(transcript.state), 72)
+    pending = bytes(transcript.buf)
+    polys_raw, rs_raw = ctypes.create_string_buffer(96 * nr), ctypes.create_string_buffer(32 * nr)
+    finals = ctypes.create_string_buffer(32 * len(tables))
+    check(lib().b200_sumcheck_batched(fid, ctypes.byref(prog), _cbuf(fields.pack(fid, coeffs)),
+                                      _cbuf(fields.to_mont_bytes(fid, e)), _cbuf(fields.pack(fid, running)), tr,
+                                      _cbuf(pending) if pending else None, len(pending), polys_raw, rs_raw, finals))
+    raw = bytes(tr)
+    transcript.round = int.from_bytes(raw[:8], "little")
+    transcript.state = raw[8:72]
+    transcript.buf = b""
+    for eng in engines:
+        eng.len = 1
+        for q in eng.eq_instances():
+            q.round += nr
+    coeffs_out = [int.from_bytes(polys_raw.raw[32 * i:32 * i + 32], "little") for i in range(3 * nr)]
+    polys = [coeffs_out[3 * j:3 * j + 3] for j in range(nr)]
+    return polys, fields.unpack(fid, rs_raw.raw), mem.final_claims(), inner.final_claims(), witness.final_claims()
+
+
+def prove_helper_device_rounds(fid, mem, inner, witness, transcript):
+    """prove_helper (ppsnark.rs:886-983) with the per-round algebra and the transcript on the device, one call per
+    launch (the building blocks b200_sc_eval_dev / b200_sc_round_batched_dev / b200_bind_top_multi_dev):
     per round the nine reductions, one b200_sc_round_batched_dev and the sixteen binds are enqueued
     without reading anything back; proof, challenges and transcript state are read once at the end.
     `transcript` needs the serialisable fields `round`, `state`, `buf` (see spartan._device_loop)."""

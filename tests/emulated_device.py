@@ -255,6 +255,159 @@ class EmulatedDevice:
         return self._sumcheck_loop(fid, lambda j: 2 if taus[j] == 0 else 1, claim, num_rounds, [A, B, C], tr, pending,
                                    pending_len, polys_out, r_out, finals_out, 3, sums, taus)
 
+    # ---- the whole batched sum-check (csrc/capi_sumcheck.inc b200_sumcheck_batched), restated: eq tables and sums by the
+    # oracle, the round through the host build of the round kernel, binds by the oracle.  With `use_simt` the sums of
+    # every round run through the REAL k_form_reduce_multi / k_form_final_multi and the last `tail_bits` variables
+    # through the REAL k_scb_tail, on host threads (tests/hostcheck/simt_host.h). ----
+    tail_bits = 2
+
+    def b200_sumcheck_tail_bits(self, bits):
+        old = self.tail_bits
+        if bits >= 0:
+            self.tail_bits = bits
+        return old
+
+    def b200_sumcheck_batched(self, fid, prog_ref, coeffs, claim, running, tr, pending, pending_len, polys_out, r_out,
+                              finals_out):
+        from nova_b200.ppsnark import SCB_MAX_CLAIMS, SCB_MAX_EQ, ScbDesc
+        P = FIELD_MODULUS[fid]
+        prog = prog_ref._obj
+        l, nc, ne, nt = prog.num_rounds, prog.nclaims, prog.neq, prog.ntables
+        fh, sh = l // 2, l - l // 2
+        keep = []  # buffers the ctypes structs point into
+
+        def buf(data: bytes):
+            b = ctypes.create_string_buffer(data, max(len(data), 1))
+            keep.append(b)
+            return b
+        eq = []
+        for g in range(ne):
+            raw = _rd(prog.taus[g], 32 * l)
+            taus = [from_mont_bytes(P, raw[32 * i:32 * i + 32]) for i in range(l)]
+            tab = lambda lo, hi: co.eq_table(fid, raw[32 * lo:32 * hi])
+            left = buf(b"".join(tab(fh - k, fh) for k in range(max(fh, 1))))
+            right = buf(b"".join(tab(l - k, l) for k in range(sh + 1)))
+            tinv = buf(b"".join(mont_bytes(P, pow(t, -1, P) if t else 0) for t in taus))
+            eq.append(dict(taus=taus, left=left, right=right, d_taus=buf(raw), d_tinv=tinv))
+        state = buf(_rd(claim, 32) + bytes(32) + _rd(tr, 72) + bytes(8) + _rd(coeffs, 32 * nc) + bytes(32 * (SCB_MAX_CLAIMS - nc))
+                    + _rd(running, 32 * nc) + bytes(32 * (SCB_MAX_CLAIMS - nc)) + mont_bytes(P, 1) * SCB_MAX_EQ)
+        assert len(state.raw) == 1296
+        tables = [prog.tables[t] for t in range(nt)]
+        eq_of = [prog.eq_of[i] if prog.kind[i] >= 2 else -1 for i in range(nc)]
+
+        def eq_ptrs(g, rnd):
+            e = eq[g]
+            if rnd < fh:
+                return (ctypes.addressof(e["left"]) + 32 * ((1 << (fh - rnd)) - 1), 32 << (fh - rnd),
+                        ctypes.addressof(e["right"]) + 32 * ((1 << sh) - 1), 32 << sh, sh)
+            return 0, 0, ctypes.addressof(e["right"]) + 32 * ((1 << (l - rnd)) - 1), 32 << (l - rnd), 0
+        length = 1 << l
+        for j in range(l):
+            if self.use_simt and l - j <= self.tail_bits:
+                self._simt_tail(fid, prog, eq, eq_of, tables, j, state, pending, pending_len, polys_out, r_out)
+                break
+            rnd = j + 1
+            plan = [(i, prog.form[i]) for i in range(nc)]
+            plan += [(i, prog.form_m1[i]) for i in range(nc) if eq_of[i] >= 0 and eq[eq_of[i]]["taus"][j] == 0]
+            d = ScbDesc()
+            d.nclaims, d.neq = nc, ne
+            for i in range(nc):
+                d.kind[i], d.eq_of[i], d.slot[i], d.slot_m1[i] = prog.kind[i], eq_of[i], 3 * i, -1
+            for k, (i, form) in enumerate(plan[nc:]):
+                d.slot_m1[i] = 3 * (nc + k)
+            for g in range(ne):
+                d.tau[g] = ctypes.addressof(eq[g]["d_taus"]) + 32 * j
+                d.tau_inv[g] = ctypes.addressof(eq[g]["d_tinv"]) + 32 * j
+            sums = ctypes.create_string_buffer(96 * len(plan))
+            if self.use_simt:
+                self._simt_multi(fid, prog, plan, eq_of, eq_ptrs, rnd, tables, length, sums)
+            else:
+                for k, (i, form) in enumerate(plan):
+                    g = lambda c: _rd(tables[prog.tab[i][c]], 32 * length) if prog.tab[i][c] >= 0 else None
+                    L = R = None
+                    shift = 0
+                    if eq_of[i] >= 0:
+                        lp, ln, rp, rn, shift = eq_ptrs(eq_of[i], rnd)
+                        L, R = (_rd(lp, ln) if lp else None), _rd(rp, rn)
+                    res = co.sc_eval(fid, form, g(0), g(1), g(2), L, R, shift)
+                    ctypes.memmove(ctypes.addressof(sums) + 96 * k, res, len(res))
+            rc = self.b200_sc_round_batched_dev(fid, d, sums, state, pending if j == 0 else None, pending_len if j == 0 else 0,
+                                                ord("p"), ord("c"), _addr(polys_out) + 96 * j, _addr(r_out) + 32 * j, None)
+            assert rc == 0
+            r = _rd(_addr(r_out) + 32 * j, 32)
+            for Z in tables:
+                _wr(Z, co.bind_top(fid, _rd(Z, 32 * length), r))
+            length //= 2
+        for t, Z in enumerate(tables):
+            _wr(_addr(finals_out) + 32 * t, _rd(Z, 32))
+        _wr(tr, state.raw[64:136])
+        return 0
+
+    def _simt_structs(self):
+        """ctypes mirrors of multi_args (poly_kernels.cuh) and scb_tail_args (sumcheck_tail.cuh), checked by size"""
+        from nova_b200.ppsnark import SCB_MAX_CLAIMS, SCB_MAX_EQ, ScbDesc
+        if getattr(self, "_structs", None) is None:
+            class MultiSum(ctypes.Structure):
+                _fields_ = [("form", ctypes.c_int32), ("shift", ctypes.c_int32), ("A", ctypes.c_void_p), ("B", ctypes.c_void_p),
+                            ("C", ctypes.c_void_p), ("eq_left", ctypes.c_void_p), ("eq_right", ctypes.c_void_p)]
+
+            class MultiArgs(ctypes.Structure):
+                _fields_ = [("n", ctypes.c_int32), ("h", ctypes.c_size_t), ("id_mul", ctypes.c_size_t), ("id_add", ctypes.c_size_t),
+                            ("s", MultiSum * 32)]
+
+            class TailEq(ctypes.Structure):
+                _fields_ = [("left", ctypes.c_void_p), ("right", ctypes.c_void_p), ("taus", ctypes.c_void_p),
+                            ("tau_inv", ctypes.c_void_p), ("tau_zero", ctypes.c_uint64)]
+
+            class TailArgs(ctypes.Structure):
+                _fields_ = [("d", ScbDesc), ("form", ctypes.c_int32 * SCB_MAX_CLAIMS), ("form_m1", ctypes.c_int32 * SCB_MAX_CLAIMS),
+                            ("tab", (ctypes.c_int32 * 3) * SCB_MAX_CLAIMS), ("ntables", ctypes.c_int32),
+                            ("num_rounds", ctypes.c_int32), ("first_round", ctypes.c_int32), ("tables", ctypes.c_void_p * 24),
+                            ("eq", TailEq * SCB_MAX_EQ)]
+            hc = self._hc_simt()
+            assert ctypes.sizeof(MultiArgs) == hc.hc_simt_sizes(0) and ctypes.sizeof(MultiSum) == hc.hc_simt_sizes(1)
+            assert ctypes.sizeof(TailArgs) == hc.hc_simt_sizes(2) and ctypes.sizeof(ScbDesc) == hc.hc_simt_sizes(3)
+            self._structs = (MultiArgs, TailArgs)
+        return self._structs
+
+    def _simt_multi(self, fid, prog, plan, eq_of, eq_ptrs, rnd, tables, length, sums):
+        MultiArgs, _ = self._simt_structs()
+        a = MultiArgs()
+        a.n, a.h, a.id_mul, a.id_add = len(plan), length // 2, 1, 0
+        for k, (i, form) in enumerate(plan):
+            m = a.s[k]
+            m.form = form
+            m.A, m.B, m.C = (_addr(tables[prog.tab[i][c]]) if prog.tab[i][c] >= 0 else None for c in range(3))
+            if eq_of[i] >= 0:
+                lp, _, rp, _, shift = eq_ptrs(eq_of[i], rnd)
+                m.eq_left, m.eq_right, m.shift = lp or None, rp, shift
+        grid = max(1, min(3, (length // 2 + 255) // 256))
+        assert self._hc_simt().hc_simt_sc_reduce_multi(fid, ctypes.byref(a), grid, sums) == 0
+
+    def _simt_tail(self, fid, prog, eq, eq_of, tables, j, state, pending, pending_len, polys_out, r_out):
+        _, TailArgs = self._simt_structs()
+        a = TailArgs()
+        nc = prog.nclaims
+        a.d.nclaims, a.d.neq = nc, prog.neq
+        for i in range(nc):
+            a.d.kind[i], a.d.eq_of[i], a.d.slot[i], a.d.slot_m1[i] = prog.kind[i], eq_of[i], 3 * i, -1
+            a.form[i], a.form_m1[i] = prog.form[i], prog.form_m1[i] if eq_of[i] >= 0 else -1
+            for c in range(3):
+                a.tab[i][c] = prog.tab[i][c]
+        a.ntables, a.num_rounds, a.first_round = prog.ntables, prog.num_rounds, j
+        for t, Z in enumerate(tables):
+            a.tables[t] = _addr(Z)
+        for g, e in enumerate(eq):
+            q = a.eq[g]
+            q.left, q.right = ctypes.addressof(e["left"]), ctypes.addressof(e["right"])
+            q.taus, q.tau_inv = ctypes.addressof(e["d_taus"]), ctypes.addressof(e["d_tinv"])
+            q.tau_zero = sum(1 << k for k, t in enumerate(e["taus"]) if t == 0)
+        sums = ctypes.create_string_buffer(96 * 32)
+        rc = self._hc_simt().hc_simt_scb_tail(fid, ctypes.byref(a), state, sums, ctypes.c_void_p(_addr(pending) if j == 0 else 0),
+                                              int(pending_len) if j == 0 else 0, ord("p"), ord("c"),
+                                              ctypes.c_void_p(_addr(polys_out)), ctypes.c_void_p(_addr(r_out)))
+        assert rc == 0
+
     # ---- sparse matrices ----------------------------------------------------------------------
     def b200_spmv_register(self, fid, data, indices, indptr, rows, cols, out_handle):
         ip = [int(indptr[i]) for i in range(rows + 1)]

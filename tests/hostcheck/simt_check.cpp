@@ -153,3 +153,60 @@ extern "C" int hc_simt_sc_eval_seg(int fid, int form, const void* A, const void*
   }
 #undef SEG_CASE
 }
+
+// ---- all sums of a batched round in one launch (k_form_reduce_multi + k_form_final_multi) and the short rounds of a
+// batched sum-check inside one CTA (k_scb_tail, sumcheck_tail.cuh): the kernels as written, grid.y emulated by a loop ----
+#include "../../nova_b200/csrc/sumcheck_tail.cuh"
+
+extern "C" int hc_simt_sc_reduce_multi(int fid, const void* args, unsigned grid, void* out) {
+  const multi_args a = *(const multi_args*)args;
+  auto run = [&](auto tag) {
+    using F = decltype(tag);
+    std::vector<fe_t> partials((size_t)a.n * grid * 3);
+    for (int y = 0; y < a.n; y++)
+      simt_launch_grid(grid, 256, [&] {
+        blockIdx.y = (unsigned)y;
+        k_form_reduce_multi<F>(a, partials.data());
+      });
+    for (int y = 0; y < a.n; y++)
+      simt_launch_grid(1, 256, [&] {
+        blockIdx.y = (unsigned)y;
+        k_form_final_multi<F>(partials.data(), (int)grid, out);
+      });
+  };
+  switch (fid) {
+    case 0: run(BN254_FR{}); break;
+    case 3: run(PALLAS_FQ{}); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+extern "C" int hc_simt_scb_tail(int fid, const void* args, void* state, void* sums, const void* pending,
+                                uint32_t pending_len, int absorb_label, int squeeze_label, void* polys, void* rs) {
+  const scb_tail_args a = *(const scb_tail_args*)args;
+  auto run = [&](auto tag) {
+    using F = decltype(tag);
+    simt_launch_grid(1, SCB_TAIL_THREADS, [&] {
+      k_scb_tail<F>(a, (scb_state*)state, sums, (const uint8_t*)pending, pending_len, (uint8_t)absorb_label,
+                    (uint8_t)squeeze_label, polys, rs);
+    });
+  };
+  switch (fid) {
+    case 0: run(BN254_FR{}); break;
+    case 3: run(PALLAS_FQ{}); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+extern "C" int hc_simt_sizes(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(multi_args);
+    case 1: return (int)sizeof(multi_sum);
+    case 2: return (int)sizeof(scb_tail_args);
+    case 3: return (int)sizeof(scb_desc);
+    case 4: return (int)sizeof(scb_state);
+    default: return -1;
+  }
+}

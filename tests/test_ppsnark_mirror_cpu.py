@@ -38,7 +38,7 @@ def test_ppsnark_prove_core_host_logic(emulated, oracle, cid, num_cons, num_vars
 
 
 @pytest.mark.parametrize("zero_rho,zero_outer", [((), ()), ((0,), ()), ((2,), (1,)), ((0, 3), (0, 3))])
-def test_batched_round_with_zero_taus(emulated, oracle, zero_rho, zero_outer):
+def test_batched_round_with_zero_taus(emulated, oracle, zero_rho, zero_outer, ell=4, helpers=None):
     """prove_helper with eq instances whose tau is 0 in some rounds (the third-sum fall-back,
     sumcheck.rs:1082-1213): host-transcript loop, device-transcript loop and the oracle's prove_helper agree.
     The engines are fed random polynomials directly (the prover does not check their consistency)."""
@@ -46,7 +46,7 @@ def test_batched_round_with_zero_taus(emulated, oracle, zero_rho, zero_outer):
     from nova_b200 import spartan as sp
     from oracle import ppsnark_ref as pr
     from oracle.pyref import FIELD_MODULUS, Keccak256Transcript, SplitMix64, mont_bytes
-    fid, ell = 0, 4
+    fid = 0
     p, N = FIELD_MODULUS[fid], 1 << ell
     rng = SplitMix64(5150 + len(zero_rho) + 7 * len(zero_outer))
     vec = lambda: [rng.field(p) for _ in range(N)]
@@ -76,7 +76,7 @@ def test_batched_round_with_zero_taus(emulated, oracle, zero_rho, zero_outer):
         return helper(fid, mem, inner, wit, tr), tr.squeeze(b"after")
 
     exp, exp_after = ref_run()
-    for helper in (dp.prove_helper, dp.prove_helper_device):
+    for helper in helpers or (dp.prove_helper, dp.prove_helper_device, dp.prove_helper_device_rounds):
         got, after = dev_run(helper)
         assert [list(q) for q in got[0]] == [list(q) for q in exp[0]], helper.__name__
         assert list(got[1]) == list(exp[1])
@@ -89,6 +89,20 @@ def test_batched_round_kernel_wrapper_on_32_threads(emulated_simt, oracle, zero_
     """The one-warp kernel wrapper itself (lane i = claim i, lanes 0..2 combine, lanes 0/1 hash, shared-memory
     hand-offs between __syncwarp barriers) through the SIMT shim."""
     test_batched_round_with_zero_taus(emulated_simt, oracle, zero_rho, zero_outer)
+
+
+@pytest.mark.parametrize("tail_bits", [0, 4])
+def test_batched_sumcheck_tail_kernel_on_host_threads(emulated_simt, oracle, tail_bits):
+    """b200_sumcheck_batched with no tail (every round: k_form_reduce_multi, k_form_final_multi, k_sc_round_batched) and
+    with ALL rounds inside k_scb_tail (512 host threads: block-wide sums, warp 0 runs the round incl. the pending
+    transcript bytes of round 0, binds, barriers), against the oracle's prove_helper."""
+    from nova_b200.native import lib
+    assert lib().use_simt
+    old = lib().b200_sumcheck_tail_bits(tail_bits)
+    try:
+        test_batched_round_with_zero_taus(emulated_simt, oracle, (0, 3), (1,))
+    finally:
+        lib().b200_sumcheck_tail_bits(old)
 
 
 def test_ppsnark_prove_core_kernel_wrapper_on_32_threads(emulated_simt, oracle):

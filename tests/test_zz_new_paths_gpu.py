@@ -317,6 +317,21 @@ def test_streamed_witness_folding_steps_on_device(b200, oracle, cid):
     run_streamed_steps(b200, oracle, cid)
 
 
+@pytest.mark.parametrize("ell,tail_bits", [(6, 0), (6, 3), (9, 0), (9, 5), (9, 9), (11, 8)])
+def test_batched_sumcheck_one_call_multi_and_tail(b200, oracle, ell, tail_bits):
+    """b200_sumcheck_batched at sizes where the reductions span several blocks, with the hand-over to k_scb_tail at
+    different rounds (0 = no tail: k_form_reduce_multi every round; = ell: every round inside the tail kernel), zero
+    taus on both sides of the hand-over; against the oracle's prove_helper (proof, challenges, final claims, transcript)."""
+    import test_ppsnark_mirror_cpu as t
+    from nova_b200 import ppsnark as dp
+    from nova_b200.native import lib
+    old = lib().b200_sumcheck_tail_bits(tail_bits)
+    try:
+        t.test_batched_round_with_zero_taus(b200, oracle, (1, ell - 2), (0, ell - 1), ell=ell, helpers=(dp.prove_helper_device,))
+    finally:
+        lib().b200_sumcheck_tail_bits(old)
+
+
 @pytest.mark.parametrize("cid,num_cons,num_vars,device_transcript", [(0, 16, 8, False), (0, 64, 64, True), (1, 32, 16, True)])
 def test_compressed_snark_half_on_device(b200, oracle, cid, num_cons, num_vars, device_transcript):
     """One curve's half of CompressedSNARK::prove (nova/mod.rs:813-881): random pair sampled and folded in,
