@@ -59,6 +59,7 @@ struct device_state {
   bool ready = false;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;  // short side jobs forked from `stream` and joined through events
   bool pool = true;
 } g_dev;
 
@@ -75,6 +76,7 @@ int ensure_init() {
                 e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
   CU(cudaSetDevice(g_dev.device));
   CU(cudaStreamCreateWithFlags(&g_dev.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g_dev.aux, cudaStreamNonBlocking));
   // b200_dev_alloc / b200_dev_free and the library's own temporaries come from the device's stream-ordered pool
   // (cudaMallocAsync on the library stream): a prover allocates and drops dozens of vectors per proof, and
   // cudaMalloc / cudaFree cost milliseconds each and synchronise the device (HyperKZG 2^22: 1012 -> ~70 ms per

@@ -118,6 +118,12 @@ __global__ void __launch_bounds__(256) k_bind_top_multi(bind_multi_args a, size_
   }
 }
 
+// out[t] = element 0 of table t (the final evaluations of a sum-check: one read-back instead of one per table)
+template <class F>
+__global__ void __launch_bounds__(BIND_MULTI_MAX) k_gather_heads(bind_multi_args a, int k, void* __restrict__ out) {
+  if ((int)threadIdx.x < k) fe_store(out, threadIdx.x, fe_load_rw(a.z[threadIdx.x], 0));
+}
+
 // ---- inner-product argument helpers (provider/ipa_pc.rs:174-285, restated without key folding) --
 // out[i] = v[i]*x_lo + v[i+half]*x_hi   (a' = a_L r + r^-1 a_R ; b' = b_L r^-1 + r b_R, ipa_pc.rs:244-254)
 template <class F>

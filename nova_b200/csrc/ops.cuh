@@ -92,6 +92,16 @@ struct field_ops {
   void (*to_mont)(cudaStream_t, const void* in_canonical, size_t n, void* out);
   // sharded MSM whose rank has no pairs: publish the identity and sum the peers' partials (plan.peer)
   void (*exchange_identity)(cudaStream_t, const msm_plan&, void* out_jac);
+  // the round with the final stage of the reductions folded in: partials = k_form_reduce_multi's output for the
+  // nsums <= 32 sums of the round (desc.slot[i] = 3 * index of claim i's sum)
+  void (*sc_round_batched_fused)(cudaStream_t, const void* desc, void* state, const void* partials, int nblocks,
+                                 int nsums, const void* pending, uint32_t pending_len, int absorb_label,
+                                 int squeeze_label, void* out_poly, void* out_r);
+  // first stage only of sc_reduce_multi; returns the blocks per sum (the nblocks of sc_round_batched_fused)
+  int (*sc_reduce_multi_partials)(cudaStream_t, const multi_args&, void* scratch);
+  void (*gather_heads)(cudaStream_t, void* const* zs, int k, void* out);  // out[t] = zs[t][0], k <= 32
+  // nested eq tables eq(taus[hi-k .. hi)), k = 0 .. K <= EQ_PREFIX_MAX_K, table k at element 2^k - 1 of out
+  void (*eq_prefix_tables)(cudaStream_t, const void* taus, int hi, int K, void* out);
   // all sums of a batched sum-check round in two launches: out[3 y + k] = output k of sum y;
   // scratch >= sc_multi_scratch_elems(n sums) * 32 B
   void (*sc_reduce_multi)(cudaStream_t, const multi_args&, void* scratch, void* out);
@@ -100,6 +110,7 @@ struct field_ops {
                    uint32_t pending_len, int absorb_label, int squeeze_label, void* polys, void* rs);
 };
 constexpr int SC_MAX_BLOCKS = 148 * 4;
+constexpr int EQ_PREFIX_MAX_K = 12;
 constexpr int SC_MULTI_BLOCKS = 148 * 2;  // blocks per sum of sc_reduce_multi (times <= 32 sums in grid.y)
 inline size_t sc_multi_scratch_elems(int nsums) { return (size_t)nsums * SC_MULTI_BLOCKS * 3; }
 // NOVA_B200_SC_SEG=1 selects the segmented reduction of the eq-weighted sum-check forms (k_form_reduce_eqseg)

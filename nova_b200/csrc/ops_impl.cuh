@@ -379,6 +379,27 @@ struct ops_impl {
     k_sc_round_batched<F><<<1, 32, 0, s>>>(*(const scb_desc*)desc, (scb_state*)state, sums, (const uint8_t*)pending,
                                            pending_len, (uint8_t)absorb_label, (uint8_t)squeeze_label, out_poly, out_r);
   }
+  static void eq_prefix_tables(cudaStream_t s, const void* taus, int hi, int K, void* out) {
+    k_eq_prefix_tables<F><<<1, 1024, 0, s>>>(taus, hi, K, out);
+  }
+  static int sc_reduce_multi_partials(cudaStream_t s, const multi_args& a, void* scratch) {
+    size_t need = (a.h + 255) / 256;
+    unsigned gx = (unsigned)(need < (size_t)SC_MULTI_BLOCKS ? (need ? need : 1) : SC_MULTI_BLOCKS);
+    k_form_reduce_multi<F><<<dim3(gx, (unsigned)a.n), 256, 0, s>>>(a, scratch);
+    return (int)gx;
+  }
+  static void sc_round_batched_fused(cudaStream_t s, const void* desc, void* state, const void* partials, int nblocks,
+                                     int nsums, const void* pending, uint32_t pending_len, int absorb_label,
+                                     int squeeze_label, void* out_poly, void* out_r) {
+    k_sc_round_batched_fused<F><<<1, 32 * nsums, 0, s>>>(*(const scb_desc*)desc, (scb_state*)state, partials, nblocks,
+                                                       (const uint8_t*)pending, pending_len, (uint8_t)absorb_label,
+                                                       (uint8_t)squeeze_label, out_poly, out_r);
+  }
+  static void gather_heads(cudaStream_t s, void* const* zs, int k, void* out) {
+    bind_multi_args a{};
+    for (int i = 0; i < k; i++) a.z[i] = zs[i];
+    k_gather_heads<F><<<1, BIND_MULTI_MAX, 0, s>>>(a, k, out);
+  }
   static void sc_reduce_multi(cudaStream_t s, const multi_args& a, void* scratch, void* out) {
     size_t need = (a.h + 255) / 256;
     unsigned gx = (unsigned)(need < (size_t)SC_MULTI_BLOCKS ? (need ? need : 1) : SC_MULTI_BLOCKS);
@@ -419,7 +440,8 @@ struct ops_impl {
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
                      sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve,
                      powers_canonical, scalar_bases, poseidon_ro, to_mont, exchange_identity,
-                     sc_reduce_multi, scb_tail};
+                     sc_round_batched_fused, sc_reduce_multi_partials, gather_heads,
+                     eq_prefix_tables, sc_reduce_multi, scb_tail};
   }
 };
 

@@ -252,6 +252,30 @@ NOVA_HD constexpr int sc_form_nout(int form) {
                                                                                 : 2;
 }
 
+// The nested eq tables of an EqSumCheckInstance (sumcheck.rs:606-664) in one launch: table k = eq(taus[hi-k .. hi)),
+// 2^k entries at element offset 2^k - 1 of `out`, for k = 0 .. K.  Table k+1 is table k times (1 - t, t) with
+// t = taus[hi-k-1] as the new TOP variable -- the recurrence of the reference's compute_eqs.  One block; K <= 12 here
+// (longer tables come from k_eq_small / k_eq_outer, which split the work over the GPU).
+template <class F>
+__global__ void __launch_bounds__(1024) k_eq_prefix_tables(const void* __restrict__ taus, int hi, int K,
+                                                           void* __restrict__ out) {
+  if (threadIdx.x == 0) fe_store(out, 0, fe_one<F>());
+  __syncthreads();
+  for (int k = 0; k < K; k++) {
+    const fe_t t = fe_load(taus, (size_t)(hi - k - 1));
+    const size_t n = (size_t)1 << k;
+    const void* src = (const char*)out + 32 * (n - 1);
+    void* dst = (char*)out + 32 * (2 * n - 1);
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const fe_t base = fe_load_rw(src, i);
+      const fe_t up = fe_mul<F>(base, t);
+      fe_store(dst, i, fe_sub<F>(base, up));
+      fe_store(dst, i + n, up);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // All sums of one round of a BATCHED sum-check in one launch (prove_helper, ppsnark.rs:886-983: nine claims over
 // sixteen tables of one length): grid = (blocks, sums), block (x, y) reduces a slice of sum y.  Two launches per

@@ -2,7 +2,7 @@
 //
 // Once the tables are a few hundred entries long a round is pure latency: two reduction launches, the round kernel and
 // the bind launch cost ~55 us while touching a few KiB.  k_scb_tail runs every remaining round inside one CTA:
-//     all sums of the round (block-wide reduction per sum)  ->  warp 0: scb_round_warp (evaluation points, combination,
+//     all sums of the round (one warp per sum, all sums at once)  ->  warp 0: scb_round_warp (evaluation points, combination,
 //     cubic, Keccak absorb / squeeze, claim and eq-bound updates)  ->  all threads: bind every table with r
 // with block barriers in between -- no launches, no host.  The tables stay in global memory (L1 / L2 resident at this
 // size) and are read through the coherent path (sc_form<.., RW = true>) because the same kernel rewrites them.
@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(SCB_TAIL_THREADS) k_scb_tail(const scb_tail_ar
                                                                 void* __restrict__ polys, void* __restrict__ rs) {
   __shared__ scb_round_smem sh;
   __shared__ scb_desc d;
-  __shared__ fe_t sm[(SCB_TAIL_THREADS / 32) * 3];
   const int l = a.num_rounds, fh = l / 2, shh = l - fh;
   if (threadIdx.x == 0) d = a.d;
   __syncthreads();
@@ -53,7 +52,10 @@ __global__ void __launch_bounds__(SCB_TAIL_THREADS) k_scb_tail(const scb_tail_ar
   for (int j = a.first_round; j < l; j++, len >>= 1) {
     const size_t half = len >> 1;
     const int round = j + 1;  // EqSumCheckInstance::round (sumcheck.rs:1233-1251)
-    for (int i = 0; i < a.d.nclaims; i++) {
+    // one warp per sum (claim i, or its third sum in a tau = 0 round): lane-strided partial sums, shuffle tree
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int t = warp; t < 2 * a.d.nclaims; t += nwarps) {
+      const int i = t % a.d.nclaims, pass = t / a.d.nclaims;
       const int g = a.d.eq_of[i];
       multi_sum m;
       m.A = a.tab[i][0] >= 0 ? a.tables[a.tab[i][0]] : nullptr;
@@ -73,25 +75,27 @@ __global__ void __launch_bounds__(SCB_TAIL_THREADS) k_scb_tail(const scb_tail_ar
         }
         tau_zero = (q.tau_zero >> j) & 1;
       }
-      const int passes = (tau_zero && a.form_m1[i] >= 0) ? 2 : 1;
-      for (int pass = 0; pass < passes; pass++) {
-        m.form = pass ? a.form_m1[i] : a.form[i];
-        fe_t acc[3] = {fe_zero<F>(), fe_zero<F>(), fe_zero<F>()};
-        multi_dispatch<F, true>(m, half, 1, 0, threadIdx.x, blockDim.x, acc);
-        block_sum<F, 3>(acc, sm);
-        if (threadIdx.x == 0) {
-          const int slot = 3 * (pass ? SCB_MAX_CLAIMS + i : i);
-          for (int k = 0; k < 3; k++) fe_store(sums, (size_t)slot + k, acc[k]);
-          if (pass == 0) {
-            d.slot[i] = slot;
-            d.slot_m1[i] = -1;
-          } else {
-            d.slot_m1[i] = slot;
-          }
+      const bool third = tau_zero && a.form_m1[i] >= 0;
+      if (pass == 1 && !third) continue;  // warp-uniform
+      m.form = pass ? a.form_m1[i] : a.form[i];
+      fe_t acc[3] = {fe_zero<F>(), fe_zero<F>(), fe_zero<F>()};
+      multi_dispatch<F, true>(m, half, 1, 0, (size_t)lane, 32, acc);
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) acc[k] = fe_add<F>(acc[k], fe_shfl_down(acc[k], dlt));
+      if (lane == 0) {
+        const int slot = 3 * (pass ? SCB_MAX_CLAIMS + i : i);
+        for (int k = 0; k < 3; k++) fe_store(sums, (size_t)slot + k, acc[k]);
+        if (pass == 0) {
+          d.slot[i] = slot;
+          if (!third) d.slot_m1[i] = -1;
+        } else {
+          d.slot_m1[i] = slot;
         }
-        __syncthreads();  // `sm` is reused by the next sum
       }
     }
+    __syncthreads();
     if (threadIdx.x < (unsigned)a.d.neq) {
       d.tau[threadIdx.x] = (const char*)a.eq[threadIdx.x].taus + 32 * (size_t)j;
       d.tau_inv[threadIdx.x] = (const char*)a.eq[threadIdx.x].tau_inv + 32 * (size_t)j;

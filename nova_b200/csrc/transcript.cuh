@@ -21,6 +21,24 @@
 
 namespace nova {
 
+// The round kernels are one warp running ~25 field products ONCE: with the multiplier inlined at every site they were
+// 138 KB of straight-line code, fetched cold from L2 (instruction-cache misses dominated the kernel).  A called
+// multiplier keeps the body resident after its first use.  -DNOVA_ROUND_INLINE_MUL restores the inlined form (A/B).
+#if defined(__CUDACC__) && !defined(NOVA_ROUND_INLINE_MUL)
+template <class F>
+__host__ __device__ __noinline__ fe_t fe_mulx(const fe_t& a, const fe_t& b) {
+  return fe_mul<F>(a, b);
+}
+#else
+template <class F>
+NOVA_HD fe_t fe_mulx(const fe_t& a, const fe_t& b) {
+  return fe_mul<F>(a, b);
+}
+#endif
+#if !defined(SCB_STAMP)
+#define SCB_STAMP(i)  // tools/roundbench.cu: clock64() stamps at the section boundaries of the round kernels
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Keccak-f[1600] and Keccak-256 (the original padding 0x01 .. 0x80, rate 136 -- sha3 crate
 // `Keccak256`, keccak.rs:9)
@@ -89,8 +107,22 @@ NOVA_HD void msg_put(msg_buf& m, uint8_t b) {
 NOVA_HD void msg_put_bytes(msg_buf& m, const uint8_t* p, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) msg_put(m, p[i]);
 }
+// four bytes at once (little-endian), at any byte position: one or two word updates instead of four
+NOVA_HD void msg_put_u32le(msg_buf& m, uint32_t v) {
+  const uint32_t w = m.len >> 3, sh = 8 * (m.len & 7);
+  m.w[w] |= (uint64_t)v << sh;
+  if (sh > 32) m.w[w + 1] |= (uint64_t)v >> (64 - sh);
+  m.len += 4;
+}
 NOVA_HD void msg_put_u64le(msg_buf& m, uint64_t v) {
-  for (int i = 0; i < 8; i++) msg_put(m, (uint8_t)(v >> (8 * i)));
+  msg_put_u32le(m, (uint32_t)v);
+  msg_put_u32le(m, (uint32_t)(v >> 32));
+}
+// zeroes the words a message of `total_len` bytes (plus its padding) occupies -- all the hash will read
+NOVA_HD void msg_reset_for(msg_buf& m, uint32_t total_len) {
+  const uint32_t nwords = (total_len / (8 * KECCAK_RATE_WORDS) + 1) * KECCAK_RATE_WORDS;
+  for (uint32_t i = 0; i < nwords; i++) m.w[i] = 0;
+  m.len = 0;
 }
 
 // Keccak-256 of the message with byte `flip_pos` XORed with `flip` (the two squeeze hashes differ
@@ -161,6 +193,76 @@ NOVA_D void keccak_f1600_warp(uint64_t& a) {
   }
 }
 
+// Two states in lockstep: the shuffles of both permutations are in flight together, so the pair costs about what one
+// costs (the warp is latency-bound).
+NOVA_D void keccak_f1600_warp2(uint64_t& a0, uint64_t& a1) {
+  constexpr uint64_t RC[24] = {
+      0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
+      0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+      0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
+      0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+      0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+      0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  constexpr int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  const int lane = (int)(threadIdx.x & 31u);
+  const int l = lane < 25 ? lane : 0;
+  const int x = l % 5, y = l / 5;
+  const int row = 5 * y;
+  const int up1 = (l + 5) % 25, up2 = (l + 10) % 25, up3 = (l + 15) % 25, up4 = (l + 20) % 25;
+  const int col_m1 = row + (x + 4) % 5, col_p1 = row + (x + 1) % 5, col_p2 = row + (x + 2) % 5;
+  const int src_pi = ((x + 3 * y) % 5) + 5 * x;
+  int rot = 0;
+#pragma unroll
+  for (int k = 0; k < 25; k++)
+    if (k == src_pi) rot = ROT[k];
+  for (int round = 0; round < 24; round++) {
+    uint64_t c0 = a0 ^ warp_get64(a0, up1) ^ warp_get64(a0, up2) ^ warp_get64(a0, up3) ^ warp_get64(a0, up4);
+    uint64_t c1 = a1 ^ warp_get64(a1, up1) ^ warp_get64(a1, up2) ^ warp_get64(a1, up3) ^ warp_get64(a1, up4);
+    a0 ^= warp_get64(c0, col_m1) ^ rotl64v(warp_get64(c0, col_p1), 1);
+    a1 ^= warp_get64(c1, col_m1) ^ rotl64v(warp_get64(c1, col_p1), 1);
+    uint64_t b0 = rotl64v(warp_get64(a0, src_pi), rot);
+    uint64_t b1 = rotl64v(warp_get64(a1, src_pi), rot);
+    a0 = b0 ^ (~warp_get64(b0, col_p1) & warp_get64(b0, col_p2));
+    a1 = b1 ^ (~warp_get64(b1, col_p1) & warp_get64(b1, col_p2));
+    if (lane == 0) {
+      a0 ^= RC[round];
+      a1 ^= RC[round];
+    }
+  }
+}
+
+// Both squeeze hashes of a transcript (keccak.rs:131-160: the same message with the last byte 0 and 1) by one warp: the
+// blocks before the one holding that byte are absorbed once, from there on the two states run in lockstep.
+// out0 / out1: the digests for flip = 0 / 1.
+NOVA_D void keccak256_msg_warp_pair(const msg_buf& m, uint32_t flip_pos, uint64_t (&out0)[4], uint64_t (&out1)[4]) {
+  const int lane = (int)(threadIdx.x & 31u);
+  uint64_t a0 = 0, a1 = 0;
+  const uint32_t nblocks = m.len / (8 * KECCAK_RATE_WORDS) + 1;
+  const uint32_t pad_w = m.len >> 3, last_w = nblocks * KECCAK_RATE_WORDS - 1, flip_w = flip_pos >> 3;
+  const uint32_t fork = flip_w / KECCAK_RATE_WORDS;  // first block in which the two messages differ
+  for (uint32_t b = 0; b < nblocks; b++) {
+    if (b == fork) a1 = a0;
+    if (lane < KECCAK_RATE_WORDS) {
+      uint32_t wi = b * KECCAK_RATE_WORDS + lane;
+      uint64_t v = m.w[wi];
+      if (wi == pad_w) v ^= (uint64_t)0x01 << (8 * (m.len & 7));
+      if (wi == last_w) v ^= (uint64_t)0x80 << 56;
+      a0 ^= v;
+      if (b >= fork) {
+        if (wi == flip_w) v ^= (uint64_t)1 << (8 * (flip_pos & 7));
+        a1 ^= v;
+      }
+    }
+    if (b < fork) keccak_f1600_warp(a0);
+    else keccak_f1600_warp2(a0, a1);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    out0[i] = warp_get64(a0, i);
+    out1[i] = warp_get64(a1, i);
+  }
+}
+
 // Keccak-256 of `m` (same padding / flip convention as keccak256_msg) computed by the whole warp; every lane returns
 // the four digest words.
 NOVA_D void keccak256_msg_warp(const msg_buf& m, uint32_t flip_pos, uint8_t flip, uint64_t (&out)[4]) {
@@ -207,7 +309,7 @@ NOVA_HD fe_t fe_from_uniform(const uint64_t (&w)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; i++) r2.l[i] = F::r2(i);
   // lo R + (hi R) R  =  (lo + 2^256 hi) R   (mod p)
-  return fe_add<F>(fe_mul<F>(lo, r2), fe_mul<F>(fe_mul<F>(hi, r2), r2));
+  return fe_add<F>(fe_mulx<F>(lo, r2), fe_mulx<F>(fe_mulx<F>(hi, r2), r2));
 }
 
 // x / 2 on any residue representation (Montgomery included): (x + (x odd ? p : 0)) >> 1
@@ -272,17 +374,17 @@ NOVA_HD void sc_round_build(int kind, const sc_state& st, const fe_t* res, const
   const fe_t e0c = fe_sub<F>(one, tau);                              // eq(tau, 0)
   const fe_t slope = fe_sub<F>(two_tau, one);                        // 2 tau - 1
   const fe_t em1c = fe_sub<F>(fe_dbl<F>(one), fe_add<F>(two_tau, tau));  // eq(tau, -1) = 2 - 3 tau
-  const fe_t qt0 = fe_mul<F>(st.q, res[0]);
-  const fe_t qtinf = fe_mul<F>(st.q, res[1]);
-  const fe_t s0 = fe_mul<F>(e0c, qt0);
-  const fe_t lead = fe_mul<F>(slope, qtinf);
+  const fe_t qt0 = fe_mulx<F>(st.q, res[0]);
+  const fe_t qtinf = fe_mulx<F>(st.q, res[1]);
+  const fe_t s0 = fe_mulx<F>(e0c, qt0);
+  const fe_t lead = fe_mulx<F>(slope, qtinf);
   fe_t em1;
   if (kind == SC_ROUND_CUBIC3_EQ_M1) {
-    em1 = fe_mul<F>(em1c, fe_mul<F>(st.q, res[2]));
+    em1 = fe_mulx<F>(em1c, fe_mulx<F>(st.q, res[2]));
   } else {
     // q t(1) = (claim - s0) / tau ;  t(-1) = 2 t(inf) + 2 t(0) - t(1)
-    fe_t qt1 = fe_mul<F>(fe_sub<F>(st.claim, s0), tau_inv);
-    em1 = fe_mul<F>(em1c, fe_sub<F>(fe_dbl<F>(fe_add<F>(qtinf, qt0)), qt1));
+    fe_t qt1 = fe_mulx<F>(fe_sub<F>(st.claim, s0), tau_inv);
+    em1 = fe_mulx<F>(em1c, fe_sub<F>(fe_dbl<F>(fe_add<F>(qtinf, qt0)), qt1));
   }
   // evals [d, a+b+c+d, a, s(-1)] -> d + c x + b x^2 + a x^3
   fe_t e1 = fe_sub<F>(st.claim, s0);
@@ -311,16 +413,16 @@ NOVA_HD int sc_round_compressed(const sc_round_poly& p, fe_t (&canon)[3]) {
 NOVA_HD uint32_t sc_round_message(msg_buf& m, const uint8_t* pending, uint32_t pending_len,
                                   uint8_t absorb_label, const fe_t* canon, int ncoef,
                                   const sc_state& st, uint8_t squeeze_label) {
-  msg_reset(m);
+  msg_reset_for(m, pending_len + 1 + 32 * (uint32_t)ncoef + 4 + 8 + 64 + 2);
   msg_put_bytes(m, pending, pending_len);
   msg_put(m, absorb_label);
   for (int k = 0; k < ncoef; k++)
-    for (int i = 0; i < 8; i++)
-      for (int b = 0; b < 4; b++) msg_put(m, (uint8_t)(canon[k].l[i] >> (8 * b)));
-  const uint8_t dom_sep[4] = {'N', 'o', 'D', 'S'};
-  msg_put_bytes(m, dom_sep, 4);
+    for (int i = 0; i < 8; i++) msg_put_u32le(m, canon[k].l[i]);
+  msg_put_u32le(m, 0x53446f4eu);  // "NoDS"
   msg_put_u64le(m, st.round);
-  msg_put_bytes(m, st.tstate, 64);
+  for (int i = 0; i < 64; i += 4)
+    msg_put_u32le(m, (uint32_t)st.tstate[i] | ((uint32_t)st.tstate[i + 1] << 8) | ((uint32_t)st.tstate[i + 2] << 16) |
+                         ((uint32_t)st.tstate[i + 3] << 24));
   msg_put(m, squeeze_label);
   uint32_t pos = m.len;
   msg_put(m, 0);
@@ -333,13 +435,13 @@ NOVA_HD fe_t sc_round_finish(int kind, sc_state& st, const sc_round_poly& p, con
   fe_t r = fe_from_uniform<F>(digest);
   // UniPoly::evaluate (Horner form of the same polynomial value)
   fe_t acc = p.c[p.deg];
-  for (int k = p.deg - 1; k >= 0; k--) acc = fe_add<F>(fe_mul<F>(acc, r), p.c[k]);
+  for (int k = p.deg - 1; k >= 0; k--) acc = fe_add<F>(fe_mulx<F>(acc, r), p.c[k]);
   st.claim = acc;
   if (kind != SC_ROUND_QUAD_PROD) {
     // eval_eq_left *= 1 - tau - r + 2 r tau            (sumcheck.rs:1226-1231)
-    fe_t rt = fe_mul<F>(r, p.tau);
+    fe_t rt = fe_mulx<F>(r, p.tau);
     fe_t f = fe_add<F>(fe_sub<F>(fe_sub<F>(fe_one<F>(), p.tau), r), fe_dbl<F>(rt));
-    st.q = fe_mul<F>(st.q, f);
+    st.q = fe_mulx<F>(st.q, f);
   }
   for (int i = 0; i < 8; i++)
     for (int b = 0; b < 8; b++) st.tstate[8 * i + b] = (uint8_t)(digest[i] >> (8 * b));
@@ -385,8 +487,7 @@ __global__ void __launch_bounds__(32) k_sc_round(int kind, sc_state* __restrict_
   uint64_t digest[8];
   {
     uint64_t d0[4], d1[4];
-    keccak256_msg_warp(msg, flip_pos_sh, 0, d0);
-    keccak256_msg_warp(msg, flip_pos_sh, 1, d1);
+    keccak256_msg_warp_pair(msg, flip_pos_sh, d0, d1);
     for (int i = 0; i < 4; i++) {
       digest[i] = d0[i];
       digest[4 + i] = d1[i];

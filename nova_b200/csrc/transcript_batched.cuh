@@ -66,20 +66,20 @@ NOVA_HD void scb_claim_evals(const scb_desc& d, int i, const scb_state& st, cons
   const fe_t two_tau = fe_dbl<F>(tau);
   const fe_t e0c = fe_sub<F>(one, tau);
   const fe_t em1c = fe_sub<F>(fe_dbl<F>(one), fe_add<F>(two_tau, tau));
-  const fe_t qt0 = fe_mul<F>(q, s[0]);
-  const fe_t s0 = fe_mul<F>(e0c, qt0);
+  const fe_t qt0 = fe_mulx<F>(q, s[0]);
+  const fe_t s0 = fe_mulx<F>(e0c, qt0);
   fe_t qtinf = fe_zero<F>();
   ev[0] = s0;
   ev[1] = fe_zero<F>();
   if (kind == SCB_EQ_DEG2) {
-    qtinf = fe_mul<F>(q, s[1]);
-    ev[1] = fe_mul<F>(fe_sub<F>(two_tau, one), qtinf);
+    qtinf = fe_mulx<F>(q, s[1]);
+    ev[1] = fe_mulx<F>(fe_sub<F>(two_tau, one), qtinf);
   }
   if (tm1) {  // tau = 0: third sum (sumcheck.rs:1082-1213)
-    ev[2] = fe_mul<F>(em1c, fe_mul<F>(q, *tm1));
+    ev[2] = fe_mulx<F>(em1c, fe_mulx<F>(q, *tm1));
   } else {    // q t(1) = (claim - s0) / tau ; t(-1) = 2 t(inf) + 2 t(0) - t(1)   (t(inf) = 0 for DEG1)
-    fe_t qt1 = fe_mul<F>(fe_sub<F>(st.claim[i], s0), tau_inv);
-    ev[2] = fe_mul<F>(em1c, fe_sub<F>(fe_dbl<F>(fe_add<F>(qtinf, qt0)), qt1));
+    fe_t qt1 = fe_mulx<F>(fe_sub<F>(st.claim[i], s0), tau_inv);
+    ev[2] = fe_mulx<F>(em1c, fe_sub<F>(fe_dbl<F>(fe_add<F>(qtinf, qt0)), qt1));
   }
 }
 
@@ -87,7 +87,7 @@ NOVA_HD void scb_claim_evals(const scb_desc& d, int i, const scb_state& st, cons
 template <class F>
 NOVA_HD fe_t scb_combine(const scb_desc& d, const scb_state& st, const fe_t (*ev)[3], int k) {
   fe_t acc = fe_zero<F>();
-  for (int i = 0; i < d.nclaims; i++) acc = fe_add<F>(acc, fe_mul<F>(ev[i][k], st.coeff[i]));
+  for (int i = 0; i < d.nclaims; i++) acc = fe_add<F>(acc, fe_mulx<F>(ev[i][k], st.coeff[i]));
   return acc;
 }
 
@@ -110,16 +110,16 @@ NOVA_HD fe_t scb_update_claim(const fe_t& claim, const fe_t (&ev)[3], const fe_t
   fe_t e1 = fe_sub<F>(claim, ev[0]);
   fe_t a1 = fe_sub<F>(fe_half<F>(fe_sub<F>(e1, ev[2])), ev[1]);
   fe_t a2 = fe_sub<F>(fe_half<F>(fe_add<F>(e1, ev[2])), ev[0]);
-  fe_t acc = fe_add<F>(fe_mul<F>(ev[1], r), a2);
-  acc = fe_add<F>(fe_mul<F>(acc, r), a1);
-  return fe_add<F>(fe_mul<F>(acc, r), ev[0]);
+  fe_t acc = fe_add<F>(fe_mulx<F>(ev[1], r), a2);
+  acc = fe_add<F>(fe_mulx<F>(acc, r), a1);
+  return fe_add<F>(fe_mulx<F>(acc, r), ev[0]);
 }
 
 // eval_eq_left *= 1 - tau - r + 2 r tau   (sumcheck.rs:1226-1231)
 template <class F>
 NOVA_HD fe_t scb_bound(const fe_t& q, const fe_t& tau, const fe_t& r) {
-  fe_t f = fe_add<F>(fe_sub<F>(fe_sub<F>(fe_one<F>(), tau), r), fe_dbl<F>(fe_mul<F>(r, tau)));
-  return fe_mul<F>(q, f);
+  fe_t f = fe_add<F>(fe_sub<F>(fe_sub<F>(fe_one<F>(), tau), r), fe_dbl<F>(fe_mulx<F>(r, tau)));
+  return fe_mulx<F>(q, f);
 }
 
 #if defined(__CUDACC__) || defined(NOVA_SIMT_HOST)  // NOVA_SIMT_HOST: tests/hostcheck/simt_host.h
@@ -130,6 +130,7 @@ struct scb_round_smem {
   uint32_t flip_pos;
   fe_t ev[SCB_MAX_CLAIMS][3];
   fe_t comb[3];
+  fe_t part[30];
   scb_state st;
 };
 
@@ -139,6 +140,7 @@ NOVA_D void scb_round_warp(const scb_desc& d, scb_state* __restrict__ state, con
                            uint8_t squeeze_label, void* __restrict__ out_poly, void* __restrict__ out_r,
                            scb_round_smem& sh) {
   const int lane = (int)(threadIdx.x & 31u);
+  SCB_STAMP(0);
   static_assert(sizeof(scb_state) % 4 == 0, "word copy");
   for (unsigned w = lane; w < sizeof(scb_state) / 4; w += 32)
     reinterpret_cast<uint32_t*>(&sh.st)[w] = reinterpret_cast<const uint32_t*>(state)[w];
@@ -161,30 +163,50 @@ NOVA_D void scb_round_warp(const scb_desc& d, scb_state* __restrict__ state, con
     for (int k = 0; k < 3; k++) sh.ev[lane][k] = ev[k];
   }
   __syncwarp();
-  if (lane < 3) sh.comb[lane] = scb_combine<F>(d, sh.st, sh.ev, lane);
+  SCB_STAMP(1);
+  {  // combination sum_i coeff_i ev_i[k]: lane 3 j + k takes claims j and j + 10, lanes 0..2 add the ten partial sums
+    static_assert(SCB_MAX_CLAIMS <= 20, "two claims per lane");
+    const int k = lane % 3, j = lane / 3;
+    fe_t part = fe_zero<F>();
+    if (lane < 30) {
+      if (j < d.nclaims) part = fe_mulx<F>(sh.ev[j][k], sh.st.coeff[j]);
+      if (j + 10 < d.nclaims) part = fe_add<F>(part, fe_mulx<F>(sh.ev[j + 10][k], sh.st.coeff[j + 10]));
+      sh.part[lane] = part;
+    }
+    __syncwarp();
+    if (lane < 3) {
+      fe_t acc = sh.part[lane];
+      for (int q = 1; q < 10; q++) acc = fe_add<F>(acc, sh.part[3 * q + lane]);
+      sh.comb[lane] = acc;
+    }
+  }
   __syncwarp();
+  SCB_STAMP(2);
   sc_round_poly poly;
   scb_poly<F>(sh.st.head.claim, sh.comb[0], sh.comb[1], sh.comb[2], poly);
   fe_t canon[3];
   sc_round_compressed<F>(poly, canon);
+  SCB_STAMP(3);
   if (lane == 0) {
     sh.flip_pos = sc_round_message(sh.msg, pending, pending_len, absorb_label, canon, 3, sh.st.head, squeeze_label);
     for (int k = 0; k < 3; k++) fe_store(out_poly, k, canon[k]);
   }
   __syncwarp();
+  SCB_STAMP(4);
   uint64_t digest[8];
   {
     uint64_t d0[4], d1[4];
-    keccak256_msg_warp(sh.msg, sh.flip_pos, 0, d0);
-    keccak256_msg_warp(sh.msg, sh.flip_pos, 1, d1);
+    keccak256_msg_warp_pair(sh.msg, sh.flip_pos, d0, d1);
     for (int i = 0; i < 4; i++) {
       digest[i] = d0[i];
       digest[4 + i] = d1[i];
     }
   }
+  SCB_STAMP(5);
   sc_state head = sh.st.head;  // every lane computes the same r and e; lane 0 stores them
   fe_t r = sc_round_finish<F>(SC_ROUND_QUAD_PROD, head, poly, digest);
   __syncwarp();                // all reads of sh.st are done
+  SCB_STAMP(6);
   if (is_eq_claim) state->claim[lane] = scb_update_claim<F>(sh.st.claim[lane], ev, r);
   if (lane < d.neq) {
     fe_t t = fe_load_rw(d.tau[lane], 0);
@@ -194,6 +216,40 @@ NOVA_D void scb_round_warp(const scb_desc& d, scb_state* __restrict__ state, con
     state->head = head;
     fe_store(out_r, 0, r);
   }
+  SCB_STAMP(7);
+}
+
+// The round with the last stage of the reductions folded in: <<<1, 32 * nsums>>>.  Warp w adds the `nblocks` partial
+// triples k_form_reduce_multi left for sum w (partials[(w * nblocks + b) * 3 + k]) -- all sums at once -- then warp 0
+// runs the round on the totals.  One launch (and one dependent-launch gap) less per round than k_form_final_multi +
+// k_sc_round_batched.
+constexpr int SCB_FUSED_MAX_SUMS = 32;
+template <class F>
+__global__ void __launch_bounds__(32 * SCB_FUSED_MAX_SUMS) k_sc_round_batched_fused(
+    scb_desc d, scb_state* __restrict__ state, const void* __restrict__ partials, int nblocks,
+    const uint8_t* __restrict__ pending, uint32_t pending_len, uint8_t absorb_label, uint8_t squeeze_label,
+    void* __restrict__ out_poly, void* __restrict__ out_r) {
+  __shared__ scb_round_smem sh;
+  __shared__ fe_t sums[3 * SCB_FUSED_MAX_SUMS];
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+  fe_t acc[3] = {fe_zero<F>(), fe_zero<F>(), fe_zero<F>()};
+  for (int b = lane; b < nblocks; b += 32)
+#pragma unroll
+    for (int k = 0; k < 3; k++) acc[k] = fe_add<F>(acc[k], fe_load_rw(partials, ((size_t)warp * nblocks + b) * 3 + k));
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+      fe_t o;
+#pragma unroll
+      for (int i = 0; i < 8; i++) o.l[i] = __shfl_down_sync(0xffffffffu, acc[k].l[i], dlt);
+      acc[k] = fe_add<F>(acc[k], o);
+    }
+    if (lane == 0) sums[3 * warp + k] = acc[k];
+  }
+  __syncthreads();
+  if (warp == 0)
+    scb_round_warp<F>(d, state, sums, pending, pending_len, absorb_label, squeeze_label, out_poly, out_r, sh);
 }
 
 // <<<1, 32>>>

@@ -260,6 +260,7 @@ class EmulatedDevice:
     # every round run through the REAL k_form_reduce_multi / k_form_final_multi and the last `tail_bits` variables
     # through the REAL k_scb_tail, on host threads (tests/hostcheck/simt_host.h). ----
     tail_bits = 2
+    fused_round = True
 
     def b200_sumcheck_tail_bits(self, bits):
         old = self.tail_bits
@@ -319,6 +320,19 @@ class EmulatedDevice:
                 d.tau[g] = ctypes.addressof(eq[g]["d_taus"]) + 32 * j
                 d.tau_inv[g] = ctypes.addressof(eq[g]["d_tinv"]) + 32 * j
             sums = ctypes.create_string_buffer(96 * len(plan))
+            if self.use_simt and self.fused_round:  # k_form_reduce_multi + k_sc_round_batched_fused, as the library does
+                a = self._multi_args(fid, prog, plan, eq_of, eq_ptrs, rnd, tables, length)
+                grid = max(1, min(3, (length // 2 + 255) // 256))
+                rc = self._hc_simt().hc_simt_round_fused(
+                    fid, ctypes.byref(a), grid, ctypes.byref(d), state, ctypes.c_void_p(_addr(pending) if j == 0 else 0),
+                    int(pending_len) if j == 0 else 0, ord("p"), ord("c"), ctypes.c_void_p(_addr(polys_out) + 96 * j),
+                    ctypes.c_void_p(_addr(r_out) + 32 * j))
+                assert rc == 0
+                r = _rd(_addr(r_out) + 32 * j, 32)
+                for Z in tables:
+                    _wr(Z, co.bind_top(fid, _rd(Z, 32 * length), r))
+                length //= 2
+                continue
             if self.use_simt:
                 self._simt_multi(fid, prog, plan, eq_of, eq_ptrs, rnd, tables, length, sums)
             else:
@@ -371,6 +385,11 @@ class EmulatedDevice:
         return self._structs
 
     def _simt_multi(self, fid, prog, plan, eq_of, eq_ptrs, rnd, tables, length, sums):
+        a = self._multi_args(fid, prog, plan, eq_of, eq_ptrs, rnd, tables, length)
+        grid = max(1, min(3, (length // 2 + 255) // 256))
+        assert self._hc_simt().hc_simt_sc_reduce_multi(fid, ctypes.byref(a), grid, sums) == 0
+
+    def _multi_args(self, fid, prog, plan, eq_of, eq_ptrs, rnd, tables, length):
         MultiArgs, _ = self._simt_structs()
         a = MultiArgs()
         a.n, a.h, a.id_mul, a.id_add = len(plan), length // 2, 1, 0
@@ -381,8 +400,7 @@ class EmulatedDevice:
             if eq_of[i] >= 0:
                 lp, _, rp, _, shift = eq_ptrs(eq_of[i], rnd)
                 m.eq_left, m.eq_right, m.shift = lp or None, rp, shift
-        grid = max(1, min(3, (length // 2 + 255) // 256))
-        assert self._hc_simt().hc_simt_sc_reduce_multi(fid, ctypes.byref(a), grid, sums) == 0
+        return a
 
     def _simt_tail(self, fid, prog, eq, eq_of, tables, j, state, pending, pending_len, polys_out, r_out):
         _, TailArgs = self._simt_structs()

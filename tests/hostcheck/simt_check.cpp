@@ -200,6 +200,48 @@ extern "C" int hc_simt_scb_tail(int fid, const void* args, void* state, void* su
   return 0;
 }
 
+// k_form_reduce_multi followed by k_sc_round_batched_fused (the last reduction stage inside the round kernel: one warp
+// per sum, then warp 0 runs the round) -- what b200_sumcheck_batched launches per round
+extern "C" int hc_simt_round_fused(int fid, const void* args, unsigned grid, const void* desc, void* state,
+                                   const void* pending, uint32_t pending_len, int absorb_label, int squeeze_label,
+                                   void* out_poly, void* out_r) {
+  const multi_args a = *(const multi_args*)args;
+  const scb_desc d = *(const scb_desc*)desc;
+  auto run = [&](auto tag) {
+    using F = decltype(tag);
+    std::vector<fe_t> partials((size_t)a.n * grid * 3);
+    for (int y = 0; y < a.n; y++)
+      simt_launch_grid(grid, 256, [&] {
+        blockIdx.y = (unsigned)y;
+        k_form_reduce_multi<F>(a, partials.data());
+      });
+    simt_launch_grid(1, 32 * (unsigned)a.n, [&] {
+      k_sc_round_batched_fused<F>(d, (scb_state*)state, partials.data(), (int)grid, (const uint8_t*)pending, pending_len,
+                                  (uint8_t)absorb_label, (uint8_t)squeeze_label, out_poly, out_r);
+    });
+  };
+  switch (fid) {
+    case 0: run(BN254_FR{}); break;
+    case 3: run(PALLAS_FQ{}); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+// nested eq tables in one block of 1024 host threads (k_eq_prefix_tables)
+extern "C" int hc_simt_eq_prefix(int fid, const void* taus, int hi, int K, void* out) {
+  auto run = [&](auto tag) {
+    using F = decltype(tag);
+    simt_launch_grid(1, 1024, [&] { k_eq_prefix_tables<F>(taus, hi, K, out); });
+  };
+  switch (fid) {
+    case 0: run(BN254_FR{}); break;
+    case 3: run(PALLAS_FQ{}); break;
+    default: return 1;
+  }
+  return 0;
+}
+
 extern "C" int hc_simt_sizes(int which) {
   switch (which) {
     case 0: return (int)sizeof(multi_args);

@@ -91,6 +91,17 @@ def test_batched_round_kernel_wrapper_on_32_threads(emulated_simt, oracle, zero_
     test_batched_round_with_zero_taus(emulated_simt, oracle, zero_rho, zero_outer)
 
 
+def test_batched_sumcheck_unfused_round_on_host_threads(emulated_simt, oracle):
+    """the four-launch form of a round (k_form_reduce_multi, k_form_final_multi, k_sc_round_batched; NOVA_B200_SC_UNFUSED=1)"""
+    from nova_b200.native import lib
+    lib().fused_round = False
+    old = lib().b200_sumcheck_tail_bits(0)
+    try:
+        test_batched_round_with_zero_taus(emulated_simt, oracle, (0, 3), (1,))
+    finally:
+        lib().b200_sumcheck_tail_bits(old)
+
+
 @pytest.mark.parametrize("tail_bits", [0, 4])
 def test_batched_sumcheck_tail_kernel_on_host_threads(emulated_simt, oracle, tail_bits):
     """b200_sumcheck_batched with no tail (every round: k_form_reduce_multi, k_form_final_multi, k_sc_round_batched) and
@@ -114,3 +125,26 @@ def test_ppsnark_prove_core_kernel_wrapper_on_32_threads(emulated_simt, oracle):
 def test_whole_ppsnark_with_hyperkzg_host_logic(emulated, oracle, num_cons, num_vars, device_transcript):
     import ppsnark_full_parity
     ppsnark_full_parity.run(emulated, oracle, num_cons, num_vars, device_transcript)
+
+
+@pytest.mark.parametrize("fid,l", [(0, 1), (0, 7), (3, 12)])
+def test_eq_prefix_tables_kernel_on_host_threads(oracle, fid, l):
+    """k_eq_prefix_tables (all nested eq tables of an EqSumCheckInstance in one launch) as 1024 host threads against the
+    oracle's eq table of every slice taus[hi-k .. hi) (sumcheck.rs:606-664)."""
+    import ctypes
+    import emulated_device
+    from oracle import coracle as co
+    from oracle.pyref import FIELD_MODULUS, SplitMix64, mont_bytes
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(77 + l)
+    taus = [rng.field(p) for _ in range(l)]
+    if l > 2:
+        taus[1] = 0
+    raw = b"".join(mont_bytes(p, t) for t in taus)
+    hc = emulated_device.EmulatedDevice()._hc_simt()
+    for hi, K in ((l // 2, max(l // 2, 1) - 1), (l, l - l // 2)):
+        out = ctypes.create_string_buffer(32 << (K + 1))
+        assert hc.hc_simt_eq_prefix(fid, ctypes.create_string_buffer(raw, len(raw)), hi, K, out) == 0
+        for k in range(K + 1):
+            off = 32 * ((1 << k) - 1)
+            assert out.raw[off:off + (32 << k)] == co.eq_table(fid, raw[32 * (hi - k):32 * hi]), (hi, k)

@@ -41,7 +41,7 @@ def main():
             check(lib().b200_sync())
             return (time.perf_counter() - t0) * 1e3, out[0][-1], tr.squeeze(b"x")
         ref = None
-        for name, helper, tb in [("rounds", dp.prove_helper_device_rounds, None)] + [("one-call tail=%d" % t, dp.prove_helper_device, t) for t in (0, 4, 6, 8, 10, 12)]:
+        for name, helper, tb in [("rounds", dp.prove_helper_device_rounds, None)] + [("one-call tail=%d" % t, dp.prove_helper_device, t) for t in (0, 8)]:
             if tb is not None:
                 lib().b200_sumcheck_tail_bits(tb)
             ts = []
