@@ -373,7 +373,7 @@ int b200_sc_round_batched_dev(int field_id, const b200_scb_desc* desc, const voi
  * device tables of 2^num_rounds elements (bound in place).  Per round: all sums in two launches, the round kernel, one
  * bind launch; the last NOVA_B200_SC_TAIL_BITS (default 8) variables run inside one kernel.
  *   kind[i]    B200_SCB_*: how claim i's sums become its evaluation points [s(0), lead, s(-1)]
- *   form[i]    sum form (sc_form_id 0..9: SC_QUAD_PROD .. SC_EQ_QUAD1_M1) over tables tab[i][0..2] (-1 = unused)
+ *   form[i]    sum form 0..9 of b200_sc_eval (the pair forms) over tables tab[i][0..2] (-1 = unused)
  *   form_m1[i] eq claims: the third-sum form (7..9) for rounds whose tau is 0 (sumcheck.rs:1082-1213)
  *   eq_of[i]   eq claims: the EqSumCheckInstance (sumcheck.rs:590-747) weighting the sum; taus[g]: its num_rounds taus
  * Host inputs (Montgomery): coeffs [nclaims] (powers of the batching challenge, ppsnark.rs:915-921), claim (their

@@ -406,6 +406,44 @@ inline SumcheckProofOut prove_cubic_with_three_inputs(int field, const Scalar& c
   }, "b200_sumcheck_cubic3");
 }
 
+// RelaxedR1CSSNARK::prove_helper (ppsnark.rs:886-983) in one call.  The claims of all engines as data: claim i reads
+// the sums of `form[i]` over the device tables tab[i][0..2] (weighted by eq instance eq_of[i] for the eq kinds) and turns
+// them into evaluation points as `kind[i]` says; `coeffs` are the powers of the batching challenge, `claim` their
+// combination with the initial claims, `running` the initial claims.  final_evals: element 0 of every table, in
+// program order.
+struct BatchedSumcheck {
+  b200_scp_program prog{};
+  std::vector<std::vector<Scalar>> taus;  // per eq instance, num_rounds Montgomery scalars (kept alive for prog.taus)
+  int add_table(void* d_table) {
+    prog.tables[prog.ntables] = d_table;
+    return prog.ntables++;
+  }
+  int add_eq(std::vector<Scalar> t) {
+    taus.push_back(std::move(t));
+    return prog.neq++;
+  }
+  // kind: B200_SCB_*; form / form_m1: sc_form ids (include/nova_b200.h); tables: indices from add_table, -1 = unused
+  void add_claim(int kind, int form, int form_m1, int a, int b, int c, int eq) {
+    const int i = prog.nclaims++;
+    prog.kind[i] = kind;
+    prog.form[i] = form;
+    prog.form_m1[i] = form_m1;
+    prog.eq_of[i] = eq;
+    prog.tab[i][0] = a;
+    prog.tab[i][1] = b;
+    prog.tab[i][2] = c;
+  }
+  SumcheckProofOut prove(int field, int num_rounds, const std::vector<Scalar>& coeffs, const Scalar& claim,
+                         const std::vector<Scalar>& running, TranscriptState& t) {
+    prog.num_rounds = num_rounds;
+    for (int g = 0; g < prog.neq; g++) prog.taus[g] = taus[g].data();
+    return detail::device_loop(t, num_rounds, 3, prog.ntables, [&](b200_transcript* tr, const void* p, size_t n,
+                                                                   void* polys, void* rs, void* fin) {
+      return b200_sumcheck_batched(field, &prog, coeffs.data(), &claim, running.data(), tr, p, n, polys, rs, fin);
+    }, "b200_sumcheck_batched");
+  }
+};
+
 // ---- one process, all GPUs of the node (b200_mgpu_*): the single call a CommitmentEngine::commit makes ------------
 // The key is distributed block-cyclically over the devices; every commit of a prefix ck[..n] is fanned out inside the
 // library and the partial sums are exchanged over NVLink inside the reduction kernels (include/nova_b200.h).
