@@ -314,13 +314,20 @@ class EqSumCheckInstance:
                 res.append([(a - b) % p for a, b in zip(prev, hi)] + hi)
             return res
 
-        left = list(reversed(taus[1:self.first_half])) if self.first_half >= 1 else []
-        right = list(reversed(taus[self.first_half:]))
-        self._left = [DeviceVec.from_bytes(fields.pack(fid, t)) for t in compute(left)]
-        self._right = [DeviceVec.from_bytes(fields.pack(fid, t)) for t in compute(right)]
+        # built on first use: the one-call loops (b200_sumcheck_batched / b200_sumcheck_cubic3) build their own on the device
+        self._compute, self._left, self._right = compute, None, None
         self.eq_tau_0_a_inf = [((1 - t) % p, (2 * t - 1) % p, (2 - 3 * t) % p) for t in taus]
 
+    def _build_tables(self):
+        taus, fid = self.taus, self.fid
+        left = list(reversed(taus[1:self.first_half])) if self.first_half >= 1 else []
+        right = list(reversed(taus[self.first_half:]))
+        self._left = [DeviceVec.from_bytes(fields.pack(fid, t)) for t in self._compute(left)]
+        self._right = [DeviceVec.from_bytes(fields.pack(fid, t)) for t in self._compute(right)]
+
     def _tables(self):
+        if self._left is None:
+            self._build_tables()
         if self.round < self.first_half:  # poly_eqs_first_half, sumcheck.rs:1233-1246
             return self._left[self.first_half - self.round], self._right[self.second_half], self.second_half
         return None, self._right[self.init_num_vars - self.round], 0  # :1248-1251
