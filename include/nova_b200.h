@@ -439,6 +439,11 @@ int b200_kzg_fold_dev(int field_id, const void* p, size_t n, const void* x, void
 int b200_poly_eval(int field_id, const void* f, size_t n, const void* us, size_t nu, void* evals);
 int b200_poly_eval_dev(int field_id, const void* f, size_t n, const void* us, size_t nu, void* evals,
                        void* stream);
+/* the same for k polynomials at the same nu <= 3 points (the 3-point evaluations of the whole HyperKZG fold chain,
+ * hyperkzg.rs:1048-1056): evals[i * nu + q] = polys[i](us[q]).  Polynomials of up to 2^12 coefficients share ONE
+ * launch; d_polys / lens are host arrays of device pointers / lengths. */
+int b200_poly_eval_many_dev(int field_id, const void* const* d_polys, const size_t* lens, size_t k, const void* d_us,
+                            size_t nu, void* d_evals, void* stream);
 /* h = f / (X - u): n-1 coefficients, h[i-1] = f[i] + u*h[i] (hyperkzg.rs:961-999) */
 int b200_poly_div(int field_id, const void* f, size_t n, const void* u, void* out);
 int b200_poly_div_dev(int field_id, const void* f, size_t n, const void* u, void* out, void* stream);

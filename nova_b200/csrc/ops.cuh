@@ -13,6 +13,7 @@ namespace nova {
 
 struct msm_plan;
 struct multi_args;     // poly_kernels.cuh
+struct poly_multi_args;
 struct scb_tail_args;  // sumcheck_tail.cuh
 
 struct field_ops {
@@ -100,6 +101,8 @@ struct field_ops {
   // first stage only of sc_reduce_multi; returns the blocks per sum (the nblocks of sc_round_batched_fused)
   int (*sc_reduce_multi_partials)(cudaStream_t, const multi_args&, void* scratch);
   void (*gather_heads)(cudaStream_t, void* const* zs, int k, void* out);  // out[t] = zs[t][0], k <= 32
+  // <= 32 polynomials of <= 2^POLY_SMALL_MAX_LOG2 coefficients at the same nu <= 3 points, one launch
+  void (*poly_eval_small_multi)(cudaStream_t, const poly_multi_args&, const void* us, int nu, void* evals);
   // nested eq tables eq(taus[hi-k .. hi)), k = 0 .. K <= EQ_PREFIX_MAX_K, table k at element 2^k - 1 of out
   void (*eq_prefix_tables)(cudaStream_t, const void* taus, int hi, int K, void* out);
   // all sums of a batched sum-check round in two launches: out[3 y + k] = output k of sum y;

@@ -395,6 +395,11 @@ struct ops_impl {
                                                        (const uint8_t*)pending, pending_len, (uint8_t)absorb_label,
                                                        (uint8_t)squeeze_label, out_poly, out_r);
   }
+  static void poly_eval_small_multi(cudaStream_t s, const poly_multi_args& a, const void* us, int nu, void* evals) {
+    if (nu == 1) k_poly_eval_small_multi<F, 1><<<a.k, 256, 0, s>>>(a, us, evals);
+    else if (nu == 2) k_poly_eval_small_multi<F, 2><<<a.k, 256, 0, s>>>(a, us, evals);
+    else k_poly_eval_small_multi<F, 3><<<a.k, 256, 0, s>>>(a, us, evals);
+  }
   static void gather_heads(cudaStream_t s, void* const* zs, int k, void* out) {
     bind_multi_args a{};
     for (int i = 0; i < k; i++) a.z[i] = zs[i];
@@ -440,7 +445,7 @@ struct ops_impl {
                      sc_reduce, eq_small, eq_outer, batch_invert, rlc, kzg_fold, poly_eval, poly_div, spmv_classify, spmv, spmv_t,
                      sc_round, fe_inv_each, digits_range, sc_round_batched, on_curve,
                      powers_canonical, scalar_bases, poseidon_ro, to_mont, exchange_identity,
-                     sc_round_batched_fused, sc_reduce_multi_partials, gather_heads,
+                     sc_round_batched_fused, sc_reduce_multi_partials, gather_heads, poly_eval_small_multi,
                      eq_prefix_tables, sc_reduce_multi, scb_tail};
   }
 };

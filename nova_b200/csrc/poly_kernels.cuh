@@ -537,6 +537,45 @@ __global__ void __launch_bounds__(256) k_poly_eval_strided(const void* __restric
     for (int q = 0; q < NU; q++) fe_store(partials, (size_t)blockIdx.x * NU + q, acc[q]);
 }
 
+// Several SHORT polynomials at the same NU points in one launch (the tail of the HyperKZG fold chain, hyperkzg.rs:1048-
+// 1056: polynomials of 2^12 .. 2 coefficients, each of which would otherwise pay three launches).  Block b takes polynomial
+// b; thread t owns coefficients t, t + 256, ...; its u^t and y = u^256 come from square-and-multiply ladders (16 products,
+// nothing next to three launch latencies).  evals[(out_index[b]) * NU + q] = f_b(u_q).
+constexpr int POLY_SMALL_MAX_LOG2 = 12;
+struct poly_multi_args {
+  const void* p[RLC_MAX];
+  size_t len[RLC_MAX];
+  int32_t out_index[RLC_MAX];
+  int k;
+};
+template <class F, int NU>
+__global__ void __launch_bounds__(256) k_poly_eval_small_multi(poly_multi_args a, const void* __restrict__ us,
+                                                               void* __restrict__ evals) {
+  __shared__ fe_t sm[8 * NU];
+  const void* f = a.p[blockIdx.x];
+  const size_t n = a.len[blockIdx.x], t = threadIdx.x, T = blockDim.x;
+  fe_t acc[NU];
+#pragma unroll
+  for (int q = 0; q < NU; q++) acc[q] = fe_zero<F>();
+  if (t < n) {
+    fe_t y[NU];
+#pragma unroll
+    for (int q = 0; q < NU; q++) y[q] = fe_pow_u64<F>(fe_load(us, q), (uint64_t)T);
+    const size_t kmax = (n - 1 - t) / T;
+    for (size_t k = kmax + 1; k-- > 0;) {
+      const fe_t c = fe_load(f, t + k * T);
+#pragma unroll
+      for (int q = 0; q < NU; q++) acc[q] = fe_add<F>(fe_mul<F>(acc[q], y[q]), c);
+    }
+#pragma unroll
+    for (int q = 0; q < NU; q++) acc[q] = fe_mul<F>(acc[q], fe_pow_u64<F>(fe_load(us, q), (uint64_t)t));
+  }
+  block_sum<F, NU>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int q = 0; q < NU; q++) fe_store(evals, (size_t)a.out_index[blockIdx.x] * NU + q, acc[q]);
+}
+
 constexpr int POLY_CHUNK = 64;
 // chunk values V_c = sum_{k<len_c} B[c*m + k] u^k  for each of the NU points (Horner per chunk)
 template <class F>

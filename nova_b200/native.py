@@ -117,6 +117,7 @@ SIGNATURES = {
     "b200_kzg_fold_dev": [c_int, _P, c_size_t, _P, _P, _P],
     "b200_poly_eval": [c_int, _P, c_size_t, _P, c_size_t, _P],
     "b200_poly_eval_dev": [c_int, _P, c_size_t, _P, c_size_t, _P, _P],
+    "b200_poly_eval_many_dev": [c_int, _P, _P, c_size_t, _P, c_size_t, _P, _P],
     "b200_poly_div": [c_int, _P, c_size_t, _P, _P],
     "b200_poly_div_dev": [c_int, _P, c_size_t, _P, _P, _P],
     "b200_spmv_register": [c_int, _P, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), c_size_t, c_size_t,

@@ -164,6 +164,16 @@ class EmulatedDevice:
         _wr(evals, co.poly_eval(fid, _rd(f, 32 * n), _rd(us, 32 * nu)))
         return 0
 
+    def b200_poly_eval_many_dev(self, fid, polys, lens, k, us, nu, evals, stream):
+        for i in range(k):
+            n = int(lens[i])
+            out = ctypes.c_void_p(_addr(evals) + 32 * nu * i)
+            if n == 0:
+                _wr(out, bytes(32 * nu))
+            else:
+                self.b200_poly_eval_dev(fid, polys[i], n, us, nu, out, stream)
+        return 0
+
     def b200_poly_div_dev(self, fid, f, n, u, out, stream):
         _wr(out, co.poly_div(fid, _rd(f, 32 * n), _rd(u, 32)))
         return 0

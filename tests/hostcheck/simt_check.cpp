@@ -242,6 +242,28 @@ extern "C" int hc_simt_eq_prefix(int fid, const void* taus, int hi, int K, void*
   return 0;
 }
 
+// several short polynomials at three points in one launch (k_poly_eval_small_multi): one block of 256 host threads each
+extern "C" int hc_simt_poly_eval_small_multi(int fid, const void* const* polys, const size_t* lens, int k, const void* us,
+                                             void* evals) {
+  poly_multi_args a;
+  a.k = k;
+  for (int i = 0; i < k; i++) {
+    a.p[i] = polys[i];
+    a.len[i] = lens[i];
+    a.out_index[i] = i;
+  }
+  auto run = [&](auto tag) {
+    using F = decltype(tag);
+    simt_launch_grid((unsigned)k, 256, [&] { k_poly_eval_small_multi<F, 3>(a, us, evals); });
+  };
+  switch (fid) {
+    case 0: run(BN254_FR{}); break;
+    case 3: run(PALLAS_FQ{}); break;
+    default: return 1;
+  }
+  return 0;
+}
+
 extern "C" int hc_simt_sizes(int which) {
   switch (which) {
     case 0: return (int)sizeof(multi_args);

@@ -148,3 +148,26 @@ def test_eq_prefix_tables_kernel_on_host_threads(oracle, fid, l):
         for k in range(K + 1):
             off = 32 * ((1 << k) - 1)
             assert out.raw[off:off + (32 << k)] == co.eq_table(fid, raw[32 * (hi - k):32 * hi]), (hi, k)
+
+
+@pytest.mark.parametrize("fid", [0, 3])
+def test_poly_eval_small_multi_kernel_on_host_threads(oracle, fid):
+    """k_poly_eval_small_multi (the short tail of the HyperKZG fold chain at three points in one launch) as blocks of 256
+    host threads against the oracle's Horner evaluation (hyperkzg.rs:1011-1019); lengths around the block size."""
+    import ctypes
+    import emulated_device
+    from oracle import coracle as co
+    from oracle.pyref import FIELD_MODULUS, SplitMix64, mont_bytes
+    p = FIELD_MODULUS[fid]
+    rng = SplitMix64(4242 + fid)
+    lens = [1, 2, 7, 255, 256, 257, 1000]
+    polys = [b"".join(mont_bytes(p, rng.field(p)) for _ in range(n)) for n in lens]
+    us = b"".join(mont_bytes(p, x) for x in (rng.field(p), 0, 1))
+    bufs = [ctypes.create_string_buffer(b, len(b)) for b in polys]
+    ptrs = (ctypes.c_void_p * len(lens))(*[ctypes.addressof(b) for b in bufs])
+    out = ctypes.create_string_buffer(96 * len(lens))
+    hc = emulated_device.EmulatedDevice()._hc_simt()
+    assert hc.hc_simt_poly_eval_small_multi(fid, ptrs, (ctypes.c_size_t * len(lens))(*lens), len(lens),
+                                            ctypes.create_string_buffer(us, 96), out) == 0
+    for i, f in enumerate(polys):
+        assert out.raw[96 * i:96 * i + 96] == co.poly_eval(fid, f, us), lens[i]

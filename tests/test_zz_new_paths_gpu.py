@@ -548,3 +548,23 @@ def test_sharded_provers_over_nccl(tmp_path):
     test_ppsnark_sharded.run_world(2, "nccl", tmp_path)
     test_sharding_pieces.run_world(2, "nccl", tmp_path)
     test_sumcheck_sharded.run_world(2, "nccl", 0, 10, 0, tmp_path)
+
+
+@pytest.mark.parametrize("fid", [0, 2])
+def test_poly_eval_many(sp, oracle, fid):
+    """b200_poly_eval_many_dev: polynomials on both sides of the short / long split (2^12 coefficients), the empty one, more
+    than 32 short ones (two launches of k_poly_eval_small_multi), each at three points, against the oracle's Horner values."""
+    import ctypes
+    from nova_b200.native import check, lib
+    lens = [0, 1, 2, 255, 256, 257, 4095, 4096, 4097, 70001] + [3 + i for i in range(34)]
+    polys = [oracle.gen_scalars(fid, 900 + i, n) if n else b"" for i, n in enumerate(lens)]
+    us = oracle.gen_scalars(fid, 33, 3)
+    dev = [sp.DeviceVec.from_bytes(f) if f else None for f in polys]
+    k = len(lens)
+    ptrs = (ctypes.c_void_p * k)(*[d.ptr.value if d else None for d in dev])
+    ud, ev = sp.DeviceVec.from_bytes(us), sp.DeviceVec(96 * k)
+    check(lib().b200_poly_eval_many_dev(fid, ptrs, (ctypes.c_size_t * k)(*lens), k, ud.ptr, 3, ev.ptr, None))
+    got = ev.to_bytes(96 * k)
+    for i, f in enumerate(polys):
+        want = oracle.poly_eval(fid, f, us) if f else bytes(96)
+        assert got[96 * i:96 * i + 96] == want, lens[i]
