@@ -291,8 +291,14 @@ struct ops_impl {
     k_eq_outer<F><<<stream_grid(n, 256), 256, 0, s>>>(left, right, right_bits, n, out);
   }
   static void batch_invert(cudaStream_t s, const void* in, size_t n, void* out, int* zero_flag) {
-    size_t threads = (n + BINV_CHUNK - 1) / BINV_CHUNK;
-    k_batch_invert<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(in, n, out, zero_flag);
+    static const int forced = [] {  // A/B: NOVA_B200_BINV_CHUNK=<elements per thread>
+      const char* e = getenv("NOVA_B200_BINV_CHUNK");
+      int v = e ? atoi(e) : 0;
+      return v >= 1 && v <= 4096 ? v : 0;
+    }();
+    const int chunk = forced ? forced : (n >= BINV_LONG_FROM ? BINV_CHUNK_LONG : BINV_CHUNK);
+    size_t threads = (n + chunk - 1) / chunk;
+    k_batch_invert<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(in, n, out, zero_flag, chunk);
   }
   static void rlc(cudaStream_t s, const void* const* polys, const size_t* lens, int k,
                   const void* coeffs, size_t n, void* out) {

@@ -403,15 +403,18 @@ __global__ void __launch_bounds__(256) k_eq_outer(const void* __restrict__ left,
 // batch inversion (spartan/mod.rs:54-145).  Each thread runs Montgomery's trick over a chunk;
 // zero inputs are reported through *zero_flag (the reference returns Err(InternalError)).
 // ------------------------------------------------------------------------------------------
-constexpr int BINV_CHUNK = 32;
+// `chunk` elements per thread: one Fermat inversion (~380 products) is shared by a chunk, so a chunk costs 3 + 380 / chunk
+// products per element; long vectors take 64 (enough threads remain), short ones 32.
+constexpr int BINV_CHUNK = 32, BINV_CHUNK_LONG = 64;
+constexpr size_t BINV_LONG_FROM = (size_t)1 << 21;
 template <class F>
 __global__ void __launch_bounds__(128) k_batch_invert(const void* __restrict__ in, size_t n,
                                                       void* __restrict__ out,
-                                                      int* __restrict__ zero_flag) {
+                                                      int* __restrict__ zero_flag, int chunk) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t lo = t * BINV_CHUNK;
+  size_t lo = t * (size_t)chunk;
   if (lo >= n) return;
-  size_t hi = lo + BINV_CHUNK < n ? lo + BINV_CHUNK : n;
+  size_t hi = lo + chunk < n ? lo + chunk : n;
   // pass 1: out[i] = product of in[lo..i)
   fe_t acc = fe_one<F>();
   for (size_t i = lo; i < hi; i++) {

@@ -900,9 +900,9 @@ def prove_core(curve, ck: CommitmentKey, S: dict, spark: SparkRepr, U: dict, W: 
         "eval_W": c_wit[0][0],
     }
     ri_dev = DeviceVec.from_bytes(fields.pack(fid, r_inner))
-    for name, v in (("eval_val_A", spark.val_A), ("eval_val_B", spark.val_B), ("eval_val_C", spark.val_C),
-                    ("eval_row", spark.row), ("eval_col", spark.col)):
-        ev[name] = _mle_eval(fid, v, nri, ri_dev)  # multi_evaluate_with, multilinear.rs:129-180
+    names = ("eval_val_A", "eval_val_B", "eval_val_C", "eval_row", "eval_col")
+    from .spartan import mle_eval_multi_dev  # multi_evaluate_with, multilinear.rs:129-180: one pair of eq tables, one read-back
+    ev.update(zip(names, mle_eval_multi_dev(fid, [spark.val_A, spark.val_B, spark.val_C, spark.row, spark.col], nri, ri_dev)))
     order = ["eval_W", "eval_E", "eval_L_row", "eval_L_col", "eval_val_A", "eval_val_B", "eval_val_C",
              "eval_t_plus_r_inv_row", "eval_row", "eval_w_plus_r_inv_row", "eval_ts_row",
              "eval_t_plus_r_inv_col", "eval_col", "eval_w_plus_r_inv_col", "eval_ts_col"]
