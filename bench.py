@@ -330,7 +330,14 @@ def run_b200(args):
         "stage_ms_per_msm": {k: round(stage_ms[i] / max(1, msms.value), 4) for i, k in enumerate(stage_names)},
         "int_mul_pipe": {"achieved": round(mul_rate, 2), "peak": 64.2, "unit": "G field-mul/s",
                          "frac": round(mul_rate / 64.2, 4), "window_bits": cc.value, "windows": nt.value,
-                         "peak_source": "measured fe_mul throughput of this multiplier (tools/microbench.cu)"},
+                         "peak_source": "measured fe_mul throughput of this multiplier (tools/microbench.cu)",
+                         # ceilings that do not depend on this multiplier: wide 32x32+64 products issued per clock and
+                         # SM, measured with tools/microbench.cu (61 without a carry flag, 30.5 with one), x 148 SMs x
+                         # 1.965 GHz / 136 wide products per Montgomery product (64 + 64 + 8)
+                         "hw_bounds": {"imad_wide_with_carry": {"peak": 65.2, "frac": round(mul_rate / 65.2, 4)},
+                                       "imad_wide_full_rate": {"peak": 130.5, "frac": round(mul_rate / 130.5, 4),
+                                                               "note": "unreachable with a carry chain; a carry-free "
+                                                                       "formulation needs ~2x the instructions (DESIGN.md §4)"}}},
     }
 
     # ---------------- CPU baseline beside it (N = 1 only) ---------------------------------------
