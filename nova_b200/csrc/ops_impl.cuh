@@ -296,7 +296,9 @@ struct ops_impl {
       int v = e ? atoi(e) : 0;
       return v >= 1 && v <= 4096 ? v : 0;
     }();
-    const int chunk = forced ? forced : (n >= BINV_LONG_FROM ? BINV_CHUNK_LONG : BINV_CHUNK);
+    int chunk = (int)(n / BINV_MIN_THREADS);
+    chunk = chunk < BINV_CHUNK ? BINV_CHUNK : (chunk > BINV_CHUNK_MAX ? BINV_CHUNK_MAX : chunk);
+    if (forced) chunk = forced;
     size_t threads = (n + chunk - 1) / chunk;
     k_batch_invert<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(in, n, out, zero_flag, chunk);
   }
