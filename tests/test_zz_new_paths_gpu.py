@@ -568,3 +568,80 @@ def test_poly_eval_many(sp, oracle, fid):
     for i, f in enumerate(polys):
         want = oracle.poly_eval(fid, f, us) if f else bytes(96)
         assert got[96 * i:96 * i + 96] == want, lens[i]
+
+
+def test_batched_sumcheck_concurrent_callers(b200, oracle):
+    """Four host threads run b200_sumcheck_batched (each with its own tables, eq instances and transcript) while a fifth
+    commits on a shared key: the calls share the library stream, the auxiliary stream (inversions) and the memory pool.
+    Every proof must equal the oracle's prove_helper for its inputs."""
+    import threading
+    from nova_b200 import ppsnark as dp
+    from nova_b200 import spartan as sp
+    from oracle import ppsnark_ref as pr
+    from oracle.pyref import CURVES
+    fid, ell = 0, 9
+    p, N = FIELD_MODULUS[fid], 1 << ell
+    pack = lambda xs: b"".join(mont_bytes(p, x) for x in xs)
+
+    def inputs(seed):
+        rng = SplitMix64(seed)
+        vec = lambda: [rng.field(p) for _ in range(N)]
+        d = dict(oracles=[vec() for _ in range(4)], aux=[vec() for _ in range(4)], ts_row=vec(), ts_col=vec(), L_row=vec(),
+                 L_col=vec(), val=vec(), E=vec(), W=vec(), rhos=[rng.field(p) for _ in range(ell)],
+                 r_outer=[0 if i == 3 else rng.field(p) for i in range(ell)], claim=rng.field(p), claim_E=rng.field(p))
+        return d
+
+    def ref_run(d):
+        mem = pr.MemorySumcheckInstance(p, d["oracles"], d["aux"], d["rhos"], d["ts_row"], d["ts_col"])
+        inner = pr.InnerBatchedSumcheckInstance(p, d["claim"], d["L_row"], d["L_col"], d["val"], d["claim_E"], d["r_outer"], d["E"])
+        wit = pr.WitnessBoundSumcheck(p, d["r_outer"], d["W"], 4)
+        tr = Keccak256Transcript(p, b"cc")
+        return pr.prove_helper(p, mem, inner, wit, tr), tr.squeeze(b"after")
+
+    def dev_run(d):
+        up = lambda v: sp.DeviceVec.from_bytes(pack(v))
+        mem = dp.MemorySumcheckInstance(fid, N, [up(v) for v in d["oracles"]], [up(v) for v in d["aux"]], d["rhos"],
+                                        up(d["ts_row"]), up(d["ts_col"]))
+        inner = dp.InnerBatchedSumcheckInstance(fid, N, d["claim"], up(d["L_row"]), up(d["L_col"]), up(d["val"]), d["claim_E"],
+                                                d["r_outer"], up(d["E"]))
+        wit = dp.WitnessBoundSumcheck(fid, N, d["r_outer"], up(d["W"]), 4)
+        tr = Keccak256Transcript(p, b"cc")
+        return dp.prove_helper_device(fid, mem, inner, wit, tr), tr.squeeze(b"after")
+
+    cases = [inputs(9000 + i) for i in range(4)]
+    want = [ref_run(d) for d in cases]
+    cid = 0
+    n_ck = 1 << 12
+    bases = oracle.gen_bases(cid, n_ck)
+    ck = b200.CommitmentKey(b200.Curve(cid), bases)
+    sc = oracle.gen_scalars(CURVES[cid].scalar_field, 77, n_ck)
+    from test_msm_gpu import aff
+    grp = b200.DlogGroup(cid)
+    want_c = aff(CURVES[cid], oracle.msm(cid, sc, bases))
+    got, errs, commits = [None] * 4, [], []
+
+    def worker(i):
+        try:
+            for _ in range(3):
+                got[i] = dev_run(cases[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    def committer():
+        try:
+            for _ in range(12):
+                commits.append(grp.vartime_multiscalar_mul(sc, ck))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(4)] + [threading.Thread(target=committer)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for i in range(4):
+        (g, after), (w, wafter) = got[i], want[i]
+        assert [list(q) for q in g[0]] == [list(q) for q in w[0]] and list(g[1]) == list(w[1]) and g[2:] == w[2:], i
+        assert after == wafter
+    assert all(c == want_c for c in commits)
+    ck.release()
