@@ -393,7 +393,12 @@ struct ops_impl {
   static int sc_reduce_multi_partials(cudaStream_t s, const multi_args& a, void* scratch) {
     size_t need = (a.h + 255) / 256;
     unsigned gx = (unsigned)(need < (size_t)SC_MULTI_BLOCKS ? (need ? need : 1) : SC_MULTI_BLOCKS);
-    k_form_reduce_multi<F><<<dim3(gx, (unsigned)a.n), 256, 0, s>>>(a, scratch);
+    static const bool occ3 = [] {
+      const char* e = getenv("NOVA_B200_SC_MULTI_OCC");
+      return e && e[0] == '3';
+    }();
+    if (occ3) k_form_reduce_multi<F, 3><<<dim3(gx, (unsigned)a.n), 256, 0, s>>>(a, scratch);
+    else k_form_reduce_multi<F, 2><<<dim3(gx, (unsigned)a.n), 256, 0, s>>>(a, scratch);
     return (int)gx;
   }
   static void sc_round_batched_fused(cudaStream_t s, const void* desc, void* state, const void* partials, int nblocks,

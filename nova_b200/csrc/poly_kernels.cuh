@@ -341,8 +341,10 @@ NOVA_D void multi_dispatch(const multi_sum& m, size_t h, size_t id_mul, size_t i
 }
 
 // partials[(y * gridDim.x + x) * 3 + k]
-template <class F>
-__global__ void __launch_bounds__(256) k_form_reduce_multi(const multi_args a, void* __restrict__ partials) {
+// MINB = resident blocks per SM the register allocation aims at (2: 124 registers, no spills; 3: 80 registers, the
+// cubic form spills) -- NOVA_B200_SC_MULTI_OCC selects at run time
+template <class F, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) k_form_reduce_multi(const multi_args a, void* __restrict__ partials) {
   __shared__ fe_t sm[8 * 3];
   fe_t acc[3] = {fe_zero<F>(), fe_zero<F>(), fe_zero<F>()};
   multi_dispatch<F, false>(a.s[blockIdx.y], a.h, a.id_mul, a.id_add, (size_t)blockIdx.x * blockDim.x + threadIdx.x,

@@ -92,7 +92,7 @@ inline uint32_t atomicMin(uint32_t* p, uint32_t v) {
 
 #define __global__
 #define __shared__ static
-#define __launch_bounds__(n)
+#define __launch_bounds__(...)
 
 // run `kernel` once per lane of one 32-lane warp (grid <<<1, 32>>>)
 inline void simt_launch_warp(const std::function<void()>& kernel) {
