@@ -75,15 +75,19 @@ def make_sides():
     return Side(1, 1, SECONDARY_CONS, 100), Side(0, 0, PRIMARY_CONS, 200)  # (Grumpkin/Fq, BN254/Fr)
 
 
-def gpu_replay(steps=5, warmup=2, return_outputs=False):
+def gpu_replay(steps=5, warmup=2, return_outputs=False, overlap=True):
+    """overlap: commit(W2) runs on a second stream beside the SpMV / cross-term chain of the same side (both only need the
+    uploaded witness; `b200_msm_dev` is asynchronous on the caller's stream) -- what a host that calls the `_dev` entry
+    points from two streams gets.  False = everything on one stream (the round-1 replay)."""
     import torch
 
     import nova_b200 as nb
     from nova_b200.native import check, lib
     L = lib()
     check(L.b200_init(0))
-    stream = torch.cuda.Stream()
+    stream, stream2 = torch.cuda.Stream(), torch.cuda.Stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
+    sp2 = ctypes.c_void_p(stream2.cuda_stream) if overlap else sp
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
     sides = make_sides()
@@ -118,13 +122,17 @@ def gpu_replay(steps=5, warmup=2, return_outputs=False):
     def nifs_and_commit(s, d):
         # fresh witness of this step arrives from the host (frontend/r1cs.rs:40-50)
         d["Z2"][:s.vars * 32].copy_(d["W2_host"], non_blocking=True)
-        check(L.b200_msm_dev(d["ck"].handle, 0, P(d["Z2"]), s.vars, P(d["comm"]), sp))          # commit(W2)
+        if overlap:
+            stream2.wait_stream(stream)                                                          # the upload
+        check(L.b200_msm_dev(d["ck"].handle, 0, P(d["Z2"]), s.vars, P(d["comm"]), sp2))         # commit(W2)
         check(L.b200_vec_add_dev(s.fid, P(d["Z1"]), P(d["Z2"]), s.zlen, P(d["Z"]), sp))         # Z1 + Z2
         for h, o in zip(d["mats"], (d["az"], d["bz"], d["cz"])):
             check(L.b200_spmv_dev(h, P(d["Z"]), None, P(o), None, sp))                           # 3 SpMV
         check(L.b200_cross_term_dev(s.fid, P(d["az"]), P(d["bz"]), P(d["cz"]), P(d["E1"]), None, P(d["u"]),
                                     s.cons, P(d["T"]), sp))                                      # T
         check(L.b200_msm_dev(d["ck"].handle, 0, P(d["T"]), s.cons, ctypes.c_void_p(d["comm"].data_ptr() + 96), sp))
+        if overlap:
+            stream.wait_stream(stream2)                                                          # comm_W is written there
         d["comm_host"].copy_(d["comm"], non_blocking=True)                                       # comm_W, comm_T -> host
         stream.synchronize()                       # the RO challenge r is derived from comm_T on the host
         check(L.b200_axpy_dev(s.fid, P(d["Z1"]), P(d["Z2"]), P(d["r"]), s.vars, P(d["Wf"]), sp)) # W fold
@@ -228,5 +236,8 @@ def cpu_replay(steps=1, return_outputs=False):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cpu":
         print(cpu_replay())
+    elif len(sys.argv) > 1 and sys.argv[1] == "ab":  # one stream vs commit(W2) beside the SpMV chain
+        for ov in (False, True, False, True):
+            print("overlap", ov, round(gpu_replay(steps=10, warmup=3, overlap=ov)["ms_per_step"], 4))
     else:
         print(gpu_replay())
