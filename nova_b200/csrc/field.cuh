@@ -456,7 +456,8 @@ NOVA_HD fe_t fe_mul(const fe_t& a, const fe_t& b) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Dedicated squaring (A/B variant, -DNOVA_SQR_DEDICATED; NOT the default until it is timed on a GPU).
+// Dedicated squaring (A/B variant, -DNOVA_SQR_DEDICATED; timed on B200: -8 % wide products, +8 % time -> not the default,
+// profiles/r02a_variants.md).
 // a^2 = sum_i a_i^2 2^(64 i) + 2 sum_{i<j} a_i a_j 2^(32 (i+j)): 28 cross products + 8 squares, then the 64
 // products of the Montgomery reduction = 100 wide products instead of 128.  Same even/odd accumulators as the
 // multiplier: a_i a_j lands in E when i + j is even, in O when it is odd; for a fixed j the partners i < j of

@@ -198,7 +198,8 @@ struct sc_form {
   }
 };
 
-// Segmented form of the same reduction for the eq-weighted sums (opt-in, NOVA_B200_SC_SEG=1; not yet timed):
+// Segmented form of the same reduction for the eq-weighted sums (opt-in, NOVA_B200_SC_SEG=1; timed on B200: no gain,
+// 3.729 vs 3.676 ms for the cubic loop at 2^22 -- profiles/r02a_variants.md -- so it stays off):
 //   sum_id left[id >> shift] right[id & mask] X(id)  =  sum_hi left[hi] * ( sum_lo right[lo] X(hi, lo) )
 // -- the order the reference's split-eq loops use (sumcheck.rs:900-966).  A block walks whole segments of 2^shift
 // indices, so the product left * right per index disappears (one product by left[hi] per thread and segment
